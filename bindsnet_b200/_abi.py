@@ -1,0 +1,148 @@
+"""ctypes mirror of ``include/snn_b200.h`` (the C ABI of the simulation core).
+
+The structs here must match the header field for field; ``tests/test_abi.py`` checks the
+sizes against the values the compiled libraries report and that every symbol the header
+declares is exported.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+SNN_ABI_VERSION = 3
+SNN_MAX_LAYERS = 8
+SNN_MAX_CONNS = 12
+
+SNN_NODE_INPUT, SNN_NODE_LIF, SNN_NODE_DC = 0, 1, 2
+SNN_CONN_DENSE, SNN_CONN_MCC = 0, 1
+SNN_RULE_NONE, SNN_RULE_NOOP, SNN_RULE_POSTPRE, SNN_RULE_WDEP_POSTPRE, SNN_RULE_MCC_POSTPRE = 0, 1, 2, 3, 4
+SNN_REDUCE_SUM, SNN_REDUCE_MEAN = 0, 1
+SNN_EXT_NONE, SNN_EXT_U8, SNN_EXT_F32 = 0, 1, 2
+
+SNN_OK = 0
+SNN_ERR_BAD_ARG = 1
+SNN_ERR_UNSUPPORTED = 2
+SNN_ERR_WORKSPACE = 4
+SNN_ERR_CUDA = 8
+SNN_ERR_NONBINARY = 16
+SNN_ERR_BARRIER = 32
+
+ERR_NAMES = {
+    SNN_ERR_BAD_ARG: "malformed plan",
+    SNN_ERR_UNSUPPORTED: "configuration not implemented by the CUDA core",
+    SNN_ERR_WORKSPACE: "workspace too small",
+    SNN_ERR_CUDA: "CUDA runtime error",
+    SNN_ERR_NONBINARY: "Input layer received values outside {0,1}",
+    SNN_ERR_BARRIER: "grid barrier timed out",
+}
+
+
+def describe_error(code: int) -> str:
+    return ", ".join(name for bit, name in ERR_NAMES.items() if code & bit) or f"status {code}"
+
+
+class SnnLayer(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("n", C.c_int32),
+        ("traces", C.c_int32),
+        ("traces_additive", C.c_int32),
+        ("sum_input", C.c_int32),
+        ("learning", C.c_int32),
+        ("one_spike", C.c_int32),
+        ("has_lbound", C.c_int32),
+        ("dt", C.c_float),
+        ("trace_decay", C.c_float),
+        ("trace_scale", C.c_float),
+        ("decay", C.c_float),
+        ("rest", C.c_float),
+        ("reset", C.c_float),
+        ("thresh", C.c_float),
+        ("refrac", C.c_float),
+        ("lbound", C.c_float),
+        ("theta_plus", C.c_float),
+        ("theta_decay", C.c_float),
+        ("ext_dtype", C.c_int32),
+        ("clamp_per_step", C.c_int32),
+        ("unclamp_per_step", C.c_int32),
+        ("inject_per_step", C.c_int32),
+        ("s", C.c_void_p),
+        ("v", C.c_void_p),
+        ("refrac_count", C.c_void_p),
+        ("x", C.c_void_p),
+        ("theta", C.c_void_p),
+        ("summed", C.c_void_p),
+        ("ext", C.c_void_p),
+        ("clamp", C.c_void_p),
+        ("unclamp", C.c_void_p),
+        ("inject_v", C.c_void_p),
+        ("rec_s", C.c_void_p),
+        ("rec_v", C.c_void_p),
+    ]
+
+
+class SnnConn(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("src", C.c_int32),
+        ("tgt", C.c_int32),
+        ("rule", C.c_int32),
+        ("reduction", C.c_int32),
+        ("has_norm", C.c_int32),
+        ("norm_abs", C.c_int32),
+        ("has_clamp", C.c_int32),
+        ("nu0", C.c_float),
+        ("nu1", C.c_float),
+        ("wmin", C.c_float),
+        ("wmax", C.c_float),
+        ("weight_decay", C.c_float),
+        ("dt_scale", C.c_float),
+        ("norm", C.c_float),
+        ("w", C.c_void_p),
+        ("b", C.c_void_p),
+    ]
+
+
+class SnnNet(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("n_conns", C.c_int32),
+        ("learning", C.c_int32),
+        ("layers", SnnLayer * SNN_MAX_LAYERS),
+        ("conns", SnnConn * SNN_MAX_CONNS),
+    ]
+
+
+class SnnRunOpts(C.Structure):
+    _fields_ = [
+        ("T", C.c_int32),
+        ("B", C.c_int32),
+        ("normalize", C.c_int32),
+        ("tier", C.c_int32),
+        ("seed", C.c_uint32),
+        ("step_offset", C.c_uint32),
+        ("err_flag", C.c_void_p),
+        ("reserved", C.c_int32),
+    ]
+
+
+def _fmix32(h: int) -> int:
+    h &= 0xFFFFFFFF
+    h ^= h >> 16
+    h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+    h ^= h >> 13
+    h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+    h ^= h >> 16
+    return h
+
+
+def one_spike_hash(seed: int, t: int, layer: int, b: int, j: int) -> int:
+    """Python restatement of ``snn_one_spike_hash`` (include/snn_b200.h)."""
+    h = _fmix32((seed ^ (0x9E3779B9 * (t + 1))) & 0xFFFFFFFF)
+    h = _fmix32((h + 0x85EBCA6B * (layer + 1) + b) & 0xFFFFFFFF)
+    h = _fmix32((h ^ (0xC2B2AE35 * (j + 1))) & 0xFFFFFFFF)
+    return h
+
+
+def one_spike_key(seed: int, t: int, layer: int, b: int, j: int) -> int:
+    return ((one_spike_hash(seed, t, layer, b, j) | 0x80000000) << 32) | j

@@ -1,0 +1,187 @@
+"""Canned networks — mirror of ``bindsnet/models/models.py`` (wiring only).
+
+``TwoLayerNetwork`` (models.py:21-91), ``DiehlAndCook2015`` (:94-244) and
+``DiehlAndCook2015v2`` (:247-346) build exactly the graphs the reference builds, out of this
+package's ``Nodes`` / ``Connection`` / ``MulticompartmentConnection`` objects, with the same
+constructor signatures and defaults.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Sequence, Union
+
+import torch
+
+from ..learning import PostPre
+from ..learning.MCC_learning import PostPre as MMCPostPre
+from ..network import Network
+from ..network.nodes import DiehlAndCookNodes, Input, LIFNodes
+from ..network.topology import Connection, MulticompartmentConnection
+from ..network.topology_features import Weight
+
+
+class TwoLayerNetwork(Network):
+    """``Input -> LIFNodes`` with a PostPre ``Connection`` (reference: models.py:21-91)."""
+
+    def __init__(
+        self,
+        n_inpt: int,
+        n_neurons: int = 100,
+        dt: float = 1.0,
+        wmin: float = 0.0,
+        wmax: float = 1.0,
+        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
+        reduction: Optional[callable] = None,
+        norm: float = 78.4,
+    ) -> None:
+        super().__init__(dt=dt)
+        self.n_inpt = n_inpt
+        self.n_neurons = n_neurons
+        self.dt = dt
+        self.add_layer(Input(n=self.n_inpt, traces=True, tc_trace=20.0), name="X")
+        self.add_layer(
+            LIFNodes(n=self.n_neurons, traces=True, rest=-65.0, reset=-65.0, thresh=-52.0, refrac=5,
+                     tc_decay=100.0, tc_trace=20.0),
+            name="Y",
+        )
+        w = 0.3 * torch.rand(self.n_inpt, self.n_neurons)
+        self.add_connection(
+            Connection(source=self.layers["X"], target=self.layers["Y"], w=w, update_rule=PostPre, nu=nu,
+                       reduction=reduction, wmin=wmin, wmax=wmax, norm=norm),
+            source="X", target="Y",
+        )
+
+
+class DiehlAndCook2015(Network):
+    """Diehl & Cook (2015): ``X -> Ae <-> Ai`` with MCC connections (reference:
+    models.py:94-244).  This is the graph the fused CUDA window kernel recognises."""
+
+    def __init__(
+        self,
+        n_inpt: int,
+        device: str = "cpu",
+        batch_size: int = None,
+        sparse: bool = False,
+        n_neurons: int = 100,
+        exc: float = 22.5,
+        inh: float = 17.5,
+        dt: float = 1.0,
+        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
+        reduction: Optional[callable] = None,
+        wmin: float = 0.0,
+        wmax: float = 1.0,
+        w_dtype: torch.dtype = torch.float32,
+        norm: float = 78.4,
+        theta_plus: float = 0.05,
+        tc_theta_decay: float = 1e7,
+        inpt_shape: Optional[Iterable[int]] = None,
+        inh_thresh: float = -40.0,
+        exc_thresh: float = -52.0,
+    ) -> None:
+        super().__init__(dt=dt)
+        self.n_inpt = n_inpt
+        self.inpt_shape = inpt_shape
+        self.n_neurons = n_neurons
+        self.exc = exc
+        self.inh = inh
+        self.dt = dt
+
+        input_layer = Input(n=self.n_inpt, shape=self.inpt_shape, traces=True, tc_trace=20.0)
+        exc_layer = DiehlAndCookNodes(
+            n=self.n_neurons, traces=True, rest=-65.0, reset=-60.0, thresh=exc_thresh, refrac=5,
+            tc_decay=100.0, tc_trace=20.0, theta_plus=theta_plus, tc_theta_decay=tc_theta_decay,
+        )
+        inh_layer = LIFNodes(
+            n=self.n_neurons, traces=False, rest=-60.0, reset=-45.0, thresh=inh_thresh, tc_decay=10.0,
+            refrac=2, tc_trace=20.0,
+        )
+
+        w = 0.3 * torch.rand(self.n_inpt, self.n_neurons)
+        input_exc_conn = MulticompartmentConnection(
+            source=input_layer, target=exc_layer, device=device,
+            pipeline=[
+                Weight("weight", w, value_dtype=w_dtype, range=[wmin, wmax], norm=norm, reduction=reduction,
+                       nu=nu, learning_rule=MMCPostPre, sparse=sparse, batch_size=batch_size)
+            ],
+        )
+        w = self.exc * torch.diag(torch.ones(self.n_neurons))
+        exc_inh_conn = MulticompartmentConnection(
+            source=exc_layer, target=inh_layer, device=device,
+            pipeline=[Weight("weight", w, value_dtype=w_dtype, range=[0, self.exc], sparse=sparse)],
+        )
+        w = -self.inh * (torch.ones(self.n_neurons, self.n_neurons) - torch.diag(torch.ones(self.n_neurons)))
+        inh_exc_conn = MulticompartmentConnection(
+            source=inh_layer, target=exc_layer, device=device,
+            pipeline=[Weight("weight", w, value_dtype=w_dtype, range=[-self.inh, 0], sparse=sparse)],
+        )
+
+        self.add_layer(input_layer, name="X")
+        self.add_layer(exc_layer, name="Ae")
+        self.add_layer(inh_layer, name="Ai")
+        self.add_connection(input_exc_conn, source="X", target="Ae")
+        self.add_connection(exc_inh_conn, source="Ae", target="Ai")
+        self.add_connection(inh_exc_conn, source="Ai", target="Ae")
+        if str(device) != "cpu":
+            self.to(device)
+
+
+class DiehlAndCook2015v2(Network):
+    """Variant with recurrent lateral inhibition instead of an inhibitory layer, built from
+    classic ``Connection`` + ``learning.PostPre`` (reference: models.py:247-346)."""
+
+    def __init__(
+        self,
+        n_inpt: int,
+        n_neurons: int = 100,
+        inh: float = 17.5,
+        dt: float = 1.0,
+        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
+        reduction: Optional[callable] = None,
+        wmin: Optional[float] = 0.0,
+        wmax: Optional[float] = 1.0,
+        norm: float = 78.4,
+        theta_plus: float = 0.05,
+        tc_theta_decay: float = 1e7,
+        inpt_shape: Optional[Iterable[int]] = None,
+        exc_thresh: float = -52.0,
+    ) -> None:
+        super().__init__(dt=dt)
+        self.n_inpt = n_inpt
+        self.inpt_shape = inpt_shape
+        self.n_neurons = n_neurons
+        self.inh = inh
+        self.dt = dt
+
+        self.add_layer(Input(n=self.n_inpt, shape=self.inpt_shape, traces=True, tc_trace=20.0), name="X")
+        self.add_layer(
+            DiehlAndCookNodes(
+                n=self.n_neurons, traces=True, rest=-65.0, reset=-60.0, thresh=exc_thresh, refrac=5,
+                tc_decay=100.0, tc_trace=20.0, theta_plus=theta_plus, tc_theta_decay=tc_theta_decay,
+            ),
+            name="Y",
+        )
+        w = 0.3 * torch.rand(self.n_inpt, self.n_neurons)
+        self.add_connection(
+            Connection(source=self.layers["X"], target=self.layers["Y"], w=w, update_rule=PostPre, nu=nu,
+                       reduction=reduction, wmin=wmin, wmax=wmax, norm=norm),
+            source="X", target="Y",
+        )
+        w = -self.inh * (torch.ones(self.n_neurons, self.n_neurons) - torch.diag(torch.ones(self.n_neurons)))
+        self.add_connection(
+            Connection(source=self.layers["Y"], target=self.layers["Y"], w=w, wmin=-self.inh, wmax=0),
+            source="Y", target="Y",
+        )
+
+
+def _unsupported(name: str, where: str):
+    class _Unsupported(Network):
+        __doc__ = f"``{name}`` (reference: {where}) — needs connection types outside the hot path."
+
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(f"models.{name} is outside the hot path bindsnet_b200 implements")
+
+    _Unsupported.__name__ = name
+    return _Unsupported
+
+
+IncreasingInhibitionNetwork = _unsupported("IncreasingInhibitionNetwork", "models.py:349-454")
+LocallyConnectedNetwork = _unsupported("LocallyConnectedNetwork", "models.py:457-584")

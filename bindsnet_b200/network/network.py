@@ -1,0 +1,256 @@
+"""``Network`` — host-side mirror of ``bindsnet/network/network.py``.
+
+Same registry API (``add_layer`` / ``add_connection`` / ``add_monitor``, network.py:119-161),
+same ``run(inputs, time, **kwargs)`` contract (network.py:252-465), same
+``reset_state_variables`` / ``train`` / ``save`` / ``load`` / ``clone``.  The difference is
+inside ``run``: instead of a Python loop over timesteps that dispatches ~80 ATen ops and
+three host syncs per step, the whole window is described once (``_plan.build_net``) and
+executed by one persistent CUDA kernel behind ``snn_b200_run_window``.
+"""
+from __future__ import annotations
+
+import tempfile
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import _abi, _backend
+from . import _plan
+from .monitors import AbstractMonitor, Monitor
+from .nodes import Nodes
+
+
+def load(file_name: str, map_location: str = "cpu", learning: bool = None) -> "Network":
+    """Reference: network.py:12-28."""
+    network = torch.load(open(file_name, "rb"), map_location=map_location, weights_only=False)
+    if learning is not None and "learning" in vars(network):
+        network.learning = learning
+    return network
+
+
+class Network(torch.nn.Module):
+    """Registry of layers, connections and monitors plus the simulation entry point
+    (reference: network.py:31-491)."""
+
+    def __init__(self, dt: float = 1.0, batch_size: int = 1, learning: bool = True, reward_fn=None) -> None:
+        super().__init__()
+        self.dt = dt
+        self.batch_size = batch_size
+        self.layers = {}
+        self.connections = {}
+        self.monitors = {}
+        self.train(learning)
+        if reward_fn is not None:
+            raise NotImplementedError("reward-modulated learning (reward_fn) is outside the implemented hot path")
+        self.reward_fn = None
+        #: seed of the last window's one_spike tie-break stream (see snn_one_spike_key)
+        self.last_one_spike_seed: Optional[int] = None
+
+    # -- registry (network.py:119-161) ----------------------------------------------------
+    def add_layer(self, layer: Nodes, name: str) -> None:
+        self.layers[name] = layer
+        self.add_module(name, layer)
+        layer.train(self.learning)
+        layer.compute_decays(self.dt)
+        layer.set_batch_size(self.batch_size)
+
+    def add_connection(self, connection, source: str, target: str) -> None:
+        self.connections[(source, target)] = connection
+        self.add_module(source + "_to_" + target, connection)
+        connection.dt = self.dt
+        connection.train(self.learning)
+
+    def add_monitor(self, monitor: AbstractMonitor, name: str) -> None:
+        self.monitors[name] = monitor
+        monitor.network = self
+        monitor.dt = self.dt
+
+    # -- persistence (network.py:163-209) -------------------------------------------------
+    def save(self, file_name: str) -> None:
+        torch.save(self, open(file_name, "wb"))
+
+    def clone(self) -> "Network":
+        virtual_file = tempfile.SpooledTemporaryFile()
+        torch.save(self, virtual_file)
+        virtual_file.seek(0)
+        return torch.load(virtual_file, weights_only=False)
+
+    # -- simulation -----------------------------------------------------------------------
+    def run(self, inputs: Dict[str, torch.Tensor], time: int, one_step=False, **kwargs) -> None:
+        """Simulate ``int(time / dt)`` steps (reference: network.py:252-465).
+
+        ``inputs[l]`` has shape ``[time, batch, *layer.shape]`` (or the shorter forms the
+        reference accepts, network.py:329-340).  Keyword arguments: ``clamp``, ``unclamp``,
+        ``injects_v`` as in the reference (network.py:268-281); ``one_spike_seed`` (extension)
+        fixes the tie-break stream of ``DiehlAndCookNodes(one_spike=True)``.
+        """
+        assert type(inputs) == dict, (
+            "'inputs' must be a dict of names of layers (str) and relevant input tensors. "
+            f"Got {type(inputs).__name__} instead."
+        )
+        if one_step:
+            raise NotImplementedError("one_step=True (feed-forward mode, network.py:383-396) is not implemented")
+        for unsupported in ("masks", "reward", "a_plus", "a_minus"):
+            if kwargs.get(unsupported):
+                raise NotImplementedError(f"run(..., {unsupported}=...) is outside the implemented hot path")
+
+        # network.py:329-353: canonical [T, B, ...] shape, batch-size inference, state reset
+        inputs = dict(inputs)
+        for key in inputs:
+            if inputs[key].dim() == 1:
+                inputs[key] = inputs[key].unsqueeze(0).unsqueeze(0)
+            elif inputs[key].dim() == 2:
+                inputs[key] = inputs[key].unsqueeze(1)
+        for key in inputs:
+            if inputs[key].size(1) != self.batch_size:
+                self.batch_size = inputs[key].size(1)
+                for l in self.layers:
+                    self.layers[l].set_batch_size(self.batch_size)
+                for m in self.monitors:
+                    self.monitors[m].reset_state_variables()
+            break
+
+        timesteps = int(time / self.dt)  # network.py:356
+        self._run_window(
+            inputs, timesteps, normalize=True,
+            clamp=kwargs.get("clamp", {}), unclamp=kwargs.get("unclamp", {}),
+            injects_v=kwargs.get("injects_v", {}), seed=kwargs.get("one_spike_seed", None),
+        )
+
+    def _device(self) -> torch.device:
+        return _plan.network_device(self)
+
+    def _stage_input(self, name: str, x: torch.Tensor, T: int, dev: torch.device) -> torch.Tensor:
+        layer = self.layers[name]
+        if x.size(0) < T:
+            raise ValueError(f"inputs['{name}'] has {x.size(0)} time steps, {T} required")
+        x = x[:T]
+        if x.dtype in (torch.bool, torch.uint8, torch.float32):
+            pass
+        elif x.dtype.is_floating_point:
+            x = x.float()
+        else:
+            x = x.to(torch.uint8) if layer.kind == _abi.SNN_NODE_INPUT else x.float()
+        x = x.to(dev, non_blocking=True)
+        return x.reshape(T, self.batch_size, layer.n).contiguous()
+
+    def _stage_mask(self, name: str, m, T: int, dev: torch.device, as_float: bool) -> torch.Tensor:
+        layer = self.layers[name]
+        m = torch.as_tensor(m)
+        is_index = not as_float and m.dtype not in (torch.bool, torch.uint8)
+        per_step = (m.dim() != 1) and not is_index  # network.py:418-421: 1-D = static, else [T, ...]
+        if as_float:
+            out = m.to(dev, torch.float32)
+        elif not is_index:
+            out = m.to(dev, torch.uint8)
+        else:  # index tensor, as accepted by ``s[:, clamp] = 1`` (network.py:419)
+            if m.dim() != 1:
+                raise NotImplementedError("per-step index clamps are not supported; pass a bool mask [T, n]")
+            out = torch.zeros(layer.n, dtype=torch.uint8, device=dev)
+            out[m.to(dev).long()] = 1
+        out = out.reshape(T, layer.n) if per_step else out.reshape(layer.n)
+        return out.contiguous()
+
+    def _fusable_monitor(self, mon) -> Optional[str]:
+        if not isinstance(mon, Monitor):
+            return None
+        for name, layer in self.layers.items():
+            if mon.obj is layer:
+                ok = all(v in Monitor.FUSED_VARS for v in mon.state_vars)
+                ok = ok and not ("v" in mon.state_vars and layer.kind == _abi.SNN_NODE_INPUT)
+                return name if ok else None
+        return None
+
+    def _run_window(self, inputs, T: int, normalize: bool, clamp=None, unclamp=None, injects_v=None,
+                    seed: Optional[int] = None, step_offset: int = 0) -> None:
+        dev = self._device()
+        B = self.batch_size
+        if T <= 0:
+            if normalize:
+                for c in self.connections.values():
+                    c.normalize()
+            return
+        ext = {k: self._stage_input(k, v, T, dev) for k, v in inputs.items() if k in self.layers}
+        clamps = {k: self._stage_mask(k, v, T, dev, False) for k, v in (clamp or {}).items() if v is not None}
+        unclamps = {k: self._stage_mask(k, v, T, dev, False) for k, v in (unclamp or {}).items() if v is not None}
+        injects = {k: self._stage_mask(k, v, T, dev, True) for k, v in (injects_v or {}).items() if v is not None}
+        if seed is None:
+            seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: torch.manual_seed governs it
+        self.last_one_spike_seed = seed
+
+        fused = {name: self._fusable_monitor(m) for name, m in self.monitors.items()}
+        if any(layer is None for layer in fused.values()):
+            return self._run_stepwise(ext, T, normalize, clamps, unclamps, injects, seed, step_offset)
+
+        rec: Dict[str, Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = {}
+        for mname, lname in fused.items():
+            mon, layer = self.monitors[mname], self.layers[lname]
+            rs, rv = rec.get(lname, (None, None))
+            if "s" in mon.state_vars and rs is None:
+                rs = torch.empty(T, B, layer.n, dtype=torch.uint8, device=dev)
+            if "v" in mon.state_vars and rv is None:
+                rv = torch.empty(T, B, layer.n, dtype=torch.float32, device=dev)
+            rec[lname] = (rs, rv)
+
+        net, keep = _plan.build_net(self, B, ext, clamps, unclamps, injects, rec)
+        opts = _abi.SnnRunOpts()
+        opts.T, opts.B, opts.normalize = T, B, int(normalize)
+        opts.tier = int(getattr(self, "force_tier", 0))
+        opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset
+        self._launch(net, opts, dev)
+        del keep
+
+        for mname, lname in fused.items():
+            mon, layer = self.monitors[mname], self.layers[lname]
+            rs, rv = rec[lname]
+            if "s" in mon.state_vars:
+                mon._push_window("s", rs.view(torch.bool).view(T, B, *layer.shape))
+            if "v" in mon.state_vars:
+                mon._push_window("v", rv.view(T, B, *layer.shape))
+
+    def _launch(self, net, opts, dev) -> None:
+        for layer in self.layers.values():
+            _backend.require_cuda(layer.s, "layer state")
+        for conn in self.connections.values():
+            _backend.require_cuda(conn.w, "connection weights")
+        _backend.run_window(net, opts, dev)
+
+    def _run_stepwise(self, ext, T, normalize, clamps, unclamps, injects, seed, step_offset) -> None:
+        """Fallback for per-step observers the kernels cannot serve (monitors on ``x``,
+        ``theta``, ``w`` ...): T one-step windows with ``Monitor.record`` after each, like
+        network.py:380-461.  Still CUDA-only; just launch-bound."""
+        B = self.batch_size
+        for t in range(T):
+            e = {k: v[t:t + 1] for k, v in ext.items()}
+            c = {k: (v[t] if v.dim() == 2 else v) for k, v in clamps.items()}
+            u = {k: (v[t] if v.dim() == 2 else v) for k, v in unclamps.items()}
+            i = {k: (v[t] if v.dim() == 2 else v) for k, v in injects.items()}
+            net, keep = _plan.build_net(self, B, e, c, u, i, {})
+            opts = _abi.SnnRunOpts()
+            opts.T, opts.B, opts.normalize = 1, B, int(normalize and t == T - 1)
+            opts.tier = int(getattr(self, "force_tier", 0))
+            opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset + t
+            self._launch(net, opts, self._device())
+            for m in self.monitors.values():
+                m.record()
+
+    def check_errors(self) -> None:
+        """Synchronise and raise if the device reported an error (non-binary input spikes,
+        barrier time-out).  Errors otherwise surface on the next ``run``."""
+        dev = self._device()
+        if dev.type == "cuda":
+            _backend.poll_errors(dev, sync=True)
+
+    def reset_state_variables(self) -> None:
+        """network.py:467-479."""
+        for layer in self.layers.values():
+            layer.reset_state_variables()
+        for connection in self.connections.values():
+            connection.reset_state_variables()
+        for monitor in self.monitors.values():
+            monitor.reset_state_variables()
+
+    def train(self, mode: bool = True) -> "torch.nn.Module":
+        """network.py:481-491."""
+        self.learning = mode
+        return super().train(mode)

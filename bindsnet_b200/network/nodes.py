@@ -1,0 +1,324 @@
+"""Neuron populations — host-side mirror of ``bindsnet/network/nodes.py``.
+
+These classes carry the same constructor signatures, attribute names and state tensors as
+the reference (``Nodes`` nodes.py:9-162, ``Input`` :172-228, ``LIFNodes`` :418-559,
+``DiehlAndCookNodes`` :981-1144) so that models written against BindsNET construct
+unchanged.  They hold state only: the arithmetic of ``forward`` runs inside the CUDA
+window kernels (``bindsnet_b200/csrc``), reached through ``Network.run`` or, for a single
+population, through ``Nodes.forward`` which submits a one-layer, one-step window.
+"""
+from __future__ import annotations
+
+from functools import reduce
+from operator import mul
+from typing import Iterable, Optional, Union
+
+import torch
+
+from .. import _abi
+
+Scalar = Union[float, int, torch.Tensor]
+
+
+def _exp_decay(dt: torch.Tensor, tc: torch.Tensor) -> torch.Tensor:
+    """``exp(-dt / tc)`` evaluated on CPU fp32 tensors exactly as the reference does
+    (nodes.py:129-131,546-548,1128-1133) so that the constants handed to the kernels are
+    bit-identical to the reference's whatever device the layer lives on."""
+    return torch.exp(-dt.detach().cpu().float() / tc.detach().cpu().float()).to(tc.device)
+
+
+def _scalar(value: Scalar, name: str) -> float:
+    if isinstance(value, torch.Tensor):
+        if value.numel() != 1:
+            raise NotImplementedError(
+                f"per-neuron tensor for '{name}' is not supported by the CUDA core yet (scalar only)"
+            )
+        return float(value.detach().cpu().reshape(()).item())
+    return float(value)
+
+
+class Nodes(torch.nn.Module):
+    """Base class of all populations (reference: nodes.py:9-162)."""
+
+    kind: Optional[int] = None  # SNN_NODE_*; None = not executable by the CUDA core
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        learning: bool = True,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        assert n is not None or shape is not None, "Must provide either no. of neurons or shape of layer"
+        self.n = int(reduce(mul, shape)) if n is None else int(n)
+        self.shape = [self.n] if shape is None else list(shape)
+        assert self.n == reduce(mul, self.shape), "No. of neurons and shape do not match"
+
+        self.traces = traces
+        self.traces_additive = traces_additive
+        self.sum_input = sum_input
+        self.register_buffer("s", torch.zeros(0, dtype=torch.bool))
+        if self.traces:
+            self.register_buffer("x", torch.zeros(0))
+            self.register_buffer("tc_trace", torch.as_tensor(tc_trace, dtype=torch.float))
+            self.register_buffer("trace_scale", torch.as_tensor(trace_scale, dtype=torch.float))
+            self.register_buffer("trace_decay", torch.empty_like(self.tc_trace))
+        if self.sum_input:
+            self.register_buffer("summed", torch.zeros(0))
+        self.dt = None
+        self.batch_size = None
+        self.learning = learning
+
+    # -- reference API -------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> None:
+        """One simulation step of this population alone (reference: ``Nodes.forward`` and
+        its overrides).  ``x`` is the input of the step, shape ``[B, *shape]``."""
+        from . import _plan
+
+        _plan.step_single_layer(self, x)
+
+    def reset_state_variables(self) -> None:
+        """nodes.py:109-120."""
+        self.s.zero_()
+        if self.traces:
+            self.x.zero_()
+        if self.sum_input:
+            self.summed.zero_()
+
+    def compute_decays(self, dt) -> None:
+        """nodes.py:122-131."""
+        self.dt = torch.tensor(dt)
+        if self.traces:
+            self.trace_decay = _exp_decay(self.dt, self.tc_trace)
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:133-151 — (re)allocates, i.e. resets, the per-sample state."""
+        self.batch_size = batch_size
+        dev = self.s.device
+        self.s = torch.zeros(batch_size, *self.shape, device=dev, dtype=torch.bool)
+        if self.traces:
+            self.x = torch.zeros(batch_size, *self.shape, device=dev)
+        if self.sum_input:
+            self.summed = torch.zeros(batch_size, *self.shape, device=dev)
+
+    def train(self, mode: bool = True) -> "Nodes":
+        """nodes.py:153-162."""
+        self.learning = mode
+        return super().train(mode)
+
+    # -- plan export -----------------------------------------------------------------------
+    def _fill_desc(self, d: "_abi.SnnLayer") -> None:
+        if self.kind is None:
+            raise NotImplementedError(
+                f"{type(self).__name__} has no CUDA implementation in bindsnet_b200 "
+                "(supported: Input, LIFNodes, DiehlAndCookNodes)"
+            )
+        d.kind = self.kind
+        d.n = self.n
+        d.traces = int(bool(self.traces))
+        d.traces_additive = int(bool(self.traces_additive))
+        d.sum_input = int(bool(self.sum_input))
+        d.learning = int(bool(self.learning))
+        d.dt = float(self.dt) if self.dt is not None else 1.0
+        if self.traces:
+            d.trace_decay = _scalar(self.trace_decay, "tc_trace")
+            d.trace_scale = _scalar(self.trace_scale, "trace_scale")
+
+
+class AbstractInput:
+    """Marker base of externally driven populations (reference: nodes.py:165-169)."""
+
+
+class Input(Nodes, AbstractInput):
+    """Population whose spikes are the user's input (reference: nodes.py:172-228)."""
+
+    kind = _abi.SNN_NODE_INPUT
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive,
+            tc_trace=tc_trace, trace_scale=trace_scale, sum_input=sum_input,
+        )
+
+
+class LIFNodes(Nodes):
+    """Leaky integrate-and-fire population (reference: nodes.py:418-559)."""
+
+    kind = _abi.SNN_NODE_LIF
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        thresh: Scalar = -52.0,
+        rest: Scalar = -65.0,
+        reset: Scalar = -65.0,
+        refrac: Scalar = 5,
+        tc_decay: Scalar = 100.0,
+        lbound: float = None,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive,
+            tc_trace=tc_trace, trace_scale=trace_scale, sum_input=sum_input,
+        )
+        self.register_buffer("rest", torch.as_tensor(rest, dtype=torch.float))
+        self.register_buffer("reset", torch.as_tensor(reset, dtype=torch.float))
+        self.register_buffer("thresh", torch.as_tensor(thresh, dtype=torch.float))
+        self.register_buffer("refrac", torch.as_tensor(refrac))
+        self.register_buffer("tc_decay", torch.as_tensor(tc_decay, dtype=torch.float))
+        self.register_buffer("decay", torch.zeros(()))
+        self.register_buffer("v", torch.zeros(0))
+        self.register_buffer("refrac_count", torch.zeros(0))
+        self.lbound = None if lbound is None else torch.tensor(lbound, dtype=torch.float)
+
+    def reset_state_variables(self) -> None:
+        """nodes.py:531-538."""
+        super().reset_state_variables()
+        self.v.fill_(self.rest)
+        self.refrac_count.zero_()
+
+    def compute_decays(self, dt) -> None:
+        """nodes.py:540-548."""
+        super().compute_decays(dt=dt)
+        self.decay = _exp_decay(self.dt, self.tc_decay)
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:550-559."""
+        super().set_batch_size(batch_size=batch_size)
+        dev = self.v.device
+        self.v = self.rest * torch.ones(batch_size, *self.shape, device=dev)
+        self.refrac_count = torch.zeros_like(self.v)
+
+    def _fill_desc(self, d) -> None:
+        super()._fill_desc(d)
+        d.decay = _scalar(self.decay, "tc_decay")
+        d.rest = _scalar(self.rest, "rest")
+        d.reset = _scalar(self.reset, "reset")
+        d.thresh = _scalar(self.thresh, "thresh")
+        d.refrac = _scalar(self.refrac, "refrac")
+        d.has_lbound = int(self.lbound is not None)
+        d.lbound = _scalar(self.lbound, "lbound") if self.lbound is not None else 0.0
+
+
+class DiehlAndCookNodes(Nodes):
+    """LIF with adaptive threshold and optional one-spike-per-step arbitration
+    (reference: nodes.py:981-1144)."""
+
+    kind = _abi.SNN_NODE_DC
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        thresh: Scalar = -52.0,
+        rest: Scalar = -65.0,
+        reset: Scalar = -65.0,
+        refrac: Scalar = 5,
+        tc_decay: Scalar = 100.0,
+        theta_plus: Scalar = 0.05,
+        tc_theta_decay: Scalar = 1e7,
+        lbound: float = None,
+        one_spike: bool = True,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive,
+            tc_trace=tc_trace, trace_scale=trace_scale, sum_input=sum_input,
+        )
+        self.register_buffer("rest", torch.as_tensor(rest, dtype=torch.float))
+        self.register_buffer("reset", torch.as_tensor(reset, dtype=torch.float))
+        self.register_buffer("thresh", torch.as_tensor(thresh, dtype=torch.float))
+        self.register_buffer("refrac", torch.as_tensor(refrac))
+        self.register_buffer("tc_decay", torch.as_tensor(tc_decay, dtype=torch.float))
+        self.register_buffer("decay", torch.zeros(()))
+        self.register_buffer("theta_plus", torch.as_tensor(theta_plus, dtype=torch.float))
+        self.register_buffer("tc_theta_decay", torch.as_tensor(tc_theta_decay, dtype=torch.float))
+        self.register_buffer("theta_decay", torch.zeros(()))
+        self.register_buffer("v", torch.zeros(0))
+        self.register_buffer("theta", torch.zeros(*self.shape))
+        self.register_buffer("refrac_count", torch.zeros(0))
+        self.lbound = lbound
+        self.one_spike = one_spike
+
+    def reset_state_variables(self) -> None:
+        """nodes.py:1113-1120 — ``theta`` is deliberately NOT reset."""
+        super().reset_state_variables()
+        self.v.fill_(self.rest)
+        self.refrac_count.zero_()
+
+    def compute_decays(self, dt) -> None:
+        """nodes.py:1122-1133."""
+        super().compute_decays(dt=dt)
+        self.decay = _exp_decay(self.dt, self.tc_decay)
+        self.theta_decay = _exp_decay(self.dt, self.tc_theta_decay)
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:1135-1144."""
+        super().set_batch_size(batch_size=batch_size)
+        dev = self.v.device
+        self.v = self.rest * torch.ones(batch_size, *self.shape, device=dev)
+        self.refrac_count = torch.zeros_like(self.v)
+
+    def _fill_desc(self, d) -> None:
+        super()._fill_desc(d)
+        d.decay = _scalar(self.decay, "tc_decay")
+        d.rest = _scalar(self.rest, "rest")
+        d.reset = _scalar(self.reset, "reset")
+        d.thresh = _scalar(self.thresh, "thresh")
+        d.refrac = _scalar(self.refrac, "refrac")
+        d.theta_plus = _scalar(self.theta_plus, "theta_plus")
+        d.theta_decay = _scalar(self.theta_decay, "tc_theta_decay")
+        d.one_spike = int(bool(self.one_spike))
+        d.has_lbound = int(self.lbound is not None)
+        d.lbound = _scalar(self.lbound, "lbound") if self.lbound is not None else 0.0
+
+
+def _unsupported(name: str, where: str):
+    class _Unsupported(Nodes):
+        __doc__ = f"``{name}`` (reference: {where}) — not on the accelerated path (SURVEY.md §8f)."
+
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(
+                f"{name} is outside the hot path bindsnet_b200 implements "
+                "(Input, LIFNodes, DiehlAndCookNodes); see DESIGN.md 'Out of scope'"
+            )
+
+    _Unsupported.__name__ = name
+    return _Unsupported
+
+
+McCullochPitts = _unsupported("McCullochPitts", "nodes.py:231-305")
+IFNodes = _unsupported("IFNodes", "nodes.py:308-415")
+BoostedLIFNodes = _unsupported("BoostedLIFNodes", "nodes.py:562-678")
+CurrentLIFNodes = _unsupported("CurrentLIFNodes", "nodes.py:681-826")
+AdaptiveLIFNodes = _unsupported("AdaptiveLIFNodes", "nodes.py:829-978")
+IzhikevichNodes = _unsupported("IzhikevichNodes", "nodes.py:1147-1316")
+CSRMNodes = _unsupported("CSRMNodes", "nodes.py:1319-1552")
+SRM0Nodes = _unsupported("SRM0Nodes", "nodes.py:1555-1701")

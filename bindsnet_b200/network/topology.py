@@ -1,0 +1,253 @@
+"""Synapse matrices — host-side mirror of ``bindsnet/network/topology.py``.
+
+``Connection`` (reference: topology.py:265-399) and ``MulticompartmentConnection`` with a
+``Weight`` feature (topology.py:402-537) keep the reference's constructor signatures and
+attributes (``w``, ``b``, ``wmin``, ``wmax``, ``norm``, ``source``, ``target``,
+``update_rule`` / ``pipeline``).  ``compute``/``update``/``normalize`` of a whole network run
+inside the CUDA window kernels; the standalone methods below submit single-connection
+work to the same kernels.
+"""
+from __future__ import annotations
+
+import warnings
+from abc import ABC
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+from torch.nn import Module, Parameter
+
+from .. import _abi
+from .nodes import Nodes
+
+
+class AbstractConnection(ABC, Module):
+    """Reference: topology.py:17-156."""
+
+    def __init__(
+        self,
+        source: Nodes,
+        target: Nodes,
+        nu: Optional[Union[float, Sequence[float], Sequence[torch.Tensor]]] = None,
+        reduction: Optional[callable] = None,
+        weight_decay: float = 0.0,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        assert isinstance(source, Nodes), "Source is not a Nodes object"
+        assert isinstance(target, Nodes), "Target is not a Nodes object"
+        self.source = source
+        self.target = target
+        self.weight_decay = weight_decay
+        self.reduction = reduction
+
+        from ..learning import NoOp
+
+        self.wmin = Parameter(torch.as_tensor(kwargs.get("wmin", -np.inf), dtype=torch.float32), requires_grad=False)
+        self.wmax = Parameter(torch.as_tensor(kwargs.get("wmax", np.inf), dtype=torch.float32), requires_grad=False)
+        self.norm = kwargs.get("norm", None)
+        self.decay = kwargs.get("decay", None)
+        if kwargs.get("Dales_rule", None) is not None:
+            raise NotImplementedError("Dales_rule is not implemented by the CUDA core (DESIGN.md 'Out of scope')")
+        self.Dales_rule = None
+
+        rule_cls = kwargs.get("update_rule", None) or NoOp
+        self.update_rule = rule_cls(connection=self, nu=nu, reduction=reduction, weight_decay=weight_decay, **kwargs)
+
+    def compute(self, s: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def update(self, **kwargs) -> None:
+        """topology.py:112-139: apply the learning rule to the current layer state."""
+        if kwargs.get("mask", None) is not None:
+            raise NotImplementedError("connection masks are not implemented by the CUDA core")
+        if kwargs.get("learning", True):
+            self.update_rule.update(**kwargs)
+
+    def reset_state_variables(self) -> None:
+        pass
+
+    @staticmethod
+    def cast_dtype_if_needed(w, w_dtype):
+        if w.dtype != w_dtype:
+            warnings.warn(f"Provided w has data type {w.dtype} but parameter w_dtype is {w_dtype}")
+            return w.to(dtype=w_dtype)
+        return w
+
+
+class Connection(AbstractConnection):
+    """Dense all-to-all synapses (reference: topology.py:265-399)."""
+
+    def __init__(
+        self,
+        source: Nodes,
+        target: Nodes,
+        nu: Optional[Union[float, Sequence[float], Sequence[torch.Tensor]]] = None,
+        reduction: Optional[callable] = None,
+        weight_decay: float = 0.0,
+        w_dtype: torch.dtype = torch.float32,
+        **kwargs,
+    ) -> None:
+        if w_dtype != torch.float32:
+            raise NotImplementedError("bindsnet_b200 computes in float32 only (SURVEY.md §8b)")
+        super().__init__(source, target, nu, reduction, weight_decay, **kwargs)
+        w = kwargs.get("w", None)
+        if w is None:
+            # topology.py:308-313
+            if (self.wmin == -np.inf).any() or (self.wmax == np.inf).any():
+                w = torch.clamp(torch.rand(source.n, target.n), self.wmin, self.wmax)
+            else:
+                w = self.wmin + torch.rand(source.n, target.n) * (self.wmax - self.wmin)
+            w = w.to(dtype=w_dtype)
+        else:
+            # topology.py:314-317
+            if (self.wmin != -np.inf).any() or (self.wmax != np.inf).any():
+                w = torch.clamp(torch.as_tensor(w), self.wmin, self.wmax)
+            w = self.cast_dtype_if_needed(torch.as_tensor(w), w_dtype)
+        self.w = Parameter(w.detach().clone().contiguous(), requires_grad=False)
+        b = kwargs.get("b", None)
+        self.b = Parameter(torch.as_tensor(b, dtype=torch.float32), requires_grad=False) if b is not None else None
+
+    def compute(self, s: torch.Tensor) -> torch.Tensor:
+        """``s.float() @ w (+ b)`` through the CUDA spike-gather (reference: topology.py:332-346)."""
+        from . import _plan
+
+        return _plan.compute_single_connection(self, s)
+
+    def normalize(self) -> None:
+        """topology.py:383-392."""
+        if self.norm is not None:
+            from . import _plan
+
+            _plan.normalize_single_connection(self)
+
+    # -- plan export -----------------------------------------------------------------------
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float) -> None:
+        d.kind = _abi.SNN_CONN_DENSE
+        if self.wmin.numel() != 1 or self.wmax.numel() != 1:
+            raise NotImplementedError("per-synapse wmin/wmax tensors are not supported by the CUDA core yet")
+        d.wmin = float(self.wmin)
+        d.wmax = float(self.wmax)
+        d.has_norm = int(self.norm is not None)
+        d.norm_abs = 1
+        d.norm = float(self.norm) if self.norm is not None else 0.0
+        d.dt_scale = 1.0
+        self.update_rule._fill_desc(d)
+
+
+class AbstractMulticompartmentConnection(ABC, Module):
+    """Reference: topology.py:159-262."""
+
+    def __init__(self, source: Nodes, target: Nodes, device, pipeline: list = None, **kwargs) -> None:
+        super().__init__()
+        assert isinstance(source, Nodes), "Source is not a Nodes object"
+        assert isinstance(target, Nodes), "Target is not a Nodes object"
+        self.source = source
+        self.target = target
+        self.device = device
+        self.pipeline = [] if pipeline is None else pipeline
+        self.feature_index = {}
+        for feature in self.pipeline:
+            self.feature_index[feature.name] = feature
+            feature.prime_feature(connection=self, device=self.device, **kwargs)
+
+    def append_pipeline(self, feature) -> None:
+        self.pipeline.append(feature)
+        feature.prime_feature(connection=self, device=self.device)
+        self.feature_index[feature.name] = feature
+
+
+class MulticompartmentConnection(AbstractMulticompartmentConnection):
+    """Feature-pipeline connection (reference: topology.py:402-537).  The CUDA core executes
+    pipelines consisting of exactly one dense ``Weight`` feature — what every model in
+    ``bindsnet.models`` builds (models.py:185-236)."""
+
+    def __init__(
+        self,
+        source: Nodes,
+        target: Nodes,
+        device="cpu",
+        pipeline: list = None,
+        manual_update: bool = False,
+        traces: bool = False,
+        **kwargs,
+    ) -> None:
+        super().__init__(source, target, device, pipeline if pipeline is not None else [], **kwargs)
+        self.traces = traces
+        self.manual_update = manual_update
+        if self.traces:
+            raise NotImplementedError("MulticompartmentConnection(traces=True) is not implemented by the CUDA core")
+
+    def _weight(self):
+        from .topology_features import Weight
+
+        if len(self.pipeline) != 1 or not isinstance(self.pipeline[0], Weight):
+            raise NotImplementedError(
+                "the CUDA core executes MulticompartmentConnection pipelines made of a single Weight feature"
+            )
+        return self.pipeline[0]
+
+    @property
+    def w(self) -> torch.Tensor:
+        return self._weight().value
+
+    def compute(self, s: torch.Tensor) -> torch.Tensor:
+        """Reference: topology.py:437-479 + Weight.compute topology_features.py:633-645."""
+        from . import _plan
+
+        return _plan.compute_single_connection(self, s)
+
+    def update(self, **kwargs) -> None:
+        """topology.py:509-518."""
+        if kwargs.get("learning", False) and not self.manual_update:
+            for f in self.pipeline:
+                f.update(**kwargs)
+
+    def normalize(self) -> None:
+        """topology.py:520-527."""
+        for f in self.pipeline:
+            f.normalize()
+
+    def reset_state_variables(self) -> None:
+        for f in self.pipeline:
+            f.reset_state_variables()
+
+    def _apply(self, fn, *args, **kwargs):
+        # Features are not nn.Modules in the reference (they take an explicit device,
+        # topology.py:169,192); here Network.to(device) carries their value along.
+        out = super()._apply(fn, *args, **kwargs)
+        for f in self.pipeline:
+            f._apply(fn)
+        return out
+
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float) -> None:
+        d.kind = _abi.SNN_CONN_MCC
+        self._weight()._fill_desc(d, dt, self.manual_update)
+
+
+def _unsupported(name: str, where: str):
+    class _Unsupported:
+        __doc__ = f"``{name}`` (reference: {where}) — not on the accelerated path (SURVEY.md §8f)."
+
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(
+                f"{name} is outside the hot path bindsnet_b200 implements (Connection, "
+                "MulticompartmentConnection[Weight]); see DESIGN.md 'Out of scope'"
+            )
+
+    _Unsupported.__name__ = name
+    return _Unsupported
+
+
+Conv1dConnection = _unsupported("Conv1dConnection", "topology.py:540-683")
+Conv2dConnection = _unsupported("Conv2dConnection", "topology.py:686-844")
+Conv3dConnection = _unsupported("Conv3dConnection", "topology.py:847-1025")
+MaxPool1dConnection = _unsupported("MaxPool1dConnection", "topology.py:1028-1121")
+MaxPool2dConnection = _unsupported("MaxPool2dConnection", "topology.py:1124-1211")
+MaxPoo3dConnection = _unsupported("MaxPoo3dConnection", "topology.py:1214-1301")
+LocalConnection = _unsupported("LocalConnection", "topology.py:1304-1484")
+LocalConnection1D = _unsupported("LocalConnection1D", "topology.py:1487-1620")
+LocalConnection2D = _unsupported("LocalConnection2D", "topology.py:1623-1767")
+LocalConnection3D = _unsupported("LocalConnection3D", "topology.py:1770-1917")
+MeanFieldConnection = _unsupported("MeanFieldConnection", "topology.py:1920-2006")
+SparseConnection = _unsupported("SparseConnection", "topology.py:2009-2017")

@@ -1,0 +1,259 @@
+/*
+ * snn_b200.h — C ABI of the B200-native SNN simulation core.
+ *
+ * This is the drop-in boundary for ONE path of BindsNET: the per-timestep loop of
+ * `Network.run()` (reference: bindsnet/network/network.py:252-465).  The reference has no
+ * native code and therefore no FFI of its own; the entry points below are what a
+ * maintainer would bind from `bindsnet/network/network.py` (see INTEGRATION.md for the
+ * ctypes stub).  Everything is plain C: pointers, sizes, POD structs, no torch types.
+ *
+ * A *window* is one call of Network.run(inputs, time=T): T timesteps over a batch of B
+ * samples.  The caller describes the network as an array of layers (reference: Nodes
+ * subclasses, bindsnet/network/nodes.py) and an array of connections (reference:
+ * AbstractConnection subclasses, bindsnet/network/topology.py) with their learning rule
+ * (bindsnet/learning/learning.py, bindsnet/learning/MCC_learning.py), in the insertion
+ * order of Network.add_layer / Network.add_connection, which fixes the accumulation order
+ * (network.py:225,246-248,386).
+ *
+ * All state pointers are the storage of the user's own tensors (layer.v, layer.x,
+ * connection.w ...) and are updated IN PLACE: after the call they hold the state the
+ * reference would hold after run() (network.py:380-465), including the end-of-run
+ * normalize (network.py:464-465).
+ *
+ * The same structs are consumed by two libraries:
+ *   - libsnn_b200.so   (bindsnet_b200/csrc, CUDA sm_100a; every pointer is a DEVICE pointer)
+ *   - libsnn_oracle.so (oracle/, plain C test infrastructure; every pointer is a HOST pointer)
+ */
+#ifndef SNN_B200_H
+#define SNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNN_ABI_VERSION 3
+#define SNN_MAX_LAYERS 8
+#define SNN_MAX_CONNS 12
+
+/* ---- node kinds (reference: bindsnet/network/nodes.py) ---- */
+#define SNN_NODE_INPUT 0 /* Input            nodes.py:172-228  */
+#define SNN_NODE_LIF 1   /* LIFNodes         nodes.py:418-559  */
+#define SNN_NODE_DC 2    /* DiehlAndCookNodes nodes.py:981-1144 */
+
+/* ---- connection kinds (reference: bindsnet/network/topology.py) ---- */
+#define SNN_CONN_DENSE 0 /* Connection: s.float() @ w + b                topology.py:332-346 */
+#define SNN_CONN_MCC 1   /* MulticompartmentConnection[Weight]: sum_i W*s  topology.py:437-479,
+                            topology_features.py:633-645 (same maths, dt-scaled STDP)          */
+
+/* ---- learning rules ---- */
+#define SNN_RULE_NONE 0        /* MCC_learning.NoOp: update() does nothing    MCC_learning.py:120-146 */
+#define SNN_RULE_NOOP 1        /* learning.NoOp: weight decay only, no clamp  learning.py:107-146     */
+#define SNN_RULE_POSTPRE 2     /* learning.PostPre._connection_update         learning.py:390-420     */
+#define SNN_RULE_WDEP_POSTPRE 3/* learning.WeightDependentPostPre             learning.py:626-653     */
+#define SNN_RULE_MCC_POSTPRE 4 /* MCC_learning.PostPre._connection_update     MCC_learning.py:224-302 */
+
+/* ---- batch reduction of the STDP update (learning.py:76-80) ---- */
+#define SNN_REDUCE_SUM 0  /* torch.sum; also torch.squeeze when B == 1 */
+#define SNN_REDUCE_MEAN 1 /* torch.mean */
+
+/* ---- external input dtype ---- */
+#define SNN_EXT_NONE 0
+#define SNN_EXT_U8 1  /* uint8 / bool, one byte per element */
+#define SNN_EXT_F32 2 /* float32 */
+
+/* ---- status codes (snn_*_run_window return value and *err_flag bits) ---- */
+#define SNN_OK 0
+#define SNN_ERR_BAD_ARG 1        /* malformed plan (sizes, indices, NULLs)                        */
+#define SNN_ERR_UNSUPPORTED 2    /* valid reference configuration this build does not implement   */
+#define SNN_ERR_WORKSPACE 4      /* workspace too small                                           */
+#define SNN_ERR_CUDA 8           /* a CUDA runtime call failed                                    */
+#define SNN_ERR_NONBINARY 16     /* (device flag) an Input layer received a value outside {0,1}   */
+#define SNN_ERR_BARRIER 32       /* (device flag) grid barrier timed out — kernel bailed out      */
+
+/* One population of neurons.  Reference: Nodes.__init__ nodes.py:15-86 + subclass ctor. */
+typedef struct snn_layer {
+    int32_t kind;            /* SNN_NODE_*                                                 */
+    int32_t n;               /* neurons per sample                                         */
+    int32_t traces;          /* Nodes.traces                                               */
+    int32_t traces_additive; /* Nodes.traces_additive                                      */
+    int32_t sum_input;       /* Nodes.sum_input                                            */
+    int32_t learning;        /* layer.learning (gates theta adaptation, nodes.py:1078,1093) */
+    int32_t one_spike;       /* DiehlAndCookNodes.one_spike (nodes.py:1097-1105)            */
+    int32_t has_lbound;      /* lbound is not None                                         */
+    float dt;                /* layer.dt (nodes.py:127)                                    */
+    float trace_decay;       /* exp(-dt/tc_trace), evaluated in fp32 like nodes.py:129-131 */
+    float trace_scale;
+    float decay;             /* exp(-dt/tc_decay)  nodes.py:546-548,1128-1130              */
+    float rest, reset, thresh, refrac, lbound;
+    float theta_plus;        /* DC only */
+    float theta_decay;       /* DC only: exp(-dt/tc_theta_decay) nodes.py:1131-1133        */
+    int32_t ext_dtype;       /* SNN_EXT_*: dtype of `ext`                                  */
+    int32_t clamp_per_step;  /* 0: clamp is [n]; 1: clamp is [T,n]   (network.py:416-421)   */
+    int32_t unclamp_per_step;
+    int32_t inject_per_step;
+    /* --- state, updated in place; shapes as in the reference --- */
+    uint8_t *s;          /* [B,n] 0/1.  in: spikes of step -1, out: spikes of step T-1      */
+    float *v;            /* [B,n]  (LIF, DC)                                                */
+    float *refrac_count; /* [B,n]  (LIF, DC)                                                */
+    float *x;            /* [B,n]  if traces                                                */
+    float *theta;        /* [n]    (DC) — shared across the batch, nodes.py:1061            */
+    float *summed;       /* [B,n]  if sum_input                                             */
+    /* --- per-window inputs --- */
+    const void *ext;        /* [T,B,n] external input (network.py:388-392) or NULL          */
+    const uint8_t *clamp;   /* bool mask, force s=1 after forward (network.py:415-421)      */
+    const uint8_t *unclamp; /* bool mask, force s=0 after forward (network.py:423-429)      */
+    const float *inject_v;  /* added to v before forward (network.py:398-404)               */
+    /* --- per-window recordings (Monitor, monitors.py:94-111); NULL = not recorded --- */
+    uint8_t *rec_s; /* [T,B,n] */
+    float *rec_v;   /* [T,B,n] */
+} snn_layer_t;
+
+/* One dense synapse matrix.  Reference: Connection (topology.py:265-399) or
+ * MulticompartmentConnection with a single Weight feature (topology.py:402-537,
+ * topology_features.py:575-671). */
+typedef struct snn_conn {
+    int32_t kind;      /* SNN_CONN_*                                                        */
+    int32_t src, tgt;  /* indices into layers[]                                             */
+    int32_t rule;      /* SNN_RULE_*                                                        */
+    int32_t reduction; /* SNN_REDUCE_*                                                      */
+    int32_t has_norm;  /* normalize at window end (network.py:464-465)                      */
+    int32_t norm_abs;  /* 1: divide by sum_i |w| (topology.py:390-392); 0: plain sum
+                          (topology_features.py:264-266)                                    */
+    int32_t has_clamp; /* rule clamps w to [wmin,wmax] after each update (learning.py:97-104,
+                          MCC_learning.py:101-110)                                          */
+    float nu0, nu1;    /* pre-/post-synaptic learning rates                                 */
+    float wmin, wmax;
+    float weight_decay;/* multiplicative per-step factor (learning.py:85,93-94); 1.0 = off  */
+    float dt_scale;    /* MCC: connection.dt factor on both STDP terms (MCC_learning.py:262,298) */
+    float norm;
+    float *w;          /* [n_src, n_tgt] row-major, updated in place                        */
+    const float *b;    /* [n_tgt] bias or NULL (topology.py:345)                            */
+} snn_conn_t;
+
+typedef struct snn_net {
+    int32_t abi_version; /* SNN_ABI_VERSION */
+    int32_t n_layers;
+    int32_t n_conns;
+    int32_t learning;    /* network.learning: gates connection.update() (network.py:448-450) */
+    snn_layer_t layers[SNN_MAX_LAYERS];
+    snn_conn_t conns[SNN_MAX_CONNS];
+} snn_net_t;
+
+typedef struct snn_run_opts {
+    int32_t T;             /* timesteps = int(time / dt)  (network.py:356)                    */
+    int32_t B;             /* batch size                                                      */
+    int32_t normalize;     /* 1: run every connection's normalize() after the loop            */
+    int32_t tier;          /* 0 = auto, 1 = force generic kernel, 2 = force fused DC2015 kernel */
+    uint32_t seed;         /* one_spike tie-break stream (see snn_one_spike_key)              */
+    uint32_t step_offset;  /* added to t in the tie-break hash (lets callers split a window)  */
+    int32_t *err_flag;     /* optional int32 (device memory for the CUDA lib); OR-ed with SNN_ERR_* */
+    int32_t reserved;
+} snn_run_opts_t;
+
+/*
+ * one_spike tie-break.  The reference draws the single winner per sample with
+ * torch.multinomial over the 0/1 candidate mask (nodes.py:1097-1105), i.e. uniformly among
+ * the threshold crossers.  We draw it as the arg-max of an i.i.d. 31-bit hash over the
+ * candidates, which is the same distribution and needs one atomicMax per sample across the
+ * whole grid.  key = ((h | 0x80000000) << 32) | j with
+ *   h = fmix32(fmix32(fmix32(seed ^ 0x9E3779B9*(t+1)) + 0x85EBCA6B*(layer+1) ^ b) + j)... —
+ * the exact function is snn_one_spike_hash() below; the oracle and the golden generator
+ * (which monkey-patches torch.multinomial with it) use the same definition.
+ */
+static inline uint32_t snn_fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h;
+}
+static inline uint32_t snn_one_spike_hash(uint32_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t j) {
+    uint32_t h = snn_fmix32(seed ^ (0x9E3779B9u * (t + 1u)));
+    h = snn_fmix32(h + 0x85EBCA6Bu * (layer + 1u) + b);
+    h = snn_fmix32(h ^ (0xC2B2AE35u * (j + 1u)));
+    return h;
+}
+static inline uint64_t snn_one_spike_key(uint32_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t j) {
+    return ((uint64_t)(snn_one_spike_hash(seed, t, layer, b, j) | 0x80000000u) << 32) | (uint64_t)j;
+}
+
+/* Row-chunking of the end-of-window column sum (normalize): rows are split into
+ * SNN_NORM_CHUNKS contiguous chunks of ceil(n_src/SNN_NORM_CHUNKS) rows, each summed in
+ * ascending row order, and the partial sums are then added in ascending chunk order.  Both
+ * libraries use this fixed order so that their results are bit-identical. */
+#define SNN_NORM_CHUNKS 16
+
+/* ------------------------------------------------------------------------------------------
+ * CUDA library (libsnn_b200.so).  Every pointer inside `net`/`opts` is a device pointer on the
+ * current device; `stream` is a cudaStream_t (NULL = legacy default stream).  Calls are
+ * asynchronous with respect to the host; no host synchronisation happens inside.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Bytes of scratch the window needs (spike bitmaps, tie-break keys, barrier words).
+ * Replaces: the per-step temporaries the reference allocates inside Network.run
+ * (network.py:240-242; topology.py:454; MCC_learning.py:234-299). */
+size_t snn_b200_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts);
+
+/* Run one window.  Replaces: Network.run's timestep loop + end-of-run normalize
+ * (network.py:380-465) together with everything it dispatches to: _get_inputs
+ * (network.py:211-250), Nodes.forward (nodes.py:96-107,211-221,500-529,1069-1111),
+ * Connection.compute / MulticompartmentConnection.compute (topology.py:332-346,437-479),
+ * LearningRule.update (learning.py:87-104,390-420,626-653; MCC_learning.py:86-110,224-302),
+ * Monitor.record (monitors.py:94-111) and normalize (topology.py:383-392;
+ * topology_features.py:250-266).  Returns SNN_OK or an SNN_ERR_* code (host-detectable
+ * errors only; device-detected errors are OR-ed into *opts->err_flag). */
+int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* Which kernel tier `tier = 0` would select for this plan: 1 generic, 2 fused DC2015. */
+int snn_b200_select_tier(const snn_net_t *net, const snn_run_opts_t *opts);
+
+/* Number of kernel launches the last snn_b200_run_window on this thread issued. */
+int snn_b200_last_launch_count(void);
+
+/* Multi-GPU window combine (no reference equivalent: SURVEY.md §8e).  After an
+ * all-reduce(sum) of dw = w_local - w0 over ranks:  w = clamp(w0 + dw_sum, wmin, wmax),
+ * then, if has_norm, the column normalisation of normalize().  n_src x n_tgt row-major. */
+int snn_b200_delta_prepare(const float *w, const float *w0, float *dw, size_t count, void *stream);
+int snn_b200_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t n_src, int32_t n_tgt,
+                         int32_t has_clamp, float wmin, float wmax, int32_t has_norm, int32_t norm_abs,
+                         float norm, void *stream);
+
+/* Single-operator entry points — the reference's per-object methods, for callers that drive
+ * the objects themselves instead of through Network.run:
+ *   snn_b200_conn_compute   = Connection.compute / MulticompartmentConnection.compute
+ *                             (topology.py:332-346,437-479): out[b,j] = sum_i s[b,i] w[i,j] (+ b[j])
+ *   snn_b200_conn_update    = connection.update(learning=True) for conns[conn_index] from the
+ *                             layers' CURRENT s / x (topology.py:112-139, learning.py:87-104,390-420,
+ *                             626-653; MCC_learning.py:86-110,224-302)
+ *   snn_b200_conn_normalize = Connection.normalize / AbstractFeature.normalize
+ *                             (topology.py:383-392, topology_features.py:250-266) */
+int snn_b200_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, int32_t B, const uint8_t *s,
+                          float *out, void *stream);
+int snn_b200_conn_update(const snn_net_t *net, int32_t conn_index, int32_t B, void *workspace,
+                         size_t workspace_bytes, void *stream);
+int snn_b200_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, void *stream);
+
+/* Library/ABI identification. */
+int snn_b200_abi_version(void);
+const char *snn_b200_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Oracle library (libsnn_oracle.so) — TEST INFRASTRUCTURE, host pointers, never shipped on the
+ * product path.  `dense` = 1 evaluates every product of the reference's dense formulation
+ * (zeros included, like `s.float() @ w` and the batch-summed outer products); 0 skips
+ * exact-zero terms.  Both give bit-identical results.  `threads` <= 0 means all cores.
+ * ------------------------------------------------------------------------------------------ */
+int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *opts, int dense, int threads);
+int snn_oracle_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t n_src, int32_t n_tgt,
+                           int32_t has_clamp, float wmin, float wmax, int32_t has_norm, int32_t norm_abs,
+                           float norm);
+int snn_oracle_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, int32_t B, const uint8_t *s,
+                            float *out);
+int snn_oracle_conn_update(const snn_net_t *net, int32_t conn_index, int32_t B);
+int snn_oracle_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt);
+int snn_oracle_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNN_B200_H */

@@ -1,0 +1,473 @@
+/*
+ * snn_oracle.c — CPU restatement of BindsNET's Network.run() hot path.
+ *
+ * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` leg may load this library; the product path (bindsnet_b200) never does.
+ *
+ * Parity pinning: the reference's own tests hold no golden vectors for this path
+ * (SURVEY.md §4, §8c), so this restatement is pinned against the LIVE reference instead:
+ * oracle/gen_golden.py imports /root/reference, runs it under fixed seeds and commits the
+ * inputs + resulting state under tests/golden/; tests/test_oracle_golden.py replays them here.
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * /root/reference/bindsnet/).  Arithmetic is fp32 with one rounding per reference ATen op
+ * (compile with -ffp-contract=off: no FMA contraction).  Where the reference leaves a
+ * summation order to ATen (sum over pre-synaptic neurons, over the batch, over rows in
+ * normalize) this file fixes it to ascending index order (normalize: SNN_NORM_CHUNKS
+ * chunks), which is the order the CUDA kernels use, so kernel-vs-oracle is bit-exact and
+ * oracle-vs-reference is within fp32 summation-order tolerance.
+ *
+ * `dense` = 1 evaluates every product of the reference's dense formulation (the zeros of
+ * `s.float() @ w` and of the batch-summed outer products included) — that is the costed
+ * restatement used as the CPU baseline; `dense` = 0 skips exact-zero terms (bit-identical,
+ * used to make large test cases fast).
+ */
+#include "../include/snn_b200.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    float *cur;      /* [B,n] input current of this step (network.py:240-248)            */
+    uint8_t *cand;   /* [B,n] DC: threshold crossers before one_spike                    */
+    int has_in;
+} layer_ws_t;
+
+typedef struct {
+    float *U, *V;    /* [n_src,n_tgt] batch-reduced pre / post outer products            */
+    float *tx;       /* [B,n_tgt] scratch                                                */
+    uint8_t *row_t;  /* [n_src] row touched by the pre term this step                    */
+    uint8_t *col_t;  /* [n_tgt] column touched by the post term this step                */
+    int first_update_done;
+} conn_ws_t;
+
+static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
+    if (!net || !o || net->abi_version != SNN_ABI_VERSION) return SNN_ERR_BAD_ARG;
+    if (net->n_layers < 0 || net->n_layers > SNN_MAX_LAYERS) return SNN_ERR_BAD_ARG;
+    if (net->n_conns < 0 || net->n_conns > SNN_MAX_CONNS) return SNN_ERR_BAD_ARG;
+    if (o->T < 0 || o->B <= 0) return SNN_ERR_BAD_ARG;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const snn_layer_t *L = &net->layers[l];
+        if (L->n <= 0 || !L->s) return SNN_ERR_BAD_ARG;
+        if (L->kind != SNN_NODE_INPUT && (!L->v || !L->refrac_count)) return SNN_ERR_BAD_ARG;
+        if (L->kind == SNN_NODE_DC && !L->theta) return SNN_ERR_BAD_ARG;
+        if (L->traces && !L->x) return SNN_ERR_BAD_ARG;
+        if (L->sum_input && !L->summed) return SNN_ERR_BAD_ARG;
+        if (L->kind < 0 || L->kind > SNN_NODE_DC) return SNN_ERR_UNSUPPORTED;
+    }
+    for (int c = 0; c < net->n_conns; ++c) {
+        const snn_conn_t *C = &net->conns[c];
+        if (C->src < 0 || C->src >= net->n_layers || C->tgt < 0 || C->tgt >= net->n_layers) return SNN_ERR_BAD_ARG;
+        if (!C->w) return SNN_ERR_BAD_ARG;
+        if (net->layers[C->tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
+        if (C->rule < 0 || C->rule > SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
+        if (C->rule >= SNN_RULE_POSTPRE) {
+            /* learning.py:373-376,597-599; MCC_learning.py:193-196: traces required */
+            if (!net->layers[C->src].traces) return SNN_ERR_BAD_ARG;
+            if (!net->layers[C->tgt].traces) return SNN_ERR_BAD_ARG; /* target.x is read by every STDP rule */
+        }
+    }
+    return SNN_OK;
+}
+
+/* Connection.compute (topology.py:332-346) / MulticompartmentConnection.compute with a
+ * Weight feature (topology.py:437-479, topology_features.py:633-645):
+ * p[b,j] = sum_i s[b,i] * w[i,j] (+ bias), i ascending; then network.py:248 adds p into the
+ * target's accumulator. */
+static void conn_compute(const snn_conn_t *C, const snn_layer_t *S, int n_tgt, int B, float *cur, int dense) {
+    const int ns = S->n;
+#pragma omp parallel
+    {
+        float *p = (float *)malloc(sizeof(float) * (size_t)n_tgt);
+#pragma omp for schedule(static)
+        for (int b = 0; b < B; ++b) {
+            const uint8_t *s = S->s + (size_t)b * ns;
+            for (int j = 0; j < n_tgt; ++j) p[j] = 0.0f;
+            for (int i = 0; i < ns; ++i) {
+                const float sv = s[i] ? 1.0f : 0.0f;
+                if (!dense && !s[i]) continue;
+                const float *wr = C->w + (size_t)i * n_tgt;
+                for (int j = 0; j < n_tgt; ++j) p[j] = p[j] + sv * wr[j];
+            }
+            float *cb = cur + (size_t)b * n_tgt;
+            if (C->b && C->kind == SNN_CONN_DENSE)
+                for (int j = 0; j < n_tgt; ++j) cb[j] = cb[j] + (p[j] + C->b[j]); /* topology.py:345 */
+            else
+                for (int j = 0; j < n_tgt; ++j) cb[j] = cb[j] + p[j];
+        }
+        free(p);
+    }
+}
+
+/* Nodes.forward: spike trace + summed input (nodes.py:96-107). */
+static inline void trace_and_sum(const snn_layer_t *L, size_t k, int s, float xin) {
+    if (L->traces) {
+        float x = L->x[k] * L->trace_decay;                 /* nodes.py:98  */
+        if (L->traces_additive) x = x + L->trace_scale * (s ? 1.0f : 0.0f); /* nodes.py:101 */
+        else if (s) x = L->trace_scale;                     /* nodes.py:103 */
+        L->x[k] = x;
+    }
+    if (L->sum_input) L->summed[k] = L->summed[k] + xin;    /* nodes.py:107 */
+}
+
+static void layer_forward(const snn_net_t *net, int l, const snn_run_opts_t *o, int t, layer_ws_t *ws, int *err) {
+    const snn_layer_t *L = &net->layers[l];
+    const int B = o->B, n = L->n;
+    const size_t BN = (size_t)B * n;
+    float *cur = ws->cur;
+
+    /* network.py:388-392: external input of this step */
+    if (L->kind == SNN_NODE_INPUT) {
+        /* Input.forward (nodes.py:211-221): s = x */
+        for (size_t k = 0; k < BN; ++k) {
+            int s = 0;
+            if (L->ext_dtype == SNN_EXT_U8) {
+                uint8_t e = ((const uint8_t *)L->ext)[(size_t)t * BN + k];
+                s = e != 0; if (e > 1) *err |= SNN_ERR_NONBINARY;
+            } else if (L->ext_dtype == SNN_EXT_F32) {
+                float e = ((const float *)L->ext)[(size_t)t * BN + k];
+                s = e != 0.0f; if (e != 0.0f && e != 1.0f) *err |= SNN_ERR_NONBINARY;
+            }
+            L->s[k] = (uint8_t)s;
+            trace_and_sum(L, k, s, s ? 1.0f : 0.0f);
+        }
+    } else {
+        if (!ws->has_in) memset(cur, 0, sizeof(float) * BN); /* network.py:408-413 */
+        if (L->ext_dtype == SNN_EXT_U8) {
+            const uint8_t *e = (const uint8_t *)L->ext + (size_t)t * BN;
+            for (size_t k = 0; k < BN; ++k) cur[k] = cur[k] + (float)e[k];
+        } else if (L->ext_dtype == SNN_EXT_F32) {
+            const float *e = (const float *)L->ext + (size_t)t * BN;
+            for (size_t k = 0; k < BN; ++k) cur[k] = cur[k] + e[k];
+        }
+        /* network.py:398-404: voltage injection before forward */
+        if (L->inject_v) {
+            const float *iv = L->inject_v + (L->inject_per_step ? (size_t)t * n : 0);
+            for (int b = 0; b < B; ++b)
+                for (int j = 0; j < n; ++j) L->v[(size_t)b * n + j] += iv[j];
+        }
+        if (L->kind == SNN_NODE_LIF) {
+            /* LIFNodes.forward (nodes.py:500-529) */
+            for (size_t k = 0; k < BN; ++k) {
+                float v = L->decay * (L->v[k] - L->rest) + L->rest;   /* :508 */
+                float xin = cur[k];
+                if (L->refrac_count[k] > 0.0f) xin = 0.0f;            /* :511 (in place on x) */
+                float rc = L->refrac_count[k] - L->dt;                /* :514 */
+                v = v + xin;                                          /* :516 */
+                int s = v >= L->thresh;                               /* :519 */
+                if (s) { rc = L->refrac; v = L->reset; }              /* :522-523 */
+                if (L->has_lbound && v < L->lbound) v = L->lbound;    /* :526-527 */
+                L->v[k] = v; L->refrac_count[k] = rc; L->s[k] = (uint8_t)s;
+                trace_and_sum(L, k, s, xin);                          /* :529 (masked x) */
+            }
+        } else { /* SNN_NODE_DC: DiehlAndCookNodes.forward (nodes.py:1069-1111) */
+            uint8_t *cand = ws->cand;
+            if (L->learning)
+                for (int j = 0; j < n; ++j) L->theta[j] = L->theta[j] * L->theta_decay; /* :1078-1079 */
+            for (size_t k = 0; k < BN; ++k) {
+                const int j = (int)(k % (size_t)n);
+                float v = L->decay * (L->v[k] - L->rest) + L->rest;   /* :1077 */
+                const float gate = L->refrac_count[k] <= 0.0f ? 1.0f : 0.0f;
+                v = v + gate * cur[k];                                /* :1082 */
+                float rc = L->refrac_count[k] - L->dt;                /* :1085 */
+                int s = v >= (L->thresh + L->theta[j]);               /* :1088 */
+                if (s) { rc = L->refrac; v = L->reset; }              /* :1091-1092 */
+                L->v[k] = v; L->refrac_count[k] = rc; cand[k] = (uint8_t)s;
+            }
+            if (L->learning) {                                        /* :1093-1094 */
+                for (int j = 0; j < n; ++j) {
+                    int cnt = 0;
+                    for (int b = 0; b < B; ++b) cnt += cand[(size_t)b * n + j];
+                    L->theta[j] = L->theta[j] + L->theta_plus * (float)cnt;
+                }
+            }
+            for (int b = 0; b < B; ++b) {                             /* :1097-1105 */
+                uint8_t *cb = cand + (size_t)b * n;
+                uint8_t *sb = L->s + (size_t)b * n;
+                if (L->one_spike) {
+                    uint64_t best = 0;
+                    for (int j = 0; j < n; ++j)
+                        if (cb[j]) {
+                            uint64_t key = snn_one_spike_key(o->seed, (uint32_t)t + o->step_offset, (uint32_t)l, (uint32_t)b, (uint32_t)j);
+                            if (key > best) best = key;
+                        }
+                    for (int j = 0; j < n; ++j) sb[j] = 0;
+                    if (best) sb[(uint32_t)(best & 0xFFFFFFFFu)] = 1;
+                } else {
+                    for (int j = 0; j < n; ++j) sb[j] = cb[j];
+                }
+            }
+            for (size_t k = 0; k < BN; ++k) {
+                float v = L->v[k];
+                if (L->has_lbound && v < L->lbound) { v = L->lbound; L->v[k] = v; } /* :1108-1109 */
+                trace_and_sum(L, k, L->s[k], cur[k]);                 /* :1111 */
+            }
+        }
+    }
+    /* network.py:415-429: clamp / unclamp after forward (traces already updated) */
+    if (L->clamp) {
+        const uint8_t *m = L->clamp + (L->clamp_per_step ? (size_t)t * n : 0);
+        for (int b = 0; b < B; ++b)
+            for (int j = 0; j < n; ++j) if (m[j]) L->s[(size_t)b * n + j] = 1;
+    }
+    if (L->unclamp) {
+        const uint8_t *m = L->unclamp + (L->unclamp_per_step ? (size_t)t * n : 0);
+        for (int b = 0; b < B; ++b)
+            for (int j = 0; j < n; ++j) if (m[j]) L->s[(size_t)b * n + j] = 0;
+    }
+}
+
+static inline float clampf(float w, float lo, float hi) {
+    /* torch.clamp_: min(max(w, lo), hi) */
+    w = w < lo ? lo : w;
+    w = w > hi ? hi : w;
+    return w;
+}
+
+/* LearningRule.update for one connection:
+ *   learning.PostPre._connection_update           learning.py:390-420
+ *   learning.WeightDependentPostPre._connection_update  learning.py:626-653
+ *   MCC_learning.PostPre._connection_update       MCC_learning.py:224-302
+ * followed by the base-class decay + clamp (learning.py:87-104, MCC_learning.py:86-110). */
+static void conn_update(const snn_net_t *net, const snn_conn_t *C, const snn_run_opts_t *o, conn_ws_t *ws, int dense) {
+    if (C->rule == SNN_RULE_NONE) return;
+    const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
+    const int B = o->B, ns = S->n, nt = G->n;
+    const size_t NW = (size_t)ns * nt;
+    float *w = C->w;
+    const int stdp = C->rule >= SNN_RULE_POSTPRE;
+    const int wdep = C->rule == SNN_RULE_WDEP_POSTPRE;
+    const int pre_on = stdp && C->nu0 != 0.0f, post_on = stdp && C->nu1 != 0.0f;
+    const float dts = C->rule == SNN_RULE_MCC_POSTPRE ? C->dt_scale : 1.0f;
+    const int use_dt = C->rule == SNN_RULE_MCC_POSTPRE;
+    const float Bf = (float)B;
+    int any_row = 0, any_col = 0;
+
+    if (pre_on) {
+        /* U[i,j] = reduce_b s_src[b,i] * (x_tgt[b,j] * nu0)   (WDEP: without nu0) */
+        float *tx = ws->tx;
+        for (size_t k = 0; k < (size_t)B * nt; ++k) tx[k] = wdep ? G->x[k] : G->x[k] * C->nu0;
+#pragma omp parallel for schedule(static) reduction(|:any_row)
+        for (int i = 0; i < ns; ++i) {
+            float *Ui = ws->U + (size_t)i * nt;
+            int touched = 0;
+            if (dense) touched = 1;
+            else for (int b = 0; b < B; ++b) if (S->s[(size_t)b * ns + i]) { touched = 1; break; }
+            ws->row_t[i] = (uint8_t)touched;
+            if (!touched) continue;
+            any_row = 1;
+            for (int j = 0; j < nt; ++j) Ui[j] = 0.0f;
+            for (int b = 0; b < B; ++b) {
+                const uint8_t sb = S->s[(size_t)b * ns + i];
+                if (!dense && !sb) continue;
+                const float sv = sb ? 1.0f : 0.0f;
+                const float *txb = tx + (size_t)b * nt;
+                for (int j = 0; j < nt; ++j) Ui[j] = Ui[j] + sv * txb[j];
+            }
+            if (C->reduction == SNN_REDUCE_MEAN) for (int j = 0; j < nt; ++j) Ui[j] = Ui[j] / Bf;
+        }
+    } else memset(ws->row_t, 0, (size_t)ns);
+
+    if (post_on) {
+        /* V[i,j] = reduce_b x_src[b,i] * (s_tgt[b,j] * nu1)   (WDEP: without nu1) */
+        for (int j = 0; j < nt; ++j) {
+            int touched = dense;
+            if (!touched) for (int b = 0; b < B; ++b) if (G->s[(size_t)b * nt + j]) { touched = 1; break; }
+            ws->col_t[j] = (uint8_t)touched;
+            any_col |= touched;
+        }
+        if (any_col) {
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < ns; ++i) {
+                float *Vi = ws->V + (size_t)i * nt;
+                for (int j = 0; j < nt; ++j) if (ws->col_t[j]) Vi[j] = 0.0f;
+                for (int b = 0; b < B; ++b) {
+                    const float xs = S->x[(size_t)b * ns + i];
+                    const uint8_t *sg = G->s + (size_t)b * nt;
+                    for (int j = 0; j < nt; ++j) {
+                        if (!ws->col_t[j]) continue;
+                        if (!dense && !sg[j]) continue;
+                        const float ts = wdep ? (sg[j] ? 1.0f : 0.0f) : (sg[j] ? 1.0f : 0.0f) * C->nu1;
+                        Vi[j] = Vi[j] + xs * ts;
+                    }
+                }
+                if (C->reduction == SNN_REDUCE_MEAN) for (int j = 0; j < nt; ++j) if (ws->col_t[j]) Vi[j] = Vi[j] / Bf;
+            }
+        }
+    } else memset(ws->col_t, 0, (size_t)nt);
+
+    /* per-entry application, in the reference's order: pre, post, decay, clamp.
+     * Untouched entries are bitwise unchanged by the reference's full-tensor ops unless the
+     * decay factor is not 1 or the entry is outside [wmin,wmax] (possible only before the
+     * first clamp of the window, e.g. right after normalize()). */
+    const int decay_on = C->weight_decay != 0.0f && C->weight_decay != 1.0f;
+    const int full = dense || decay_on || (C->has_clamp && !ws->first_update_done);
+    ws->first_update_done = 1;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < ns; ++i) {
+        const int rt = ws->row_t[i];
+        if (!full && !rt && !any_col) continue;
+        float *wi = w + (size_t)i * nt;
+        const float *Ui = ws->U + (size_t)i * nt, *Vi = ws->V + (size_t)i * nt;
+        for (int j = 0; j < nt; ++j) {
+            const int ct = ws->col_t[j];
+            if (!full && !rt && !ct) continue;
+            float x = wi[j];
+            if (wdep) {
+                float upd = 0.0f;
+                if (pre_on) upd = upd - (C->nu0 * (rt ? Ui[j] : 0.0f)) * (x - C->wmin);  /* learning.py:643-644 */
+                if (post_on) upd = upd + (C->nu1 * (ct ? Vi[j] : 0.0f)) * (C->wmax - x); /* learning.py:648-649 */
+                x = x + upd;                                                             /* learning.py:651     */
+            } else {
+                if (pre_on && rt) x = use_dt ? x - Ui[j] * dts : x - Ui[j];   /* learning.py:405 / MCC:260-263 */
+                if (post_on && ct) x = use_dt ? x + Vi[j] * dts : x + Vi[j];  /* learning.py:417 / MCC:296-299 */
+            }
+            if (C->weight_decay != 0.0f) x = x * C->weight_decay;             /* learning.py:93-94   */
+            if (C->has_clamp) x = clampf(x, C->wmin, C->wmax);                /* learning.py:97-104  */
+            wi[j] = x;
+        }
+    }
+    (void)NW;
+}
+
+/* Connection.normalize (topology.py:383-392) / AbstractFeature.normalize
+ * (topology_features.py:250-266). */
+static void normalize_cols(float *w, int ns, int nt, int norm_abs, float norm) {
+    const int chunk = (ns + SNN_NORM_CHUNKS - 1) / SNN_NORM_CHUNKS;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < nt; ++j) {
+        float tot = 0.0f;
+        for (int c = 0; c < SNN_NORM_CHUNKS; ++c) {
+            float part = 0.0f;
+            const int i1 = (c + 1) * chunk < ns ? (c + 1) * chunk : ns;
+            for (int i = c * chunk; i < i1; ++i) {
+                const float x = w[(size_t)i * nt + j];
+                part = part + (norm_abs ? fabsf(x) : x);
+            }
+            tot = tot + part;
+        }
+        if (tot == 0.0f) tot = 1.0f;
+        const float f = norm / tot;
+        for (int i = 0; i < ns; ++i) w[(size_t)i * nt + j] = w[(size_t)i * nt + j] * f;
+    }
+}
+
+int snn_oracle_abi_version(void) { return SNN_ABI_VERSION; }
+
+int snn_oracle_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t n_src, int32_t n_tgt,
+                           int32_t has_clamp, float wmin, float wmax, int32_t has_norm, int32_t norm_abs,
+                           float norm) {
+    const size_t N = (size_t)n_src * n_tgt;
+    for (size_t k = 0; k < N; ++k) {
+        float x = w0[k] + dw_sum[k];
+        if (has_clamp) x = clampf(x, wmin, wmax);
+        w[k] = x;
+    }
+    if (has_norm) normalize_cols(w, n_src, n_tgt, norm_abs, norm);
+    return SNN_OK;
+}
+
+/* Network.run (network.py:252-465): the timestep loop. */
+int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int dense, int threads) {
+    int rc = check_plan(net, o);
+    if (rc) return rc;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+    const int B = o->B, T = o->T;
+    layer_ws_t lws[SNN_MAX_LAYERS];
+    conn_ws_t cws[SNN_MAX_CONNS];
+    memset(lws, 0, sizeof(lws)); memset(cws, 0, sizeof(cws));
+    for (int l = 0; l < net->n_layers; ++l) {
+        const size_t BN = (size_t)B * net->layers[l].n;
+        lws[l].cur = (float *)calloc(BN, sizeof(float));
+        lws[l].cand = (uint8_t *)calloc(BN, 1);
+    }
+    for (int c = 0; c < net->n_conns; ++c) {
+        const snn_conn_t *C = &net->conns[c];
+        const int ns = net->layers[C->src].n, nt = net->layers[C->tgt].n;
+        if (C->rule >= SNN_RULE_POSTPRE) {
+            cws[c].U = (float *)calloc((size_t)ns * nt, sizeof(float));
+            cws[c].V = (float *)calloc((size_t)ns * nt, sizeof(float));
+            cws[c].tx = (float *)calloc((size_t)B * nt, sizeof(float));
+        }
+        cws[c].row_t = (uint8_t *)calloc((size_t)ns, 1);
+        cws[c].col_t = (uint8_t *)calloc((size_t)nt, 1);
+    }
+    int err = 0;
+    for (int t = 0; t < T; ++t) {
+        /* 1. _get_inputs (network.py:211-250): currents from the PREVIOUS step's spikes */
+        for (int l = 0; l < net->n_layers; ++l) lws[l].has_in = 0;
+        for (int c = 0; c < net->n_conns; ++c) {
+            const snn_conn_t *C = &net->conns[c];
+            const snn_layer_t *G = &net->layers[C->tgt];
+            if (!lws[C->tgt].has_in) { memset(lws[C->tgt].cur, 0, sizeof(float) * (size_t)B * G->n); lws[C->tgt].has_in = 1; }
+            conn_compute(C, &net->layers[C->src], G->n, B, lws[C->tgt].cur, dense);
+        }
+        /* 2. layers in insertion order (network.py:386-429) */
+        for (int l = 0; l < net->n_layers; ++l) layer_forward(net, l, o, t, &lws[l], &err);
+        /* 3. connection updates in insertion order (network.py:431-454) */
+        if (net->learning)
+            for (int c = 0; c < net->n_conns; ++c) conn_update(net, &net->conns[c], o, &cws[c], dense);
+        /* 4. monitors (network.py:460-461, monitors.py:94-111) */
+        for (int l = 0; l < net->n_layers; ++l) {
+            const snn_layer_t *L = &net->layers[l];
+            const size_t BN = (size_t)B * L->n;
+            if (L->rec_s) memcpy(L->rec_s + (size_t)t * BN, L->s, BN);
+            if (L->rec_v && L->v) memcpy(L->rec_v + (size_t)t * BN, L->v, BN * sizeof(float));
+        }
+    }
+    /* network.py:464-465: normalize every connection once after the loop */
+    if (o->normalize)
+        for (int c = 0; c < net->n_conns; ++c) {
+            const snn_conn_t *C = &net->conns[c];
+            if (C->has_norm) normalize_cols(C->w, net->layers[C->src].n, net->layers[C->tgt].n, C->norm_abs, C->norm);
+        }
+    for (int l = 0; l < net->n_layers; ++l) { free(lws[l].cur); free(lws[l].cand); }
+    for (int c = 0; c < net->n_conns; ++c) { free(cws[c].U); free(cws[c].V); free(cws[c].tx); free(cws[c].row_t); free(cws[c].col_t); }
+    if (o->err_flag) *o->err_flag |= err;
+    return SNN_OK;
+}
+
+/* ---- single-operator entry points (same restatements, exposed per object) ---- */
+
+/* Connection.compute (topology.py:332-346) / MulticompartmentConnection.compute
+ * (topology.py:437-479): out[b,j] = sum_i s[b,i] w[i,j] (+ b[j]). */
+int snn_oracle_conn_compute(const snn_conn_t *C, int32_t n_src, int32_t n_tgt, int32_t B, const uint8_t *s, float *out) {
+    if (!C || !C->w || !s || !out) return SNN_ERR_BAD_ARG;
+    snn_layer_t S; memset(&S, 0, sizeof(S)); S.n = n_src; S.s = (uint8_t *)s;
+    memset(out, 0, sizeof(float) * (size_t)B * n_tgt);
+    conn_compute(C, &S, n_tgt, B, out, 0);
+    return SNN_OK;
+}
+
+/* connection.update(learning=True) from the layers' current s/x (topology.py:112-139). */
+int snn_oracle_conn_update(const snn_net_t *net, int32_t ci, int32_t B) {
+    if (!net || ci < 0 || ci >= net->n_conns) return SNN_ERR_BAD_ARG;
+    const snn_conn_t *C = &net->conns[ci];
+    const int ns = net->layers[C->src].n, nt = net->layers[C->tgt].n;
+    conn_ws_t ws; memset(&ws, 0, sizeof(ws));
+    ws.U = (float *)calloc((size_t)ns * nt, sizeof(float));
+    ws.V = (float *)calloc((size_t)ns * nt, sizeof(float));
+    ws.tx = (float *)calloc((size_t)B * nt, sizeof(float));
+    ws.row_t = (uint8_t *)calloc((size_t)ns, 1);
+    ws.col_t = (uint8_t *)calloc((size_t)nt, 1);
+    snn_run_opts_t o; memset(&o, 0, sizeof(o)); o.B = B; o.T = 1;
+    conn_update(net, C, &o, &ws, 0);
+    free(ws.U); free(ws.V); free(ws.tx); free(ws.row_t); free(ws.col_t);
+    return SNN_OK;
+}
+
+/* Connection.normalize (topology.py:383-392) / AbstractFeature.normalize
+ * (topology_features.py:250-266). */
+int snn_oracle_conn_normalize(const snn_conn_t *C, int32_t n_src, int32_t n_tgt) {
+    if (!C || !C->w) return SNN_ERR_BAD_ARG;
+    if (C->has_norm) normalize_cols(C->w, n_src, n_tgt, C->norm_abs, C->norm);
+    return SNN_OK;
+}

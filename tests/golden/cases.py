@@ -1,0 +1,207 @@
+"""Golden-vector cases: one builder per case, written against an abstract namespace ``ns`` so
+that the SAME code builds the live reference network (``gen_golden.py``, ns = reference
+modules) and ours (tests, ns = ``bindsnet_b200`` modules).
+
+Each builder returns ``(network, inputs, run_kwargs)`` with every random draw taken from the
+torch CPU generator seeded by the case's seed, and initial weights passed explicitly, so the
+two sides start from identical state.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+
+def namespace(kind: str) -> SimpleNamespace:
+    """``kind`` = "reference" (live /root/reference via the stub package of SURVEY.md §8c) or
+    "b200" (this repo)."""
+    if kind == "b200":
+        import bindsnet_b200 as pkg
+        from bindsnet_b200 import encoding, learning, models
+        from bindsnet_b200.network import Network, monitors, nodes, topology
+    else:
+        import sys
+        import types
+
+        if "bindsnet" not in sys.modules:
+            pkg = types.ModuleType("bindsnet")
+            pkg.__path__ = ["/root/reference/bindsnet"]
+            sys.modules["bindsnet"] = pkg
+        import bindsnet.utils  # noqa: F401  (import order matters: SURVEY.md §8b)
+        import bindsnet.network  # noqa: F401
+        import bindsnet.learning as learning
+        import bindsnet.models as models
+        import bindsnet.encoding as encoding
+        from bindsnet.network import Network, monitors, nodes, topology
+    return SimpleNamespace(
+        kind=kind, Network=Network, nodes=nodes, topology=topology, learning=learning, models=models,
+        monitors=monitors, encoding=encoding,
+    )
+
+
+def _poisson_inputs(ns, T, B, shape, seed, active=0.19, max_rate=128.0):
+    """SURVEY.md §8d synthetic input: rate image 128*U(0,1)*Bernoulli(0.19) Hz per pixel,
+    Poisson-encoded with the reference's own encoder (stored in the fixture, so our side never
+    regenerates it)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(B):
+        rate = max_rate * torch.rand(*shape, generator=g) * torch.bernoulli(active * torch.ones(*shape), generator=g)
+        out.append(ns.encoding.poisson(datum=rate, time=T, dt=1.0))
+    return torch.stack(out, dim=1).byte()
+
+
+def _bernoulli_inputs(T, B, shape, p, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.bernoulli(p * torch.ones(T, B, *shape), generator=g).byte()
+
+
+def _w(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return scale * torch.rand(*shape, generator=g)
+
+
+def _set_dc_weights(net, w0):
+    f = net.connections[("X", "Ae")].pipeline[0]
+    with torch.no_grad():
+        f.value.copy_(w0)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json config 1: Input(100) -> LIFNodes(100), Connection + PostPre, T=100, B=1
+def c1_lif_postpre(ns, inputs=None):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=100, traces=True)
+    Y = ns.nodes.LIFNodes(n=100, traces=True)
+    C = ns.topology.Connection(source=X, target=Y, w=_w((100, 100), 11), update_rule=ns.learning.PostPre,
+                               nu=(1e-4, 1e-2), wmin=0.0, wmax=1.0)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y"); net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(100, 1, (100,), 0.1, 12)}
+    return net, inputs, {}, 100
+
+
+# Same topology, batch 4, explicit sum reduction, normalisation, bias, weight decay
+def lif_postpre_batch(ns, inputs=None):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=80, traces=True, traces_additive=True, tc_trace=15.0, trace_scale=0.5, sum_input=True)
+    Y = ns.nodes.LIFNodes(n=48, traces=True, thresh=-55.0, rest=-65.0, reset=-62.0, refrac=3, tc_decay=50.0,
+                          lbound=-70.0, sum_input=True)
+    C = ns.topology.Connection(source=X, target=Y, w=_w((80, 48), 21, 0.8), b=_w((48,), 22, 0.3) - 0.1,
+                               update_rule=ns.learning.PostPre, nu=(2e-3, 1e-2), reduction=torch.sum,
+                               weight_decay=1e-3, wmin=0.0, wmax=1.0, norm=20.0)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y"); net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(120, 4, (80,), 0.12, 23)}
+    return net, inputs, {}, 120
+
+
+# WeightDependentPostPre, mean reduction
+def lif_wdep(ns, inputs=None):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=64, traces=True)
+    Y = ns.nodes.LIFNodes(n=32, traces=True, thresh=-58.0)
+    C = ns.topology.Connection(source=X, target=Y, w=_w((64, 32), 31, 0.9),
+                               update_rule=ns.learning.WeightDependentPostPre, nu=(1e-2, 5e-2),
+                               reduction=torch.mean, wmin=0.0, wmax=1.0)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y"); net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(100, 4, (64,), 0.15, 32)}
+    return net, inputs, {}, 100
+
+
+# clamp / unclamp / injects_v run-kwargs, two stacked LIF layers, NoOp connection with decay
+def lif_clamps(ns, inputs=None):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=40, traces=True)
+    H = ns.nodes.LIFNodes(n=24, traces=True, thresh=-60.0)
+    O = ns.nodes.LIFNodes(n=10, traces=True, thresh=-62.0, refrac=2)
+    C1 = ns.topology.Connection(source=X, target=H, w=_w((40, 24), 41, 1.5), update_rule=ns.learning.PostPre,
+                                nu=(1e-3, 1e-2), reduction=torch.sum, wmin=0.0, wmax=2.0)
+    C2 = ns.topology.Connection(source=H, target=O, w=_w((24, 10), 42, 3.0) - 0.5, weight_decay=5e-3)
+    net.add_layer(X, "X"); net.add_layer(H, "H"); net.add_layer(O, "O")
+    net.add_connection(C1, "X", "H"); net.add_connection(C2, "H", "O")
+    T = 60
+    g = torch.Generator().manual_seed(43)
+    kw = {
+        "clamp": {"O": torch.bernoulli(0.05 * torch.ones(T, 10), generator=g).bool()},
+        "unclamp": {"H": (torch.arange(24) % 5 == 0)},
+        "injects_v": {"H": 0.5 * torch.rand(T, 24, generator=g), "O": 0.2 * torch.rand(10, generator=g)},
+    }
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(T, 3, (40,), 0.2, 44)}
+    return net, inputs, kw, T
+
+
+def _dc2015(ns, n, B, T, inp_seed, w_seed, one_spike, inputs, inh=120.0, poisson=False):
+    net = ns.models.DiehlAndCook2015(n_inpt=784, n_neurons=n, batch_size=B, inpt_shape=(1, 28, 28), dt=1.0,
+                                     nu=(1e-4, 1e-2), norm=78.4, theta_plus=0.05, exc=22.5, inh=inh)
+    _set_dc_weights(net, _w((784, n), w_seed, 0.3))
+    net.layers["Ae"].one_spike = one_spike
+    if inputs is None:
+        if poisson:
+            inputs = {"X": _poisson_inputs(ns, T, B, (1, 28, 28), inp_seed)}
+        else:
+            inputs = {"X": _bernoulli_inputs(T, B, (1, 28, 28), 0.05, inp_seed)}
+    return net, inputs, {}, T
+
+
+# SURVEY.md §0.10 configuration: deterministic dynamics (one_spike off)
+def dc2015_multi(ns, inputs=None):
+    return _dc2015(ns, 64, 8, 120, 51, 52, False, inputs)
+
+
+# default one_spike=True, tie-break via the shared hash
+def dc2015_onespike(ns, inputs=None):
+    return _dc2015(ns, 100, 16, 150, 61, 62, True, inputs)
+
+
+# BASELINE.json config 2: n=400, B=32, T=250, Poisson 28x28
+def dc2015_c2(ns, inputs=None):
+    return _dc2015(ns, 400, 32, 250, 71, 72, True, inputs, poisson=True)
+
+
+# metric configuration n=1600, B=128, shortened to T=40 (the live reference needs ~2 s/step)
+def dc2015_metric_t40(ns, inputs=None):
+    return _dc2015(ns, 1600, 128, 40, 81, 82, True, inputs, poisson=True)
+
+
+# classic Connection + learning.PostPre path with a recurrent inhibitory Connection
+def dc2015v2(ns, inputs=None):
+    net = ns.models.DiehlAndCook2015v2(n_inpt=196, n_neurons=64, inh=60.0, nu=(1e-4, 1e-2), reduction=torch.sum,
+                                       norm=30.0, inpt_shape=(1, 14, 14))
+    with torch.no_grad():
+        net.connections[("X", "Y")].w.copy_(_w((196, 64), 91, 0.3))
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(120, 4, (1, 14, 14), 0.08, 92)}
+    return net, inputs, {}, 120
+
+
+# learning switched off (network.train(False)): no STDP, no theta adaptation
+def dc2015_eval(ns, inputs=None):
+    net, inputs, kw, T = _dc2015(ns, 49, 5, 80, 101, 102, True, inputs)
+    net.train(False)
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(103)
+        net.layers["Ae"].theta.copy_(2.0 * torch.rand(49, generator=g))
+    return net, inputs, kw, T
+
+
+CASES = {
+    "c1_lif_postpre": c1_lif_postpre,
+    "lif_postpre_batch": lif_postpre_batch,
+    "lif_wdep": lif_wdep,
+    "lif_clamps": lif_clamps,
+    "dc2015_multi": dc2015_multi,
+    "dc2015_onespike": dc2015_onespike,
+    "dc2015v2": dc2015v2,
+    "dc2015_eval": dc2015_eval,
+    "dc2015_c2": dc2015_c2,
+    "dc2015_metric_t40": dc2015_metric_t40,
+}
+
+#: cases whose fixture stores subsampled weights only (full tensors would be several MB)
+LARGE = {"dc2015_metric_t40"}
+#: one_spike tie-break seed used by every case
+ONE_SPIKE_SEED = 20260922
