@@ -1,0 +1,140 @@
+// snn_common.cuh — device-side helpers shared by the window kernels.
+//
+// Arithmetic contract: every floating-point operation below is a single IEEE fp32 rounding, in
+// the order the reference's ATen ops apply them (the library is compiled with --fmad=false, so
+// the compiler never contracts a*b+c).  Where the reference leaves a summation order to ATen
+// the kernels sum in ascending index order, like oracle/snn_oracle.c, so kernel and oracle
+// agree bit for bit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/snn_b200.h"
+
+#define SNN_TILE 32          // neurons (columns) per work item: one warp lane per column
+#define SNN_GEN_THREADS 256  // generic kernel: 8 warps per CTA
+#define SNN_GEN_WARPS (SNN_GEN_THREADS / 32)
+
+struct DevLayer {
+    snn_layer_t L;
+    uint32_t *bits;             // [2][B][nw]  bit-packed spikes, slot t&1 holds s(t)
+    uint32_t *candbits;         // [B][nw]     DC one_spike: threshold crossers of this step
+    unsigned long long *keys;   // [2][B]      DC one_spike: arg-max tie-break keys
+    float *xpub;                // [2][B][n]   trace published for STDP readers (slot t&1), or NULL
+    int32_t nw;                 // ceil(n / 32)
+    int32_t item0;              // first work-item index of this layer
+};
+
+struct DevNet {
+    int32_t n_layers, n_conns, learning, T, B, normalize, total_items, any_one_spike;
+    uint32_t seed, step_offset;
+    int32_t *err;               // device error flags (may be NULL)
+    unsigned int *bar;          // [0] arrival count, [32] generation, [64] abort
+    DevLayer layers[SNN_MAX_LAYERS];
+    snn_conn_t conns[SNN_MAX_CONNS];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Sense-reversal grid barrier on (count, generation) words in global memory.  Requires all
+// CTAs of the grid to be co-resident (cooperative launch).  A time-out (~2 s) raises
+// SNN_ERR_BARRIER and makes every CTA leave the time loop instead of hanging the device.
+__device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nblocks, int32_t *err) {
+    __shared__ int s_abort;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int *count = bar, *gen = bar + 32, *abort_w = bar + 64;
+        const unsigned int g = ld_acquire_u32(gen);
+        __threadfence();
+        const unsigned int prev = atomicAdd(count, 1u);
+        int ab = 0;
+        if (prev == nblocks - 1) {
+            *count = 0u;
+            __threadfence();
+            st_release_u32(gen, g + 1u);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_u32(gen) == g) {
+                if (clock64() - t0 > 4000000000LL) {
+                    if (err) atomicOr(err, SNN_ERR_BARRIER);
+                    atomicExch(abort_w, 1u);
+                    break;
+                }
+            }
+        }
+        __threadfence();
+        ab = (int)ld_acquire_u32(abort_w);
+        s_abort = ab;
+    }
+    __syncthreads();
+    return s_abort == 0;
+}
+
+__device__ __forceinline__ float clampf(float w, float lo, float hi) {
+    w = w < lo ? lo : w;
+    w = w > hi ? hi : w;
+    return w;
+}
+
+// Nodes.forward trace update (nodes.py:96-103): decay, then set / add on spike.
+__device__ __forceinline__ float trace_step(float x, bool s, float decay, float scale, int additive) {
+    x = x * decay;
+    if (additive) x = x + scale * (s ? 1.0f : 0.0f);
+    else if (s) x = scale;
+    return x;
+}
+
+// LIFNodes.forward (nodes.py:500-529).  `xin` is masked in place like the reference does.
+__device__ __forceinline__ bool lif_step(const snn_layer_t &L, float &v, float &rc, float &xin) {
+    v = L.decay * (v - L.rest) + L.rest;
+    if (rc > 0.0f) xin = 0.0f;
+    rc = rc - L.dt;
+    v = v + xin;
+    const bool s = v >= L.thresh;
+    if (s) { rc = L.refrac; v = L.reset; }
+    if (L.has_lbound && v < L.lbound) v = L.lbound;
+    return s;
+}
+
+// DiehlAndCookNodes.forward up to the threshold test (nodes.py:1077-1092); `theta` is the
+// already decayed adaptive threshold of the neuron.  Returns the candidate flag.
+__device__ __forceinline__ bool dc_step(const snn_layer_t &L, float &v, float &rc, float xin, float theta) {
+    v = L.decay * (v - L.rest) + L.rest;
+    const float gate = rc <= 0.0f ? 1.0f : 0.0f;
+    v = v + gate * xin;
+    rc = rc - L.dt;
+    const bool s = v >= (L.thresh + theta);
+    if (s) { rc = L.refrac; v = L.reset; }
+    return s;
+}
+
+// One STDP-family update of a single synapse, in the reference's order: pre term, post term,
+// weight decay, clamp (learning.py:87-104,390-420,626-653; MCC_learning.py:86-110,224-302).
+// U / V are the batch-reduced outer products of this step for this synapse (0 if untouched).
+__device__ __forceinline__ float apply_rule(const snn_conn_t &C, float w, float U, bool pre_t, float V, bool post_t) {
+    if (C.rule == SNN_RULE_WDEP_POSTPRE) {
+        float upd = 0.0f;
+        if (C.nu0 != 0.0f) upd = upd - (C.nu0 * (pre_t ? U : 0.0f)) * (w - C.wmin);
+        if (C.nu1 != 0.0f) upd = upd + (C.nu1 * (post_t ? V : 0.0f)) * (C.wmax - w);
+        w = w + upd;
+    } else if (C.rule == SNN_RULE_MCC_POSTPRE) {
+        if (pre_t) w = w - U * C.dt_scale;
+        if (post_t) w = w + V * C.dt_scale;
+    } else if (C.rule == SNN_RULE_POSTPRE) {
+        if (pre_t) w = w - U;
+        if (post_t) w = w + V;
+    }
+    if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+    if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+    return w;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

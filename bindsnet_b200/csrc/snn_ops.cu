@@ -1,0 +1,141 @@
+// snn_ops.cu — single-operator entry points of the C ABI (the reference's per-object methods:
+// Connection.compute, connection.update, normalize) and the multi-GPU window-combine kernels.
+#include "snn_phases.cuh"
+
+namespace {
+
+// out[b,j] = sum_{i: s[b,i]} w[i,j] (+ bias).  Connection.compute (topology.py:332-346).
+__global__ void __launch_bounds__(SNN_GEN_THREADS) conn_compute_kernel(snn_conn_t C, int ns, int nt, int B,
+                                                                        const uint8_t *__restrict__ s, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x, j = tile * SNN_TILE + lane;
+    const bool valid = j < nt;
+    for (int b = blockIdx.y * SNN_GEN_WARPS + warp; b < B; b += gridDim.y * SNN_GEN_WARPS) {
+        float p = 0.0f;
+        for (int i0 = 0; i0 < ns; i0 += 32) {
+            const bool sp = (i0 + lane < ns) && s[(size_t)b * ns + i0 + lane] != 0;
+            uint32_t word = __ballot_sync(0xffffffffu, sp);
+            while (word) {
+                const int i = i0 + __ffs(word) - 1;
+                word &= word - 1;
+                if (valid) p = p + C.w[(size_t)i * nt + j];
+            }
+        }
+        if (valid) out[(size_t)b * nt + j] = C.b ? p + C.b[j] : p;
+    }
+}
+
+// bit-pack the CURRENT spikes of the two layers of a connection into slot 0
+__global__ void pack_bits_kernel(const uint8_t *__restrict__ s, uint32_t *__restrict__ bits, int B, int n, int nw) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= B * nw) return;
+    const int b = gw / nw, w = gw % nw, j = w * 32 + lane;
+    const bool sp = j < n && s[(size_t)b * n + j] != 0;
+    const uint32_t word = __ballot_sync(0xffffffffu, sp);
+    if (lane == 0) bits[(size_t)b * nw + w] = word;
+}
+
+__global__ void __launch_bounds__(SNN_GEN_THREADS) conn_update_kernel(const __grid_constant__ DevNet N, int ci) {
+    extern __shared__ float smem[];
+    float *s_acc = smem;
+    uint32_t *s_colmask = (uint32_t *)(s_acc + SNN_GEN_WARPS * 32 * 32);
+    __shared__ int32_t s_flag;
+    phase3(N, ci, blockIdx.x, 0, s_acc, s_colmask, &s_flag);
+}
+
+__global__ void __launch_bounds__(SNN_GEN_THREADS) conn_normalize_kernel(snn_conn_t C, int ns, int nt) {
+    __shared__ float s_part[(SNN_NORM_CHUNKS + 1) * 32];
+    normalize_tile(C, ns, nt, blockIdx.x, s_part);
+}
+
+__global__ void delta_prepare_kernel(const float *__restrict__ w, const float *__restrict__ w0, float *__restrict__ dw, size_t n) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dw[k] = w[k] - w0[k];
+}
+
+// w = clamp(w0 + sum_r dw_r), then normalize() — all on one column tile.
+__global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t C, const float *__restrict__ w0,
+                                                                       const float *__restrict__ dws, int ns, int nt) {
+    __shared__ float s_part[(SNN_NORM_CHUNKS + 1) * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * SNN_TILE + lane;
+    if (j < nt)
+        for (int i = warp; i < ns; i += SNN_GEN_WARPS) {
+            const size_t k = (size_t)i * nt + j;
+            float x = w0[k] + dws[k];
+            if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
+            C.w[k] = x;
+        }
+    if (C.has_norm) normalize_tile(C, ns, nt, blockIdx.x, s_part);
+}
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? SNN_OK : SNN_ERR_CUDA; }
+
+}  // namespace
+
+extern "C" {
+
+int snn_b200_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, int32_t B, const uint8_t *s, float *out,
+                          void *stream) {
+    if (!conn || !conn->w || !s || !out || n_src <= 0 || n_tgt <= 0 || B <= 0) return SNN_ERR_BAD_ARG;
+    dim3 grid((n_tgt + SNN_TILE - 1) / SNN_TILE, (B + SNN_GEN_WARPS - 1) / SNN_GEN_WARPS);
+    if (grid.y > 64) grid.y = 64;
+    conn_compute_kernel<<<grid, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt, B, s, out);
+    return cuda_rc(cudaGetLastError());
+}
+
+int snn_b200_conn_update(const snn_net_t *net, int32_t ci, int32_t B, void *workspace, size_t workspace_bytes, void *stream_) {
+    if (!net || ci < 0 || ci >= net->n_conns || B <= 0 || !workspace) return SNN_ERR_BAD_ARG;
+    const snn_conn_t &C = net->conns[ci];
+    if (C.rule == SNN_RULE_NONE) return SNN_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DevNet N;
+    memset(&N, 0, sizeof(N));
+    N.n_layers = net->n_layers; N.n_conns = net->n_conns; N.learning = 1; N.T = 1; N.B = B;
+    for (int c = 0; c < net->n_conns; ++c) N.conns[c] = net->conns[c];
+    size_t off = 0;
+    const int ends[2] = {C.src, C.tgt};
+    for (int e = 0; e < 2; ++e) {
+        const int l = ends[e];
+        DevLayer &D = N.layers[l];
+        if (D.bits) continue;  // recurrent connection: same layer twice
+        D.L = net->layers[l];
+        D.nw = (D.L.n + 31) / 32;
+        D.bits = (uint32_t *)((char *)workspace + off);
+        off += (sizeof(uint32_t) * (size_t)B * D.nw + 255) / 256 * 256;
+        D.xpub = D.L.x;  // slot 0 = the layer's current trace
+        if (off > workspace_bytes) return SNN_ERR_WORKSPACE;
+        const int warps = B * D.nw;
+        pack_bits_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(D.L.s, D.bits, B, D.L.n, D.nw);
+    }
+    const size_t smem = sizeof(float) * SNN_GEN_WARPS * 32 * 32 + sizeof(uint32_t) * 32 * (size_t)((B + 31) / 32);
+    cudaFuncSetAttribute(conn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    conn_update_kernel<<<N.layers[C.tgt].nw, SNN_GEN_THREADS, smem, stream>>>(N, ci);
+    return cuda_rc(cudaGetLastError());
+}
+
+int snn_b200_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, void *stream) {
+    if (!conn || !conn->w || n_src <= 0 || n_tgt <= 0) return SNN_ERR_BAD_ARG;
+    if (!conn->has_norm) return SNN_OK;
+    conn_normalize_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt);
+    return cuda_rc(cudaGetLastError());
+}
+
+int snn_b200_delta_prepare(const float *w, const float *w0, float *dw, size_t count, void *stream) {
+    if (!w || !w0 || !dw) return SNN_ERR_BAD_ARG;
+    const int blocks = (int)((count + 1023) / 1024 < 1184 ? (count + 1023) / 1024 : 1184);
+    delta_prepare_kernel<<<blocks > 0 ? blocks : 1, 256, 0, (cudaStream_t)stream>>>(w, w0, dw, count);
+    return cuda_rc(cudaGetLastError());
+}
+
+int snn_b200_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t n_src, int32_t n_tgt, int32_t has_clamp,
+                         float wmin, float wmax, int32_t has_norm, int32_t norm_abs, float norm, void *stream) {
+    if (!w || !w0 || !dw_sum || n_src <= 0 || n_tgt <= 0) return SNN_ERR_BAD_ARG;
+    snn_conn_t C;
+    memset(&C, 0, sizeof(C));
+    C.w = w; C.has_clamp = has_clamp; C.wmin = wmin; C.wmax = wmax; C.has_norm = has_norm; C.norm_abs = norm_abs; C.norm = norm;
+    delta_apply_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(C, w0, dw_sum, n_src, n_tgt);
+    return cuda_rc(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -156,23 +156,27 @@ typedef struct snn_run_opts {
 /*
  * one_spike tie-break.  The reference draws the single winner per sample with
  * torch.multinomial over the 0/1 candidate mask (nodes.py:1097-1105), i.e. uniformly among
- * the threshold crossers.  We draw it as the arg-max of an i.i.d. 31-bit hash over the
- * candidates, which is the same distribution and needs one atomicMax per sample across the
- * whole grid.  key = ((h | 0x80000000) << 32) | j with
- *   h = fmix32(fmix32(fmix32(seed ^ 0x9E3779B9*(t+1)) + 0x85EBCA6B*(layer+1) ^ b) + j)... —
- * the exact function is snn_one_spike_hash() below; the oracle and the golden generator
- * (which monkey-patches torch.multinomial with it) use the same definition.
+ * the threshold crossers.  We draw it as the arg-max over the candidates of an i.i.d. 31-bit
+ * hash of (seed, step, layer, sample, neuron) — the same distribution, but computable with one
+ * atomicMax per sample across the whole grid.  The key packs the hash above the neuron index so
+ * that the arg-max also returns the winner.  The oracle and the golden generator (which
+ * monkey-patches torch.multinomial with it) use this very definition.
  */
-static inline uint32_t snn_fmix32(uint32_t h) {
+#ifdef __CUDACC__
+#define SNN_HD __host__ __device__
+#else
+#define SNN_HD
+#endif
+static inline SNN_HD uint32_t snn_fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h;
 }
-static inline uint32_t snn_one_spike_hash(uint32_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t j) {
+static inline SNN_HD uint32_t snn_one_spike_hash(uint32_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t j) {
     uint32_t h = snn_fmix32(seed ^ (0x9E3779B9u * (t + 1u)));
     h = snn_fmix32(h + 0x85EBCA6Bu * (layer + 1u) + b);
     h = snn_fmix32(h ^ (0xC2B2AE35u * (j + 1u)));
     return h;
 }
-static inline uint64_t snn_one_spike_key(uint32_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t j) {
+static inline SNN_HD uint64_t snn_one_spike_key(uint32_t seed, uint32_t t, uint32_t layer, uint32_t b, uint32_t j) {
     return ((uint64_t)(snn_one_spike_hash(seed, t, layer, b, j) | 0x80000000u) << 32) | (uint64_t)j;
 }
 

@@ -23,3 +23,11 @@ def test_oracle_dense_equals_sparse(name):
     _, s_dense, c_dense = helpers.run_case_oracle(name, dense=1)
     helpers.assert_bit_identical(s_sparse, s_dense, name)
     helpers.assert_bit_identical(c_sparse, c_dense, name)
+
+
+@pytest.mark.parametrize("name", ["dc2015_c2", "dc2015_metric_t40"])
+def test_oracle_matches_reference_baseline_configs(name):
+    """BASELINE.json config 2 (n=400, B=32, T=250) and the metric configuration (n=1600, B=128;
+    the live reference needs ~2 s per step there, so the fixture stops at T=40)."""
+    fx, state, counts = helpers.run_case_oracle(name)
+    helpers.assert_close_to_golden(fx, state, counts)
