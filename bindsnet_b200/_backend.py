@@ -126,8 +126,16 @@ def _check(rc: int, what: str) -> None:
         raise BackendError(f"{what}: {_abi.describe_error(rc)}")
 
 
+#: when set to a list, every window appends a (start, end) pair of CUDA events recorded on the
+#: launching stream immediately around the kernel launch (bench.py's roofline measurement)
+kernel_events: Optional[list] = None
+#: number of window kernels launched through this module since import
+launches_total = 0
+
+
 def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts, device: torch.device) -> None:
     """One ``Network.run`` window on ``device`` (asynchronous)."""
+    global launches_total
     L = lib()
     poll_errors(device)
     flag = err_flag(device)
@@ -135,8 +143,15 @@ def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts, device: torch.device) ->
     with torch.cuda.device(device):
         nbytes = int(L.snn_b200_workspace_bytes(C.byref(net), C.byref(opts)))
         ws = workspace(device, nbytes)
+        if kernel_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         rc = L.snn_b200_run_window(C.byref(net), C.byref(opts), ws.data_ptr(), ws.numel(), _stream_ptr(device))
+        if kernel_events is not None:
+            ev[1].record()
+            kernel_events.append(ev)
         _check(rc, "snn_b200_run_window")
+        launches_total += int(L.snn_b200_last_launch_count())
         _err_host[_index(device)].copy_(flag, non_blocking=True)
 
 

@@ -1,0 +1,82 @@
+"""Multi-GPU windows: batch shards with ONE exchange per window.
+
+The reference has no multi-device path at all.  The north_star defines one: every rank holds
+a full replica of the weights and adaptive thresholds and a shard of the input batch, runs the
+ordinary window locally (per-step STDP / clamp / theta on its shard), and at the window
+boundary the accumulated changes are summed over ranks —
+
+    dW_r = W_r - W0,  dtheta_r = theta_r - theta0          (snn_b200_delta_prepare)
+    all_reduce(sum) of one fused fp32 buffer over NCCL      (no per-timestep collective)
+    W = clamp(W0 + sum_r dW_r, wmin, wmax); theta = theta0 + sum_r dtheta_r
+    normalize()                                             (snn_b200_delta_apply)
+
+This is "replicas + one exchange", NOT a single-process run at the global batch size: that
+would need the batch-summed dW and dtheta exchanged every timestep.  tests/test_distributed.py
+checks it against the combination of independent oracle replicas.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _abi, _backend
+
+
+class ShardedWindowRunner:
+    """Wraps a ``Network`` replica; ``run`` has ``Network.run``'s signature."""
+
+    def __init__(self, network, process_group: Optional["dist.ProcessGroup"] = None):
+        self.network = network
+        self.group = process_group
+        self._flat: Optional[torch.Tensor] = None
+        self._snap: Optional[torch.Tensor] = None
+
+    def _learned(self) -> List[Tuple[object, "_abi.SnnConn"]]:
+        out = []
+        for conn in self.network.connections.values():
+            d = _abi.SnnConn()
+            conn._fill_desc(d, float(self.network.dt))
+            if d.rule >= _abi.SNN_RULE_POSTPRE or d.has_norm:
+                out.append((conn, d))
+        return out
+
+    def _thetas(self) -> List[torch.Tensor]:
+        return [l.theta for l in self.network.layers.values() if getattr(l, "kind", None) == _abi.SNN_NODE_DC]
+
+    def run(self, inputs: Dict[str, torch.Tensor], time: int, **kwargs) -> None:
+        net = self.network
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        learned = self._learned() if net.learning else []
+        thetas = self._thetas() if net.learning else []
+        if world == 1 or not net.learning:
+            net.run(inputs, time, **kwargs)
+            return
+        total = sum(c.w.numel() for c, _ in learned) + sum(t.numel() for t in thetas)
+        dev = net._device()
+        if self._flat is None or self._flat.numel() != total or self._flat.device != dev:
+            self._flat = torch.empty(total, dtype=torch.float32, device=dev)
+            self._snap = torch.empty(total, dtype=torch.float32, device=dev)
+        # snapshot W0 / theta0
+        off = 0
+        views = []
+        for t in [c.w for c, _ in learned] + thetas:
+            v = self._snap[off:off + t.numel()].view_as(t)
+            v.copy_(t.detach())
+            views.append((t, v, off))
+            off += t.numel()
+
+        net.run(inputs, time, b200_normalize=False, **kwargs)
+
+        for t, v0, o in views:
+            _backend.delta_prepare(t.detach(), v0, self._flat[o:o + t.numel()].view_as(t))
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+        k = 0
+        for conn, d in learned:
+            t, v0, o = views[k]; k += 1
+            _backend.delta_apply(conn.w.detach(), v0, self._flat[o:o + t.numel()].view_as(t), d.has_clamp, d.wmin,
+                                 d.wmax, d.has_norm, d.norm_abs, d.norm)
+        for th in thetas:
+            t, v0, o = views[k]; k += 1
+            th.copy_(v0 + self._flat[o:o + t.numel()].view_as(t))

@@ -81,8 +81,10 @@ class Network(torch.nn.Module):
 
         ``inputs[l]`` has shape ``[time, batch, *layer.shape]`` (or the shorter forms the
         reference accepts, network.py:329-340).  Keyword arguments: ``clamp``, ``unclamp``,
-        ``injects_v`` as in the reference (network.py:268-281); ``one_spike_seed`` (extension)
-        fixes the tie-break stream of ``DiehlAndCookNodes(one_spike=True)``.
+        ``injects_v`` as in the reference (network.py:268-281).  Extensions: ``one_spike_seed``
+        fixes the tie-break stream of ``DiehlAndCookNodes(one_spike=True)``;
+        ``b200_normalize=False`` skips the end-of-run normalize (used by the multi-GPU combine,
+        ``bindsnet_b200.distributed``).
         """
         assert type(inputs) == dict, (
             "'inputs' must be a dict of names of layers (str) and relevant input tensors. "
@@ -112,7 +114,7 @@ class Network(torch.nn.Module):
 
         timesteps = int(time / self.dt)  # network.py:356
         self._run_window(
-            inputs, timesteps, normalize=True,
+            inputs, timesteps, normalize=bool(kwargs.get("b200_normalize", True)),
             clamp=kwargs.get("clamp", {}), unclamp=kwargs.get("unclamp", {}),
             injects_v=kwargs.get("injects_v", {}), seed=kwargs.get("one_spike_seed", None),
         )
