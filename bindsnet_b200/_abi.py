@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SNN_ABI_VERSION = 3
+SNN_ABI_VERSION = 4
 SNN_MAX_LAYERS = 8
 SNN_MAX_CONNS = 12
 
@@ -17,6 +17,7 @@ SNN_CONN_DENSE, SNN_CONN_MCC = 0, 1
 SNN_RULE_NONE, SNN_RULE_NOOP, SNN_RULE_POSTPRE, SNN_RULE_WDEP_POSTPRE, SNN_RULE_MCC_POSTPRE = 0, 1, 2, 3, 4
 SNN_REDUCE_SUM, SNN_REDUCE_MEAN = 0, 1
 SNN_EXT_NONE, SNN_EXT_U8, SNN_EXT_F32 = 0, 1, 2
+SNN_W_DENSE, SNN_W_DIAG, SNN_W_OFFDIAG = 0, 1, 2
 
 SNN_OK = 0
 SNN_ERR_BAD_ARG = 1
@@ -90,6 +91,7 @@ class SnnConn(C.Structure):
         ("has_norm", C.c_int32),
         ("norm_abs", C.c_int32),
         ("has_clamp", C.c_int32),
+        ("structure", C.c_int32),
         ("nu0", C.c_float),
         ("nu1", C.c_float),
         ("wmin", C.c_float),
@@ -97,6 +99,7 @@ class SnnConn(C.Structure):
         ("weight_decay", C.c_float),
         ("dt_scale", C.c_float),
         ("norm", C.c_float),
+        ("structure_val", C.c_float),
         ("w", C.c_void_p),
         ("b", C.c_void_p),
     ]

@@ -50,6 +50,31 @@ def fill_layer(d: "_abi.SnnLayer", layer, name: str, B: int) -> None:
         d.summed = _ptr(_state(layer.summed, "summed", name))
 
 
+def weight_structure(conn, w: torch.Tensor):
+    """Plan-time structure detection for STATIC square weight matrices (DiehlAndCook2015's
+    ``exc * I`` and ``-inh * (1 - I)``, models.py:204,217-220): lets the fused kernel replace an
+    n x n matrix by one constant.  Verified on the actual tensor (one small reduction + host
+    read) and cached until the tensor is modified in place (``Tensor._version``) or replaced."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), str(w.device))
+    cached = getattr(conn, "_b200_structure", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    result = (_abi.SNN_W_DENSE, 0.0)
+    if w.dim() == 2 and w.shape[0] == w.shape[1] and w.shape[0] > 1:
+        with torch.no_grad():
+            diag = torch.diagonal(w)
+            d0, o0 = diag[0], w[0, 1]
+            eye = torch.eye(w.shape[0], dtype=torch.bool, device=w.device)
+            is_diag = bool(((w == 0) | eye).all() & (diag == d0).all())
+            is_off = bool(((w == o0) | eye).all() & (diag == 0).all())
+        if is_diag:
+            result = (_abi.SNN_W_DIAG, float(d0))
+        elif is_off:
+            result = (_abi.SNN_W_OFFDIAG, float(o0))
+    conn._b200_structure = (key, result)
+    return result
+
+
 def fill_conn(d: "_abi.SnnConn", conn, src_idx: int, tgt_idx: int, dt: float, B: int) -> None:
     d.src, d.tgt = src_idx, tgt_idx
     conn._fill_desc(d, dt)
@@ -59,6 +84,9 @@ def fill_conn(d: "_abi.SnnConn", conn, src_idx: int, tgt_idx: int, dt: float, B:
     if tuple(w.shape) != (conn.source.n, conn.target.n):
         raise ValueError(f"weight shape {tuple(w.shape)} != ({conn.source.n}, {conn.target.n})")
     d.w = _ptr(w)
+    static = d.rule == _abi.SNN_RULE_NONE or (d.rule == _abi.SNN_RULE_NOOP and d.weight_decay in (0.0, 1.0))
+    if static and not d.has_norm:
+        d.structure, d.structure_val = weight_structure(conn, w)
     b = getattr(conn, "b", None)
     d.b = _ptr(b) if b is not None else None
     rule = getattr(conn, "update_rule", None)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 3
+#define SNN_ABI_VERSION 4
 #define SNN_MAX_LAYERS 8
 #define SNN_MAX_CONNS 12
 
@@ -54,6 +54,12 @@ extern "C" {
 #define SNN_RULE_POSTPRE 2     /* learning.PostPre._connection_update         learning.py:390-420     */
 #define SNN_RULE_WDEP_POSTPRE 3/* learning.WeightDependentPostPre             learning.py:626-653     */
 #define SNN_RULE_MCC_POSTPRE 4 /* MCC_learning.PostPre._connection_update     MCC_learning.py:224-302 */
+
+/* ---- weight-matrix structure hints (DiehlAndCook2015's static exc/inh matrices,
+ *      models.py:204,217-220) ---- */
+#define SNN_W_DENSE 0   /* arbitrary dense matrix                                              */
+#define SNN_W_DIAG 1    /* square, w[i][i] = structure_val, 0 elsewhere                        */
+#define SNN_W_OFFDIAG 2 /* square, w[i][i] = 0, structure_val elsewhere                        */
 
 /* ---- batch reduction of the STDP update (learning.py:76-80) ---- */
 #define SNN_REDUCE_SUM 0  /* torch.sum; also torch.squeeze when B == 1 */
@@ -124,11 +130,14 @@ typedef struct snn_conn {
                           (topology_features.py:264-266)                                    */
     int32_t has_clamp; /* rule clamps w to [wmin,wmax] after each update (learning.py:97-104,
                           MCC_learning.py:101-110)                                          */
+    int32_t structure; /* SNN_W_*: caller-verified structure of w (plan-time hint that lets the
+                          fused kernel skip a static n x n matrix; SNN_W_DENSE is always valid) */
     float nu0, nu1;    /* pre-/post-synaptic learning rates                                 */
     float wmin, wmax;
     float weight_decay;/* multiplicative per-step factor (learning.py:85,93-94); 1.0 = off  */
     float dt_scale;    /* MCC: connection.dt factor on both STDP terms (MCC_learning.py:262,298) */
     float norm;
+    float structure_val; /* the constant of SNN_W_DIAG / SNN_W_OFFDIAG                      */
     float *w;          /* [n_src, n_tgt] row-major, updated in place                        */
     const float *b;    /* [n_tgt] bias or NULL (topology.py:345)                            */
 } snn_conn_t;
