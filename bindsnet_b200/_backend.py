@@ -131,11 +131,13 @@ def _check(rc: int, what: str) -> None:
 kernel_events: Optional[list] = None
 #: number of window kernels launched through this module since import
 launches_total = 0
+#: kernel tier of the last window (1 generic, 2 fused DiehlAndCook2015)
+last_tier = 0
 
 
 def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts, device: torch.device) -> None:
     """One ``Network.run`` window on ``device`` (asynchronous)."""
-    global launches_total
+    global launches_total, last_tier
     L = lib()
     poll_errors(device)
     flag = err_flag(device)
@@ -151,6 +153,7 @@ def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts, device: torch.device) ->
             ev[1].record()
             kernel_events.append(ev)
         _check(rc, "snn_b200_run_window")
+        last_tier = int(L.snn_b200_select_tier(C.byref(net), C.byref(opts)))
         launches_total += int(L.snn_b200_last_launch_count())
         _err_host[_index(device)].copy_(flag, non_blocking=True)
 

@@ -41,19 +41,13 @@ DC = [c for c in ALL if c.startswith("dc2015") and c != "dc2015v2"]
 def test_fused_kernel_selected_and_bit_exact_vs_oracle(name):
     """tier=0 (auto) must pick the fused DiehlAndCook2015 kernel for these graphs, and the
     fused kernel must agree with the oracle bit for bit."""
-    from bindsnet_b200 import _abi, _backend
-    from bindsnet_b200.network import _plan
+    from bindsnet_b200 import _backend
 
-    fx = helpers.Fixture(name)
-    net, inputs, kw, T = fx.build("cuda")
-    B = next(iter(inputs.values())).shape[1]
-    plan, _keep = _plan.build_net(net, B, {k: net._stage_input(k, v, T, net._device()) for k, v in inputs.items()}, {}, {}, {}, {})
-    opts = _abi.SnnRunOpts(); opts.T, opts.B, opts.normalize = T, B, 1
-    assert _backend.select_tier(plan, opts) == 2
     _, s_gpu, c_gpu = run_case_gpu(name, tier=0)
     _, s_cpu, c_cpu = helpers.run_case_oracle(name)
     helpers.assert_bit_identical(s_gpu, s_cpu, f"{name} state (fused)")
     helpers.assert_bit_identical(c_gpu, c_cpu, f"{name} spike counts (fused)")
+    assert _backend.last_tier == 2, "auto tier selection did not pick the fused kernel"
 
 
 @pytest.mark.parametrize("name", DC)
