@@ -14,9 +14,10 @@
 // Per step the grid exchanges only: per sample the arg-max one_spike key (atomicMax) and the
 // number of Ai spikes (atomicAdd) — the Ai->Ae matrix is constant off-diagonal, so lateral
 // inhibition needs just that count — plus the input-trace rows of the few winners.
-// The step's input spikes arrive as two bit matrices (per sample over pixels for the gather,
-// per pixel over samples for the STDP pre term), produced once per window by a pre-pass and
-// staged a step ahead into shared memory with cp.async.bulk (TMA bulk copy) + mbarrier.
+// The step's input spikes are prepared once per window by a pre-pass in two forms — per sample
+// an ascending list of spiking pixels (for the gather) and per pixel a bit mask over samples
+// (for the STDP pre term) — and staged a step ahead into shared memory with cp.async.bulk
+// (TMA bulk copy) + mbarrier.
 //
 // Loop iteration t = [finalise step t-1: exchange results, winner, Ae trace, STDP on the tile]
 //                    [step t: gather, Ae/Ai update, candidates -> atomics] [grid barrier].
@@ -30,22 +31,26 @@
 
 namespace {
 
-constexpr int XR = 8;  // input-trace rows staged per CTA per step (samples with a candidate)
+constexpr int XR = 8;        // input-trace rows staged per CTA per step (samples with a candidate)
+constexpr int EV_CAP = 32;   // staged events per sample and step; longer lists take the slow path
 
 struct FusedParams {
     snn_layer_t X, E, I;      // Input, DiehlAndCookNodes (Ae), LIFNodes (Ai)
     snn_conn_t C;             // X -> Ae
     float exc, inh_neg;       // diag value of Ae->Ai, off-diag value of Ai->Ae
     int32_t T, B, P, n, learning, normalize;
-    int32_t SW, BW;           // words per sample row of inS / per pixel row of inT (multiples of 4)
+    int32_t SW;               // words per sample row of inS
+    int32_t SB;               // bytes of one event-list block
     int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
     uint32_t seed, step_offset;
     uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
     uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
+    unsigned char *evS;       // [T+1][SB]     same spikes as lists: u16 count[B] (16 B padded),
+                              //               then u16 idx[B][EV_CAP] ascending, padded with P
     unsigned long long *win;  // [3][B] arg-max keys, slot t % 3
     unsigned int *sisum;      // [3][B] Ai spike counts, slot t % 3 (slot 2 = step -1)
     float *xpub;              // [2][B][P] published input traces, slot t & 1
-    unsigned int *bar;
+    unsigned int *bar;        // [0] arrivals (monotonic), [32] generation
     int32_t *err;
 };
 
@@ -71,6 +76,35 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Grid barrier, one L2 round trip to arrive and a polling load to leave: a monotonic arrival
+// counter (acq_rel atomic; the last arriver of generation g publishes g) and a generation word.
+// All cross-CTA data is read with ld.global.cg, so no L1 invalidation is needed.
+__device__ __forceinline__ bool grid_barrier_fast(unsigned int *bar, unsigned int nblocks, unsigned int &gen, int32_t *err) {
+    __shared__ int s_ok;
+    __syncthreads();
+    gen += 1;
+    if (threadIdx.x == 0) {
+        unsigned int prev;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+        int ok = 1;
+        if (prev + 1u == nblocks * gen) {
+            st_release_u32(bar + 32, gen);
+        } else {
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_u32(bar + 32) - gen) < 0) {
+                if (clock64() - t0 > 4000000000LL) {
+                    if (err) atomicOr(err, SNN_ERR_BARRIER);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
 struct Misc {  // small per-step scratch (lives in shared memory)
     uint64_t mbar[2];
     int cnt[32];            // candidates per column (theta update)
@@ -83,15 +117,16 @@ struct Misc {  // small per-step scratch (lives in shared memory)
     int8_t wslot[256];      // sample -> staged row slot, -1 = not staged
 };
 
-struct SmemLayout { size_t W, tx, inS, inT, xrow, rep, xown, theta, misc, total; };
+struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, misc, total; };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int SW, int BW, int n, int own) {
+__host__ __device__ inline int ev_block_bytes(int B) { return (int)(al16(2 * (size_t)B) + 2 * (size_t)B * EV_CAP); }
+__host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, int n, int own) {
     SmemLayout L;
     size_t o = 0;
-    L.W = o; o += al16(sizeof(float) * (size_t)P * TJ);
+    L.W = o; o += al16(sizeof(float) * (size_t)(P + 1) * TJ);  // + one all-zero row (list padding)
     L.tx = o; o += al16(sizeof(float) * (size_t)B * TJ);
-    L.inS = o; o += al16(sizeof(uint32_t) * 2 * (size_t)B * SW);
+    L.ev = o; o += 2 * al16((size_t)ev_block_bytes(B));
     L.inT = o; o += al16(sizeof(uint32_t) * 2 * (size_t)P * BW);
     L.xrow = o; o += al16(sizeof(float) * (size_t)XR * P);
     L.rep = o; o += al16(sizeof(float) * (size_t)(n + 1));
@@ -102,17 +137,20 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int SW, 
     return L;
 }
 
-template <int TJ>
-__global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
+// TJ: neurons per CTA (4 per thread); BW: 32-bit words of a per-pixel sample mask (4 -> B <= 128,
+// 8 -> B <= 256).  Threads = B * TJ/4 <= 32 * BW * TJ/4.
+template <int TJ, int BW>
+__global__ void __launch_bounds__((8 * BW * TJ < 1024 ? 8 * BW * TJ : 1024), 1)
+snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     constexpr int CG = TJ / 4;  // float4 column groups = lanes that share one sample
     extern __shared__ __align__(16) unsigned char smem[];
-    const int B = Q.B, P = Q.P, n = Q.n, SW = Q.SW, BW = Q.BW, T = Q.T;
+    const int B = Q.B, P = Q.P, n = Q.n, T = Q.T;
     const unsigned int G = gridDim.x;
     const int own = (B + (int)G - 1) / (int)G;
-    const SmemLayout SL = smem_layout(P, TJ, B, SW, BW, n, own);
+    const SmemLayout SL = smem_layout(P, TJ, B, BW, n, own);
     float *W = (float *)(smem + SL.W);
     float *tx = (float *)(smem + SL.tx);
-    uint32_t *inS = (uint32_t *)(smem + SL.inS);
+    unsigned char *evb = smem + SL.ev;
     uint32_t *inT = (uint32_t *)(smem + SL.inT);
     float *xrow = (float *)(smem + SL.xrow);
     float *rep = (float *)(smem + SL.rep);
@@ -135,13 +173,17 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
     const bool update_on = Q.learning && C.rule != SNN_RULE_NONE && (stdp || decay_on);
     const bool stage_on = update_on && post_on && X.traces;
     const float Bf = (float)B;
+    const int evblk = (int)al16((size_t)Q.SB);  // stride between the two staged list blocks
+    const int cntb = (int)al16(2 * (size_t)B);  // bytes of the count array inside a block
+    float *Wc = W + 4 * cg;                     // my 4 columns of row 0
+    unsigned int gen = 0;
 
     // ---- prologue: W tile, theta, inhibition table, owned input traces, state registers ----
-    for (int idx = tid; idx < P * TJ; idx += nthr) {
-        const int i = idx / TJ, jj = idx % TJ;
-        W[idx] = (j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
+    for (int idx = tid; idx < (P + 1) * TJ; idx += nthr) {
+        const int i = idx / TJ, jj = idx - i * TJ;
+        W[idx] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
     }
-    for (int jj = tid; jj < TJ; jj += nthr) theta_s[jj] = (j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
+    for (int jj = tid; jj < 32; jj += nthr) theta_s[jj] = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
     if (tid == 0) {
         // rep[m] = m-fold sequential sum of the Ai->Ae weight: what the reference's dense sum
         // over k of sI[b,k] * w_ie[k,j] evaluates to when m inhibitory neurons (other than j) spike
@@ -177,17 +219,17 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
         if (ok && I.s[k]) sIprev |= 1u << c;
     }
     if (act && stdp) {
-        *(float4 *)(tx + (size_t)b * TJ + 4 * cg) =
+        *(float4 *)(tx + b * TJ + 4 * cg) =
             make_float4(wdep ? xE[0] : xE[0] * C.nu0, wdep ? xE[1] : xE[1] * C.nu0, wdep ? xE[2] : xE[2] * C.nu0,
                         wdep ? xE[3] : xE[3] * C.nu0);
     }
     __syncthreads();
     if (act && stdp && (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)) atomicOr(&M.nz[b >> 5], 1u << (b & 31));
 
-    const uint32_t bytesS = (uint32_t)(sizeof(uint32_t) * (size_t)B * SW), bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
+    const uint32_t bytesE = (uint32_t)Q.SB, bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
     if (tid == 0) {  // stage slot 0 (spikes of step -1 = the Input layer's incoming spike state)
-        mbar_expect_tx(&M.mbar[0], bytesS + bytesT);
-        bulk_g2s(inS, Q.inS, bytesS, &M.mbar[0]);
+        mbar_expect_tx(&M.mbar[0], bytesE + bytesT);
+        bulk_g2s(evb, Q.evS, bytesE, &M.mbar[0]);
         bulk_g2s(inT, Q.inT, bytesT, &M.mbar[0]);
     }
     uint32_t ph0 = 0, ph1 = 0;
@@ -196,15 +238,15 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
     // =====================================================================================
     for (int t = 0; t <= T; ++t) {
         const int buf = t & 1;
-        const uint32_t *cS = inS + (size_t)buf * B * SW;  // spikes of step t-1, per sample
-        const uint32_t *cT = inT + (size_t)buf * P * BW;  // spikes of step t-1, per pixel
+        const unsigned char *cE = evb + buf * evblk;              // spikes of step t-1: lists
+        const uint4 *cT = (const uint4 *)(inT + buf * P * BW);    // spikes of step t-1: per pixel
 
         // prefetch slot t+1 into the other buffer (its readers finished before the last barrier)
         if (tid == 0 && t + 1 <= T) {
             const int nb = buf ^ 1;
-            mbar_expect_tx(&M.mbar[nb], bytesS + bytesT);
-            bulk_g2s(inS + (size_t)nb * B * SW, Q.inS + (size_t)(t + 1) * B * SW, bytesS, &M.mbar[nb]);
-            bulk_g2s(inT + (size_t)nb * P * BW, Q.inT + (size_t)(t + 1) * P * BW, bytesT, &M.mbar[nb]);
+            mbar_expect_tx(&M.mbar[nb], bytesE + bytesT);
+            bulk_g2s(evb + nb * evblk, Q.evS + (size_t)(t + 1) * Q.SB, bytesE, &M.mbar[nb]);
+            bulk_g2s(inT + nb * P * BW, Q.inT + (size_t)(t + 1) * P * BW, bytesT, &M.mbar[nb]);
         }
 
         // ---- A. exchange results of step t-1 (slot (t-1) % 3; for t = 0 the pre-pass filled it)
@@ -212,17 +254,18 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
         unsigned long long key = 0ull;
         unsigned int isum = 0;
         if (act) {
-            isum = __ldcg(Q.sisum + (size_t)xs * B + b);
-            if (t > 0) key = __ldcg(Q.win + (size_t)xs * B + b);
+            isum = __ldcg(Q.sisum + xs * B + b);
+            if (t > 0 && candE) key = __ldcg(Q.win + xs * B + b);
         }
         if (t > 0 && stage_on) {  // speculative: input-trace rows of this tile's candidate samples
             const int ns = min(M.ncand, XR);
-            for (int idx = tid; idx < ns * P; idx += nthr) {
-                const int r = idx / P, i = idx - r * P;
-                xrow[idx] = __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + M.candb[r]) * P + i);
+            for (int r = 0; r < ns; ++r) {
+                const float4 *src = (const float4 *)(Q.xpub + ((size_t)((t - 1) & 1) * B + M.candb[r]) * P);
+                float4 *dst = (float4 *)(xrow + r * P);
+                for (int i4 = tid; i4 < (P >> 2); i4 += nthr) dst[i4] = __ldcg(src + i4);
             }
         }
-        // wait for this iteration's spike matrices (prefetched during the previous iteration)
+        // wait for this iteration's spike data (prefetched during the previous iteration)
         {
             uint32_t &ph = buf ? ph1 : ph0;
             while (!mbar_try_wait(&M.mbar[buf], ph)) {}
@@ -245,7 +288,7 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
                 }
                 if (update_on && stdp) {
                     if (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)
-                        *(float4 *)(tx + (size_t)b * TJ + 4 * cg) =
+                        *(float4 *)(tx + b * TJ + 4 * cg) =
                             make_float4(wdep ? xE[0] : xE[0] * C.nu0, wdep ? xE[1] : xE[1] * C.nu0,
                                         wdep ? xE[2] : xE[2] * C.nu0, wdep ? xE[3] : xE[3] * C.nu0);
                     if (sE) {
@@ -285,30 +328,39 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
             // and skipped — except on the first update of the window (entries may sit outside
             // [wmin, wmax] after normalize()) or with a weight decay.
             const bool full = decay_on || (C.has_clamp && t == 1);
-            uint32_t nzm[8];
+            uint32_t nzm[BW];
             #pragma unroll
-            for (int g = 0; g < 8; ++g) nzm[g] = g < BW ? M.nz[g] : 0u;
+            for (int g = 0; g < BW; ++g) nzm[g] = pre_on ? M.nz[g] : 0u;
             const uint32_t mycolwin = post_on ? ((M.colwin >> (4 * cg)) & 0xFu) : 0u;
+            const bool simple = !wdep && C.reduction == SNN_REDUCE_SUM;
+            const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
             for (int i = rslot; i < P; i += NRS) {
-                uint32_t m[8];
+                uint32_t m[BW];
+                {
+                    const uint4 q0 = cT[i * (BW / 4)];
+                    m[0] = q0.x & nzm[0]; m[1] = q0.y & nzm[1]; m[2] = q0.z & nzm[2]; m[3] = q0.w & nzm[3];
+                    if (BW == 8) {
+                        const uint4 q1 = cT[i * (BW / 4) + 1];
+                        m[BW - 4] = q1.x & nzm[BW - 4]; m[BW - 3] = q1.y & nzm[BW - 3];
+                        m[BW - 2] = q1.z & nzm[BW - 2]; m[BW - 1] = q1.w & nzm[BW - 1];
+                    }
+                }
                 uint32_t anym = 0;
                 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    m[g] = (pre_on && g < BW) ? (cT[(size_t)i * BW + g] & nzm[g]) : 0u;
-                    anym |= m[g];
-                }
+                for (int g = 0; g < BW; ++g) anym |= m[g];
                 const bool pre_t = anym != 0u;
                 if (!(full || pre_t || mycolwin)) continue;
-                const float4 w4 = *(const float4 *)(W + (size_t)i * TJ + 4 * cg);
+                float *wp = Wc + i * TJ;
+                const float4 w4 = *(const float4 *)wp;
                 float U[4] = {0.f, 0.f, 0.f, 0.f};
                 if (pre_t) {
                     #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
+                    for (int g = 0; g < BW; ++g) {
                         uint32_t mm = m[g];
                         while (mm) {
                             const int bb = g * 32 + __ffs(mm) - 1;
                             mm &= mm - 1;
-                            const float4 t4 = *(const float4 *)(tx + (size_t)bb * TJ + 4 * cg);
+                            const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * cg);
                             U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
                         }
                     }
@@ -326,16 +378,27 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
                                 const int bb = g * 32 + __ffs(mm) - 1;
                                 mm &= mm - 1;
                                 const int s = M.wslot[bb];
-                                const float xsv = (s >= 0) ? xrow[(size_t)s * P + i]
+                                const float xsv = (s >= 0) ? xrow[s * P + i]
                                                            : __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + bb) * P + i);
                                 V = V + xsv * (wdep ? 1.0f : C.nu1);
                             }
                         }
                         if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
                     }
-                    wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
+                    if (simple) {
+                        // PostPre family: w - U*dt, + V*dt, decay, clamp (x * 1.0f is exact, so the
+                        // classic rule's missing dt factor is dts = 1)
+                        float w = wv[c];
+                        if (pre_t) w = w - U[c] * dts;
+                        if (post_t) w = w + V * dts;
+                        if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+                        if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+                        wv[c] = w;
+                    } else {
+                        wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
+                    }
                 }
-                *(float4 *)(W + (size_t)i * TJ + 4 * cg) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+                *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
             }
             __syncthreads();
             if (M.winany) {
@@ -358,22 +421,34 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
         int nI = 0;
         if (act) {
             // spike-gather: p[c] = sum_{i in sX(t-1)[b]} W[i][c], i ascending (topology.py:437-479)
-            float p[4] = {0.f, 0.f, 0.f, 0.f};
-            const uint32_t *row = cS + (size_t)b * SW;
-            for (int w4i = 0; w4i < SW; w4i += 4) {
-                const uint4 q = *(const uint4 *)(row + w4i);
-                const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t word = ww[u];
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+            const int cnt = ((const uint16_t *)cE)[b];
+            if (cnt <= EV_CAP) {
+                const uint2 *l4 = (const uint2 *)(cE + cntb + b * (2 * EV_CAP));
+                for (int k = 0; k < cnt; k += 4) {
+                    const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
+                    const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * TJ);
+                    const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * TJ);
+                    const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * TJ);
+                    const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * TJ);
+                    p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
+                    p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
+                    p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
+                    p0 = p0 + r3.x; p1 = p1 + r3.y; p2 = p2 + r3.z; p3 = p3 + r3.w;
+                }
+            } else {  // dense sample: walk the bit row in global memory (rare, slow path)
+                const uint32_t *row = Q.inS + ((size_t)t * B + b) * Q.SW;
+                for (int w = 0; w < Q.SW; ++w) {
+                    uint32_t word = __ldg(row + w);
                     while (word) {
-                        const int i = (w4i + u) * 32 + __ffs(word) - 1;
+                        const int i = w * 32 + __ffs(word) - 1;
                         word &= word - 1;
-                        const float4 r4 = *(const float4 *)(W + (size_t)i * TJ + 4 * cg);
-                        p[0] = p[0] + r4.x; p[1] = p[1] + r4.y; p[2] = p[2] + r4.z; p[3] = p[3] + r4.w;
+                        const float4 r4 = *(const float4 *)(Wc + i * TJ);
+                        p0 = p0 + r4.x; p1 = p1 + r4.y; p2 = p2 + r4.z; p3 = p3 + r4.w;
                     }
                 }
             }
+            const float p[4] = {p0, p1, p2, p3};
             const float4 th4 = *(const float4 *)(theta_s + 4 * cg);
             const float th[4] = {th4.x, th4.y, th4.z, th4.w};
             #pragma unroll
@@ -415,8 +490,8 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
         }
         if (act && cg == 0) {
             const int ws = t % 3;
-            if (mykey) atomicMax(Q.win + (size_t)ws * B + b, mykey);
-            if (nI) atomicAdd(Q.sisum + (size_t)ws * B + b, (unsigned int)nI);
+            if (mykey) atomicMax(Q.win + ws * B + b, mykey);
+            if (nI) atomicAdd(Q.sisum + ws * B + b, (unsigned int)nI);
             if (anyc && stage_on) {
                 const int s = atomicAdd(&M.ncand, 1);
                 if (s < XR) { M.candb[s] = b; M.wslot[b] = (int8_t)s; }
@@ -431,13 +506,18 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
             for (int o = 0; o < own; ++o) {
                 const int bo = blockIdx.x + o * (int)G;
                 if (bo < B) {
-                    const uint32_t *srow = Q.inS + ((size_t)(t + 1) * B + bo) * SW;
-                    float *dst = Q.xpub + ((size_t)(t & 1) * B + bo) * P;
-                    for (int i = tid; i < P; i += nthr) {
-                        const bool s = (__ldg(srow + (i >> 5)) >> (i & 31)) & 1u;
-                        const float x = trace_step(xown[o * P + i], s, X.trace_decay, X.trace_scale, X.traces_additive);
-                        xown[o * P + i] = x;
-                        dst[i] = x;
+                    const uint32_t *srow = Q.inS + ((size_t)(t + 1) * B + bo) * Q.SW;
+                    float4 *dst = (float4 *)(Q.xpub + ((size_t)(t & 1) * B + bo) * P);
+                    float4 *xo = (float4 *)(xown + o * P);
+                    for (int i4 = tid; i4 < (P >> 2); i4 += nthr) {
+                        const uint32_t bits = __ldg(srow + (i4 >> 3)) >> ((i4 & 7) * 4);
+                        float4 x = xo[i4];
+                        x.x = trace_step(x.x, bits & 1u, X.trace_decay, X.trace_scale, X.traces_additive);
+                        x.y = trace_step(x.y, bits & 2u, X.trace_decay, X.trace_scale, X.traces_additive);
+                        x.z = trace_step(x.z, bits & 4u, X.trace_decay, X.trace_scale, X.traces_additive);
+                        x.w = trace_step(x.w, bits & 8u, X.trace_decay, X.trace_scale, X.traces_additive);
+                        xo[i4] = x;
+                        dst[i4] = x;
                     }
                 }
             }
@@ -445,8 +525,8 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
         // clear the exchange slot step t+1 will accumulate into (last read before the previous barrier)
         if (blockIdx.x == 0)
             for (int k = tid; k < B; k += nthr) {
-                Q.win[(size_t)((t + 1) % 3) * B + k] = 0ull;
-                Q.sisum[(size_t)((t + 1) % 3) * B + k] = 0u;
+                Q.win[((t + 1) % 3) * B + k] = 0ull;
+                Q.sisum[((t + 1) % 3) * B + k] = 0u;
             }
         __syncthreads();
         // theta += theta_plus * (number of candidates in the column)  (nodes.py:1093-1094)
@@ -454,7 +534,7 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
             if (E.learning) theta_s[tid] = theta_s[tid] + E.theta_plus * (float)M.cnt[tid];
             M.cnt[tid] = 0;
         }
-        if (!grid_barrier(Q.bar, G, Q.err)) return;
+        if (!grid_barrier_fast(Q.bar, G, gen, Q.err)) return;
     }
 
     // ---- epilogue: normalize() on the tile (network.py:464-465), write everything back -----
@@ -466,7 +546,7 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
             const int c = idx / TJ, jj = idx % TJ;
             float a = 0.0f;
             const int i1 = min((c + 1) * chunk, P);
-            for (int i = c * chunk; i < i1; ++i) { const float x = W[(size_t)i * TJ + jj]; a = a + (C.norm_abs ? fabsf(x) : x); }
+            for (int i = c * chunk; i < i1; ++i) { const float x = W[i * TJ + jj]; a = a + (C.norm_abs ? fabsf(x) : x); }
             part[idx] = a;
         }
         __syncthreads();
@@ -501,7 +581,7 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
     for (int o = 0; o < own; ++o) {
         const int bo = blockIdx.x + o * (int)G;
         if (bo < B) {
-            const uint32_t *srow = Q.inS + ((size_t)T * B + bo) * SW;  // slot T = spikes of step T-1
+            const uint32_t *srow = Q.inS + ((size_t)T * B + bo) * Q.SW;  // slot T = spikes of step T-1
             for (int i = tid; i < P; i += nthr) {
                 if (X.traces) X.x[(size_t)bo * P + i] = xown[o * P + i];
                 X.s[(size_t)bo * P + i] = (__ldg(srow + (i >> 5)) >> (i & 31)) & 1u;
@@ -513,16 +593,21 @@ __global__ void __launch_bounds__(1024, 1) snn_dc_fused_window(const __grid_cons
 // ---------------------------------------------------------------------------------------
 // Pre-pass: one CTA per slot.  Slot 0 = the Input layer's incoming spike state, slot t+1 = the
 // external input of step t (network.py:388-392 / Input.forward nodes.py:211-221).  Produces the
-// per-sample and per-pixel bit matrices, the Input monitor raster, flags non-binary input;
-// CTA 0 also resets the exchange slots and counts the incoming Ai spikes.
-__global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ FusedParams Q) {
+// per-sample bit rows and pixel lists, the per-pixel sample masks, the Input monitor raster,
+// flags non-binary input; CTA 0 also resets the exchange slots and counts the incoming Ai spikes.
+__global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ FusedParams Q, int BW) {
     extern __shared__ uint32_t sbits[];  // [B][SW]
-    const int B = Q.B, P = Q.P, SW = Q.SW, BW = Q.BW, PW = (P + 31) / 32;
+    const int B = Q.B, P = Q.P, SW = Q.SW, PW = (P + 31) / 32;
     const int slot = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const snn_layer_t &X = Q.X;
+    unsigned char *blk = Q.evS + (size_t)slot * Q.SB;
+    uint16_t *ecnt = (uint16_t *)blk;
+    uint16_t *elist = (uint16_t *)(blk + al16(2 * (size_t)B));
     bool nonbin = false;
     for (int b = warp; b < B; b += nwarp) {
+        int total = 0;
+        uint16_t *lst = elist + b * EV_CAP;
         for (int w = 0; w < SW; ++w) {
             const int i = w * 32 + lane;
             bool s = false;
@@ -537,13 +622,21 @@ __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ Fu
             }
             const uint32_t word = __ballot_sync(0xffffffffu, s);
             if (lane == 0) { sbits[b * SW + w] = word; Q.inS[((size_t)slot * B + b) * SW + w] = word; }
+            if (s) {  // ascending pixel list: position = spikes before me
+                const int pos = total + __popc(word & ((1u << lane) - 1u));
+                if (pos < EV_CAP) lst[pos] = (uint16_t)i;
+            }
+            total += __popc(word);
         }
+        const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
+        if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+        if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
     }
     __syncthreads();
     // transpose 32x32 bit blocks: inT[pixel][g] bit b' = inS[g*32+b'][pixel/32] bit pixel%32
     const int NG = (B + 31) / 32;
-    for (int blk = warp; blk < BW * PW; blk += nwarp) {
-        const int g = blk / PW, w = blk % PW;
+    for (int bk = warp; bk < BW * PW; bk += nwarp) {
+        const int g = bk / PW, w = bk % PW;
         uint32_t mine = 0;
         if (g < NG) {
             const int bb = g * 32 + lane;
@@ -572,7 +665,7 @@ __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ Fu
 }
 
 struct Match {
-    int lX, lE, lI, cXE, cEI, cIE, TJ, threads, grid, SW, BW, own;
+    int lX, lE, lI, cXE, cEI, cIE, TJ, BW, threads, grid, SW, SB, own;
     size_t smem;
 };
 
@@ -599,7 +692,6 @@ bool match(const snn_net_t *net, const snn_run_opts_t *o, Match &m) {
     if (m.lX < 0 || m.lE < 0 || m.lI < 0) return false;
     const snn_layer_t &X = net->layers[m.lX], &E = net->layers[m.lE], &I = net->layers[m.lI];
     if (E.ext || I.ext || I.traces || E.n != I.n) return false;
-    if (X.rec_v) return false;
     m.cXE = m.cEI = m.cIE = -1;
     for (int c = 0; c < 3; ++c) {
         const snn_conn_t &C = net->conns[c];
@@ -610,43 +702,47 @@ bool match(const snn_net_t *net, const snn_run_opts_t *o, Match &m) {
     }
     if (m.cXE < 0 || m.cEI < 0 || m.cIE < 0 || m.cXE > m.cIE) return false;  // accumulation order into Ae
     const snn_conn_t &CX = net->conns[m.cXE], &CEI = net->conns[m.cEI], &CIE = net->conns[m.cIE];
-    auto is_static = [](const snn_conn_t &C) { return (C.rule == SNN_RULE_NONE || (C.rule == SNN_RULE_NOOP && (C.weight_decay == 1.0f || C.weight_decay == 0.0f))) && !C.has_norm; };
+    auto is_static = [](const snn_conn_t &C) {
+        return (C.rule == SNN_RULE_NONE || (C.rule == SNN_RULE_NOOP && (C.weight_decay == 1.0f || C.weight_decay == 0.0f))) && !C.has_norm;
+    };
     if (!is_static(CEI) || !is_static(CIE)) return false;
     if (CEI.structure != SNN_W_DIAG || CIE.structure != SNN_W_OFFDIAG) return false;
     if (CX.rule >= SNN_RULE_POSTPRE && (!X.traces || !E.traces)) return false;
     const int n = E.n, P = X.n, B = o->B;
-    if (B > 256) return false;
+    if (B > 256 || (P & 3) || P >= 65535) return false;
     const int sms = device_sms();
     m.SW = ((P + 31) / 32 + 3) / 4 * 4;
-    m.BW = ((B + 31) / 32 + 3) / 4 * 4;
+    m.BW = B <= 128 ? 4 : 8;
+    m.SB = ev_block_bytes(B);
     for (int TJ : {4, 8, 16, 32}) {
         const int grid = (n + TJ - 1) / TJ;
-        const int threads = ((B * (TJ / 4)) + 31) / 32 * 32;
+        int threads = ((B * (TJ / 4)) + 31) / 32 * 32;
         if (grid > sms || threads > 1024) continue;
         const int own = (B + grid - 1) / grid;
-        const SmemLayout SL = smem_layout(P, TJ, B, m.SW, m.BW, n, own);
+        const SmemLayout SL = smem_layout(P, TJ, B, m.BW, n, own);
         if (SL.total > 227 * 1024) continue;
-        m.TJ = TJ; m.grid = grid; m.threads = threads < 32 ? 32 : threads; m.own = own; m.smem = SL.total;
+        m.TJ = TJ; m.grid = grid; m.threads = threads; m.own = own; m.smem = SL.total;
         return true;
     }
     return false;
 }
 
-template <int TJ>
+template <int TJ, int BW>
 cudaError_t launch_tj(const FusedParams &Q, const Match &m, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(snn_dc_fused_window<TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
+    cudaError_t e = cudaFuncSetAttribute(snn_dc_fused_window<TJ, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&Q};
-    return cudaLaunchCooperativeKernel((void *)snn_dc_fused_window<TJ>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
+    return cudaLaunchCooperativeKernel((void *)snn_dc_fused_window<TJ, BW>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
 }
 
-struct WsLayout { size_t bar, inS, inT, win, sisum, xpub, total; };
+struct WsLayout { size_t bar, inS, inT, evS, win, sisum, xpub, total; };
 WsLayout ws_layout(const Match &m, int T, int B, int P) {
     WsLayout L; size_t o = 0;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     L.bar = o; o += al(sizeof(unsigned int) * 96);
     L.inS = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * B * m.SW);
     L.inT = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * P * m.BW);
+    L.evS = o; o += al((size_t)(T + 1) * m.SB);
     L.win = o; o += al(sizeof(unsigned long long) * 3 * B);
     L.sisum = o; o += al(sizeof(unsigned int) * 3 * B);
     L.xpub = o; o += al(sizeof(float) * 2 * (size_t)B * P);
@@ -681,19 +777,27 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.C = net->conns[m.cXE];
     Q.exc = net->conns[m.cEI].structure_val; Q.inh_neg = net->conns[m.cIE].structure_val;
     Q.T = T; Q.B = B; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
-    Q.SW = m.SW; Q.BW = m.BW; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
-    Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT);
+    Q.SW = m.SW; Q.SB = m.SB; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
+    Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
     Q.win = (unsigned long long *)(ws + WL.win); Q.sisum = (unsigned int *)(ws + WL.sisum);
     Q.xpub = (float *)(ws + WL.xpub); Q.bar = (unsigned int *)(ws + WL.bar); Q.err = opts->err_flag;
     if (cudaMemsetAsync(Q.bar, 0, sizeof(unsigned int) * 96, stream) != cudaSuccess) return SNN_ERR_CUDA;
-    snn_dc_prepass<<<T + 1, 256, sizeof(uint32_t) * (size_t)B * m.SW, stream>>>(Q);
+    snn_dc_prepass<<<T + 1, 256, sizeof(uint32_t) * (size_t)B * m.SW, stream>>>(Q, m.BW);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
-        switch (m.TJ) {
-            case 4: e = launch_tj<4>(Q, m, stream); break;
-            case 8: e = launch_tj<8>(Q, m, stream); break;
-            case 16: e = launch_tj<16>(Q, m, stream); break;
-            default: e = launch_tj<32>(Q, m, stream); break;
+        if (m.BW == 4) {
+            switch (m.TJ) {
+                case 4: e = launch_tj<4, 4>(Q, m, stream); break;
+                case 8: e = launch_tj<8, 4>(Q, m, stream); break;
+                case 16: e = launch_tj<16, 4>(Q, m, stream); break;
+                default: e = launch_tj<32, 4>(Q, m, stream); break;
+            }
+        } else {
+            switch (m.TJ) {
+                case 4: e = launch_tj<4, 8>(Q, m, stream); break;
+                case 8: e = launch_tj<8, 8>(Q, m, stream); break;
+                default: e = launch_tj<16, 8>(Q, m, stream); break;
+            }
         }
     }
     if (e != cudaSuccess) {
