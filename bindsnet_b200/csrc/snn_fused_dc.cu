@@ -25,6 +25,7 @@
 // Arithmetic and summation orders are those of snn_phases.cuh / oracle/snn_oracle.c, so the
 // result is bit-identical to the generic kernel and to the oracle.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "snn_common.cuh"
@@ -42,6 +43,8 @@ struct FusedParams {
     int32_t SW;               // words per sample row of inS
     int32_t SB;               // bytes of one event-list block
     int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
+    int32_t dbg;              // profiling only (env SNN_B200_DEBUG): 1 no barrier wait, 2 skip STDP,
+                              // 4 skip gather, 8 skip trace publish, 16 skip staging — results invalid
     uint32_t seed, step_offset;
     uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
     uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
@@ -79,7 +82,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // Grid barrier, one L2 round trip to arrive and a polling load to leave: a monotonic arrival
 // counter (acq_rel atomic; the last arriver of generation g publishes g) and a generation word.
 // All cross-CTA data is read with ld.global.cg, so no L1 invalidation is needed.
-__device__ __forceinline__ bool grid_barrier_fast(unsigned int *bar, unsigned int nblocks, unsigned int &gen, int32_t *err) {
+__device__ __forceinline__ bool grid_barrier_fast(unsigned int *bar, unsigned int nblocks, unsigned int &gen, int32_t *err, bool nowait = false) {
     __shared__ int s_ok;
     __syncthreads();
     gen += 1;
@@ -89,7 +92,7 @@ __device__ __forceinline__ bool grid_barrier_fast(unsigned int *bar, unsigned in
         int ok = 1;
         if (prev + 1u == nblocks * gen) {
             st_release_u32(bar + 32, gen);
-        } else {
+        } else if (!nowait) {
             const long long t0 = clock64();
             while ((int)(ld_acquire_u32(bar + 32) - gen) < 0) {
                 if (clock64() - t0 > 4000000000LL) {
@@ -109,7 +112,9 @@ struct Misc {  // small per-step scratch (lives in shared memory)
     uint64_t mbar[2];
     int cnt[32];            // candidates per column (theta update)
     uint32_t wmask[32][8];  // winners: per column, bit mask over samples
-    uint32_t nz[8];         // samples that have a non-zero Ae trace in this tile
+    uint32_t nz4[8][8];     // per column group: samples with a non-zero Ae trace in that group
+    int nlive;              // live (sample, column group) pairs, listed in live[]
+    int nwork;              // (row, column group) items of this step's STDP work list
     int ncand;              // samples with a candidate in this tile this step
     int candb[XR];          // ... the first XR of them (their input-trace rows get staged)
     int winany;
@@ -117,7 +122,7 @@ struct Misc {  // small per-step scratch (lives in shared memory)
     int8_t wslot[256];      // sample -> staged row slot, -1 = not staged
 };
 
-struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, misc, total; };
+struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, live, touched, work, misc, total; };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline int ev_block_bytes(int B) { return (int)(al16(2 * (size_t)B) + 2 * (size_t)B * EV_CAP); }
@@ -132,6 +137,9 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, 
     L.rep = o; o += al16(sizeof(float) * (size_t)(n + 1));
     L.xown = o; o += al16(sizeof(float) * (size_t)own * P);
     L.theta = o; o += al16(sizeof(float) * 32);
+    L.live = o; o += al16(sizeof(uint16_t) * (size_t)B * (TJ / 4));
+    L.touched = o; o += al16(sizeof(uint32_t) * (size_t)(TJ / 4) * ((P + 31) / 32));
+    L.work = o; o += al16(sizeof(uint16_t) * (size_t)P * (TJ / 4));
     L.misc = o; o += al16(sizeof(Misc));
     L.total = o;
     return L;
@@ -156,7 +164,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     float *rep = (float *)(smem + SL.rep);
     float *xown = (float *)(smem + SL.xown);
     float *theta_s = (float *)(smem + SL.theta);
+    uint16_t *live = (uint16_t *)(smem + SL.live);
+    uint32_t *touched = (uint32_t *)(smem + SL.touched);
+    uint16_t *work = (uint16_t *)(smem + SL.work);
     Misc &M = *(Misc *)(smem + SL.misc);
+    const int PW = (P + 31) >> 5;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int b = tid / CG, cg = tid % CG;   // state ownership: sample b, neurons jc..jc+3
@@ -193,9 +205,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         mbar_init(&M.mbar[0], 1);
         mbar_init(&M.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        M.ncand = 0; M.winany = 0; M.colwin = 0;
+        M.ncand = 0; M.winany = 0; M.colwin = 0; M.nlive = 0; M.nwork = 0;
     }
-    for (int k = tid; k < 8; k += nthr) M.nz[k] = 0;
+    for (int k = tid; k < 64; k += nthr) (&M.nz4[0][0])[k] = 0;
     for (int k = tid; k < 32; k += nthr) M.cnt[k] = 0;
     for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
     for (int k = tid; k < 256; k += nthr) M.wslot[k] = -1;
@@ -224,7 +236,12 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                         wdep ? xE[3] : xE[3] * C.nu0);
     }
     __syncthreads();
-    if (act && stdp && (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)) atomicOr(&M.nz[b >> 5], 1u << (b & 31));
+    bool livep = false;  // my (sample, column group) pair has a non-zero Ae trace
+    if (act && stdp && (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)) {
+        livep = true;
+        atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
+        live[atomicAdd(&M.nlive, 1)] = (uint16_t)tid;
+    }
 
     const uint32_t bytesE = (uint32_t)Q.SB, bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
     if (tid == 0) {  // stage slot 0 (spikes of step -1 = the Input layer's incoming spike state)
@@ -257,7 +274,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             isum = __ldcg(Q.sisum + xs * B + b);
             if (t > 0 && candE) key = __ldcg(Q.win + xs * B + b);
         }
-        if (t > 0 && stage_on) {  // speculative: input-trace rows of this tile's candidate samples
+        if (t > 0 && stage_on && !(Q.dbg & 16)) {  // speculative: input-trace rows of this tile's candidate samples
             const int ns = min(M.ncand, XR);
             for (int r = 0; r < ns; ++r) {
                 const float4 *src = (const float4 *)(Q.xpub + ((size_t)((t - 1) & 1) * B + M.candb[r]) * P);
@@ -291,8 +308,12 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                         *(float4 *)(tx + b * TJ + 4 * cg) =
                             make_float4(wdep ? xE[0] : xE[0] * C.nu0, wdep ? xE[1] : xE[1] * C.nu0,
                                         wdep ? xE[2] : xE[2] * C.nu0, wdep ? xE[3] : xE[3] * C.nu0);
+                    if (sE && !livep) {
+                        livep = true;
+                        atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
+                        live[atomicAdd(&M.nlive, 1)] = (uint16_t)tid;
+                    }
                     if (sE) {
-                        atomicOr(&M.nz[b >> 5], 1u << (b & 31));
                         #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             if ((sE >> c) & 1u) {
@@ -319,38 +340,88 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         }
         __syncthreads();
 
-        if (t > 0 && update_on) {
+        if (t > 0 && update_on && !(Q.dbg & 2)) {
             // ---- C. learning-rule update of step t-1 on the W tile --------------------------
             //   U[i,j] = reduce_b sX[b,i] * (xE[b,j]*nu0)   pre term  (MCC_learning.py:234-263)
             //   V[i,j] = reduce_b xX[b,i] * (sE[b,j]*nu1)   post term (MCC_learning.py:267-299)
-            // then decay + clamp (MCC_learning.py:86-110).  Rows without a pre spike from a
-            // sample with a live Ae trace, in columns without a winner, are bitwise unchanged
-            // and skipped — except on the first update of the window (entries may sit outside
+            // then decay + clamp (MCC_learning.py:86-110).  The reference rewrites all of W; only
+            // (row i, column group) items with a pre spike from a sample whose Ae trace is live in
+            // that group, or in a group holding a winner, can change bits — everything else is
+            // skipped, except on the first update of the window (entries may sit outside
             // [wmin, wmax] after normalize()) or with a weight decay.
+            // Pass 1 marks those items from the (sample, group) pairs with a live trace and the
+            // sample's event list, pass 1b compacts them into a work list, pass 2 runs one
+            // float4 item per thread — no divergence on the sparse structure.
             const bool full = decay_on || (C.has_clamp && t == 1);
-            uint32_t nzm[BW];
-            #pragma unroll
-            for (int g = 0; g < BW; ++g) nzm[g] = pre_on ? M.nz[g] : 0u;
-            const uint32_t mycolwin = post_on ? ((M.colwin >> (4 * cg)) & 0xFu) : 0u;
-            const bool simple = !wdep && C.reduction == SNN_REDUCE_SUM;
+            const uint32_t colwin = post_on ? M.colwin : 0u;
             const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
-            for (int i = rslot; i < P; i += NRS) {
-                uint32_t m[BW];
-                {
-                    const uint4 q0 = cT[i * (BW / 4)];
-                    m[0] = q0.x & nzm[0]; m[1] = q0.y & nzm[1]; m[2] = q0.z & nzm[2]; m[3] = q0.w & nzm[3];
-                    if (BW == 8) {
-                        const uint4 q1 = cT[i * (BW / 4) + 1];
-                        m[BW - 4] = q1.x & nzm[BW - 4]; m[BW - 3] = q1.y & nzm[BW - 3];
-                        m[BW - 2] = q1.z & nzm[BW - 2]; m[BW - 1] = q1.w & nzm[BW - 1];
+            const int ntw = CG * PW;
+            if (full) {
+                for (int k = tid; k < P * CG; k += nthr) work[k] = (uint16_t)k;
+                if (tid == 0) M.nwork = P * CG;
+            } else {
+                for (int k = tid; k < ntw; k += nthr) touched[k] = 0u;
+                if (tid == 0) M.nwork = 0;
+                __syncthreads();
+                if (pre_on) {
+                    const uint16_t *ec = (const uint16_t *)cE;
+                    const uint16_t *el = (const uint16_t *)(cE + cntb);
+                    const int nl = M.nlive;
+                    for (int idx = tid; idx < nl * 16; idx += nthr) {
+                        const int lp = live[idx >> 4], e = idx & 15;
+                        const int bb = lp / CG, c4 = lp % CG;
+                        const int cnt = ec[bb];
+                        if (cnt > EV_CAP) {  // dense sample: conservatively mark every row of the group
+                            for (int w = e; w < PW; w += 16) touched[c4 * PW + w] = 0xffffffffu;
+                        } else {
+                            for (int k = e; k < cnt; k += 16) {
+                                const int i = el[bb * EV_CAP + k];
+                                atomicOr(&touched[c4 * PW + (i >> 5)], 1u << (i & 31));
+                            }
+                        }
                     }
                 }
+                if (colwin) {  // a winner: every row of its column group gets the post term
+                    for (int k = tid; k < ntw; k += nthr)
+                        if ((colwin >> (4 * (k / PW))) & 0xFu) touched[k] = 0xffffffffu;
+                }
+                __syncthreads();
+                for (int k = tid; k < ntw; k += nthr) {
+                    const int w = k % PW;
+                    uint32_t bits = touched[k];
+                    if (w == PW - 1 && (P & 31)) bits &= (1u << (P & 31)) - 1u;
+                    if (bits) {
+                        int pos = atomicAdd(&M.nwork, __popc(bits));
+                        const int c4 = k / PW;
+                        while (bits) {
+                            const int i = w * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            work[pos++] = (uint16_t)(i * CG + c4);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const int nwork = M.nwork;
+            for (int k = tid; k < nwork; k += nthr) {
+                const int item = work[k];
+                const int i = item / CG, c4 = item % CG;
+                uint32_t m[BW];
                 uint32_t anym = 0;
-                #pragma unroll
-                for (int g = 0; g < BW; ++g) anym |= m[g];
+                if (pre_on) {
+                    const uint4 q0 = cT[i * (BW / 4)];
+                    const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+                    m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+                    if (BW == 8) {
+                        const uint4 q1 = cT[i * (BW / 4) + 1];
+                        const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                        m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+                    }
+                    #pragma unroll
+                    for (int g = 0; g < BW; ++g) anym |= m[g];
+                }
                 const bool pre_t = anym != 0u;
-                if (!(full || pre_t || mycolwin)) continue;
-                float *wp = Wc + i * TJ;
+                float *wp = W + i * TJ + 4 * c4;
                 const float4 w4 = *(const float4 *)wp;
                 float U[4] = {0.f, 0.f, 0.f, 0.f};
                 if (pre_t) {
@@ -360,12 +431,13 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                         while (mm) {
                             const int bb = g * 32 + __ffs(mm) - 1;
                             mm &= mm - 1;
-                            const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * cg);
+                            const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
                             U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
                         }
                     }
                     if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
                 }
+                const uint32_t mycolwin = (colwin >> (4 * c4)) & 0xFu;
                 float wv[4] = {w4.x, w4.y, w4.z, w4.w};
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -373,19 +445,19 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     const bool post_t = (mycolwin >> c) & 1u;
                     if (post_t) {
                         for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = M.wmask[4 * cg + c][g];
+                            uint32_t mm = M.wmask[4 * c4 + c][g];
                             while (mm) {
                                 const int bb = g * 32 + __ffs(mm) - 1;
                                 mm &= mm - 1;
-                                const int s = M.wslot[bb];
-                                const float xsv = (s >= 0) ? xrow[s * P + i]
-                                                           : __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + bb) * P + i);
+                                const int sl = M.wslot[bb];
+                                const float xsv = (sl >= 0) ? xrow[sl * P + i]
+                                                            : __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + bb) * P + i);
                                 V = V + xsv * (wdep ? 1.0f : C.nu1);
                             }
                         }
                         if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
                     }
-                    if (simple) {
+                    if (!wdep) {
                         // PostPre family: w - U*dt, + V*dt, decay, clamp (x * 1.0f is exact, so the
                         // classic rule's missing dt factor is dts = 1)
                         float w = wv[c];
@@ -423,7 +495,8 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             // spike-gather: p[c] = sum_{i in sX(t-1)[b]} W[i][c], i ascending (topology.py:437-479)
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
             const int cnt = ((const uint16_t *)cE)[b];
-            if (cnt <= EV_CAP) {
+            if (Q.dbg & 4) {
+            } else if (cnt <= EV_CAP) {
                 const uint2 *l4 = (const uint2 *)(cE + cntb + b * (2 * EV_CAP));
                 for (int k = 0; k < cnt; k += 4) {
                     const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
@@ -502,7 +575,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
 
         // input trace of the samples this CTA owns: x = s ? scale : x * decay (nodes.py:96-103),
         // published for the winners' post-synaptic STDP term of THIS step
-        if (X.traces) {
+        if (X.traces && !(Q.dbg & 8)) {
             for (int o = 0; o < own; ++o) {
                 const int bo = blockIdx.x + o * (int)G;
                 if (bo < B) {
@@ -534,7 +607,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             if (E.learning) theta_s[tid] = theta_s[tid] + E.theta_plus * (float)M.cnt[tid];
             M.cnt[tid] = 0;
         }
-        if (!grid_barrier_fast(Q.bar, G, gen, Q.err)) return;
+        if (!grid_barrier_fast(Q.bar, G, gen, Q.err, Q.dbg & 1)) return;
     }
 
     // ---- epilogue: normalize() on the tile (network.py:464-465), write everything back -----
@@ -777,6 +850,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.C = net->conns[m.cXE];
     Q.exc = net->conns[m.cEI].structure_val; Q.inh_neg = net->conns[m.cIE].structure_val;
     Q.T = T; Q.B = B; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
+    { const char *d = getenv("SNN_B200_DEBUG"); Q.dbg = d ? atoi(d) : 0; }
     Q.SW = m.SW; Q.SB = m.SB; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
     Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
     Q.win = (unsigned long long *)(ws + WL.win); Q.sisum = (unsigned int *)(ws + WL.sisum);
