@@ -55,7 +55,9 @@ struct FusedParams {
     float *xpub;              // [2][B][P] published input traces, slot t & 1
     unsigned int *bar;        // [0] arrivals (monotonic), [32] generation
     int32_t *err;
+    long long *prof;          // profiling only (env SNN_B200_PROF): [grid][NPROF] phase cycles of thread 0
 };
+constexpr int NPROF = 12;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -82,25 +84,35 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // Grid barrier, one L2 round trip to arrive and a polling load to leave: a monotonic arrival
 // counter (acq_rel atomic; the last arriver of generation g publishes g) and a generation word.
 // All cross-CTA data is read with ld.global.cg, so no L1 invalidation is needed.
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier on ONE monotonic arrival counter: a release reduction to arrive, relaxed polling
+// of the same word until nblocks * generation arrivals are in, then one acquire fence.
+// (scripts/barrier_bench.cu: 1.2 us on B200 against 1.9 us for the counter + generation-word
+// scheme and 1.3 us for cooperative groups' grid.sync; 0.85 us is the no-ordering floor.)
+// All cross-CTA data is read with ld.global.cg, so no L1 invalidation is needed.
 __device__ __forceinline__ bool grid_barrier_fast(unsigned int *bar, unsigned int nblocks, unsigned int &gen, int32_t *err, bool nowait = false) {
     __shared__ int s_ok;
     __syncthreads();
     gen += 1;
     if (threadIdx.x == 0) {
-        unsigned int prev;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         int ok = 1;
-        if (prev + 1u == nblocks * gen) {
-            st_release_u32(bar + 32, gen);
-        } else if (!nowait) {
+        if (!nowait) {
+            const unsigned int target = nblocks * gen;
             const long long t0 = clock64();
-            while ((int)(ld_acquire_u32(bar + 32) - gen) < 0) {
+            while ((int)(ld_relaxed_u32(bar) - target) < 0) {
                 if (clock64() - t0 > 4000000000LL) {
                     if (err) atomicOr(err, SNN_ERR_BARRIER);
                     ok = 0;
                     break;
                 }
             }
+            asm volatile("fence.acquire.gpu;" ::: "memory");
         }
         s_ok = ok;
     }
@@ -129,7 +141,8 @@ __host__ __device__ inline int ev_block_bytes(int B) { return (int)(al16(2 * (si
 __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, int n, int own) {
     SmemLayout L;
     size_t o = 0;
-    L.W = o; o += al16(sizeof(float) * (size_t)(P + 1) * TJ);  // + one all-zero row (list padding)
+    L.W = o; o += al16(sizeof(float) * (size_t)(P + 1) * (TJ + 4));  // row stride TJ+4 (column passes
+                                                                        // hit 8 banks, not 2); + one zero row
     L.tx = o; o += al16(sizeof(float) * (size_t)B * TJ);
     L.ev = o; o += 2 * al16((size_t)ev_block_bytes(B));
     L.inT = o; o += al16(sizeof(uint32_t) * 2 * (size_t)P * BW);
@@ -151,6 +164,7 @@ template <int TJ, int BW>
 __global__ void __launch_bounds__((8 * BW * TJ < 1024 ? 8 * BW * TJ : 1024), 1)
 snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     constexpr int CG = TJ / 4;  // float4 column groups = lanes that share one sample
+    constexpr int WS = TJ + 4;  // row stride of the W tile in shared memory (floats)
     extern __shared__ __align__(16) unsigned char smem[];
     const int B = Q.B, P = Q.P, n = Q.n, T = Q.T;
     const unsigned int G = gridDim.x;
@@ -188,12 +202,19 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     const int evblk = (int)al16((size_t)Q.SB);  // stride between the two staged list blocks
     const int cntb = (int)al16(2 * (size_t)B);  // bytes of the count array inside a block
     float *Wc = W + 4 * cg;                     // my 4 columns of row 0
+    // an Ai neuron at rest with no input stays bitwise at rest (decay*(rest-rest)+rest == rest)
+    const bool ai_rest_ok = I.rest < I.thresh && !(I.has_lbound && I.rest < I.lbound);
     unsigned int gen = 0;
+    long long pc[NPROF], pm[NPROF];
+    #pragma unroll
+    for (int k = 0; k < NPROF; ++k) { pc[k] = 0; pm[k] = 0; }
+    long long pt = clock64();
+    #define PROF(k) { if (Q.prof) { const long long now_ = clock64(); const long long d_ = now_ - pt; pc[k] += d_; pm[k] = d_ > pm[k] ? d_ : pm[k]; pt = now_; } }
 
     // ---- prologue: W tile, theta, inhibition table, owned input traces, state registers ----
     for (int idx = tid; idx < (P + 1) * TJ; idx += nthr) {
         const int i = idx / TJ, jj = idx - i * TJ;
-        W[idx] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
+        W[i * WS + jj] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
     }
     for (int jj = tid; jj < 32; jj += nthr) theta_s[jj] = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
     if (tid == 0) {
@@ -252,6 +273,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     uint32_t ph0 = 0, ph1 = 0;
     __syncthreads();
 
+    PROF(0)  // prologue
     // =====================================================================================
     for (int t = 0; t <= T; ++t) {
         const int buf = t & 1;
@@ -282,6 +304,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 for (int i4 = tid; i4 < (P >> 2); i4 += nthr) dst[i4] = __ldcg(src + i4);
             }
         }
+        PROF(1)  // A: exchange loads + staging issue
         // wait for this iteration's spike data (prefetched during the previous iteration)
         {
             uint32_t &ph = buf ? ph1 : ph0;
@@ -289,6 +312,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             ph ^= 1u;
         }
 
+        PROF(2)  // mbarrier wait
         if (t > 0) {
             // ---- B. finalise step t-1: winner (nodes.py:1097-1105), Ae trace (nodes.py:96-103)
             uint32_t sE = 0;
@@ -339,6 +363,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             sEprev = sE;
         }
         __syncthreads();
+        PROF(3)  // B finalise + sync
 
         if (t > 0 && update_on && !(Q.dbg & 2)) {
             // ---- C. learning-rule update of step t-1 on the W tile --------------------------
@@ -381,10 +406,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                         }
                     }
                 }
-                if (colwin) {  // a winner: every row of its column group gets the post term
-                    for (int k = tid; k < ntw; k += nthr)
-                        if ((colwin >> (4 * (k / PW))) & 0xFu) touched[k] = 0xffffffffu;
-                }
                 __syncthreads();
                 for (int k = tid; k < ntw; k += nthr) {
                     const int w = k % PW;
@@ -402,6 +423,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 }
             }
             __syncthreads();
+            PROF(4)  // C mark + compact
             const int nwork = M.nwork;
             for (int k = tid; k < nwork; k += nthr) {
                 const int item = work[k];
@@ -421,7 +443,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     for (int g = 0; g < BW; ++g) anym |= m[g];
                 }
                 const bool pre_t = anym != 0u;
-                float *wp = W + i * TJ + 4 * c4;
+                float *wp = W + i * WS + 4 * c4;
                 const float4 w4 = *(const float4 *)wp;
                 float U[4] = {0.f, 0.f, 0.f, 0.f};
                 if (pre_t) {
@@ -441,42 +463,71 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 float wv[4] = {w4.x, w4.y, w4.z, w4.w};
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float V = 0.0f;
-                    const bool post_t = (mycolwin >> c) & 1u;
-                    if (post_t) {
-                        for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = M.wmask[4 * c4 + c][g];
-                            while (mm) {
-                                const int bb = g * 32 + __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                const int sl = M.wslot[bb];
-                                const float xsv = (sl >= 0) ? xrow[sl * P + i]
-                                                            : __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + bb) * P + i);
-                                V = V + xsv * (wdep ? 1.0f : C.nu1);
-                            }
-                        }
-                        if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
-                    }
+                    if ((mycolwin >> c) & 1u) continue;  // winner column: handled whole by pass 3
                     if (!wdep) {
-                        // PostPre family: w - U*dt, + V*dt, decay, clamp (x * 1.0f is exact, so the
-                        // classic rule's missing dt factor is dts = 1)
+                        // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic
+                        // rule's missing dt factor is dts = 1)
                         float w = wv[c];
                         if (pre_t) w = w - U[c] * dts;
-                        if (post_t) w = w + V * dts;
                         if (C.weight_decay != 0.0f) w = w * C.weight_decay;
                         if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
                         wv[c] = w;
                     } else {
-                        wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
+                        wv[c] = apply_rule(C, wv[c], U[c], pre_t, 0.0f, false);
                     }
                 }
                 *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            }
+            // pass 3: columns with a winner get pre + post term on every row, one element per thread
+            if (colwin) __syncthreads();  // pass 2 rewrote whole float4s (winner components unchanged)
+            for (uint32_t cw = colwin; cw; cw &= cw - 1) {
+                const int j = __ffs(cw) - 1, c4 = j >> 2;
+                for (int i = tid; i < P; i += nthr) {
+                    float U = 0.0f, V = 0.0f;
+                    bool pre_t = false;
+                    if (pre_on) {
+                        #pragma unroll
+                        for (int g = 0; g < BW; ++g) {
+                            uint32_t mm = inT[buf * P * BW + i * BW + g] & M.nz4[c4][g];
+                            pre_t |= mm != 0u;
+                            while (mm) {
+                                const int bb = g * 32 + __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                U = U + tx[bb * TJ + j];
+                            }
+                        }
+                        if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
+                    }
+                    for (int g = 0; g < BW; ++g) {
+                        uint32_t mm = M.wmask[j][g];
+                        while (mm) {
+                            const int bb = g * 32 + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const int sl = M.wslot[bb];
+                            const float xsv = (sl >= 0) ? xrow[sl * P + i]
+                                                        : __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + bb) * P + i);
+                            V = V + xsv * (wdep ? 1.0f : C.nu1);
+                        }
+                    }
+                    if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
+                    float w = W[i * WS + j];
+                    if (!wdep) {
+                        if (pre_t) w = w - U * dts;
+                        w = w + V * dts;
+                        if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+                        if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+                    } else {
+                        w = apply_rule(C, w, U, pre_t, V, true);
+                    }
+                    W[i * WS + j] = w;
+                }
             }
             __syncthreads();
             if (M.winany) {
                 for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
             }
         }
+        PROF(5)  // C items
         if (t > 0) {
             // reset the per-step candidate / winner bookkeeping
             for (int k = tid; k < B; k += nthr) M.wslot[k] = -1;
@@ -488,6 +539,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         // ---- D. step t: theta decay, gather, Ae / Ai update, candidates ---------------------
         if (tid < TJ && E.learning) theta_s[tid] = theta_s[tid] * E.theta_decay;  // nodes.py:1078-1079
         __syncthreads();
+        PROF(6)  // reset + theta decay + syncs
         uint32_t cand = 0, sI = 0;
         unsigned long long mykey = 0ull;
         int nI = 0;
@@ -500,10 +552,10 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 const uint2 *l4 = (const uint2 *)(cE + cntb + b * (2 * EV_CAP));
                 for (int k = 0; k < cnt; k += 4) {
                     const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
-                    const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * TJ);
-                    const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * TJ);
-                    const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * TJ);
-                    const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * TJ);
+                    const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
+                    const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
+                    const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
+                    const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * WS);
                     p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
                     p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
                     p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
@@ -516,7 +568,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     while (word) {
                         const int i = w * 32 + __ffs(word) - 1;
                         word &= word - 1;
-                        const float4 r4 = *(const float4 *)(Wc + i * TJ);
+                        const float4 r4 = *(const float4 *)(Wc + i * WS);
                         p0 = p0 + r4.x; p1 = p1 + r4.y; p2 = p2 + r4.z; p3 = p3 + r4.w;
                     }
                 }
@@ -533,8 +585,13 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     cur = cur + rep[mI];
                     if (dc_step(E, vE[c], rE[c], cur, th[c])) cand |= 1u << c;       // nodes.py:1077-1092
                     if (E.has_lbound && vE[c] < E.lbound) vE[c] = E.lbound;           // nodes.py:1108-1109
-                    float curI = ((sEprev >> c) & 1u) ? (0.0f + Q.exc) : 0.0f;        // diagonal Ae->Ai
-                    if (lif_step(I, vI[c], rI[c], curI)) { sI |= 1u << c; ++nI; }     // nodes.py:500-529
+                    const bool inI = (sEprev >> c) & 1u;
+                    if (inI || !ai_rest_ok || vI[c] != I.rest || rI[c] > 0.0f) {
+                        float curI = inI ? (0.0f + Q.exc) : 0.0f;                     // diagonal Ae->Ai
+                        if (lif_step(I, vI[c], rI[c], curI)) { sI |= 1u << c; ++nI; } // nodes.py:500-529
+                    } else {
+                        rI[c] = rI[c] - I.dt;  // resting, unrefractory, no input: v stays exactly at rest
+                    }
                 }
             }
             if (cand && E.one_spike) {
@@ -552,6 +609,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     if ((cand >> c) & 1u) atomicAdd(&M.cnt[4 * cg + c], 1);
             }
         }
+        PROF(7)  // D gather + neuron updates
         // reductions over the CG lanes that share a sample (all lanes of the warp take part)
         uint32_t anyc = cand;
         #pragma unroll
@@ -595,6 +653,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 }
             }
         }
+        PROF(8)  // reductions, atomics, trace publish
         // clear the exchange slot step t+1 will accumulate into (last read before the previous barrier)
         if (blockIdx.x == 0)
             for (int k = tid; k < B; k += nthr) {
@@ -607,7 +666,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             if (E.learning) theta_s[tid] = theta_s[tid] + E.theta_plus * (float)M.cnt[tid];
             M.cnt[tid] = 0;
         }
+        PROF(9)  // slot clear, theta update, sync
         if (!grid_barrier_fast(Q.bar, G, gen, Q.err, Q.dbg & 1)) return;
+        PROF(10)  // grid barrier
     }
 
     // ---- epilogue: normalize() on the tile (network.py:464-465), write everything back -----
@@ -619,7 +680,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             const int c = idx / TJ, jj = idx % TJ;
             float a = 0.0f;
             const int i1 = min((c + 1) * chunk, P);
-            for (int i = c * chunk; i < i1; ++i) { const float x = W[i * TJ + jj]; a = a + (C.norm_abs ? fabsf(x) : x); }
+            for (int i = c * chunk; i < i1; ++i) { const float x = W[i * WS + jj]; a = a + (C.norm_abs ? fabsf(x) : x); }
             part[idx] = a;
         }
         __syncthreads();
@@ -630,12 +691,12 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             part[SNN_NORM_CHUNKS * TJ + tid] = C.norm / tot;
         }
         __syncthreads();
-        for (int idx = tid; idx < P * TJ; idx += nthr) W[idx] = W[idx] * part[SNN_NORM_CHUNKS * TJ + (idx % TJ)];
+        for (int idx = tid; idx < P * TJ; idx += nthr) { const int i = idx / TJ, jj = idx % TJ; W[i * WS + jj] = W[i * WS + jj] * part[SNN_NORM_CHUNKS * TJ + jj]; }
         __syncthreads();
     }
     for (int idx = tid; idx < P * TJ; idx += nthr) {
         const int i = idx / TJ, jj = idx % TJ;
-        if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[idx];
+        if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[i * WS + jj];
     }
     for (int jj = tid; jj < TJ; jj += nthr)
         if (j0 + jj < n) E.theta[j0 + jj] = theta_s[jj];
@@ -651,6 +712,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 I.s[k] = (sIprev >> c) & 1u;
             }
     }
+    PROF(11)  // epilogue (partial)
+    if (Q.prof && tid == 0)
+        for (int k = 0; k < NPROF; ++k) { Q.prof[blockIdx.x * NPROF + k] = pc[k]; Q.prof[(160 + blockIdx.x) * NPROF + k] = pm[k]; }
     for (int o = 0; o < own; ++o) {
         const int bo = blockIdx.x + o * (int)G;
         if (bo < B) {
@@ -808,7 +872,7 @@ cudaError_t launch_tj(const FusedParams &Q, const Match &m, cudaStream_t stream)
     return cudaLaunchCooperativeKernel((void *)snn_dc_fused_window<TJ, BW>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
 }
 
-struct WsLayout { size_t bar, inS, inT, evS, win, sisum, xpub, total; };
+struct WsLayout { size_t bar, inS, inT, evS, win, sisum, xpub, prof, total; };
 WsLayout ws_layout(const Match &m, int T, int B, int P) {
     WsLayout L; size_t o = 0;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -819,6 +883,7 @@ WsLayout ws_layout(const Match &m, int T, int B, int P) {
     L.win = o; o += al(sizeof(unsigned long long) * 3 * B);
     L.sisum = o; o += al(sizeof(unsigned int) * 3 * B);
     L.xpub = o; o += al(sizeof(float) * 2 * (size_t)B * P);
+    L.prof = o; o += al(sizeof(long long) * 320 * NPROF);
     L.total = o;
     return L;
 }
@@ -855,6 +920,8 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
     Q.win = (unsigned long long *)(ws + WL.win); Q.sisum = (unsigned int *)(ws + WL.sisum);
     Q.xpub = (float *)(ws + WL.xpub); Q.bar = (unsigned int *)(ws + WL.bar); Q.err = opts->err_flag;
+    const bool prof = getenv("SNN_B200_PROF") != nullptr;
+    Q.prof = prof ? (long long *)(ws + WL.prof) : nullptr;
     if (cudaMemsetAsync(Q.bar, 0, sizeof(unsigned int) * 96, stream) != cudaSuccess) return SNN_ERR_CUDA;
     snn_dc_prepass<<<T + 1, 256, sizeof(uint32_t) * (size_t)B * m.SW, stream>>>(Q, m.BW);
     cudaError_t e = cudaGetLastError();
@@ -877,6 +944,32 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     if (e != cudaSuccess) {
         fprintf(stderr, "libsnn_b200: fused DC2015 window launch failed: %s\n", cudaGetErrorString(e));
         return SNN_ERR_CUDA;
+    }
+    if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
+        static const char *names[NPROF] = {"prologue", "A exchange+stage", "mbar wait", "B finalise", "C mark+compact", "C items",
+                                           "reset+theta", "D gather+neurons", "atomics+publish", "clear+theta", "grid barrier", "epilogue"};
+        cudaStreamSynchronize(stream);
+        static long long hostp[320 * NPROF];
+        cudaMemcpy(hostp, Q.prof, sizeof(long long) * 320 * NPROF, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[snn_b200 prof] grid=%d T=%d (cycles per timestep, thread 0 of each CTA: min / mean / max)\n", m.grid, T);
+        for (int k = 0; k < NPROF; ++k) {
+            double sum = 0, mx = 0, mn = 1e300;
+            for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[g * NPROF + k]; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
+            const double div = (k == 0 || k == NPROF - 1) ? 1.0 : (double)T;
+            double smx = 0, smean = 0;
+            for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[(160 + g) * NPROF + k]; smx = v > smx ? v : smx; smean += v / m.grid; }
+            fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   worst single step: mean over CTAs %8.0f, max %8.0f\n", names[k], mn / div,
+                    sum / m.grid / div, mx / div, smean, smx);
+        }
+        {
+            double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
+            for (int g = 0; g < m.grid; ++g) {
+                double v = 0;
+                for (int k = 1; k <= 9; ++k) v += (double)hostp[g * NPROF + k];
+                sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
+            }
+            fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
+        }
     }
     if (launches) *launches = 2;  // pre-pass + persistent window kernel
     return SNN_OK;
