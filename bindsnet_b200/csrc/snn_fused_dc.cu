@@ -669,6 +669,12 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         PROF(9)  // slot clear, theta update, sync
         if (!grid_barrier_fast(Q.bar, G, gen, Q.err, Q.dbg & 1)) return;
         PROF(10)  // grid barrier
+        if (Q.prof && tid == 0 && t >= 100 && t < 132) {
+            long long w = 0;
+            for (int k = 1; k <= 9; ++k) w += pc[k];
+            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 0] = w;       // cumulative work up to step t
+            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 1] = pc[10];  // cumulative barrier wait
+        }
     }
 
     // ---- epilogue: normalize() on the tile (network.py:464-465), write everything back -----
@@ -883,7 +889,7 @@ WsLayout ws_layout(const Match &m, int T, int B, int P) {
     L.win = o; o += al(sizeof(unsigned long long) * 3 * B);
     L.sisum = o; o += al(sizeof(unsigned int) * 3 * B);
     L.xpub = o; o += al(sizeof(float) * 2 * (size_t)B * P);
-    L.prof = o; o += al(sizeof(long long) * 320 * NPROF);
+    L.prof = o; o += al(sizeof(long long) * (320 * NPROF + 2 * 32 * 160 + 640));
     L.total = o;
     return L;
 }
@@ -960,6 +966,22 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
             for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[(160 + g) * NPROF + k]; smx = v > smx ? v : smx; smean += v / m.grid; }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   worst single step: mean over CTAs %8.0f, max %8.0f\n", names[k], mn / div,
                     sum / m.grid / div, mx / div, smean, smx);
+        }
+        {   // per-step trace (steps 101..131): how much of the barrier wait is imbalance?
+            static long long tr[2 * 32 * 160];
+            cudaMemcpy(tr, Q.prof + 320 * NPROF, sizeof(tr), cudaMemcpyDeviceToHost);
+            double s_maxw = 0, s_meanw = 0, s_minb = 0, s_meanb = 0; int cnt = 0;
+            for (int st = 1; st < 32; ++st) {
+                double maxw = 0, meanw = 0, minb = 1e300, meanb = 0;
+                for (int g = 0; g < m.grid; ++g) {
+                    const double w = (double)(tr[(st * 160 + g) * 2] - tr[((st - 1) * 160 + g) * 2]);
+                    const double bw = (double)(tr[(st * 160 + g) * 2 + 1] - tr[((st - 1) * 160 + g) * 2 + 1]);
+                    maxw = w > maxw ? w : maxw; meanw += w / m.grid; minb = bw < minb ? bw : minb; meanb += bw / m.grid;
+                }
+                s_maxw += maxw; s_meanw += meanw; s_minb += minb; s_meanb += meanb; ++cnt;
+            }
+            fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA %.0f, barrier wait mean %.0f, min %.0f\n",
+                    s_meanw / cnt, s_maxw / cnt, s_meanb / cnt, s_minb / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;

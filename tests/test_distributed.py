@@ -1,0 +1,101 @@
+"""World-size-2 gloo test of the multi-GPU window combine (bindsnet_b200/distributed.py) on CPU:
+two ranks, each a replica on its batch shard driven by the oracle, one all-reduce of dW + dtheta
+per window — checked against the same combination computed in one process from independent
+oracle replicas (the multi-GPU oracle of SURVEY.md §8e)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _make(B, n=40, seed=3):
+    from bindsnet_b200.models import DiehlAndCook2015
+
+    g = torch.Generator().manual_seed(seed)
+    net = DiehlAndCook2015(n_inpt=196, n_neurons=n, batch_size=B, inpt_shape=(1, 14, 14), inh=60.0, norm=20.0)
+    with torch.no_grad():
+        net.connections[("X", "Ae")].w.copy_(0.3 * torch.rand(196, n, generator=g))
+        net.layers["Ae"].theta.copy_(0.5 * torch.rand(n, generator=g))
+    return net
+
+
+def _inputs(T=60, B=8, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return torch.bernoulli(0.08 * torch.ones(T, B, 1, 14, 14), generator=g).byte()
+
+
+def _patch_cpu_combine():
+    """The combine kernels are CUDA-only; on CPU ranks route them to the oracle's restatement."""
+    import ctypes as C
+    from bindsnet_b200 import _backend
+    from oracle import oracle
+
+    def prepare(w, w0, dw):
+        dw.copy_(w - w0)
+
+    def apply(w, w0, dws, has_clamp, wmin, wmax, has_norm, norm_abs, norm):
+        assert oracle.lib().snn_oracle_delta_apply(w.data_ptr(), w0.data_ptr(), dws.contiguous().data_ptr(), w.shape[0],
+                                                   w.shape[1], int(has_clamp), float(wmin), float(wmax), int(has_norm),
+                                                   int(norm_abs), float(norm)) == 0
+
+    _backend.delta_prepare, _backend.delta_apply = prepare, apply
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bindsnet_b200.distributed import ShardedWindowRunner
+    from oracle.oracle import OracleBackend
+
+    _patch_cpu_combine()
+    x = _inputs()
+    shard = x[:, rank * 4:(rank + 1) * 4]
+    net = _make(4)
+    with OracleBackend():
+        runner = ShardedWindowRunner(net)
+        runner.run({"X": shard}, time=60, one_spike_seed=17 + rank)
+        net.reset_state_variables()
+        runner.run({"X": shard}, time=60, one_spike_seed=27 + rank)
+    torch.save({"w": net.connections[("X", "Ae")].w.detach().clone(), "theta": net.layers["Ae"].theta.clone()},
+               os.path.join(out, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_window_combine_matches_replica_oracle(tmp_path):
+    port = 29500 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt"); r1 = torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0["w"], r1["w"]) and torch.equal(r0["theta"], r1["theta"]), "ranks diverged"
+
+    # single-process oracle of the same procedure: independent replicas + one exchange per window
+    from oracle.oracle import OracleBackend
+    from oracle import oracle
+
+    x = _inputs()
+    nets = [_make(4), _make(4)]
+    w = nets[0].connections[("X", "Ae")].w.detach().clone()
+    th = nets[0].layers["Ae"].theta.clone()
+    with OracleBackend():
+        for window, seed0 in enumerate((17, 27)):
+            dws, dths = [], []
+            for r, net in enumerate(nets):
+                with torch.no_grad():
+                    net.connections[("X", "Ae")].w.copy_(w); net.layers["Ae"].theta.copy_(th)
+                if window:
+                    net.reset_state_variables()
+                net.run({"X": x[:, r * 4:(r + 1) * 4]}, time=60, one_spike_seed=seed0 + r, b200_normalize=False)
+                dws.append(net.connections[("X", "Ae")].w.detach() - w)
+                dths.append(net.layers["Ae"].theta - th)
+            dsum = (dws[0] + dws[1]).contiguous()
+            wn = torch.empty_like(w)
+            assert oracle.lib().snn_oracle_delta_apply(wn.data_ptr(), w.data_ptr(), dsum.data_ptr(), 196, 40, 1, 0.0, 1.0, 1, 0, 20.0) == 0
+            w, th = wn, th + (dths[0] + dths[1])
+    assert np.array_equal(r0["w"].numpy(), w.numpy())
+    assert np.array_equal(r0["theta"].numpy(), th.numpy())

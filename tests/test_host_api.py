@@ -1,0 +1,170 @@
+"""Host-side logic (plan building, reference API quirks) exercised on CPU through the oracle
+backend — mirrors what the reference's own tests check (test/network/test_network.py,
+test_monitors.py, test_nodes.py, test/models/test_models.py) plus the run() semantics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from bindsnet_b200 import _abi, _backend
+from bindsnet_b200.learning import NoOp, PostPre, WeightDependentPostPre, MSTDP
+from bindsnet_b200.models import DiehlAndCook2015, DiehlAndCook2015v2, TwoLayerNetwork
+from bindsnet_b200.network import Network, load
+from bindsnet_b200.network.monitors import Monitor
+from bindsnet_b200.network.nodes import DiehlAndCookNodes, IFNodes, Input, LIFNodes
+from bindsnet_b200.network.topology import Connection, Conv2dConnection, MulticompartmentConnection
+from bindsnet_b200.network.topology_features import Weight
+from oracle.oracle import OracleBackend
+
+
+def test_model_wiring_matches_reference_tests():
+    # test/models/test_models.py:6-67
+    net = TwoLayerNetwork(n_inpt=50, n_neurons=32)
+    assert isinstance(net.layers["X"], Input) and isinstance(net.layers["Y"], LIFNodes)
+    assert net.connections[("X", "Y")].w.shape == (50, 32)
+    dc = DiehlAndCook2015(n_inpt=50, n_neurons=20, exc=22.5, inh=17.5)
+    assert isinstance(dc.layers["Ae"], DiehlAndCookNodes) and isinstance(dc.layers["Ai"], LIFNodes)
+    assert set(dc.connections) == {("X", "Ae"), ("Ae", "Ai"), ("Ai", "Ae")}
+    assert torch.equal(dc.connections[("Ae", "Ai")].w, 22.5 * torch.eye(20))
+    assert isinstance(dc.connections[("X", "Ae")], MulticompartmentConnection)
+    v2 = DiehlAndCook2015v2(n_inpt=50, n_neurons=20)
+    assert set(v2.connections) == {("X", "Y"), ("Y", "Y")}
+
+
+def test_nodes_initial_state_like_reference():
+    # test/network/test_nodes.py:17-59
+    for cls in (LIFNodes, DiehlAndCookNodes):
+        l = cls(n=100, traces=True)
+        l.compute_decays(1.0); l.set_batch_size(3)
+        assert l.s.shape == (3, 100) and not l.s.any()
+        assert torch.all(l.v == l.rest) and torch.all(l.x == 0) and torch.all(l.refrac_count == 0)
+    # decays are exp(-dt/tc) evaluated in fp32 like nodes.py:129-131,546-548
+    l = LIFNodes(n=4, tc_decay=100.0)
+    l.compute_decays(1.0)
+    assert float(l.decay) == float(torch.exp(-torch.tensor(1.0) / torch.tensor(100.0)))
+
+
+def test_unsupported_reference_features_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        IFNodes(n=10)
+    with pytest.raises(NotImplementedError):
+        Conv2dConnection(None, None, 3)
+    X, Y = Input(n=4, traces=True), LIFNodes(n=4, traces=True)
+    with pytest.raises(NotImplementedError):
+        Connection(X, Y, update_rule=MSTDP)
+    with pytest.raises(NotImplementedError):
+        Connection(X, Y, w_dtype=torch.float16)
+    net = TwoLayerNetwork(n_inpt=8, n_neurons=4)
+    with pytest.raises(NotImplementedError):
+        net.run({"X": torch.zeros(3, 1, 8)}, time=3, one_step=True)
+    with pytest.raises(AssertionError):
+        net.run([torch.zeros(3, 1, 8)], time=3)
+
+
+def test_batch_size_inference_resets_state_and_monitor_shapes():
+    # network.py:329-353; test/network/test_monitors.py:8-84
+    net = TwoLayerNetwork(n_inpt=30, n_neurons=12, reduction=torch.sum)
+    net.add_monitor(Monitor(net.layers["Y"], ["s", "v"], time=20), "Y")
+    net.add_monitor(Monitor(net.layers["X"], ["s"], time=20), "X")
+    g = torch.Generator().manual_seed(0)
+    with OracleBackend():
+        net.run({"X": torch.bernoulli(0.3 * torch.ones(20, 30), generator=g)}, time=20)  # [T, n] -> batch 1
+        assert net.batch_size == 1 and net.monitors["Y"].get("s").shape == (20, 1, 12)
+        assert net.monitors["Y"].get("v").shape == (20, 1, 12) and net.monitors["X"].get("s").shape == (20, 1, 30)
+        net.layers["Y"].v.fill_(-55.0)
+        net.run({"X": torch.bernoulli(0.3 * torch.ones(20, 5, 30), generator=g).byte()}, time=20)  # batch 5
+        assert net.batch_size == 5 and net.layers["Y"].v.shape == (5, 12)
+        assert net.monitors["Y"].get("s").shape == (20, 5, 12)
+        # X's monitor returns exactly the input spikes
+        x = torch.bernoulli(0.3 * torch.ones(20, 5, 30), generator=g).byte()
+        net.run({"X": x}, time=20)
+        assert torch.equal(net.monitors["X"].get("s"), x.bool())
+
+
+def test_stepwise_fallback_equals_fused_window():
+    """A monitor on a variable the kernels do not record (x) makes run() fall back to one-step
+    windows; the result must equal the fused window bit for bit (same tie-break stream)."""
+    def build():
+        torch.manual_seed(1)
+        return DiehlAndCook2015(n_inpt=64, n_neurons=24, batch_size=3, inpt_shape=(1, 8, 8), inh=60.0)
+    g = torch.Generator().manual_seed(2)
+    x = torch.bernoulli(0.15 * torch.ones(40, 3, 1, 8, 8), generator=g).byte()
+    a, b = build(), build()
+    b.add_monitor(Monitor(b.layers["Ae"], ["x", "s"], time=40), "trace")
+    with OracleBackend():
+        a.run({"X": x}, time=40, one_spike_seed=9)
+        b.run({"X": x}, time=40, one_spike_seed=9)
+    for name in ("Ae", "Ai"):
+        assert torch.equal(a.layers[name].v, b.layers[name].v) and torch.equal(a.layers[name].s, b.layers[name].s)
+    assert torch.equal(a.connections[("X", "Ae")].w, b.connections[("X", "Ae")].w)
+    assert b.monitors["trace"].get("x").shape == (40, 3, 24)
+
+
+def test_learning_off_freezes_weights_and_theta():
+    net = DiehlAndCook2015(n_inpt=64, n_neurons=16, batch_size=2, inpt_shape=(1, 8, 8))
+    net.train(False)
+    w0 = net.connections[("X", "Ae")].w.detach().clone()
+    net.layers["Ae"].theta.fill_(0.5)
+    with OracleBackend():
+        net.run({"X": torch.ones(30, 2, 1, 8, 8, dtype=torch.uint8)}, time=30)
+    # no STDP; the end-of-run normalize still runs, learning or not (network.py:464-465)
+    assert torch.allclose(net.connections[("X", "Ae")].w, w0 * (78.4 / w0.sum(0)), rtol=1e-5)
+    assert torch.all(net.layers["Ae"].theta == 0.5)
+
+
+def test_reset_state_variables_keeps_theta_and_w():
+    # nodes.py:1113-1120: theta is not reset
+    net = DiehlAndCook2015(n_inpt=64, n_neurons=16, batch_size=2, inpt_shape=(1, 8, 8), inh=60.0)
+    with OracleBackend():
+        net.run({"X": torch.ones(40, 2, 1, 8, 8, dtype=torch.uint8)}, time=40)
+    theta = net.layers["Ae"].theta.clone(); w = net.connections[("X", "Ae")].w.detach().clone()
+    assert theta.abs().sum() > 0
+    net.reset_state_variables()
+    assert torch.equal(net.layers["Ae"].theta, theta) and torch.equal(net.connections[("X", "Ae")].w, w)
+    assert torch.all(net.layers["Ae"].v == -65.0) and not net.layers["Ae"].s.any() and torch.all(net.layers["X"].x == 0)
+
+
+def test_save_load_clone_round_trip(tmp_path):
+    # test/network/test_network.py:15-68
+    net = DiehlAndCook2015(n_inpt=16, n_neurons=8, batch_size=1, inpt_shape=(1, 4, 4))
+    net.add_monitor(Monitor(net.layers["Ae"], ["s"], time=5), "m")
+    p = tmp_path / "net.pt"
+    net.save(str(p))
+    net2 = load(str(p), learning=False)
+    assert net2.dt == net.dt and net2.learning is False
+    assert list(net2.layers) == list(net.layers) and list(net2.connections) == list(net.connections)
+    assert torch.equal(net2.connections[("X", "Ae")].w, net.connections[("X", "Ae")].w)
+    net3 = net.clone()
+    assert list(net3.monitors) == ["m"]
+
+
+def test_squeeze_reduction_pitfall_is_reported():
+    # TwoLayerNetwork builds its rule with reduction=squeeze (batch_size==1 at construction)
+    net = TwoLayerNetwork(n_inpt=10, n_neurons=4)
+    with OracleBackend():
+        net.run({"X": torch.zeros(3, 1, 10, dtype=torch.uint8)}, time=3)   # batch 1: fine
+        with pytest.raises(RuntimeError, match="squeeze"):
+            net.run({"X": torch.zeros(3, 2, 10, dtype=torch.uint8)}, time=3)
+
+
+def test_structure_hints_detected_for_static_matrices():
+    from bindsnet_b200.network import _plan
+
+    net = DiehlAndCook2015(n_inpt=16, n_neurons=8, batch_size=2, inpt_shape=(1, 4, 4), exc=22.5, inh=120.0)
+    plan, _ = _plan.build_net(net, 2, {}, {}, {}, {}, {})
+    kinds = [(plan.conns[i].structure, plan.conns[i].structure_val) for i in range(3)]
+    assert kinds[0][0] == _abi.SNN_W_DENSE
+    assert kinds[1] == (_abi.SNN_W_DIAG, 22.5) and kinds[2] == (_abi.SNN_W_OFFDIAG, -120.0)
+    with torch.no_grad():
+        net.connections[("Ai", "Ae")].w[0, 1] = -1.0            # in-place edit bumps Tensor._version
+    plan, _ = _plan.build_net(net, 2, {}, {}, {}, {}, {})
+    assert plan.conns[2].structure == _abi.SNN_W_DENSE
+
+
+def test_nonbinary_input_flag_from_oracle_backend():
+    net = TwoLayerNetwork(n_inpt=6, n_neurons=3)
+    x = torch.zeros(4, 1, 6, dtype=torch.uint8); x[1, 0, 2] = 5
+    with OracleBackend() as ob:
+        net.run({"X": x}, time=4)
+    assert ob.err & _abi.SNN_ERR_NONBINARY
