@@ -52,7 +52,7 @@ struct FusedParams {
                               //               then u16 idx[B][EV_CAP] ascending, padded with P
     unsigned long long *win;  // [3][B] arg-max keys, slot t % 3
     unsigned int *sisum;      // [3][B] Ai spike counts, slot t % 3 (slot 2 = step -1)
-    float *xpub;              // [2][B][P] published input traces, slot t & 1
+    float *xpub;              // [3][B][P] published input traces, slot t % 3
     unsigned int *bar;        // [0] arrivals (monotonic), [32] generation
     int32_t *err;
     long long *prof;          // profiling only (env SNN_B200_PROF): [grid][NPROF] phase cycles of thread 0
@@ -90,51 +90,28 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
     return v;
 }
 
-// Grid barrier on ONE monotonic arrival counter: a release reduction to arrive, relaxed polling
-// of the same word until nblocks * generation arrivals are in, then one acquire fence.
-// (scripts/barrier_bench.cu: 1.2 us on B200 against 1.9 us for the counter + generation-word
-// scheme and 1.3 us for cooperative groups' grid.sync; 0.85 us is the no-ordering floor.)
-// All cross-CTA data is read with ld.global.cg, so no L1 invalidation is needed.
-__device__ __forceinline__ bool grid_barrier_fast(unsigned int *bar, unsigned int nblocks, unsigned int &gen, int32_t *err, bool nowait = false) {
-    __shared__ int s_ok;
-    __syncthreads();
-    gen += 1;
-    if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        int ok = 1;
-        if (!nowait) {
-            const unsigned int target = nblocks * gen;
-            const long long t0 = clock64();
-            while ((int)(ld_relaxed_u32(bar) - target) < 0) {
-                if (clock64() - t0 > 4000000000LL) {
-                    if (err) atomicOr(err, SNN_ERR_BARRIER);
-                    ok = 0;
-                    break;
-                }
-            }
-            asm volatile("fence.acquire.gpu;" ::: "memory");
-        }
-        s_ok = ok;
-    }
-    __syncthreads();
-    return s_ok != 0;
-}
+// The grid barrier is ONE monotonic arrival counter: a release reduction to arrive, relaxed polling
+// of the same word until nblocks * generation arrivals are in, then one acquire fence
+// (scripts/barrier_bench.cu: 1.2 us on B200 against 1.9 us for a counter + generation-word scheme
+// and 1.3 us for cooperative groups' grid.sync; 0.85 us is the no-ordering floor).  It is split
+// into arrive / wait inside the time loop.  All cross-CTA data is read with ld.global.cg, so no
+// L1 invalidation is needed.
 
 struct Misc {  // small per-step scratch (lives in shared memory)
     uint64_t mbar[2];
-    int cnt[32];            // candidates per column (theta update)
-    uint32_t wmask[32][8];  // winners: per column, bit mask over samples
+    int cnt[2][32];         // candidates per column (theta update), double-buffered by step parity
+    uint32_t wmask[32][8];  // winners of the step being finalised: per column, bit mask over samples
     uint32_t nz4[8][8];     // per column group: samples with a non-zero Ae trace in that group
     int nlive;              // live (sample, column group) pairs, listed in live[]
-    int nwork;              // (row, column group) items of this step's STDP work list
-    int ncand;              // samples with a candidate in this tile this step
-    int candb[XR];          // ... the first XR of them (their input-trace rows get staged)
-    int winany;
-    uint32_t colwin;        // bit j: column j has a winner this step
-    int8_t wslot[256];      // sample -> staged row slot, -1 = not staged
+    int ncand[2];           // samples with a candidate in this tile (by step parity)
+    int candb[2][XR];       // ... the first XR of them: their input-trace rows get staged
+    uint32_t candgrp[2];    // column groups holding a candidate (by step parity)
+    uint32_t colwin;        // bit j: column j has a winner in the step being finalised
+    int abort;              // barrier time-out: leave the time loop
+    int16_t wslot[256];     // sample -> (step tag << 3 | staged row slot)
 };
 
-struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, live, touched, work, misc, total; };
+struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, live, claim, misc, total; };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline int ev_block_bytes(int B) { return (int)(al16(2 * (size_t)B) + 2 * (size_t)B * EV_CAP); }
@@ -151,8 +128,7 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, 
     L.xown = o; o += al16(sizeof(float) * (size_t)own * P);
     L.theta = o; o += al16(sizeof(float) * 32);
     L.live = o; o += al16(sizeof(uint16_t) * (size_t)B * (TJ / 4));
-    L.touched = o; o += al16(sizeof(uint32_t) * (size_t)(TJ / 4) * ((P + 31) / 32));
-    L.work = o; o += al16(sizeof(uint16_t) * (size_t)P * (TJ / 4));
+    L.claim = o; o += al16(sizeof(uint16_t) * (size_t)P * (TJ / 4));
     L.misc = o; o += al16(sizeof(Misc));
     L.total = o;
     return L;
@@ -160,6 +136,13 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, 
 
 // TJ: neurons per CTA (4 per thread); BW: 32-bit words of a per-pixel sample mask (4 -> B <= 128,
 // 8 -> B <= 256).  Threads = B * TJ/4 <= 32 * BW * TJ/4.
+//
+// Software pipeline of one timestep t (the grid barrier is split into arrive / wait so that its
+// L2 round trips overlap the bulk of the STDP work):
+//   wait(t-1) | late(t-1): exchange read, winners, traces + STDP of column groups that held a
+//   candidate | D(t): gather, Ae/Ai update, candidates -> atomics | arrive(t) | early(t): traces +
+//   STDP pre term of the column groups WITHOUT a candidate (their step-t state is already final),
+//   input trace of step t+1 published
 template <int TJ, int BW>
 __global__ void __launch_bounds__((8 * BW * TJ < 1024 ? 8 * BW * TJ : 1024), 1)
 snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
@@ -179,26 +162,24 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     float *xown = (float *)(smem + SL.xown);
     float *theta_s = (float *)(smem + SL.theta);
     uint16_t *live = (uint16_t *)(smem + SL.live);
-    uint32_t *touched = (uint32_t *)(smem + SL.touched);
-    uint16_t *work = (uint16_t *)(smem + SL.work);
+    uint16_t *claim = (uint16_t *)(smem + SL.claim);
     Misc &M = *(Misc *)(smem + SL.misc);
-    const int PW = (P + 31) >> 5;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int b = tid / CG, cg = tid % CG;   // state ownership: sample b, neurons jc..jc+3
     const bool act = b < B;
     const int j0 = blockIdx.x * TJ;
     const int jc = j0 + 4 * cg;
-    const int NRS = nthr / CG, rslot = tid / CG;  // row slots of the STDP row loop
     const snn_layer_t &E = Q.E, &I = Q.I, &X = Q.X;
     const snn_conn_t &C = Q.C;
     const bool stdp = C.rule >= SNN_RULE_POSTPRE;
     const bool wdep = C.rule == SNN_RULE_WDEP_POSTPRE;
     const bool pre_on = stdp && C.nu0 != 0.0f, post_on = stdp && C.nu1 != 0.0f;
     const bool decay_on = C.weight_decay != 0.0f && C.weight_decay != 1.0f;
-    const bool update_on = Q.learning && C.rule != SNN_RULE_NONE && (stdp || decay_on);
+    const bool update_on = Q.learning && C.rule != SNN_RULE_NONE && (stdp || decay_on) && !(Q.dbg & 2);
     const bool stage_on = update_on && post_on && X.traces;
     const float Bf = (float)B;
+    const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
     const int evblk = (int)al16((size_t)Q.SB);  // stride between the two staged list blocks
     const int cntb = (int)al16(2 * (size_t)B);  // bytes of the count array inside a block
     float *Wc = W + 4 * cg;                     // my 4 columns of row 0
@@ -217,6 +198,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         W[i * WS + jj] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
     }
     for (int jj = tid; jj < 32; jj += nthr) theta_s[jj] = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
+    for (int k = tid; k < P * CG; k += nthr) claim[k] = 0xffffu;
     if (tid == 0) {
         // rep[m] = m-fold sequential sum of the Ai->Ae weight: what the reference's dense sum
         // over k of sI[b,k] * w_ie[k,j] evaluates to when m inhibitory neurons (other than j) spike
@@ -226,10 +208,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         mbar_init(&M.mbar[0], 1);
         mbar_init(&M.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        M.ncand = 0; M.winany = 0; M.colwin = 0; M.nlive = 0; M.nwork = 0;
+        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.nlive = 0; M.abort = 0;
     }
-    for (int k = tid; k < 64; k += nthr) (&M.nz4[0][0])[k] = 0;
-    for (int k = tid; k < 32; k += nthr) M.cnt[k] = 0;
+    for (int k = tid; k < 64; k += nthr) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
     for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
     for (int k = tid; k < 256; k += nthr) M.wslot[k] = -1;
     if (X.traces)
@@ -265,87 +246,199 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     }
 
     const uint32_t bytesE = (uint32_t)Q.SB, bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
-    if (tid == 0) {  // stage slot 0 (spikes of step -1 = the Input layer's incoming spike state)
+    if (tid == 0) {  // stage slot 0 (spikes of step -1) and slot 1 (spikes of step 0)
         mbar_expect_tx(&M.mbar[0], bytesE + bytesT);
         bulk_g2s(evb, Q.evS, bytesE, &M.mbar[0]);
         bulk_g2s(inT, Q.inT, bytesT, &M.mbar[0]);
+        mbar_expect_tx(&M.mbar[1], bytesE + bytesT);
+        bulk_g2s(evb + evblk, Q.evS + Q.SB, bytesE, &M.mbar[1]);
+        bulk_g2s(inT + P * BW, Q.inT + (size_t)P * BW, bytesT, &M.mbar[1]);
     }
     uint32_t ph0 = 0, ph1 = 0;
+    // input trace of step 0 for the samples this CTA owns, published in xpub slot 0
+    auto publish_trace = [&](int step) {
+        if (!X.traces || (Q.dbg & 8)) return;
+        for (int o = 0; o < own; ++o) {
+            const int bo = blockIdx.x + o * (int)G;
+            if (bo < B) {
+                const uint32_t *srow = Q.inS + ((size_t)(step + 1) * B + bo) * Q.SW;
+                float4 *dst = (float4 *)(Q.xpub + ((size_t)(step % 3) * B + bo) * P);
+                float4 *xo = (float4 *)(xown + o * P);
+                for (int i4 = tid; i4 < (P >> 2); i4 += nthr) {
+                    const uint32_t bits = __ldg(srow + (i4 >> 3)) >> ((i4 & 7) * 4);
+                    float4 x = xo[i4];
+                    x.x = trace_step(x.x, bits & 1u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    x.y = trace_step(x.y, bits & 2u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    x.z = trace_step(x.z, bits & 4u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    x.w = trace_step(x.w, bits & 8u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    xo[i4] = x;
+                    dst[i4] = x;
+                }
+            }
+        }
+    };
+    publish_trace(0);
     __syncthreads();
 
-    PROF(0)  // prologue
-    // =====================================================================================
-    for (int t = 0; t <= T; ++t) {
-        const int buf = t & 1;
-        const unsigned char *cE = evb + buf * evblk;              // spikes of step t-1: lists
-        const uint4 *cT = (const uint4 *)(inT + buf * P * BW);    // spikes of step t-1: per pixel
-
-        // prefetch slot t+1 into the other buffer (its readers finished before the last barrier)
-        if (tid == 0 && t + 1 <= T) {
-            const int nb = buf ^ 1;
-            mbar_expect_tx(&M.mbar[nb], bytesE + bytesT);
-            bulk_g2s(evb + nb * evblk, Q.evS + (size_t)(t + 1) * Q.SB, bytesE, &M.mbar[nb]);
-            bulk_g2s(inT + nb * P * BW, Q.inT + (size_t)(t + 1) * P * BW, bytesT, &M.mbar[nb]);
+    // One STDP item = (row i, column group c4): all 4 columns of the group get the pre term of
+    // `step` (spike masks / lists in buffer `sb`) — U = sum over the samples with a spike at pixel
+    // i and a live trace in the group, ascending — then decay + clamp.  Columns in `skipcols`
+    // (winner columns, handled whole by the column pass) are left untouched.
+    auto stdp_item = [&](int i, int c4, int sb, uint32_t skipcols) {
+        uint32_t m[BW];
+        uint32_t anym = 0;
+        if (pre_on) {
+            const uint4 *cT = (const uint4 *)(inT + sb * P * BW);
+            const uint4 q0 = cT[i * (BW / 4)];
+            const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+            if (BW == 8) {
+                const uint4 q1 = cT[i * (BW / 4) + 1];
+                const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+            }
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) anym |= m[g];
         }
+        const bool pre_t = anym != 0u;
+        float *wp = W + i * WS + 4 * c4;
+        const float4 w4 = *(const float4 *)wp;
+        float U[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pre_t) {
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = m[g];
+                while (mm) {
+                    const int bb = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
+                    U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                }
+            }
+            if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
+        }
+        const uint32_t skip = (skipcols >> (4 * c4)) & 0xFu;
+        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        #pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if ((skip >> c) & 1u) continue;
+            if (!wdep) {
+                // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic rule's
+                // missing dt factor is dts = 1)
+                float w = wv[c];
+                if (pre_t) w = w - U[c] * dts;
+                if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+                if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+                wv[c] = w;
+            } else {
+                wv[c] = apply_rule(C, wv[c], U[c], pre_t, 0.0f, false);
+            }
+        }
+        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    };
 
-        // ---- A. exchange results of step t-1 (slot (t-1) % 3; for t = 0 the pre-pass filled it)
+    // STDP pre-term pass of `step` over the column groups selected by `groups` (bit per group).
+    // Items are enumerated from the live (sample, group) pairs x the sample's event list; the
+    // first thread to claim an item (step/stage tag) processes it.  `full`: every row (first
+    // update of the window, weight decay, or a sample whose list overflowed).
+    auto stdp_pass = [&](int step, int sb, uint32_t groups, uint32_t skipcols, bool full, uint16_t tag) {
+        if (!groups) return;
+        if (full) {
+            for (int k = tid; k < P * CG; k += nthr) {
+                const int i = k / CG, c4 = k % CG;
+                if ((groups >> c4) & 1u) stdp_item(i, c4, sb, skipcols);
+            }
+            return;
+        }
+        if (!pre_on) return;
+        const uint16_t *ec = (const uint16_t *)(evb + sb * evblk);
+        const uint16_t *el = (const uint16_t *)(evb + sb * evblk + cntb);
+        const int nl = M.nlive;
+        for (int idx = tid; idx < nl * 16; idx += nthr) {
+            const int lp = live[idx >> 4], e = idx & 15;
+            const int bb = lp / CG, c4 = lp % CG;
+            if (!((groups >> c4) & 1u)) continue;
+            const int cnt = ec[bb];
+            const bool dense = cnt > EV_CAP;  // list overflowed: conservatively visit every row of the group
+            for (int k = e; k < (dense ? P : cnt); k += 16) {
+                const int i = dense ? k : (int)el[bb * EV_CAP + k];
+                // claim (i, c4): 16-bit tags packed two per word
+                uint32_t *cw = (uint32_t *)claim + ((i * CG + c4) >> 1);
+                const int sh = ((i * CG + c4) & 1) * 16;
+                uint32_t old = *cw, assumed;
+                bool mine = false;
+                do {
+                    assumed = old;
+                    if (((assumed >> sh) & 0xffffu) == tag) break;
+                    old = atomicCAS(cw, assumed, (assumed & ~(0xffffu << sh)) | ((uint32_t)tag << sh));
+                    mine = old == assumed;
+                } while (!mine);
+                if (mine) stdp_item(i, c4, sb, skipcols);
+            }
+        }
+    };
+
+    // =====================================================================================
+    PROF(0)  // prologue
+    uint32_t pend = 0;         // my candidates of the step being finalised are still undecided
+    for (int t = 0; t <= T; ++t) {
+        const int buf = t & 1;                                       // slot t   = spikes of step t-1
+        const unsigned char *cE = evb + buf * evblk;
+        const int par = t & 1, ppar = par ^ 1;                      // parity of step t / of step t-1
+
+        // ---- late(t-1): exchange results of step t-1 (slot (t-1) % 3; t = 0: from the pre-pass)
         const int xs = (t + 2) % 3;
         unsigned long long key = 0ull;
         unsigned int isum = 0;
         if (act) {
             isum = __ldcg(Q.sisum + xs * B + b);
-            if (t > 0 && candE) key = __ldcg(Q.win + xs * B + b);
+            if (t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
         }
-        if (t > 0 && stage_on && !(Q.dbg & 16)) {  // speculative: input-trace rows of this tile's candidate samples
-            const int ns = min(M.ncand, XR);
+        const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
+        if (t > 0 && stage_on && lategrp && !(Q.dbg & 16)) {         // input-trace rows of candidate samples
+            const int ns = min(M.ncand[ppar], XR);
             for (int r = 0; r < ns; ++r) {
-                const float4 *src = (const float4 *)(Q.xpub + ((size_t)((t - 1) & 1) * B + M.candb[r]) * P);
+                const float4 *src = (const float4 *)(Q.xpub + ((size_t)((t - 1) % 3) * B + M.candb[ppar][r]) * P);
                 float4 *dst = (float4 *)(xrow + r * P);
                 for (int i4 = tid; i4 < (P >> 2); i4 += nthr) dst[i4] = __ldcg(src + i4);
             }
         }
-        PROF(1)  // A: exchange loads + staging issue
-        // wait for this iteration's spike data (prefetched during the previous iteration)
-        {
-            uint32_t &ph = buf ? ph1 : ph0;
-            while (!mbar_try_wait(&M.mbar[buf], ph)) {}
-            ph ^= 1u;
-        }
-
-        PROF(2)  // mbarrier wait
+        PROF(1)  // exchange loads + staging issue
         if (t > 0) {
-            // ---- B. finalise step t-1: winner (nodes.py:1097-1105), Ae trace (nodes.py:96-103)
             uint32_t sE = 0;
             if (act) {
-                if (E.one_spike) {
-                    if (candE && key != 0ull) {
-                        const int wj = (int)(uint32_t)(key & 0xffffffffull) - jc;
-                        if (wj >= 0 && wj < 4 && ((candE >> wj) & 1u)) sE = 1u << wj;
-                    }
-                } else sE = candE;
-                if (E.traces) {
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], (sE >> c) & 1u, E.trace_decay, E.trace_scale, E.traces_additive);
-                }
-                if (update_on && stdp) {
-                    if (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)
-                        *(float4 *)(tx + b * TJ + 4 * cg) =
-                            make_float4(wdep ? xE[0] : xE[0] * C.nu0, wdep ? xE[1] : xE[1] * C.nu0,
-                                        wdep ? xE[2] : xE[2] * C.nu0, wdep ? xE[3] : xE[3] * C.nu0);
-                    if (sE && !livep) {
-                        livep = true;
-                        atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
-                        live[atomicAdd(&M.nlive, 1)] = (uint16_t)tid;
-                    }
-                    if (sE) {
+                if (pend) {  // candidates of step t-1: winner (nodes.py:1097-1105), then the trace
+                    if (E.one_spike) {
+                        if (key != 0ull) {
+                            const int wj = (int)(uint32_t)(key & 0xffffffffull) - jc;
+                            if (wj >= 0 && wj < 4 && ((candE >> wj) & 1u)) sE = 1u << wj;
+                        }
+                    } else sE = candE;
+                    if (E.traces) {
                         #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if ((sE >> c) & 1u) {
-                                atomicOr(&M.wmask[4 * cg + c][b >> 5], 1u << (b & 31));
-                                atomicOr(&M.colwin, 1u << (4 * cg + c));
-                            }
-                        M.winany = 1;
+                        for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], (sE >> c) & 1u, E.trace_decay, E.trace_scale, E.traces_additive);
                     }
+                    if (update_on && stdp) {
+                        if (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f) {
+                            *(float4 *)(tx + b * TJ + 4 * cg) =
+                                make_float4(wdep ? xE[0] : xE[0] * C.nu0, wdep ? xE[1] : xE[1] * C.nu0,
+                                            wdep ? xE[2] : xE[2] * C.nu0, wdep ? xE[3] : xE[3] * C.nu0);
+                            if (!livep) {
+                                livep = true;
+                                atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
+                                live[atomicAdd(&M.nlive, 1)] = (uint16_t)tid;
+                            }
+                        }
+                        if (sE && post_on) {
+                            #pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if ((sE >> c) & 1u) {
+                                    atomicOr(&M.wmask[4 * cg + c][b >> 5], 1u << (b & 31));
+                                    atomicOr(&M.colwin, 1u << (4 * cg + c));
+                                }
+                        }
+                    }
+                    pend = 0;
                 }
                 // monitors (monitors.py:94-111): spikes / voltages of step t-1
                 if (E.rec_s || I.rec_s || E.rec_v || I.rec_v) {
@@ -362,124 +455,14 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             }
             sEprev = sE;
         }
-        __syncthreads();
-        PROF(3)  // B finalise + sync
-
-        if (t > 0 && update_on && !(Q.dbg & 2)) {
-            // ---- C. learning-rule update of step t-1 on the W tile --------------------------
-            //   U[i,j] = reduce_b sX[b,i] * (xE[b,j]*nu0)   pre term  (MCC_learning.py:234-263)
-            //   V[i,j] = reduce_b xX[b,i] * (sE[b,j]*nu1)   post term (MCC_learning.py:267-299)
-            // then decay + clamp (MCC_learning.py:86-110).  The reference rewrites all of W; only
-            // (row i, column group) items with a pre spike from a sample whose Ae trace is live in
-            // that group, or in a group holding a winner, can change bits — everything else is
-            // skipped, except on the first update of the window (entries may sit outside
-            // [wmin, wmax] after normalize()) or with a weight decay.
-            // Pass 1 marks those items from the (sample, group) pairs with a live trace and the
-            // sample's event list, pass 1b compacts them into a work list, pass 2 runs one
-            // float4 item per thread — no divergence on the sparse structure.
-            const bool full = decay_on || (C.has_clamp && t == 1);
-            const uint32_t colwin = post_on ? M.colwin : 0u;
-            const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
-            const int ntw = CG * PW;
-            if (full) {
-                for (int k = tid; k < P * CG; k += nthr) work[k] = (uint16_t)k;
-                if (tid == 0) M.nwork = P * CG;
-            } else {
-                for (int k = tid; k < ntw; k += nthr) touched[k] = 0u;
-                if (tid == 0) M.nwork = 0;
-                __syncthreads();
-                if (pre_on) {
-                    const uint16_t *ec = (const uint16_t *)cE;
-                    const uint16_t *el = (const uint16_t *)(cE + cntb);
-                    const int nl = M.nlive;
-                    for (int idx = tid; idx < nl * 16; idx += nthr) {
-                        const int lp = live[idx >> 4], e = idx & 15;
-                        const int bb = lp / CG, c4 = lp % CG;
-                        const int cnt = ec[bb];
-                        if (cnt > EV_CAP) {  // dense sample: conservatively mark every row of the group
-                            for (int w = e; w < PW; w += 16) touched[c4 * PW + w] = 0xffffffffu;
-                        } else {
-                            for (int k = e; k < cnt; k += 16) {
-                                const int i = el[bb * EV_CAP + k];
-                                atomicOr(&touched[c4 * PW + (i >> 5)], 1u << (i & 31));
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
-                for (int k = tid; k < ntw; k += nthr) {
-                    const int w = k % PW;
-                    uint32_t bits = touched[k];
-                    if (w == PW - 1 && (P & 31)) bits &= (1u << (P & 31)) - 1u;
-                    if (bits) {
-                        int pos = atomicAdd(&M.nwork, __popc(bits));
-                        const int c4 = k / PW;
-                        while (bits) {
-                            const int i = w * 32 + __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            work[pos++] = (uint16_t)(i * CG + c4);
-                        }
-                    }
-                }
-            }
+        if (t > 0 && update_on && lategrp) {
+            // STDP of step t-1 for the groups that held a candidate: pre term on the listed items,
+            // then every row of each winner column (pre + post term, MCC_learning.py:234-299)
             __syncthreads();
-            PROF(4)  // C mark + compact
-            const int nwork = M.nwork;
-            for (int k = tid; k < nwork; k += nthr) {
-                const int item = work[k];
-                const int i = item / CG, c4 = item % CG;
-                uint32_t m[BW];
-                uint32_t anym = 0;
-                if (pre_on) {
-                    const uint4 q0 = cT[i * (BW / 4)];
-                    const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
-                    m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
-                    if (BW == 8) {
-                        const uint4 q1 = cT[i * (BW / 4) + 1];
-                        const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
-                        m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
-                    }
-                    #pragma unroll
-                    for (int g = 0; g < BW; ++g) anym |= m[g];
-                }
-                const bool pre_t = anym != 0u;
-                float *wp = W + i * WS + 4 * c4;
-                const float4 w4 = *(const float4 *)wp;
-                float U[4] = {0.f, 0.f, 0.f, 0.f};
-                if (pre_t) {
-                    #pragma unroll
-                    for (int g = 0; g < BW; ++g) {
-                        uint32_t mm = m[g];
-                        while (mm) {
-                            const int bb = g * 32 + __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
-                            U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
-                        }
-                    }
-                    if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
-                }
-                const uint32_t mycolwin = (colwin >> (4 * c4)) & 0xFu;
-                float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-                #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if ((mycolwin >> c) & 1u) continue;  // winner column: handled whole by pass 3
-                    if (!wdep) {
-                        // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic
-                        // rule's missing dt factor is dts = 1)
-                        float w = wv[c];
-                        if (pre_t) w = w - U[c] * dts;
-                        if (C.weight_decay != 0.0f) w = w * C.weight_decay;
-                        if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
-                        wv[c] = w;
-                    } else {
-                        wv[c] = apply_rule(C, wv[c], U[c], pre_t, 0.0f, false);
-                    }
-                }
-                *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
-            }
-            // pass 3: columns with a winner get pre + post term on every row, one element per thread
-            if (colwin) __syncthreads();  // pass 2 rewrote whole float4s (winner components unchanged)
+            const uint32_t colwin = M.colwin;
+            const bool full = decay_on || (C.has_clamp && t == 1);
+            stdp_pass(t - 1, buf, lategrp, colwin, full, (uint16_t)(2 * t + 1));
+            if (colwin) __syncthreads();  // items rewrote whole float4s (winner components unchanged)
             for (uint32_t cw = colwin; cw; cw &= cw - 1) {
                 const int j = __ffs(cw) - 1, c4 = j >> 2;
                 for (int i = tid; i < P; i += nthr) {
@@ -503,9 +486,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                         while (mm) {
                             const int bb = g * 32 + __ffs(mm) - 1;
                             mm &= mm - 1;
-                            const int sl = M.wslot[bb];
-                            const float xsv = (sl >= 0) ? xrow[sl * P + i]
-                                                        : __ldcg(Q.xpub + ((size_t)((t - 1) & 1) * B + bb) * P + i);
+                            const int ws = M.wslot[bb];
+                            const float xsv = ((ws >> 3) == ((t - 1) & 0xfff)) ? xrow[(ws & 7) * P + i]
+                                                                                : __ldcg(Q.xpub + ((size_t)((t - 1) % 3) * B + bb) * P + i);
                             V = V + xsv * (wdep ? 1.0f : C.nu1);
                         }
                     }
@@ -523,23 +506,23 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 }
             }
             __syncthreads();
-            if (M.winany) {
+            if (colwin) {
                 for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
+                if (tid == 0) M.colwin = 0;
             }
         }
-        PROF(5)  // C items
-        if (t > 0) {
-            // reset the per-step candidate / winner bookkeeping
-            for (int k = tid; k < B; k += nthr) M.wslot[k] = -1;
-            __syncthreads();
-            if (tid == 0) { M.winany = 0; M.colwin = 0; M.ncand = 0; }
-        }
+        PROF(2)  // late finalise + late STDP
         if (t == T) break;
 
-        // ---- D. step t: theta decay, gather, Ae / Ai update, candidates ---------------------
-        if (tid < TJ && E.learning) theta_s[tid] = theta_s[tid] * E.theta_decay;  // nodes.py:1078-1079
-        __syncthreads();
-        PROF(6)  // reset + theta decay + syncs
+        // ---- D(t): gather, Ae / Ai update, candidates ----------------------------------------
+        {   // this iteration's spike lists (slot t) were prefetched one iteration ago
+            uint32_t &ph = buf ? ph1 : ph0;
+            while (!mbar_try_wait(&M.mbar[buf], ph)) {}
+            ph ^= 1u;
+        }
+        if (tid == 0) { M.ncand[par] = 0; M.candgrp[par] = 0; }
+        __syncthreads();   // late STDP done (W final for step t-1); bookkeeping of parity `par` reset
+        PROF(3)  // mbarrier wait + sync
         uint32_t cand = 0, sI = 0;
         unsigned long long mykey = 0ull;
         int nI = 0;
@@ -575,9 +558,10 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             }
             const float p[4] = {p0, p1, p2, p3};
             const float4 th4 = *(const float4 *)(theta_s + 4 * cg);
-            const float th[4] = {th4.x, th4.y, th4.z, th4.w};
+            float th[4] = {th4.x, th4.y, th4.z, th4.w};
             #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                if (E.learning) th[c] = th[c] * E.theta_decay;  // nodes.py:1078-1079 (stored after the step)
                 if (jc + c < n) {
                     // network.py:225-248: X->Ae first, then Ai->Ae; the latter is rep[#spiking Ai other than j]
                     const int mI = (int)isum - (int)((sIprev >> c) & 1u);
@@ -594,22 +578,29 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     }
                 }
             }
-            if (cand && E.one_spike) {
-                #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if ((cand >> c) & 1u) {
-                        const unsigned long long k2 = snn_one_spike_key(Q.seed, (uint32_t)t + Q.step_offset, (uint32_t)Q.liE,
-                                                                        (uint32_t)b, (uint32_t)(jc + c));
-                        mykey = k2 > mykey ? k2 : mykey;
-                    }
-            }
             if (cand) {
                 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    if ((cand >> c) & 1u) atomicAdd(&M.cnt[4 * cg + c], 1);
+                    if ((cand >> c) & 1u) {
+                        atomicAdd(&M.cnt[par][4 * cg + c], 1);
+                        if (E.one_spike) {
+                            const unsigned long long k2 = snn_one_spike_key(Q.seed, (uint32_t)t + Q.step_offset, (uint32_t)Q.liE,
+                                                                            (uint32_t)b, (uint32_t)(jc + c));
+                            mykey = k2 > mykey ? k2 : mykey;
+                        }
+                    }
+                atomicOr(&M.candgrp[par], 1u << cg);
+            } else if (E.traces) {
+                // no candidate among my neurons: their step-t trace is already final (no spike)
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], false, E.trace_decay, E.trace_scale, E.traces_additive);
+                if (update_on && stdp && livep)
+                    *(float4 *)(tx + b * TJ + 4 * cg) =
+                        make_float4(wdep ? xE[0] : xE[0] * C.nu0, wdep ? xE[1] : xE[1] * C.nu0,
+                                    wdep ? xE[2] : xE[2] * C.nu0, wdep ? xE[3] : xE[3] * C.nu0);
             }
         }
-        PROF(7)  // D gather + neuron updates
+        PROF(4)  // gather + neuron updates
         // reductions over the CG lanes that share a sample (all lanes of the warp take part)
         uint32_t anyc = cand;
         #pragma unroll
@@ -624,36 +615,13 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             if (mykey) atomicMax(Q.win + ws * B + b, mykey);
             if (nI) atomicAdd(Q.sisum + ws * B + b, (unsigned int)nI);
             if (anyc && stage_on) {
-                const int s = atomicAdd(&M.ncand, 1);
-                if (s < XR) { M.candb[s] = b; M.wslot[b] = (int8_t)s; }
+                const int s = atomicAdd(&M.ncand[par], 1);
+                if (s < XR) { M.candb[par][s] = b; M.wslot[b] = (int16_t)(((t & 0xfff) << 3) | s); }
             }
         }
         candE = cand;
+        pend = cand;
         sIprev = sI;
-
-        // input trace of the samples this CTA owns: x = s ? scale : x * decay (nodes.py:96-103),
-        // published for the winners' post-synaptic STDP term of THIS step
-        if (X.traces && !(Q.dbg & 8)) {
-            for (int o = 0; o < own; ++o) {
-                const int bo = blockIdx.x + o * (int)G;
-                if (bo < B) {
-                    const uint32_t *srow = Q.inS + ((size_t)(t + 1) * B + bo) * Q.SW;
-                    float4 *dst = (float4 *)(Q.xpub + ((size_t)(t & 1) * B + bo) * P);
-                    float4 *xo = (float4 *)(xown + o * P);
-                    for (int i4 = tid; i4 < (P >> 2); i4 += nthr) {
-                        const uint32_t bits = __ldg(srow + (i4 >> 3)) >> ((i4 & 7) * 4);
-                        float4 x = xo[i4];
-                        x.x = trace_step(x.x, bits & 1u, X.trace_decay, X.trace_scale, X.traces_additive);
-                        x.y = trace_step(x.y, bits & 2u, X.trace_decay, X.trace_scale, X.traces_additive);
-                        x.z = trace_step(x.z, bits & 4u, X.trace_decay, X.trace_scale, X.traces_additive);
-                        x.w = trace_step(x.w, bits & 8u, X.trace_decay, X.trace_scale, X.traces_additive);
-                        xo[i4] = x;
-                        dst[i4] = x;
-                    }
-                }
-            }
-        }
-        PROF(8)  // reductions, atomics, trace publish
         // clear the exchange slot step t+1 will accumulate into (last read before the previous barrier)
         if (blockIdx.x == 0)
             for (int k = tid; k < B; k += nthr) {
@@ -661,19 +629,51 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 Q.sisum[((t + 1) % 3) * B + k] = 0u;
             }
         __syncthreads();
-        // theta += theta_plus * (number of candidates in the column)  (nodes.py:1093-1094)
+        PROF(5)  // reductions, atomics, sync
+        // theta = theta * decay + theta_plus * (#candidates of the column)  (nodes.py:1078-1094)
         if (tid < TJ) {
-            if (E.learning) theta_s[tid] = theta_s[tid] + E.theta_plus * (float)M.cnt[tid];
-            M.cnt[tid] = 0;
+            if (E.learning) theta_s[tid] = theta_s[tid] * E.theta_decay + E.theta_plus * (float)M.cnt[par][tid];
+            M.cnt[par][tid] = 0;
         }
-        PROF(9)  // slot clear, theta update, sync
-        if (!grid_barrier_fast(Q.bar, G, gen, Q.err, Q.dbg & 1)) return;
-        PROF(10)  // grid barrier
+        // prefetch slot t+2 into the buffer the gather just finished with
+        if (tid == 0 && t + 2 <= T) {
+            mbar_expect_tx(&M.mbar[buf], bytesE + bytesT);
+            bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar[buf]);
+            bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar[buf]);
+        }
+        // ---- arrive(t): this CTA's contributions to step t's exchange are issued -----------------
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
+        gen += 1;
+        PROF(6)  // theta, prefetch, arrive
+        // ---- early(t): in the shadow of the barrier ------------------------------------------------
+        if (update_on) {
+            const int nb = buf ^ 1;                                  // slot t+1 = spikes of step t
+            while (!mbar_try_wait(&M.mbar[nb], nb ? ph1 : ph0)) {}  // landed? (phase is consumed by D(t+1))
+            const uint32_t allg = (1u << CG) - 1u;
+            const uint32_t earlygrp = allg & ~M.candgrp[par];
+            const bool full = decay_on || (C.has_clamp && t == 0);
+            stdp_pass(t, nb, earlygrp, 0u, full, (uint16_t)(2 * t + 2));
+        }
+        PROF(7)  // early STDP
+        if (t + 1 < T) publish_trace(t + 1);  // input trace of step t+1 (its winners read it after barrier t+1)
+        PROF(8)  // trace publish
+        // ---- wait(t) ----------------------------------------------------------------------------
+        if (tid == 0 && !(Q.dbg & 1)) {
+            const unsigned int target = G * gen;
+            const long long t0 = clock64();
+            while ((int)(ld_relaxed_u32(Q.bar) - target) < 0) {
+                if (clock64() - t0 > 4000000000LL) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
+            }
+            asm volatile("fence.acquire.gpu;" ::: "memory");
+        }
+        __syncthreads();
+        if (M.abort) return;
+        PROF(9)  // barrier wait
         if (Q.prof && tid == 0 && t >= 100 && t < 132) {
             long long w = 0;
-            for (int k = 1; k <= 9; ++k) w += pc[k];
-            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 0] = w;       // cumulative work up to step t
-            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 1] = pc[10];  // cumulative barrier wait
+            for (int k = 1; k <= 8; ++k) w += pc[k];
+            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 0] = w;      // cumulative work up to step t
+            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 1] = pc[9];  // cumulative barrier wait
         }
     }
 
@@ -888,7 +888,7 @@ WsLayout ws_layout(const Match &m, int T, int B, int P) {
     L.evS = o; o += al((size_t)(T + 1) * m.SB);
     L.win = o; o += al(sizeof(unsigned long long) * 3 * B);
     L.sisum = o; o += al(sizeof(unsigned int) * 3 * B);
-    L.xpub = o; o += al(sizeof(float) * 2 * (size_t)B * P);
+    L.xpub = o; o += al(sizeof(float) * 3 * (size_t)B * P);
     L.prof = o; o += al(sizeof(long long) * (320 * NPROF + 2 * 32 * 160 + 640));
     L.total = o;
     return L;
@@ -952,8 +952,8 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
         return SNN_ERR_CUDA;
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
-        static const char *names[NPROF] = {"prologue", "A exchange+stage", "mbar wait", "B finalise", "C mark+compact", "C items",
-                                           "reset+theta", "D gather+neurons", "atomics+publish", "clear+theta", "grid barrier", "epilogue"};
+        static const char *names[NPROF] = {"prologue", "exchange+stage", "late final+STDP", "mbar wait+sync", "gather+neurons", "reduce+atomics",
+                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(unused)", "epilogue"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
         cudaMemcpy(hostp, Q.prof, sizeof(long long) * 320 * NPROF, cudaMemcpyDeviceToHost);
@@ -987,7 +987,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
             for (int g = 0; g < m.grid; ++g) {
                 double v = 0;
-                for (int k = 1; k <= 9; ++k) v += (double)hostp[g * NPROF + k];
+                for (int k = 1; k <= 8; ++k) v += (double)hostp[g * NPROF + k];
                 sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
             }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
