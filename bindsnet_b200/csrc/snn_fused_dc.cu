@@ -395,14 +395,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             if (t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
         }
         const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
-        if (t > 0 && stage_on && lategrp && !(Q.dbg & 16)) {         // input-trace rows of candidate samples
-            const int ns = min(M.ncand[ppar], XR);
-            for (int r = 0; r < ns; ++r) {
-                const float4 *src = (const float4 *)(Q.xpub + ((size_t)((t - 1) % 3) * B + M.candb[ppar][r]) * P);
-                float4 *dst = (float4 *)(xrow + r * P);
-                for (int i4 = tid; i4 < (P >> 2); i4 += nthr) dst[i4] = __ldcg(src + i4);
-            }
-        }
+        if (Q.prof && t > 0) { pc[10] += M.ncand[ppar]; pm[10] += __popc(lategrp); }
         PROF(1)  // exchange loads + staging issue
         if (t > 0) {
             uint32_t sE = 0;
@@ -460,18 +453,45 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             // then every row of each winner column (pre + post term, MCC_learning.py:234-299)
             __syncthreads();
             const uint32_t colwin = M.colwin;
+            if (Q.prof) pm[9] += __popc(colwin);
             const bool full = decay_on || (C.has_clamp && t == 1);
             stdp_pass(t - 1, buf, lategrp, colwin, full, (uint16_t)(2 * t + 1));
             if (colwin) __syncthreads();  // items rewrote whole float4s (winner components unchanged)
+            // every row of each winner column: pre + post term, one element per thread.  The
+            // winners' input-trace rows come straight from L2 (published before the barrier).
             for (uint32_t cw = colwin; cw; cw &= cw - 1) {
                 const int j = __ffs(cw) - 1, c4 = j >> 2;
+                uint32_t wm[BW], nzc[BW];
+                #pragma unroll
+                for (int g = 0; g < BW; ++g) { wm[g] = M.wmask[j][g]; nzc[g] = pre_on ? M.nz4[c4][g] : 0u; }
+                const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
                 for (int i = tid; i < P; i += nthr) {
-                    float U = 0.0f, V = 0.0f;
+                    float V = 0.0f;
+                    #pragma unroll
+                    for (int g = 0; g < BW; ++g) {
+                        uint32_t mm = wm[g];
+                        while (mm) {
+                            const int bb = g * 32 + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                        }
+                    }
+                    if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
+                    float U = 0.0f;
                     bool pre_t = false;
                     if (pre_on) {
+                        const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
+                        uint32_t mrow[BW];
+                        const uint4 q0 = cTl[i * (BW / 4)];
+                        mrow[0] = q0.x & nzc[0]; mrow[1] = q0.y & nzc[1]; mrow[2] = q0.z & nzc[2]; mrow[3] = q0.w & nzc[3];
+                        if (BW == 8) {
+                            const uint4 q1 = cTl[i * (BW / 4) + 1];
+                            mrow[BW - 4] = q1.x & nzc[BW - 4]; mrow[BW - 3] = q1.y & nzc[BW - 3];
+                            mrow[BW - 2] = q1.z & nzc[BW - 2]; mrow[BW - 1] = q1.w & nzc[BW - 1];
+                        }
                         #pragma unroll
                         for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = inT[buf * P * BW + i * BW + g] & M.nz4[c4][g];
+                            uint32_t mm = mrow[g];
                             pre_t |= mm != 0u;
                             while (mm) {
                                 const int bb = g * 32 + __ffs(mm) - 1;
@@ -481,18 +501,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                         }
                         if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
                     }
-                    for (int g = 0; g < BW; ++g) {
-                        uint32_t mm = M.wmask[j][g];
-                        while (mm) {
-                            const int bb = g * 32 + __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const int ws = M.wslot[bb];
-                            const float xsv = ((ws >> 3) == ((t - 1) & 0xfff)) ? xrow[(ws & 7) * P + i]
-                                                                                : __ldcg(Q.xpub + ((size_t)((t - 1) % 3) * B + bb) * P + i);
-                            V = V + xsv * (wdep ? 1.0f : C.nu1);
-                        }
-                    }
-                    if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
                     float w = W[i * WS + j];
                     if (!wdep) {
                         if (pre_t) w = w - U * dts;
@@ -614,10 +622,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             const int ws = t % 3;
             if (mykey) atomicMax(Q.win + ws * B + b, mykey);
             if (nI) atomicAdd(Q.sisum + ws * B + b, (unsigned int)nI);
-            if (anyc && stage_on) {
-                const int s = atomicAdd(&M.ncand[par], 1);
-                if (s < XR) { M.candb[par][s] = b; M.wslot[b] = (int16_t)(((t & 0xfff) << 3) | s); }
-            }
+            if (anyc && Q.prof) atomicAdd(&M.ncand[par], 1);
         }
         candE = cand;
         pend = cand;
@@ -669,11 +674,8 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         __syncthreads();
         if (M.abort) return;
         PROF(9)  // barrier wait
-        if (Q.prof && tid == 0 && t >= 100 && t < 132) {
-            long long w = 0;
-            for (int k = 1; k <= 8; ++k) w += pc[k];
-            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 0] = w;      // cumulative work up to step t
-            Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2 + 1] = pc[9];  // cumulative barrier wait
+        if (Q.prof && tid == 0 && t >= 100 && t < 132) {  // per-step trace: cumulative phase cycles
+            for (int k = 0; k < NPROF; ++k) Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * NPROF + k] = pc[k];
         }
     }
 
@@ -889,7 +891,7 @@ WsLayout ws_layout(const Match &m, int T, int B, int P) {
     L.win = o; o += al(sizeof(unsigned long long) * 3 * B);
     L.sisum = o; o += al(sizeof(unsigned int) * 3 * B);
     L.xpub = o; o += al(sizeof(float) * 3 * (size_t)B * P);
-    L.prof = o; o += al(sizeof(long long) * (320 * NPROF + 2 * 32 * 160 + 640));
+    L.prof = o; o += al(sizeof(long long) * (320 * NPROF + NPROF * 32 * 160 + 640));
     L.total = o;
     return L;
 }
@@ -967,21 +969,31 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   worst single step: mean over CTAs %8.0f, max %8.0f\n", names[k], mn / div,
                     sum / m.grid / div, mx / div, smean, smx);
         }
-        {   // per-step trace (steps 101..131): how much of the barrier wait is imbalance?
-            static long long tr[2 * 32 * 160];
+        {   // per-step trace (steps 101..131): which phase makes the slowest CTA of a step slow?
+            static long long tr[NPROF * 32 * 160];
             cudaMemcpy(tr, Q.prof + 320 * NPROF, sizeof(tr), cudaMemcpyDeviceToHost);
-            double s_maxw = 0, s_meanw = 0, s_minb = 0, s_meanb = 0; int cnt = 0;
+            double slow[NPROF] = {0}, mean[NPROF] = {0}, s_maxw = 0, s_meanw = 0; int cnt = 0;
             for (int st = 1; st < 32; ++st) {
-                double maxw = 0, meanw = 0, minb = 1e300, meanb = 0;
+                int gmax = 0; double maxw = -1, meanw = 0;
                 for (int g = 0; g < m.grid; ++g) {
-                    const double w = (double)(tr[(st * 160 + g) * 2] - tr[((st - 1) * 160 + g) * 2]);
-                    const double bw = (double)(tr[(st * 160 + g) * 2 + 1] - tr[((st - 1) * 160 + g) * 2 + 1]);
-                    maxw = w > maxw ? w : maxw; meanw += w / m.grid; minb = bw < minb ? bw : minb; meanb += bw / m.grid;
+                    double w = 0;
+                    for (int k = 1; k <= 8; ++k) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
+                    meanw += w / m.grid;
+                    if (w > maxw) { maxw = w; gmax = g; }
                 }
-                s_maxw += maxw; s_meanw += meanw; s_minb += minb; s_meanb += meanb; ++cnt;
+                for (int k = 1; k <= 9; ++k) {
+                    slow[k] += (double)(tr[(st * 160 + gmax) * NPROF + k] - tr[((st - 1) * 160 + gmax) * NPROF + k]);
+                    for (int g = 0; g < m.grid; ++g) mean[k] += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]) / m.grid;
+                }
+                s_maxw += maxw; s_meanw += meanw; ++cnt;
             }
-            fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA %.0f, barrier wait mean %.0f, min %.0f\n",
-                    s_meanw / cnt, s_maxw / cnt, s_meanb / cnt, s_minb / cnt);
+            {
+                double nc = 0, ng = 0, nwc = 0;
+                for (int g = 0; g < m.grid; ++g) { nc += (double)hostp[g * NPROF + 10]; ng += (double)hostp[(160 + g) * NPROF + 10]; nwc += (double)hostp[(160 + g) * NPROF + 9]; }
+                fprintf(stderr, "  per CTA-step: candidate samples %.3f, candidate column groups %.3f, winner columns %.3f\n", nc / m.grid / T, ng / m.grid / T, nwc / m.grid / T);
+            }
+            fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA of each step %.0f; by phase (mean CTA / slowest CTA):\n", s_meanw / cnt, s_maxw / cnt);
+            for (int k = 1; k <= 9; ++k) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
