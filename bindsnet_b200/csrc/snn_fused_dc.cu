@@ -48,7 +48,7 @@ struct FusedParams {
     uint32_t seed, step_offset;
     uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
     uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
-    unsigned char *evS;       // [T+1][SB]     same spikes as lists: u16 count[B] (16 B padded),
+    unsigned char *evS;       // [T+1][SB]     same spikes as lists: u16 count[B], dense flag, pad to 16 B,
                               //               then u16 idx[B][EV_CAP] ascending, padded with P
     unsigned long long *win;  // [3][B] arg-max keys, slot t % 3
     unsigned int *sisum;      // [3][B] Ai spike counts, slot t % 3 (slot 2 = step -1)
@@ -57,7 +57,7 @@ struct FusedParams {
     int32_t *err;
     long long *prof;          // profiling only (env SNN_B200_PROF): [grid][NPROF] phase cycles of thread 0
 };
-constexpr int NPROF = 12;
+constexpr int NPROF = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -114,7 +114,8 @@ struct Misc {  // small per-step scratch (lives in shared memory)
 struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, live, claim, misc, total; };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline int ev_block_bytes(int B) { return (int)(al16(2 * (size_t)B) + 2 * (size_t)B * EV_CAP); }
+__host__ __device__ inline int ev_count_bytes(int B) { return (int)al16(2 * (size_t)(B + 8)); }  // u16 count[B], then [B] = dense flag
+__host__ __device__ inline int ev_block_bytes(int B) { return ev_count_bytes(B) + 2 * B * EV_CAP; }
 __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, int n, int own) {
     SmemLayout L;
     size_t o = 0;
@@ -133,6 +134,118 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, 
     L.total = o;
     return L;
 }
+
+// Constants of the STDP passes, kept in shared memory so that the pass can live out of line
+// (one copy of its code: the kernel's hot loop has to stay inside the instruction cache).
+struct PassCtx {
+    float *W, *tx;
+    const uint32_t *inT;
+    const unsigned char *evb;
+    const uint16_t *live;
+    uint16_t *claim;
+    const Misc *M;
+    int P, evblk, cntb;
+    int pre_on, wdep, reduce_mean, has_clamp;
+    float Bf, dts, weight_decay, wmin, wmax, nu0, nu1;
+};
+
+// STDP pre-term pass of one step over the column groups selected by `groups` (bit per group).
+// One item = (row i, column group c4): the 4 columns of the group get  w - U*dt, decay, clamp  with
+// U = sum over the samples with a spike at pixel i and a live trace in the group, ascending
+// (MCC_learning.py:234-263, 86-110).  Columns in `skipcols` (winner columns, handled whole by the
+// column pass) are left untouched.  Items are enumerated from the live (sample, group) pairs x the
+// sample's event list; the first thread to claim an item (step/stage tag) processes it.  `full`:
+// every row (first update of the window, weight decay, or a sample whose list overflowed).
+template <int TJ, int BW>
+__device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t groups, uint32_t skipcols, int full, uint32_t tag) {
+    constexpr int CG = TJ / 4, WS = TJ + 4;
+    const int tid = threadIdx.x, nthr = blockDim.x, P = cx->P;
+    const Misc &M = *cx->M;
+    const uint16_t *ec = (const uint16_t *)(cx->evb + sb * cx->evblk);
+    const uint16_t *el = (const uint16_t *)(cx->evb + sb * cx->evblk + cx->cntb);
+    if (!full && ec[(cx->cntb >> 1) - 8]) full = 1;  // count[B]: the slot holds a sample whose list overflowed
+    const int total = full ? P * CG : (cx->pre_on ? M.nlive * EV_CAP : 0);
+    for (int idx = tid; idx < total; idx += nthr) {
+        int i, c4;
+        if (full) {
+            i = idx / CG; c4 = idx % CG;
+            if (!((groups >> c4) & 1u)) continue;
+        } else {
+            const int lp = cx->live[idx / EV_CAP], k = idx % EV_CAP;
+            const int bb = lp / CG;
+            c4 = lp % CG;
+            if (!((groups >> c4) & 1u) || k >= (int)ec[bb]) continue;
+            i = el[bb * EV_CAP + k];
+            // claim (i, c4): 16-bit tags packed two per word
+            uint32_t *cw = (uint32_t *)cx->claim + ((i * CG + c4) >> 1);
+            const int sh = ((i * CG + c4) & 1) * 16;
+            uint32_t old = *(volatile uint32_t *)cw, assumed;
+            bool mine = false;
+            do {
+                assumed = old;
+                if (((assumed >> sh) & 0xffffu) == tag) break;
+                old = atomicCAS(cw, assumed, (assumed & ~(0xffffu << sh)) | (tag << sh));
+                mine = old == assumed;
+            } while (!mine);
+            if (!mine) continue;
+        }
+        uint32_t m[BW];
+        uint32_t anym = 0;
+        if (cx->pre_on) {
+            const uint4 *cT = (const uint4 *)(cx->inT + sb * P * BW);
+            const uint4 q0 = cT[i * (BW / 4)];
+            const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+            if (BW == 8) {
+                const uint4 q1 = cT[i * (BW / 4) + 1];
+                const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+            }
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) anym |= m[g];
+        }
+        const bool pre_t = anym != 0u;
+        float *wp = cx->W + i * WS + 4 * c4;
+        const float4 w4 = *(const float4 *)wp;
+        float U[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pre_t) {
+            #pragma unroll 1
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = m[g];
+                while (mm) {
+                    const int bb = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 t4 = *(const float4 *)(cx->tx + bb * TJ + 4 * c4);
+                    U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                }
+            }
+            if (cx->reduce_mean) { U[0] = U[0] / cx->Bf; U[1] = U[1] / cx->Bf; U[2] = U[2] / cx->Bf; U[3] = U[3] / cx->Bf; }
+        }
+        const uint32_t skip = (skipcols >> (4 * c4)) & 0xFu;
+        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        #pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if ((skip >> c) & 1u) continue;
+            float w = wv[c];
+            if (!cx->wdep) {
+                // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic rule's
+                // missing dt factor is dts = 1)
+                if (pre_t) w = w - U[c] * cx->dts;
+            } else {
+                // WeightDependentPostPre, pre term only (learning.py:641-644, 651)
+                float upd = 0.0f;
+                if (cx->nu0 != 0.0f) upd = upd - (cx->nu0 * (pre_t ? U[c] : 0.0f)) * (w - cx->wmin);
+                if (cx->nu1 != 0.0f) upd = upd + (cx->nu1 * 0.0f) * (cx->wmax - w);
+                w = w + upd;
+            }
+            if (cx->weight_decay != 0.0f) w = w * cx->weight_decay;
+            if (cx->has_clamp) w = clampf(w, cx->wmin, cx->wmax);
+            wv[c] = w;
+        }
+        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    }
+}
+
 
 // TJ: neurons per CTA (4 per thread); BW: 32-bit words of a per-pixel sample mask (4 -> B <= 128,
 // 8 -> B <= 256).  Threads = B * TJ/4 <= 32 * BW * TJ/4.
@@ -164,6 +277,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     uint16_t *live = (uint16_t *)(smem + SL.live);
     uint16_t *claim = (uint16_t *)(smem + SL.claim);
     Misc &M = *(Misc *)(smem + SL.misc);
+    __shared__ PassCtx s_cx;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int b = tid / CG, cg = tid % CG;   // state ownership: sample b, neurons jc..jc+3
@@ -181,10 +295,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     const float Bf = (float)B;
     const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
     const int evblk = (int)al16((size_t)Q.SB);  // stride between the two staged list blocks
-    const int cntb = (int)al16(2 * (size_t)B);  // bytes of the count array inside a block
+    const int cntb = ev_count_bytes(B);         // bytes of the count array inside a block
     float *Wc = W + 4 * cg;                     // my 4 columns of row 0
     // an Ai neuron at rest with no input stays bitwise at rest (decay*(rest-rest)+rest == rest)
     const bool ai_rest_ok = I.rest < I.thresh && !(I.has_lbound && I.rest < I.lbound);
+    const bool rows2 = P <= 2 * nthr;           // the column pass covers the tile in <= 2 rows per thread
     unsigned int gen = 0;
     long long pc[NPROF], pm[NPROF];
     #pragma unroll
@@ -209,6 +324,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         mbar_init(&M.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.nlive = 0; M.abort = 0;
+        s_cx.W = W; s_cx.tx = tx; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.claim = claim; s_cx.M = &M;
+        s_cx.P = P; s_cx.evblk = evblk; s_cx.cntb = cntb;
+        s_cx.pre_on = pre_on; s_cx.wdep = wdep; s_cx.reduce_mean = C.reduction == SNN_REDUCE_MEAN; s_cx.has_clamp = C.has_clamp;
+        s_cx.Bf = Bf; s_cx.dts = dts; s_cx.weight_decay = C.weight_decay; s_cx.wmin = C.wmin; s_cx.wmax = C.wmax;
+        s_cx.nu0 = C.nu0; s_cx.nu1 = C.nu1;
     }
     for (int k = tid; k < 64; k += nthr) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
     for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
@@ -280,104 +400,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     publish_trace(0);
     __syncthreads();
 
-    // One STDP item = (row i, column group c4): all 4 columns of the group get the pre term of
-    // `step` (spike masks / lists in buffer `sb`) — U = sum over the samples with a spike at pixel
-    // i and a live trace in the group, ascending — then decay + clamp.  Columns in `skipcols`
-    // (winner columns, handled whole by the column pass) are left untouched.
-    auto stdp_item = [&](int i, int c4, int sb, uint32_t skipcols) {
-        uint32_t m[BW];
-        uint32_t anym = 0;
-        if (pre_on) {
-            const uint4 *cT = (const uint4 *)(inT + sb * P * BW);
-            const uint4 q0 = cT[i * (BW / 4)];
-            const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
-            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
-            if (BW == 8) {
-                const uint4 q1 = cT[i * (BW / 4) + 1];
-                const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
-                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
-            }
-            #pragma unroll
-            for (int g = 0; g < BW; ++g) anym |= m[g];
-        }
-        const bool pre_t = anym != 0u;
-        float *wp = W + i * WS + 4 * c4;
-        const float4 w4 = *(const float4 *)wp;
-        float U[4] = {0.f, 0.f, 0.f, 0.f};
-        if (pre_t) {
-            #pragma unroll
-            for (int g = 0; g < BW; ++g) {
-                uint32_t mm = m[g];
-                while (mm) {
-                    const int bb = g * 32 + __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
-                    U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
-                }
-            }
-            if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
-        }
-        const uint32_t skip = (skipcols >> (4 * c4)) & 0xFu;
-        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if ((skip >> c) & 1u) continue;
-            if (!wdep) {
-                // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic rule's
-                // missing dt factor is dts = 1)
-                float w = wv[c];
-                if (pre_t) w = w - U[c] * dts;
-                if (C.weight_decay != 0.0f) w = w * C.weight_decay;
-                if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
-                wv[c] = w;
-            } else {
-                wv[c] = apply_rule(C, wv[c], U[c], pre_t, 0.0f, false);
-            }
-        }
-        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
-    };
-
-    // STDP pre-term pass of `step` over the column groups selected by `groups` (bit per group).
-    // Items are enumerated from the live (sample, group) pairs x the sample's event list; the
-    // first thread to claim an item (step/stage tag) processes it.  `full`: every row (first
-    // update of the window, weight decay, or a sample whose list overflowed).
-    auto stdp_pass = [&](int step, int sb, uint32_t groups, uint32_t skipcols, bool full, uint16_t tag) {
-        if (!groups) return;
-        if (full) {
-            for (int k = tid; k < P * CG; k += nthr) {
-                const int i = k / CG, c4 = k % CG;
-                if ((groups >> c4) & 1u) stdp_item(i, c4, sb, skipcols);
-            }
-            return;
-        }
-        if (!pre_on) return;
-        const uint16_t *ec = (const uint16_t *)(evb + sb * evblk);
-        const uint16_t *el = (const uint16_t *)(evb + sb * evblk + cntb);
-        const int nl = M.nlive;
-        for (int idx = tid; idx < nl * 16; idx += nthr) {
-            const int lp = live[idx >> 4], e = idx & 15;
-            const int bb = lp / CG, c4 = lp % CG;
-            if (!((groups >> c4) & 1u)) continue;
-            const int cnt = ec[bb];
-            const bool dense = cnt > EV_CAP;  // list overflowed: conservatively visit every row of the group
-            for (int k = e; k < (dense ? P : cnt); k += 16) {
-                const int i = dense ? k : (int)el[bb * EV_CAP + k];
-                // claim (i, c4): 16-bit tags packed two per word
-                uint32_t *cw = (uint32_t *)claim + ((i * CG + c4) >> 1);
-                const int sh = ((i * CG + c4) & 1) * 16;
-                uint32_t old = *cw, assumed;
-                bool mine = false;
-                do {
-                    assumed = old;
-                    if (((assumed >> sh) & 0xffffu) == tag) break;
-                    old = atomicCAS(cw, assumed, (assumed & ~(0xffffu << sh)) | ((uint32_t)tag << sh));
-                    mine = old == assumed;
-                } while (!mine);
-                if (mine) stdp_item(i, c4, sb, skipcols);
-            }
-        }
-    };
-
     // =====================================================================================
     PROF(0)  // prologue
     uint32_t pend = 0;         // my candidates of the step being finalised are still undecided
@@ -395,6 +417,24 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             if (t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
         }
         const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
+        // input-trace values of this tile's candidate samples for my two rows of the column pass:
+        // issued together with the exchange loads, so one L2 round trip covers both
+        constexpr int XP = 4;
+        float xv0[XP], xv1[XP];
+        int xb[XP];
+        #pragma unroll
+        for (int c = 0; c < XP; ++c) { xv0[c] = 0.0f; xv1[c] = 0.0f; xb[c] = -1; }
+        if (t > 0 && stage_on && lategrp && rows2 && !(Q.dbg & 16)) {
+            const int ns = min(M.ncand[ppar], XP);
+            const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
+            #pragma unroll
+            for (int c = 0; c < XP; ++c)
+                if (c < ns) {
+                    xb[c] = M.candb[ppar][c];
+                    if (tid < P) xv0[c] = __ldcg(xsrc + (size_t)xb[c] * P + tid);
+                    if (tid + nthr < P) xv1[c] = __ldcg(xsrc + (size_t)xb[c] * P + tid + nthr);
+                }
+        }
         if (Q.prof && t > 0) { pc[10] += M.ncand[ppar]; pm[10] += __popc(lategrp); }
         PROF(1)  // exchange loads + staging issue
         if (t > 0) {
@@ -448,6 +488,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             }
             sEprev = sE;
         }
+        PROF(12)  // late finalise (winner, trace, monitors)
         if (t > 0 && update_on && lategrp) {
             // STDP of step t-1 for the groups that held a candidate: pre term on the listed items,
             // then every row of each winner column (pre + post term, MCC_learning.py:234-299)
@@ -455,7 +496,8 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             const uint32_t colwin = M.colwin;
             if (Q.prof) pm[9] += __popc(colwin);
             const bool full = decay_on || (C.has_clamp && t == 1);
-            stdp_pass(t - 1, buf, lategrp, colwin, full, (uint16_t)(2 * t + 1));
+            stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, full, (uint32_t)((2 * t + 1) & 0xffff));
+            PROF(13)  // late STDP items
             if (colwin) __syncthreads();  // items rewrote whole float4s (winner components unchanged)
             // every row of each winner column: pre + post term, one element per thread.  The
             // winners' input-trace rows come straight from L2 (published before the barrier).
@@ -465,15 +507,21 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 #pragma unroll
                 for (int g = 0; g < BW; ++g) { wm[g] = M.wmask[j][g]; nzc[g] = pre_on ? M.nz4[c4][g] : 0u; }
                 const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
-                for (int i = tid; i < P; i += nthr) {
+                for (int i = tid, r = 0; i < P; i += nthr, ++r) {
                     float V = 0.0f;
-                    #pragma unroll
+                    #pragma unroll 1
                     for (int g = 0; g < BW; ++g) {
                         uint32_t mm = wm[g];
                         while (mm) {
                             const int bb = g * 32 + __ffs(mm) - 1;
                             mm &= mm - 1;
-                            V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                            float xs;
+                            bool hit = false;
+                            #pragma unroll
+                            for (int c = 0; c < XP; ++c)
+                                if (xb[c] == bb) { xs = r == 0 ? xv0[c] : xv1[c]; hit = true; }
+                            if (!hit || r > 1) xs = __ldcg(xsrc + (size_t)bb * P + i);
+                            V = V + xs * (wdep ? 1.0f : C.nu1);
                         }
                     }
                     if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
@@ -513,6 +561,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     W[i * WS + j] = w;
                 }
             }
+            PROF(14)  // winner column pass
             __syncthreads();
             if (colwin) {
                 for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
@@ -622,7 +671,10 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             const int ws = t % 3;
             if (mykey) atomicMax(Q.win + ws * B + b, mykey);
             if (nI) atomicAdd(Q.sisum + ws * B + b, (unsigned int)nI);
-            if (anyc && Q.prof) atomicAdd(&M.ncand[par], 1);
+            if (anyc && (stage_on || Q.prof)) {
+                const int s = atomicAdd(&M.ncand[par], 1);
+                if (s < XR) M.candb[par][s] = b;
+            }
         }
         candE = cand;
         pend = cand;
@@ -657,7 +709,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             const uint32_t allg = (1u << CG) - 1u;
             const uint32_t earlygrp = allg & ~M.candgrp[par];
             const bool full = decay_on || (C.has_clamp && t == 0);
-            stdp_pass(t, nb, earlygrp, 0u, full, (uint16_t)(2 * t + 2));
+            stdp_pass_fn<TJ, BW>(&s_cx, nb, earlygrp, 0u, full, (uint32_t)((2 * t + 2) & 0xffff));
         }
         PROF(7)  // early STDP
         if (t + 1 < T) publish_trace(t + 1);  // input trace of step t+1 (its winners read it after barrier t+1)
@@ -748,7 +800,10 @@ __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ Fu
     const snn_layer_t &X = Q.X;
     unsigned char *blk = Q.evS + (size_t)slot * Q.SB;
     uint16_t *ecnt = (uint16_t *)blk;
-    uint16_t *elist = (uint16_t *)(blk + al16(2 * (size_t)B));
+    uint16_t *elist = (uint16_t *)(blk + ev_count_bytes(B));
+    __shared__ int s_dense;
+    if (threadIdx.x == 0) s_dense = 0;
+    __syncthreads();
     bool nonbin = false;
     for (int b = warp; b < B; b += nwarp) {
         int total = 0;
@@ -775,9 +830,10 @@ __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ Fu
         }
         const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
         if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
-        if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
+        if (lane == 0) { ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total); if (total > EV_CAP) s_dense = 1; }
     }
     __syncthreads();
+    if (threadIdx.x < 8) ecnt[B + threadIdx.x] = (threadIdx.x == 0) ? (uint16_t)s_dense : (uint16_t)0;
     // transpose 32x32 bit blocks: inT[pixel][g] bit b' = inS[g*32+b'][pixel/32] bit pixel%32
     const int NG = (B + 31) / 32;
     for (int bk = warp; bk < BW * PW; bk += nwarp) {
@@ -954,8 +1010,9 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
         return SNN_ERR_CUDA;
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
-        static const char *names[NPROF] = {"prologue", "exchange+stage", "late final+STDP", "mbar wait+sync", "gather+neurons", "reduce+atomics",
-                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(unused)", "epilogue"};
+        static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
+                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(counts)", "epilogue",
+                                           "late finalise", "late STDP items", "winner col pass", "(unused)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
         cudaMemcpy(hostp, Q.prof, sizeof(long long) * 320 * NPROF, cudaMemcpyDeviceToHost);
@@ -963,7 +1020,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
         for (int k = 0; k < NPROF; ++k) {
             double sum = 0, mx = 0, mn = 1e300;
             for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[g * NPROF + k]; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
-            const double div = (k == 0 || k == NPROF - 1) ? 1.0 : (double)T;
+            const double div = (k == 0 || k == 11) ? 1.0 : (double)T;
             double smx = 0, smean = 0;
             for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[(160 + g) * NPROF + k]; smx = v > smx ? v : smx; smean += v / m.grid; }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   worst single step: mean over CTAs %8.0f, max %8.0f\n", names[k], mn / div,
@@ -977,11 +1034,11 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 int gmax = 0; double maxw = -1, meanw = 0;
                 for (int g = 0; g < m.grid; ++g) {
                     double w = 0;
-                    for (int k = 1; k <= 8; ++k) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
+                    for (int k = 1; k <= 14; ++k) if (k <= 8 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
                     meanw += w / m.grid;
                     if (w > maxw) { maxw = w; gmax = g; }
                 }
-                for (int k = 1; k <= 9; ++k) {
+                for (int k = 1; k <= 14; ++k) {
                     slow[k] += (double)(tr[(st * 160 + gmax) * NPROF + k] - tr[((st - 1) * 160 + gmax) * NPROF + k]);
                     for (int g = 0; g < m.grid; ++g) mean[k] += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]) / m.grid;
                 }
@@ -993,13 +1050,13 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 fprintf(stderr, "  per CTA-step: candidate samples %.3f, candidate column groups %.3f, winner columns %.3f\n", nc / m.grid / T, ng / m.grid / T, nwc / m.grid / T);
             }
             fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA of each step %.0f; by phase (mean CTA / slowest CTA):\n", s_meanw / cnt, s_maxw / cnt);
-            for (int k = 1; k <= 9; ++k) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
+            for (int k = 1; k <= 14; ++k) if (k != 10 && k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
             for (int g = 0; g < m.grid; ++g) {
                 double v = 0;
-                for (int k = 1; k <= 8; ++k) v += (double)hostp[g * NPROF + k];
+                for (int k = 1; k <= 14; ++k) if (k <= 8 || k >= 12) v += (double)hostp[g * NPROF + k];
                 sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
             }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
