@@ -144,7 +144,7 @@ struct PassCtx {
     const uint16_t *live;
     uint16_t *claim;
     const Misc *M;
-    int P, evblk, cntb;
+    int P, B, evblk, cntb;
     int pre_on, wdep, reduce_mean, has_clamp;
     float Bf, dts, weight_decay, wmin, wmax, nu0, nu1;
 };
@@ -163,7 +163,7 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
     const Misc &M = *cx->M;
     const uint16_t *ec = (const uint16_t *)(cx->evb + sb * cx->evblk);
     const uint16_t *el = (const uint16_t *)(cx->evb + sb * cx->evblk + cx->cntb);
-    if (!full && ec[(cx->cntb >> 1) - 8]) full = 1;  // count[B]: the slot holds a sample whose list overflowed
+    if (!full && ec[cx->B]) full = 1;  // count[B]: the slot holds a sample whose list overflowed
     const int total = full ? P * CG : (cx->pre_on ? M.nlive * EV_CAP : 0);
     for (int idx = tid; idx < total; idx += nthr) {
         int i, c4;
@@ -256,9 +256,20 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
 //   candidate | D(t): gather, Ae/Ai update, candidates -> atomics | arrive(t) | early(t): traces +
 //   STDP pre term of the column groups WITHOUT a candidate (their step-t state is already final),
 //   input trace of step t+1 published
-template <int TJ, int BW>
+// VAR bit 0 (lean): the rarely used options — additive traces, voltage lower bounds, voltage
+// monitors, WeightDependentPostPre, mean reduction — are compiled out (match() proves them off),
+// which keeps the per-step code inside the instruction cache.  VAR bit 1: phase timers compiled in.
+template <int TJ, int BW, int VAR>
 __global__ void __launch_bounds__((8 * BW * TJ < 1024 ? 8 * BW * TJ : 1024), 1)
-snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
+snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
+    constexpr bool LEAN = (VAR & 1) != 0, PROFV = (VAR & 2) != 0;
+    // a local copy whose option fields are compile-time constants in the lean variant
+    FusedParams Q = Q0;
+    if (LEAN) {
+        Q.X.traces_additive = 0; Q.E.traces_additive = 0; Q.E.has_lbound = 0; Q.I.has_lbound = 0;
+        Q.E.rec_v = nullptr; Q.I.rec_v = nullptr; Q.C.reduction = SNN_REDUCE_SUM;
+        if (Q.C.rule == SNN_RULE_WDEP_POSTPRE) Q.C.rule = SNN_RULE_POSTPRE;
+    }
     constexpr int CG = TJ / 4;  // float4 column groups = lanes that share one sample
     constexpr int WS = TJ + 4;  // row stride of the W tile in shared memory (floats)
     extern __shared__ __align__(16) unsigned char smem[];
@@ -305,38 +316,45 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     #pragma unroll
     for (int k = 0; k < NPROF; ++k) { pc[k] = 0; pm[k] = 0; }
     long long pt = clock64();
-    #define PROF(k) { if (Q.prof) { const long long now_ = clock64(); const long long d_ = now_ - pt; pc[k] += d_; pm[k] = d_ > pm[k] ? d_ : pm[k]; pt = now_; } }
+    #define PROF(k) { if (PROFV && Q.prof) { const long long now_ = clock64(); const long long d_ = now_ - pt; pc[k] += d_; pm[k] = d_ > pm[k] ? d_ : pm[k]; pt = now_; } }
 
     // ---- prologue: W tile, theta, inhibition table, owned input traces, state registers ----
+    #pragma unroll 1
     for (int idx = tid; idx < (P + 1) * TJ; idx += nthr) {
         const int i = idx / TJ, jj = idx - i * TJ;
         W[i * WS + jj] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
     }
+    #pragma unroll 1
     for (int jj = tid; jj < 32; jj += nthr) theta_s[jj] = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
+    #pragma unroll 1
     for (int k = tid; k < P * CG; k += nthr) claim[k] = 0xffffu;
     if (tid == 0) {
         // rep[m] = m-fold sequential sum of the Ai->Ae weight: what the reference's dense sum
         // over k of sI[b,k] * w_ie[k,j] evaluates to when m inhibitory neurons (other than j) spike
         float a = 0.0f;
         rep[0] = 0.0f;
+        #pragma unroll 1
         for (int m = 1; m <= n; ++m) { a = a + Q.inh_neg; rep[m] = a; }
         mbar_init(&M.mbar[0], 1);
         mbar_init(&M.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.nlive = 0; M.abort = 0;
         s_cx.W = W; s_cx.tx = tx; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.claim = claim; s_cx.M = &M;
-        s_cx.P = P; s_cx.evblk = evblk; s_cx.cntb = cntb;
+        s_cx.P = P; s_cx.B = B; s_cx.evblk = evblk; s_cx.cntb = cntb;
         s_cx.pre_on = pre_on; s_cx.wdep = wdep; s_cx.reduce_mean = C.reduction == SNN_REDUCE_MEAN; s_cx.has_clamp = C.has_clamp;
         s_cx.Bf = Bf; s_cx.dts = dts; s_cx.weight_decay = C.weight_decay; s_cx.wmin = C.wmin; s_cx.wmax = C.wmax;
         s_cx.nu0 = C.nu0; s_cx.nu1 = C.nu1;
     }
+    #pragma unroll 1
     for (int k = tid; k < 64; k += nthr) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
+    #pragma unroll 1
     for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
     for (int k = tid; k < 256; k += nthr) M.wslot[k] = -1;
     if (X.traces)
         for (int o = 0; o < own; ++o) {
             const int bo = blockIdx.x + o * (int)G;
             if (bo < B)
+                #pragma unroll 1
                 for (int i = tid; i < P; i += nthr) xown[o * P + i] = X.x[(size_t)bo * P + i];
         }
 
@@ -384,6 +402,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                 const uint32_t *srow = Q.inS + ((size_t)(step + 1) * B + bo) * Q.SW;
                 float4 *dst = (float4 *)(Q.xpub + ((size_t)(step % 3) * B + bo) * P);
                 float4 *xo = (float4 *)(xown + o * P);
+                #pragma unroll 1
                 for (int i4 = tid; i4 < (P >> 2); i4 += nthr) {
                     const uint32_t bits = __ldg(srow + (i4 >> 3)) >> ((i4 & 7) * 4);
                     float4 x = xo[i4];
@@ -435,7 +454,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
                     if (tid + nthr < P) xv1[c] = __ldcg(xsrc + (size_t)xb[c] * P + tid + nthr);
                 }
         }
-        if (Q.prof && t > 0) { pc[10] += M.ncand[ppar]; pm[10] += __popc(lategrp); }
+        if (PROFV && Q.prof && t > 0) { pc[10] += M.ncand[ppar]; pm[10] += __popc(lategrp); }
         PROF(1)  // exchange loads + staging issue
         if (t > 0) {
             uint32_t sE = 0;
@@ -494,7 +513,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             // then every row of each winner column (pre + post term, MCC_learning.py:234-299)
             __syncthreads();
             const uint32_t colwin = M.colwin;
-            if (Q.prof) pm[9] += __popc(colwin);
             const bool full = decay_on || (C.has_clamp && t == 1);
             stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, full, (uint32_t)((2 * t + 1) & 0xffff));
             PROF(13)  // late STDP items
@@ -590,6 +608,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             if (Q.dbg & 4) {
             } else if (cnt <= EV_CAP) {
                 const uint2 *l4 = (const uint2 *)(cE + cntb + b * (2 * EV_CAP));
+                #pragma unroll 1
                 for (int k = 0; k < cnt; k += 4) {
                     const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
                     const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
@@ -671,7 +690,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             const int ws = t % 3;
             if (mykey) atomicMax(Q.win + ws * B + b, mykey);
             if (nI) atomicAdd(Q.sisum + ws * B + b, (unsigned int)nI);
-            if (anyc && (stage_on || Q.prof)) {
+            if (anyc && (stage_on || (PROFV && Q.prof))) {
                 const int s = atomicAdd(&M.ncand[par], 1);
                 if (s < XR) M.candb[par][s] = b;
             }
@@ -726,7 +745,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
         __syncthreads();
         if (M.abort) return;
         PROF(9)  // barrier wait
-        if (Q.prof && tid == 0 && t >= 100 && t < 132) {  // per-step trace: cumulative phase cycles
+        if (PROFV && Q.prof && tid == 0 && t >= 100 && t < 132) {  // per-step trace: cumulative phase cycles
             for (int k = 0; k < NPROF; ++k) Q.prof[320 * NPROF + ((t - 100) * 160 + blockIdx.x) * NPROF + k] = pc[k];
         }
     }
@@ -736,10 +755,12 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
     if (Q.normalize && C.has_norm) {
         float *part = xrow;  // [SNN_NORM_CHUNKS + 1][TJ]
         const int chunk = (P + SNN_NORM_CHUNKS - 1) / SNN_NORM_CHUNKS;
+        #pragma unroll 1
         for (int idx = tid; idx < SNN_NORM_CHUNKS * TJ; idx += nthr) {
             const int c = idx / TJ, jj = idx % TJ;
             float a = 0.0f;
             const int i1 = min((c + 1) * chunk, P);
+            #pragma unroll 1
             for (int i = c * chunk; i < i1; ++i) { const float x = W[i * WS + jj]; a = a + (C.norm_abs ? fabsf(x) : x); }
             part[idx] = a;
         }
@@ -751,9 +772,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             part[SNN_NORM_CHUNKS * TJ + tid] = C.norm / tot;
         }
         __syncthreads();
+        #pragma unroll 1
         for (int idx = tid; idx < P * TJ; idx += nthr) { const int i = idx / TJ, jj = idx % TJ; W[i * WS + jj] = W[i * WS + jj] * part[SNN_NORM_CHUNKS * TJ + jj]; }
         __syncthreads();
     }
+    #pragma unroll 1
     for (int idx = tid; idx < P * TJ; idx += nthr) {
         const int i = idx / TJ, jj = idx % TJ;
         if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[i * WS + jj];
@@ -773,12 +796,13 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q) {
             }
     }
     PROF(11)  // epilogue (partial)
-    if (Q.prof && tid == 0)
+    if (PROFV && Q.prof && tid == 0)
         for (int k = 0; k < NPROF; ++k) { Q.prof[blockIdx.x * NPROF + k] = pc[k]; Q.prof[(160 + blockIdx.x) * NPROF + k] = pm[k]; }
     for (int o = 0; o < own; ++o) {
         const int bo = blockIdx.x + o * (int)G;
         if (bo < B) {
             const uint32_t *srow = Q.inS + ((size_t)T * B + bo) * Q.SW;  // slot T = spikes of step T-1
+            #pragma unroll 1
             for (int i = tid; i < P; i += nthr) {
                 if (X.traces) X.x[(size_t)bo * P + i] = xown[o * P + i];
                 X.s[(size_t)bo * P + i] = (__ldg(srow + (i >> 5)) >> (i & 31)) & 1u;
@@ -928,12 +952,21 @@ bool match(const snn_net_t *net, const snn_run_opts_t *o, Match &m) {
     return false;
 }
 
-template <int TJ, int BW>
-cudaError_t launch_tj(const FusedParams &Q, const Match &m, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(snn_dc_fused_window<TJ, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
+template <int TJ, int BW, int VAR>
+cudaError_t launch_var(const FusedParams &Q, const Match &m, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(snn_dc_fused_window<TJ, BW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&Q};
-    return cudaLaunchCooperativeKernel((void *)snn_dc_fused_window<TJ, BW>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
+    return cudaLaunchCooperativeKernel((void *)snn_dc_fused_window<TJ, BW, VAR>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
+}
+
+template <int TJ, int BW>
+cudaError_t launch_tj(const FusedParams &Q, const Match &m, cudaStream_t stream) {
+    // lean variant when none of the rare options is in use
+    const bool lean = !Q.X.traces_additive && !Q.E.traces_additive && !Q.E.has_lbound && !Q.I.has_lbound && !Q.E.rec_v && !Q.I.rec_v &&
+                      Q.C.reduction == SNN_REDUCE_SUM && Q.C.rule != SNN_RULE_WDEP_POSTPRE;
+    if (Q.prof) return lean ? launch_var<TJ, BW, 3>(Q, m, stream) : launch_var<TJ, BW, 2>(Q, m, stream);
+    return lean ? launch_var<TJ, BW, 1>(Q, m, stream) : launch_var<TJ, BW, 0>(Q, m, stream);
 }
 
 struct WsLayout { size_t bar, inS, inT, evS, win, sisum, xpub, prof, total; };
