@@ -310,7 +310,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     float *Wc = W + 4 * cg;                     // my 4 columns of row 0
     // an Ai neuron at rest with no input stays bitwise at rest (decay*(rest-rest)+rest == rest)
     const bool ai_rest_ok = I.rest < I.thresh && !(I.has_lbound && I.rest < I.lbound);
-    const bool rows2 = P <= 2 * nthr;           // the column pass covers the tile in <= 2 rows per thread
     unsigned int gen = 0;
     long long pc[NPROF], pm[NPROF];
     #pragma unroll
@@ -436,25 +435,17 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             if (t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
         }
         const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
-        // input-trace values of this tile's candidate samples for my two rows of the column pass:
-        // issued together with the exchange loads, so one L2 round trip covers both
-        constexpr int XP = 4;
-        float xv0[XP], xv1[XP];
-        int xb[XP];
-        #pragma unroll
-        for (int c = 0; c < XP; ++c) { xv0[c] = 0.0f; xv1[c] = 0.0f; xb[c] = -1; }
-        if (t > 0 && stage_on && lategrp && rows2 && !(Q.dbg & 16)) {
-            const int ns = min(M.ncand[ppar], XP);
-            const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
-            #pragma unroll
-            for (int c = 0; c < XP; ++c)
-                if (c < ns) {
-                    xb[c] = M.candb[ppar][c];
-                    if (tid < P) xv0[c] = __ldcg(xsrc + (size_t)xb[c] * P + tid);
-                    if (tid + nthr < P) xv1[c] = __ldcg(xsrc + (size_t)xb[c] * P + tid + nthr);
-                }
+        // stage the input-trace rows of this tile's candidate samples (the possible winners) in
+        // shared memory: issued together with the exchange loads, so one L2 round trip covers both
+        if (t > 0 && stage_on && lategrp && !(Q.dbg & 16)) {
+            const int ns = min(M.ncand[ppar], XR);
+            const int P4 = P >> 2;
+            const float4 *xsrc = (const float4 *)(Q.xpub + (size_t)((t - 1) % 3) * B * P);
+            for (int idx = tid; idx < ns * P4; idx += nthr) {
+                const int r = idx / P4, i4 = idx - r * P4;
+                ((float4 *)xrow)[idx] = __ldcg(xsrc + (size_t)M.candb[ppar][r] * P4 + i4);
+            }
         }
-        if (PROFV && Q.prof && t > 0) { pc[10] += M.ncand[ppar]; pm[10] += __popc(lategrp); }
         PROF(1)  // exchange loads + staging issue
         if (t > 0) {
             uint32_t sE = 0;
@@ -517,55 +508,71 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, full, (uint32_t)((2 * t + 1) & 0xffff));
             PROF(13)  // late STDP items
             if (colwin) __syncthreads();  // items rewrote whole float4s (winner components unchanged)
-            // every row of each winner column: pre + post term, one element per thread.  The
-            // winners' input-trace rows come straight from L2 (published before the barrier).
+            // every row of each winner column: pre + post term (MCC_learning.py:234-299), one
+            // element per thread; the winners' input-trace rows were staged at the top of the iteration
             for (uint32_t cw = colwin; cw; cw &= cw - 1) {
                 const int j = __ffs(cw) - 1, c4 = j >> 2;
-                uint32_t wm[BW], nzc[BW];
-                #pragma unroll
-                for (int g = 0; g < BW; ++g) { wm[g] = M.wmask[j][g]; nzc[g] = pre_on ? M.nz4[c4][g] : 0u; }
+                // winners of the column, ascending (usually exactly one) -> staged row offsets
+                int nwin = 0, wrow[4];
+                bool generic = false;
+                for (int g = 0; g < BW; ++g) {
+                    uint32_t mm = M.wmask[j][g];
+                    while (mm) {
+                        const int bb = g * 32 + __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        int sl = -1;
+                        const int ns = min(M.ncand[ppar], XR);
+                        for (int c = 0; c < ns; ++c) if (M.candb[ppar][c] == bb) sl = c;
+                        if (nwin < 4 && sl >= 0) wrow[nwin] = sl * P; else generic = true;
+                        ++nwin;
+                    }
+                }
+                const uint4 nzq = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
+                const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
                 const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
-                for (int i = tid, r = 0; i < P; i += nthr, ++r) {
+                for (int i = tid; i < P; i += nthr) {
                     float V = 0.0f;
-                    #pragma unroll 1
-                    for (int g = 0; g < BW; ++g) {
-                        uint32_t mm = wm[g];
-                        while (mm) {
-                            const int bb = g * 32 + __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            float xs;
-                            bool hit = false;
-                            #pragma unroll
-                            for (int c = 0; c < XP; ++c)
-                                if (xb[c] == bb) { xs = r == 0 ? xv0[c] : xv1[c]; hit = true; }
-                            if (!hit || r > 1) xs = __ldcg(xsrc + (size_t)bb * P + i);
-                            V = V + xs * (wdep ? 1.0f : C.nu1);
+                    if (!generic) {
+                        #pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            if (w < nwin) V = V + xrow[wrow[w] + i] * (wdep ? 1.0f : C.nu1);
+                    } else {  // more winners than staged rows: read them from L2 (rare)
+                        for (int g = 0; g < BW; ++g) {
+                            uint32_t mm = M.wmask[j][g];
+                            while (mm) {
+                                const int bb = g * 32 + __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                            }
                         }
                     }
                     if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
                     float U = 0.0f;
                     bool pre_t = false;
                     if (pre_on) {
-                        const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
-                        uint32_t mrow[BW];
                         const uint4 q0 = cTl[i * (BW / 4)];
-                        mrow[0] = q0.x & nzc[0]; mrow[1] = q0.y & nzc[1]; mrow[2] = q0.z & nzc[2]; mrow[3] = q0.w & nzc[3];
+                        uint32_t mrow[BW];
+                        mrow[0] = q0.x & nzq.x; mrow[1] = q0.y & nzq.y; mrow[2] = q0.z & nzq.z; mrow[3] = q0.w & nzq.w;
+                        uint32_t anym = mrow[0] | mrow[1] | mrow[2] | mrow[3];
                         if (BW == 8) {
                             const uint4 q1 = cTl[i * (BW / 4) + 1];
-                            mrow[BW - 4] = q1.x & nzc[BW - 4]; mrow[BW - 3] = q1.y & nzc[BW - 3];
-                            mrow[BW - 2] = q1.z & nzc[BW - 2]; mrow[BW - 1] = q1.w & nzc[BW - 1];
+                            const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                            mrow[BW - 4] = q1.x & z1.x; mrow[BW - 3] = q1.y & z1.y; mrow[BW - 2] = q1.z & z1.z; mrow[BW - 1] = q1.w & z1.w;
+                            anym |= mrow[BW - 4] | mrow[BW - 3] | mrow[BW - 2] | mrow[BW - 1];
                         }
-                        #pragma unroll
-                        for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = mrow[g];
-                            pre_t |= mm != 0u;
-                            while (mm) {
-                                const int bb = g * 32 + __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                U = U + tx[bb * TJ + j];
+                        if (anym) {
+                            pre_t = true;
+                            #pragma unroll 1
+                            for (int g = 0; g < BW; ++g) {
+                                uint32_t mm = mrow[g];
+                                while (mm) {
+                                    const int bb = g * 32 + __ffs(mm) - 1;
+                                    mm &= mm - 1;
+                                    U = U + tx[bb * TJ + j];
+                                }
                             }
+                            if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
                         }
-                        if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
                     }
                     float w = W[i * WS + j];
                     if (!wdep) {
@@ -712,15 +719,16 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             M.cnt[par][tid] = 0;
         }
         // prefetch slot t+2 into the buffer the gather just finished with
-        if (tid == 0 && t + 2 <= T) {
+        if (tid == 32 % nthr && t + 2 <= T) {  // (not thread 0: it is about to arrive at the grid barrier)
             mbar_expect_tx(&M.mbar[buf], bytesE + bytesT);
             bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar[buf]);
             bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar[buf]);
         }
         // ---- arrive(t): this CTA's contributions to step t's exchange are issued -----------------
+        PROF(6)  // theta, prefetch issue
         if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
         gen += 1;
-        PROF(6)  // theta, prefetch, arrive
+        PROF(15)  // arrive (release)
         // ---- early(t): in the shadow of the barrier ------------------------------------------------
         if (update_on) {
             const int nb = buf ^ 1;                                  // slot t+1 = spikes of step t
@@ -1045,7 +1053,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
                                            "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(counts)", "epilogue",
-                                           "late finalise", "late STDP items", "winner col pass", "(unused)"};
+                                           "late finalise", "late STDP items", "winner col pass", "arrive (release)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
         cudaMemcpy(hostp, Q.prof, sizeof(long long) * 320 * NPROF, cudaMemcpyDeviceToHost);
@@ -1067,11 +1075,11 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 int gmax = 0; double maxw = -1, meanw = 0;
                 for (int g = 0; g < m.grid; ++g) {
                     double w = 0;
-                    for (int k = 1; k <= 14; ++k) if (k <= 8 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
+                    for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
                     meanw += w / m.grid;
                     if (w > maxw) { maxw = w; gmax = g; }
                 }
-                for (int k = 1; k <= 14; ++k) {
+                for (int k = 1; k <= 15; ++k) {
                     slow[k] += (double)(tr[(st * 160 + gmax) * NPROF + k] - tr[((st - 1) * 160 + gmax) * NPROF + k]);
                     for (int g = 0; g < m.grid; ++g) mean[k] += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]) / m.grid;
                 }
@@ -1083,13 +1091,13 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 fprintf(stderr, "  per CTA-step: candidate samples %.3f, candidate column groups %.3f, winner columns %.3f\n", nc / m.grid / T, ng / m.grid / T, nwc / m.grid / T);
             }
             fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA of each step %.0f; by phase (mean CTA / slowest CTA):\n", s_meanw / cnt, s_maxw / cnt);
-            for (int k = 1; k <= 14; ++k) if (k != 10 && k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
+            for (int k = 1; k <= 15; ++k) if (k != 10 && k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
             for (int g = 0; g < m.grid; ++g) {
                 double v = 0;
-                for (int k = 1; k <= 14; ++k) if (k <= 8 || k >= 12) v += (double)hostp[g * NPROF + k];
+                for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) v += (double)hostp[g * NPROF + k];
                 sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
             }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
