@@ -500,93 +500,103 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         PROF(12)  // late finalise (winner, trace, monitors)
         if (t > 0 && update_on && lategrp) {
-            // STDP of step t-1 for the groups that held a candidate: pre term on the listed items,
-            // then every row of each winner column (pre + post term, MCC_learning.py:234-299)
+            // STDP of step t-1 for the column groups that held a candidate: ONE row loop per group,
+            // every row visited (two per thread): pre term where a live sample spiked at the pixel,
+            // post term on the winner columns of the group (MCC_learning.py:234-299), decay, clamp.
             __syncthreads();
-            const uint32_t colwin = M.colwin;
+            const uint32_t colwin = post_on ? M.colwin : 0u;
             const bool full = decay_on || (C.has_clamp && t == 1);
-            stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, full, (uint32_t)((2 * t + 1) & 0xffff));
-            PROF(13)  // late STDP items
-            if (colwin) __syncthreads();  // items rewrote whole float4s (winner components unchanged)
-            // every row of each winner column: pre + post term (MCC_learning.py:234-299), one
-            // element per thread; the winners' input-trace rows were staged at the top of the iteration
-            for (uint32_t cw = colwin; cw; cw &= cw - 1) {
-                const int j = __ffs(cw) - 1, c4 = j >> 2;
-                // winners of the column, ascending (usually exactly one) -> staged row offsets
-                int nwin = 0, wrow[4];
+            const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
+            const int ns = min(M.ncand[ppar], XR);
+            PROF(13)  // late sync
+            for (uint32_t lg = lategrp; lg; lg &= lg - 1) {
+                const int c4 = __ffs(lg) - 1;
+                const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
+                // staged trace-row offset of each winner (ascending sample order) per winner column
+                int nwin[4] = {0, 0, 0, 0}, wrow[4][2];
                 bool generic = false;
-                for (int g = 0; g < BW; ++g) {
-                    uint32_t mm = M.wmask[j][g];
-                    while (mm) {
-                        const int bb = g * 32 + __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        int sl = -1;
-                        const int ns = min(M.ncand[ppar], XR);
-                        for (int c = 0; c < ns; ++c) if (M.candb[ppar][c] == bb) sl = c;
-                        if (nwin < 4 && sl >= 0) wrow[nwin] = sl * P; else generic = true;
-                        ++nwin;
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!((gwin >> c) & 1u)) continue;
+                    for (int g = 0; g < BW; ++g) {
+                        uint32_t mm = M.wmask[4 * c4 + c][g];
+                        while (mm) {
+                            const int bb = g * 32 + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            int sl = -1;
+                            for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
+                            if (nwin[c] < 2 && sl >= 0) wrow[c][nwin[c]] = sl * P; else generic = true;
+                            ++nwin[c];
+                        }
                     }
                 }
-                const uint4 nzq = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
-                const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
+                const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
                 const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
                 for (int i = tid; i < P; i += nthr) {
-                    float V = 0.0f;
-                    if (!generic) {
-                        #pragma unroll
-                        for (int w = 0; w < 4; ++w)
-                            if (w < nwin) V = V + xrow[wrow[w] + i] * (wdep ? 1.0f : C.nu1);
-                    } else {  // more winners than staged rows: read them from L2 (rare)
+                    uint32_t m[BW];
+                    const uint4 q0 = cTl[i * (BW / 4)];
+                    m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+                    uint32_t anym = m[0] | m[1] | m[2] | m[3];
+                    if (BW == 8) {
+                        const uint4 q1 = cTl[i * (BW / 4) + 1];
+                        const uint4 z1 = pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
+                        m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+                        anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+                    }
+                    const bool pre_t = anym != 0u;
+                    if (!(pre_t || gwin || full)) continue;
+                    float U[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (pre_t) {
+                        #pragma unroll 1
                         for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = M.wmask[j][g];
+                            uint32_t mm = m[g];
                             while (mm) {
                                 const int bb = g * 32 + __ffs(mm) - 1;
                                 mm &= mm - 1;
-                                V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                                const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
+                                U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
                             }
                         }
+                        if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
                     }
-                    if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
-                    float U = 0.0f;
-                    bool pre_t = false;
-                    if (pre_on) {
-                        const uint4 q0 = cTl[i * (BW / 4)];
-                        uint32_t mrow[BW];
-                        mrow[0] = q0.x & nzq.x; mrow[1] = q0.y & nzq.y; mrow[2] = q0.z & nzq.z; mrow[3] = q0.w & nzq.w;
-                        uint32_t anym = mrow[0] | mrow[1] | mrow[2] | mrow[3];
-                        if (BW == 8) {
-                            const uint4 q1 = cTl[i * (BW / 4) + 1];
-                            const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
-                            mrow[BW - 4] = q1.x & z1.x; mrow[BW - 3] = q1.y & z1.y; mrow[BW - 2] = q1.z & z1.z; mrow[BW - 1] = q1.w & z1.w;
-                            anym |= mrow[BW - 4] | mrow[BW - 3] | mrow[BW - 2] | mrow[BW - 1];
-                        }
-                        if (anym) {
-                            pre_t = true;
-                            #pragma unroll 1
-                            for (int g = 0; g < BW; ++g) {
-                                uint32_t mm = mrow[g];
-                                while (mm) {
-                                    const int bb = g * 32 + __ffs(mm) - 1;
-                                    mm &= mm - 1;
-                                    U = U + tx[bb * TJ + j];
+                    float *wp = W + i * WS + 4 * c4;
+                    const float4 w4 = *(const float4 *)wp;
+                    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const bool post_t = (gwin >> c) & 1u;
+                        float V = 0.0f;
+                        if (post_t) {
+                            if (!generic) {
+                                V = V + xrow[wrow[c][0] + i] * (wdep ? 1.0f : C.nu1);
+                                if (nwin[c] > 1) V = V + xrow[wrow[c][1] + i] * (wdep ? 1.0f : C.nu1);
+                            } else {  // more winners than staged rows: read them from L2 (rare)
+                                for (int g = 0; g < BW; ++g) {
+                                    uint32_t mm = M.wmask[4 * c4 + c][g];
+                                    while (mm) {
+                                        const int bb = g * 32 + __ffs(mm) - 1;
+                                        mm &= mm - 1;
+                                        V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                                    }
                                 }
                             }
-                            if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
+                            if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
+                        }
+                        if (!wdep) {
+                            float w = wv[c];
+                            if (pre_t) w = w - U[c] * dts;
+                            if (post_t) w = w + V * dts;
+                            if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+                            if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+                            wv[c] = w;
+                        } else {
+                            wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
                         }
                     }
-                    float w = W[i * WS + j];
-                    if (!wdep) {
-                        if (pre_t) w = w - U * dts;
-                        w = w + V * dts;
-                        if (C.weight_decay != 0.0f) w = w * C.weight_decay;
-                        if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
-                    } else {
-                        w = apply_rule(C, w, U, pre_t, V, true);
-                    }
-                    W[i * WS + j] = w;
+                    *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
-            PROF(14)  // winner column pass
+            PROF(14)  // late group pass
             __syncthreads();
             if (colwin) {
                 for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
@@ -1053,7 +1063,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
                                            "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(counts)", "epilogue",
-                                           "late finalise", "late STDP items", "winner col pass", "arrive (release)"};
+                                           "late finalise", "late sync", "late group pass", "arrive (release)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
         cudaMemcpy(hostp, Q.prof, sizeof(long long) * 320 * NPROF, cudaMemcpyDeviceToHost);
