@@ -500,100 +500,48 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         PROF(12)  // late finalise (winner, trace, monitors)
         if (t > 0 && update_on && lategrp) {
-            // STDP of step t-1 for the column groups that held a candidate: ONE row loop per group,
-            // every row visited (two per thread): pre term where a live sample spiked at the pixel,
-            // post term on the winner columns of the group (MCC_learning.py:234-299), decay, clamp.
+            // STDP of step t-1 for the column groups that held a candidate.  This path runs on few
+            // CTAs per step but gates the whole grid, and it is COLD code: its cost is dominated by
+            // instruction fetch, so it is kept tiny — the pre term reuses the (warm) pass of the
+            // early stage in every-row mode, and the winner columns get a small scalar loop.
             __syncthreads();
             const uint32_t colwin = post_on ? M.colwin : 0u;
-            const bool full = decay_on || (C.has_clamp && t == 1);
-            const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
-            const int ns = min(M.ncand[ppar], XR);
             PROF(13)  // late sync
-            for (uint32_t lg = lategrp; lg; lg &= lg - 1) {
-                const int c4 = __ffs(lg) - 1;
-                const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
-                // staged trace-row offset of each winner (ascending sample order) per winner column
-                int nwin[4] = {0, 0, 0, 0}, wrow[4][2];
-                bool generic = false;
-                #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (!((gwin >> c) & 1u)) continue;
-                    for (int g = 0; g < BW; ++g) {
-                        uint32_t mm = M.wmask[4 * c4 + c][g];
-                        while (mm) {
-                            const int bb = g * 32 + __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            int sl = -1;
-                            for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
-                            if (nwin[c] < 2 && sl >= 0) wrow[c][nwin[c]] = sl * P; else generic = true;
-                            ++nwin[c];
-                        }
-                    }
-                }
-                const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
+            stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, 1, 0u);
+            if (colwin) {
+                __syncthreads();  // the pass rewrote whole float4s (winner components unchanged)
+                const int ns = min(M.ncand[ppar], XR);
                 const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
-                for (int i = tid; i < P; i += nthr) {
-                    uint32_t m[BW];
-                    const uint4 q0 = cTl[i * (BW / 4)];
-                    m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
-                    uint32_t anym = m[0] | m[1] | m[2] | m[3];
-                    if (BW == 8) {
-                        const uint4 q1 = cTl[i * (BW / 4) + 1];
-                        const uint4 z1 = pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
-                        m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
-                        anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
-                    }
-                    const bool pre_t = anym != 0u;
-                    if (!(pre_t || gwin || full)) continue;
-                    float U[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (pre_t) {
+                const float post_scale = wdep ? 1.0f : C.nu1;
+                #pragma unroll 1
+                for (uint32_t cw = colwin; cw; cw &= cw - 1) {
+                    const int j = __ffs(cw) - 1, c4 = j >> 2;
+                    #pragma unroll 1
+                    for (int i = tid; i < P; i += nthr) {
+                        float U = 0.0f, V = 0.0f;
+                        bool pre_t = false;
                         #pragma unroll 1
                         for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = m[g];
-                            while (mm) {
+                            uint32_t mm = pre_on ? (inT[(buf * P + i) * BW + g] & M.nz4[c4][g]) : 0u;
+                            pre_t |= mm != 0u;
+                            while (mm) {            // pre term: live samples with a spike at pixel i
                                 const int bb = g * 32 + __ffs(mm) - 1;
                                 mm &= mm - 1;
-                                const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
-                                U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                                U = U + tx[bb * TJ + j];
+                            }
+                            uint32_t wm = M.wmask[j][g];
+                            while (wm) {            // post term: the winners' input traces, ascending
+                                const int bb = g * 32 + __ffs(wm) - 1;
+                                wm &= wm - 1;
+                                int sl = -1;
+                                for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
+                                const float xs = sl >= 0 ? xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i);
+                                V = V + xs * post_scale;
                             }
                         }
-                        if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
+                        if (C.reduction == SNN_REDUCE_MEAN) { U = U / Bf; V = V / Bf; }
+                        W[i * WS + j] = apply_rule(C, W[i * WS + j], U, pre_t, V, true);
                     }
-                    float *wp = W + i * WS + 4 * c4;
-                    const float4 w4 = *(const float4 *)wp;
-                    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const bool post_t = (gwin >> c) & 1u;
-                        float V = 0.0f;
-                        if (post_t) {
-                            if (!generic) {
-                                V = V + xrow[wrow[c][0] + i] * (wdep ? 1.0f : C.nu1);
-                                if (nwin[c] > 1) V = V + xrow[wrow[c][1] + i] * (wdep ? 1.0f : C.nu1);
-                            } else {  // more winners than staged rows: read them from L2 (rare)
-                                for (int g = 0; g < BW; ++g) {
-                                    uint32_t mm = M.wmask[4 * c4 + c][g];
-                                    while (mm) {
-                                        const int bb = g * 32 + __ffs(mm) - 1;
-                                        mm &= mm - 1;
-                                        V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
-                                    }
-                                }
-                            }
-                            if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
-                        }
-                        if (!wdep) {
-                            float w = wv[c];
-                            if (pre_t) w = w - U[c] * dts;
-                            if (post_t) w = w + V * dts;
-                            if (C.weight_decay != 0.0f) w = w * C.weight_decay;
-                            if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
-                            wv[c] = w;
-                        } else {
-                            wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
-                        }
-                    }
-                    *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
             PROF(14)  // late group pass
