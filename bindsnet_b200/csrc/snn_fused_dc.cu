@@ -159,25 +159,29 @@ struct PassCtx {
 template <int TJ, int BW>
 __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t groups, uint32_t skipcols, int full, uint32_t tag) {
     constexpr int CG = TJ / 4, WS = TJ + 4;
-    const int tid = threadIdx.x, nthr = blockDim.x, P = cx->P;
-    const Misc &M = *cx->M;
-    const uint16_t *ec = (const uint16_t *)(cx->evb + sb * cx->evblk);
-    const uint16_t *el = (const uint16_t *)(cx->evb + sb * cx->evblk + cx->cntb);
-    if (!full && ec[cx->B]) full = 1;  // count[B]: the slot holds a sample whose list overflowed
-    const int total = full ? P * CG : (cx->pre_on ? M.nlive * EV_CAP : 0);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    // the context lives in shared memory: read it ONCE into registers (the stores to W below would
+    // otherwise force every field to be reloaded per item)
+    const PassCtx c_ = *cx;
+    const int P = c_.P;
+    const Misc &M = *c_.M;
+    const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
+    const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
+    if (!full && ec[c_.B]) full = 1;  // count[B]: the slot holds a sample whose list overflowed
+    const int total = full ? P * CG : (c_.pre_on ? M.nlive * EV_CAP : 0);
     for (int idx = tid; idx < total; idx += nthr) {
         int i, c4;
         if (full) {
             i = idx / CG; c4 = idx % CG;
             if (!((groups >> c4) & 1u)) continue;
         } else {
-            const int lp = cx->live[idx / EV_CAP], k = idx % EV_CAP;
+            const int lp = c_.live[idx / EV_CAP], k = idx % EV_CAP;
             const int bb = lp / CG;
             c4 = lp % CG;
             if (!((groups >> c4) & 1u) || k >= (int)ec[bb]) continue;
             i = el[bb * EV_CAP + k];
             // claim (i, c4): 16-bit tags packed two per word
-            uint32_t *cw = (uint32_t *)cx->claim + ((i * CG + c4) >> 1);
+            uint32_t *cw = (uint32_t *)c_.claim + ((i * CG + c4) >> 1);
             const int sh = ((i * CG + c4) & 1) * 16;
             uint32_t old = *(volatile uint32_t *)cw, assumed;
             bool mine = false;
@@ -191,8 +195,8 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
         }
         uint32_t m[BW];
         uint32_t anym = 0;
-        if (cx->pre_on) {
-            const uint4 *cT = (const uint4 *)(cx->inT + sb * P * BW);
+        if (c_.pre_on) {
+            const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
             const uint4 q0 = cT[i * (BW / 4)];
             const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
             m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
@@ -205,7 +209,7 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
             for (int g = 0; g < BW; ++g) anym |= m[g];
         }
         const bool pre_t = anym != 0u;
-        float *wp = cx->W + i * WS + 4 * c4;
+        float *wp = c_.W + i * WS + 4 * c4;
         const float4 w4 = *(const float4 *)wp;
         float U[4] = {0.f, 0.f, 0.f, 0.f};
         if (pre_t) {
@@ -215,11 +219,11 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
                 while (mm) {
                     const int bb = g * 32 + __ffs(mm) - 1;
                     mm &= mm - 1;
-                    const float4 t4 = *(const float4 *)(cx->tx + bb * TJ + 4 * c4);
+                    const float4 t4 = *(const float4 *)(c_.tx + bb * TJ + 4 * c4);
                     U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
                 }
             }
-            if (cx->reduce_mean) { U[0] = U[0] / cx->Bf; U[1] = U[1] / cx->Bf; U[2] = U[2] / cx->Bf; U[3] = U[3] / cx->Bf; }
+            if (c_.reduce_mean) { U[0] = U[0] / c_.Bf; U[1] = U[1] / c_.Bf; U[2] = U[2] / c_.Bf; U[3] = U[3] / c_.Bf; }
         }
         const uint32_t skip = (skipcols >> (4 * c4)) & 0xFu;
         float wv[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -227,19 +231,19 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
         for (int c = 0; c < 4; ++c) {
             if ((skip >> c) & 1u) continue;
             float w = wv[c];
-            if (!cx->wdep) {
+            if (!c_.wdep) {
                 // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic rule's
                 // missing dt factor is dts = 1)
-                if (pre_t) w = w - U[c] * cx->dts;
+                if (pre_t) w = w - U[c] * c_.dts;
             } else {
                 // WeightDependentPostPre, pre term only (learning.py:641-644, 651)
                 float upd = 0.0f;
-                if (cx->nu0 != 0.0f) upd = upd - (cx->nu0 * (pre_t ? U[c] : 0.0f)) * (w - cx->wmin);
-                if (cx->nu1 != 0.0f) upd = upd + (cx->nu1 * 0.0f) * (cx->wmax - w);
+                if (c_.nu0 != 0.0f) upd = upd - (c_.nu0 * (pre_t ? U[c] : 0.0f)) * (w - c_.wmin);
+                if (c_.nu1 != 0.0f) upd = upd + (c_.nu1 * 0.0f) * (c_.wmax - w);
                 w = w + upd;
             }
-            if (cx->weight_decay != 0.0f) w = w * cx->weight_decay;
-            if (cx->has_clamp) w = clampf(w, cx->wmin, cx->wmax);
+            if (c_.weight_decay != 0.0f) w = w * c_.weight_decay;
+            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
             wv[c] = w;
         }
         *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
@@ -508,6 +512,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             const uint32_t colwin = post_on ? M.colwin : 0u;
             PROF(13)  // late sync
             stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, 1, 0u);
+            PROF(10)  // late pre-term pass (every-row mode)
             if (colwin) {
                 __syncthreads();  // the pass rewrote whole float4s (winner components unchanged)
                 const int ns = min(M.ncand[ppar], XR);
@@ -1010,7 +1015,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
-                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(counts)", "epilogue",
+                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "late pre pass", "epilogue",
                                            "late finalise", "late sync", "late group pass", "arrive (release)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
@@ -1033,7 +1038,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 int gmax = 0; double maxw = -1, meanw = 0;
                 for (int g = 0; g < m.grid; ++g) {
                     double w = 0;
-                    for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
+                    for (int k = 1; k <= 15; ++k) if (k != 9 && k != 11) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
                     meanw += w / m.grid;
                     if (w > maxw) { maxw = w; gmax = g; }
                 }
@@ -1043,19 +1048,14 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 }
                 s_maxw += maxw; s_meanw += meanw; ++cnt;
             }
-            {
-                double nc = 0, ng = 0, nwc = 0;
-                for (int g = 0; g < m.grid; ++g) { nc += (double)hostp[g * NPROF + 10]; ng += (double)hostp[(160 + g) * NPROF + 10]; nwc += (double)hostp[(160 + g) * NPROF + 9]; }
-                fprintf(stderr, "  per CTA-step: candidate samples %.3f, candidate column groups %.3f, winner columns %.3f\n", nc / m.grid / T, ng / m.grid / T, nwc / m.grid / T);
-            }
             fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA of each step %.0f; by phase (mean CTA / slowest CTA):\n", s_meanw / cnt, s_maxw / cnt);
-            for (int k = 1; k <= 15; ++k) if (k != 10 && k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
+            for (int k = 1; k <= 15; ++k) if (k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
             for (int g = 0; g < m.grid; ++g) {
                 double v = 0;
-                for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) v += (double)hostp[g * NPROF + k];
+                for (int k = 1; k <= 15; ++k) if (k != 9 && k != 11) v += (double)hostp[g * NPROF + k];
                 sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
             }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
