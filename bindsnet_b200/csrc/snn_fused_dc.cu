@@ -504,49 +504,154 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         PROF(12)  // late finalise (winner, trace, monitors)
         if (t > 0 && update_on && lategrp) {
-            // STDP of step t-1 for the column groups that held a candidate.  This path runs on few
-            // CTAs per step but gates the whole grid, and it is COLD code: its cost is dominated by
-            // instruction fetch, so it is kept tiny — the pre term reuses the (warm) pass of the
-            // early stage in every-row mode, and the winner columns get a small scalar loop.
+            // STDP of step t-1 for the column groups that held a candidate: ONE row loop per group,
+            // every row visited (two per thread): pre term where a live sample spiked at the pixel,
+            // post term on the winner columns of the group (MCC_learning.py:234-299), decay, clamp.
             __syncthreads();
             const uint32_t colwin = post_on ? M.colwin : 0u;
+            const bool full = decay_on || (C.has_clamp && t == 1);
+            const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
+            const int ns = min(M.ncand[ppar], XR);
             PROF(13)  // late sync
-            stdp_pass_fn<TJ, BW>(&s_cx, buf, lategrp, colwin, 1, 0u);
-            PROF(10)  // late pre-term pass (every-row mode)
-            if (colwin) {
-                __syncthreads();  // the pass rewrote whole float4s (winner components unchanged)
-                const int ns = min(M.ncand[ppar], XR);
-                const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
-                const float post_scale = wdep ? 1.0f : C.nu1;
+            // fast path for the typical case: one group, at most one winner column with one
+            // (staged) winner — short straight-line code, because this path gates the whole grid
+            bool fast = BW == 4 && !wdep && C.reduction == SNN_REDUCE_SUM && !full && (lategrp & (lategrp - 1)) == 0 &&
+                        (colwin & (colwin - 1)) == 0;
+            int fj = -1, frow = 0;
+            if (fast && colwin) {
+                fj = __ffs(colwin) - 1;
+                const uint32_t w0 = M.wmask[fj][0], w1 = M.wmask[fj][1], w2 = M.wmask[fj][2], w3 = M.wmask[fj][3];
+                const int nw = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
+                const int bb = w0 ? __ffs(w0) - 1 : (w1 ? 32 + __ffs(w1) - 1 : (w2 ? 64 + __ffs(w2) - 1 : 96 + __ffs(w3) - 1));
+                int sl = -1;
+                for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
+                fast = nw == 1 && sl >= 0;
+                frow = sl * P;
+            }
+            if (fast) {
+                const int c4 = __ffs(lategrp) - 1;
+                const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
+                const int fc = fj >= 0 ? fj - 4 * c4 : -1;     // winner column inside the group
                 #pragma unroll 1
-                for (uint32_t cw = colwin; cw; cw &= cw - 1) {
-                    const int j = __ffs(cw) - 1, c4 = j >> 2;
-                    #pragma unroll 1
-                    for (int i = tid; i < P; i += nthr) {
-                        float U = 0.0f, V = 0.0f;
-                        bool pre_t = false;
+                for (int i = tid; i < P; i += nthr) {
+                    const uint4 q0 = cTl[i];
+                    const uint32_t m0 = q0.x & z0.x, m1 = q0.y & z0.y, m2 = q0.z & z0.z, m3 = q0.w & z0.w;
+                    const bool pre_t = (m0 | m1 | m2 | m3) != 0u;
+                    if (!pre_t && fc < 0) continue;
+                    float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
+                    if (pre_t) {
+                        uint32_t mw[4] = {m0, m1, m2, m3};
                         #pragma unroll 1
-                        for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = pre_on ? (inT[(buf * P + i) * BW + g] & M.nz4[c4][g]) : 0u;
-                            pre_t |= mm != 0u;
-                            while (mm) {            // pre term: live samples with a spike at pixel i
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t mm = mw[g];
+                            while (mm) {
                                 const int bb = g * 32 + __ffs(mm) - 1;
                                 mm &= mm - 1;
-                                U = U + tx[bb * TJ + j];
-                            }
-                            uint32_t wm = M.wmask[j][g];
-                            while (wm) {            // post term: the winners' input traces, ascending
-                                const int bb = g * 32 + __ffs(wm) - 1;
-                                wm &= wm - 1;
-                                int sl = -1;
-                                for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
-                                const float xs = sl >= 0 ? xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i);
-                                V = V + xs * post_scale;
+                                const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
+                                U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
                             }
                         }
-                        if (C.reduction == SNN_REDUCE_MEAN) { U = U / Bf; V = V / Bf; }
-                        W[i * WS + j] = apply_rule(C, W[i * WS + j], U, pre_t, V, true);
                     }
+                    float *wp = W + i * WS + 4 * c4;
+                    float4 w4 = *(const float4 *)wp;
+                    if (pre_t) { w4.x = w4.x - U0 * dts; w4.y = w4.y - U1 * dts; w4.z = w4.z - U2 * dts; w4.w = w4.w - U3 * dts; }
+                    if (fc >= 0) {
+                        const float V = (0.0f + xrow[frow + i] * C.nu1) * dts;
+                        if (fc == 0) w4.x = w4.x + V; else if (fc == 1) w4.y = w4.y + V; else if (fc == 2) w4.z = w4.z + V; else w4.w = w4.w + V;
+                    }
+                    if (C.weight_decay != 0.0f) { w4.x *= C.weight_decay; w4.y *= C.weight_decay; w4.z *= C.weight_decay; w4.w *= C.weight_decay; }
+                    if (C.has_clamp) {
+                        w4.x = clampf(w4.x, C.wmin, C.wmax); w4.y = clampf(w4.y, C.wmin, C.wmax);
+                        w4.z = clampf(w4.z, C.wmin, C.wmax); w4.w = clampf(w4.w, C.wmin, C.wmax);
+                    }
+                    *(float4 *)wp = w4;
+                }
+            } else
+            for (uint32_t lg = lategrp; lg; lg &= lg - 1) {
+                const int c4 = __ffs(lg) - 1;
+                const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
+                // staged trace-row offset of each winner (ascending sample order) per winner column
+                int nwin[4] = {0, 0, 0, 0}, wrow[4][2];
+                bool generic = false;
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!((gwin >> c) & 1u)) continue;
+                    for (int g = 0; g < BW; ++g) {
+                        uint32_t mm = M.wmask[4 * c4 + c][g];
+                        while (mm) {
+                            const int bb = g * 32 + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            int sl = -1;
+                            for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
+                            if (nwin[c] < 2 && sl >= 0) wrow[c][nwin[c]] = sl * P; else generic = true;
+                            ++nwin[c];
+                        }
+                    }
+                }
+                const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
+                const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
+                for (int i = tid; i < P; i += nthr) {
+                    uint32_t m[BW];
+                    const uint4 q0 = cTl[i * (BW / 4)];
+                    m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+                    uint32_t anym = m[0] | m[1] | m[2] | m[3];
+                    if (BW == 8) {
+                        const uint4 q1 = cTl[i * (BW / 4) + 1];
+                        const uint4 z1 = pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
+                        m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+                        anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+                    }
+                    const bool pre_t = anym != 0u;
+                    if (!(pre_t || gwin || full)) continue;
+                    float U[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (pre_t) {
+                        #pragma unroll 1
+                        for (int g = 0; g < BW; ++g) {
+                            uint32_t mm = m[g];
+                            while (mm) {
+                                const int bb = g * 32 + __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
+                                U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                            }
+                        }
+                        if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
+                    }
+                    float *wp = W + i * WS + 4 * c4;
+                    const float4 w4 = *(const float4 *)wp;
+                    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const bool post_t = (gwin >> c) & 1u;
+                        float V = 0.0f;
+                        if (post_t) {
+                            if (!generic) {
+                                V = V + xrow[wrow[c][0] + i] * (wdep ? 1.0f : C.nu1);
+                                if (nwin[c] > 1) V = V + xrow[wrow[c][1] + i] * (wdep ? 1.0f : C.nu1);
+                            } else {  // more winners than staged rows: read them from L2 (rare)
+                                for (int g = 0; g < BW; ++g) {
+                                    uint32_t mm = M.wmask[4 * c4 + c][g];
+                                    while (mm) {
+                                        const int bb = g * 32 + __ffs(mm) - 1;
+                                        mm &= mm - 1;
+                                        V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                                    }
+                                }
+                            }
+                            if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
+                        }
+                        if (!wdep) {
+                            float w = wv[c];
+                            if (pre_t) w = w - U[c] * dts;
+                            if (post_t) w = w + V * dts;
+                            if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+                            if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+                            wv[c] = w;
+                        } else {
+                            wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
+                        }
+                    }
+                    *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 }
             }
             PROF(14)  // late group pass
@@ -1015,7 +1120,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
-                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "late pre pass", "epilogue",
+                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(counts)", "epilogue",
                                            "late finalise", "late sync", "late group pass", "arrive (release)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
@@ -1038,7 +1143,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 int gmax = 0; double maxw = -1, meanw = 0;
                 for (int g = 0; g < m.grid; ++g) {
                     double w = 0;
-                    for (int k = 1; k <= 15; ++k) if (k != 9 && k != 11) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
+                    for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
                     meanw += w / m.grid;
                     if (w > maxw) { maxw = w; gmax = g; }
                 }
@@ -1048,14 +1153,19 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 }
                 s_maxw += maxw; s_meanw += meanw; ++cnt;
             }
+            {
+                double nc = 0, ng = 0, nwc = 0;
+                for (int g = 0; g < m.grid; ++g) { nc += (double)hostp[g * NPROF + 10]; ng += (double)hostp[(160 + g) * NPROF + 10]; nwc += (double)hostp[(160 + g) * NPROF + 9]; }
+                fprintf(stderr, "  per CTA-step: candidate samples %.3f, candidate column groups %.3f, winner columns %.3f\n", nc / m.grid / T, ng / m.grid / T, nwc / m.grid / T);
+            }
             fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA of each step %.0f; by phase (mean CTA / slowest CTA):\n", s_meanw / cnt, s_maxw / cnt);
-            for (int k = 1; k <= 15; ++k) if (k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
+            for (int k = 1; k <= 15; ++k) if (k != 10 && k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
             for (int g = 0; g < m.grid; ++g) {
                 double v = 0;
-                for (int k = 1; k <= 15; ++k) if (k != 9 && k != 11) v += (double)hostp[g * NPROF + k];
+                for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) v += (double)hostp[g * NPROF + k];
                 sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
             }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
