@@ -187,14 +187,18 @@ def conn_normalize(conn: _abi.SnnConn, n_src: int, n_tgt: int, device: torch.dev
 
 
 def delta_prepare(w: torch.Tensor, w0: torch.Tensor, dw: torch.Tensor) -> None:
+    global launches_total
     require_cuda(w, "w")
+    launches_total += 1
     with torch.cuda.device(w.device):
         _check(lib().snn_b200_delta_prepare(w.data_ptr(), w0.data_ptr(), dw.data_ptr(), w.numel(),
                                             _stream_ptr(w.device)), "snn_b200_delta_prepare")
 
 
 def delta_apply(w, w0, dw_sum, has_clamp, wmin, wmax, has_norm, norm_abs, norm) -> None:
+    global launches_total
     require_cuda(w, "w")
+    launches_total += 1
     with torch.cuda.device(w.device):
         _check(lib().snn_b200_delta_apply(w.data_ptr(), w0.data_ptr(), dw_sum.data_ptr(), w.shape[0], w.shape[1],
                                           int(has_clamp), float(wmin), float(wmax), int(has_norm), int(norm_abs),

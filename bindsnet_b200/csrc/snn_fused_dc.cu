@@ -54,6 +54,7 @@ struct FusedParams {
     unsigned int *sisum;      // [3][B] Ai spike counts, slot t % 3 (slot 2 = step -1)
     float *xpub;              // [3][B][P] published input traces, slot t % 3
     unsigned int *bar;        // [0] arrivals (monotonic), [32] generation
+    int *dense;               // [T+1] slot holds a sample whose event list overflowed EV_CAP
     int32_t *err;
     long long *prof;          // profiling only (env SNN_B200_PROF): [grid][NPROF] phase cycles of thread 0
 };
@@ -144,6 +145,7 @@ struct PassCtx {
     const uint16_t *live;
     uint16_t *claim;
     const Misc *M;
+    const int *dense;    // global, per slot
     int P, B, evblk, cntb;
     int pre_on, wdep, reduce_mean, has_clamp;
     float Bf, dts, weight_decay, wmin, wmax, nu0, nu1;
@@ -157,7 +159,7 @@ struct PassCtx {
 // sample's event list; the first thread to claim an item (step/stage tag) processes it.  `full`:
 // every row (first update of the window, weight decay, or a sample whose list overflowed).
 template <int TJ, int BW>
-__device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t groups, uint32_t skipcols, int full, uint32_t tag) {
+__device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, int slot, uint32_t groups, uint32_t skipcols, int full, uint32_t tag) {
     constexpr int CG = TJ / 4, WS = TJ + 4;
     const int tid = threadIdx.x, nthr = blockDim.x;
     // the context lives in shared memory: read it ONCE into registers (the stores to W below would
@@ -167,7 +169,7 @@ __device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, uint32_t gr
     const Misc &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
     const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
-    if (!full && ec[c_.B]) full = 1;  // count[B]: the slot holds a sample whose list overflowed
+    if (!full && __ldg(c_.dense + slot)) full = 1;  // the slot holds a sample whose list overflowed
     const int total = full ? P * CG : (c_.pre_on ? M.nlive * EV_CAP : 0);
     for (int idx = tid; idx < total; idx += nthr) {
         int i, c4;
@@ -342,6 +344,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         mbar_init(&M.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.nlive = 0; M.abort = 0;
+        s_cx.dense = Q.dense;
         s_cx.W = W; s_cx.tx = tx; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.claim = claim; s_cx.M = &M;
         s_cx.P = P; s_cx.B = B; s_cx.evblk = evblk; s_cx.cntb = cntb;
         s_cx.pre_on = pre_on; s_cx.wdep = wdep; s_cx.reduce_mean = C.reduction == SNN_REDUCE_MEAN; s_cx.has_clamp = C.has_clamp;
@@ -804,7 +807,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             const uint32_t allg = (1u << CG) - 1u;
             const uint32_t earlygrp = allg & ~M.candgrp[par];
             const bool full = decay_on || (C.has_clamp && t == 0);
-            stdp_pass_fn<TJ, BW>(&s_cx, nb, earlygrp, 0u, full, (uint32_t)((2 * t + 2) & 0xffff));
+            stdp_pass_fn<TJ, BW>(&s_cx, nb, t + 1, earlygrp, 0u, full, (uint32_t)((2 * t + 2) & 0xffff));
         }
         PROF(7)  // early STDP
         if (t + 1 < T) publish_trace(t + 1);  // input trace of step t+1 (its winners read it after barrier t+1)
@@ -893,66 +896,70 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
 // per-sample bit rows and pixel lists, the per-pixel sample masks, the Input monitor raster,
 // flags non-binary input; CTA 0 also resets the exchange slots and counts the incoming Ai spikes.
 __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ FusedParams Q, int BW) {
-    extern __shared__ uint32_t sbits[];  // [B][SW]
+    // grid = (slot, group of 32 samples): each CTA converts 32 samples of one timestep
+    extern __shared__ uint32_t sbits[];  // [32][SW]
     const int B = Q.B, P = Q.P, SW = Q.SW, PW = (P + 31) / 32;
-    const int slot = blockIdx.x;
+    const int slot = blockIdx.x, grp = blockIdx.y, b0 = grp * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const snn_layer_t &X = Q.X;
     unsigned char *blk = Q.evS + (size_t)slot * Q.SB;
     uint16_t *ecnt = (uint16_t *)blk;
     uint16_t *elist = (uint16_t *)(blk + ev_count_bytes(B));
-    __shared__ int s_dense;
-    if (threadIdx.x == 0) s_dense = 0;
-    __syncthreads();
-    bool nonbin = false;
-    for (int b = warp; b < B; b += nwarp) {
+    bool nonbin = false, dense = false;
+    for (int bl = warp; bl < 32; bl += nwarp) {
+        const int b = b0 + bl;
         int total = 0;
-        uint16_t *lst = elist + b * EV_CAP;
-        for (int w = 0; w < SW; ++w) {
-            const int i = w * 32 + lane;
-            bool s = false;
-            if (w < PW && i < P) {
-                if (slot == 0) s = X.s[(size_t)b * P + i] != 0;
-                else if (X.ext) {
-                    const size_t idx = ((size_t)(slot - 1) * B + b) * P + i;
-                    if (X.ext_dtype == SNN_EXT_U8) { const uint8_t e = ((const uint8_t *)X.ext)[idx]; s = e != 0; nonbin |= e > 1; }
-                    else { const float e = ((const float *)X.ext)[idx]; s = e != 0.0f; nonbin |= (e != 0.0f && e != 1.0f); }
+        if (b < B) {
+            uint16_t *lst = elist + b * EV_CAP;
+            for (int w = 0; w < SW; ++w) {
+                const int i = w * 32 + lane;
+                bool s = false;
+                if (w < PW && i < P) {
+                    if (slot == 0) s = X.s[(size_t)b * P + i] != 0;
+                    else if (X.ext) {
+                        const size_t idx = ((size_t)(slot - 1) * B + b) * P + i;
+                        if (X.ext_dtype == SNN_EXT_U8) { const uint8_t e = ((const uint8_t *)X.ext)[idx]; s = e != 0; nonbin |= e > 1; }
+                        else { const float e = ((const float *)X.ext)[idx]; s = e != 0.0f; nonbin |= (e != 0.0f && e != 1.0f); }
+                    }
+                    if (slot > 0 && X.rec_s) X.rec_s[((size_t)(slot - 1) * B + b) * P + i] = s ? 1 : 0;
                 }
-                if (slot > 0 && X.rec_s) X.rec_s[((size_t)(slot - 1) * B + b) * P + i] = s ? 1 : 0;
+                const uint32_t word = __ballot_sync(0xffffffffu, s);
+                if (lane == 0) { sbits[bl * SW + w] = word; Q.inS[((size_t)slot * B + b) * SW + w] = word; }
+                if (s) {  // ascending pixel list: position = spikes before me
+                    const int pos = total + __popc(word & ((1u << lane) - 1u));
+                    if (pos < EV_CAP) lst[pos] = (uint16_t)i;
+                }
+                total += __popc(word);
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, s);
-            if (lane == 0) { sbits[b * SW + w] = word; Q.inS[((size_t)slot * B + b) * SW + w] = word; }
-            if (s) {  // ascending pixel list: position = spikes before me
-                const int pos = total + __popc(word & ((1u << lane) - 1u));
-                if (pos < EV_CAP) lst[pos] = (uint16_t)i;
-            }
-            total += __popc(word);
+            const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
+            if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+            if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
+            dense |= total > EV_CAP;
+        } else {
+            for (int w = lane; w < SW; w += 32) sbits[bl * SW + w] = 0u;
         }
-        const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
-        if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
-        if (lane == 0) { ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total); if (total > EV_CAP) s_dense = 1; }
     }
+    if (dense && lane == 0) atomicOr(Q.dense + slot, 1);
+    if (grp == 0 && threadIdx.x < 8) ecnt[B + threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x < 8) ecnt[B + threadIdx.x] = (threadIdx.x == 0) ? (uint16_t)s_dense : (uint16_t)0;
-    // transpose 32x32 bit blocks: inT[pixel][g] bit b' = inS[g*32+b'][pixel/32] bit pixel%32
-    const int NG = (B + 31) / 32;
-    for (int bk = warp; bk < BW * PW; bk += nwarp) {
-        const int g = bk / PW, w = bk % PW;
+    // transpose 32x32 bit blocks: inT[pixel][grp] bit b' = inS[b0+b'][pixel/32] bit pixel%32
+    for (int w = warp; w < PW; w += nwarp) {
+        const uint32_t word = sbits[lane * SW + w];
         uint32_t mine = 0;
-        if (g < NG) {
-            const int bb = g * 32 + lane;
-            const uint32_t word = bb < B ? sbits[bb * SW + w] : 0u;
-            #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const uint32_t mm = __ballot_sync(0xffffffffu, (word >> r) & 1u);
-                if (lane == r) mine = mm;
-            }
+        #pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t mm = __ballot_sync(0xffffffffu, (word >> r) & 1u);
+            if (lane == r) mine = mm;
         }
         const int i = w * 32 + lane;
-        if (i < P) Q.inT[((size_t)slot * P + i) * BW + g] = mine;
+        if (i < P) {
+            Q.inT[((size_t)slot * P + i) * BW + grp] = mine;
+            if (grp == 0)  // zero the padding groups of the per-pixel masks
+                for (int g = (B + 31) / 32; g < BW; ++g) Q.inT[((size_t)slot * P + i) * BW + g] = 0u;
+        }
     }
     if (nonbin && Q.err) atomicOr(Q.err, SNN_ERR_NONBINARY);
-    if (slot == 0) {
+    if (slot == 0 && grp == 0) {
         for (int k = threadIdx.x; k < 3 * B; k += blockDim.x) Q.win[k] = 0ull;
         for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) Q.sisum[k] = 0u;
         for (int b = warp; b < B; b += nwarp) {  // Ai spikes of step -1 (slot 2 = (-1) mod 3)
@@ -1045,11 +1052,12 @@ cudaError_t launch_tj(const FusedParams &Q, const Match &m, cudaStream_t stream)
     return lean ? launch_var<TJ, BW, 1>(Q, m, stream) : launch_var<TJ, BW, 0>(Q, m, stream);
 }
 
-struct WsLayout { size_t bar, inS, inT, evS, win, sisum, xpub, prof, total; };
+struct WsLayout { size_t bar, dense, inS, inT, evS, win, sisum, xpub, prof, total; };
 WsLayout ws_layout(const Match &m, int T, int B, int P) {
     WsLayout L; size_t o = 0;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     L.bar = o; o += al(sizeof(unsigned int) * 96);
+    L.dense = o; o += al(sizeof(int) * (size_t)(T + 1));
     L.inS = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * B * m.SW);
     L.inT = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * P * m.BW);
     L.evS = o; o += al((size_t)(T + 1) * m.SB);
@@ -1095,8 +1103,10 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.xpub = (float *)(ws + WL.xpub); Q.bar = (unsigned int *)(ws + WL.bar); Q.err = opts->err_flag;
     const bool prof = getenv("SNN_B200_PROF") != nullptr;
     Q.prof = prof ? (long long *)(ws + WL.prof) : nullptr;
-    if (cudaMemsetAsync(Q.bar, 0, sizeof(unsigned int) * 96, stream) != cudaSuccess) return SNN_ERR_CUDA;
-    snn_dc_prepass<<<T + 1, 256, sizeof(uint32_t) * (size_t)B * m.SW, stream>>>(Q, m.BW);
+    Q.dense = (int *)(ws + WL.dense);
+    // barrier words and per-slot dense flags are adjacent: one memset node
+    if (cudaMemsetAsync(Q.bar, 0, WL.inS - WL.bar, stream) != cudaSuccess) return SNN_ERR_CUDA;
+    snn_dc_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
         if (m.BW == 4) {
