@@ -10,5 +10,6 @@ from . import network  # noqa: F401  (must precede learning: circular import ord
 from . import learning  # noqa: F401
 from . import models  # noqa: F401
 from . import encoding  # noqa: F401
+from . import pipeline  # noqa: F401
 
 __version__ = "0.1.0"
