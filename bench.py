@@ -252,14 +252,15 @@ def main():
     value = world * BATCH * T_STEPS * K / (ms_total * 1e-3)
 
     # ---- e2e: host buffers through the public API, H2D + result D2H inside the timed region --
-    net.add_monitor(Monitor(net.layers["Ae"], ["s"], time=T_STEPS, device=str(dev)), "Ae_spikes")
+    from bindsnet_b200.network.monitors import SpikeCounter
+
+    net.add_monitor(SpikeCounter(net.layers["Ae"]), "Ae_spikes")   # per-sample, per-neuron spike counts of the window
     counts_host = torch.empty(BATCH, N_NEURONS, dtype=torch.int32).pin_memory()
 
     def consume(x_dev):
         net.reset_state_variables()
         runner.run({"X": x_dev}, time=T_STEPS)
-        counts = net.monitors["Ae_spikes"].get("s").sum(0, dtype=torch.int32)  # per-sample spike counts [B, n]
-        counts_host.copy_(counts, non_blocking=False)                          # D2H of the step's result
+        counts_host.copy_(net.monitors["Ae_spikes"].get("s"), non_blocking=False)  # D2H of the step's result [B, n] int32
         return counts_host
 
     from bindsnet_b200.pipeline import WindowPrefetcher
@@ -314,7 +315,7 @@ def main():
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T_STEPS * BATCH * N_INPT,
                     "d2h_bytes_per_step": BATCH * N_NEURONS * 4,
-                    "note": "pinned host uint8 spike trains -> WindowPrefetcher (H2D on a side stream, overlapped) -> Network.run + Ae spike monitor, per-sample counts read back (D2H) every window",
+                    "note": "pinned host uint8 spike trains -> WindowPrefetcher (H2D on a side stream, overlapped) -> Network.run + SpikeCounter on Ae; the [B, n] per-sample spike counts (what label assignment consumes) read back (D2H) every window",
                     "wall_s": wall_e2e},
             "gpu_launches": launches,
             "clocks": clocks.summary(),

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SNN_ABI_VERSION = 4
+SNN_ABI_VERSION = 5
 SNN_MAX_LAYERS = 8
 SNN_MAX_CONNS = 12
 
@@ -78,6 +78,7 @@ class SnnLayer(C.Structure):
         ("inject_v", C.c_void_p),
         ("rec_s", C.c_void_p),
         ("rec_v", C.c_void_p),
+        ("rec_count", C.c_void_p),
     ]
 
 

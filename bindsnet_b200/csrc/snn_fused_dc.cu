@@ -366,6 +366,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
 
     float vE[4], rE[4], xE[4], vI[4], rI[4];
     uint32_t sEprev = 0, sIprev = 0, candE = 0;  // 4-bit masks over my neurons
+    uint32_t cE01 = 0, cE23 = 0, cI01 = 0, cI23 = 0;  // spike counters of my neurons, 16 bits each
     #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const bool ok = act && jc + c < n;
@@ -492,18 +493,27 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
                 }
                 // monitors (monitors.py:94-111): spikes / voltages of step t-1
                 if (E.rec_s || I.rec_s || E.rec_v || I.rec_v) {
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (jc + c < n) {
-                            const size_t k = ((size_t)(t - 1) * B + b) * n + jc + c;
-                            if (E.rec_s) E.rec_s[k] = (sE >> c) & 1u;
-                            if (I.rec_s) I.rec_s[k] = (sIprev >> c) & 1u;
-                            if (E.rec_v) E.rec_v[k] = vE[c];
-                            if (I.rec_v) I.rec_v[k] = vI[c];
-                        }
+                    const size_t k0 = ((size_t)(t - 1) * B + b) * n + jc;
+                    if (((n & 3) == 0) && jc + 3 < n) {  // 4 rasters bytes in one store
+                        if (E.rec_s) *(uint32_t *)(E.rec_s + k0) = (sE & 1u) | ((sE & 2u) << 7) | ((sE & 4u) << 14) | ((sE & 8u) << 21);
+                        if (I.rec_s) *(uint32_t *)(I.rec_s + k0) = (sIprev & 1u) | ((sIprev & 2u) << 7) | ((sIprev & 4u) << 14) | ((sIprev & 8u) << 21);
+                        if (E.rec_v) *(float4 *)(E.rec_v + k0) = make_float4(vE[0], vE[1], vE[2], vE[3]);
+                        if (I.rec_v) *(float4 *)(I.rec_v + k0) = make_float4(vI[0], vI[1], vI[2], vI[3]);
+                    } else {
+                        #pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (jc + c < n) {
+                                if (E.rec_s) E.rec_s[k0 + c] = (sE >> c) & 1u;
+                                if (I.rec_s) I.rec_s[k0 + c] = (sIprev >> c) & 1u;
+                                if (E.rec_v) E.rec_v[k0 + c] = vE[c];
+                                if (I.rec_v) I.rec_v[k0 + c] = vI[c];
+                            }
+                    }
                 }
             }
             sEprev = sE;
+            if (E.rec_count) { cE01 += (sE & 1u) | ((sE & 2u) << 15); cE23 += ((sE >> 2) & 1u) | ((sE & 8u) << 13); }
+            if (I.rec_count) { cI01 += (sIprev & 1u) | ((sIprev & 2u) << 15); cI23 += ((sIprev >> 2) & 1u) | ((sIprev & 8u) << 13); }
         }
         PROF(12)  // late finalise (winner, trace, monitors)
         if (t > 0 && update_on && lategrp) {
@@ -872,6 +882,8 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
                 E.s[k] = (sEprev >> c) & 1u;
                 I.v[k] = vI[c]; I.refrac_count[k] = rI[c];
                 I.s[k] = (sIprev >> c) & 1u;
+                if (E.rec_count) E.rec_count[k] += (int)(((c < 2 ? cE01 : cE23) >> ((c & 1) * 16)) & 0xffffu);
+                if (I.rec_count) I.rec_count[k] += (int)(((c < 2 ? cI01 : cI23) >> ((c & 1) * 16)) & 0xffffu);
             }
     }
     PROF(11)  // epilogue (partial)
@@ -1000,6 +1012,7 @@ bool match(const snn_net_t *net, const snn_run_opts_t *o, Match &m) {
     if (m.lX < 0 || m.lE < 0 || m.lI < 0) return false;
     const snn_layer_t &X = net->layers[m.lX], &E = net->layers[m.lE], &I = net->layers[m.lI];
     if (E.ext || I.ext || I.traces || E.n != I.n) return false;
+    if (X.rec_count || ((E.rec_count || I.rec_count) && o->T > 65535)) return false;
     m.cXE = m.cEI = m.cIE = -1;
     for (int c = 0; c < 3; ++c) {
         const snn_conn_t &C = net->conns[c];

@@ -129,6 +129,7 @@ __device__ void phase1(const DevNet &N, int li, int tile, int t, float *s_red, i
                 if (L.unclamp && L.unclamp[(L.unclamp_per_step ? (size_t)t * n : 0) + j]) sf = false;
                 if (t == N.T - 1) L.s[k] = sf ? 1 : 0;
                 if (L.rec_s) L.rec_s[((size_t)t * B + b) * n + j] = sf ? 1 : 0;
+                if (L.rec_count && sf) L.rec_count[k] += 1;
             }
             const uint32_t fw = __ballot_sync(0xffffffffu, valid && sf);
             if (lane == 0) D.bits[((size_t)wr * B + b) * nw + tile] = fw;
@@ -182,6 +183,7 @@ __device__ void phase2(const DevNet &N, int li, int tile, int t) {
             if (L.unclamp && L.unclamp[(L.unclamp_per_step ? (size_t)t * n : 0) + j]) sf = false;
             if (t == N.T - 1) L.s[k] = sf ? 1 : 0;
             if (L.rec_s) L.rec_s[((size_t)t * B + b) * n + j] = sf ? 1 : 0;
+            if (L.rec_count && sf) L.rec_count[k] += 1;
         }
         const uint32_t fw = __ballot_sync(0xffffffffu, valid && sf);
         if (lane == 0) D.bits[((size_t)wr * B + b) * nw + tile] = fw;

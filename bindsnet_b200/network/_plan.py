@@ -154,6 +154,8 @@ def build_net(
                 d.rec_s = _ptr(_as_u8(r[0])); keep.append(r[0])
             if r[1] is not None:
                 d.rec_v = _ptr(r[1]); keep.append(r[1])
+            if len(r) > 2 and r[2] is not None:
+                d.rec_count = _ptr(r[2]); keep.append(r[2])
     for i, ((src, tgt), conn) in enumerate(network.connections.items()):
         fill_conn(net.conns[i], conn, index[src], index[tgt], float(network.dt), B)
     return net, keep

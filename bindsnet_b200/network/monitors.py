@@ -87,6 +87,45 @@ class Monitor(AbstractMonitor):
         self.clean = True
 
 
+class SpikeCounter(AbstractMonitor):
+    """Per-neuron spike counts of the last ``run`` window, ``[batch, *shape]`` int32 — what the
+    reference's callers reduce the full raster to (``spikes.sum(time)``, e.g.
+    examples/mnist/batch_eth_mnist.py:280-284; ``evaluation.assign_labels`` consumes exactly
+    this, evaluation/evaluation.py:8-61).  The window kernels count in registers, so no
+    ``[T, B, n]`` raster is ever written.  Extension: not in the reference.
+    """
+
+    def __init__(self, obj, device: str = None):
+        super().__init__()
+        self.obj = obj
+        self.device = device
+        self.counts = None
+
+    def get(self, var: str = "s") -> torch.Tensor:
+        assert var == "s", "SpikeCounter records spikes only"
+        if self.counts is None:
+            return torch.empty(0, dtype=torch.int32)
+        out = self.counts.view(self.counts.shape[0], *self.obj.shape)
+        return out if self.device is None else out.to(self.device)
+
+    def record(self) -> None:  # step-wise fallback path
+        s = self.obj.s
+        if self.counts is None or self.counts.shape[0] != s.shape[0] or self.counts.device != s.device:
+            self.counts = torch.zeros(s.shape[0], self.obj.n, dtype=torch.int32, device=s.device)
+        self.counts += s.reshape(s.shape[0], -1).to(torch.int32)
+
+    def _begin_window(self, B: int, device) -> torch.Tensor:
+        if self.counts is None or self.counts.shape[0] != B or self.counts.device != device:
+            self.counts = torch.zeros(B, self.obj.n, dtype=torch.int32, device=device)
+        else:
+            self.counts.zero_()
+        return self.counts
+
+    def reset_state_variables(self) -> None:
+        if self.counts is not None:
+            self.counts.zero_()
+
+
 class NetworkMonitor(AbstractMonitor):
     """Reference: monitors.py:127-329 — whole-network snapshots every step; not on the
     accelerated path."""

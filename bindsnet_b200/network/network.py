@@ -16,7 +16,7 @@ import torch
 
 from .. import _abi, _backend
 from . import _plan
-from .monitors import AbstractMonitor, Monitor
+from .monitors import AbstractMonitor, Monitor, SpikeCounter
 from .nodes import Nodes
 
 
@@ -154,6 +154,11 @@ class Network(torch.nn.Module):
         return out.contiguous()
 
     def _fusable_monitor(self, mon) -> Optional[str]:
+        if isinstance(mon, SpikeCounter):
+            for name, layer in self.layers.items():
+                if mon.obj is layer:
+                    return name
+            return None
         if not isinstance(mon, Monitor):
             return None
         for name, layer in self.layers.items():
@@ -184,15 +189,18 @@ class Network(torch.nn.Module):
         if any(layer is None for layer in fused.values()):
             return self._run_stepwise(ext, T, normalize, clamps, unclamps, injects, seed, step_offset)
 
-        rec: Dict[str, Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = {}
+        rec: Dict[str, Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]] = {}
         for mname, lname in fused.items():
             mon, layer = self.monitors[mname], self.layers[lname]
-            rs, rv = rec.get(lname, (None, None))
+            rs, rv, rc = rec.get(lname, (None, None, None))
+            if isinstance(mon, SpikeCounter):
+                rec[lname] = (rs, rv, mon._begin_window(B, dev))
+                continue
             if "s" in mon.state_vars and rs is None:
                 rs = torch.empty(T, B, layer.n, dtype=torch.uint8, device=dev)
             if "v" in mon.state_vars and rv is None:
                 rv = torch.empty(T, B, layer.n, dtype=torch.float32, device=dev)
-            rec[lname] = (rs, rv)
+            rec[lname] = (rs, rv, rc)
 
         net, keep = _plan.build_net(self, B, ext, clamps, unclamps, injects, rec)
         opts = _abi.SnnRunOpts()
@@ -204,7 +212,9 @@ class Network(torch.nn.Module):
 
         for mname, lname in fused.items():
             mon, layer = self.monitors[mname], self.layers[lname]
-            rs, rv = rec[lname]
+            if isinstance(mon, SpikeCounter):
+                continue
+            rs, rv, _ = rec[lname]
             if "s" in mon.state_vars:
                 mon._push_window("s", rs.view(torch.bool).view(T, B, *layer.shape))
             if "v" in mon.state_vars:
@@ -234,6 +244,8 @@ class Network(torch.nn.Module):
             opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset + t
             self._launch(net, opts, self._device())
             for m in self.monitors.values():
+                if isinstance(m, SpikeCounter) and t == 0:
+                    m._begin_window(B, self._device())
                 m.record()
 
     def check_errors(self) -> None:

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 4
+#define SNN_ABI_VERSION 5
 #define SNN_MAX_LAYERS 8
 #define SNN_MAX_CONNS 12
 
@@ -115,6 +115,9 @@ typedef struct snn_layer {
     /* --- per-window recordings (Monitor, monitors.py:94-111); NULL = not recorded --- */
     uint8_t *rec_s; /* [T,B,n] */
     float *rec_v;   /* [T,B,n] */
+    int32_t *rec_count; /* [B,n] += number of spikes of each neuron over the window (what the
+                           reference's callers compute as spikes.sum(time), e.g.
+                           examples/mnist/batch_eth_mnist.py:280-284); NULL = not counted */
 } snn_layer_t;
 
 /* One dense synapse matrix.  Reference: Connection (topology.py:265-399) or

@@ -421,6 +421,7 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
             const size_t BN = (size_t)B * L->n;
             if (L->rec_s) memcpy(L->rec_s + (size_t)t * BN, L->s, BN);
             if (L->rec_v && L->v) memcpy(L->rec_v + (size_t)t * BN, L->v, BN * sizeof(float));
+            if (L->rec_count) for (size_t k = 0; k < BN; ++k) L->rec_count[k] += L->s[k] ? 1 : 0;
         }
     }
     /* network.py:464-465: normalize every connection once after the loop */

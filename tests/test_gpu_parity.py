@@ -154,3 +154,25 @@ def test_nonbinary_input_is_reported():
     net.run({"X": x}, time=5)
     with pytest.raises(_backend.BackendError):
         net.check_errors()
+
+
+@pytest.mark.parametrize("tier", [0, 1])
+def test_spike_counter_on_gpu(tier):
+    """In-kernel spike counts (fused: registers, generic: global) == raster summed over time."""
+    from bindsnet_b200.models import DiehlAndCook2015
+    from bindsnet_b200.network.monitors import Monitor, SpikeCounter
+
+    g = torch.Generator().manual_seed(8)
+    net = DiehlAndCook2015(n_inpt=784, n_neurons=96, batch_size=8, inpt_shape=(1, 28, 28), inh=120.0).to("cuda")
+    net.force_tier = tier
+    net.add_monitor(Monitor(net.layers["Ae"], ["s"], time=80, device="cuda"), "raster")
+    net.add_monitor(SpikeCounter(net.layers["Ae"]), "count")
+    net.add_monitor(SpikeCounter(net.layers["Ai"]), "count_i")
+    net.add_monitor(Monitor(net.layers["Ai"], ["s"], time=80, device="cuda"), "raster_i")
+    for _ in range(2):
+        x = torch.bernoulli(0.06 * torch.ones(80, 8, 1, 28, 28), generator=g).byte().cuda()
+        net.run({"X": x}, time=80, one_spike_seed=2)
+        net.check_errors()
+        assert torch.equal(net.monitors["count"].get("s"), net.monitors["raster"].get("s").sum(0).to(torch.int32))
+        assert torch.equal(net.monitors["count_i"].get("s"), net.monitors["raster_i"].get("s").sum(0).to(torch.int32))
+        assert net.monitors["count"].get("s").sum() > 0

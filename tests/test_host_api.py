@@ -168,3 +168,23 @@ def test_nonbinary_input_flag_from_oracle_backend():
     with OracleBackend() as ob:
         net.run({"X": x}, time=4)
     assert ob.err & _abi.SNN_ERR_NONBINARY
+
+
+def test_spike_counter_equals_raster_sum():
+    """SpikeCounter (in-kernel counts, no raster) == Monitor raster summed over time."""
+    from bindsnet_b200.network.monitors import SpikeCounter
+
+    torch.manual_seed(4)
+    net = DiehlAndCook2015(n_inpt=64, n_neurons=24, batch_size=3, inpt_shape=(1, 8, 8), inh=60.0)
+    net.add_monitor(Monitor(net.layers["Ae"], ["s"], time=50), "raster")
+    net.add_monitor(SpikeCounter(net.layers["Ae"]), "count")
+    net.add_monitor(SpikeCounter(net.layers["Ai"]), "count_i")
+    g = torch.Generator().manual_seed(5)
+    with OracleBackend():
+        for _ in range(2):  # counts restart every window
+            x = torch.bernoulli(0.2 * torch.ones(50, 3, 1, 8, 8), generator=g).byte()
+            net.run({"X": x}, time=50, one_spike_seed=1)
+            raster = net.monitors["raster"].get("s")
+            assert torch.equal(net.monitors["count"].get("s"), raster.sum(0).to(torch.int32))
+            assert net.monitors["count"].get("s").shape == (3, 24) and raster.sum() > 0
+            assert net.monitors["count_i"].get("s").sum() > 0
