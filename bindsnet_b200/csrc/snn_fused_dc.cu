@@ -437,11 +437,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         // ---- late(t-1): exchange results of step t-1 (slot (t-1) % 3; t = 0: from the pre-pass)
         const int xs = (t + 2) % 3;
         unsigned long long key = 0ull;
-        unsigned int isum = 0;
-        if (act) {
-            isum = __ldcg(Q.sisum + xs * B + b);
-            if (t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
-        }
+        if (act && t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
         const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
         // stage the input-trace rows of this tile's candidate samples (the possible winners) in
         // shared memory: issued together with the exchange loads, so one L2 round trip covers both
@@ -689,6 +685,8 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         uint32_t cand = 0, sI = 0;
         unsigned long long mykey = 0ull;
         int nI = 0;
+        // Ai spike count of step t-1 (lateral inhibition): issued here, consumed after the gather
+        const unsigned int isum = act ? __ldcg(Q.sisum + xs * B + b) : 0u;
         if (act) {
             // spike-gather: p[c] = sum_{i in sX(t-1)[b]} W[i][c], i ascending (topology.py:437-479)
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
