@@ -74,7 +74,9 @@ class LearningRule(ABC):
         d.nu1 = float(self.nu[1])
         d.weight_decay = float(self.weight_decay)
         # learning.py:97-104: clamp iff a bound is finite and the rule is not NoOp
-        finite = bool((self.connection.wmin != -np.inf).any() or (self.connection.wmax != np.inf).any())
+        from ..network.nodes import _scalar
+
+        finite = _scalar(self.connection.wmin, "wmin") != -np.inf or _scalar(self.connection.wmax, "wmax") != np.inf
         d.has_clamp = int(finite and not isinstance(self, NoOp))
 
 

@@ -27,13 +27,27 @@ def _exp_decay(dt: torch.Tensor, tc: torch.Tensor) -> torch.Tensor:
     return torch.exp(-dt.detach().cpu().float() / tc.detach().cpu().float()).to(tc.device)
 
 
+_SCALAR_CACHE: dict = {}
+
+
 def _scalar(value: Scalar, name: str) -> float:
+    """Host float of a (possibly device-resident) scalar parameter.  Reading a CUDA tensor costs a
+    device synchronisation, so the value is cached per tensor object and version: building the
+    plan of a window must not stall the stream the previous window is still running on."""
     if isinstance(value, torch.Tensor):
         if value.numel() != 1:
             raise NotImplementedError(
                 f"per-neuron tensor for '{name}' is not supported by the CUDA core yet (scalar only)"
             )
-        return float(value.detach().cpu().reshape(()).item())
+        key = id(value)
+        hit = _SCALAR_CACHE.get(key)
+        if hit is not None and hit[0] is value and hit[1] == value._version:
+            return hit[2]
+        out = float(value.detach().cpu().reshape(()).item())
+        if len(_SCALAR_CACHE) > 4096:
+            _SCALAR_CACHE.clear()
+        _SCALAR_CACHE[key] = (value, value._version, out)
+        return out
     return float(value)
 
 

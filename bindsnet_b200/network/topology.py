@@ -18,7 +18,7 @@ import torch
 from torch.nn import Module, Parameter
 
 from .. import _abi
-from .nodes import Nodes
+from .nodes import Nodes, _scalar
 
 
 class AbstractConnection(ABC, Module):
@@ -126,8 +126,8 @@ class Connection(AbstractConnection):
         d.kind = _abi.SNN_CONN_DENSE
         if self.wmin.numel() != 1 or self.wmax.numel() != 1:
             raise NotImplementedError("per-synapse wmin/wmax tensors are not supported by the CUDA core yet")
-        d.wmin = float(self.wmin)
-        d.wmax = float(self.wmax)
+        d.wmin = _scalar(self.wmin, "wmin")
+        d.wmax = _scalar(self.wmax, "wmax")
         d.has_norm = int(self.norm is not None)
         d.norm_abs = 1
         d.norm = float(self.norm) if self.norm is not None else 0.0
