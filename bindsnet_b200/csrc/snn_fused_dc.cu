@@ -24,6 +24,7 @@
 //
 // Arithmetic and summation orders are those of snn_phases.cuh / oracle/snn_oracle.c, so the
 // result is bit-identical to the generic kernel and to the oracle.
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,8 +44,10 @@ struct FusedParams {
     int32_t SW;               // words per sample row of inS
     int32_t SB;               // bytes of one event-list block
     int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
+    int32_t pregather;        // env SNN_B200_PREGATHER: gather of step t+1 in the shadow of barrier t
     int32_t dbg;              // profiling only (env SNN_B200_DEBUG): 1 no barrier wait, 2 skip STDP,
-                              // 4 skip gather, 8 skip trace publish, 16 skip staging — results invalid
+                              // 4 skip gather, 8 skip trace publish, 16 skip staging, 64 late pass on every CTA and step
+                              // — results invalid
     uint32_t seed, step_offset;
     uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
     uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
@@ -100,19 +103,24 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
 
 struct Misc {  // small per-step scratch (lives in shared memory)
     uint64_t mbar[2];
+    uint32_t wl[4];         // first 4 winners of the step being finalised: column << 16 | sample << 8 | staged row slot (0xff: none)
     int cnt[2][32];         // candidates per column (theta update), double-buffered by step parity
     uint32_t wmask[32][8];  // winners of the step being finalised: per column, bit mask over samples
     uint32_t nz4[8][8];     // per column group: samples with a non-zero Ae trace in that group
+    int nwl;                // number of winners of the step being finalised
     int nlive;              // live (sample, column group) pairs, listed in live[]
+    int denseflag[2];       // staged slot (by buffer) holds a sample whose event list overflowed EV_CAP
     int ncand[2];           // samples with a candidate in this tile (by step parity)
     int candb[2][XR];       // ... the first XR of them: their input-trace rows get staged
     uint32_t candgrp[2];    // column groups holding a candidate (by step parity)
     uint32_t colwin;        // bit j: column j has a winner in the step being finalised
     int abort;              // barrier time-out: leave the time loop
-    int16_t wslot[256];     // sample -> (step tag << 3 | staged row slot)
+    long long lc[8];        // late-pass statistics (profiling variant only)
+    long long pc[16];       // phase timers of thread 0 (profiling variant only)
 };
 
-struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, live, claim, misc, total; };
+static_assert(offsetof(Misc, wl) % 16 == 0 && offsetof(Misc, nz4) % 16 == 0 && offsetof(Misc, wmask) % 16 == 0, "Misc: 16-byte rows");
+struct SmemLayout { size_t W, tx, ev, inT, xrow, rep, xown, theta, live, misc, total; };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline int ev_count_bytes(int B) { return (int)al16(2 * (size_t)(B + 8)); }  // u16 count[B], then [B] = dense flag
@@ -130,128 +138,338 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int TJ, int B, int BW, 
     L.xown = o; o += al16(sizeof(float) * (size_t)own * P);
     L.theta = o; o += al16(sizeof(float) * 32);
     L.live = o; o += al16(sizeof(uint16_t) * (size_t)B * (TJ / 4));
-    L.claim = o; o += al16(sizeof(uint16_t) * (size_t)P * (TJ / 4));
     L.misc = o; o += al16(sizeof(Misc));
     L.total = o;
     return L;
 }
 
-// Constants of the STDP passes, kept in shared memory so that the pass can live out of line
-// (one copy of its code: the kernel's hot loop has to stay inside the instruction cache).
+// Constants of the STDP passes, kept in shared memory so that the passes can live out of line.
+// The kernel is bound by instruction fetch as much as by anything else (measured: a code path that
+// is not resident in the 32 KB L1.5 instruction cache runs at ~7 cycles per instruction), so the
+// late (rare) STDP pass and the early (every step) pass share ONE body, stdp_rows.
 struct PassCtx {
     float *W, *tx;
+    const float *xrow;
     const uint32_t *inT;
     const unsigned char *evb;
     const uint16_t *live;
-    uint16_t *claim;
-    const Misc *M;
-    const int *dense;    // global, per slot
+    Misc *M;
     int P, B, evblk, cntb;
     int pre_on, wdep, reduce_mean, has_clamp;
     float Bf, dts, weight_decay, wmin, wmax, nu0, nu1;
 };
 
-// STDP pre-term pass of one step over the column groups selected by `groups` (bit per group).
-// One item = (row i, column group c4): the 4 columns of the group get  w - U*dt, decay, clamp  with
-// U = sum over the samples with a spike at pixel i and a live trace in the group, ascending
-// (MCC_learning.py:234-263, 86-110).  Columns in `skipcols` (winner columns, handled whole by the
-// column pass) are left untouched.  Items are enumerated from the live (sample, group) pairs x the
-// sample's event list; the first thread to claim an item (step/stage tag) processes it.  `full`:
-// every row (first update of the window, weight decay, or a sample whose list overflowed).
+// STDP of one step on the column groups selected by `groups` (bit per group), thread = input row i
+// (MCC_learning.py:234-299, 86-110; learning.py:641-651 for the weight-dependent pre term).
+//   pre term: for every selected group whose live samples (non-zero Ae trace, Misc::nz4) spiked at
+//     pixel i:  w - U*dt  on the group's 4 columns, U = sum of the traces in ascending sample order;
+//   columns without a pending post term (not in `colwin`) are finished here: decay, clamp;
+//   post term: for each of the `nwl` winners (Misc::wl, distinct columns, staged rows):
+//     w + x_pre[b,i]*nu1*dt, decay, clamp on that one column.
+// `full`: every row of the selected groups is decayed / clamped (first update of a window, weight
+// decay).  Per column the operation order is the reference's: pre, post, decay, clamp.
 template <int TJ, int BW>
-__device__ __noinline__ void stdp_pass_fn(const PassCtx *cx, int sb, int slot, uint32_t groups, uint32_t skipcols, int full, uint32_t tag) {
-    constexpr int CG = TJ / 4, WS = TJ + 4;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+__device__ __noinline__ void stdp_rows(const PassCtx *cx, int sb, uint32_t groups, int nwl, uint32_t colwin, int full) {
+    constexpr int WS = TJ + 4;
     // the context lives in shared memory: read it ONCE into registers (the stores to W below would
-    // otherwise force every field to be reloaded per item)
+    // otherwise force every field to be reloaded per row)
+    const PassCtx c_ = *cx;
+    const int P = c_.P;
+    const Misc &M = *c_.M;
+    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    #pragma unroll 1
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        float *wrow = c_.W + i * WS;
+        uint32_t q[BW];
+        {
+            const uint4 q0 = cT[i * (BW / 4)];
+            q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w;
+            if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; q[BW - 4] = q1.x; q[BW - 3] = q1.y; q[BW - 2] = q1.z; q[BW - 1] = q1.w; }
+        }
+        uint32_t anyq = 0;
+        #pragma unroll
+        for (int g = 0; g < BW; ++g) anyq |= q[g];
+        if (!c_.pre_on) anyq = 0;
+        if (anyq | (uint32_t)full) {
+            #pragma unroll 1
+            for (uint32_t lg = groups; lg; lg &= lg - 1) {
+                const int c4 = __ffs(lg) - 1;
+                uint32_t a[BW], anya = 0;
+                {
+                    const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+                    a[0] = q[0] & z0.x; a[1] = q[1] & z0.y; a[2] = q[2] & z0.z; a[3] = q[3] & z0.w;
+                    if (BW == 8) {
+                        const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                        a[BW - 4] = q[BW - 4] & z1.x; a[BW - 3] = q[BW - 3] & z1.y; a[BW - 2] = q[BW - 2] & z1.z; a[BW - 1] = q[BW - 1] & z1.w;
+                    }
+                }
+                #pragma unroll
+                for (int g = 0; g < BW; ++g) anya |= a[g];
+                if (!c_.pre_on) anya = 0;
+                if (!(anya | (uint32_t)full)) continue;
+                float U[4] = {0.f, 0.f, 0.f, 0.f};
+                if (anya) {
+                    #pragma unroll
+                    for (int g = 0; g < BW; ++g) {
+                        uint32_t mm = a[g];
+                        while (mm) {  // live samples with a spike at pixel i, ascending
+                            const int bb = g * 32 + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const float4 t4 = *(const float4 *)(c_.tx + bb * TJ + 4 * c4);
+                            U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                        }
+                    }
+                    if (c_.reduce_mean) { U[0] = U[0] / c_.Bf; U[1] = U[1] / c_.Bf; U[2] = U[2] / c_.Bf; U[3] = U[3] / c_.Bf; }
+                }
+                const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;  // these columns finish in the post step
+                float *wp = wrow + 4 * c4;
+                const float4 w4 = *(const float4 *)wp;
+                float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float w = wv[c];
+                    if (!c_.wdep) {
+                        // PostPre family: w - U*dt (x * 1.0f is exact, so the classic rule's missing dt
+                        // factor is dts = 1)
+                        if (anya) w = w - U[c] * c_.dts;
+                    } else {
+                        // WeightDependentPostPre, pre term only (learning.py:641-644, 651)
+                        float upd = 0.0f;
+                        if (c_.nu0 != 0.0f) upd = upd - (c_.nu0 * (anya ? U[c] : 0.0f)) * (w - c_.wmin);
+                        if (c_.nu1 != 0.0f) upd = upd + (c_.nu1 * 0.0f) * (c_.wmax - w);
+                        w = w + upd;
+                    }
+                    if (!((gwin >> c) & 1u)) {
+                        if (c_.weight_decay != 0.0f) w = w * c_.weight_decay;
+                        if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+                    }
+                    wv[c] = w;
+                }
+                *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            }
+        }
+        #pragma unroll 1
+        for (int k = 0; k < nwl; ++k) {
+            const uint32_t e = M.wl[k];  // column << 16 | sample << 8 | staged row slot
+            float *wp = wrow + (e >> 16);
+            float w = *wp;
+            const float V = 0.0f + c_.xrow[(e & 0xffu) * P + i] * c_.nu1;
+            w = w + V * c_.dts;
+            if (c_.weight_decay != 0.0f) w = w * c_.weight_decay;
+            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+            *wp = w;
+        }
+    }
+}
+
+// Early STDP of one step (pre term only) in list form: the work items are (live (sample, group)
+// pair, event of that sample) — far fewer than rows x groups while few pairs are live.  Several
+// samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel
+// owns the row (no atomics), sums all of them in ascending order and updates the group's 4 columns:
+// w - U*dt, decay, clamp (MCC_learning.py:234-263, 86-110).  Threads tid0 < 0 (warp 0, busy arriving
+// at the grid barrier) do not take part.
+constexpr int EVH = 16;  // list slots enumerated per pair and round
+template <int TJ, int BW>
+__device__ __noinline__ void stdp_list(const PassCtx *cx, int sb, uint32_t groups, uint32_t colwin, int tid0, int nthr0) {
+    constexpr int CG = TJ / 4, WS = TJ + 4;
     const PassCtx c_ = *cx;
     const int P = c_.P;
     const Misc &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
     const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
-    if (!full && __ldg(c_.dense + slot)) full = 1;  // the slot holds a sample whose list overflowed
-    const int total = full ? P * CG : (c_.pre_on ? M.nlive * EV_CAP : 0);
-    for (int idx = tid; idx < total; idx += nthr) {
-        int i, c4;
-        if (full) {
-            i = idx / CG; c4 = idx % CG;
-            if (!((groups >> c4) & 1u)) continue;
-        } else {
-            const int lp = c_.live[idx / EV_CAP], k = idx % EV_CAP;
-            const int bb = lp / CG;
-            c4 = lp % CG;
-            if (!((groups >> c4) & 1u) || k >= (int)ec[bb]) continue;
-            i = el[bb * EV_CAP + k];
-            // claim (i, c4): 16-bit tags packed two per word
-            uint32_t *cw = (uint32_t *)c_.claim + ((i * CG + c4) >> 1);
-            const int sh = ((i * CG + c4) & 1) * 16;
-            uint32_t old = *(volatile uint32_t *)cw, assumed;
-            bool mine = false;
-            do {
-                assumed = old;
-                if (((assumed >> sh) & 0xffffu) == tag) break;
-                old = atomicCAS(cw, assumed, (assumed & ~(0xffffu << sh)) | (tag << sh));
-                mine = old == assumed;
-            } while (!mine);
-            if (!mine) continue;
-        }
-        uint32_t m[BW];
-        uint32_t anym = 0;
-        if (c_.pre_on) {
-            const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
-            const uint4 q0 = cT[i * (BW / 4)];
-            const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
-            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
-            if (BW == 8) {
-                const uint4 q1 = cT[i * (BW / 4) + 1];
-                const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
-                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
-            }
-            #pragma unroll
-            for (int g = 0; g < BW; ++g) anym |= m[g];
-        }
-        const bool pre_t = anym != 0u;
-        float *wp = c_.W + i * WS + 4 * c4;
-        const float4 w4 = *(const float4 *)wp;
-        float U[4] = {0.f, 0.f, 0.f, 0.f};
-        if (pre_t) {
-            #pragma unroll 1
-            for (int g = 0; g < BW; ++g) {
-                uint32_t mm = m[g];
-                while (mm) {
-                    const int bb = g * 32 + __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const float4 t4 = *(const float4 *)(c_.tx + bb * TJ + 4 * c4);
-                    U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    const int total = M.nlive * EVH;
+    if (tid0 < 0) return;
+    #pragma unroll 1
+    for (int idx = tid0; idx < total; idx += nthr0) {
+        const int lp = c_.live[idx / EVH];
+        const int bb = lp / CG, c4 = lp % CG;
+        if (!((groups >> c4) & 1u)) continue;
+        const int cnt = min((int)ec[bb], EV_CAP);
+        #pragma unroll 1
+        for (int k = idx % EVH; k < cnt; k += EVH) {
+            const int i = el[bb * EV_CAP + k];
+            uint32_t a[BW];
+            {
+                const uint4 q0 = cT[i * (BW / 4)];
+                const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+                a[0] = q0.x & z0.x; a[1] = q0.y & z0.y; a[2] = q0.z & z0.z; a[3] = q0.w & z0.w;
+                if (BW == 8) {
+                    const uint4 q1 = cT[i * (BW / 4) + 1];
+                    const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                    a[BW - 4] = q1.x & z1.x; a[BW - 3] = q1.y & z1.y; a[BW - 2] = q1.z & z1.z; a[BW - 1] = q1.w & z1.w;
                 }
             }
-            if (c_.reduce_mean) { U[0] = U[0] / c_.Bf; U[1] = U[1] / c_.Bf; U[2] = U[2] / c_.Bf; U[3] = U[3] / c_.Bf; }
-        }
-        const uint32_t skip = (skipcols >> (4 * c4)) & 0xFu;
-        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if ((skip >> c) & 1u) continue;
-            float w = wv[c];
-            if (!c_.wdep) {
-                // PostPre family: w - U*dt, decay, clamp (x * 1.0f is exact, so the classic rule's
-                // missing dt factor is dts = 1)
-                if (pre_t) w = w - U[c] * c_.dts;
-            } else {
-                // WeightDependentPostPre, pre term only (learning.py:641-644, 651)
-                float upd = 0.0f;
-                if (c_.nu0 != 0.0f) upd = upd - (c_.nu0 * (pre_t ? U[c] : 0.0f)) * (w - c_.wmin);
-                if (c_.nu1 != 0.0f) upd = upd + (c_.nu1 * 0.0f) * (c_.wmax - w);
-                w = w + upd;
+            // owner of row i in this group = the lowest live sample spiking at pixel i
+            uint32_t lower = 0;  // any live spiking sample below bb?
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) {
+                const uint32_t below = g < (bb >> 5) ? 0xffffffffu : (g == (bb >> 5) ? ((1u << (bb & 31)) - 1u) : 0u);
+                lower |= a[g] & below;
             }
-            if (c_.weight_decay != 0.0f) w = w * c_.weight_decay;
-            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
-            wv[c] = w;
+            if (lower) continue;
+            float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = a[g];
+                while (mm) {
+                    const int b2 = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 t4 = *(const float4 *)(c_.tx + b2 * TJ + 4 * c4);
+                    U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
+                }
+            }
+            if (c_.reduce_mean) { U0 = U0 / c_.Bf; U1 = U1 / c_.Bf; U2 = U2 / c_.Bf; U3 = U3 / c_.Bf; }
+            float *wp = c_.W + i * WS + 4 * c4;
+            const float4 w4 = *(const float4 *)wp;
+            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float Uv[4] = {U0, U1, U2, U3};
+            const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;  // columns with a pending post term finish there
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float w = wv[c];
+                if (!c_.wdep) {
+                    w = w - Uv[c] * c_.dts;
+                } else {  // WeightDependentPostPre, pre term only (learning.py:641-644, 651)
+                    float upd = 0.0f;
+                    if (c_.nu0 != 0.0f) upd = upd - (c_.nu0 * Uv[c]) * (w - c_.wmin);
+                    if (c_.nu1 != 0.0f) upd = upd + (c_.nu1 * 0.0f) * (c_.wmax - w);
+                    w = w + upd;
+                }
+                if (!((gwin >> c) & 1u)) {
+                    if (c_.weight_decay != 0.0f) w = w * c_.weight_decay;
+                    if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+                }
+                wv[c] = w;
+            }
+            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
         }
-        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
     }
 }
 
+// Late STDP, general form (rare: more than 4 winners in the tile, two winners in one column, a
+// winner whose input-trace row is not staged, WeightDependentPostPre, mean reduction, or a full
+// pass): one row loop per candidate column group, pre and post term of a column applied together.
+template <int TJ, int BW>
+__device__ __noinline__ void late_generic_fn(const PassCtx *cx, const snn_conn_t *Cp, int sb, int ppar, uint32_t lategrp, uint32_t colwin,
+                                             int full, const float *xsrc) {
+    constexpr int WS = TJ + 4;
+    const PassCtx c_ = *cx;
+    const snn_conn_t &C = *Cp;
+    const Misc &M = *c_.M;
+    const int P = c_.P, tid = threadIdx.x, nthr = blockDim.x;
+    const bool wdep = c_.wdep != 0, pre_on = c_.pre_on != 0;
+    const float Bf = c_.Bf, dts = c_.dts;
+    float *W = c_.W;
+    const float *tx = c_.tx, *xrow = c_.xrow;
+    const uint4 *cTl = (const uint4 *)(c_.inT + sb * P * BW);
+    const int ns = min(M.ncand[ppar], XR);
+    #pragma unroll 1
+    for (uint32_t lg = lategrp; lg; lg &= lg - 1) {
+        const int c4 = __ffs(lg) - 1;
+        const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
+        // staged trace-row offset of each winner (ascending sample order) per winner column
+        int nwin[4] = {0, 0, 0, 0}, wrow[4][2];
+        bool generic = false;
+        #pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            if (!((gwin >> c) & 1u)) continue;
+            #pragma unroll 1
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = M.wmask[4 * c4 + c][g];
+                while (mm) {
+                    const int bb = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    int sl = -1;
+                    for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
+                    if (nwin[c] < 2 && sl >= 0) wrow[c][nwin[c]] = sl * P; else generic = true;
+                    ++nwin[c];
+                }
+            }
+        }
+        const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
+        #pragma unroll 1
+        for (int i = tid; i < P; i += nthr) {
+            uint32_t m[BW];
+            const uint4 q0 = cTl[i * (BW / 4)];
+            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+            uint32_t anym = m[0] | m[1] | m[2] | m[3];
+            if (BW == 8) {
+                const uint4 q1 = cTl[i * (BW / 4) + 1];
+                const uint4 z1 = pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
+                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+                anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+            }
+            const bool pre_t = anym != 0u;
+            if (!(pre_t || gwin || full)) continue;
+            float U[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pre_t) {
+                #pragma unroll 1
+                for (int g = 0; g < BW; ++g) {
+                    uint32_t mm = m[g];
+                    while (mm) {
+                        const int bb = g * 32 + __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
+                        U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                    }
+                }
+                if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
+            }
+            float *wp = W + i * WS + 4 * c4;
+            const float4 w4 = *(const float4 *)wp;
+            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            #pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const bool post_t = (gwin >> c) & 1u;
+                float V = 0.0f;
+                if (post_t) {
+                    if (!generic) {
+                        V = V + xrow[wrow[c][0] + i] * (wdep ? 1.0f : C.nu1);
+                        if (nwin[c] > 1) V = V + xrow[wrow[c][1] + i] * (wdep ? 1.0f : C.nu1);
+                    } else {  // more winners than staged rows: read them from L2 (rare)
+                        for (int g = 0; g < BW; ++g) {
+                            uint32_t mm = M.wmask[4 * c4 + c][g];
+                            while (mm) {
+                                const int bb = g * 32 + __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
+                            }
+                        }
+                    }
+                    if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
+                }
+                if (!wdep) {
+                    float w = wv[c];
+                    if (pre_t) w = w - U[c] * dts;
+                    if (post_t) w = w + V * dts;
+                    if (C.weight_decay != 0.0f) w = w * C.weight_decay;
+                    if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
+                    wv[c] = w;
+                } else {
+                    wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
+                }
+            }
+            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    }
+}
+
+// Spike-gather of a sample whose event list overflowed EV_CAP: walk its bit row in global memory
+// (rare; out of line to keep the hot loop small).
+__device__ __noinline__ float4 gather_dense(const uint32_t *row, int SW, const float *Wc, int WS) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    for (int w = 0; w < SW; ++w) {
+        uint32_t word = __ldg(row + w);
+        while (word) {
+            const int i = w * 32 + __ffs(word) - 1;
+            word &= word - 1;
+            const float4 r4 = *(const float4 *)(Wc + i * WS);
+            p0 = p0 + r4.x; p1 = p1 + r4.y; p2 = p2 + r4.z; p3 = p3 + r4.w;
+        }
+    }
+    return make_float4(p0, p1, p2, p3);
+}
 
 // TJ: neurons per CTA (4 per thread); BW: 32-bit words of a per-pixel sample mask (4 -> B <= 128,
 // 8 -> B <= 256).  Threads = B * TJ/4 <= 32 * BW * TJ/4.
@@ -292,7 +510,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     float *xown = (float *)(smem + SL.xown);
     float *theta_s = (float *)(smem + SL.theta);
     uint16_t *live = (uint16_t *)(smem + SL.live);
-    uint16_t *claim = (uint16_t *)(smem + SL.claim);
     Misc &M = *(Misc *)(smem + SL.misc);
     __shared__ PassCtx s_cx;
 
@@ -317,11 +534,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     // an Ai neuron at rest with no input stays bitwise at rest (decay*(rest-rest)+rest == rest)
     const bool ai_rest_ok = I.rest < I.thresh && !(I.has_lbound && I.rest < I.lbound);
     unsigned int gen = 0;
-    long long pc[NPROF], pm[NPROF];
+    long long *pc = M.pc;  // phase timers of thread 0 (profiling variant only)
     #pragma unroll
-    for (int k = 0; k < NPROF; ++k) { pc[k] = 0; pm[k] = 0; }
+    for (int k = 0; k < NPROF; ++k) if (PROFV && tid == 0) pc[k] = 0;
     long long pt = clock64();
-    #define PROF(k) { if (PROFV && Q.prof) { const long long now_ = clock64(); const long long d_ = now_ - pt; pc[k] += d_; pm[k] = d_ > pm[k] ? d_ : pm[k]; pt = now_; } }
+    #define PROF(k) { if (PROFV && Q.prof && tid == 0) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
 
     // ---- prologue: W tile, theta, inhibition table, owned input traces, state registers ----
     #pragma unroll 1
@@ -331,8 +548,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     }
     #pragma unroll 1
     for (int jj = tid; jj < 32; jj += nthr) theta_s[jj] = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
-    #pragma unroll 1
-    for (int k = tid; k < P * CG; k += nthr) claim[k] = 0xffffu;
     if (tid == 0) {
         // rep[m] = m-fold sequential sum of the Ai->Ae weight: what the reference's dense sum
         // over k of sI[b,k] * w_ie[k,j] evaluates to when m inhibitory neurons (other than j) spike
@@ -343,9 +558,10 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         mbar_init(&M.mbar[0], 1);
         mbar_init(&M.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.nlive = 0; M.abort = 0;
-        s_cx.dense = Q.dense;
-        s_cx.W = W; s_cx.tx = tx; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.claim = claim; s_cx.M = &M;
+        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.abort = 0; M.nwl = 0; M.nlive = 0;
+        M.denseflag[0] = Q.dense[0]; M.denseflag[1] = T >= 1 ? Q.dense[1] : 0;
+        for (int k = 0; k < 8; ++k) M.lc[k] = 0;
+        s_cx.W = W; s_cx.tx = tx; s_cx.xrow = xrow; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.M = &M;
         s_cx.P = P; s_cx.B = B; s_cx.evblk = evblk; s_cx.cntb = cntb;
         s_cx.pre_on = pre_on; s_cx.wdep = wdep; s_cx.reduce_mean = C.reduction == SNN_REDUCE_MEAN; s_cx.has_clamp = C.has_clamp;
         s_cx.Bf = Bf; s_cx.dts = dts; s_cx.weight_decay = C.weight_decay; s_cx.wmin = C.wmin; s_cx.wmax = C.wmax;
@@ -355,7 +571,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     for (int k = tid; k < 64; k += nthr) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
     #pragma unroll 1
     for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
-    for (int k = tid; k < 256; k += nthr) M.wslot[k] = -1;
     if (X.traces)
         for (int o = 0; o < own; ++o) {
             const int bo = blockIdx.x + o * (int)G;
@@ -401,8 +616,20 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     }
     uint32_t ph0 = 0, ph1 = 0;
     // input trace of step 0 for the samples this CTA owns, published in xpub slot 0
+    // Warp 0 is busy with the grid barrier while the others publish: work is spread over the threads
+    // ptid = tid - 32 (all threads when the block is a single warp).  The spike bits of the first
+    // item of each of the first two owned samples can be loaded ahead (publish_load) so that their
+    // L2 latency hides behind the early STDP.
+    const int ptid = nthr > 32 ? tid - 32 : tid, pn = nthr > 32 ? nthr - 32 : nthr;
+    uint32_t pubw0 = 0, pubw1 = 0;
+    auto publish_load = [&](int step) {
+        if (!X.traces || (Q.dbg & 8) || ptid < 0 || ptid >= (P >> 2)) return;
+        const int b0_ = blockIdx.x, b1_ = blockIdx.x + (int)G;
+        if (b0_ < B) pubw0 = __ldg(Q.inS + ((size_t)(step + 1) * B + b0_) * Q.SW + (ptid >> 3));
+        if (own > 1 && b1_ < B) pubw1 = __ldg(Q.inS + ((size_t)(step + 1) * B + b1_) * Q.SW + (ptid >> 3));
+    };
     auto publish_trace = [&](int step) {
-        if (!X.traces || (Q.dbg & 8)) return;
+        if (!X.traces || (Q.dbg & 8) || ptid < 0) return;
         for (int o = 0; o < own; ++o) {
             const int bo = blockIdx.x + o * (int)G;
             if (bo < B) {
@@ -410,8 +637,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
                 float4 *dst = (float4 *)(Q.xpub + ((size_t)(step % 3) * B + bo) * P);
                 float4 *xo = (float4 *)(xown + o * P);
                 #pragma unroll 1
-                for (int i4 = tid; i4 < (P >> 2); i4 += nthr) {
-                    const uint32_t bits = __ldg(srow + (i4 >> 3)) >> ((i4 & 7) * 4);
+                for (int i4 = ptid; i4 < (P >> 2); i4 += pn) {
+                    const uint32_t word = (i4 == ptid && o < 2) ? (o == 0 ? pubw0 : pubw1) : __ldg(srow + (i4 >> 3));
+                    const uint32_t bits = word >> ((i4 & 7) * 4);
                     float4 x = xo[i4];
                     x.x = trace_step(x.x, bits & 1u, X.trace_decay, X.trace_scale, X.traces_additive);
                     x.y = trace_step(x.y, bits & 2u, X.trace_decay, X.trace_scale, X.traces_additive);
@@ -423,12 +651,45 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             }
         }
     };
+    publish_load(0);
     publish_trace(0);
     __syncthreads();
+
+    // spike-gather of my 4 columns for the spikes of list block `blk` (slot `slot`):
+    // p[c] = sum_{i in sX[b]} W[i][c], i ascending (topology.py:437-479)
+    auto gather = [&](const unsigned char *blk, int slot) -> float4 {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        const int cnt = ((const uint16_t *)blk)[b];
+        if (Q.dbg & 4) {
+        } else if (cnt <= EV_CAP) {
+            const uint2 *l4 = (const uint2 *)(blk + cntb + b * (2 * EV_CAP));
+            #pragma unroll 1
+            for (int k = 0; k < cnt; k += 4) {
+                const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
+                const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
+                const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
+                const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
+                const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * WS);
+                p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
+                p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
+                p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
+                p0 = p0 + r3.x; p1 = p1 + r3.y; p2 = p2 + r3.z; p3 = p3 + r3.w;
+            }
+        } else {  // dense sample: walk the bit row in global memory (rare, slow path)
+            return gather_dense(Q.inS + ((size_t)slot * B + b) * Q.SW, Q.SW, Wc, WS);
+        }
+        return make_float4(p0, p1, p2, p3);
+    };
+    // The gather of step t+1 runs in the shadow of barrier t for the column groups whose W is
+    // already final (no candidate at step t); step 0's gather runs in D(0).
+    float4 pg = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool pg_done = false;
+    int myslot = -1;           // staged input-trace row of my sample's candidates (step being finalised)
 
     // =====================================================================================
     PROF(0)  // prologue
     uint32_t pend = 0;         // my candidates of the step being finalised are still undecided
+    int dflag = 0;
     for (int t = 0; t <= T; ++t) {
         const int buf = t & 1;                                       // slot t   = spikes of step t-1
         const unsigned char *cE = evb + buf * evblk;
@@ -438,7 +699,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         const int xs = (t + 2) % 3;
         unsigned long long key = 0ull;
         if (act && t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
-        const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
+        // Ai spike count of step t-1 (lateral inhibition): issued here, consumed by the neuron update
+        const unsigned int isum = act ? __ldcg(Q.sisum + xs * B + b) : 0u;
+        const uint32_t lategrp = t > 0 ? (M.candgrp[ppar] | ((Q.dbg & 64) ? 1u : 0u)) : 0u;  // groups that held a candidate at t-1
         // stage the input-trace rows of this tile's candidate samples (the possible winners) in
         // shared memory: issued together with the exchange loads, so one L2 round trip covers both
         if (t > 0 && stage_on && lategrp && !(Q.dbg & 16)) {
@@ -482,6 +745,8 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
                                 if ((sE >> c) & 1u) {
                                     atomicOr(&M.wmask[4 * cg + c][b >> 5], 1u << (b & 31));
                                     atomicOr(&M.colwin, 1u << (4 * cg + c));
+                                    const int k = atomicAdd(&M.nwl, 1);
+                                    if (k < 4) M.wl[k] = ((uint32_t)(4 * cg + c) << 16) | ((uint32_t)b << 8) | (myslot >= 0 ? (uint32_t)myslot : 0xffu);
                                 }
                         }
                     }
@@ -513,161 +778,63 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         PROF(12)  // late finalise (winner, trace, monitors)
         if (t > 0 && update_on && lategrp) {
-            // STDP of step t-1 for the column groups that held a candidate: ONE row loop per group,
-            // every row visited (two per thread): pre term where a live sample spiked at the pixel,
-            // post term on the winner columns of the group (MCC_learning.py:234-299), decay, clamp.
+            // STDP of step t-1 for the column groups that held a candidate (MCC_learning.py:234-299).
             __syncthreads();
             const uint32_t colwin = post_on ? M.colwin : 0u;
             const bool full = decay_on || (C.has_clamp && t == 1);
-            const uint4 *cTl = (const uint4 *)(inT + buf * P * BW);
-            const int ns = min(M.ncand[ppar], XR);
             PROF(13)  // late sync
-            // fast path for the typical case: one group, at most one winner column with one
-            // (staged) winner — short straight-line code, because this path gates the whole grid
-            bool fast = BW == 4 && !wdep && C.reduction == SNN_REDUCE_SUM && !full && (lategrp & (lategrp - 1)) == 0 &&
-                        (colwin & (colwin - 1)) == 0;
-            int fj = -1, frow = 0;
-            if (fast && colwin) {
-                fj = __ffs(colwin) - 1;
-                const uint32_t w0 = M.wmask[fj][0], w1 = M.wmask[fj][1], w2 = M.wmask[fj][2], w3 = M.wmask[fj][3];
-                const int nw = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
-                const int bb = w0 ? __ffs(w0) - 1 : (w1 ? 32 + __ffs(w1) - 1 : (w2 ? 64 + __ffs(w2) - 1 : 96 + __ffs(w3) - 1));
-                int sl = -1;
-                for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
-                fast = nw == 1 && sl >= 0;
-                frow = sl * P;
+            // Typical case — at most 4 winners in the tile, in distinct columns, their input-trace rows
+            // staged: the row pass shared with the early STDP (its code is resident in the instruction
+            // cache; this path gates the whole grid).  Anything else takes the general form.
+            const int nwl = post_on ? M.nwl : 0;
+            bool fast = !wdep && C.reduction == SNN_REDUCE_SUM && !full && nwl <= 4 && nwl == __popc(colwin);
+            if (fast && nwl) {
+                const uint4 wl4 = *(const uint4 *)M.wl;  // column << 16 | sample << 8 | row slot (0xff: not staged)
+                if ((wl4.x & 0xffu) == 0xffu || (nwl > 1 && (wl4.y & 0xffu) == 0xffu) || (nwl > 2 && (wl4.z & 0xffu) == 0xffu) ||
+                    (nwl > 3 && (wl4.w & 0xffu) == 0xffu))
+                    fast = false;
             }
-            if (fast) {
-                const int c4 = __ffs(lategrp) - 1;
-                const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
-                const int fc = fj >= 0 ? fj - 4 * c4 : -1;     // winner column inside the group
-                #pragma unroll 1
-                for (int i = tid; i < P; i += nthr) {
-                    const uint4 q0 = cTl[i];
-                    const uint32_t m0 = q0.x & z0.x, m1 = q0.y & z0.y, m2 = q0.z & z0.z, m3 = q0.w & z0.w;
-                    const bool pre_t = (m0 | m1 | m2 | m3) != 0u;
-                    if (!pre_t && fc < 0) continue;
-                    float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
-                    if (pre_t) {
-                        uint32_t mw[4] = {m0, m1, m2, m3};
-                        #pragma unroll 1
-                        for (int g = 0; g < 4; ++g) {
-                            uint32_t mm = mw[g];
-                            while (mm) {
-                                const int bb = g * 32 + __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
-                                U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
-                            }
-                        }
-                    }
-                    float *wp = W + i * WS + 4 * c4;
-                    float4 w4 = *(const float4 *)wp;
-                    if (pre_t) { w4.x = w4.x - U0 * dts; w4.y = w4.y - U1 * dts; w4.z = w4.z - U2 * dts; w4.w = w4.w - U3 * dts; }
-                    if (fc >= 0) {
-                        const float V = (0.0f + xrow[frow + i] * C.nu1) * dts;
-                        if (fc == 0) w4.x = w4.x + V; else if (fc == 1) w4.y = w4.y + V; else if (fc == 2) w4.z = w4.z + V; else w4.w = w4.w + V;
-                    }
-                    if (C.weight_decay != 0.0f) { w4.x *= C.weight_decay; w4.y *= C.weight_decay; w4.z *= C.weight_decay; w4.w *= C.weight_decay; }
-                    if (C.has_clamp) {
-                        w4.x = clampf(w4.x, C.wmin, C.wmax); w4.y = clampf(w4.y, C.wmin, C.wmax);
-                        w4.z = clampf(w4.z, C.wmin, C.wmax); w4.w = clampf(w4.w, C.wmin, C.wmax);
-                    }
-                    *(float4 *)wp = w4;
-                }
-            } else
-            for (uint32_t lg = lategrp; lg; lg &= lg - 1) {
-                const int c4 = __ffs(lg) - 1;
-                const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
-                // staged trace-row offset of each winner (ascending sample order) per winner column
-                int nwin[4] = {0, 0, 0, 0}, wrow[4][2];
-                bool generic = false;
-                #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (!((gwin >> c) & 1u)) continue;
-                    for (int g = 0; g < BW; ++g) {
-                        uint32_t mm = M.wmask[4 * c4 + c][g];
-                        while (mm) {
-                            const int bb = g * 32 + __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            int sl = -1;
-                            for (int q = 0; q < ns; ++q) if (M.candb[ppar][q] == bb) sl = q;
-                            if (nwin[c] < 2 && sl >= 0) wrow[c][nwin[c]] = sl * P; else generic = true;
-                            ++nwin[c];
-                        }
-                    }
-                }
-                const uint4 z0 = pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
-                const float *xsrc = Q.xpub + (size_t)((t - 1) % 3) * B * P;
-                for (int i = tid; i < P; i += nthr) {
-                    uint32_t m[BW];
-                    const uint4 q0 = cTl[i * (BW / 4)];
-                    m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
-                    uint32_t anym = m[0] | m[1] | m[2] | m[3];
-                    if (BW == 8) {
-                        const uint4 q1 = cTl[i * (BW / 4) + 1];
-                        const uint4 z1 = pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
-                        m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
-                        anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
-                    }
-                    const bool pre_t = anym != 0u;
-                    if (!(pre_t || gwin || full)) continue;
-                    float U[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (pre_t) {
-                        #pragma unroll 1
-                        for (int g = 0; g < BW; ++g) {
-                            uint32_t mm = m[g];
-                            while (mm) {
-                                const int bb = g * 32 + __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                const float4 t4 = *(const float4 *)(tx + bb * TJ + 4 * c4);
-                                U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
-                            }
-                        }
-                        if (C.reduction == SNN_REDUCE_MEAN) { U[0] = U[0] / Bf; U[1] = U[1] / Bf; U[2] = U[2] / Bf; U[3] = U[3] / Bf; }
-                    }
-                    float *wp = W + i * WS + 4 * c4;
-                    const float4 w4 = *(const float4 *)wp;
-                    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const bool post_t = (gwin >> c) & 1u;
-                        float V = 0.0f;
-                        if (post_t) {
-                            if (!generic) {
-                                V = V + xrow[wrow[c][0] + i] * (wdep ? 1.0f : C.nu1);
-                                if (nwin[c] > 1) V = V + xrow[wrow[c][1] + i] * (wdep ? 1.0f : C.nu1);
-                            } else {  // more winners than staged rows: read them from L2 (rare)
-                                for (int g = 0; g < BW; ++g) {
-                                    uint32_t mm = M.wmask[4 * c4 + c][g];
-                                    while (mm) {
-                                        const int bb = g * 32 + __ffs(mm) - 1;
-                                        mm &= mm - 1;
-                                        V = V + __ldcg(xsrc + (size_t)bb * P + i) * (wdep ? 1.0f : C.nu1);
-                                    }
-                                }
-                            }
-                            if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
-                        }
-                        if (!wdep) {
-                            float w = wv[c];
-                            if (pre_t) w = w - U[c] * dts;
-                            if (post_t) w = w + V * dts;
-                            if (C.weight_decay != 0.0f) w = w * C.weight_decay;
-                            if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);
-                            wv[c] = w;
-                        } else {
-                            wv[c] = apply_rule(C, wv[c], U[c], pre_t, V, post_t);
-                        }
-                    }
-                    *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
-                }
+            if (PROFV && tid == 0) {
+                long long *lc = M.lc;
+                lc[0] += 1; lc[1] += fast ? 1 : 0;
+                lc[4] += colwin ? 1 : 0; lc[6] += M.ncand[ppar];
+                if (fast) lc[2] += clock64() - pt;   // set-up
             }
+            if (fast && !M.denseflag[buf]) {
+                // pre term through the list pass the early STDP uses every step (its code is resident),
+                // then the post term: one scalar update per (row, winner column); constants from shared
+                // memory (a rarely used kernel-parameter line costs a constant-cache miss per use here)
+                if (pre_on) {
+                    stdp_list<TJ, BW>(&s_cx, buf, lategrp, colwin, tid, nthr);
+                    __syncthreads();
+                }
+                if (nwl) {
+                    const float l_dts = s_cx.dts, l_nu1 = s_cx.nu1, l_wmin = s_cx.wmin, l_wmax = s_cx.wmax, l_wd = s_cx.weight_decay;
+                    const int l_clamp = s_cx.has_clamp, l_P = s_cx.P;
+                    #pragma unroll 1
+                    for (int k = 0; k < nwl; ++k) {
+                        const uint32_t e = M.wl[k];  // column << 16 | sample << 8 | staged row slot
+                        float *wcol = W + (e >> 16);
+                        const float *xr = xrow + (e & 0xffu) * l_P;
+                        #pragma unroll 1
+                        for (int i = tid; i < l_P; i += nthr) {
+                            float w = wcol[i * WS];
+                            const float V = 0.0f + xr[i] * l_nu1;
+                            w = w + V * l_dts;
+                            if (l_wd != 0.0f) w = w * l_wd;
+                            if (l_clamp) w = clampf(w, l_wmin, l_wmax);
+                            wcol[i * WS] = w;
+                        }
+                    }
+                }
+            } else if (fast) stdp_rows<TJ, BW>(&s_cx, buf, lategrp, nwl, colwin, 0);
+            else late_generic_fn<TJ, BW>(&s_cx, &Q0.C, buf, ppar, lategrp, colwin, full ? 1 : 0, Q.xpub + (size_t)((t - 1) % 3) * B * P);
+            if (PROFV && Q.prof && tid == 0) { const long long now_ = clock64(); if (fast) M.lc[7] += now_ - pt; }
             PROF(14)  // late group pass
             __syncthreads();
             if (colwin) {
                 for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
-                if (tid == 0) M.colwin = 0;
+                if (tid == 0) { M.colwin = 0; M.nwl = 0; }
             }
         }
         PROF(2)  // late finalise + late STDP
@@ -685,40 +852,10 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         uint32_t cand = 0, sI = 0;
         unsigned long long mykey = 0ull;
         int nI = 0;
-        // Ai spike count of step t-1 (lateral inhibition): issued here, consumed after the gather
-        const unsigned int isum = act ? __ldcg(Q.sisum + xs * B + b) : 0u;
         if (act) {
-            // spike-gather: p[c] = sum_{i in sX(t-1)[b]} W[i][c], i ascending (topology.py:437-479)
-            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-            const int cnt = ((const uint16_t *)cE)[b];
-            if (Q.dbg & 4) {
-            } else if (cnt <= EV_CAP) {
-                const uint2 *l4 = (const uint2 *)(cE + cntb + b * (2 * EV_CAP));
-                #pragma unroll 1
-                for (int k = 0; k < cnt; k += 4) {
-                    const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
-                    const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
-                    const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
-                    const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
-                    const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * WS);
-                    p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
-                    p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
-                    p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
-                    p0 = p0 + r3.x; p1 = p1 + r3.y; p2 = p2 + r3.z; p3 = p3 + r3.w;
-                }
-            } else {  // dense sample: walk the bit row in global memory (rare, slow path)
-                const uint32_t *row = Q.inS + ((size_t)t * B + b) * Q.SW;
-                for (int w = 0; w < Q.SW; ++w) {
-                    uint32_t word = __ldg(row + w);
-                    while (word) {
-                        const int i = w * 32 + __ffs(word) - 1;
-                        word &= word - 1;
-                        const float4 r4 = *(const float4 *)(Wc + i * WS);
-                        p0 = p0 + r4.x; p1 = p1 + r4.y; p2 = p2 + r4.z; p3 = p3 + r4.w;
-                    }
-                }
-            }
-            const float p[4] = {p0, p1, p2, p3};
+            // columns whose step-(t-1) STDP was late (or everything, first time): gather now
+            if (!pg_done) pg = gather(cE, t);
+            const float p[4] = {pg.x, pg.y, pg.z, pg.w};
             const float4 th4 = *(const float4 *)(theta_s + 4 * cg);
             float th[4] = {th4.x, th4.y, th4.z, th4.w};
             #pragma unroll
@@ -772,15 +909,17 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             nI += __shfl_xor_sync(0xffffffffu, nI, o);
             anyc |= __shfl_xor_sync(0xffffffffu, anyc, o);
         }
+        int slot_ = -1;
         if (act && cg == 0) {
             const int ws = t % 3;
             if (mykey) atomicMax(Q.win + ws * B + b, mykey);
             if (nI) atomicAdd(Q.sisum + ws * B + b, (unsigned int)nI);
             if (anyc && (stage_on || (PROFV && Q.prof))) {
                 const int s = atomicAdd(&M.ncand[par], 1);
-                if (s < XR) M.candb[par][s] = b;
+                if (s < XR) { M.candb[par][s] = b; slot_ = s; }
             }
         }
+        myslot = __shfl_sync(0xffffffffu, slot_, (tid & 31) & ~(CG - 1));  // from the sample's first lane
         candE = cand;
         pend = cand;
         sIprev = sI;
@@ -802,6 +941,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             mbar_expect_tx(&M.mbar[buf], bytesE + bytesT);
             bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar[buf]);
             bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar[buf]);
+            dflag = __ldg(Q.dense + t + 2);  // stored below, read by the early pass one step from now
         }
         // ---- arrive(t): this CTA's contributions to step t's exchange are issued -----------------
         PROF(6)  // theta, prefetch issue
@@ -809,16 +949,30 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         gen += 1;
         PROF(15)  // arrive (release)
         // ---- early(t): in the shadow of the barrier ------------------------------------------------
+        if (t + 1 < T) publish_load(t + 1);
+        const int nb = buf ^ 1;                                      // slot t+1 = spikes of step t
+        while (!mbar_try_wait(&M.mbar[nb], nb ? ph1 : ph0)) {}      // landed? (phase is consumed by D(t+1))
         if (update_on) {
-            const int nb = buf ^ 1;                                  // slot t+1 = spikes of step t
-            while (!mbar_try_wait(&M.mbar[nb], nb ? ph1 : ph0)) {}  // landed? (phase is consumed by D(t+1))
             const uint32_t allg = (1u << CG) - 1u;
             const uint32_t earlygrp = allg & ~M.candgrp[par];
             const bool full = decay_on || (C.has_clamp && t == 0);
-            stdp_pass_fn<TJ, BW>(&s_cx, nb, t + 1, earlygrp, 0u, full, (uint32_t)((2 * t + 2) & 0xffff));
+            // list form while every sample's event list is complete; row form otherwise
+            if (full || M.denseflag[nb]) stdp_rows<TJ, BW>(&s_cx, nb, earlygrp, 0, 0u, full ? 1 : 0);
+            else if (pre_on) stdp_list<TJ, BW>(&s_cx, nb, earlygrp, 0u, nthr > 32 ? tid - 32 : tid, nthr > 32 ? nthr - 32 : nthr);
         }
         PROF(7)  // early STDP
+        pg_done = false;
+        if (Q.pregather && t + 1 < T) {
+            __syncthreads();  // early STDP complete: W of the groups without a candidate is final for step t+1
+            const uint32_t cgrp = update_on ? M.candgrp[par] : 0u;
+            if (!((cgrp >> cg) & 1u)) {
+                if (act) pg = gather(evb + nb * evblk, t + 1);
+                pg_done = true;
+            }
+        }
+        PROF(10)  // pre-gather
         if (t + 1 < T) publish_trace(t + 1);  // input trace of step t+1 (its winners read it after barrier t+1)
+        if (tid == 32 % nthr && t + 2 <= T) M.denseflag[buf] = dflag;
         PROF(8)  // trace publish
         // ---- wait(t) ----------------------------------------------------------------------------
         if (tid == 0 && !(Q.dbg & 1)) {
@@ -886,7 +1040,10 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     }
     PROF(11)  // epilogue (partial)
     if (PROFV && Q.prof && tid == 0)
-        for (int k = 0; k < NPROF; ++k) { Q.prof[blockIdx.x * NPROF + k] = pc[k]; Q.prof[(160 + blockIdx.x) * NPROF + k] = pm[k]; }
+    {
+        for (int k = 0; k < NPROF; ++k) { Q.prof[blockIdx.x * NPROF + k] = pc[k]; Q.prof[(160 + blockIdx.x) * NPROF + k] = 0; }
+        for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long *)(Q.prof + 320 * NPROF + NPROF * 32 * 160 + 600 + k), (unsigned long long)M.lc[k]);
+    }
     for (int o = 0; o < own; ++o) {
         const int bo = blockIdx.x + o * (int)G;
         if (bo < B) {
@@ -1108,6 +1265,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.exc = net->conns[m.cEI].structure_val; Q.inh_neg = net->conns[m.cIE].structure_val;
     Q.T = T; Q.B = B; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
     { const char *d = getenv("SNN_B200_DEBUG"); Q.dbg = d ? atoi(d) : 0; }
+    { const char *d = getenv("SNN_B200_PREGATHER"); Q.pregather = d ? atoi(d) : 0; }
     Q.SW = m.SW; Q.SB = m.SB; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
     Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
     Q.win = (unsigned long long *)(ws + WL.win); Q.sisum = (unsigned int *)(ws + WL.sisum);
@@ -1117,6 +1275,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.dense = (int *)(ws + WL.dense);
     // barrier words and per-slot dense flags are adjacent: one memset node
     if (cudaMemsetAsync(Q.bar, 0, WL.inS - WL.bar, stream) != cudaSuccess) return SNN_ERR_CUDA;
+    if (prof && cudaMemsetAsync(Q.prof + 320 * NPROF + NPROF * 32 * 160 + 600, 0, 8 * sizeof(long long), stream) != cudaSuccess) return SNN_ERR_CUDA;
     snn_dc_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
@@ -1141,7 +1300,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
-                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(counts)", "epilogue",
+                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "pre-gather", "epilogue",
                                            "late finalise", "late sync", "late group pass", "arrive (release)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
@@ -1164,7 +1323,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 int gmax = 0; double maxw = -1, meanw = 0;
                 for (int g = 0; g < m.grid; ++g) {
                     double w = 0;
-                    for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
+                    for (int k = 1; k <= 15; ++k) if (k <= 8 || k == 10 || k >= 12) w += (double)(tr[(st * 160 + g) * NPROF + k] - tr[((st - 1) * 160 + g) * NPROF + k]);
                     meanw += w / m.grid;
                     if (w > maxw) { maxw = w; gmax = g; }
                 }
@@ -1175,18 +1334,23 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
                 s_maxw += maxw; s_meanw += meanw; ++cnt;
             }
             {
-                double nc = 0, ng = 0, nwc = 0;
-                for (int g = 0; g < m.grid; ++g) { nc += (double)hostp[g * NPROF + 10]; ng += (double)hostp[(160 + g) * NPROF + 10]; nwc += (double)hostp[(160 + g) * NPROF + 9]; }
-                fprintf(stderr, "  per CTA-step: candidate samples %.3f, candidate column groups %.3f, winner columns %.3f\n", nc / m.grid / T, ng / m.grid / T, nwc / m.grid / T);
+                long long lcs[8];
+                double tot14 = 0;
+                for (int g = 0; g < m.grid; ++g) tot14 += (double)hostp[g * NPROF + 14];
+                cudaMemcpy(lcs, Q.prof + 320 * NPROF + NPROF * 32 * 160 + 600, sizeof(lcs), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "  late passes %lld (%.1f%% of CTA-steps): fast %lld, set-up cycles %lld, set-up + first row cycles %lld, with winner %lld, pre-part cycles %lld, "
+                        "candidate samples per pass %.2f; cycles per fast pass %.0f, per other pass %.0f\n", lcs[0], 100.0 * lcs[0] / ((double)m.grid * T), lcs[1], lcs[2], lcs[3], lcs[4], lcs[5],
+                        (double)lcs[6] / (lcs[0] ? lcs[0] : 1), (double)lcs[7] / (lcs[1] ? lcs[1] : 1),
+                        (tot14 - (double)lcs[7]) / (lcs[0] - lcs[1] ? lcs[0] - lcs[1] : 1));
             }
             fprintf(stderr, "  per-step (t=101..131): work mean %.0f, work of the slowest CTA of each step %.0f; by phase (mean CTA / slowest CTA):\n", s_meanw / cnt, s_maxw / cnt);
-            for (int k = 1; k <= 15; ++k) if (k != 10 && k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
+            for (int k = 1; k <= 15; ++k) if (k != 11) fprintf(stderr, "      %-18s %8.0f %8.0f\n", names[k], mean[k] / cnt, slow[k] / cnt);
         }
         {
             double sum = 0, mx = 0, mn = 1e300; int amx = 0, amn = 0;
             for (int g = 0; g < m.grid; ++g) {
                 double v = 0;
-                for (int k = 1; k <= 15; ++k) if (k <= 8 || k >= 12) v += (double)hostp[g * NPROF + k];
+                for (int k = 1; k <= 15; ++k) if (k <= 8 || k == 10 || k >= 12) v += (double)hostp[g * NPROF + k];
                 sum += v; if (v > mx) { mx = v; amx = g; } if (v < mn) { mn = v; amn = g; }
             }
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
