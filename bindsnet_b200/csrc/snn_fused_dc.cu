@@ -976,10 +976,26 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         PROF(8)  // trace publish
         // ---- wait(t) ----------------------------------------------------------------------------
         if (tid == 0 && !(Q.dbg & 1)) {
+            // three polling loads kept in flight a third of an L2 round trip apart: the completion is
+            // seen ~1/6 of a round trip after it becomes visible instead of ~1/2
             const unsigned int target = G * gen;
             const long long t0 = clock64();
-            while ((int)(ld_relaxed_u32(Q.bar) - target) < 0) {
-                if (clock64() - t0 > 4000000000LL) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
+            unsigned int r0 = ld_relaxed_u32(Q.bar), r1 = r0, r2 = r0;
+            if ((int)(r0 - target) < 0) {
+                r0 = ld_relaxed_u32(Q.bar);
+                { const long long s0 = clock64(); while (clock64() - s0 < 220) {} }
+                r1 = ld_relaxed_u32(Q.bar);
+                { const long long s0 = clock64(); while (clock64() - s0 < 220) {} }
+                r2 = ld_relaxed_u32(Q.bar);
+                for (;;) {
+                    if ((int)(r0 - target) >= 0) break;
+                    r0 = ld_relaxed_u32(Q.bar);
+                    if ((int)(r1 - target) >= 0) break;
+                    r1 = ld_relaxed_u32(Q.bar);
+                    if ((int)(r2 - target) >= 0) break;
+                    r2 = ld_relaxed_u32(Q.bar);
+                    if (clock64() - t0 > 4000000000LL) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
+                }
             }
             asm volatile("fence.acquire.gpu;" ::: "memory");
         }
