@@ -1089,10 +1089,65 @@ __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ Fu
     uint16_t *ecnt = (uint16_t *)blk;
     uint16_t *elist = (uint16_t *)(blk + ev_count_bytes(B));
     bool nonbin = false, dense = false;
+    // fast path: byte spikes (uint8 / bool input, or the layer's own spike state for slot 0) in
+    // 16-byte aligned rows — one 16-byte load per lane covers 16 pixels
+    const bool bytes_in = slot == 0 || (X.ext && X.ext_dtype == SNN_EXT_U8);
+    const unsigned char *src0 = slot == 0 ? (const unsigned char *)X.s : (const unsigned char *)X.ext + (size_t)(slot - 1) * B * P;
+    const bool fast16 = bytes_in && (P & 15) == 0 && (((size_t)src0) & 15) == 0 && (((size_t)X.rec_s) & 15) == 0;
     for (int bl = warp; bl < 32; bl += nwarp) {
         const int b = b0 + bl;
         int total = 0;
-        if (b < B) {
+        if (b < B && fast16) {
+            uint16_t *lst = elist + b * EV_CAP;
+            const uint4 *row = (const uint4 *)(src0 + (size_t)b * P);
+            unsigned char *rec = (slot > 0 && X.rec_s) ? X.rec_s + ((size_t)(slot - 1) * B + b) * P : nullptr;
+            const int nchunk = P >> 4;
+            for (int c0 = 0; c0 < nchunk; c0 += 32) {
+                const int c = c0 + lane;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (c < nchunk) v = __ldg(row + c);
+                if (slot > 0) nonbin |= ((v.x | v.y | v.z | v.w) & 0xfefefefeu) != 0u;
+                const uint32_t zx = __vcmpne4(v.x, 0u) & 0x01010101u, zy = __vcmpne4(v.y, 0u) & 0x01010101u,
+                               zz = __vcmpne4(v.z, 0u) & 0x01010101u, zw = __vcmpne4(v.w, 0u) & 0x01010101u;
+                if (rec && c < nchunk) ((uint4 *)rec)[c] = make_uint4(zx, zy, zz, zw);
+                // 4 flag bytes -> 4 bits: the multiply moves byte k's bit 0 to bit 24 + k
+                const uint32_t m16 = ((zx * 0x01020408u) >> 24) | (((zy * 0x01020408u) >> 24) << 4) | (((zz * 0x01020408u) >> 24) << 8) |
+                                     (((zw * 0x01020408u) >> 24) << 12);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, m16, 1);
+                if (!(lane & 1)) {  // even lane: the 32-pixel word of chunks c, c + 1
+                    const int w = c >> 1;
+                    if (w < SW) {
+                        const uint32_t word = m16 | (other << 16);
+                        sbits[bl * SW + w] = word;
+                        Q.inS[((size_t)slot * B + b) * SW + w] = word;
+                    }
+                }
+                // ascending pixel list: position = spikes before me
+                const int mine = __popc(m16);
+                int incl = mine;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                int pos = total + incl - mine;
+                uint32_t mm = m16;
+                while (mm) {
+                    const int bit = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (pos < EV_CAP) lst[pos] = (uint16_t)(c * 16 + bit);
+                    ++pos;
+                }
+                total += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            for (int w = (P >> 5) + lane; w < SW; w += 32) {  // words past the last pixel (odd chunk count: half word above)
+                if (w * 32 >= P) { sbits[bl * SW + w] = 0u; Q.inS[((size_t)slot * B + b) * SW + w] = 0u; }
+            }
+            const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
+            if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+            if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
+            dense |= total > EV_CAP;
+        } else if (b < B) {
             uint16_t *lst = elist + b * EV_CAP;
             for (int w = 0; w < SW; ++w) {
                 const int i = w * 32 + lane;
@@ -1126,17 +1181,18 @@ __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ Fu
     if (grp == 0 && threadIdx.x < 8) ecnt[B + threadIdx.x] = 0;
     __syncthreads();
     // transpose 32x32 bit blocks: inT[pixel][grp] bit b' = inS[b0+b'][pixel/32] bit pixel%32
+    // (5 butterfly steps: lanes l and l ^ j swap the bit blocks whose index differs in bit j)
     for (int w = warp; w < PW; w += nwarp) {
-        const uint32_t word = sbits[lane * SW + w];
-        uint32_t mine = 0;
+        uint32_t x = sbits[lane * SW + w];
         #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const uint32_t mm = __ballot_sync(0xffffffffu, (word >> r) & 1u);
-            if (lane == r) mine = mm;
+        for (int j = 16; j >= 1; j >>= 1) {
+            const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            x = (lane & j) ? (((y & ~m) >> j) | (x & ~m)) : ((x & m) | ((y & m) << j));
         }
         const int i = w * 32 + lane;
         if (i < P) {
-            Q.inT[((size_t)slot * P + i) * BW + grp] = mine;
+            Q.inT[((size_t)slot * P + i) * BW + grp] = x;
             if (grp == 0)  // zero the padding groups of the per-pixel masks
                 for (int g = (B + 31) / 32; g < BW; ++g) Q.inT[((size_t)slot * P + i) * BW + g] = 0u;
         }

@@ -9,6 +9,10 @@ device staging) while the window kernel of batch k runs, and hands ``run`` a dev
     pre = WindowPrefetcher(device, iter_of_host_tensors)
     for x_dev in pre:                 # x_dev is ready on the compute stream
         net.run({"X": x_dev}, time=T)
+
+``AsyncReadback`` is the other direction: the per-window result (spike counts for label assignment,
+``examples/mnist/batch_eth_mnist.py:300-318``) is copied to pinned host memory without stalling the
+launch of the next window; the host consumes window k-1's result while window k runs.
 """
 from __future__ import annotations
 
@@ -78,3 +82,47 @@ class WindowPrefetcher:
         """Record that the consumer is done with the tensor returned last (call after ``run``)."""
         slot, ev = self._last
         ev.record(torch.cuda.current_stream(self.device))
+
+
+class AsyncReadback:
+    """Device→host result pipeline: ``push`` enqueues a non-blocking copy of a device tensor into a
+    ring of pinned host buffers; ``pop`` returns the oldest copy once it has landed (waiting only on
+    that copy's event, never on later launches).
+
+        rb = AsyncReadback(depth=2)
+        for x_dev in pre:
+            net.run({"X": x_dev}, time=T)
+            rb.push(counter.get("s"))
+            if len(rb) == rb.depth:      # window k-1's counts, while window k runs
+                use(rb.pop())
+        while len(rb): use(rb.pop())
+    """
+
+    def __init__(self, depth: int = 2):
+        self.depth = max(1, depth)
+        self._host = [None] * self.depth
+        self._queue = []   # (slot, event) in submission order
+        self._k = 0
+
+    def __len__(self) -> int:
+        return len(self._queue)
+
+    def push(self, t: torch.Tensor) -> None:
+        if len(self._queue) >= self.depth:
+            raise RuntimeError("AsyncReadback ring is full: pop() before pushing again")
+        slot = self._k % self.depth
+        self._k += 1
+        h = self._host[slot]
+        if h is None or h.shape != t.shape or h.dtype != t.dtype:
+            h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._host[slot] = h
+        h.copy_(t, non_blocking=True)            # stream-ordered after the producer of ``t``
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        self._queue.append((slot, ev))
+
+    def pop(self) -> torch.Tensor:
+        """Oldest result as a pinned host tensor (valid until ``depth`` further pushes)."""
+        slot, ev = self._queue.pop(0)
+        ev.synchronize()
+        return self._host[slot]
