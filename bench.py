@@ -261,7 +261,9 @@ def main():
 
     def use(counts_host):
         consumed[0] += 1
-        consumed[1] += int(counts_host.sum())  # the host really reads the [B, n] int32 result
+        # the host really reads the [B, n] int32 result (numpy: a single-threaded pass; torch's CPU
+        # reduction would wake a 128-thread pool per call, which costs milliseconds on this box)
+        consumed[1] += int(counts_host.numpy().sum())
 
     rb = AsyncReadback(depth=2)  # pinned host ring, allocated once
 
@@ -283,6 +285,14 @@ def main():
 
     e2e_loop(W, 0)
     barrier()
+    # host->device bandwidth of this box for one window of spikes (context for the e2e number:
+    # 25 MB per window has to cross PCIe inside every timed step)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    resident[0].copy_(host[0], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = host[0].numel() * host[0].element_size() / (h0.elapsed_time(h1) * 1e-3) / 1e9
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -324,7 +334,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T_STEPS * BATCH * N_INPT,
                     "d2h_bytes_per_step": BATCH * N_NEURONS * 4,
                     "note": "pinned host uint8 spike trains -> WindowPrefetcher (H2D on a side stream, overlapped) -> Network.run + SpikeCounter on Ae -> AsyncReadback: the [B, n] per-sample spike counts (what label assignment consumes) copied to pinned host memory and read there every window, one window behind the launches",
-                    "wall_s": wall_e2e, "windows_read_on_host": consumed[0], "ae_spikes_seen_on_host": consumed[1]},
+                    "wall_s": wall_e2e, "h2d_gbs_measured": h2d_gbs, "windows_read_on_host": consumed[0], "ae_spikes_seen_on_host": consumed[1]},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -85,9 +85,10 @@ class WindowPrefetcher:
 
 
 class AsyncReadback:
-    """Device→host result pipeline: ``push`` enqueues a non-blocking copy of a device tensor into a
-    ring of pinned host buffers; ``pop`` returns the oldest copy once it has landed (waiting only on
-    that copy's event, never on later launches).
+    """Device→host result pipeline: ``push`` snapshots a device tensor (device-to-device, on the
+    caller's stream), then copies the snapshot into a ring of pinned host buffers on a side stream,
+    so that neither the copy nor the host's read of it delays the next window's launch; ``pop``
+    returns the oldest copy once it has landed (waiting only on that copy's event).
 
         rb = AsyncReadback(depth=2)
         for x_dev in pre:
@@ -101,8 +102,11 @@ class AsyncReadback:
     def __init__(self, depth: int = 2):
         self.depth = max(1, depth)
         self._host = [None] * self.depth
-        self._queue = []   # (slot, event) in submission order
+        self._snap = [None] * self.depth
+        self._done = [None] * self.depth   # event: D2H out of the snapshot finished
+        self._queue = []                   # slots in submission order
         self._k = 0
+        self._stream = None
 
     def __len__(self) -> int:
         return len(self._queue)
@@ -114,15 +118,42 @@ class AsyncReadback:
         self._k += 1
         h = self._host[slot]
         if h is None or h.shape != t.shape or h.dtype != t.dtype:
-            h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            h = torch.empty(t.shape, dtype=t.dtype)
+            if t.is_cuda:
+                h = h.pin_memory()
             self._host[slot] = h
-        h.copy_(t, non_blocking=True)            # stream-ordered after the producer of ``t``
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(t.device))
-        self._queue.append((slot, ev))
+        if not t.is_cuda:  # host tensor (CPU tests): nothing to overlap
+            h.copy_(t)
+            self._done[slot] = None
+            self._queue.append(slot)
+            return
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=t.device)
+        cur = torch.cuda.current_stream(t.device)
+        snap = self._snap[slot]
+        if snap is None or snap.shape != t.shape or snap.dtype != t.dtype:
+            snap = torch.empty_like(t)
+            self._snap[slot] = snap
+        if self._done[slot] is not None:
+            cur.wait_event(self._done[slot])   # the previous copy out of this snapshot (long finished)
+        snap.copy_(t)                          # stream-ordered after the producer of ``t``
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            h.copy_(snap, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        self._done[slot] = done
+        self._queue.append(slot)
 
     def pop(self) -> torch.Tensor:
         """Oldest result as a pinned host tensor (valid until ``depth`` further pushes)."""
-        slot, ev = self._queue.pop(0)
-        ev.synchronize()
+        slot = self._queue.pop(0)
+        ev = self._done[slot]
+        if ev is not None:
+            # poll instead of cudaEventSynchronize: a blocking wait can return milliseconds late
+            # (measured on virtualised hosts), which would stall the launch of the next window
+            while not ev.query():
+                pass
         return self._host[slot]

@@ -188,3 +188,21 @@ def test_spike_counter_equals_raster_sum():
             assert torch.equal(net.monitors["count"].get("s"), raster.sum(0).to(torch.int32))
             assert net.monitors["count"].get("s").shape == (3, 24) and raster.sum() > 0
             assert net.monitors["count_i"].get("s").sum() > 0
+
+
+def test_async_readback_ring_order_and_overflow():
+    """pipeline.AsyncReadback hands results back in submission order, one window behind."""
+    from bindsnet_b200.pipeline import AsyncReadback
+
+    rb = AsyncReadback(depth=2)
+    seen = []
+    for k in range(5):
+        rb.push(torch.full((3, 4), k, dtype=torch.int32))
+        if len(rb) == rb.depth:
+            seen.append(int(rb.pop()[0, 0]))
+    while len(rb):
+        seen.append(int(rb.pop()[0, 0]))
+    assert seen == [0, 1, 2, 3, 4]
+    rb.push(torch.zeros(2)); rb.push(torch.zeros(2))
+    with pytest.raises(RuntimeError):
+        rb.push(torch.zeros(2))
