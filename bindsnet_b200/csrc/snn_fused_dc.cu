@@ -44,10 +44,10 @@ struct FusedParams {
     int32_t SW;               // words per sample row of inS
     int32_t SB;               // bytes of one event-list block
     int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
+    uint32_t o_W, o_tx, o_ev, o_inT, o_xrow, o_rep, o_xown, o_theta, o_live, o_misc;  // smem_layout() byte offsets
     int32_t pregather;        // env SNN_B200_PREGATHER: gather of step t+1 in the shadow of barrier t
     int32_t dbg;              // profiling only (env SNN_B200_DEBUG): 1 no barrier wait, 2 skip STDP,
-                              // 4 skip gather, 8 skip trace publish, 16 skip staging, 64 late pass on every CTA and step
-                              // — results invalid
+                              // 4 skip gather, 8 skip trace publish, 16 skip staging — results invalid
     uint32_t seed, step_offset;
     uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
     uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
@@ -500,17 +500,18 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     const int B = Q.B, P = Q.P, n = Q.n, T = Q.T;
     const unsigned int G = gridDim.x;
     const int own = (B + (int)G - 1) / (int)G;
-    const SmemLayout SL = smem_layout(P, TJ, B, BW, n, own);
-    float *W = (float *)(smem + SL.W);
-    float *tx = (float *)(smem + SL.tx);
-    unsigned char *evb = smem + SL.ev;
-    uint32_t *inT = (uint32_t *)(smem + SL.inT);
-    float *xrow = (float *)(smem + SL.xrow);
-    float *rep = (float *)(smem + SL.rep);
-    float *xown = (float *)(smem + SL.xown);
-    float *theta_s = (float *)(smem + SL.theta);
-    uint16_t *live = (uint16_t *)(smem + SL.live);
-    Misc &M = *(Misc *)(smem + SL.misc);
+    // shared-memory carve-up: byte offsets computed by the host (smem_layout) and passed as kernel
+    // parameters, so that a pointer the compiler chooses to rematerialise costs one add
+    float *W = (float *)(smem + Q.o_W);
+    float *tx = (float *)(smem + Q.o_tx);
+    unsigned char *evb = smem + Q.o_ev;
+    uint32_t *inT = (uint32_t *)(smem + Q.o_inT);
+    float *xrow = (float *)(smem + Q.o_xrow);
+    float *rep = (float *)(smem + Q.o_rep);
+    float *xown = (float *)(smem + Q.o_xown);
+    float *theta_s = (float *)(smem + Q.o_theta);
+    uint16_t *live = (uint16_t *)(smem + Q.o_live);
+    Misc &M = *(Misc *)(smem + Q.o_misc);
     __shared__ PassCtx s_cx;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -614,13 +615,13 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         bulk_g2s(evb + evblk, Q.evS + Q.SB, bytesE, &M.mbar[1]);
         bulk_g2s(inT + P * BW, Q.inT + (size_t)P * BW, bytesT, &M.mbar[1]);
     }
-    uint32_t ph0 = 0, ph1 = 0;
     // input trace of step 0 for the samples this CTA owns, published in xpub slot 0
     // Warp 0 is busy with the grid barrier while the others publish: work is spread over the threads
     // ptid = tid - 32 (all threads when the block is a single warp).  The spike bits of the first
     // item of each of the first two owned samples can be loaded ahead (publish_load) so that their
     // L2 latency hides behind the early STDP.
     const int ptid = nthr > 32 ? tid - 32 : tid, pn = nthr > 32 ? nthr - 32 : nthr;
+    const int tid_pf = nthr > 32 ? 32 : 0;  // the thread that issues the bulk prefetches (not thread 0: it arrives at the barrier)
     uint32_t pubw0 = 0, pubw1 = 0;
     auto publish_load = [&](int step) {
         if (!X.traces || (Q.dbg & 8) || ptid < 0 || ptid >= (P >> 2)) return;
@@ -701,7 +702,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         if (act && t > 0 && pend) key = __ldcg(Q.win + xs * B + b);
         // Ai spike count of step t-1 (lateral inhibition): issued here, consumed by the neuron update
         const unsigned int isum = act ? __ldcg(Q.sisum + xs * B + b) : 0u;
-        const uint32_t lategrp = t > 0 ? (M.candgrp[ppar] | ((Q.dbg & 64) ? 1u : 0u)) : 0u;  // groups that held a candidate at t-1
+        const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;      // groups that held a candidate at t-1
         // stage the input-trace rows of this tile's candidate samples (the possible winners) in
         // shared memory: issued together with the exchange loads, so one L2 round trip covers both
         if (t > 0 && stage_on && lategrp && !(Q.dbg & 16)) {
@@ -841,11 +842,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         if (t == T) break;
 
         // ---- D(t): gather, Ae / Ai update, candidates ----------------------------------------
-        {   // this iteration's spike lists (slot t) were prefetched one iteration ago
-            uint32_t &ph = buf ? ph1 : ph0;
-            while (!mbar_try_wait(&M.mbar[buf], ph)) {}
-            ph ^= 1u;
-        }
+        // this iteration's spike lists (slot t) were prefetched one iteration ago; buffer `buf` is
+        // filled for the (t >> 1)-th time, which is its mbarrier phase
+        while (!mbar_try_wait(&M.mbar[buf], (uint32_t)(t >> 1) & 1u)) {}
         if (tid == 0) { M.ncand[par] = 0; M.candgrp[par] = 0; }
         __syncthreads();   // late STDP done (W final for step t-1); bookkeeping of parity `par` reset
         PROF(3)  // mbarrier wait + sync
@@ -937,7 +936,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             M.cnt[par][tid] = 0;
         }
         // prefetch slot t+2 into the buffer the gather just finished with
-        if (tid == 32 % nthr && t + 2 <= T) {  // (not thread 0: it is about to arrive at the grid barrier)
+        if (tid == tid_pf && t + 2 <= T) {  // (not thread 0: it is about to arrive at the grid barrier)
             mbar_expect_tx(&M.mbar[buf], bytesE + bytesT);
             bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar[buf]);
             bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar[buf]);
@@ -951,7 +950,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         // ---- early(t): in the shadow of the barrier ------------------------------------------------
         if (t + 1 < T) publish_load(t + 1);
         const int nb = buf ^ 1;                                      // slot t+1 = spikes of step t
-        while (!mbar_try_wait(&M.mbar[nb], nb ? ph1 : ph0)) {}      // landed? (phase is consumed by D(t+1))
+        while (!mbar_try_wait(&M.mbar[nb], (uint32_t)((t + 1) >> 1) & 1u)) {}  // slot t+1 landed? (waited again by D(t+1))
         if (update_on) {
             const uint32_t allg = (1u << CG) - 1u;
             const uint32_t earlygrp = allg & ~M.candgrp[par];
@@ -972,7 +971,7 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         PROF(10)  // pre-gather
         if (t + 1 < T) publish_trace(t + 1);  // input trace of step t+1 (its winners read it after barrier t+1)
-        if (tid == 32 % nthr && t + 2 <= T) M.denseflag[buf] = dflag;
+        if (tid == tid_pf && t + 2 <= T) M.denseflag[buf] = dflag;
         PROF(8)  // trace publish
         // ---- wait(t) ----------------------------------------------------------------------------
         if (tid == 0 && !(Q.dbg & 1)) {
@@ -1338,6 +1337,12 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.T = T; Q.B = B; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
     { const char *d = getenv("SNN_B200_DEBUG"); Q.dbg = d ? atoi(d) : 0; }
     { const char *d = getenv("SNN_B200_PREGATHER"); Q.pregather = d ? atoi(d) : 0; }
+    {
+        const SmemLayout SL = smem_layout(P, m.TJ, B, m.BW, Q.n, m.own);
+        Q.o_W = (uint32_t)SL.W; Q.o_tx = (uint32_t)SL.tx; Q.o_ev = (uint32_t)SL.ev; Q.o_inT = (uint32_t)SL.inT; Q.o_xrow = (uint32_t)SL.xrow;
+        Q.o_rep = (uint32_t)SL.rep; Q.o_xown = (uint32_t)SL.xown; Q.o_theta = (uint32_t)SL.theta; Q.o_live = (uint32_t)SL.live;
+        Q.o_misc = (uint32_t)SL.misc;
+    }
     Q.SW = m.SW; Q.SB = m.SB; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
     Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
     Q.win = (unsigned long long *)(ws + WL.win); Q.sisum = (unsigned int *)(ws + WL.sisum);

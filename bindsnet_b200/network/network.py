@@ -256,9 +256,24 @@ class Network(torch.nn.Module):
             _backend.poll_errors(dev, sync=True)
 
     def reset_state_variables(self) -> None:
-        """network.py:467-479."""
+        """network.py:467-479.  Layers whose reset is the stock one (it is for every population this
+        package implements) are cleared together: one multi-tensor zero plus one fill per voltage,
+        instead of three to four launches per layer."""
+        from .nodes import Nodes, LIFNodes, DiehlAndCookNodes
+
+        stock = {Nodes.reset_state_variables, LIFNodes.reset_state_variables, DiehlAndCookNodes.reset_state_variables}
+        zeros, fills = [], []
         for layer in self.layers.values():
-            layer.reset_state_variables()
+            if type(layer).reset_state_variables in stock and hasattr(layer, "_reset_plan"):
+                z, f = layer._reset_plan()
+                zeros += z
+                fills += f
+            else:
+                layer.reset_state_variables()
+        if zeros:
+            torch._foreach_zero_(zeros)
+        for t, value in fills:
+            t.fill_(value)
         for connection in self.connections.values():
             connection.reset_state_variables()
         for monitor in self.monitors.values():

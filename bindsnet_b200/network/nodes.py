@@ -105,6 +105,16 @@ class Nodes(torch.nn.Module):
         if self.sum_input:
             self.summed.zero_()
 
+    def _reset_plan(self):
+        """(tensors to zero, [(tensor, fill value)]) of ``reset_state_variables`` — lets
+        ``Network.reset_state_variables`` clear a whole network with one multi-tensor launch."""
+        zeros = [self.s]
+        if self.traces:
+            zeros.append(self.x)
+        if self.sum_input:
+            zeros.append(self.summed)
+        return zeros, []
+
     def compute_decays(self, dt) -> None:
         """nodes.py:122-131."""
         self.dt = torch.tensor(dt)
@@ -213,6 +223,10 @@ class LIFNodes(Nodes):
         self.v.fill_(self.rest)
         self.refrac_count.zero_()
 
+    def _reset_plan(self):
+        zeros, fills = super()._reset_plan()
+        return zeros + [self.refrac_count], fills + [(self.v, self.rest)]
+
     def compute_decays(self, dt) -> None:
         """nodes.py:540-548."""
         super().compute_decays(dt=dt)
@@ -286,6 +300,10 @@ class DiehlAndCookNodes(Nodes):
         super().reset_state_variables()
         self.v.fill_(self.rest)
         self.refrac_count.zero_()
+
+    def _reset_plan(self):
+        zeros, fills = super()._reset_plan()
+        return zeros + [self.refrac_count], fills + [(self.v, self.rest)]
 
     def compute_decays(self, dt) -> None:
         """nodes.py:1122-1133."""
