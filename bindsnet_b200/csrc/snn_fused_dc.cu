@@ -45,7 +45,6 @@ struct FusedParams {
     int32_t SB;               // bytes of one event-list block
     int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
     uint32_t o_W, o_tx, o_ev, o_inT, o_xrow, o_rep, o_xown, o_theta, o_live, o_misc;  // smem_layout() byte offsets
-    int32_t pregather;        // env SNN_B200_PREGATHER: gather of step t+1 in the shadow of barrier t
     int32_t dbg;              // profiling only (env SNN_B200_DEBUG): 1 no barrier wait, 2 skip STDP,
                               // 4 skip gather, 8 skip trace publish, 16 skip staging — results invalid
     uint32_t seed, step_offset;
@@ -681,10 +680,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         return make_float4(p0, p1, p2, p3);
     };
-    // The gather of step t+1 runs in the shadow of barrier t for the column groups whose W is
-    // already final (no candidate at step t); step 0's gather runs in D(0).
-    float4 pg = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool pg_done = false;
     int myslot = -1;           // staged input-trace row of my sample's candidates (step being finalised)
 
     // =====================================================================================
@@ -853,7 +848,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         int nI = 0;
         if (act) {
             // columns whose step-(t-1) STDP was late (or everything, first time): gather now
-            if (!pg_done) pg = gather(cE, t);
+            // (running this gather one step ahead, in the shadow of the barrier, for the groups whose W
+            // is already final was measured: no gain — the CTAs are busy, not idle, in that shadow)
+            const float4 pg = gather(cE, t);
             const float p[4] = {pg.x, pg.y, pg.z, pg.w};
             const float4 th4 = *(const float4 *)(theta_s + 4 * cg);
             float th[4] = {th4.x, th4.y, th4.z, th4.w};
@@ -960,16 +957,6 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
             else if (pre_on) stdp_list<TJ, BW>(&s_cx, nb, earlygrp, 0u, nthr > 32 ? tid - 32 : tid, nthr > 32 ? nthr - 32 : nthr);
         }
         PROF(7)  // early STDP
-        pg_done = false;
-        if (Q.pregather && t + 1 < T) {
-            __syncthreads();  // early STDP complete: W of the groups without a candidate is final for step t+1
-            const uint32_t cgrp = update_on ? M.candgrp[par] : 0u;
-            if (!((cgrp >> cg) & 1u)) {
-                if (act) pg = gather(evb + nb * evblk, t + 1);
-                pg_done = true;
-            }
-        }
-        PROF(10)  // pre-gather
         if (t + 1 < T) publish_trace(t + 1);  // input trace of step t+1 (its winners read it after barrier t+1)
         if (tid == tid_pf && t + 2 <= T) M.denseflag[buf] = dflag;
         PROF(8)  // trace publish
@@ -1336,7 +1323,6 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.exc = net->conns[m.cEI].structure_val; Q.inh_neg = net->conns[m.cIE].structure_val;
     Q.T = T; Q.B = B; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
     { const char *d = getenv("SNN_B200_DEBUG"); Q.dbg = d ? atoi(d) : 0; }
-    { const char *d = getenv("SNN_B200_PREGATHER"); Q.pregather = d ? atoi(d) : 0; }
     {
         const SmemLayout SL = smem_layout(P, m.TJ, B, m.BW, Q.n, m.own);
         Q.o_W = (uint32_t)SL.W; Q.o_tx = (uint32_t)SL.tx; Q.o_ev = (uint32_t)SL.ev; Q.o_inT = (uint32_t)SL.inT; Q.o_xrow = (uint32_t)SL.xrow;
@@ -1377,7 +1363,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange loads", "late sync+reset", "mbar wait+sync", "gather+neurons", "reduce+atomics",
-                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "pre-gather", "epilogue",
+                                           "theta+prefetch+arr", "early STDP", "trace publish", "barrier wait", "(unused)", "epilogue",
                                            "late finalise", "late sync", "late group pass", "arrive (release)"};
         cudaStreamSynchronize(stream);
         static long long hostp[320 * NPROF];
