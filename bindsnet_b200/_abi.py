@@ -8,13 +8,13 @@ from __future__ import annotations
 
 import ctypes as C
 
-SNN_ABI_VERSION = 5
+SNN_ABI_VERSION = 6
 SNN_MAX_LAYERS = 8
 SNN_MAX_CONNS = 12
 
 SNN_NODE_INPUT, SNN_NODE_LIF, SNN_NODE_DC = 0, 1, 2
-SNN_CONN_DENSE, SNN_CONN_MCC = 0, 1
-SNN_RULE_NONE, SNN_RULE_NOOP, SNN_RULE_POSTPRE, SNN_RULE_WDEP_POSTPRE, SNN_RULE_MCC_POSTPRE = 0, 1, 2, 3, 4
+SNN_CONN_DENSE, SNN_CONN_MCC, SNN_CONN_CONV2D = 0, 1, 2
+SNN_RULE_NONE, SNN_RULE_NOOP, SNN_RULE_POSTPRE, SNN_RULE_WDEP_POSTPRE, SNN_RULE_MCC_POSTPRE, SNN_RULE_MSTDP = 0, 1, 2, 3, 4, 5
 SNN_REDUCE_SUM, SNN_REDUCE_MEAN = 0, 1
 SNN_EXT_NONE, SNN_EXT_U8, SNN_EXT_F32 = 0, 1, 2
 SNN_W_DENSE, SNN_W_DIAG, SNN_W_OFFDIAG = 0, 1, 2
@@ -103,6 +103,20 @@ class SnnConn(C.Structure):
         ("structure_val", C.c_float),
         ("w", C.c_void_p),
         ("b", C.c_void_p),
+        ("cin", C.c_int32), ("hin", C.c_int32), ("win", C.c_int32),
+        ("cout", C.c_int32), ("hout", C.c_int32), ("wout", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("ph", C.c_int32), ("pw", C.c_int32), ("dh", C.c_int32), ("dw", C.c_int32),
+        ("reward", C.c_float),
+        ("a_plus", C.c_float),
+        ("a_minus", C.c_float),
+        ("p_plus_decay", C.c_float),
+        ("p_minus_decay", C.c_float),
+        ("p_plus", C.c_void_p),
+        ("p_minus", C.c_void_p),
+        ("elig", C.c_void_p),
+        ("mst_spre", C.c_void_p),
+        ("mst_spost", C.c_void_p),
     ]
 
 

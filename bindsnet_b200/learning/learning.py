@@ -120,6 +120,85 @@ class WeightDependentPostPre(LearningRule):
             raise NotImplementedError("This learning rule is not supported for this Connection type.")
 
 
+class MSTDP(LearningRule):
+    """Reward-modulated STDP (reference: learning.py:1440-2121): dense ``Connection``
+    (``_connection_update`` :1504-1574) and ``Conv2dConnection`` (``_conv2d_connection_update``
+    :1942-2015).  Rule state lives here like in the reference: ``p_plus``, ``p_minus`` and — for the
+    convolutional form — ``eligibility`` ``[B, *w.shape]``.  The dense form never materialises the
+    ``[B, n_src, n_tgt]`` eligibility: it is ``p_plus (x) s_post + s_pre (x) p_minus`` of the previous
+    step, so the spikes the rule saw last are kept instead (``eligibility`` rebuilds it on request).
+    ``Network.run(..., reward=r)`` is mandatory, ``a_plus`` / ``a_minus`` optional (:1540-1556).  For
+    ``Conv2dConnection`` the eligibility is per sample for any batch size (the reference's final
+    ``.view(w.size())`` at :2013 only works for batch size 1)."""
+
+    rule_code = _abi.SNN_RULE_MSTDP
+
+    def __init__(self, connection, nu=None, reduction=None, weight_decay: float = 0.0, **kwargs) -> None:
+        super().__init__(connection=connection, nu=nu, reduction=reduction, weight_decay=weight_decay, **kwargs)
+        from ..network.topology import Connection, Conv2dConnection
+
+        if not isinstance(connection, (Connection, Conv2dConnection)):
+            raise NotImplementedError("This learning rule is not supported for this Connection type.")
+        self._conv = isinstance(connection, Conv2dConnection)
+        if self._conv and connection._geometry[3] != (1, 1):
+            raise NotImplementedError("MSTDP on a dilated Conv2dConnection is undefined in the reference (im2col ignores dilation)")
+        self.tc_plus = torch.tensor(kwargs.get("tc_plus", 20.0))
+        self.tc_minus = torch.tensor(kwargs.get("tc_minus", 20.0))
+        self._run_kwargs = {}
+
+    def update(self, **kwargs) -> None:
+        raise NotImplementedError("MSTDP.update is fused into Network.run (it needs the run's reward); the standalone call is not exposed")
+
+    def _prepare(self, B: int, dev: torch.device, run_kwargs: dict) -> None:
+        """Allocate / validate the rule state for a window (learning.py:1519-1535, 1958-1961, 1979-1991)."""
+        if run_kwargs.get("reward", None) is None:
+            raise KeyError("reward")  # learning.py:1541: kwargs["reward"]
+        for key in ("reward", "a_plus", "a_minus"):
+            v = run_kwargs.get(key, None)
+            if isinstance(v, dict) or (isinstance(v, torch.Tensor) and v.numel() != 1):
+                raise NotImplementedError(f"run(..., {key}=...) must be a scalar for the CUDA core")
+        self._run_kwargs = run_kwargs
+        src, tgt = self.source, self.target
+
+        def ensure(name, shape, dtype=torch.float32):
+            t = getattr(self, name, None)
+            if not isinstance(t, torch.Tensor) or tuple(t.shape) != tuple(shape) or t.device != dev or t.dtype != dtype:
+                setattr(self, name, torch.zeros(*shape, dtype=dtype, device=dev))
+
+        if self._conv:
+            ensure("p_plus", (B, *src.shape))
+            ensure("p_minus", (B, tgt.shape[0], tgt.shape[1] * tgt.shape[2]))
+            ensure("_elig", (B, *self.connection.w.shape))
+        else:
+            ensure("p_plus", (B, src.n))
+            ensure("p_minus", (B, tgt.n))
+            ensure("_spre", (B, src.n), torch.uint8)
+            ensure("_spost", (B, tgt.n), torch.uint8)
+
+    @property
+    def eligibility(self) -> torch.Tensor:
+        """``[B, *w.shape]`` eligibility that the next update will apply (learning.py:1568-1572, 2005-2010)."""
+        if self._conv:
+            return self._elig
+        return torch.bmm(self.p_plus.unsqueeze(2), self._spost.float().unsqueeze(1)) + torch.bmm(
+            self._spre.float().unsqueeze(2), self.p_minus.unsqueeze(1))
+
+    def _fill_desc(self, d: "_abi.SnnConn") -> None:
+        super()._fill_desc(d)
+        rk = self._run_kwargs
+        dt = float(self.connection.dt)
+        d.reward = float(rk["reward"])
+        d.a_plus = float(rk["a_plus"]) if rk.get("a_plus", None) is not None else 1.0
+        d.a_minus = float(rk["a_minus"]) if rk.get("a_minus", None) is not None else -1.0
+        d.p_plus_decay = float(torch.exp(-dt / self.tc_plus))    # learning.py:1565 (fp32 tensor arithmetic)
+        d.p_minus_decay = float(torch.exp(-dt / self.tc_minus))  # learning.py:1567
+        d.p_plus, d.p_minus = self.p_plus.data_ptr(), self.p_minus.data_ptr()
+        if self._conv:
+            d.elig = self._elig.data_ptr()
+        else:
+            d.mst_spre, d.mst_spost = self._spre.data_ptr(), self._spost.data_ptr()
+
+
 def _unsupported(name: str, where: str):
     class _Unsupported(LearningRule):
         __doc__ = f"``{name}`` (reference: {where}) — not on the accelerated path (SURVEY.md §8f)."
@@ -132,6 +211,5 @@ def _unsupported(name: str, where: str):
 
 
 Hebbian = _unsupported("Hebbian", "learning.py:1052-1438")
-MSTDP = _unsupported("MSTDP", "learning.py:1441-2121")
 MSTDPET = _unsupported("MSTDPET", "learning.py:2124-2855")
 Rmax = _unsupported("Rmax", "learning.py:2858-2960")

@@ -75,13 +75,16 @@ def weight_structure(conn, w: torch.Tensor):
     return result
 
 
-def fill_conn(d: "_abi.SnnConn", conn, src_idx: int, tgt_idx: int, dt: float, B: int) -> None:
+def fill_conn(d: "_abi.SnnConn", conn, src_idx: int, tgt_idx: int, dt: float, B: int, rule_kwargs=None) -> None:
     d.src, d.tgt = src_idx, tgt_idx
+    rule0 = getattr(conn, "update_rule", None)
+    if hasattr(rule0, "_prepare"):  # rules with state of their own (MSTDP): allocate for this batch size / device
+        rule0._prepare(B, conn.w.device, rule_kwargs or {})
     conn._fill_desc(d, dt)
     w = conn.w
     if w.dtype != torch.float32 or not w.is_contiguous():
         raise TypeError("connection weights must be contiguous float32")
-    if tuple(w.shape) != (conn.source.n, conn.target.n):
+    if d.kind != _abi.SNN_CONN_CONV2D and tuple(w.shape) != (conn.source.n, conn.target.n):
         raise ValueError(f"weight shape {tuple(w.shape)} != ({conn.source.n}, {conn.target.n})")
     d.w = _ptr(w)
     static = d.rule == _abi.SNN_RULE_NONE or (d.rule == _abi.SNN_RULE_NOOP and d.weight_decay in (0.0, 1.0))
@@ -157,7 +160,7 @@ def build_net(
             if len(r) > 2 and r[2] is not None:
                 d.rec_count = _ptr(r[2]); keep.append(r[2])
     for i, ((src, tgt), conn) in enumerate(network.connections.items()):
-        fill_conn(net.conns[i], conn, index[src], index[tgt], float(network.dt), B)
+        fill_conn(net.conns[i], conn, index[src], index[tgt], float(network.dt), B, getattr(network, "_rule_kwargs", None))
     return net, keep
 
 

@@ -92,9 +92,11 @@ class Network(torch.nn.Module):
         )
         if one_step:
             raise NotImplementedError("one_step=True (feed-forward mode, network.py:383-396) is not implemented")
-        for unsupported in ("masks", "reward", "a_plus", "a_minus"):
-            if kwargs.get(unsupported):
-                raise NotImplementedError(f"run(..., {unsupported}=...) is outside the implemented hot path")
+        if kwargs.get("masks"):
+            raise NotImplementedError("run(..., masks=...) is outside the implemented hot path")
+        # reward-modulated rules (learning.MSTDP) read these from the run's kwargs (network.py:319-377,
+        # learning.py:1540-1556); the reward_fn hook of the constructor is not implemented
+        self._rule_kwargs = {k: kwargs.get(k, None) for k in ("reward", "a_plus", "a_minus")}
 
         # network.py:329-353: canonical [T, B, ...] shape, batch-size inference, state reset
         inputs = dict(inputs)

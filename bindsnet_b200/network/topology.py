@@ -135,6 +135,100 @@ class Connection(AbstractConnection):
         self.update_rule._fill_desc(d)
 
 
+def _pair(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+class Conv2dConnection(AbstractConnection):
+    """2-D convolutional synapses (reference: topology.py:686-844).  ``w`` is
+    ``[out_channels, in_channels, kh, kw]``, ``b`` ``[out_channels]`` (zeros by default, :795-797);
+    source / target populations are ``[C, H, W]`` shaped.  Inside ``Network.run`` the convolution is a
+    spike-gather over each target neuron's receptive field; ``MSTDP`` is the learning rule the CUDA
+    core fuses for it (learning.py:1942-2015)."""
+
+    def __init__(
+        self,
+        source: Nodes,
+        target: Nodes,
+        kernel_size,
+        stride=1,
+        padding=0,
+        dilation=1,
+        nu: Optional[Union[float, Sequence[float], Sequence[torch.Tensor]]] = None,
+        reduction: Optional[callable] = None,
+        weight_decay: float = 0.0,
+        w_dtype: torch.dtype = torch.float32,
+        **kwargs,
+    ) -> None:
+        if w_dtype != torch.float32:
+            raise NotImplementedError("bindsnet_b200 computes in float32 only (SURVEY.md §8b)")
+        # geometry first: the learning rule built by the base constructor looks at it
+        self_kernel, self_stride = _pair(kernel_size), _pair(stride)
+        self_padding, self_dilation = _pair(padding), _pair(dilation)
+        assert len(source.shape) == 3 and len(target.shape) == 3, "Conv2dConnection needs [C, H, W] populations"
+        in_channels, input_height, input_width = source.shape
+        out_channels = target.shape[0]
+        # topology.py:752-772 (the reference swaps the names width / height; the values are these)
+        out_h = int((input_height - self_kernel[0] + 2 * self_padding[0]) / self_stride[0] + 1)
+        out_w = int((input_width - self_kernel[1] + 2 * self_padding[1]) / self_stride[1] + 1)
+        assert target.shape[1] == out_h and target.shape[2] == out_w, (
+            "Target dimensionality must be (out_channels, ?,"
+            "(input_height - filter_height + 2 * padding_height) / stride_height + 1,"
+            "(input_width - filter_width + 2 * padding_width) / stride_width + 1"
+        )
+        object.__setattr__(self, "_geometry", (self_kernel, self_stride, self_padding, self_dilation))
+        super().__init__(source, target, nu, reduction, weight_decay, **kwargs)
+        self.kernel_size, self.stride, self.padding, self.dilation = self_kernel, self_stride, self_padding, self_dilation
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        w = kwargs.get("w", None)
+        shape = (self.out_channels, self.in_channels, *self.kernel_size)
+        if w is None:
+            # topology.py:775-786
+            if (self.wmin == -np.inf).any() or (self.wmax == np.inf).any():
+                w = torch.clamp(torch.rand(*shape), self.wmin, self.wmax)
+            else:
+                w = (self.wmax - self.wmin) * torch.rand(*shape)
+                w = w + self.wmin
+        else:
+            # topology.py:787-790
+            w = torch.as_tensor(w)
+            if (self.wmin == -np.inf).any() or (self.wmax == np.inf).any():
+                w = torch.clamp(w, self.wmin, self.wmax)
+            w = self.cast_dtype_if_needed(w, w_dtype)
+        assert tuple(w.shape) == shape, f"w must have shape {shape}"
+        self.w = Parameter(w.detach().clone().float().contiguous(), requires_grad=False)
+        self.b = Parameter(torch.as_tensor(kwargs.get("b", torch.zeros(self.out_channels)), dtype=torch.float32).clone(),
+                           requires_grad=False)
+
+    def compute(self, s: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError(
+            "Conv2dConnection.compute runs inside the Network.run window kernels; the standalone call is not exposed"
+        )
+
+    def normalize(self) -> None:
+        """topology.py:824-837 (runs at the end of every ``Network.run`` window)."""
+        if self.norm is not None:
+            raise NotImplementedError("standalone Conv2dConnection.normalize is not exposed; Network.run applies it")
+
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float) -> None:
+        d.kind = _abi.SNN_CONN_CONV2D
+        if self.wmin.numel() != 1 or self.wmax.numel() != 1:
+            raise NotImplementedError("per-synapse wmin/wmax tensors are not supported by the CUDA core yet")
+        d.wmin = _scalar(self.wmin, "wmin")
+        d.wmax = _scalar(self.wmax, "wmax")
+        d.has_norm = int(self.norm is not None)
+        d.norm_abs = 0
+        d.norm = float(self.norm) if self.norm is not None else 0.0
+        d.dt_scale = 1.0
+        d.cin, d.hin, d.win = (int(v) for v in self.source.shape)
+        d.cout, d.hout, d.wout = (int(v) for v in self.target.shape)
+        d.kh, d.kw = self.kernel_size
+        d.sh, d.sw = self.stride
+        d.ph, d.pw = self.padding
+        d.dh, d.dw = self.dilation
+        self.update_rule._fill_desc(d)
+
+
 class AbstractMulticompartmentConnection(ABC, Module):
     """Reference: topology.py:159-262."""
 
@@ -240,7 +334,6 @@ def _unsupported(name: str, where: str):
 
 
 Conv1dConnection = _unsupported("Conv1dConnection", "topology.py:540-683")
-Conv2dConnection = _unsupported("Conv2dConnection", "topology.py:686-844")
 Conv3dConnection = _unsupported("Conv3dConnection", "topology.py:847-1025")
 MaxPool1dConnection = _unsupported("MaxPool1dConnection", "topology.py:1028-1121")
 MaxPool2dConnection = _unsupported("MaxPool2dConnection", "topology.py:1124-1211")

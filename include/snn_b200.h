@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 5
+#define SNN_ABI_VERSION 6
 #define SNN_MAX_LAYERS 8
 #define SNN_MAX_CONNS 12
 
@@ -47,6 +47,9 @@ extern "C" {
 #define SNN_CONN_DENSE 0 /* Connection: s.float() @ w + b                topology.py:332-346 */
 #define SNN_CONN_MCC 1   /* MulticompartmentConnection[Weight]: sum_i W*s  topology.py:437-479,
                             topology_features.py:633-645 (same maths, dt-scaled STDP)          */
+#define SNN_CONN_CONV2D 2 /* Conv2dConnection: F.conv2d(s.float(), w, b, stride, padding, dilation)
+                             topology.py:799-815; w is [Cout, Cin, kh, kw], b is [Cout]; the source layer's
+                             neurons are indexed (ci, y, x), the target's (co, oy, ox), row-major */
 
 /* ---- learning rules ---- */
 #define SNN_RULE_NONE 0        /* MCC_learning.NoOp: update() does nothing    MCC_learning.py:120-146 */
@@ -54,6 +57,8 @@ extern "C" {
 #define SNN_RULE_POSTPRE 2     /* learning.PostPre._connection_update         learning.py:390-420     */
 #define SNN_RULE_WDEP_POSTPRE 3/* learning.WeightDependentPostPre             learning.py:626-653     */
 #define SNN_RULE_MCC_POSTPRE 4 /* MCC_learning.PostPre._connection_update     MCC_learning.py:224-302 */
+#define SNN_RULE_MSTDP 5       /* learning.MSTDP: reward-modulated STDP; _connection_update learning.py:1504-1574
+                                  on SNN_CONN_DENSE, _conv2d_connection_update :1942-2015 on SNN_CONN_CONV2D */
 
 /* ---- weight-matrix structure hints (DiehlAndCook2015's static exc/inh matrices,
  *      models.py:204,217-220) ---- */
@@ -141,8 +146,23 @@ typedef struct snn_conn {
     float dt_scale;    /* MCC: connection.dt factor on both STDP terms (MCC_learning.py:262,298) */
     float norm;
     float structure_val; /* the constant of SNN_W_DIAG / SNN_W_OFFDIAG                      */
-    float *w;          /* [n_src, n_tgt] row-major, updated in place                        */
-    const float *b;    /* [n_tgt] bias or NULL (topology.py:345)                            */
+    float *w;          /* [n_src, n_tgt] row-major, updated in place (CONV2D: [Cout,Cin,kh,kw]) */
+    const float *b;    /* [n_tgt] bias or NULL (topology.py:345); CONV2D: [Cout]            */
+    /* SNN_CONN_CONV2D geometry (topology.py:738-760): source [cin,hin,win], target [cout,hout,wout] */
+    int32_t cin, hin, win, cout, hout, wout, kh, kw, sh, sw, ph, pw, dh, dw;
+    /* SNN_RULE_MSTDP (learning.py:1440-1574, 1942-2015).  State of the rule, updated in place:
+         DENSE : p_plus [B,n_src], p_minus [B,n_tgt]; the eligibility [B,n_src,n_tgt] of the previous
+                 step is NOT materialised: it is p_plus (x) s_post + s_pre (x) p_minus of that step, so
+                 the spikes the rule saw last are kept instead (mst_spre [B,n_src], mst_spost [B,n_tgt],
+                 one byte per neuron);
+         CONV2D: p_plus is the [B,cin,hin,win] trace image whose im2col the reference stores
+                 (unfold is linear), p_minus [B,cout*hout*wout], elig [B,cout,cin*kh*kw] (fp32,
+                 materialised like the reference's, applied one step later).                  */
+    float reward;      /* the run's scalar reward (network.py:319-377 -> kwargs["reward"])  */
+    float a_plus, a_minus;           /* defaults +1 / -1 (learning.py:1543-1556)            */
+    float p_plus_decay, p_minus_decay; /* exp(-dt/tc_plus), exp(-dt/tc_minus), computed by the host in fp32 */
+    float *p_plus, *p_minus, *elig;
+    uint8_t *mst_spre, *mst_spost;
 } snn_conn_t;
 
 typedef struct snn_net {

@@ -64,8 +64,21 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
         if (C->src < 0 || C->src >= net->n_layers || C->tgt < 0 || C->tgt >= net->n_layers) return SNN_ERR_BAD_ARG;
         if (!C->w) return SNN_ERR_BAD_ARG;
         if (net->layers[C->tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
-        if (C->rule < 0 || C->rule > SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
-        if (C->rule >= SNN_RULE_POSTPRE) {
+        if (C->rule < 0 || C->rule > SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+        if (C->kind < 0 || C->kind > SNN_CONN_CONV2D) return SNN_ERR_UNSUPPORTED;
+        if (C->kind == SNN_CONN_CONV2D) {
+            const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
+            if (C->cin * C->hin * C->win != S->n || C->cout * C->hout * C->wout != G->n) return SNN_ERR_BAD_ARG;
+            if (C->kh < 1 || C->kw < 1 || C->sh < 1 || C->sw < 1 || C->dh < 1 || C->dw < 1 || !C->b) return SNN_ERR_BAD_ARG;
+            if (C->rule != SNN_RULE_NONE && C->rule != SNN_RULE_NOOP && C->rule != SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+        }
+        if (C->rule == SNN_RULE_MSTDP) {
+            if (!C->p_plus || !C->p_minus) return SNN_ERR_BAD_ARG;
+            if (C->kind == SNN_CONN_CONV2D) { if (!C->elig || C->dh != 1 || C->dw != 1) return SNN_ERR_BAD_ARG; }
+            else if (C->kind == SNN_CONN_DENSE) { if (!C->mst_spre || !C->mst_spost) return SNN_ERR_BAD_ARG; }
+            else return SNN_ERR_UNSUPPORTED;
+        }
+        if (C->rule >= SNN_RULE_POSTPRE && C->rule <= SNN_RULE_MCC_POSTPRE) {
             /* learning.py:373-376,597-599; MCC_learning.py:193-196: traces required */
             if (!net->layers[C->src].traces) return SNN_ERR_BAD_ARG;
             if (!net->layers[C->tgt].traces) return SNN_ERR_BAD_ARG; /* target.x is read by every STDP rule */
@@ -100,6 +113,37 @@ static void conn_compute(const snn_conn_t *C, const snn_layer_t *S, int n_tgt, i
                 for (int j = 0; j < n_tgt; ++j) cb[j] = cb[j] + p[j];
         }
         free(p);
+    }
+}
+
+/* Conv2dConnection.compute (topology.py:799-815): F.conv2d(s.float(), w, b, stride, padding,
+ * dilation) on zero-padded spikes; w is [Cout,Cin,kh,kw].  Summation order (ATen leaves it to the
+ * backend): ascending (ci, ky, kx), bias added last. */
+static void conv_compute(const snn_conn_t *C, const snn_layer_t *S, int B, float *cur, int dense) {
+    const int L = C->hout * C->wout, nt = C->cout * L, ns = S->n;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const uint8_t *s = S->s + (size_t)b * ns;
+        float *cb = cur + (size_t)b * nt;
+        for (int co = 0; co < C->cout; ++co)
+            for (int oy = 0; oy < C->hout; ++oy)
+                for (int ox = 0; ox < C->wout; ++ox) {
+                    float p = 0.0f;
+                    for (int ci = 0; ci < C->cin; ++ci)
+                        for (int ky = 0; ky < C->kh; ++ky) {
+                            const int iy = oy * C->sh - C->ph + ky * C->dh;
+                            if (iy < 0 || iy >= C->hin) continue;
+                            for (int kx = 0; kx < C->kw; ++kx) {
+                                const int ix = ox * C->sw - C->pw + kx * C->dw;
+                                if (ix < 0 || ix >= C->win) continue;
+                                const uint8_t sv = s[((size_t)ci * C->hin + iy) * C->win + ix];
+                                if (!dense && !sv) continue;
+                                p = p + (sv ? 1.0f : 0.0f) * C->w[(((size_t)co * C->cin + ci) * C->kh + ky) * C->kw + kx];
+                            }
+                        }
+                    const size_t j = ((size_t)co * C->hout + oy) * C->wout + ox;
+                    cb[j] = cb[j] + (p + C->b[co]);
+                }
     }
 }
 
@@ -334,6 +378,113 @@ static void conn_update(const snn_net_t *net, const snn_conn_t *C, const snn_run
     (void)NW;
 }
 
+/* learning.MSTDP._connection_update (learning.py:1504-1574) on a dense Connection, then the base
+ * class decay + clamp (learning.py:87-104).  The reference keeps eligibility[B,n_src,n_tgt] from the
+ * previous step; it equals p_plus (x) s_post + s_pre (x) p_minus of that step (:1568-1572), so it is
+ * rebuilt here from the rule's p_plus / p_minus (not yet updated for this step) and the spikes the
+ * rule saw last (mst_spre / mst_spost).  Batch reduction in ascending b. */
+static void mstdp_dense_update(const snn_net_t *net, const snn_conn_t *C, const snn_run_opts_t *o, int dense) {
+    const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
+    const int B = o->B, ns = S->n, nt = G->n;
+    const float Bf = (float)B;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < nt; ++j) {
+            float upd = 0.0f;
+            for (int b = 0; b < B; ++b) {
+                const uint8_t ss = C->mst_spre[(size_t)b * ns + i], sp = C->mst_spost[(size_t)b * nt + j];
+                if (!dense && !ss && !sp) continue;
+                const float e = C->p_plus[(size_t)b * ns + i] * (sp ? 1.0f : 0.0f) + (ss ? 1.0f : 0.0f) * C->p_minus[(size_t)b * nt + j];
+                upd = upd + C->reward * e;                                   /* learning.py:1559 */
+            }
+            if (C->reduction == SNN_REDUCE_MEAN) upd = upd / Bf;
+            float x = C->w[(size_t)i * nt + j] + C->nu0 * upd;               /* learning.py:1562 */
+            if (C->weight_decay != 0.0f) x = x * C->weight_decay;            /* learning.py:93-94 */
+            if (C->has_clamp) x = clampf(x, C->wmin, C->wmax);               /* learning.py:97-104 */
+            C->w[(size_t)i * nt + j] = x;
+        }
+    /* P+ / P- (learning.py:1564-1567), then remember the spikes of this step */
+    for (size_t k = 0; k < (size_t)B * ns; ++k) {
+        float x = C->p_plus[k] * C->p_plus_decay;
+        C->p_plus[k] = x + C->a_plus * (S->s[k] ? 1.0f : 0.0f);
+        C->mst_spre[k] = S->s[k] ? 1 : 0;
+    }
+    for (size_t k = 0; k < (size_t)B * nt; ++k) {
+        float x = C->p_minus[k] * C->p_minus_decay;
+        C->p_minus[k] = x + C->a_minus * (G->s[k] ? 1.0f : 0.0f);
+        C->mst_spost[k] = G->s[k] ? 1 : 0;
+    }
+}
+
+/* learning.MSTDP._conv2d_connection_update (learning.py:1942-2015) with the per-sample eligibility
+ * the code intends (:1958-1961 allocate [B,*w.shape]; the final .view(w.size()) at :2013 only works for
+ * B = 1, SURVEY.md §0.8: for B > 1 this is the reference with that view taken per sample).  p_plus is
+ * kept as the [B,cin,hin,win] image whose unfold the reference stores.  bmm sums run over the output
+ * positions l = (oy, ox) in ascending order. */
+static void mstdp_conv_update(const snn_net_t *net, const snn_conn_t *C, const snn_run_opts_t *o, int dense) {
+    const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
+    const int B = o->B, ns = S->n, nt = G->n, L = C->hout * C->wout, K = C->cin * C->kh * C->kw;
+    /* weight update from the previous step's eligibility (:1973-1974) */
+    for (int co = 0; co < C->cout; ++co)
+        for (int k = 0; k < K; ++k) {
+            float upd = 0.0f;
+            for (int b = 0; b < B; ++b) upd = upd + C->reward * C->elig[((size_t)b * C->cout + co) * K + k];
+            C->w[(size_t)co * K + k] = C->w[(size_t)co * K + k] + C->nu0 * upd;
+        }
+    /* P+ / P- (:1999-2003) */
+    for (size_t k = 0; k < (size_t)B * ns; ++k) {
+        float x = C->p_plus[k] * C->p_plus_decay;
+        C->p_plus[k] = x + C->a_plus * (S->s[k] ? 1.0f : 0.0f);
+    }
+    for (size_t k = 0; k < (size_t)B * nt; ++k) {
+        float x = C->p_minus[k] * C->p_minus_decay;
+        C->p_minus[k] = x + C->a_minus * (G->s[k] ? 1.0f : 0.0f);
+    }
+    /* eligibility (:2005-2009): bmm(target_s, p_plus_col^T) + bmm(p_minus, source_s_col^T) */
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int co = 0; co < C->cout; ++co)
+            for (int ci = 0; ci < C->cin; ++ci)
+                for (int ky = 0; ky < C->kh; ++ky)
+                    for (int kx = 0; kx < C->kw; ++kx) {
+                        float s1 = 0.0f, s2 = 0.0f;
+                        for (int oy = 0; oy < C->hout; ++oy) {
+                            const int iy = oy * C->sh - C->ph + ky;
+                            if (iy < 0 || iy >= C->hin) continue;
+                            for (int ox = 0; ox < C->wout; ++ox) {
+                                const int ix = ox * C->sw - C->pw + kx;
+                                if (ix < 0 || ix >= C->win) continue;
+                                const size_t src = (size_t)b * ns + ((size_t)ci * C->hin + iy) * C->win + ix;
+                                const size_t tgt = (size_t)b * nt + (size_t)co * L + (size_t)oy * C->wout + ox;
+                                const uint8_t ts = G->s[tgt], ss = S->s[src];
+                                if (dense || ts) s1 = s1 + (ts ? 1.0f : 0.0f) * C->p_plus[src];
+                                if (dense || ss) s2 = s2 + C->p_minus[tgt] * (ss ? 1.0f : 0.0f);
+                            }
+                        }
+                        const int k = (ci * C->kh + ky) * C->kw + kx;
+                        C->elig[((size_t)b * C->cout + co) * K + k] = s1 + s2;
+                    }
+    /* base class (learning.py:87-104) */
+    for (size_t k = 0; k < (size_t)C->cout * K; ++k) {
+        float x = C->w[k];
+        if (C->weight_decay != 0.0f) x = x * C->weight_decay;
+        if (C->has_clamp) x = clampf(x, C->wmin, C->wmax);
+        C->w[k] = x;
+    }
+}
+
+/* Conv2dConnection.normalize (topology.py:824-837): every (out, in) filter is scaled to sum `norm`
+ * (plain sum over kh*kw in ascending order; no guard against a zero sum, like the reference). */
+static void normalize_conv(const snn_conn_t *C) {
+    const int F = C->cout * C->cin, KK = C->kh * C->kw;
+    for (int f = 0; f < F; ++f) {
+        float tot = 0.0f;
+        for (int k = 0; k < KK; ++k) tot = tot + C->w[(size_t)f * KK + k];
+        const float fac = C->norm / tot;
+        for (int k = 0; k < KK; ++k) C->w[(size_t)f * KK + k] = C->w[(size_t)f * KK + k] * fac;
+    }
+}
+
 /* Connection.normalize (topology.py:383-392) / AbstractFeature.normalize
  * (topology_features.py:250-266). */
 static void normalize_cols(float *w, int ns, int nt, int norm_abs, float norm) {
@@ -392,7 +543,7 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
     for (int c = 0; c < net->n_conns; ++c) {
         const snn_conn_t *C = &net->conns[c];
         const int ns = net->layers[C->src].n, nt = net->layers[C->tgt].n;
-        if (C->rule >= SNN_RULE_POSTPRE) {
+        if (C->rule >= SNN_RULE_POSTPRE && C->rule <= SNN_RULE_MCC_POSTPRE) {
             cws[c].U = (float *)calloc((size_t)ns * nt, sizeof(float));
             cws[c].V = (float *)calloc((size_t)ns * nt, sizeof(float));
             cws[c].tx = (float *)calloc((size_t)B * nt, sizeof(float));
@@ -408,13 +559,22 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
             const snn_conn_t *C = &net->conns[c];
             const snn_layer_t *G = &net->layers[C->tgt];
             if (!lws[C->tgt].has_in) { memset(lws[C->tgt].cur, 0, sizeof(float) * (size_t)B * G->n); lws[C->tgt].has_in = 1; }
-            conn_compute(C, &net->layers[C->src], G->n, B, lws[C->tgt].cur, dense);
+            if (C->kind == SNN_CONN_CONV2D) conv_compute(C, &net->layers[C->src], B, lws[C->tgt].cur, dense);
+            else conn_compute(C, &net->layers[C->src], G->n, B, lws[C->tgt].cur, dense);
         }
         /* 2. layers in insertion order (network.py:386-429) */
         for (int l = 0; l < net->n_layers; ++l) layer_forward(net, l, o, t, &lws[l], &err);
         /* 3. connection updates in insertion order (network.py:431-454) */
         if (net->learning)
-            for (int c = 0; c < net->n_conns; ++c) conn_update(net, &net->conns[c], o, &cws[c], dense);
+            for (int c = 0; c < net->n_conns; ++c) {
+                const snn_conn_t *C = &net->conns[c];
+                if (C->rule == SNN_RULE_MSTDP && C->kind == SNN_CONN_CONV2D) mstdp_conv_update(net, C, o, dense);
+                else if (C->rule == SNN_RULE_MSTDP) mstdp_dense_update(net, C, o, dense);
+                else if (C->kind == SNN_CONN_CONV2D) {  /* learning.NoOp on a conv connection: decay only */
+                    if (C->rule == SNN_RULE_NOOP && C->weight_decay != 0.0f)
+                        for (size_t k = 0; k < (size_t)C->cout * C->cin * C->kh * C->kw; ++k) C->w[k] = C->w[k] * C->weight_decay;
+                } else conn_update(net, C, o, &cws[c], dense);
+            }
         /* 4. monitors (network.py:460-461, monitors.py:94-111) */
         for (int l = 0; l < net->n_layers; ++l) {
             const snn_layer_t *L = &net->layers[l];
@@ -428,7 +588,8 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
     if (o->normalize)
         for (int c = 0; c < net->n_conns; ++c) {
             const snn_conn_t *C = &net->conns[c];
-            if (C->has_norm) normalize_cols(C->w, net->layers[C->src].n, net->layers[C->tgt].n, C->norm_abs, C->norm);
+            if (C->has_norm && C->kind == SNN_CONN_CONV2D) normalize_conv(C);
+            else if (C->has_norm) normalize_cols(C->w, net->layers[C->src].n, net->layers[C->tgt].n, C->norm_abs, C->norm);
         }
     for (int l = 0; l < net->n_layers; ++l) { free(lws[l].cur); free(lws[l].cand); }
     for (int c = 0; c < net->n_conns; ++c) { free(cws[c].U); free(cws[c].V); free(cws[c].tx); free(cws[c].row_t); free(cws[c].col_t); }

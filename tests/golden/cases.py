@@ -188,6 +188,57 @@ def dc2015_eval(ns, inputs=None):
     return net, inputs, kw, T
 
 
+# Reward-modulated STDP on a dense Connection (learning.MSTDP._connection_update, learning.py:1504-1574)
+def mstdp_dense(ns, inputs=None):
+    net = ns.Network(dt=1.0, batch_size=3)
+    X = ns.nodes.Input(n=60, traces=True)
+    Y = ns.nodes.LIFNodes(n=20, traces=True, thresh=-62.0, refrac=2)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    C = ns.topology.Connection(source=X, target=Y, w=_w((60, 20), 111, 1.2) - 0.2, update_rule=ns.learning.MSTDP,
+                               nu=5e-2, reduction=torch.sum, wmin=-1.0, wmax=1.5, tc_plus=15.0, tc_minus=25.0)
+    net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(80, 3, (60,), 0.12, 112)}
+    return net, inputs, {"reward": 0.7, "a_plus": 0.9, "a_minus": -1.1}, 80
+
+
+def _conv_net(ns, B, T, in_shape, out_ch, k, stride, padding, rule, seeds, n_out=6, norm=None, conv_nu=1e-2):
+    """BASELINE.json config 4 in small: Input[C,H,W] -> Conv2dConnection -> LIFNodes[Co,Ho,Wo] -> Connection ->
+    LIFNodes(n_out), MSTDP on both connections (or no rule), weights in [-1, 1]."""
+    cin, hin, win = in_shape
+    ho = (hin - k + 2 * padding) // stride + 1
+    wo = (win - k + 2 * padding) // stride + 1
+    net = ns.Network(dt=1.0, batch_size=B)
+    X = ns.nodes.Input(shape=[cin, hin, win], traces=True)
+    H = ns.nodes.LIFNodes(shape=[out_ch, ho, wo], traces=True, thresh=-63.5, refrac=2, tc_decay=60.0)
+    O = ns.nodes.LIFNodes(n=n_out, traces=True, thresh=-62.0, refrac=3)
+    net.add_layer(X, "X"); net.add_layer(H, "H"); net.add_layer(O, "O")
+    kw = dict(update_rule=rule, nu=conv_nu, reduction=torch.sum) if rule is not None else {}
+    conv = ns.topology.Conv2dConnection(source=X, target=H, kernel_size=k, stride=stride, padding=padding,
+                                        w=_w((out_ch, cin, k, k), seeds[0], 1.0) - 0.2, wmin=-1.0, wmax=1.0, norm=norm, **kw)
+    dense = ns.topology.Connection(source=H, target=O, w=_w((out_ch * ho * wo, n_out), seeds[1], 0.5) - 0.1,
+                                   wmin=-1.0, wmax=1.0, **kw)
+    net.add_connection(conv, "X", "H"); net.add_connection(dense, "H", "O")
+    return net
+
+
+# conv + dense MSTDP, batch 4 (per-sample eligibility: SURVEY.md §0.8 / §8c — the reference is run with
+# the one-line fix of learning.py:2013 that gen_golden.py applies)
+def conv_mstdp(ns, inputs=None):
+    net = _conv_net(ns, 4, 60, (1, 12, 12), 4, 3, 1, 0, ns.learning.MSTDP, (121, 122))
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(60, 4, (1, 12, 12), 0.1, 123)}
+    return net, inputs, {"reward": 1.0}, 60
+
+
+# conv geometry: two input channels, stride 2, padding 1, filter normalisation, no learning rule
+def conv_stride_norm(ns, inputs=None):
+    net = _conv_net(ns, 2, 40, (2, 9, 9), 3, 3, 2, 1, None, (131, 132), n_out=5, norm=1.5)
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(40, 2, (2, 9, 9), 0.15, 133)}
+    return net, inputs, {}, 40
+
+
 CASES = {
     "c1_lif_postpre": c1_lif_postpre,
     "lif_postpre_batch": lif_postpre_batch,
@@ -199,6 +250,9 @@ CASES = {
     "dc2015_eval": dc2015_eval,
     "dc2015_c2": dc2015_c2,
     "dc2015_metric_t40": dc2015_metric_t40,
+    "mstdp_dense": mstdp_dense,
+    "conv_mstdp": conv_mstdp,
+    "conv_stride_norm": conv_stride_norm,
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)

@@ -105,8 +105,33 @@ def conn_weight(conn) -> torch.Tensor:
     return conn.w if hasattr(conn, "w") and not hasattr(conn, "pipeline") else conn.pipeline[0].value
 
 
+def patch_reference_conv_mstdp(ns) -> None:
+    """``MSTDP._conv2d_connection_update`` allocates a per-sample eligibility
+    ``[B, *w.shape]`` (learning.py:1958-1961) and sums ``reward * eligibility`` over dim 0 (:1973-1974), but its
+    last line views the new eligibility as ``w.size()`` (:2013) — that raises for B > 1 and, for B = 1, makes
+    the next step sum over the OUTPUT CHANNELS instead of the batch.  The goldens are produced by the
+    reference's own code with that one view taken per sample (the source is re-executed from
+    /root/reference at run time, nothing is copied)."""
+    import inspect
+    import textwrap
+
+    L = ns.learning
+    if getattr(L.MSTDP, "_b200_patched", False):
+        return
+    src = textwrap.dedent(inspect.getsource(L.MSTDP._conv2d_connection_update))
+    bad = "self.eligibility = self.eligibility.view(self.connection.w.size())"
+    assert bad in src and "super().update()" in src
+    src = src.replace(bad, "self.eligibility = self.eligibility.view(batch_size, *self.connection.w.size())")
+    src = src.replace("super().update()", "LearningRule.update(self)")  # zero-arg super() has no __class__ cell under exec
+    g = dict(vars(sys.modules[L.MSTDP.__module__]))
+    exec(src, g)
+    L.MSTDP._conv2d_connection_update = g["_conv2d_connection_update"]
+    L.MSTDP._b200_patched = True
+
+
 def generate(name: str) -> None:
     ns = cases.namespace("reference")
+    patch_reference_conv_mstdp(ns)
     torch.manual_seed(1234)
     net, inputs, kw, T = cases.CASES[name](ns)
     w0 = {f"{s}->{t}": conn_weight(c).detach().clone() for (s, t), c in net.connections.items()}

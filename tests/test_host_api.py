@@ -8,12 +8,12 @@ import pytest
 import torch
 
 from bindsnet_b200 import _abi, _backend
-from bindsnet_b200.learning import NoOp, PostPre, WeightDependentPostPre, MSTDP
+from bindsnet_b200.learning import NoOp, PostPre, WeightDependentPostPre, MSTDP, MSTDPET
 from bindsnet_b200.models import DiehlAndCook2015, DiehlAndCook2015v2, TwoLayerNetwork
 from bindsnet_b200.network import Network, load
 from bindsnet_b200.network.monitors import Monitor
 from bindsnet_b200.network.nodes import DiehlAndCookNodes, IFNodes, Input, LIFNodes
-from bindsnet_b200.network.topology import Connection, Conv2dConnection, MulticompartmentConnection
+from bindsnet_b200.network.topology import Connection, Conv1dConnection, Conv2dConnection, MulticompartmentConnection
 from bindsnet_b200.network.topology_features import Weight
 from oracle.oracle import OracleBackend
 
@@ -49,10 +49,17 @@ def test_unsupported_reference_features_fail_loudly():
     with pytest.raises(NotImplementedError):
         IFNodes(n=10)
     with pytest.raises(NotImplementedError):
-        Conv2dConnection(None, None, 3)
+        Conv1dConnection(None, None, 3)
     X, Y = Input(n=4, traces=True), LIFNodes(n=4, traces=True)
     with pytest.raises(NotImplementedError):
-        Connection(X, Y, update_rule=MSTDP)
+        Connection(X, Y, update_rule=MSTDPET)
+    # MSTDP is implemented; its reward is mandatory like in the reference
+    net = Network(dt=1.0, batch_size=1)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    net.add_connection(Connection(X, Y, update_rule=MSTDP, nu=1e-2, wmin=-1.0, wmax=1.0), "X", "Y")
+    with OracleBackend():
+        with pytest.raises(KeyError):
+            net.run({"X": torch.zeros(3, 1, 4)}, time=3)
     with pytest.raises(NotImplementedError):
         Connection(X, Y, w_dtype=torch.float16)
     net = TwoLayerNetwork(n_inpt=8, n_neurons=4)
