@@ -34,15 +34,29 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
         const snn_conn_t &C = net->conns[c];
         if (C.src < 0 || C.src >= net->n_layers || C.tgt < 0 || C.tgt >= net->n_layers || !C.w) return SNN_ERR_BAD_ARG;
         if (net->layers[C.tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
-        if (C.rule < SNN_RULE_NONE || C.rule > SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
-        if (C.rule >= SNN_RULE_POSTPRE && (!net->layers[C.src].traces || !net->layers[C.tgt].traces)) return SNN_ERR_BAD_ARG;
+        if (C.rule < SNN_RULE_NONE || C.rule > SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+        if (C.kind < SNN_CONN_DENSE || C.kind > SNN_CONN_CONV2D) return SNN_ERR_UNSUPPORTED;
+        if (C.kind == SNN_CONN_CONV2D) {
+            const snn_layer_t &S = net->layers[C.src], &G = net->layers[C.tgt];
+            if (C.cin * C.hin * C.win != S.n || C.cout * C.hout * C.wout != G.n || !C.b) return SNN_ERR_BAD_ARG;
+            if (C.kh < 1 || C.kw < 1 || C.sh < 1 || C.sw < 1 || C.dh < 1 || C.dw < 1) return SNN_ERR_BAD_ARG;
+            if (C.rule != SNN_RULE_NONE && C.rule != SNN_RULE_NOOP && C.rule != SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+        }
+        if (C.rule == SNN_RULE_MSTDP) {
+            if (!C.p_plus || !C.p_minus) return SNN_ERR_BAD_ARG;
+            if (C.kind == SNN_CONN_CONV2D) { if (!C.elig || C.dh != 1 || C.dw != 1) return SNN_ERR_BAD_ARG; }
+            else if (C.kind == SNN_CONN_DENSE) { if (!C.mst_spre || !C.mst_spost) return SNN_ERR_BAD_ARG; }
+            else return SNN_ERR_UNSUPPORTED;
+        }
+        if (C.rule >= SNN_RULE_POSTPRE && C.rule <= SNN_RULE_MCC_POSTPRE && (!net->layers[C.src].traces || !net->layers[C.tgt].traces))
+            return SNN_ERR_BAD_ARG;
     }
     return SNN_OK;
 }
 
 static bool layer_needs_xpub(const snn_net_t *net, int l) {
     for (int c = 0; c < net->n_conns; ++c)
-        if (net->conns[c].src == l && net->conns[c].rule >= SNN_RULE_POSTPRE) return true;
+        if (net->conns[c].src == l && net->conns[c].rule >= SNN_RULE_POSTPRE && net->conns[c].rule <= SNN_RULE_MCC_POSTPRE) return true;
     return false;
 }
 
@@ -71,6 +85,25 @@ static size_t layout_generic(const snn_net_t *net, const snn_run_opts_t *o, char
         if (N && os) N->any_one_spike = 1;
     }
     if (N) N->total_items = items;
+    // second slot of every MSTDP rule's state (DevMstdp)
+    for (int c = 0; c < net->n_conns; ++c) {
+        const snn_conn_t &C = net->conns[c];
+        if (C.rule != SNN_RULE_MSTDP) continue;
+        const size_t ns = (size_t)net->layers[C.src].n, nt = (size_t)net->layers[C.tgt].n;
+        auto take = [&](size_t bytes) { char *p = ws ? ws + off : nullptr; off += align_up(bytes); return p; };
+        char *pp = take(sizeof(float) * B * ns), *pm = take(sizeof(float) * B * nt);
+        if (N) {
+            DevMstdp &M = N->mst[c];
+            M.pp[0] = C.p_plus; M.pm[0] = C.p_minus; M.pp[1] = (float *)pp; M.pm[1] = (float *)pm;
+        }
+        if (C.kind == SNN_CONN_CONV2D) {
+            char *el = take(sizeof(float) * B * (size_t)C.cout * C.cin * C.kh * C.kw);
+            if (N) { N->mst[c].el[0] = C.elig; N->mst[c].el[1] = (float *)el; }
+        } else {
+            char *sp = take(B * ns), *st = take(B * nt);
+            if (N) { N->mst[c].sp[0] = C.mst_spre; N->mst[c].st[0] = C.mst_spost; N->mst[c].sp[1] = (uint8_t *)sp; N->mst[c].st[1] = (uint8_t *)st; }
+        }
+    }
     return off;
 }
 
@@ -79,7 +112,7 @@ extern "C" {
 int snn_b200_abi_version(void) { return SNN_ABI_VERSION; }
 
 const char *snn_b200_build_info(void) {
-    return "libsnn_b200 sm_100a (generic window + fused DC2015 window), ABI " "5" ", built " __DATE__ " " __TIME__;
+    return "libsnn_b200 sm_100a (generic window + fused DC2015 window), ABI " "6" ", built " __DATE__ " " __TIME__;
 }
 
 int snn_b200_last_launch_count(void) { return g_last_launches; }

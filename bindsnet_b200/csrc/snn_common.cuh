@@ -26,6 +26,14 @@ struct DevLayer {
     int32_t item0;              // first work-item index of this layer
 };
 
+// State of an MSTDP rule, double-buffered: step t reads slot (t + T) & 1 and writes the other one, so
+// that no thread overwrites a value another one still needs in the same step; slot 0 is the caller's
+// tensors (snn_conn_t::p_plus ...), slot 1 lives in the workspace.
+struct DevMstdp {
+    float *pp[2], *pm[2], *el[2];
+    uint8_t *sp[2], *st[2];
+};
+
 struct DevNet {
     int32_t n_layers, n_conns, learning, T, B, normalize, total_items, any_one_spike;
     uint32_t seed, step_offset;
@@ -33,6 +41,7 @@ struct DevNet {
     unsigned int *bar;          // [0] arrival count, [32] generation, [64] abort
     DevLayer layers[SNN_MAX_LAYERS];
     snn_conn_t conns[SNN_MAX_CONNS];
+    DevMstdp mst[SNN_MAX_CONNS];
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {

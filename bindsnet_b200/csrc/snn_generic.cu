@@ -52,6 +52,22 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) snn_generic_window(const __gr
         }
         if (D.keys && tile == 0)
             for (int b = threadIdx.x; b < 2 * N.B; b += blockDim.x) D.keys[b] = 0ull;
+        // MSTDP state: step t reads slot (t + T) & 1; for an odd T the first read is slot 1, so the
+        // caller's tensors (slot 0) are copied there — the last step then writes slot 0
+        if (N.learning && (N.T & 1))
+            for (int c = 0; c < N.n_conns; ++c) {
+                const snn_conn_t &C = N.conns[c];
+                if (C.tgt != li || C.rule != SNN_RULE_MSTDP) continue;
+                const DevMstdp &M = N.mst[c];
+                const size_t ns = (size_t)N.layers[C.src].L.n, nt = (size_t)D.L.n, Bz = (size_t)N.B;
+                const size_t start = (size_t)tile * SNN_GEN_THREADS + threadIdx.x, stride = (size_t)D.nw * SNN_GEN_THREADS;
+                for (size_t k = start; k < Bz * ns; k += stride) { M.pp[1][k] = M.pp[0][k]; if (M.sp[0]) M.sp[1][k] = M.sp[0][k]; }
+                for (size_t k = start; k < Bz * nt; k += stride) { M.pm[1][k] = M.pm[0][k]; if (M.st[0]) M.st[1][k] = M.st[0][k]; }
+                if (M.el[0]) {
+                    const size_t ne = Bz * (size_t)C.cout * C.cin * C.kh * C.kw;
+                    for (size_t k = start; k < ne; k += stride) M.el[1][k] = M.el[0][k];
+                }
+            }
     }
     if (!grid_barrier(N.bar, G, N.err)) return;
 
@@ -72,9 +88,13 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) snn_generic_window(const __gr
         if (N.learning) {
             for (int item = blockIdx.x; item < N.total_items; item += G) {
                 int li, tile; item_of(N, item, li, tile);
-                for (int c = 0; c < N.n_conns; ++c)
-                    if (N.conns[c].tgt == li && N.conns[c].rule != SNN_RULE_NONE)
-                        phase3(N, c, tile, t, s_acc, s_colmask, &s_flag);
+                for (int c = 0; c < N.n_conns; ++c) {
+                    const snn_conn_t &C = N.conns[c];
+                    if (C.tgt != li || C.rule == SNN_RULE_NONE) continue;
+                    if (C.kind == SNN_CONN_CONV2D) phase3_conv(N, c, tile, t);
+                    else if (C.rule == SNN_RULE_MSTDP) phase3_mstdp_dense(N, c, tile, t);
+                    else phase3(N, c, tile, t, s_acc, s_colmask, &s_flag);
+                }
             }
             __syncthreads();
         }
@@ -84,8 +104,10 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) snn_generic_window(const __gr
         for (int item = blockIdx.x; item < N.total_items; item += G) {
             int li, tile; item_of(N, item, li, tile);
             for (int c = 0; c < N.n_conns; ++c)
-                if (N.conns[c].tgt == li && N.conns[c].has_norm)
-                    normalize_tile(N.conns[c], N.layers[N.conns[c].src].L.n, N.layers[li].L.n, tile, s_red);
+                if (N.conns[c].tgt == li && N.conns[c].has_norm) {
+                    if (N.conns[c].kind == SNN_CONN_CONV2D) normalize_conv_item(N.conns[c], tile, N.layers[li].nw);
+                    else normalize_tile(N.conns[c], N.layers[N.conns[c].src].L.n, N.layers[li].L.n, tile, s_red);
+                }
         }
     }
 }

@@ -43,6 +43,28 @@ __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__r
     return p;
 }
 
+// Conv2dConnection.compute (topology.py:799-815) for one target neuron j = (co, oy, ox) of one
+// sample: the sum of the filter taps whose (zero-padded) input position spiked, in ascending
+// (ci, ky, kx) order, then the bias.
+__device__ __forceinline__ float gather_conv(const snn_conn_t &C, const uint32_t *__restrict__ sb, int j, bool valid) {
+    if (!valid) return 0.0f;
+    const int L = C.hout * C.wout;
+    const int co = j / L, l = j - co * L, oy = l / C.wout, ox = l - oy * C.wout;
+    float p = 0.0f;
+    for (int ci = 0; ci < C.cin; ++ci)
+        for (int ky = 0; ky < C.kh; ++ky) {
+            const int iy = oy * C.sh - C.ph + ky * C.dh;
+            if (iy < 0 || iy >= C.hin) continue;
+            for (int kx = 0; kx < C.kw; ++kx) {
+                const int ix = ox * C.sw - C.pw + kx * C.dw;
+                if (ix < 0 || ix >= C.win) continue;
+                const int i = (ci * C.hin + iy) * C.win + ix;
+                if ((__ldcg(sb + (i >> 5)) >> (i & 31)) & 1u) p = p + C.w[((co * C.cin + ci) * C.kh + ky) * C.kw + kx];
+            }
+        }
+    return p + C.b[co];
+}
+
 // ---------------------------------------------------------------------------------------
 // phase 1
 __device__ void phase1(const DevNet &N, int li, int tile, int t, float *s_red, int32_t *s_flag) {
@@ -80,8 +102,13 @@ __device__ void phase1(const DevNet &N, int li, int tile, int t, float *s_red, i
                 const snn_conn_t &C = N.conns[c];
                 if (C.tgt != li) continue;
                 const DevLayer &S = N.layers[C.src];
-                float p = gather(C, S.bits + ((size_t)rd * B + b) * S.nw, S.nw, S.L.n, n, j, valid, lane);
-                if (C.b && valid) p = p + C.b[j];
+                float p;
+                if (C.kind == SNN_CONN_CONV2D) {
+                    p = gather_conv(C, S.bits + ((size_t)rd * B + b) * S.nw, j, valid);
+                } else {
+                    p = gather(C, S.bits + ((size_t)rd * B + b) * S.nw, S.nw, S.L.n, n, j, valid, lane);
+                    if (C.b && valid) p = p + C.b[j];
+                }
                 cur = cur + p;
             }
             if (valid) {
@@ -300,6 +327,130 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int t, float *s_acc, u
     }
     __syncthreads();
     (void)s_flag;
+}
+
+// ---------------------------------------------------------------------------------------
+// phase 3 for reward-modulated STDP and for convolutional connections.  The rule's state is double
+// buffered (DevMstdp): everything is READ from slot `in` and WRITTEN to slot `out`, so no thread
+// overwrites a value another thread still needs in this step; the work is spread over the items
+// (32-neuron tiles) of the connection's target layer with grid-stride loops.
+__device__ __forceinline__ float mst_trace(float p, float decay, float a, bool s) {
+    // learning.py:1564-1567 / 1999-2003:  P *= exp(-dt/tc);  P += a * s
+    const float x = p * decay;
+    return x + a * (s ? 1.0f : 0.0f);
+}
+__device__ __forceinline__ bool bit_of(const uint32_t *row, int i) { return (__ldcg(row + (i >> 5)) >> (i & 31)) & 1u; }
+
+// learning.MSTDP._connection_update (learning.py:1504-1574) + base class decay / clamp (:87-104).
+__device__ void phase3_mstdp_dense(const DevNet &N, int ci_, int tile, int t) {
+    const snn_conn_t &C = N.conns[ci_];
+    const DevMstdp &M = N.mst[ci_];
+    const DevLayer &S = N.layers[C.src], &G = N.layers[C.tgt];
+    const int B = N.B, ns = S.L.n, nt = G.L.n, ntiles = G.nw;
+    const int in = (t + N.T) & 1, out = in ^ 1, wr = t & 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = tile * SNN_TILE + lane;
+    const float Bf = (float)B;
+    const float *pp = M.pp[in], *pm = M.pm[in];
+    const uint8_t *sp = M.sp[in], *st = M.st[in];
+    // weight update from the eligibility of the previous step = p_plus (x) s_post + s_pre (x) p_minus
+    if (j < nt)
+        for (int i = warp; i < ns; i += SNN_GEN_WARPS) {
+            float upd = 0.0f;
+            for (int b = 0; b < B; ++b) {
+                const bool ss = sp[(size_t)b * ns + i] != 0, tt = st[(size_t)b * nt + j] != 0;
+                if (!ss && !tt) continue;
+                const float e = pp[(size_t)b * ns + i] * (tt ? 1.0f : 0.0f) + (ss ? 1.0f : 0.0f) * pm[(size_t)b * nt + j];
+                upd = upd + C.reward * e;
+            }
+            if (C.reduction == SNN_REDUCE_MEAN) upd = upd / Bf;
+            float x = C.w[(size_t)i * nt + j] + C.nu0 * upd;
+            if (C.weight_decay != 0.0f) x = x * C.weight_decay;
+            if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
+            C.w[(size_t)i * nt + j] = x;
+        }
+    // P+, P- and the spikes of this step, for the next one
+    for (size_t k = (size_t)tile * SNN_GEN_THREADS + threadIdx.x; k < (size_t)B * ns; k += (size_t)ntiles * SNN_GEN_THREADS) {
+        const int b = (int)(k / ns), i = (int)(k - (size_t)b * ns);
+        const bool s = bit_of(S.bits + ((size_t)wr * B + b) * S.nw, i);
+        M.pp[out][k] = mst_trace(pp[k], C.p_plus_decay, C.a_plus, s);
+        M.sp[out][k] = s ? 1 : 0;
+    }
+    for (size_t k = (size_t)tile * SNN_GEN_THREADS + threadIdx.x; k < (size_t)B * nt; k += (size_t)ntiles * SNN_GEN_THREADS) {
+        const int b = (int)(k / nt), jj = (int)(k - (size_t)b * nt);
+        const bool s = bit_of(G.bits + ((size_t)wr * B + b) * G.nw, jj);
+        M.pm[out][k] = mst_trace(pm[k], C.p_minus_decay, C.a_minus, s);
+        M.st[out][k] = s ? 1 : 0;
+    }
+}
+
+// learning.MSTDP._conv2d_connection_update (learning.py:1942-2015) with a per-sample eligibility
+// (SURVEY.md §0.8), and the decay-only update of a conv connection without a rule (learning.NoOp).
+__device__ void phase3_conv(const DevNet &N, int ci_, int tile, int t) {
+    const snn_conn_t &C = N.conns[ci_];
+    const DevMstdp &M = N.mst[ci_];
+    const DevLayer &S = N.layers[C.src], &G = N.layers[C.tgt];
+    const int B = N.B, ns = S.L.n, nt = G.L.n, ntiles = G.nw;
+    const int K = C.cin * C.kh * C.kw, L = C.hout * C.wout, NWT = C.cout * K;
+    const size_t start = (size_t)tile * SNN_GEN_THREADS + threadIdx.x, stride = (size_t)ntiles * SNN_GEN_THREADS;
+    if (C.rule != SNN_RULE_MSTDP) {  // learning.NoOp: w *= weight_decay (learning.py:93-94), no clamp
+        if (C.rule == SNN_RULE_NOOP && C.weight_decay != 0.0f)
+            for (size_t k = start; k < (size_t)NWT; k += stride) C.w[k] = C.w[k] * C.weight_decay;
+        return;
+    }
+    const int in = (t + N.T) & 1, out = in ^ 1, wr = t & 1;
+    const float *pp = M.pp[in], *pm = M.pm[in], *el = M.el[in];
+    // w += nu0 * sum_b reward * eligibility(t-1)  (:1973-1974), then decay / clamp (learning.py:87-104)
+    for (size_t k = start; k < (size_t)NWT; k += stride) {
+        float upd = 0.0f;
+        for (int b = 0; b < B; ++b) upd = upd + C.reward * el[(size_t)b * NWT + k];
+        float x = C.w[k] + C.nu0 * upd;
+        if (C.weight_decay != 0.0f) x = x * C.weight_decay;
+        if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
+        C.w[k] = x;
+    }
+    // P+ (trace image of the source), P- (:1999-2003)
+    for (size_t k = start; k < (size_t)B * ns; k += stride) {
+        const int b = (int)(k / ns), i = (int)(k - (size_t)b * ns);
+        M.pp[out][k] = mst_trace(pp[k], C.p_plus_decay, C.a_plus, bit_of(S.bits + ((size_t)wr * B + b) * S.nw, i));
+    }
+    for (size_t k = start; k < (size_t)B * nt; k += stride) {
+        const int b = (int)(k / nt), jj = (int)(k - (size_t)b * nt);
+        M.pm[out][k] = mst_trace(pm[k], C.p_minus_decay, C.a_minus, bit_of(G.bits + ((size_t)wr * B + b) * G.nw, jj));
+    }
+    // eligibility(t)[b,co,k] = sum_l s_post[b,co,l] * P+col[b,k,l]  +  sum_l P-[b,co,l] * s_pre_col[b,k,l]
+    // (:2005-2009), l = (oy, ox) ascending, with the UPDATED traces (recomputed here from slot `in`)
+    for (size_t e = start; e < (size_t)B * NWT; e += stride) {
+        const int b = (int)(e / NWT), r = (int)(e - (size_t)b * NWT), co = r / K, k = r - co * K;
+        const int ci = k / (C.kh * C.kw), kk = k - ci * C.kh * C.kw, ky = kk / C.kw, kx = kk - ky * C.kw;
+        const uint32_t *sb = S.bits + ((size_t)wr * B + b) * S.nw, *gb = G.bits + ((size_t)wr * B + b) * G.nw;
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int oy = 0; oy < C.hout; ++oy) {
+            const int iy = oy * C.sh - C.ph + ky;
+            if (iy < 0 || iy >= C.hin) continue;
+            for (int ox = 0; ox < C.wout; ++ox) {
+                const int ix = ox * C.sw - C.pw + kx;
+                if (ix < 0 || ix >= C.win) continue;
+                const int src = (ci * C.hin + iy) * C.win + ix, tgt = co * L + oy * C.wout + ox;
+                const bool ss = bit_of(sb, src), ts = bit_of(gb, tgt);
+                if (ts) s1 = s1 + mst_trace(pp[(size_t)b * ns + src], C.p_plus_decay, C.a_plus, ss);
+                if (ss) s2 = s2 + mst_trace(pm[(size_t)b * nt + tgt], C.p_minus_decay, C.a_minus, ts);
+            }
+        }
+        M.el[out][e] = s1 + s2;
+    }
+}
+
+// Conv2dConnection.normalize (topology.py:824-837): every (out, in) filter scaled to sum `norm`
+// (plain sum in ascending order; no guard against a zero sum, like the reference).
+__device__ void normalize_conv_item(const snn_conn_t &C, int tile, int ntiles) {
+    const int F = C.cout * C.cin, KK = C.kh * C.kw;
+    for (int f = tile * SNN_GEN_THREADS + threadIdx.x; f < F; f += ntiles * SNN_GEN_THREADS) {
+        float tot = 0.0f;
+        for (int k = 0; k < KK; ++k) tot = tot + C.w[(size_t)f * KK + k];
+        const float fac = C.norm / tot;
+        for (int k = 0; k < KK; ++k) C.w[(size_t)f * KK + k] = C.w[(size_t)f * KK + k] * fac;
+    }
 }
 
 // normalize(): Connection.normalize (topology.py:383-392) / AbstractFeature.normalize
