@@ -274,6 +274,27 @@ def main():
     net.check_errors()
     value = world * BATCH * T_STEPS * K / (ms_total * 1e-3)
 
+    # ---- the same loop with Ae + Ai spike monitors on (report both) -------------------
+    K2 = max(1, min(K, 5))
+    for lname in ("Ae", "Ai"):
+        net.add_monitor(Monitor(net.layers[lname], ["s"], time=T_STEPS, device=dev), f"{lname}_s")
+    for i in range(2):
+        window(resident[i % POOL])
+    barrier()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for i in range(K2):
+        window(resident[(2 + i) % POOL])
+    m1.record()
+    barrier()
+    msm = torch.tensor([m0.elapsed_time(m1)], device=dev)
+    if world > 1:
+        dist.all_reduce(msm, op=dist.ReduceOp.MAX)
+    value_monitors = world * BATCH * T_STEPS * K2 / (float(msm) * 1e-3)
+    for lname in ("Ae", "Ai"):
+        del net.monitors[f"{lname}_s"]
+    net.check_errors()
+
     # ---- e2e: host buffers through the public API, H2D + result D2H inside the timed region --
     from bindsnet_b200.network.monitors import SpikeCounter
 
@@ -354,6 +375,7 @@ def main():
                 "l2": f"inputs cycle through {POOL} distinct windows ({POOL * 25} MB > 126 MB L2); the 5 MB weight matrix is resident by design",
                 "kernel_tier": tier, "state_reset_between_windows": True,
             },
+            "value_with_spike_monitors": value_monitors,  # Ae + Ai [T, B, n] rasters written by the kernel every window
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T_STEPS * BATCH * N_INPT,
                     "d2h_bytes_per_step": BATCH * N_NEURONS * 4,
                     "note": "pinned host uint8 spike trains -> WindowPrefetcher (H2D on a side stream, overlapped) -> Network.run + SpikeCounter on Ae -> AsyncReadback: the [B, n] per-sample spike counts (what label assignment consumes) copied to pinned host memory and read there every window, one window behind the launches",

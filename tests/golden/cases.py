@@ -239,6 +239,25 @@ def conv_stride_norm(ns, inputs=None):
     return net, inputs, {}, 40
 
 
+# BASELINE.json config 4 at full geometry (Input[1,32,32] -conv k5 s1-> LIFNodes[16,28,28] -> Connection ->
+# LIFNodes(10), MSTDP nu=1e-2 on both, w in [-1,1] drawn like the constructors do, reward 1, Bernoulli(0.1)
+# input), batch 8 and 40 steps to keep the live reference and the fixture small
+def conv_mstdp_c4(ns, inputs=None):
+    net = ns.Network(dt=1.0, batch_size=8)
+    X = ns.nodes.Input(shape=[1, 32, 32], traces=True)
+    H = ns.nodes.LIFNodes(shape=[16, 28, 28], traces=True)
+    O = ns.nodes.LIFNodes(n=10, traces=True)
+    net.add_layer(X, "X"); net.add_layer(H, "H"); net.add_layer(O, "O")
+    conv = ns.topology.Conv2dConnection(source=X, target=H, kernel_size=5, stride=1, w=2.0 * _w((16, 1, 5, 5), 141) - 1.0,
+                                        update_rule=ns.learning.MSTDP, nu=1e-2, reduction=torch.sum, wmin=-1.0, wmax=1.0)
+    dense = ns.topology.Connection(source=H, target=O, w=2.0 * _w((16 * 28 * 28, 10), 142) - 1.0,
+                                   update_rule=ns.learning.MSTDP, nu=1e-2, reduction=torch.sum, wmin=-1.0, wmax=1.0)
+    net.add_connection(conv, "X", "H"); net.add_connection(dense, "H", "O")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(40, 8, (1, 32, 32), 0.1, 143)}
+    return net, inputs, {"reward": 1.0}, 40
+
+
 CASES = {
     "c1_lif_postpre": c1_lif_postpre,
     "lif_postpre_batch": lif_postpre_batch,
@@ -253,9 +272,10 @@ CASES = {
     "mstdp_dense": mstdp_dense,
     "conv_mstdp": conv_mstdp,
     "conv_stride_norm": conv_stride_norm,
+    "conv_mstdp_c4": conv_mstdp_c4,
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)
-LARGE = {"dc2015_metric_t40"}
+LARGE = {"dc2015_metric_t40", "conv_mstdp_c4"}
 #: one_spike tie-break seed used by every case
 ONE_SPIKE_SEED = 20260922
