@@ -152,7 +152,11 @@ int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *
     N.n_layers = net->n_layers; N.n_conns = net->n_conns; N.learning = net->learning;
     N.T = opts->T; N.B = opts->B; N.normalize = opts->normalize;
     N.seed = opts->seed; N.step_offset = opts->step_offset; N.err = opts->err_flag;
-    for (int c = 0; c < net->n_conns; ++c) N.conns[c] = net->conns[c];
+    for (int c = 0; c < net->n_conns; ++c) {
+        N.conns[c] = net->conns[c];
+        const snn_conn_t &C = net->conns[c];
+        if (C.rule == SNN_RULE_MSTDP || (C.kind == SNN_CONN_CONV2D && C.rule != SNN_RULE_NONE)) N.sync_after_learning = 1;
+    }
     if (cudaMemsetAsync(N.bar, 0, sizeof(unsigned int) * 96, stream) != cudaSuccess) return SNN_ERR_CUDA;
     const int e = snn_generic_launch(N, stream);
     if (e != 0) {

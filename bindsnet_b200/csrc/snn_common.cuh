@@ -36,6 +36,8 @@ struct DevMstdp {
 
 struct DevNet {
     int32_t n_layers, n_conns, learning, T, B, normalize, total_items, any_one_spike;
+    int32_t sync_after_learning;  // some rule updates weights another CTA gathers from in the next step
+                                  // (MSTDP, conv connections): one more grid barrier per step
     uint32_t seed, step_offset;
     int32_t *err;               // device error flags (may be NULL)
     unsigned int *bar;          // [0] arrival count, [32] generation, [64] abort

@@ -17,7 +17,8 @@
 //   barrier  (only if some DiehlAndCookNodes layer has one_spike)
 //   phase 2  one_spike layers: resolve the winner per sample, final spikes, traces
 //   barrier
-//   phase 3  STDP + decay + clamp on the item's weight tiles (learning.py / MCC_learning.py)
+//   phase 3  STDP + decay + clamp on the item's weight tiles (learning.py / MCC_learning.py); MSTDP and
+//            conv connections (weights shared between items): + one barrier
 // After the last step: normalize() of the item's tiles (network.py:464-465).
 #include "snn_phases.cuh"
 
@@ -90,13 +91,20 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) snn_generic_window(const __gr
                 int li, tile; item_of(N, item, li, tile);
                 for (int c = 0; c < N.n_conns; ++c) {
                     const snn_conn_t &C = N.conns[c];
-                    if (C.tgt != li || C.rule == SNN_RULE_NONE) continue;
+                    if (C.rule == SNN_RULE_NONE) continue;
+                    if (C.rule == SNN_RULE_MSTDP && C.kind != SNN_CONN_CONV2D) {  // dense MSTDP: by source rows
+                        if (C.src == li) phase3_mstdp_dense(N, c, tile, t);
+                        continue;
+                    }
+                    if (C.tgt != li) continue;
                     if (C.kind == SNN_CONN_CONV2D) phase3_conv(N, c, tile, t);
-                    else if (C.rule == SNN_RULE_MSTDP) phase3_mstdp_dense(N, c, tile, t);
                     else phase3(N, c, tile, t, s_acc, s_colmask, &s_flag);
                 }
             }
             __syncthreads();
+            // PostPre-family updates touch only the item's own column tile; MSTDP (spread over the source
+            // rows) and conv filters are read by other CTAs in the next step's gather
+            if (N.sync_after_learning && !grid_barrier(N.bar, G, N.err)) return;
         }
     }
 

@@ -25,6 +25,7 @@ __device__ __forceinline__ float ld_ext(const snn_layer_t &L, size_t idx, bool &
 __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__restrict__ sb, int nw_src,
                                         int n_src, int n_tgt, int j, bool valid, int lane) {
     float p = 0.0f;
+    const bool shared_w = C.rule == SNN_RULE_MSTDP;
     for (int w0 = 0; w0 < nw_src; w0 += 32) {
         const uint32_t mine = (w0 + lane < nw_src) ? __ldcg(sb + w0 + lane) : 0u;
         uint32_t nz = __ballot_sync(0xffffffffu, mine != 0u);
@@ -36,7 +37,8 @@ __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__r
             while (word) {
                 const int i = base + __ffs(word) - 1;
                 word &= word - 1;
-                if (valid && i < n_src) p = p + C.w[(size_t)i * n_tgt + j];
+                // MSTDP weights are written by other CTAs (phase3_mstdp_dense): read them from L2
+                if (valid && i < n_src) p = p + (shared_w ? __ldcg(C.w + (size_t)i * n_tgt + j) : C.w[(size_t)i * n_tgt + j]);
             }
         }
     }
@@ -59,7 +61,7 @@ __device__ __forceinline__ float gather_conv(const snn_conn_t &C, const uint32_t
                 const int ix = ox * C.sw - C.pw + kx * C.dw;
                 if (ix < 0 || ix >= C.win) continue;
                 const int i = (ci * C.hin + iy) * C.win + ix;
-                if ((__ldcg(sb + (i >> 5)) >> (i & 31)) & 1u) p = p + C.w[((co * C.cin + ci) * C.kh + ky) * C.kw + kx];
+                if ((__ldcg(sb + (i >> 5)) >> (i & 31)) & 1u) p = p + __ldcg(C.w + ((co * C.cin + ci) * C.kh + ky) * C.kw + kx);
             }
         }
     return p + C.b[co];
@@ -342,25 +344,28 @@ __device__ __forceinline__ float mst_trace(float p, float decay, float a, bool s
 __device__ __forceinline__ bool bit_of(const uint32_t *row, int i) { return (__ldcg(row + (i >> 5)) >> (i & 31)) & 1u; }
 
 // learning.MSTDP._connection_update (learning.py:1504-1574) + base class decay / clamp (:87-104).
+// Work is spread over the items of the SOURCE layer (a dense layer's target is often tiny — 10 output
+// neurons in BASELINE config 4 — while its source has thousands of rows): item = 32 rows i (one per
+// lane) x all columns j (warps stride over them); the batch sum runs in ascending b per (i, j).
 __device__ void phase3_mstdp_dense(const DevNet &N, int ci_, int tile, int t) {
     const snn_conn_t &C = N.conns[ci_];
     const DevMstdp &M = N.mst[ci_];
     const DevLayer &S = N.layers[C.src], &G = N.layers[C.tgt];
-    const int B = N.B, ns = S.L.n, nt = G.L.n, ntiles = G.nw;
+    const int B = N.B, ns = S.L.n, nt = G.L.n;
     const int in = (t + N.T) & 1, out = in ^ 1, wr = t & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = tile * SNN_TILE + lane;
+    const int i = tile * SNN_TILE + lane;
     const float Bf = (float)B;
     const float *pp = M.pp[in], *pm = M.pm[in];
     const uint8_t *sp = M.sp[in], *st = M.st[in];
     // weight update from the eligibility of the previous step = p_plus (x) s_post + s_pre (x) p_minus
-    if (j < nt)
-        for (int i = warp; i < ns; i += SNN_GEN_WARPS) {
+    if (i < ns)
+        for (int j = warp; j < nt; j += SNN_GEN_WARPS) {
             float upd = 0.0f;
             for (int b = 0; b < B; ++b) {
-                const bool ss = sp[(size_t)b * ns + i] != 0, tt = st[(size_t)b * nt + j] != 0;
+                const bool ss = __ldcg(sp + (size_t)b * ns + i) != 0, tt = __ldcg(st + (size_t)b * nt + j) != 0;
                 if (!ss && !tt) continue;
-                const float e = pp[(size_t)b * ns + i] * (tt ? 1.0f : 0.0f) + (ss ? 1.0f : 0.0f) * pm[(size_t)b * nt + j];
+                const float e = __ldcg(pp + (size_t)b * ns + i) * (tt ? 1.0f : 0.0f) + (ss ? 1.0f : 0.0f) * __ldcg(pm + (size_t)b * nt + j);
                 upd = upd + C.reward * e;
             }
             if (C.reduction == SNN_REDUCE_MEAN) upd = upd / Bf;
@@ -369,19 +374,21 @@ __device__ void phase3_mstdp_dense(const DevNet &N, int ci_, int tile, int t) {
             if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
             C.w[(size_t)i * nt + j] = x;
         }
-    // P+, P- and the spikes of this step, for the next one
-    for (size_t k = (size_t)tile * SNN_GEN_THREADS + threadIdx.x; k < (size_t)B * ns; k += (size_t)ntiles * SNN_GEN_THREADS) {
-        const int b = (int)(k / ns), i = (int)(k - (size_t)b * ns);
-        const bool s = bit_of(S.bits + ((size_t)wr * B + b) * S.nw, i);
-        M.pp[out][k] = mst_trace(pp[k], C.p_plus_decay, C.a_plus, s);
-        M.sp[out][k] = s ? 1 : 0;
-    }
-    for (size_t k = (size_t)tile * SNN_GEN_THREADS + threadIdx.x; k < (size_t)B * nt; k += (size_t)ntiles * SNN_GEN_THREADS) {
-        const int b = (int)(k / nt), jj = (int)(k - (size_t)b * nt);
-        const bool s = bit_of(G.bits + ((size_t)wr * B + b) * G.nw, jj);
-        M.pm[out][k] = mst_trace(pm[k], C.p_minus_decay, C.a_minus, s);
-        M.st[out][k] = s ? 1 : 0;
-    }
+    // P+ and the pre-synaptic spikes of this step for my rows; tile 0 also does P- and the post side
+    if (i < ns)
+        for (int b = warp; b < B; b += SNN_GEN_WARPS) {
+            const size_t k = (size_t)b * ns + i;
+            const bool s = bit_of(S.bits + ((size_t)wr * B + b) * S.nw, i);
+            M.pp[out][k] = mst_trace(__ldcg(pp + k), C.p_plus_decay, C.a_plus, s);
+            M.sp[out][k] = s ? 1 : 0;
+        }
+    if (tile == 0)
+        for (size_t k = threadIdx.x; k < (size_t)B * nt; k += SNN_GEN_THREADS) {
+            const int b = (int)(k / nt), jj = (int)(k - (size_t)b * nt);
+            const bool s = bit_of(G.bits + ((size_t)wr * B + b) * G.nw, jj);
+            M.pm[out][k] = mst_trace(__ldcg(pm + k), C.p_minus_decay, C.a_minus, s);
+            M.st[out][k] = s ? 1 : 0;
+        }
 }
 
 // learning.MSTDP._conv2d_connection_update (learning.py:1942-2015) with a per-sample eligibility
@@ -403,7 +410,7 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int tile, int t) {
     // w += nu0 * sum_b reward * eligibility(t-1)  (:1973-1974), then decay / clamp (learning.py:87-104)
     for (size_t k = start; k < (size_t)NWT; k += stride) {
         float upd = 0.0f;
-        for (int b = 0; b < B; ++b) upd = upd + C.reward * el[(size_t)b * NWT + k];
+        for (int b = 0; b < B; ++b) upd = upd + C.reward * __ldcg(el + (size_t)b * NWT + k);
         float x = C.w[k] + C.nu0 * upd;
         if (C.weight_decay != 0.0f) x = x * C.weight_decay;
         if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
@@ -412,11 +419,11 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int tile, int t) {
     // P+ (trace image of the source), P- (:1999-2003)
     for (size_t k = start; k < (size_t)B * ns; k += stride) {
         const int b = (int)(k / ns), i = (int)(k - (size_t)b * ns);
-        M.pp[out][k] = mst_trace(pp[k], C.p_plus_decay, C.a_plus, bit_of(S.bits + ((size_t)wr * B + b) * S.nw, i));
+        M.pp[out][k] = mst_trace(__ldcg(pp + k), C.p_plus_decay, C.a_plus, bit_of(S.bits + ((size_t)wr * B + b) * S.nw, i));
     }
     for (size_t k = start; k < (size_t)B * nt; k += stride) {
         const int b = (int)(k / nt), jj = (int)(k - (size_t)b * nt);
-        M.pm[out][k] = mst_trace(pm[k], C.p_minus_decay, C.a_minus, bit_of(G.bits + ((size_t)wr * B + b) * G.nw, jj));
+        M.pm[out][k] = mst_trace(__ldcg(pm + k), C.p_minus_decay, C.a_minus, bit_of(G.bits + ((size_t)wr * B + b) * G.nw, jj));
     }
     // eligibility(t)[b,co,k] = sum_l s_post[b,co,l] * P+col[b,k,l]  +  sum_l P-[b,co,l] * s_pre_col[b,k,l]
     // (:2005-2009), l = (oy, ox) ascending, with the UPDATED traces (recomputed here from slot `in`)
@@ -433,8 +440,8 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int tile, int t) {
                 if (ix < 0 || ix >= C.win) continue;
                 const int src = (ci * C.hin + iy) * C.win + ix, tgt = co * L + oy * C.wout + ox;
                 const bool ss = bit_of(sb, src), ts = bit_of(gb, tgt);
-                if (ts) s1 = s1 + mst_trace(pp[(size_t)b * ns + src], C.p_plus_decay, C.a_plus, ss);
-                if (ss) s2 = s2 + mst_trace(pm[(size_t)b * nt + tgt], C.p_minus_decay, C.a_minus, ts);
+                if (ts) s1 = s1 + mst_trace(__ldcg(pp + (size_t)b * ns + src), C.p_plus_decay, C.a_plus, ss);
+                if (ss) s2 = s2 + mst_trace(__ldcg(pm + (size_t)b * nt + tgt), C.p_minus_decay, C.a_minus, ts);
             }
         }
         M.el[out][e] = s1 + s2;
