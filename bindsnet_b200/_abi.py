@@ -140,7 +140,7 @@ class SnnRunOpts(C.Structure):
         ("seed", C.c_uint32),
         ("step_offset", C.c_uint32),
         ("err_flag", C.c_void_p),
-        ("reserved", C.c_int32),
+        ("one_step", C.c_int32),
     ]
 
 

@@ -152,6 +152,7 @@ int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *
     N.n_layers = net->n_layers; N.n_conns = net->n_conns; N.learning = net->learning;
     N.T = opts->T; N.B = opts->B; N.normalize = opts->normalize;
     N.seed = opts->seed; N.step_offset = opts->step_offset; N.err = opts->err_flag;
+    N.one_step = opts->one_step ? 1 : 0;
     for (int c = 0; c < net->n_conns; ++c) {
         N.conns[c] = net->conns[c];
         const snn_conn_t &C = net->conns[c];

@@ -1213,7 +1213,7 @@ int device_sms() {
 }
 
 bool match(const snn_net_t *net, const snn_run_opts_t *o, Match &m) {
-    if (net->n_layers != 3 || net->n_conns != 3 || o->T < 1) return false;
+    if (net->n_layers != 3 || net->n_conns != 3 || o->T < 1 || o->one_step) return false;
     m.lX = m.lE = m.lI = -1;
     for (int l = 0; l < 3; ++l) {
         const snn_layer_t &L = net->layers[l];

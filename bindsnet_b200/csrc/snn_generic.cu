@@ -73,11 +73,25 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) snn_generic_window(const __gr
     if (!grid_barrier(N.bar, G, N.err)) return;
 
     for (int t = 0; t < N.T; ++t) {
+        if (N.one_step) {
+            // feed-forward mode (network.py:383-396): layer by layer in insertion order, each one reading the
+            // spikes its predecessors produced in THIS step — a grid barrier per layer
+            for (int l = 0; l < N.n_layers; ++l) {
+                const DevLayer &D = N.layers[l];
+                for (int tile = blockIdx.x; tile < D.nw; tile += G) phase1(N, l, tile, t, s_red, &s_flag);
+                if (D.L.kind == SNN_NODE_DC && D.L.one_spike) {
+                    if (!grid_barrier(N.bar, G, N.err)) return;
+                    for (int tile = blockIdx.x; tile < D.nw; tile += G) phase2(N, l, tile, t);
+                }
+                if (l + 1 < N.n_layers && !grid_barrier(N.bar, G, N.err)) return;
+            }
+        } else {
         for (int item = blockIdx.x; item < N.total_items; item += G) {
             int li, tile; item_of(N, item, li, tile);
             phase1(N, li, tile, t, s_red, &s_flag);
         }
-        if (N.any_one_spike) {
+        }
+        if (N.any_one_spike && !N.one_step) {
             if (!grid_barrier(N.bar, G, N.err)) return;
             for (int item = blockIdx.x; item < N.total_items; item += G) {
                 int li, tile; item_of(N, item, li, tile);

@@ -100,21 +100,27 @@ __device__ void phase1(const DevNet &N, int li, int tile, int t, float *s_red, i
         } else {
             // network.py:211-250: accumulate every incoming connection in insertion order
             float cur = 0.0f;
+            bool has_in = false;
             for (int c = 0; c < N.n_conns; ++c) {
                 const snn_conn_t &C = N.conns[c];
                 if (C.tgt != li) continue;
+                has_in = true;
                 const DevLayer &S = N.layers[C.src];
+                // one-step mode (network.py:393-396): sources earlier in the insertion order have already
+                // produced this step's spikes (slot wr); everything else is still at step t-1 (slot rd)
+                const int slot = (N.one_step && C.src < li) ? wr : rd;
                 float p;
                 if (C.kind == SNN_CONN_CONV2D) {
-                    p = gather_conv(C, S.bits + ((size_t)rd * B + b) * S.nw, j, valid);
+                    p = gather_conv(C, S.bits + ((size_t)slot * B + b) * S.nw, j, valid);
                 } else {
-                    p = gather(C, S.bits + ((size_t)rd * B + b) * S.nw, S.nw, S.L.n, n, j, valid, lane);
+                    p = gather(C, S.bits + ((size_t)slot * B + b) * S.nw, S.nw, S.L.n, n, j, valid, lane);
                     if (C.b && valid) p = p + C.b[j];
                 }
                 cur = cur + p;
             }
             if (valid) {
-                if (L.ext) { bool nb = false; cur = cur + ld_ext(L, ((size_t)t * B + b) * n + j, nb); }
+                // (one-step mode: the connection input REPLACES the external one, network.py:393-396)
+                if (L.ext && !(N.one_step && has_in)) { bool nb = false; cur = cur + ld_ext(L, ((size_t)t * B + b) * n + j, nb); }
                 float v = L.v[k], rc = L.refrac_count[k];
                 if (L.inject_v) v = v + L.inject_v[(L.inject_per_step ? (size_t)t * n : 0) + j];  // network.py:398-404
                 float xin = cur;

@@ -90,8 +90,6 @@ class Network(torch.nn.Module):
             "'inputs' must be a dict of names of layers (str) and relevant input tensors. "
             f"Got {type(inputs).__name__} instead."
         )
-        if one_step:
-            raise NotImplementedError("one_step=True (feed-forward mode, network.py:383-396) is not implemented")
         if kwargs.get("masks"):
             raise NotImplementedError("run(..., masks=...) is outside the implemented hot path")
         # reward-modulated rules (learning.MSTDP) read these from the run's kwargs (network.py:319-377,
@@ -118,7 +116,7 @@ class Network(torch.nn.Module):
         self._run_window(
             inputs, timesteps, normalize=bool(kwargs.get("b200_normalize", True)),
             clamp=kwargs.get("clamp", {}), unclamp=kwargs.get("unclamp", {}),
-            injects_v=kwargs.get("injects_v", {}), seed=kwargs.get("one_spike_seed", None),
+            injects_v=kwargs.get("injects_v", {}), seed=kwargs.get("one_spike_seed", None), one_step=bool(one_step),
         )
 
     def _device(self) -> torch.device:
@@ -171,7 +169,8 @@ class Network(torch.nn.Module):
         return None
 
     def _run_window(self, inputs, T: int, normalize: bool, clamp=None, unclamp=None, injects_v=None,
-                    seed: Optional[int] = None, step_offset: int = 0) -> None:
+                    seed: Optional[int] = None, step_offset: int = 0, one_step: bool = False) -> None:
+        self._one_step = bool(one_step)
         dev = self._device()
         B = self.batch_size
         if T <= 0:
@@ -209,6 +208,7 @@ class Network(torch.nn.Module):
         opts.T, opts.B, opts.normalize = T, B, int(normalize)
         opts.tier = int(getattr(self, "force_tier", 0))
         opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset
+        opts.one_step = int(self._one_step)
         self._launch(net, opts, dev)
         del keep
 
@@ -244,6 +244,7 @@ class Network(torch.nn.Module):
             opts.T, opts.B, opts.normalize = 1, B, int(normalize and t == T - 1)
             opts.tier = int(getattr(self, "force_tier", 0))
             opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset + t
+            opts.one_step = int(getattr(self, "_one_step", False))
             self._launch(net, opts, self._device())
             for m in self.monitors.values():
                 if isinstance(m, SpikeCounter) and t == 0:

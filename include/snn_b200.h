@@ -182,7 +182,8 @@ typedef struct snn_run_opts {
     uint32_t seed;         /* one_spike tie-break stream (see snn_one_spike_key)              */
     uint32_t step_offset;  /* added to t in the tie-break hash (lets callers split a window)  */
     int32_t *err_flag;     /* optional int32 (device memory for the CUDA lib); OR-ed with SNN_ERR_* */
-    int32_t reserved;
+    int32_t one_step;  /* Network.run(one_step=True), network.py:383-396: each layer's input is recomputed from
+                          the CURRENT spikes of its sources just before its forward (generic tier only) */
 } snn_run_opts_t;
 
 /*

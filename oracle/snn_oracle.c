@@ -181,7 +181,11 @@ static void layer_forward(const snn_net_t *net, int l, const snn_run_opts_t *o, 
         }
     } else {
         if (!ws->has_in) memset(cur, 0, sizeof(float) * BN); /* network.py:408-413 */
-        if (L->ext_dtype == SNN_EXT_U8) {
+        /* one_step mode (network.py:393-396): `current_inputs.update(self._get_inputs(layers=[l]))` REPLACES the
+         * entry that held the external input whenever the layer has an incoming connection */
+        const int drop_ext = o->one_step && ws->has_in;
+        if (drop_ext) {
+        } else if (L->ext_dtype == SNN_EXT_U8) {
             const uint8_t *e = (const uint8_t *)L->ext + (size_t)t * BN;
             for (size_t k = 0; k < BN; ++k) cur[k] = cur[k] + (float)e[k];
         } else if (L->ext_dtype == SNN_EXT_F32) {
@@ -555,7 +559,7 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
     for (int t = 0; t < T; ++t) {
         /* 1. _get_inputs (network.py:211-250): currents from the PREVIOUS step's spikes */
         for (int l = 0; l < net->n_layers; ++l) lws[l].has_in = 0;
-        for (int c = 0; c < net->n_conns; ++c) {
+        for (int c = 0; c < net->n_conns && !o->one_step; ++c) {
             const snn_conn_t *C = &net->conns[c];
             const snn_layer_t *G = &net->layers[C->tgt];
             if (!lws[C->tgt].has_in) { memset(lws[C->tgt].cur, 0, sizeof(float) * (size_t)B * G->n); lws[C->tgt].has_in = 1; }
@@ -563,7 +567,22 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
             else conn_compute(C, &net->layers[C->src], G->n, B, lws[C->tgt].cur, dense);
         }
         /* 2. layers in insertion order (network.py:386-429) */
-        for (int l = 0; l < net->n_layers; ++l) layer_forward(net, l, o, t, &lws[l], &err);
+        for (int l = 0; l < net->n_layers; ++l) {
+            if (o->one_step) {
+                /* one-step (feed-forward) mode, network.py:393-396: this layer's input is recomputed just
+                 * before its forward, from the CURRENT spikes of its sources — layers earlier in the
+                 * insertion order have already been updated this step */
+                for (int c = 0; c < net->n_conns; ++c) {
+                    const snn_conn_t *C = &net->conns[c];
+                    if (C->tgt != l) continue;
+                    const snn_layer_t *G = &net->layers[l];
+                    if (!lws[l].has_in) { memset(lws[l].cur, 0, sizeof(float) * (size_t)B * G->n); lws[l].has_in = 1; }
+                    if (C->kind == SNN_CONN_CONV2D) conv_compute(C, &net->layers[C->src], B, lws[l].cur, dense);
+                    else conn_compute(C, &net->layers[C->src], G->n, B, lws[l].cur, dense);
+                }
+            }
+            layer_forward(net, l, o, t, &lws[l], &err);
+        }
         /* 3. connection updates in insertion order (network.py:431-454) */
         if (net->learning)
             for (int c = 0; c < net->n_conns; ++c) {

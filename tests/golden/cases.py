@@ -258,6 +258,29 @@ def conv_mstdp_c4(ns, inputs=None):
     return net, inputs, {"reward": 1.0}, 40
 
 
+# Network.run(one_step=True) (network.py:383-396): feed-forward mode — every layer's input is recomputed from
+# the current spikes of its sources just before its forward.  Includes a backward connection (source later in
+# the insertion order: previous-step spikes) and an external current on a layer that also has incoming
+# connections (the reference's dict.update drops it in this mode).
+def one_step_ff(ns, inputs=None):
+    net = ns.Network(dt=1.0, batch_size=3)
+    X = ns.nodes.Input(n=40, traces=True)
+    H = ns.nodes.LIFNodes(n=24, traces=True, thresh=-60.0)
+    O = ns.nodes.LIFNodes(n=10, traces=True, thresh=-61.0, refrac=2)
+    net.add_layer(X, "X"); net.add_layer(H, "H"); net.add_layer(O, "O")
+    c1 = ns.topology.Connection(source=X, target=H, w=_w((40, 24), 151, 1.6), update_rule=ns.learning.PostPre,
+                                nu=(1e-3, 1e-2), reduction=torch.sum, wmin=0.0, wmax=2.0)
+    c2 = ns.topology.Connection(source=H, target=O, w=_w((24, 10), 152, 2.5), update_rule=ns.learning.PostPre,
+                                nu=(1e-3, 1e-2), reduction=torch.sum, wmin=0.0, wmax=3.0)
+    c3 = ns.topology.Connection(source=O, target=H, w=-_w((10, 24), 153, 1.5))
+    net.add_connection(c1, "X", "H"); net.add_connection(c2, "H", "O"); net.add_connection(c3, "O", "H")
+    T = 70
+    if inputs is None:
+        g = torch.Generator().manual_seed(155)
+        inputs = {"X": _bernoulli_inputs(T, 3, (40,), 0.2, 154), "H": 0.8 * torch.rand(T, 3, 24, generator=g)}
+    return net, inputs, {"one_step": True}, T
+
+
 CASES = {
     "c1_lif_postpre": c1_lif_postpre,
     "lif_postpre_batch": lif_postpre_batch,
@@ -273,6 +296,7 @@ CASES = {
     "conv_mstdp": conv_mstdp,
     "conv_stride_norm": conv_stride_norm,
     "conv_mstdp_c4": conv_mstdp_c4,
+    "one_step_ff": one_step_ff,
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)

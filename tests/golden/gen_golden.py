@@ -146,7 +146,10 @@ def generate(name: str) -> None:
     meta = {"case": name, "T": T, "seed": cases.ONE_SPIKE_SEED, "ref_wall_s": wall,
             "torch": torch.__version__, "threads": torch.get_num_threads(), "layers": {}, "conns": {}, "inputs": {}}
     for k, v in inputs.items():
-        out[f"in/{k}"] = pack(v)
+        if v.dtype.is_floating_point and not bool(((v == 0) | (v == 1)).all()):
+            out[f"inf/{k}"] = v.float().numpy()   # analog input current: stored as is
+        else:
+            out[f"in/{k}"] = pack(v)
         meta["inputs"][k] = list(v.shape)
     for lname, layer in net.layers.items():
         B = layer.s.shape[0]

@@ -25,6 +25,9 @@ class Fixture:
         out = {}
         for k, shape in self.meta["inputs"].items():
             n = int(np.prod(shape))
+            if f"inf/{k}" in self.z:  # analog input current
+                out[k] = torch.from_numpy(self.z[f"inf/{k}"].copy())
+                continue
             out[k] = torch.from_numpy(np.unpackbits(self.z[f"in/{k}"])[:n].reshape(shape).copy())
         return out
 

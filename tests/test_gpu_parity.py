@@ -23,7 +23,7 @@ def run_case_gpu(name, tier=1):
     net, inputs, kw, T = fx.build("cuda")
     net.force_tier = tier
     helpers.add_spike_monitors(net, T, device="cuda")
-    kw = {k: {l: v.cuda() for l, v in d.items()} for k, d in kw.items()}
+    kw = {k: ({l: v.cuda() for l, v in d.items()} if isinstance(d, dict) else d) for k, d in kw.items()}
     net.run(inputs={k: v.cuda() for k, v in inputs.items()}, time=T, one_spike_seed=cases.ONE_SPIKE_SEED, **kw)
     net.check_errors()
     return fx, helpers.snapshot(net), helpers.spike_counts(net, T)

@@ -64,7 +64,7 @@ def test_unsupported_reference_features_fail_loudly():
         Connection(X, Y, w_dtype=torch.float16)
     net = TwoLayerNetwork(n_inpt=8, n_neurons=4)
     with pytest.raises(NotImplementedError):
-        net.run({"X": torch.zeros(3, 1, 8)}, time=3, one_step=True)
+        net.run({"X": torch.zeros(3, 1, 8)}, time=3, masks={("X", "Y"): torch.ones(8, 4, dtype=torch.bool)})
     with pytest.raises(AssertionError):
         net.run([torch.zeros(3, 1, 8)], time=3)
 
