@@ -213,3 +213,48 @@ def test_async_readback_ring_order_and_overflow():
     rb.push(torch.zeros(2)); rb.push(torch.zeros(2))
     with pytest.raises(RuntimeError):
         rb.push(torch.zeros(2))
+
+
+def test_conv2d_connection_constructor_and_window_like_reference_tests():
+    """test/network/test_connections.py (Conv2dConnection cases): constructor geometry checks, default
+    weights inside [wmin, wmax], zero bias, and a short run through the window path."""
+    from bindsnet_b200.network.nodes import Input as In
+
+    X = In(shape=[2, 9, 9], traces=True)
+    H = LIFNodes(shape=[3, 5, 5], traces=True)
+    c = Conv2dConnection(X, H, kernel_size=3, stride=2, padding=1, wmin=-0.5, wmax=0.5)
+    assert tuple(c.w.shape) == (3, 2, 3, 3) and tuple(c.b.shape) == (3,) and not c.b.any()
+    assert float(c.w.min()) >= -0.5 and float(c.w.max()) <= 0.5
+    with pytest.raises(AssertionError):
+        Conv2dConnection(X, LIFNodes(shape=[3, 4, 4]), kernel_size=3, stride=2, padding=1)   # wrong target size
+    with pytest.raises(NotImplementedError):
+        c.compute(torch.zeros(1, 2, 9, 9))                                                    # window-only
+    net = Network(dt=1.0, batch_size=2)
+    net.add_layer(X, "X"); net.add_layer(H, "H")
+    net.add_connection(c, "X", "H")
+    net.add_monitor(Monitor(H, ["s", "v"], time=12), "H")
+    g = torch.Generator().manual_seed(5)
+    with OracleBackend():
+        net.run({"X": torch.bernoulli(0.3 * torch.ones(12, 2, 2, 9, 9), generator=g).byte()}, time=12)
+    assert net.monitors["H"].get("s").shape == (12, 2, 3, 5, 5) and net.monitors["H"].get("v").shape == (12, 2, 3, 5, 5)
+
+
+def test_mstdp_rule_state_and_eligibility_view():
+    """learning.MSTDP keeps p_plus / p_minus like the reference and rebuilds the dense eligibility on request
+    (learning.py:1519-1535, 1568-1572)."""
+    X, Y = Input(n=6, traces=True), LIFNodes(n=4, traces=True, thresh=-64.0)
+    net = Network(dt=1.0, batch_size=2)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    c = Connection(X, Y, update_rule=MSTDP, nu=1e-1, reduction=torch.sum, wmin=-1.0, wmax=1.0, w=0.5 * torch.ones(6, 4))
+    net.add_connection(c, "X", "Y")
+    x = torch.ones(8, 2, 6, dtype=torch.uint8)
+    with OracleBackend():
+        net.run({"X": x}, time=8, reward=1.0)
+    r = c.update_rule
+    assert r.p_plus.shape == (2, 6) and r.p_minus.shape == (2, 4) and r.eligibility.shape == (2, 6, 4)
+    # constant input: P+ = sum_k decay^k after 8 steps of a_plus = 1 (fp32, same order as the rule)
+    p = torch.tensor(0.0)
+    for _ in range(8):
+        p = p * torch.exp(torch.tensor(-1.0) / r.tc_plus) + 1.0
+    assert torch.allclose(r.p_plus, p.expand(2, 6))
+    assert not torch.equal(c.w, 0.5 * torch.ones(6, 4))   # reward-modulated update happened
