@@ -281,6 +281,48 @@ def one_step_ff(ns, inputs=None):
     return net, inputs, {"one_step": True}, T
 
 
+# MSTDP with mean reduction, weight decay and a negative reward
+def mstdp_mean_decay(ns, inputs=None):
+    net = ns.Network(dt=1.0, batch_size=4)
+    X = ns.nodes.Input(n=30, traces=True)
+    Y = ns.nodes.LIFNodes(n=12, traces=True, thresh=-62.5, refrac=1)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    C = ns.topology.Connection(source=X, target=Y, w=_w((30, 12), 161, 1.5), update_rule=ns.learning.MSTDP,
+                               nu=3e-2, reduction=torch.mean, weight_decay=2e-3, wmin=-0.5, wmax=1.6)
+    net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(50, 4, (30,), 0.2, 162)}
+    return net, inputs, {"reward": -0.5}, 50
+
+
+# strided convolution with a non-zero bias, no learning rule (dilation > 1 cannot be constructed: the reference's
+# shape assertion, topology.py:752-772, ignores it)
+def conv_bias_stride(ns, inputs=None):
+    net = ns.Network(dt=1.0, batch_size=2)
+    X = ns.nodes.Input(shape=[1, 11, 11], traces=True)
+    H = ns.nodes.LIFNodes(shape=[2, 5, 5], traces=True, thresh=-63.0)
+    net.add_layer(X, "X"); net.add_layer(H, "H")
+    conv = ns.topology.Conv2dConnection(source=X, target=H, kernel_size=3, stride=2, padding=0,
+                                        w=_w((2, 1, 3, 3), 171, 1.2) - 0.2, b=torch.tensor([0.25, -0.1]), wmin=-1.0, wmax=1.0)
+    net.add_connection(conv, "X", "H")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(30, 2, (1, 11, 11), 0.15, 172)}
+    return net, inputs, {}, 30
+
+
+# edge sizes: one sample, one timestep; and a window without a single input spike
+def dc2015_b1_t1(ns, inputs=None):
+    net, inputs, kw, _ = _dc2015(ns, 36, 1, 1, 181, 182, True, inputs)
+    return net, inputs, kw, 1
+
+
+def dc2015_silent(ns, inputs=None):
+    if inputs is None:
+        inputs = {"X": torch.zeros(12, 3, 1, 28, 28, dtype=torch.uint8)}
+    net, inputs, kw, _ = _dc2015(ns, 40, 3, 12, 191, 192, True, inputs)
+    return net, inputs, kw, 12
+
+
 CASES = {
     "c1_lif_postpre": c1_lif_postpre,
     "lif_postpre_batch": lif_postpre_batch,
@@ -297,6 +339,10 @@ CASES = {
     "conv_stride_norm": conv_stride_norm,
     "conv_mstdp_c4": conv_mstdp_c4,
     "one_step_ff": one_step_ff,
+    "mstdp_mean_decay": mstdp_mean_decay,
+    "conv_bias_stride": conv_bias_stride,
+    "dc2015_b1_t1": dc2015_b1_t1,
+    "dc2015_silent": dc2015_silent,
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)
