@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tier", type=int, default=0, help="0 auto, 1 generic kernel, 2 fused DC2015 kernel")
+    ap.add_argument("--tier", type=int, default=0, help="0 auto, 1 generic kernel, 2 fused DC2015 kernel v1 (grid barrier), 3 fused DC2015 kernel v2 (message exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -363,7 +363,7 @@ def main():
             except Exception:
                 traffic = None
         from bindsnet_b200 import _abi
-        tier = {0: "auto", 1: "generic", 2: "fused_dc2015"}[args.tier]
+        tier = {0: "auto", 1: "generic", 2: "fused_dc2015_v1", 3: "fused_dc2015_v2"}[args.tier]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -131,7 +131,7 @@ def _check(rc: int, what: str) -> None:
 kernel_events: Optional[list] = None
 #: number of window kernels launched through this module since import
 launches_total = 0
-#: kernel tier of the last window (1 generic, 2 fused DiehlAndCook2015)
+#: kernel tier of the last window (1 generic, 2 fused DiehlAndCook2015 v1, 3 fused DiehlAndCook2015 v2)
 last_tier = 0
 
 

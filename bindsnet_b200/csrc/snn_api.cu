@@ -10,6 +10,10 @@ int snn_fused_dc_supported(const snn_net_t *net, const snn_run_opts_t *opts);
 size_t snn_fused_dc_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts);
 int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *ws, size_t ws_bytes,
                         cudaStream_t stream, int *launches);
+int snn_fused_dc2_supported(const snn_net_t *net, const snn_run_opts_t *opts);
+size_t snn_fused_dc2_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts);
+int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *ws, size_t ws_bytes,
+                         cudaStream_t stream, int *launches);
 
 static thread_local int g_last_launches = 0;
 
@@ -112,7 +116,7 @@ extern "C" {
 int snn_b200_abi_version(void) { return SNN_ABI_VERSION; }
 
 const char *snn_b200_build_info(void) {
-    return "libsnn_b200 sm_100a (generic window + fused DC2015 window), ABI " "6" ", built " __DATE__ " " __TIME__;
+    return "libsnn_b200 sm_100a (generic window + fused DC2015 windows v1/v2), ABI " "6" ", built " __DATE__ " " __TIME__;
 }
 
 int snn_b200_last_launch_count(void) { return g_last_launches; }
@@ -120,6 +124,8 @@ int snn_b200_last_launch_count(void) { return g_last_launches; }
 int snn_b200_select_tier(const snn_net_t *net, const snn_run_opts_t *opts) {
     if (validate(net, opts) != SNN_OK) return 0;
     if (opts->tier == 1) return 1;
+    if (opts->tier != 2 && snn_fused_dc2_supported(net, opts)) return 3;
+    if (opts->tier == 3) return 0;
     if (snn_fused_dc_supported(net, opts)) return 2;
     return opts->tier == 2 ? 0 : 1;
 }
@@ -128,6 +134,8 @@ size_t snn_b200_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts
     if (validate(net, opts) != SNN_OK) return 0;
     size_t g = layout_generic(net, opts, nullptr, nullptr);
     size_t f = snn_fused_dc_supported(net, opts) ? snn_fused_dc_workspace_bytes(net, opts) : 0;
+    size_t f2 = snn_fused_dc2_supported(net, opts) ? snn_fused_dc2_workspace_bytes(net, opts) : 0;
+    if (f2 > f) f = f2;
     return g > f ? g : f;
 }
 
@@ -141,6 +149,10 @@ int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *
     const int tier = snn_b200_select_tier(net, opts);
     if (tier == 0) return SNN_ERR_UNSUPPORTED;
     if (!workspace) return SNN_ERR_WORKSPACE;
+    if (tier == 3) {
+        if (workspace_bytes < snn_fused_dc2_workspace_bytes(net, opts)) return SNN_ERR_WORKSPACE;
+        return snn_fused_dc2_launch(net, opts, workspace, workspace_bytes, stream, &g_last_launches);
+    }
     if (tier == 2) {
         if (workspace_bytes < snn_fused_dc_workspace_bytes(net, opts)) return SNN_ERR_WORKSPACE;
         return snn_fused_dc_launch(net, opts, workspace, workspace_bytes, stream, &g_last_launches);

@@ -1,0 +1,1340 @@
+// snn_fused_dc2.cu — fused persistent window kernel for the DiehlAndCook2015 graph, second generation
+//     X (Input) --W, learned--> Ae (DiehlAndCookNodes) --exc*I--> Ai (LIFNodes) --(-inh)(1-I)--> Ae
+// (reference wiring: bindsnet/models/models.py:94-244; per-step semantics: SURVEY.md App. A).
+//
+// Same partition as snn_fused_dc.cu — a CTA owns TJ columns (neurons of Ae and their partners in Ai)
+// for all B samples, W[:, tile] lives in shared memory for the whole window, Ae state in registers —
+// but the per-step grid dependency is served differently, because the round-1 profile showed the
+// step to be bound by synchronisation latency, not by work:
+//
+//   * NO grid barrier, NO atomics in global memory.  What the grid has to exchange per step — per
+//     sample the one_spike arg-max key (nodes.py:1097-1105) and the number of Ai spikes (lateral
+//     inhibition, models.py:217-220) — travels as self-validating 64-bit MESSAGES: every CTA stores
+//     a header {step tag | number of entries} and its entries {step tag | sample | payload} into
+//     its own slot (relaxed 64-bit stores, single-copy atomic), warp 0 of every CTA polls all G
+//     headers and folds the (few) entries into shared-memory tables.  One L2 store + one L2 load
+//     on the critical path; no release/acquire fences because a word is only believed when it
+//     carries the step's tag, and no other global data is shared between CTAs.
+//   * The input traces the STDP post term needs (x_pre of the winner's sample, learning.py:407-417 /
+//     MCC_learning.py:267-299) are a pure function of the input spikes, so a pre-pass scans them for
+//     the whole window ([T,B,P] fp32); the window kernel only bulk-copies (cp.async.bulk + mbarrier)
+//     the rows of its own candidate samples, issued the moment a candidate appears, one exchange
+//     ahead of their use.
+//   * Ai (LIFNodes, nodes.py:500-529) is event driven: a neuron at rest without input stays bitwise
+//     at rest (decay * (rest - rest) + rest == rest), only its refractory counter runs, and that is
+//     replayed in closed form at the end.  Neurons that ever received a spike live in a compact list.
+//   * Spike rasters and spike counts are written sparsely (the launch code clears the rasters).
+//   * Thread layout is column-group major (warp = 32 samples of ONE float4 column group), so TJ need
+//     not be a power of two: n = 1600 runs as 134 CTAs x 12 columns instead of 100 x 16.
+//
+// Loop iteration t = [exchange of step t-1] [winners, traces, late STDP of t-1] [step t: gather,
+// Ae update, Ai list, candidates -> messages] [early STDP of t in the shadow of the exchange].
+//
+// Arithmetic and summation orders are those of snn_phases.cuh / oracle/snn_oracle.c (one fp32
+// rounding per reference op, ascending index sums), so results are bit-identical to the generic
+// kernel, to snn_fused_dc.cu and to the oracle.  Options outside the lean set (weight-dependent
+// rule, mean reduction, additive traces, voltage bounds / monitors, weight decay, B > 128) stay
+// with snn_fused_dc.cu.
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "snn_common.cuh"
+
+namespace {
+
+constexpr int XR = 8;        // input-trace rows staged per CTA and step (samples with a candidate)
+constexpr int EV_CAP = 32;   // staged events per sample and step; longer lists take the slow path
+constexpr int NPROF = 16;
+constexpr int NHMAX = 5;     // headers polled per lane of warp 0: grids up to 160 CTAs
+constexpr int BIGX = 96;     // more entries than this in one step: the whole CTA reads them
+constexpr unsigned AI_NONE = 0xFFFFu;
+
+struct F2Params {
+    snn_layer_t X, E, I;      // Input, DiehlAndCookNodes (Ae), LIFNodes (Ai)
+    snn_conn_t C;             // X -> Ae
+    float exc, inh_neg;       // diag value of Ae->Ai, off-diag value of Ai->Ae
+    int32_t T, B, Bp, P, n, learning, normalize;
+    int32_t SW;               // words per sample row of inS
+    int32_t SB;               // bytes of one event-list block
+    int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
+    int32_t G;                // CTAs of the window kernel
+    int32_t nrep;             // entries of the inhibition table rep[0..nrep]
+    int32_t ecap;             // message entries per CTA and step
+    uint32_t o_W, o_tx, o_ev, o_inT, o_xrow, o_rep, o_theta, o_live, o_tab, o_ai, o_misc;  // smem byte offsets
+    uint32_t seed, step_offset;
+    uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
+    uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
+    unsigned char *evS;       // [T+1][SB]     same spikes as lists: u16 count[B] (padded), then u16 idx[B][EV_CAP]
+    int *dense;               // [T+1] slot holds a sample whose event list overflowed EV_CAP
+    float *xtr;               // [T][B][P] input traces of every step (pre-pass scan), or NULL
+    float *rep;               // [nrep+1] m-fold sequential sums of the Ai->Ae weight
+    unsigned int *sisum0;     // [B] Ai spikes of step -1
+    unsigned long long *hdr;  // [2][G] message headers, by step parity
+    unsigned long long *ent;  // [2][G][ecap] message entries
+    int32_t *err;
+    long long *prof;          // profiling only (env SNN_B200_PROF): [G][NPROF] phase cycles of thread 0
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {  // no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- messages -------------------------------------------------------------------------------
+// header: tag[63:48] | number of entries[31:0]
+// entry : tag[63:48] | kind[47] | sample[46:39] | payload
+//   kind 1 (candidate): hash31[38:8] | column within the sender's tile[7:0]   (nodes.py:1097-1105)
+//   kind 0 (Ai spikes): count[7:0]                                             (models.py:217-220)
+// Steps t and t+2 share a slot; tags differ for any two steps less than 131070 apart.
+__device__ __forceinline__ uint32_t msg_tag(int t) { return (uint32_t)((t >> 1) % 65535) + 1u; }
+__device__ __forceinline__ unsigned long long msg_cand(uint32_t tag, int b, uint32_t hash, int col) {
+    return ((unsigned long long)tag << 48) | (1ull << 47) | ((unsigned long long)b << 39) |
+           ((unsigned long long)(hash & 0x7fffffffu) << 8) | (unsigned long long)col;
+}
+__device__ __forceinline__ unsigned long long msg_ai(uint32_t tag, int b, int count) {
+    return ((unsigned long long)tag << 48) | ((unsigned long long)b << 39) | (unsigned long long)count;
+}
+
+struct Misc2 {  // small per-step scratch (shared memory)
+    uint64_t mbar_in[2];    // staged spike lists / pixel masks, by buffer
+    uint64_t mbar_x;        // staged input-trace rows of the step's candidate samples
+    uint64_t pad_;
+    uint32_t wl[XR];        // winners of the step being finalised: column << 16 | sample << 8 | staged row slot (0xff: none)
+    uint32_t nz4[8][8];     // per column group: samples with a non-zero Ae trace in that group
+    uint32_t wmask[32][8];  // winners of the step being finalised: per column, bit mask over samples
+    int cnt[2][32];         // candidates per column (theta update), by step parity
+    int candb[2][XR];       // samples whose input-trace row is staged in xrow, by step parity
+    int ncand[2];           // samples with a candidate in this tile (by step parity)
+    uint32_t candgrp[2];    // column groups holding a candidate (by step parity)
+    uint32_t colwin;        // bit j: column j has a winner in the step being finalised
+    int nwl;                // number of winners of the step being finalised
+    int nlive;              // live (sample, column group) pairs, listed in live[]
+    int nact;               // entries of the Ai list
+    int nent;               // message entries written this step
+    int bigx;               // entries of a large exchange (read by the whole CTA), else 0
+    int abort;              // exchange time-out: leave the time loop
+    int denseflag[2];       // staged slot (by buffer) holds a sample whose event list overflowed EV_CAP
+    uint16_t hcnt[32 * NHMAX];  // large exchange: entries per sender
+    long long pc[NPROF];    // phase timers of thread 0 (profiling variant only)
+};
+static_assert(offsetof(Misc2, wl) % 16 == 0 && offsetof(Misc2, nz4) % 16 == 0 && offsetof(Misc2, wmask) % 16 == 0, "Misc2: 16-byte rows");
+
+struct SmemLayout2 { size_t W, tx, ev, inT, xrow, rep, theta, live, tab, ai, misc, total; };
+
+__host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline int ev_count_bytes(int B) { return (int)al16(2 * (size_t)(B + 8)); }  // u16 count[B], then [B] = dense flag
+__host__ __device__ inline int ev_block_bytes(int B) { return ev_count_bytes(B) + 2 * B * EV_CAP; }
+__host__ __device__ inline int tile_stride(int TJ) { return ((TJ / 4) & 1) ? TJ : TJ + 4; }  // odd number of 16-byte chunks per row
+// tab region: keyT u64 [2][Bp] | isumT u32 [2][Bp] | aispk u32 [2][Bp] | candstamp u32 [Bp] | candslot i32 [Bp]
+__host__ __device__ inline size_t tab_bytes(int Bp) { return (size_t)Bp * (16 + 8 + 8 + 4 + 4); }
+// ai region: v f32 [cap] | rc f32 [cap] | id u16 [cap] | in u16 [cap] | idxmap u16 [cap] | fl u8 [cap]
+__host__ __device__ inline size_t ai_bytes(int cap) { return al16((size_t)cap * (4 + 4 + 2 + 2 + 2 + 1)); }
+__host__ __device__ inline SmemLayout2 smem_layout2(int P, int TJ, int B, int Bp, int BW, int nrep) {
+    SmemLayout2 L;
+    size_t o = 0;
+    L.W = o; o += al16(sizeof(float) * (size_t)(P + 1) * tile_stride(TJ));  // + one zero row (list padding)
+    L.tx = o; o += al16(sizeof(float) * (size_t)Bp * TJ);
+    L.ev = o; o += 2 * al16((size_t)ev_block_bytes(B));
+    L.inT = o; o += al16(sizeof(uint32_t) * 2 * (size_t)P * BW);
+    L.xrow = o; o += al16(sizeof(float) * (size_t)XR * P);
+    L.rep = o; o += al16(sizeof(float) * (size_t)(nrep + 1));
+    L.theta = o; o += al16(sizeof(float) * 64);
+    L.live = o; o += al16(sizeof(uint16_t) * (size_t)Bp * (TJ / 4));
+    L.tab = o; o += al16(tab_bytes(Bp));
+    L.ai = o; o += ai_bytes(Bp * TJ);
+    L.misc = o; o += al16(sizeof(Misc2));
+    L.total = o;
+    return L;
+}
+
+// Constants and pointers of the STDP passes, kept in shared memory so that the passes live out of line
+// (the per-step code has to stay inside the instruction cache).
+struct PassCtx2 {
+    float *W, *tx;
+    const float *xrow;
+    const uint32_t *inT;
+    const unsigned char *evb;
+    const uint16_t *live;
+    Misc2 *M;
+    int P, B, evblk, cntb, WS;
+    int pre_on, has_clamp;
+    float dts, wmin, wmax, nu1;
+};
+
+// STDP of one step in list form on the column groups selected by `groups` (MCC_learning.py:234-299,
+// learning.py:390-420): the work items are (live (sample, group) pair, event of that sample).  Several
+// samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel owns the
+// row (no atomics), sums the traces of all of them in ascending sample order (the oracle's order) and
+// rewrites the group's 4 weights:  w - U*dt [+ x_pre*nu1*dt for a winner column], clamp.
+// `colwin` != 0 (late pass): columns with a winner get their post term here; rows this pass does not
+// touch get it from post_rows().  Threads tid0 < 0 do not take part.
+constexpr int EVH = 16;  // list slots enumerated per pair and round
+template <int CG, int BW>
+__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, uint32_t groups, uint32_t colwin, int tid0, int nthr0) {
+    const PassCtx2 c_ = *cx;
+    const int P = c_.P, WS = c_.WS;
+    const Misc2 &M = *c_.M;
+    const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
+    const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
+    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    const int total = M.nlive * EVH;
+    if (tid0 < 0) return;
+    #pragma unroll 1
+    for (int idx = tid0; idx < total; idx += nthr0) {
+        const int lp = c_.live[idx / EVH];
+        const int bb = lp / CG, c4 = lp % CG;
+        if (!((groups >> c4) & 1u)) continue;
+        const int cnt = min((int)ec[bb], EV_CAP);
+        #pragma unroll 1
+        for (int k = idx % EVH; k < cnt; k += EVH) {
+            const int i = el[bb * EV_CAP + k];
+            uint32_t a[BW];
+            {
+                const uint4 q0 = cT[i * (BW / 4)];
+                const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+                a[0] = q0.x & z0.x; a[1] = q0.y & z0.y; a[2] = q0.z & z0.z; a[3] = q0.w & z0.w;
+                if (BW == 8) {
+                    const uint4 q1 = cT[i * (BW / 4) + 1];
+                    const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
+                    a[BW - 4] = q1.x & z1.x; a[BW - 3] = q1.y & z1.y; a[BW - 2] = q1.z & z1.z; a[BW - 1] = q1.w & z1.w;
+                }
+            }
+            // owner of row i in this group = the lowest live sample spiking at pixel i
+            uint32_t lower = 0;
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) {
+                const uint32_t below = g < (bb >> 5) ? 0xffffffffu : (g == (bb >> 5) ? ((1u << (bb & 31)) - 1u) : 0u);
+                lower |= a[g] & below;
+            }
+            if (lower) continue;
+            float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = a[g];
+                while (mm) {
+                    const int b2 = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 t4 = *(const float4 *)(c_.tx + b2 * (4 * CG) + 4 * c4);
+                    U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
+                }
+            }
+            float *wp = c_.W + i * WS + 4 * c4;
+            const float4 w4 = *(const float4 *)wp;
+            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float Uv[4] = {U0, U1, U2, U3};
+            const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float w = wv[c];
+                w = w - Uv[c] * c_.dts;  // x * 1.0f is exact: the classic rule's missing dt factor is dts = 1
+                if ((gwin >> c) & 1u) {  // the column's single winner (fast late pass): post term
+                    uint32_t e = M.wl[0];
+                    #pragma unroll 1
+                    for (int k2 = 1; k2 < M.nwl; ++k2) if ((M.wl[k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[k2];
+                    const float V = 0.0f + c_.xrow[(e & 0xffu) * P + i] * c_.nu1;
+                    w = w + V * c_.dts;
+                }
+                if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+                wv[c] = w;
+            }
+            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    }
+}
+
+// Post term of the fast late pass for the rows stdp_list2 did not touch: per winner (column, staged
+// row): w + x_pre[b,i]*nu1*dt, clamp (MCC_learning.py:267-299, 86-110).  A row of the winner's column
+// group was handled by the list pass iff a live sample of that group spiked at its pixel.
+template <int CG, int BW>
+__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int nwl) {
+    const PassCtx2 c_ = *cx;
+    const int P = c_.P, WS = c_.WS;
+    const Misc2 &M = *c_.M;
+    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    #pragma unroll 1
+    for (int k = 0; k < nwl; ++k) {
+        const uint32_t e = M.wl[k];
+        const int col = (int)(e >> 16), c4 = col >> 2;
+        const float *xr = c_.xrow + (e & 0xffu) * P;
+        uint32_t z[BW];
+        {
+            const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w;
+            if (BW == 8) { const uint4 z1 = *(const uint4 *)&M.nz4[c4][4]; z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
+        }
+        #pragma unroll 1
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            if (c_.pre_on) {
+                const uint4 q0 = cT[i * (BW / 4)];
+                uint32_t any = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
+                if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
+                if (any) continue;  // done by the list pass
+            }
+            float *wp = c_.W + i * WS + col;
+            float w = *wp;
+            const float V = 0.0f + xr[i] * c_.nu1;
+            w = w + V * c_.dts;
+            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+            *wp = w;
+        }
+    }
+}
+
+// STDP of one step in row form, general: one row loop per selected column group, pre and post term of a
+// column applied together (pre, post, clamp — the reference's order).  Used for slots with an overflowed
+// event list, more than XR winners, two winners in one column, a winner whose trace row is not staged.
+// `cand` = staged samples (rows of xrow), `xsrc` = the step's input traces in global memory.
+template <int CG, int BW>
+__device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, uint32_t groups, uint32_t colwin, const int *cand, int ns,
+                                        const float *xsrc) {
+    const PassCtx2 c_ = *cx;
+    const int P = c_.P, WS = c_.WS, TJ = 4 * CG;
+    const Misc2 &M = *c_.M;
+    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    #pragma unroll 1
+    for (uint32_t lg = groups; lg; lg &= lg - 1) {
+        const int c4 = __ffs(lg) - 1;
+        const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
+        const uint4 z0 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
+        #pragma unroll 1
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            uint32_t m[BW];
+            const uint4 q0 = cT[i * (BW / 4)];
+            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+            uint32_t anym = m[0] | m[1] | m[2] | m[3];
+            if (BW == 8) {
+                const uint4 q1 = cT[i * (BW / 4) + 1];
+                const uint4 z1 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
+                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+                anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+            }
+            const bool pre_t = anym != 0u;
+            if (!(pre_t || gwin)) continue;
+            float U[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pre_t) {
+                #pragma unroll 1
+                for (int g = 0; g < BW; ++g) {
+                    uint32_t mm = m[g];
+                    while (mm) {
+                        const int bb = g * 32 + __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const float4 t4 = *(const float4 *)(c_.tx + bb * TJ + 4 * c4);
+                        U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                    }
+                }
+            }
+            float *wp = c_.W + i * WS + 4 * c4;
+            const float4 w4 = *(const float4 *)wp;
+            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            #pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const bool post_t = (gwin >> c) & 1u;
+                float w = wv[c];
+                if (pre_t) w = w - U[c] * c_.dts;
+                if (post_t) {
+                    float V = 0.0f;
+                    #pragma unroll 1
+                    for (int g = 0; g < BW; ++g) {  // winners of this column, ascending sample order
+                        uint32_t mm = M.wmask[4 * c4 + c][g];
+                        while (mm) {
+                            const int bb = g * 32 + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            int sl = -1;
+                            for (int q = 0; q < ns; ++q) if (cand[q] == bb) sl = q;
+                            const float xv = sl >= 0 ? c_.xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i);
+                            V = V + xv * c_.nu1;
+                        }
+                    }
+                    w = w + V * c_.dts;
+                }
+                if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+                wv[c] = w;
+            }
+            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    }
+}
+
+// Spike-gather of a sample whose event list overflowed EV_CAP: walk its bit row in global memory
+// (rare; out of line to keep the hot loop small).
+__device__ __noinline__ float4 gather_dense2(const uint32_t *row, int SW, const float *Wc, int WS) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    for (int w = 0; w < SW; ++w) {
+        uint32_t word = __ldg(row + w);
+        while (word) {
+            const int i = w * 32 + __ffs(word) - 1;
+            word &= word - 1;
+            const float4 r4 = *(const float4 *)(Wc + i * WS);
+            p0 = p0 + r4.x; p1 = p1 + r4.y; p2 = p2 + r4.z; p3 = p3 + r4.w;
+        }
+    }
+    return make_float4(p0, p1, p2, p3);
+}
+
+// T-fold sequential  rc = rc - dt  (what the refractory counter of an undisturbed neuron does over the
+// window, nodes.py:514); closed form when every intermediate value is an exactly representable integer.
+__device__ __forceinline__ float refrac_replay(float rc, float dt, int T) {
+    if (dt == 1.0f && rc == truncf(rc) && fabsf(rc) < 4194304.0f && T < 4194304) return rc - (float)T;
+    #pragma unroll 1
+    for (int k = 0; k < T; ++k) rc = rc - dt;
+    return rc;
+}
+
+// CG: float4 column groups per CTA (TJ = 4 CG columns); BW: 32-bit words of a per-pixel sample mask
+// (4 -> B <= 128).  Threads = Bp * CG, Bp = B rounded up to a multiple of 32: thread (cg, b).
+// VAR bit 1: phase timers compiled in.
+template <int CG, int BW, int VAR>
+__global__ void __launch_bounds__((32 * BW * CG < 1024 ? 32 * BW * CG : 1024), 1)
+snn_dc2_window(const __grid_constant__ F2Params Q) {
+    constexpr bool PROFV = (VAR & 2) != 0;
+    constexpr int TJ = 4 * CG;
+    constexpr int WS = (CG & 1) ? TJ : TJ + 4;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int B = Q.B, Bp = Q.Bp, P = Q.P, n = Q.n, T = Q.T;
+    const int G = (int)gridDim.x;
+    float *W = (float *)(smem + Q.o_W);
+    float *tx = (float *)(smem + Q.o_tx);
+    unsigned char *evb = smem + Q.o_ev;
+    uint32_t *inT = (uint32_t *)(smem + Q.o_inT);
+    float *xrow = (float *)(smem + Q.o_xrow);
+    float *rep = (float *)(smem + Q.o_rep);
+    float *theta_s = (float *)(smem + Q.o_theta);   // [32] theta, [32] thresh + decayed theta
+    float *thr_s = theta_s + 32;
+    uint16_t *live = (uint16_t *)(smem + Q.o_live);
+    unsigned long long *keyT = (unsigned long long *)(smem + Q.o_tab);  // [2][Bp]
+    uint32_t *isumT = (uint32_t *)(keyT + 2 * Bp);                      // [2][Bp]
+    uint32_t *aispk = isumT + 2 * Bp;                                   // [2][Bp] bit col: Ai (b, col) spiked in that step
+    uint32_t *candstamp = aispk + 2 * Bp;                               // [Bp] step + 1 of the sample's last staged row
+    int *candslot = (int *)(candstamp + Bp);                            // [Bp] its slot in xrow (-1: not staged)
+    const int aicap = Bp * TJ;
+    float *ai_v = (float *)(smem + Q.o_ai);
+    float *ai_rc = ai_v + aicap;
+    uint16_t *ai_id = (uint16_t *)(ai_rc + aicap);      // b * TJ + col
+    uint16_t *ai_in = ai_id + aicap;                     // step at which the partner Ae neuron's spike arrives
+    uint16_t *ai_map = ai_in + aicap;                    // (b * TJ + col) -> list entry, AI_NONE
+    uint8_t *ai_fl = (uint8_t *)(ai_map + aicap);        // bit 0: refractory counter still the undisturbed one; bit 1: spiked last step
+    Misc2 &M = *(Misc2 *)(smem + Q.o_misc);
+    __shared__ PassCtx2 s_cx;
+
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int cg = tid / Bp, b = tid - cg * Bp;   // state ownership: sample b, neurons jc..jc+3 (warp-uniform cg)
+    const int j0 = blockIdx.x * TJ;
+    const int jc = j0 + 4 * cg;
+    const bool act = b < B && jc < n;
+    const snn_layer_t &E = Q.E, &I = Q.I, &X = Q.X;
+    const snn_conn_t &C = Q.C;
+    const bool stdp = C.rule >= SNN_RULE_POSTPRE;
+    const bool pre_on = stdp && C.nu0 != 0.0f, post_on = stdp && C.nu1 != 0.0f;
+    const bool update_on = Q.learning && stdp;
+    const bool stage_on = update_on && post_on && Q.xtr != nullptr;
+    const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
+    const int evblk = (int)al16((size_t)Q.SB);
+    const int cntb = ev_count_bytes(B);
+    float *Wc = W + 4 * cg;
+    long long *pc = M.pc;
+    long long pt = clock64();
+    #define PROF(k) { if (PROFV && tid == 0) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
+
+    // ---- prologue: W tile, theta, inhibition table, tables, Ai list, state registers -----------
+    #pragma unroll 1
+    for (int idx = tid; idx < (P + 1) * TJ; idx += nthr) {
+        const int i = idx / TJ, jj = idx - i * TJ;
+        W[i * WS + jj] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
+    }
+    #pragma unroll 1
+    for (int jj = tid; jj < 32; jj += nthr) {
+        const float th = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
+        theta_s[jj] = th;
+        thr_s[jj] = E.thresh + (E.learning ? th * E.theta_decay : th);   // nodes.py:1078-1079, 1088
+    }
+    #pragma unroll 1
+    for (int k = tid; k <= Q.nrep; k += nthr) rep[k] = Q.rep[k];
+    #pragma unroll 1
+    for (int k = tid; k < 2 * Bp; k += nthr) { keyT[k] = 0ull; isumT[k] = 0u; aispk[k] = 0u; }
+    #pragma unroll 1
+    for (int k = tid; k < Bp; k += nthr) { candstamp[k] = 0u; candslot[k] = -1; }
+    #pragma unroll 1
+    for (int k = tid; k < aicap; k += nthr) ai_map[k] = (uint16_t)AI_NONE;
+    #pragma unroll 1
+    for (int k = tid; k < 64; k += nthr) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
+    #pragma unroll 1
+    for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
+    if (tid == 0) {
+        mbar_init(&M.mbar_in[0], 1);
+        mbar_init(&M.mbar_in[1], 1);
+        mbar_init(&M.mbar_x, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.abort = 0; M.nwl = 0; M.nlive = 0;
+        M.nact = 0; M.nent = 0; M.bigx = 0;
+        M.denseflag[0] = Q.dense[0]; M.denseflag[1] = T >= 1 ? Q.dense[1] : 0;
+        for (int k = 0; k < NPROF; ++k) M.pc[k] = 0;
+        s_cx.W = W; s_cx.tx = tx; s_cx.xrow = xrow; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.M = &M;
+        s_cx.P = P; s_cx.B = B; s_cx.evblk = evblk; s_cx.cntb = cntb; s_cx.WS = WS;
+        s_cx.pre_on = pre_on; s_cx.has_clamp = C.has_clamp;
+        s_cx.dts = dts; s_cx.wmin = C.wmin; s_cx.wmax = C.wmax; s_cx.nu1 = C.nu1;
+    }
+    __syncthreads();
+
+    float vE[4], rE[4], xE[4];
+    uint32_t candE = 0, pend = 0, sEfin = 0;  // 4-bit masks over my neurons
+    uint32_t vm = 0;                          // my neurons that exist (column < n)
+    #pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool ok = act && jc + c < n;
+        if (ok) vm |= 1u << c;
+        const size_t k = ok ? (size_t)b * n + jc + c : 0;
+        vE[c] = ok ? E.v[k] : 0.0f; rE[c] = ok ? E.refrac_count[k] : 0.0f;
+        xE[c] = (ok && E.traces) ? E.x[k] : 0.0f;
+        if (ok) {
+            // Ai: a neuron that is not exactly at rest, is refractory, or whose partner spiked at step -1
+            // starts in the list (nodes.py:500-529); everything else is at rest until a spike arrives
+            const float v0 = I.v[k], r0 = I.refrac_count[k];
+            const bool sE0 = E.s[k] != 0, sI0 = I.s[k] != 0;
+            if (sI0) atomicOr(&aispk[Bp + b], 1u << (4 * cg + c));   // parity 1 = step -1
+            if (v0 != I.rest || r0 > 0.0f || sE0) {
+                const int e = atomicAdd(&M.nact, 1);
+                ai_v[e] = v0; ai_rc[e] = r0; ai_id[e] = (uint16_t)(b * TJ + 4 * cg + c);
+                ai_in[e] = sE0 ? (uint16_t)0 : (uint16_t)AI_NONE; ai_fl[e] = 0;
+                ai_map[b * TJ + 4 * cg + c] = (uint16_t)e;
+            }
+        }
+    }
+    if (cg == 0 && b < B) isumT[Bp + b] = Q.sisum0[b];
+    if (act && stdp) *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
+    else if (b < Bp && cg < CG) *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool livep = false;  // my (sample, column group) pair has a non-zero Ae trace
+    if (act && stdp && (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)) {
+        livep = true;
+        atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
+        live[atomicAdd(&M.nlive, 1)] = (uint16_t)(b * CG + cg);
+    }
+    const uint32_t bytesE = (uint32_t)Q.SB, bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
+    const int tid_pf = nthr > 32 ? 32 : 0;  // the thread that issues the slot prefetches
+    if (tid == tid_pf) {  // stage slot 0 (spikes of step -1) and slot 1 (spikes of step 0)
+        mbar_arrive_expect_tx(&M.mbar_in[0], bytesE + bytesT);
+        bulk_g2s(evb, Q.evS, bytesE, &M.mbar_in[0]);
+        bulk_g2s(inT, Q.inT, bytesT, &M.mbar_in[0]);
+        mbar_arrive_expect_tx(&M.mbar_in[1], bytesE + bytesT);
+        bulk_g2s(evb + evblk, Q.evS + Q.SB, bytesE, &M.mbar_in[1]);
+        bulk_g2s(inT + P * BW, Q.inT + (size_t)P * BW, bytesT, &M.mbar_in[1]);
+    }
+    __syncthreads();
+    PROF(0)  // prologue
+
+    // spike-gather of my 4 columns for the spikes of list block `blk` (slot `slot`):
+    // p[c] = sum_{i in sX[b]} W[i][c], i ascending (topology.py:437-479)
+    auto gather = [&](const unsigned char *blk, int slot) -> float4 {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        const int cnt = ((const uint16_t *)blk)[b];
+        if (cnt <= EV_CAP) {
+            const uint2 *l4 = (const uint2 *)(blk + cntb + b * (2 * EV_CAP));
+            #pragma unroll 1
+            for (int k = 0; k < cnt; k += 4) {
+                const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
+                const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
+                const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
+                const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
+                const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * WS);
+                p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
+                p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
+                p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
+                p0 = p0 + r3.x; p1 = p1 + r3.y; p2 = p2 + r3.z; p3 = p3 + r3.w;
+            }
+        } else {  // dense sample: walk the bit row in global memory (rare, slow path)
+            return gather_dense2(Q.inS + ((size_t)slot * B + b) * Q.SW, Q.SW, Wc, WS);
+        }
+        return make_float4(p0, p1, p2, p3);
+    };
+
+    unsigned long long *myent = Q.ent + (size_t)blockIdx.x * Q.ecap;          // + parity * G * ecap
+    const size_t entpar = (size_t)G * Q.ecap;
+
+    // =====================================================================================
+    for (int t = 0; t <= T; ++t) {
+        const int buf = t & 1;                       // slot t = spikes of step t-1
+        const unsigned char *cE = evb + buf * evblk;
+        const int par = t & 1, ppar = par ^ 1;       // parity of step t / of step t-1
+
+        // ---- exchange of step t-1: warp 0 collects every CTA's message ---------------------------
+        if (t > 0 && warp == 0) {
+            const unsigned long long *H = Q.hdr + (size_t)ppar * G;
+            const uint32_t tag = msg_tag(t - 1);
+            unsigned long long h[NHMAX];
+            uint32_t need = 0;
+            #pragma unroll
+            for (int k = 0; k < NHMAX; ++k) if (lane + 32 * k < G) need |= 1u << k;
+            const long long t0 = clock64();
+            #pragma unroll 1
+            while (need) {
+                #pragma unroll
+                for (int k = 0; k < NHMAX; ++k) if ((need >> k) & 1u) h[k] = ld_relaxed_u64(H + lane + 32 * k);
+                #pragma unroll
+                for (int k = 0; k < NHMAX; ++k) if (((need >> k) & 1u) && (uint32_t)(h[k] >> 48) == tag) need &= ~(1u << k);
+                if (need && clock64() - t0 > 4000000000LL) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
+            }
+            uint32_t mine = 0;
+            #pragma unroll
+            for (int k = 0; k < NHMAX; ++k) if (lane + 32 * k < G && !((need >> k) & 1u)) mine += (uint32_t)h[k];
+            uint32_t total = mine;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (total > BIGX) {  // rare (many simultaneous candidates, e.g. the first steps of fresh weights)
+                #pragma unroll
+                for (int k = 0; k < NHMAX; ++k) if (lane + 32 * k < G) M.hcnt[lane + 32 * k] = (uint16_t)h[k];
+                if (lane == 0) M.bigx = (int)total;
+            } else if (mine) {
+                #pragma unroll 1
+                for (int k = 0; k < NHMAX; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c >= G) break;
+                    const int ne = (int)(uint32_t)h[k];
+                    const unsigned long long *ep = Q.ent + (size_t)ppar * entpar + (size_t)c * Q.ecap;
+                    #pragma unroll 1
+                    for (int e = 0; e < ne; ++e) {
+                        unsigned long long w;
+                        do { w = ld_relaxed_u64(ep + e); } while ((uint32_t)(w >> 48) != tag && clock64() - t0 < 4000000000LL);
+                        const int sb_ = (int)((w >> 39) & 0xffu);
+                        if (w & (1ull << 47)) {
+                            const unsigned long long key = ((unsigned long long)((uint32_t)((w >> 8) & 0x7fffffffu) | 0x80000000u) << 32) |
+                                                           (unsigned long long)(c * TJ + (int)(w & 0xffu));
+                            atomicMax(keyT + ppar * Bp + sb_, key);
+                        } else atomicAdd(isumT + ppar * Bp + sb_, (uint32_t)(w & 0xffu));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (M.abort) return;
+        PROF(1)  // exchange wait
+        if (t > 0 && M.bigx) {  // large exchange: all warps read the entries
+            const uint32_t tag = msg_tag(t - 1);
+            const int nw = nthr >> 5;
+            #pragma unroll 1
+            for (int c = warp; c < G; c += nw) {
+                const int ne = M.hcnt[c];
+                const unsigned long long *ep = Q.ent + (size_t)ppar * entpar + (size_t)c * Q.ecap;
+                #pragma unroll 1
+                for (int e = lane; e < ne; e += 32) {
+                    unsigned long long w;
+                    const long long t0 = clock64();
+                    do { w = ld_relaxed_u64(ep + e); } while ((uint32_t)(w >> 48) != tag && clock64() - t0 < 4000000000LL);
+                    const int sb_ = (int)((w >> 39) & 0xffu);
+                    if (w & (1ull << 47)) {
+                        const unsigned long long key = ((unsigned long long)((uint32_t)((w >> 8) & 0x7fffffffu) | 0x80000000u) << 32) |
+                                                       (unsigned long long)(c * TJ + (int)(w & 0xffu));
+                        atomicMax(keyT + ppar * Bp + sb_, key);
+                    } else atomicAdd(isumT + ppar * Bp + sb_, (uint32_t)(w & 0xffu));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) M.bigx = 0;
+        }
+
+        // ---- winners of step t-1 (nodes.py:1097-1105), Ae trace, partner Ai input, monitors ------
+        const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;
+        if (t > 0 && pend) {
+            uint32_t sE = 0;
+            if (E.one_spike) {
+                const unsigned long long key = keyT[ppar * Bp + b];
+                const int wj = (int)(uint32_t)(key & 0xffffffffull) - jc;
+                if (key != 0ull && wj >= 0 && wj < 4 && ((candE >> wj) & 1u)) sE = 1u << wj;
+            } else sE = candE;
+            if (E.traces) {
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], (sE >> c) & 1u, E.trace_decay, E.trace_scale, 0);
+            }
+            if (update_on) {
+                if (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f) {
+                    *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
+                    if (!livep) {
+                        livep = true;
+                        atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
+                        live[atomicAdd(&M.nlive, 1)] = (uint16_t)(b * CG + cg);
+                    }
+                }
+            }
+            if (sE) {
+                const int slot = (stage_on && candstamp[b] == (uint32_t)t) ? candslot[b] : -1;   // staged at step t-1
+                #pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if ((sE >> c) & 1u) {
+                        const int col = 4 * cg + c;
+                        if (update_on && post_on) {
+                            atomicOr(&M.wmask[col][b >> 5], 1u << (b & 31));
+                            atomicOr(&M.colwin, 1u << col);
+                            const int k = atomicAdd(&M.nwl, 1);
+                            if (k < XR) M.wl[k] = ((uint32_t)col << 16) | ((uint32_t)b << 8) | (slot >= 0 ? (uint32_t)slot : 0xffu);
+                        }
+                        // diagonal Ae->Ai: the partner receives `exc` at step t (network.py:225-248)
+                        unsigned e = ai_map[b * TJ + col];
+                        if (e == AI_NONE) {
+                            e = (unsigned)atomicAdd(&M.nact, 1);
+                            ai_v[e] = I.rest; ai_rc[e] = 0.0f; ai_id[e] = (uint16_t)(b * TJ + col); ai_fl[e] = 1;
+                            ai_map[b * TJ + col] = (uint16_t)e;
+                        }
+                        ai_in[e] = (uint16_t)t;
+                        // monitors (monitors.py:94-111): the launch code cleared the raster
+                        if (E.rec_s) E.rec_s[((size_t)(t - 1) * B + b) * n + jc + c] = 1;
+                        if (E.rec_count) atomicAdd(E.rec_count + (size_t)b * n + jc + c, 1);
+                    }
+            }
+            if (t == T) sEfin = sE;
+            pend = 0;
+        }
+        PROF(2)  // winners
+        if (t > 0 && update_on && lategrp) {
+            // STDP of step t-1 for the column groups that held a candidate (MCC_learning.py:234-299)
+            __syncthreads();
+            const int sb_ = buf;   // slot t = spikes of step t-1
+            const uint32_t colwin = post_on ? M.colwin : 0u;
+            const int nwl = post_on ? M.nwl : 0;
+            bool fast = nwl <= XR && nwl == __popc(colwin) && !M.denseflag[sb_];
+            if (fast) {
+                #pragma unroll 1
+                for (int k = 0; k < nwl; ++k) if ((M.wl[k] & 0xffu) == 0xffu) fast = false;
+            }
+            if (nwl && stage_on) { while (!mbar_try_wait(&M.mbar_x, (uint32_t)(t - 1) & 1u)) {} }   // rows staged at step t-1
+            PROF(3)  // late set-up
+            if (fast) {
+                if (pre_on) stdp_list2<CG, BW>(&s_cx, sb_, lategrp, colwin, tid, nthr);
+                if (nwl) post_rows2<CG, BW>(&s_cx, sb_, nwl);
+            } else {
+                stdp_rows2<CG, BW>(&s_cx, sb_, lategrp, colwin, M.candb[ppar], min(M.ncand[ppar], XR),
+                                   Q.xtr ? Q.xtr + (size_t)(t - 1) * B * P : nullptr);
+            }
+            PROF(4)  // late pass
+            __syncthreads();
+            if (colwin) {
+                for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
+                if (tid == 0) { M.colwin = 0; M.nwl = 0; }
+            }
+        }
+        if (t == 1 && update_on && C.has_clamp) {
+            // the reference clamps the whole matrix every step (MCC_learning.py:101-110, learning.py:97-104);
+            // after the first step that is a no-op for untouched weights, so one sweep after step 0 covers it
+            __syncthreads();
+            #pragma unroll 1
+            for (int idx = tid; idx < P * TJ; idx += nthr) { const int i = idx / TJ, jj = idx - i * TJ; W[i * WS + jj] = clampf(W[i * WS + jj], C.wmin, C.wmax); }
+        }
+        if (t == T) break;
+
+        // ---- step t: gather, Ae update, Ai list, candidates ------------------------------------------
+        while (!mbar_try_wait(&M.mbar_in[buf], (uint32_t)(t >> 1) & 1u)) {}   // slot t landed (prefetched one step ago)
+        if (tid == 0) { M.ncand[par] = 0; M.candgrp[par] = 0; M.nent = 0; }
+        __syncthreads();   // W final for step t-1; bookkeeping of parity `par` reset
+        PROF(5)  // slot wait + sync
+        uint32_t cand = 0;
+        if (act) {
+            const float4 pg = gather(cE, t);
+            const float p[4] = {pg.x, pg.y, pg.z, pg.w};
+            const float4 th4 = *(const float4 *)(thr_s + 4 * cg);
+            const float thr[4] = {th4.x, th4.y, th4.z, th4.w};
+            const int isum = (int)isumT[ppar * Bp + b];                 // Ai spikes of step t-1 (lateral inhibition)
+            const uint32_t own = (aispk[ppar * Bp + b] >> (4 * cg)) & 0xFu;  // ... of which my neurons' own partners
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if ((vm >> c) & 1u) {
+                    // network.py:225-248: X->Ae first, then Ai->Ae; the latter is rep[#spiking Ai other than j]
+                    const int mI = isum - (int)((own >> c) & 1u);
+                    float cur = 0.0f + p[c];
+                    float inh;
+                    if (mI <= Q.nrep) inh = rep[mI];
+                    else { inh = rep[Q.nrep]; for (int m = Q.nrep; m < mI; ++m) inh = inh + Q.inh_neg; }
+                    cur = cur + inh;
+                    // DiehlAndCookNodes.forward up to the threshold test (nodes.py:1077-1092)
+                    vE[c] = E.decay * (vE[c] - E.rest) + E.rest;
+                    const float gate = rE[c] <= 0.0f ? 1.0f : 0.0f;
+                    vE[c] = vE[c] + gate * cur;
+                    rE[c] = rE[c] - E.dt;
+                    if (vE[c] >= thr[c]) { cand |= 1u << c; rE[c] = E.refrac; vE[c] = E.reset; }
+                }
+            }
+            if (cand) {
+                uint32_t bh = 0; int bc = 0;
+                #pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if ((cand >> c) & 1u) {
+                        atomicAdd(&M.cnt[par][4 * cg + c], 1);
+                        if (E.one_spike) {
+                            const uint32_t hh = snn_one_spike_hash(Q.seed, (uint32_t)t + Q.step_offset, (uint32_t)Q.liE, (uint32_t)b,
+                                                                   (uint32_t)(jc + c)) | 0x80000000u;
+                            if (hh >= bh) { bh = hh; bc = c; }   // ties: the larger neuron index wins, like the 64-bit key
+                        }
+                    }
+                atomicOr(&M.candgrp[par], 1u << cg);
+                if (E.one_spike) {
+                    const int e = atomicAdd(&M.nent, 1);
+                    st_relaxed_u64(myent + (size_t)par * entpar + e, msg_cand(msg_tag(t), b, bh, 4 * cg + bc));
+                }
+                if (stage_on) {  // stage x_pre[b,:] of step t for the post term, once per sample
+                    const uint32_t old = atomicExch(&candstamp[b], (uint32_t)(t + 1));
+                    if (old != (uint32_t)(t + 1)) {
+                        const int s = atomicAdd(&M.ncand[par], 1);
+                        if (s < XR) {
+                            M.candb[par][s] = b;
+                            candslot[b] = s;
+                            mbar_expect_tx(&M.mbar_x, (uint32_t)(P * 4));
+                            bulk_g2s(xrow + s * P, Q.xtr + ((size_t)t * B + b) * P, (uint32_t)(P * 4), &M.mbar_x);
+                        } else candslot[b] = -1;
+                    }
+                }
+            } else if (E.traces) {
+                // no candidate among my neurons: their step-t trace is already final (no spike)
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) xE[c] = xE[c] * E.trace_decay;
+                if (update_on && livep) *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
+            }
+        }
+        candE = cand;
+        pend = cand;
+        // Ai list (LIFNodes.forward, nodes.py:500-529): input `exc` from the partner's spike of step t-1
+        {
+            const int nact = M.nact;
+            #pragma unroll 1
+            for (int k = tid; k < nact; k += nthr) {
+                float v = ai_v[k], rc = ai_rc[k];
+                uint32_t fl = ai_fl[k];
+                float xin = ai_in[k] == (uint16_t)t ? (0.0f + Q.exc) : 0.0f;
+                v = I.decay * (v - I.rest) + I.rest;
+                if (!(fl & 1u)) { if (rc > 0.0f) xin = 0.0f; rc = rc - I.dt; }   // undisturbed counter: <= 0 by construction
+                v = v + xin;
+                fl &= ~2u;
+                if (v >= I.thresh) {
+                    rc = I.refrac; v = I.reset; fl = 2u;
+                    const int id = ai_id[k], sb_ = id / TJ, col = id - sb_ * TJ;
+                    atomicOr(&aispk[par * Bp + sb_], 1u << col);
+                    const int e = atomicAdd(&M.nent, 1);
+                    st_relaxed_u64(myent + (size_t)par * entpar + e, msg_ai(msg_tag(t), sb_, 1));
+                    if (I.rec_s) I.rec_s[((size_t)t * B + sb_) * n + j0 + col] = 1;
+                    if (I.rec_count) atomicAdd(I.rec_count + (size_t)sb_ * n + j0 + col, 1);
+                }
+                ai_v[k] = v; ai_rc[k] = rc; ai_fl[k] = (uint8_t)fl;
+            }
+        }
+        PROF(6)  // gather + neurons
+        __syncthreads();
+        // ---- publish step t's message; theta; prefetch -----------------------------------------------
+        if (tid == 0) {
+            st_relaxed_u64(Q.hdr + (size_t)par * G + blockIdx.x, ((unsigned long long)msg_tag(t) << 48) | (unsigned long long)(uint32_t)M.nent);
+            mbar_arrive(&M.mbar_x);   // phase t of the staged rows: complete once the copies issued above have landed
+        }
+        if (tid < TJ) {
+            // theta = theta * decay + theta_plus * (#candidates of the column)  (nodes.py:1078-1094)
+            float th = theta_s[tid];
+            if (E.learning) th = th * E.theta_decay + E.theta_plus * (float)M.cnt[par][tid];
+            theta_s[tid] = th;
+            thr_s[tid] = E.thresh + (E.learning ? th * E.theta_decay : th);
+            M.cnt[par][tid] = 0;
+        }
+        // tables of step t-1 are consumed: clear them for step t+1
+        for (int k = tid; k < Bp; k += nthr) { keyT[ppar * Bp + k] = 0ull; isumT[ppar * Bp + k] = 0u; aispk[ppar * Bp + k] = 0u; }
+        int dflag = 0;
+        if (tid == tid_pf && t + 2 <= T) {  // prefetch slot t+2 into the buffer the gather just finished with
+            mbar_arrive_expect_tx(&M.mbar_in[buf], bytesE + bytesT);
+            bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar_in[buf]);
+            bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar_in[buf]);
+            dflag = __ldg(Q.dense + t + 2);
+        }
+        PROF(7)  // publish
+        // ---- early STDP of step t, in the shadow of the exchange: pre term of the column groups WITHOUT a
+        // candidate (their step-t traces are final).  Warp 0 goes straight to the exchange.
+        const int nb = buf ^ 1;                                      // slot t+1 = spikes of step t
+        if (update_on && pre_on && (warp > 0 || nthr == 32)) {
+            while (!mbar_try_wait(&M.mbar_in[nb], (uint32_t)((t + 1) >> 1) & 1u)) {}
+            const uint32_t earlygrp = ((1u << CG) - 1u) & ~M.candgrp[par];
+            if (M.denseflag[nb]) {
+                // row form needs every thread: done below, after the exchange (rare)
+            } else stdp_list2<CG, BW>(&s_cx, nb, earlygrp, 0u, nthr > 32 ? tid - 32 : tid, nthr > 32 ? nthr - 32 : nthr);
+        }
+        if (tid == tid_pf && t + 2 <= T) M.denseflag[buf] = dflag;   // read one step from now
+        PROF(8)  // early STDP
+        if (update_on && pre_on && M.denseflag[nb]) {
+            // a sample's event list overflowed: early pass in row form with the whole CTA (its own barrier)
+            while (!mbar_try_wait(&M.mbar_in[nb], (uint32_t)((t + 1) >> 1) & 1u)) {}
+            __syncthreads();
+            const uint32_t earlygrp = ((1u << CG) - 1u) & ~M.candgrp[par];
+            stdp_rows2<CG, BW>(&s_cx, nb, earlygrp, 0u, M.candb[par], 0, nullptr);
+        }
+    }
+
+    // ---- epilogue: normalize() on the tile (network.py:464-465), write everything back -----
+    __syncthreads();
+    if (Q.normalize && C.has_norm) {
+        float *part = xrow;  // [SNN_NORM_CHUNKS + 1][TJ]
+        const int chunk = (P + SNN_NORM_CHUNKS - 1) / SNN_NORM_CHUNKS;
+        #pragma unroll 1
+        for (int idx = tid; idx < SNN_NORM_CHUNKS * TJ; idx += nthr) {
+            const int c = idx / TJ, jj = idx % TJ;
+            float a = 0.0f;
+            const int i1 = min((c + 1) * chunk, P);
+            #pragma unroll 1
+            for (int i = c * chunk; i < i1; ++i) { const float x = W[i * WS + jj]; a = a + (C.norm_abs ? fabsf(x) : x); }
+            part[idx] = a;
+        }
+        __syncthreads();
+        if (tid < TJ) {
+            float tot = 0.0f;
+            for (int c = 0; c < SNN_NORM_CHUNKS; ++c) tot = tot + part[c * TJ + tid];
+            if (tot == 0.0f) tot = 1.0f;
+            part[SNN_NORM_CHUNKS * TJ + tid] = C.norm / tot;
+        }
+        __syncthreads();
+        #pragma unroll 1
+        for (int idx = tid; idx < P * TJ; idx += nthr) { const int i = idx / TJ, jj = idx % TJ; W[i * WS + jj] = W[i * WS + jj] * part[SNN_NORM_CHUNKS * TJ + jj]; }
+        __syncthreads();
+    }
+    #pragma unroll 1
+    for (int idx = tid; idx < P * TJ; idx += nthr) {
+        const int i = idx / TJ, jj = idx % TJ;
+        if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[i * WS + jj];
+    }
+    for (int jj = tid; jj < TJ; jj += nthr)
+        if (j0 + jj < n) E.theta[j0 + jj] = theta_s[jj];
+    if (act) {
+        #pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if ((vm >> c) & 1u) {
+                const size_t k = (size_t)b * n + jc + c;
+                E.v[k] = vE[c]; E.refrac_count[k] = rE[c];
+                if (E.traces) E.x[k] = xE[c];
+                E.s[k] = (sEfin >> c) & 1u;
+                // Ai: listed neurons from the list, the others only ran their refractory counter down
+                const unsigned e = ai_map[b * TJ + 4 * cg + c];
+                if (e == AI_NONE) {
+                    I.refrac_count[k] = refrac_replay(I.refrac_count[k], I.dt, T);
+                    I.s[k] = 0;
+                } else {
+                    I.v[k] = ai_v[e];
+                    I.refrac_count[k] = (ai_fl[e] & 1u) ? refrac_replay(I.refrac_count[k], I.dt, T) : ai_rc[e];
+                    I.s[k] = (ai_fl[e] >> 1) & 1u;
+                }
+            }
+    }
+    PROF(9)  // epilogue
+    if (PROFV && Q.prof && tid == 0)
+        for (int k = 0; k < NPROF; ++k) Q.prof[blockIdx.x * NPROF + k] = pc[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// Pre-pass 1 (bits): grid = (slot, group of 32 samples).  Slot 0 = the Input layer's incoming spike
+// state, slot t+1 = the external input of step t (network.py:388-392 / Input.forward nodes.py:211-221).
+// Produces the per-sample bit rows and ascending pixel lists, the per-pixel sample masks, the Input
+// monitor raster, flags non-binary input; one CTA also counts the incoming Ai spikes and builds the
+// inhibition table.
+__global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F2Params Q, int BW) {
+    extern __shared__ uint32_t sbits[];  // [32][SW]
+    const int B = Q.B, P = Q.P, SW = Q.SW, PW = (P + 31) / 32;
+    const int slot = blockIdx.x, grp = blockIdx.y, b0 = grp * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const snn_layer_t &X = Q.X;
+    unsigned char *blk = Q.evS + (size_t)slot * Q.SB;
+    uint16_t *ecnt = (uint16_t *)blk;
+    uint16_t *elist = (uint16_t *)(blk + ev_count_bytes(B));
+    bool nonbin = false, dense = false;
+    // fast path: byte spikes (uint8 / bool input, or the layer's own spike state for slot 0) in
+    // 16-byte aligned rows — one 16-byte load per lane covers 16 pixels
+    const bool bytes_in = slot == 0 || (X.ext && X.ext_dtype == SNN_EXT_U8);
+    const unsigned char *src0 = slot == 0 ? (const unsigned char *)X.s : (const unsigned char *)X.ext + (size_t)(slot - 1) * B * P;
+    const bool fast16 = bytes_in && (P & 15) == 0 && (((size_t)src0) & 15) == 0 && (((size_t)X.rec_s) & 15) == 0;
+    for (int bl = warp; bl < 32; bl += nwarp) {
+        const int b = b0 + bl;
+        int total = 0;
+        if (b < B && fast16) {
+            uint16_t *lst = elist + b * EV_CAP;
+            const uint4 *row = (const uint4 *)(src0 + (size_t)b * P);
+            unsigned char *rec = (slot > 0 && X.rec_s) ? X.rec_s + ((size_t)(slot - 1) * B + b) * P : nullptr;
+            const int nchunk = P >> 4;
+            for (int c0 = 0; c0 < nchunk; c0 += 32) {
+                const int c = c0 + lane;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (c < nchunk) v = __ldg(row + c);
+                if (slot > 0) nonbin |= ((v.x | v.y | v.z | v.w) & 0xfefefefeu) != 0u;
+                const uint32_t zx = __vcmpne4(v.x, 0u) & 0x01010101u, zy = __vcmpne4(v.y, 0u) & 0x01010101u,
+                               zz = __vcmpne4(v.z, 0u) & 0x01010101u, zw = __vcmpne4(v.w, 0u) & 0x01010101u;
+                if (rec && c < nchunk) ((uint4 *)rec)[c] = make_uint4(zx, zy, zz, zw);
+                // 4 flag bytes -> 4 bits: the multiply moves byte k's bit 0 to bit 24 + k
+                const uint32_t m16 = ((zx * 0x01020408u) >> 24) | (((zy * 0x01020408u) >> 24) << 4) | (((zz * 0x01020408u) >> 24) << 8) |
+                                     (((zw * 0x01020408u) >> 24) << 12);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, m16, 1);
+                if (!(lane & 1)) {  // even lane: the 32-pixel word of chunks c, c + 1
+                    const int w = c >> 1;
+                    if (w < SW) {
+                        const uint32_t word = m16 | (other << 16);
+                        sbits[bl * SW + w] = word;
+                        Q.inS[((size_t)slot * B + b) * SW + w] = word;
+                    }
+                }
+                // ascending pixel list: position = spikes before me
+                const int mine = __popc(m16);
+                int incl = mine;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                int pos = total + incl - mine;
+                uint32_t mm = m16;
+                while (mm) {
+                    const int bit = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (pos < EV_CAP) lst[pos] = (uint16_t)(c * 16 + bit);
+                    ++pos;
+                }
+                total += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            for (int w = (P >> 5) + lane; w < SW; w += 32) {  // words past the last pixel (odd chunk count: half word above)
+                if (w * 32 >= P) { sbits[bl * SW + w] = 0u; Q.inS[((size_t)slot * B + b) * SW + w] = 0u; }
+            }
+            const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
+            if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+            if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
+            dense |= total > EV_CAP;
+        } else if (b < B) {
+            uint16_t *lst = elist + b * EV_CAP;
+            for (int w = 0; w < SW; ++w) {
+                const int i = w * 32 + lane;
+                bool s = false;
+                if (w < PW && i < P) {
+                    if (slot == 0) s = X.s[(size_t)b * P + i] != 0;
+                    else if (X.ext) {
+                        const size_t idx = ((size_t)(slot - 1) * B + b) * P + i;
+                        if (X.ext_dtype == SNN_EXT_U8) { const uint8_t e = ((const uint8_t *)X.ext)[idx]; s = e != 0; nonbin |= e > 1; }
+                        else { const float e = ((const float *)X.ext)[idx]; s = e != 0.0f; nonbin |= (e != 0.0f && e != 1.0f); }
+                    }
+                    if (slot > 0 && X.rec_s) X.rec_s[((size_t)(slot - 1) * B + b) * P + i] = s ? 1 : 0;
+                }
+                const uint32_t word = __ballot_sync(0xffffffffu, s);
+                if (lane == 0) { sbits[bl * SW + w] = word; Q.inS[((size_t)slot * B + b) * SW + w] = word; }
+                if (s) {  // ascending pixel list: position = spikes before me
+                    const int pos = total + __popc(word & ((1u << lane) - 1u));
+                    if (pos < EV_CAP) lst[pos] = (uint16_t)i;
+                }
+                total += __popc(word);
+            }
+            const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
+            if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+            if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
+            dense |= total > EV_CAP;
+        } else {
+            for (int w = lane; w < SW; w += 32) sbits[bl * SW + w] = 0u;
+        }
+    }
+    if (dense && lane == 0) atomicOr(Q.dense + slot, 1);
+    if (grp == 0 && threadIdx.x < 8) ecnt[B + threadIdx.x] = 0;
+    __syncthreads();
+    // transpose 32x32 bit blocks: inT[pixel][grp] bit b' = inS[b0+b'][pixel/32] bit pixel%32
+    // (5 butterfly steps: lanes l and l ^ j swap the bit blocks whose index differs in bit j)
+    for (int w = warp; w < PW; w += nwarp) {
+        uint32_t x = sbits[lane * SW + w];
+        #pragma unroll
+        for (int j = 16; j >= 1; j >>= 1) {
+            const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            x = (lane & j) ? (((y & ~m) >> j) | (x & ~m)) : ((x & m) | ((y & m) << j));
+        }
+        const int i = w * 32 + lane;
+        if (i < P) {
+            Q.inT[((size_t)slot * P + i) * BW + grp] = x;
+            if (grp == 0)  // zero the padding groups of the per-pixel masks
+                for (int g = (B + 31) / 32; g < BW; ++g) Q.inT[((size_t)slot * P + i) * BW + g] = 0u;
+        }
+    }
+    if (nonbin && Q.err) atomicOr(Q.err, SNN_ERR_NONBINARY);
+    if (slot == 0 && grp == 0) {
+        for (int b = warp; b < B; b += nwarp) {  // Ai spikes of step -1
+            int c = 0;
+            for (int j = lane; j < Q.n; j += 32) c += Q.I.s[(size_t)b * Q.n + j] != 0;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) Q.sisum0[b] = (unsigned int)c;
+        }
+    }
+    if (slot == (gridDim.x > 1 ? 1 : 0) && grp == 0 && threadIdx.x == 0) {
+        // rep[m] = m-fold sequential sum of the Ai->Ae weight: what the reference's dense sum over k of
+        // sI[b,k] * w_ie[k,j] evaluates to when m inhibitory neurons (other than j) spike (topology.py:437-479)
+        float a = 0.0f;
+        Q.rep[0] = 0.0f;
+        for (int m = 1; m <= Q.nrep; ++m) { a = a + Q.inh_neg; Q.rep[m] = a; }
+    }
+}
+
+// Pre-pass 2 (trace scan): the Input layer's trace for every step of the window, Nodes.forward
+// (nodes.py:96-103) applied T times per pixel: xtr[t][b][i] = x after step t.  Thread = 4 pixels of one
+// sample; loads run SCAN_U steps ahead.  Also leaves the layer's final state (x, s) behind.
+constexpr int SCAN_U = 10;
+__global__ void __launch_bounds__(256) snn_dc2_trace_scan(const __grid_constant__ F2Params Q) {
+    const int P4 = Q.P >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Q.B * P4) return;
+    const snn_layer_t &X = Q.X;
+    const size_t stride4 = (size_t)Q.B * P4;  // float4 / uchar4 units per timestep
+    float4 x = X.traces ? ((const float4 *)X.x)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t last = 0;
+    for (int t0 = 0; t0 < Q.T; t0 += SCAN_U) {
+        uint32_t bits[SCAN_U];
+        #pragma unroll
+        for (int u = 0; u < SCAN_U; ++u) {
+            bits[u] = 0;
+            if (t0 + u < Q.T && X.ext) {
+                if (X.ext_dtype == SNN_EXT_U8) {
+                    const uint32_t w = __ldg((const uint32_t *)X.ext + (size_t)(t0 + u) * stride4 + idx);
+                    bits[u] = __vcmpne4(w, 0u) & 0x01010101u;
+                } else {
+                    const float4 f = __ldg((const float4 *)X.ext + (size_t)(t0 + u) * stride4 + idx);
+                    bits[u] = (f.x != 0.0f ? 1u : 0u) | (f.y != 0.0f ? 0x100u : 0u) | (f.z != 0.0f ? 0x10000u : 0u) | (f.w != 0.0f ? 0x1000000u : 0u);
+                }
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < SCAN_U; ++u) {
+            if (t0 + u < Q.T) {
+                const uint32_t w = bits[u];
+                if (X.traces) {
+                    x.x = trace_step(x.x, w & 0x1u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    x.y = trace_step(x.y, w & 0x100u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    x.z = trace_step(x.z, w & 0x10000u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    x.w = trace_step(x.w, w & 0x1000000u, X.trace_decay, X.trace_scale, X.traces_additive);
+                    if (Q.xtr) __stcs((float4 *)Q.xtr + (size_t)(t0 + u) * stride4 + idx, x);
+                }
+                last = w;
+            }
+        }
+    }
+    if (Q.T > 0) {
+        if (X.traces) ((float4 *)X.x)[idx] = x;
+        ((uint32_t *)X.s)[idx] = last;
+    }
+}
+
+struct Match2 {
+    int lX, lE, lI, cXE, cEI, cIE, CG, BW, threads, grid, SW, SB, Bp, nrep, ecap;
+    size_t smem;
+};
+
+int device_sms2() {
+    static int sms = -1;
+    if (sms < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        else { sms = 148; (void)cudaGetLastError(); }
+    }
+    return sms;
+}
+
+bool match2(const snn_net_t *net, const snn_run_opts_t *o, Match2 &m) {
+    if (net->n_layers != 3 || net->n_conns != 3 || o->T < 1 || o->T > 65000 || o->one_step) return false;
+    m.lX = m.lE = m.lI = -1;
+    for (int l = 0; l < 3; ++l) {
+        const snn_layer_t &L = net->layers[l];
+        if (L.clamp || L.unclamp || L.inject_v || L.sum_input) return false;
+        if (L.kind == SNN_NODE_INPUT) m.lX = l;
+        else if (L.kind == SNN_NODE_DC) m.lE = l;
+        else if (L.kind == SNN_NODE_LIF) m.lI = l;
+    }
+    if (m.lX < 0 || m.lE < 0 || m.lI < 0) return false;
+    const snn_layer_t &X = net->layers[m.lX], &E = net->layers[m.lE], &I = net->layers[m.lI];
+    if (E.ext || I.ext || I.traces || E.n != I.n) return false;
+    if (X.rec_count || X.rec_v || E.rec_v || I.rec_v) return false;
+    // the lean option set (everything else: snn_fused_dc.cu)
+    if (X.traces_additive || E.traces_additive || E.has_lbound || I.has_lbound) return false;
+    if (!(I.rest < I.thresh)) return false;   // an Ai neuron at rest must stay silent
+    m.cXE = m.cEI = m.cIE = -1;
+    for (int c = 0; c < 3; ++c) {
+        const snn_conn_t &C = net->conns[c];
+        if (C.b || C.kind == SNN_CONN_CONV2D || C.rule > SNN_RULE_MCC_POSTPRE) return false;
+        if (C.src == m.lX && C.tgt == m.lE) m.cXE = c;
+        else if (C.src == m.lE && C.tgt == m.lI) m.cEI = c;
+        else if (C.src == m.lI && C.tgt == m.lE) m.cIE = c;
+    }
+    if (m.cXE < 0 || m.cEI < 0 || m.cIE < 0 || m.cXE > m.cIE) return false;  // accumulation order into Ae
+    const snn_conn_t &CX = net->conns[m.cXE], &CEI = net->conns[m.cEI], &CIE = net->conns[m.cIE];
+    auto is_static = [](const snn_conn_t &C) {
+        return (C.rule == SNN_RULE_NONE || (C.rule == SNN_RULE_NOOP && (C.weight_decay == 1.0f || C.weight_decay == 0.0f))) && !C.has_norm;
+    };
+    if (!is_static(CEI) || !is_static(CIE)) return false;
+    if (CEI.structure != SNN_W_DIAG || CIE.structure != SNN_W_OFFDIAG) return false;
+    if (CX.rule == SNN_RULE_WDEP_POSTPRE || CX.reduction != SNN_REDUCE_SUM) return false;
+    if (CX.weight_decay != 0.0f && CX.weight_decay != 1.0f) return false;
+    if (CX.rule == SNN_RULE_NOOP) return false;
+    if (CX.rule >= SNN_RULE_POSTPRE && (!X.traces || !E.traces)) return false;
+    const int n = E.n, P = X.n, B = o->B;
+    if (B > 128 || (P & 3) || P >= 65535 || n >= 65535) return false;
+    const int sms = device_sms2();
+    m.SW = ((P + 31) / 32 + 3) / 4 * 4;
+    m.BW = 4;
+    m.SB = ev_block_bytes(B);
+    m.Bp = (B + 31) / 32 * 32;
+    m.nrep = n < 1023 ? n : 1023;
+    for (int CG = 1; CG <= 8; ++CG) {
+        const int TJ = 4 * CG;
+        const int grid = (n + TJ - 1) / TJ;
+        const int threads = m.Bp * CG;
+        if (grid > sms || grid > 32 * NHMAX || threads > 1024) continue;
+        const SmemLayout2 SL = smem_layout2(P, TJ, B, m.Bp, m.BW, m.nrep);
+        if (SL.total > 227 * 1024) continue;
+        m.CG = CG; m.grid = grid; m.threads = threads; m.smem = SL.total;
+        m.ecap = m.Bp * CG + m.Bp * TJ;   // one candidate entry per thread + one entry per Ai spike
+        return true;
+    }
+    return false;
+}
+
+template <int CG, int BW, int VAR>
+cudaError_t launch_var2(const F2Params &Q, const Match2 &m, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(snn_dc2_window<CG, BW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
+    if (e != cudaSuccess) return e;
+    void *args[] = {(void *)&Q};
+    return cudaLaunchCooperativeKernel((void *)snn_dc2_window<CG, BW, VAR>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
+}
+
+template <int CG>
+cudaError_t launch_cg2(const F2Params &Q, const Match2 &m, cudaStream_t stream) {
+    return Q.prof ? launch_var2<CG, 4, 2>(Q, m, stream) : launch_var2<CG, 4, 0>(Q, m, stream);
+}
+
+struct WsLayout2 { size_t dense, hdr, ent, inS, inT, evS, rep, sisum0, xtr, prof, total; };
+WsLayout2 ws_layout2(const Match2 &m, int T, int B, int P, bool traces) {
+    WsLayout2 L; size_t o = 0;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    // dense flags, headers and entries are adjacent: one memset node per window
+    L.dense = o; o += al(sizeof(int) * (size_t)(T + 1));
+    L.hdr = o; o += al(sizeof(unsigned long long) * 2 * (size_t)m.grid);
+    L.ent = o; o += al(sizeof(unsigned long long) * 2 * (size_t)m.grid * m.ecap);
+    L.inS = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * B * m.SW);
+    L.inT = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * P * m.BW);
+    L.evS = o; o += al((size_t)(T + 1) * m.SB);
+    L.rep = o; o += al(sizeof(float) * (size_t)(m.nrep + 1));
+    L.sisum0 = o; o += al(sizeof(unsigned int) * (size_t)B);
+    L.xtr = o; o += traces ? al(sizeof(float) * (size_t)T * B * P) : 0;
+    L.prof = o; o += al(sizeof(long long) * 160 * NPROF);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+int snn_fused_dc2_supported(const snn_net_t *net, const snn_run_opts_t *opts) {
+    Match2 m;
+    return match2(net, opts, m) ? 1 : 0;
+}
+
+size_t snn_fused_dc2_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts) {
+    Match2 m;
+    if (!match2(net, opts, m)) return 0;
+    const snn_layer_t &X = net->layers[m.lX];
+    return ws_layout2(m, opts->T, opts->B, X.n, X.traces != 0).total;
+}
+
+int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *ws_, size_t ws_bytes, cudaStream_t stream,
+                         int *launches) {
+    Match2 m;
+    if (!match2(net, opts, m)) return SNN_ERR_UNSUPPORTED;
+    const int T = opts->T, B = opts->B, P = net->layers[m.lX].n;
+    const bool traces = net->layers[m.lX].traces != 0;
+    const WsLayout2 WL = ws_layout2(m, T, B, P, traces);
+    if (ws_bytes < WL.total) return SNN_ERR_WORKSPACE;
+    char *ws = (char *)ws_;
+    F2Params Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.X = net->layers[m.lX]; Q.E = net->layers[m.lE]; Q.I = net->layers[m.lI];
+    Q.C = net->conns[m.cXE];
+    Q.exc = net->conns[m.cEI].structure_val; Q.inh_neg = net->conns[m.cIE].structure_val;
+    Q.T = T; Q.B = B; Q.Bp = m.Bp; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
+    Q.G = m.grid; Q.nrep = m.nrep; Q.ecap = m.ecap;
+    {
+        const SmemLayout2 SL = smem_layout2(P, 4 * m.CG, B, m.Bp, m.BW, m.nrep);
+        Q.o_W = (uint32_t)SL.W; Q.o_tx = (uint32_t)SL.tx; Q.o_ev = (uint32_t)SL.ev; Q.o_inT = (uint32_t)SL.inT; Q.o_xrow = (uint32_t)SL.xrow;
+        Q.o_rep = (uint32_t)SL.rep; Q.o_theta = (uint32_t)SL.theta; Q.o_live = (uint32_t)SL.live; Q.o_tab = (uint32_t)SL.tab;
+        Q.o_ai = (uint32_t)SL.ai; Q.o_misc = (uint32_t)SL.misc;
+    }
+    Q.SW = m.SW; Q.SB = m.SB; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
+    Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
+    Q.dense = (int *)(ws + WL.dense); Q.hdr = (unsigned long long *)(ws + WL.hdr); Q.ent = (unsigned long long *)(ws + WL.ent);
+    Q.rep = (float *)(ws + WL.rep); Q.sisum0 = (unsigned int *)(ws + WL.sisum0);
+    const bool stdp = Q.C.rule >= SNN_RULE_POSTPRE;
+    Q.xtr = (traces && stdp && net->learning && Q.C.nu1 != 0.0f) ? (float *)(ws + WL.xtr) : nullptr;
+    Q.err = opts->err_flag;
+    const bool prof = getenv("SNN_B200_PROF") != nullptr;
+    Q.prof = prof ? (long long *)(ws + WL.prof) : nullptr;
+    int nl = 0;
+    // dense flags + message area: stale tags of an earlier window must not be believed
+    if (cudaMemsetAsync(ws + WL.dense, 0, WL.inS - WL.dense, stream) != cudaSuccess) return SNN_ERR_CUDA;
+    // sparse monitors: the window kernel only writes the ones
+    if (Q.E.rec_s && cudaMemsetAsync(Q.E.rec_s, 0, (size_t)T * B * Q.n, stream) != cudaSuccess) return SNN_ERR_CUDA;
+    if (Q.I.rec_s && cudaMemsetAsync(Q.I.rec_s, 0, (size_t)T * B * Q.n, stream) != cudaSuccess) return SNN_ERR_CUDA;
+    snn_dc2_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
+    ++nl;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        const int items = B * (P >> 2);
+        snn_dc2_trace_scan<<<(items + 255) / 256, 256, 0, stream>>>(Q);
+        ++nl;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        switch (m.CG) {
+            case 1: e = launch_cg2<1>(Q, m, stream); break;
+            case 2: e = launch_cg2<2>(Q, m, stream); break;
+            case 3: e = launch_cg2<3>(Q, m, stream); break;
+            case 4: e = launch_cg2<4>(Q, m, stream); break;
+            case 5: e = launch_cg2<5>(Q, m, stream); break;
+            case 6: e = launch_cg2<6>(Q, m, stream); break;
+            case 7: e = launch_cg2<7>(Q, m, stream); break;
+            default: e = launch_cg2<8>(Q, m, stream); break;
+        }
+        ++nl;
+    }
+    if (e != cudaSuccess) {
+        fprintf(stderr, "libsnn_b200: fused DC2015 (v2) window launch failed: %s\n", cudaGetErrorString(e));
+        return SNN_ERR_CUDA;
+    }
+    if (prof) {  // debug only: synchronise and print the per-phase cycle counts (min / mean / max over CTAs)
+        static const char *names[NPROF] = {"prologue", "exchange wait", "winners", "late set-up", "late pass", "slot wait+sync", "gather+neurons",
+                                           "publish", "early STDP", "epilogue", "", "", "", "", "", ""};
+        cudaStreamSynchronize(stream);
+        static long long hostp[160 * NPROF];
+        cudaMemcpy(hostp, Q.prof, sizeof(long long) * (size_t)m.grid * NPROF, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[snn_b200 prof v2] grid=%d threads=%d T=%d (cycles per timestep, thread 0 of each CTA: min / mean / max)\n", m.grid, m.threads, T);
+        for (int k = 0; k < 10; ++k) {
+            double sum = 0, mx = 0, mn = 1e300;
+            for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[g * NPROF + k]; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
+            const double div = (k == 0 || k == 9) ? 1.0 : (double)T;
+            fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f\n", names[k], mn / div, sum / m.grid / div, mx / div);
+        }
+    }
+    if (launches) *launches = nl;  // two pre-passes + the persistent window kernel
+    return SNN_OK;
+}

@@ -178,7 +178,8 @@ typedef struct snn_run_opts {
     int32_t T;             /* timesteps = int(time / dt)  (network.py:356)                    */
     int32_t B;             /* batch size                                                      */
     int32_t normalize;     /* 1: run every connection's normalize() after the loop            */
-    int32_t tier;          /* 0 = auto, 1 = force generic kernel, 2 = force fused DC2015 kernel */
+    int32_t tier;          /* 0 = auto, 1 = force generic kernel, 2 = force fused DC2015 kernel (v1: grid barrier),
+                              3 = force fused DC2015 kernel v2 (message exchange) */
     uint32_t seed;         /* one_spike tie-break stream (see snn_one_spike_key)              */
     uint32_t step_offset;  /* added to t in the tie-break hash (lets callers split a window)  */
     int32_t *err_flag;     /* optional int32 (device memory for the CUDA lib); OR-ed with SNN_ERR_* */
@@ -241,7 +242,7 @@ size_t snn_b200_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts
 int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *workspace,
                         size_t workspace_bytes, void *stream);
 
-/* Which kernel tier `tier = 0` would select for this plan: 1 generic, 2 fused DC2015. */
+/* Which kernel tier `tier = 0` would select for this plan: 1 generic, 2 fused DC2015 (v1), 3 fused DC2015 (v2). */
 int snn_b200_select_tier(const snn_net_t *net, const snn_run_opts_t *opts);
 
 /* Number of kernel launches the last snn_b200_run_window on this thread issued. */
