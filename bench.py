@@ -125,56 +125,125 @@ def hbm_peak_gbs():
     return 6650.0, "fallback"
 
 
-def cpu_baseline(steps_budget_s: float = 15.0, threads: int = 0):
+def host_threads() -> int:
+    """Threads the CPU legs use: every core of the box, set explicitly (torchrun exports
+    OMP_NUM_THREADS=1 to its children, which must not silently shrink the baseline)."""
+    return os.cpu_count() or 1
+
+
+def cpu_baseline(steps_budget_s: float = 15.0):
     """The oracle's dense restatement of the reference algorithm (oracle/snn_oracle.c, every
     zero of `s.float() @ w` and of the batch-summed outer products multiplied like the reference
     does) on the host cores, on a bounded number of timesteps of the same workload."""
-    import torch
     from oracle.oracle import OracleBackend
 
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     net = make_network(None)
     x = synth_windows(1, seed=999, T=64)[0]
-    with OracleBackend(dense=1, threads=threads) as ob:
+    with OracleBackend(dense=1, threads=cores) as ob:
         t0 = time.perf_counter(); net.run({"X": x[:2]}, time=2); probe = (time.perf_counter() - t0) / 2
         T_s = int(max(4, min(60, steps_budget_s / max(probe, 1e-3))))
         net.reset_state_variables()
         t0 = time.perf_counter(); net.run({"X": x[:T_s]}, time=T_s); wall = time.perf_counter() - t0
     return {"value": BATCH * T_s / wall, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{T_s} of {T_STEPS} timesteps of the same workload (n={N_NEURONS}, B={BATCH}), dense mode, "
-                      f"{wall:.2f} s wall, OpenMP over {cores} cores"}
+                      f"{wall:.2f} s wall, OpenMP with {cores} threads (set explicitly)"}
+
+
+def import_reference():
+    """The UNMODIFIED reference from baseline/_ref (baseline/install_ref.sh), imported through a stub
+    package because `import bindsnet` itself pulls in matplotlib & co.; only the
+    sub-packages of the hot path are loaded, in the order the reference's circular imports need."""
+    import importlib
+    import types
+
+    ref = os.path.join(ROOT, "baseline", "_ref", "bindsnet")
+    if not os.path.isdir(ref):
+        return None, f"baseline/_ref/bindsnet not found (run baseline/install_ref.sh in the build container)"
+    try:
+        pkg = types.ModuleType("bindsnet")
+        pkg.__path__ = [ref]
+        sys.modules["bindsnet"] = pkg
+        for sub in ("bindsnet.utils", "bindsnet.network", "bindsnet.learning", "bindsnet.models"):
+            importlib.import_module(sub)
+        return sys.modules["bindsnet.models"], None
+    except Exception as e:  # missing dependency on this box
+        return None, f"{type(e).__name__}: {e}"
+
+
+def reference_baseline(budget_s: float = 20.0):
+    """cpu_baseline leg of our arm: the live reference timed on this box's cores on a bounded sample."""
+    import torch
+
+    models, why = import_reference()
+    if models is None:
+        return None
+    cores = host_threads()
+    old = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    try:
+        torch.manual_seed(1234)
+        net = models.DiehlAndCook2015(n_inpt=N_INPT, n_neurons=N_NEURONS, batch_size=BATCH, inpt_shape=(1, 28, 28), dt=1.0,
+                                      nu=(1e-4, 1e-2), norm=78.4, theta_plus=0.05, exc=22.5, inh=120.0)
+        x = synth_windows(1, seed=999, T=32)[0]
+        t0 = time.perf_counter(); net.run({"X": x[:1]}, time=1); probe = time.perf_counter() - t0
+        T_ref = int(max(1, min(32, budget_s / max(probe, 1e-3))))
+        net.reset_state_variables()
+        t0 = time.perf_counter(); net.run({"X": x[:T_ref]}, time=T_ref); wall = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(old)
+    return {"value": BATCH * T_ref / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{T_ref} of {T_STEPS} timesteps of the same workload through the unmodified reference "
+                      f"(bindsnet.models.DiehlAndCook2015.run, torch CPU, {cores} threads), {wall:.2f} s wall"}
 
 
 def run_reference(args):
+    """--impl reference: the live reference's own `DiehlAndCook2015.run` on the host cores — same network
+    (n=1600, B=128, inh=120), same synthetic windows, every step a bounded T_ref-timestep sample of the
+    250-step window (the reference costs ~seconds per timestep here: SURVEY.md §0.3)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle.oracle import OracleBackend
 
-    cores = os.cpu_count() or 1
-    net = make_network(None)
-    T_s = 10
-    xs = synth_windows(2, seed=999, T=T_s)
-    with OracleBackend(dense=1) as ob:
-        for i in range(args.warmup):
-            net.reset_state_variables(); net.run({"X": xs[i % 2]}, time=T_s)
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            net.reset_state_variables(); net.run({"X": xs[i % 2]}, time=T_s)
-        wall = time.perf_counter() - t0
-    value = BATCH * T_s * args.steps / wall
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    models, why = import_reference()
+    if models is None:
+        emit({"impl": "reference", "unavailable": why})
+        return
+    torch.manual_seed(1234)
+    net = models.DiehlAndCook2015(n_inpt=N_INPT, n_neurons=N_NEURONS, batch_size=BATCH, inpt_shape=(1, 28, 28), dt=1.0,
+                                  nu=(1e-4, 1e-2), norm=78.4, theta_plus=0.05, exc=22.5, inh=120.0)
+    xs = synth_windows(2, seed=999, T=16)
+    # probe one timestep, then size T_ref so that the whole run stays within ~2 minutes
+    t0 = time.perf_counter(); net.run({"X": xs[0][:1]}, time=1); probe = time.perf_counter() - t0
+    total = max(args.steps + args.warmup, 1)
+    T_ref = int(max(1, min(16, 120.0 / (total * max(probe, 1e-3)))))
+    for i in range(args.warmup):
+        net.reset_state_variables(); net.run({"X": xs[i % 2][:T_ref]}, time=T_ref)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        net.reset_state_variables(); net.run({"X": xs[i % 2][:T_ref]}, time=T_ref)
+    wall = time.perf_counter() - t0
+    value = BATCH * T_ref * args.steps / wall
+    sample = (f"{args.steps} x {T_ref} timesteps of the {T_STEPS}-step window through bindsnet.models.DiehlAndCook2015.run "
+              f"(unmodified reference, torch {torch.__version__} CPU, {cores} threads), state reset between steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH, "timesteps": T_STEPS,
-                   "sample": f"each step is a {T_s}-timestep sample of the {T_STEPS}-step window (state reset between steps)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x {T_s} timesteps, dense restatement (oracle/snn_oracle.c), OpenMP {cores} cores"},
+                   "sample": f"each step is a {T_ref}-timestep sample of the {T_STEPS}-step window (state reset between steps)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_cpu_baseline:
+        try:
+            line["oracle_port"] = cpu_baseline(10.0)   # second, labelled leg: the C restatement on the same cores
+        except Exception as e:
+            line["oracle_port"] = {"unavailable": f"{type(e).__name__}: {e}"}
     emit(line)
 
 
@@ -387,7 +456,10 @@ def main():
                          "algorithmic_bytes_per_launch": per_launch_bytes},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            ref = reference_baseline(20.0)
+            port = cpu_baseline()
+            line["cpu_baseline"] = ref if ref is not None else port
+            line["cpu_baseline_port"] = port   # the C restatement of the same path on the same cores, for orientation
         emit(line)
     if world > 1:
         dist.barrier()

@@ -26,6 +26,7 @@ SNN_ERR_WORKSPACE = 4
 SNN_ERR_CUDA = 8
 SNN_ERR_NONBINARY = 16
 SNN_ERR_BARRIER = 32
+SNN_ERR_STRUCTURE = 64
 
 ERR_NAMES = {
     SNN_ERR_BAD_ARG: "malformed plan",
@@ -34,6 +35,7 @@ ERR_NAMES = {
     SNN_ERR_CUDA: "CUDA runtime error",
     SNN_ERR_NONBINARY: "Input layer received values outside {0,1}",
     SNN_ERR_BARRIER: "grid barrier timed out",
+    SNN_ERR_STRUCTURE: "a static weight matrix no longer has the diagonal / constant off-diagonal structure it was planned with",
 }
 
 

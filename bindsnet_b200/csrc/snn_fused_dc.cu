@@ -31,6 +31,8 @@
 
 #include "snn_common.cuh"
 
+int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t stream);
+
 namespace {
 
 constexpr int XR = 8;        // input-trace rows staged per CTA per step (samples with a candidate)
@@ -1339,6 +1341,8 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     // barrier words and per-slot dense flags are adjacent: one memset node
     if (cudaMemsetAsync(Q.bar, 0, WL.inS - WL.bar, stream) != cudaSuccess) return SNN_ERR_CUDA;
     if (prof && cudaMemsetAsync(Q.prof + 320 * NPROF + NPROF * 32 * 160 + 600, 0, 8 * sizeof(long long), stream) != cudaSuccess) return SNN_ERR_CUDA;
+    // the two static matrices are replaced by their constants: make sure they still have that structure
+    if (snn_verify_structure(net->conns[m.cEI], Q.n, Q.err, stream) != SNN_OK || snn_verify_structure(net->conns[m.cIE], Q.n, Q.err, stream) != SNN_OK) return SNN_ERR_CUDA;
     snn_dc_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
@@ -1419,6 +1423,6 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f   (slowest CTA %d, fastest %d)\n", "work w/o barrier", mn / T, sum / m.grid / T, mx / T, amx, amn);
         }
     }
-    if (launches) *launches = 2;  // pre-pass + persistent window kernel
+    if (launches) *launches = 4;  // 2 structure checks + pre-pass + persistent window kernel
     return SNN_OK;
 }

@@ -3,32 +3,32 @@
 // (reference wiring: bindsnet/models/models.py:94-244; per-step semantics: SURVEY.md App. A).
 //
 // Same partition as snn_fused_dc.cu — a CTA owns TJ columns (neurons of Ae and their partners in Ai)
-// for all B samples, W[:, tile] lives in shared memory for the whole window, Ae state in registers —
-// but the per-step grid dependency is served differently, because the round-1 profile showed the
-// step to be bound by synchronisation latency, not by work:
+// for all B samples, W[:, tile] lives in shared memory for the whole window, Ae state in registers,
+// one split-phase grid barrier per timestep — but the step is reorganised around what the round-1
+// profile showed: the step is bound by the latency of the grid exchange (about four L2 round trips:
+// scripts/exchange_bench.cu measures 1.45 us for barrier + data on 100-148 CTAs; message passing
+// between all pairs of CTAs is slower, 1.8-2.9 us) and by shared-memory bank conflicts of the
+// spike-gather, not by arithmetic.  Therefore:
 //
-//   * NO grid barrier, NO atomics in global memory.  What the grid has to exchange per step — per
-//     sample the one_spike arg-max key (nodes.py:1097-1105) and the number of Ai spikes (lateral
-//     inhibition, models.py:217-220) — travels as self-validating 64-bit MESSAGES: every CTA stores
-//     a header {step tag | number of entries} and its entries {step tag | sample | payload} into
-//     its own slot (relaxed 64-bit stores, single-copy atomic), warp 0 of every CTA polls all G
-//     headers and folds the (few) entries into shared-memory tables.  One L2 store + one L2 load
-//     on the critical path; no release/acquire fences because a word is only believed when it
-//     carries the step's tag, and no other global data is shared between CTAs.
-//   * The input traces the STDP post term needs (x_pre of the winner's sample, learning.py:407-417 /
+//   * a dedicated EXCHANGE WARP per CTA arrives at the barrier, polls it, and copies the exchanged
+//     per-sample words (one_spike arg-max key, nodes.py:1097-1105; number of Ai spikes = lateral
+//     inhibition, models.py:217-220) into shared-memory tables, while the compute warps spend the same
+//     time on everything of step t+1 that does not depend on the exchange: the early STDP AND the
+//     spike-gather of step t+1 for the column groups whose weights are already final;
+//   * the input traces the STDP post term needs (x_pre of the winner's sample, learning.py:407-417 /
 //     MCC_learning.py:267-299) are a pure function of the input spikes, so a pre-pass scans them for
-//     the whole window ([T,B,P] fp32); the window kernel only bulk-copies (cp.async.bulk + mbarrier)
-//     the rows of its own candidate samples, issued the moment a candidate appears, one exchange
-//     ahead of their use.
+//     the whole window ([T,B,P] fp32); the window kernel bulk-copies (cp.async.bulk + mbarrier) the
+//     rows of its own candidate samples the moment a candidate appears — before the barrier, not after;
 //   * Ai (LIFNodes, nodes.py:500-529) is event driven: a neuron at rest without input stays bitwise
 //     at rest (decay * (rest - rest) + rest == rest), only its refractory counter runs, and that is
-//     replayed in closed form at the end.  Neurons that ever received a spike live in a compact list.
-//   * Spike rasters and spike counts are written sparsely (the launch code clears the rasters).
-//   * Thread layout is column-group major (warp = 32 samples of ONE float4 column group), so TJ need
-//     not be a power of two: n = 1600 runs as 134 CTAs x 12 columns instead of 100 x 16.
+//     replayed in closed form at the end.  Neurons that ever received a spike live in a compact list;
+//   * spike rasters and spike counts are written sparsely (the launch code clears the rasters);
+//   * thread layout is column-group major (warp = 32 samples of ONE float4 column group), so early /
+//     late column groups are warp-uniform and TJ need not be a power of two: n = 1600 runs as
+//     134 CTAs x 12 columns instead of 100 x 16.
 //
-// Loop iteration t = [exchange of step t-1] [winners, traces, late STDP of t-1] [step t: gather,
-// Ae update, Ai list, candidates -> messages] [early STDP of t in the shadow of the exchange].
+// Loop iteration t = [exchange of step t-1 lands] [winners, traces, late STDP of t-1] [step t: gather of
+// the late groups, Ae update, Ai list, candidates -> atomics] [arrive] [early STDP of t, gather of t+1].
 //
 // Arithmetic and summation orders are those of snn_phases.cuh / oracle/snn_oracle.c (one fp32
 // rounding per reference op, ascending index sums), so results are bit-identical to the generic
@@ -42,13 +42,13 @@
 
 #include "snn_common.cuh"
 
+int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t stream);
+
 namespace {
 
 constexpr int XR = 8;        // input-trace rows staged per CTA and step (samples with a candidate)
 constexpr int EV_CAP = 32;   // staged events per sample and step; longer lists take the slow path
 constexpr int NPROF = 16;
-constexpr int NHMAX = 5;     // headers polled per lane of warp 0: grids up to 160 CTAs
-constexpr int BIGX = 96;     // more entries than this in one step: the whole CTA reads them
 constexpr unsigned AI_NONE = 0xFFFFu;
 
 struct F2Params {
@@ -61,7 +61,6 @@ struct F2Params {
     int32_t liE;              // index of Ae in the user's layer list (enters the tie-break hash)
     int32_t G;                // CTAs of the window kernel
     int32_t nrep;             // entries of the inhibition table rep[0..nrep]
-    int32_t ecap;             // message entries per CTA and step
     uint32_t o_W, o_tx, o_ev, o_inT, o_xrow, o_rep, o_theta, o_live, o_tab, o_ai, o_misc;  // smem byte offsets
     uint32_t seed, step_offset;
     uint32_t *inS;            // [T+1][B][SW]  slot t = spikes of step t-1: bit i of sample b
@@ -71,9 +70,12 @@ struct F2Params {
     float *xtr;               // [T][B][P] input traces of every step (pre-pass scan), or NULL
     float *rep;               // [nrep+1] m-fold sequential sums of the Ai->Ae weight
     unsigned int *sisum0;     // [B] Ai spikes of step -1
-    unsigned long long *hdr;  // [2][G] message headers, by step parity
-    unsigned long long *ent;  // [2][G][ecap] message entries
+    unsigned long long *win;  // [3][B] one_spike arg-max keys, slot t % 3
+    unsigned int *sisum;      // [3][B] Ai spike counts, slot t % 3
+    unsigned int *bar;        // grid barrier: monotonic arrival counter
     int32_t *err;
+    int32_t dbg;              // profiling only (env SNN_B200_DEBUG): 1 no slot prefetch, 2 no early STDP, 4 no gather ahead,
+                              // 8 no trace-row staging, 16 no barrier wait — results invalid
     long long *prof;          // profiling only (env SNN_B200_PROF): [G][NPROF] phase cycles of thread 0
 };
 
@@ -104,64 +106,52 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
-// ---- messages -------------------------------------------------------------------------------
-// header: tag[63:48] | number of entries[31:0]
-// entry : tag[63:48] | kind[47] | sample[46:39] | payload
-//   kind 1 (candidate): hash31[38:8] | column within the sender's tile[7:0]   (nodes.py:1097-1105)
-//   kind 0 (Ai spikes): count[7:0]                                             (models.py:217-220)
-// Steps t and t+2 share a slot; tags differ for any two steps less than 131070 apart.
-__device__ __forceinline__ uint32_t msg_tag(int t) { return (uint32_t)((t >> 1) % 65535) + 1u; }
-__device__ __forceinline__ unsigned long long msg_cand(uint32_t tag, int b, uint32_t hash, int col) {
-    return ((unsigned long long)tag << 48) | (1ull << 47) | ((unsigned long long)b << 39) |
-           ((unsigned long long)(hash & 0x7fffffffu) << 8) | (unsigned long long)col;
-}
-__device__ __forceinline__ unsigned long long msg_ai(uint32_t tag, int b, int count) {
-    return ((unsigned long long)tag << 48) | ((unsigned long long)b << 39) | (unsigned long long)count;
+__device__ __forceinline__ void bar_group(int id, int count) {   // named barrier among `count` threads
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 struct Misc2 {  // small per-step scratch (shared memory)
     uint64_t mbar_in[2];    // staged spike lists / pixel masks, by buffer
-    uint64_t mbar_x;        // staged input-trace rows of the step's candidate samples
-    uint64_t pad_;
-    uint32_t wl[XR];        // winners of the step being finalised: column << 16 | sample << 8 | staged row slot (0xff: none)
+    uint64_t mbar_x[2];     // staged input-trace rows of a step's candidate samples, by step parity
+    uint32_t wl[8][XR];     // per column group: winners of the step being finalised: column << 16 | sample << 8 | staged row slot (0xff: none)
     uint32_t nz4[8][8];     // per column group: samples with a non-zero Ae trace in that group
     uint32_t wmask[32][8];  // winners of the step being finalised: per column, bit mask over samples
     int cnt[2][32];         // candidates per column (theta update), by step parity
     int candb[2][XR];       // samples whose input-trace row is staged in xrow, by step parity
     int ncand[2];           // samples with a candidate in this tile (by step parity)
     uint32_t candgrp[2];    // column groups holding a candidate (by step parity)
-    uint32_t colwin;        // bit j: column j has a winner in the step being finalised
-    int nwl;                // number of winners of the step being finalised
-    int nlive;              // live (sample, column group) pairs, listed in live[]
+    uint32_t colwin[8];     // per column group: bit c: column 4g+c has a winner in the step being finalised
+    int nwl[8];             // per column group: number of winners of the step being finalised
+    int nlive[8];           // per column group: samples with a non-zero trace, listed in live[g * Bp ...]
     int nact;               // entries of the Ai list
-    int nent;               // message entries written this step
-    int bigx;               // entries of a large exchange (read by the whole CTA), else 0
+    int nact_snap;          // ... at the last step boundary: what the list pass of the running step covers
     int abort;              // exchange time-out: leave the time loop
     int denseflag[2];       // staged slot (by buffer) holds a sample whose event list overflowed EV_CAP
-    uint16_t hcnt[32 * NHMAX];  // large exchange: entries per sender
-    long long pc[NPROF];    // phase timers of thread 0 (profiling variant only)
+    long long pc[NPROF];    // phase timers (profiling variant only)
 };
 static_assert(offsetof(Misc2, wl) % 16 == 0 && offsetof(Misc2, nz4) % 16 == 0 && offsetof(Misc2, wmask) % 16 == 0, "Misc2: 16-byte rows");
 
 struct SmemLayout2 { size_t W, tx, ev, inT, xrow, rep, theta, live, tab, ai, misc, total; };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline int ev_count_bytes(int B) { return (int)al16(2 * (size_t)(B + 8)); }  // u16 count[B], then [B] = dense flag
+// One event-list block (one slot): u16 count[B] (+ 8 spare, padded to 16 bytes), then the ascending pixel
+// lists in CHUNK-MAJOR order — chunk c (list positions 4c..4c+3) of all samples back to back, 8 bytes per
+// (chunk, sample) — so that the 32 samples of a warp read consecutive words (no bank conflicts).
+__host__ __device__ inline int ev_count_bytes(int B) { return (int)al16(2 * (size_t)(B + 8)); }
 __host__ __device__ inline int ev_block_bytes(int B) { return ev_count_bytes(B) + 2 * B * EV_CAP; }
+__host__ __device__ inline int ev_pos(int B, int b, int k) { return ((k >> 2) * B + b) * 4 + (k & 3); }   // u16 index behind the counts
 __host__ __device__ inline int tile_stride(int TJ) { return ((TJ / 4) & 1) ? TJ : TJ + 4; }  // odd number of 16-byte chunks per row
-// tab region: keyT u64 [2][Bp] | isumT u32 [2][Bp] | aispk u32 [2][Bp] | candstamp u32 [Bp] | candslot i32 [Bp]
-__host__ __device__ inline size_t tab_bytes(int Bp) { return (size_t)Bp * (16 + 8 + 8 + 4 + 4); }
-// ai region: v f32 [cap] | rc f32 [cap] | id u16 [cap] | in u16 [cap] | idxmap u16 [cap] | fl u8 [cap]
-__host__ __device__ inline size_t ai_bytes(int cap) { return al16((size_t)cap * (4 + 4 + 2 + 2 + 2 + 1)); }
+// tab region: keyT u64 [2][Bp] | isumT u32 [2][Bp] | aispk u32 [2][Bp] | candstamp u32 [2][Bp] | candslot i32 [2][Bp]
+__host__ __device__ inline size_t tab_bytes(int Bp) { return (size_t)Bp * (16 + 8 + 8 + 8 + 8); }
+// ai region: v f32 [cap] | rc f32 [cap] | id u16 [cap] | claim u16 [2][cap] | map u16 [cap] | fl u8 [cap]
+__host__ __device__ inline size_t ai_bytes(int cap) { return al16((size_t)cap * (4 + 4 + 2 + 4 + 2 + 1)); }
 __host__ __device__ inline SmemLayout2 smem_layout2(int P, int TJ, int B, int Bp, int BW, int nrep) {
     SmemLayout2 L;
     size_t o = 0;
@@ -169,7 +159,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int P, int TJ, int B, int Bp
     L.tx = o; o += al16(sizeof(float) * (size_t)Bp * TJ);
     L.ev = o; o += 2 * al16((size_t)ev_block_bytes(B));
     L.inT = o; o += al16(sizeof(uint32_t) * 2 * (size_t)P * BW);
-    L.xrow = o; o += al16(sizeof(float) * (size_t)XR * P);
+    L.xrow = o; o += al16(sizeof(float) * 2 * (size_t)XR * P);   // by step parity
     L.rep = o; o += al16(sizeof(float) * (size_t)(nrep + 1));
     L.theta = o; o += al16(sizeof(float) * 64);
     L.live = o; o += al16(sizeof(uint16_t) * (size_t)Bp * (TJ / 4));
@@ -189,47 +179,49 @@ struct PassCtx2 {
     const unsigned char *evb;
     const uint16_t *live;
     Misc2 *M;
-    int P, B, evblk, cntb, WS;
+    int P, B, Bp, evblk, cntb, WS;
     int pre_on, has_clamp;
     float dts, wmin, wmax, nu1;
 };
 
-// STDP of one step in list form on the column groups selected by `groups` (MCC_learning.py:234-299,
-// learning.py:390-420): the work items are (live (sample, group) pair, event of that sample).  Several
-// samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel owns the
-// row (no atomics), sums the traces of all of them in ascending sample order (the oracle's order) and
+// STDP of one step in list form on ONE column group c4 (MCC_learning.py:234-299, learning.py:390-420), run by
+// the nthr0 threads that own the group: the work items are (live sample of the group, event of that sample).
+// Several samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel owns
+// the row (no atomics), sums the traces of all of them in ascending sample order (the oracle's order) and
 // rewrites the group's 4 weights:  w - U*dt [+ x_pre*nu1*dt for a winner column], clamp.
-// `colwin` != 0 (late pass): columns with a winner get their post term here; rows this pass does not
-// touch get it from post_rows().  Threads tid0 < 0 do not take part.
-constexpr int EVH = 16;  // list slots enumerated per pair and round
+// `gwin` != 0 (late pass): columns with a winner get their post term here; rows this pass does not touch
+// get it from post_rows2().
+constexpr int EVH = 16;  // list slots enumerated per live sample and round
 template <int CG, int BW>
-__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, uint32_t groups, uint32_t colwin, int tid0, int nthr0) {
+__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const float *xrow, int tid0, int nthr0) {
     const PassCtx2 c_ = *cx;
-    const int P = c_.P, WS = c_.WS;
+    const int P = c_.P, WS = c_.WS, B = c_.B;
     const Misc2 &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
     const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
-    const int total = M.nlive * EVH;
-    if (tid0 < 0) return;
+    const uint16_t *lv = c_.live + c4 * c_.Bp;
+    const int total = M.nlive[c4] * EVH;
+    uint32_t z[BW];
+    {
+        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w;
+        if (BW == 8) { const uint4 z1 = *(const uint4 *)&M.nz4[c4][4]; z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
+    }
     #pragma unroll 1
     for (int idx = tid0; idx < total; idx += nthr0) {
-        const int lp = c_.live[idx / EVH];
-        const int bb = lp / CG, c4 = lp % CG;
-        if (!((groups >> c4) & 1u)) continue;
+        const int bb = lv[idx / EVH];
         const int cnt = min((int)ec[bb], EV_CAP);
         #pragma unroll 1
         for (int k = idx % EVH; k < cnt; k += EVH) {
-            const int i = el[bb * EV_CAP + k];
+            const int i = el[ev_pos(B, bb, k)];
             uint32_t a[BW];
             {
                 const uint4 q0 = cT[i * (BW / 4)];
-                const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
-                a[0] = q0.x & z0.x; a[1] = q0.y & z0.y; a[2] = q0.z & z0.z; a[3] = q0.w & z0.w;
+                a[0] = q0.x & z[0]; a[1] = q0.y & z[1]; a[2] = q0.z & z[2]; a[3] = q0.w & z[3];
                 if (BW == 8) {
                     const uint4 q1 = cT[i * (BW / 4) + 1];
-                    const uint4 z1 = *(const uint4 *)&M.nz4[c4][4];
-                    a[BW - 4] = q1.x & z1.x; a[BW - 3] = q1.y & z1.y; a[BW - 2] = q1.z & z1.z; a[BW - 1] = q1.w & z1.w;
+                    a[BW - 4] = q1.x & z[BW - 4]; a[BW - 3] = q1.y & z[BW - 3]; a[BW - 2] = q1.z & z[BW - 2]; a[BW - 1] = q1.w & z[BW - 1];
                 }
             }
             // owner of row i in this group = the lowest live sample spiking at pixel i
@@ -255,16 +247,15 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, uint32_t gro
             const float4 w4 = *(const float4 *)wp;
             float wv[4] = {w4.x, w4.y, w4.z, w4.w};
             const float Uv[4] = {U0, U1, U2, U3};
-            const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
             #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float w = wv[c];
                 w = w - Uv[c] * c_.dts;  // x * 1.0f is exact: the classic rule's missing dt factor is dts = 1
                 if ((gwin >> c) & 1u) {  // the column's single winner (fast late pass): post term
-                    uint32_t e = M.wl[0];
+                    uint32_t e = M.wl[c4][0];
                     #pragma unroll 1
-                    for (int k2 = 1; k2 < M.nwl; ++k2) if ((M.wl[k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[k2];
-                    const float V = 0.0f + c_.xrow[(e & 0xffu) * P + i] * c_.nu1;
+                    for (int k2 = 1; k2 < M.nwl[c4]; ++k2) if ((M.wl[c4][k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[c4][k2];
+                    const float V = 0.0f + xrow[(e & 0xffu) * P + i] * c_.nu1;
                     w = w + V * c_.dts;
                 }
                 if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
@@ -275,37 +266,35 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, uint32_t gro
     }
 }
 
-// Post term of the fast late pass for the rows stdp_list2 did not touch: per winner (column, staged
-// row): w + x_pre[b,i]*nu1*dt, clamp (MCC_learning.py:267-299, 86-110).  A row of the winner's column
-// group was handled by the list pass iff a live sample of that group spiked at its pixel.
+// Post term of the fast late pass of column group c4 for the rows stdp_list2 did not touch: per winner
+// (column, staged row): w + x_pre[b,i]*nu1*dt, clamp (MCC_learning.py:267-299, 86-110).  A row was handled
+// by the list pass iff a live sample of the group spiked at its pixel.
 template <int CG, int BW>
-__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int nwl) {
+__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int nwl, const float *xrow, int tid0, int nthr0) {
     const PassCtx2 c_ = *cx;
     const int P = c_.P, WS = c_.WS;
     const Misc2 &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    uint32_t z[BW];
+    {
+        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w;
+        if (BW == 8) { const uint4 z1 = *(const uint4 *)&M.nz4[c4][4]; z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
+    }
     #pragma unroll 1
-    for (int k = 0; k < nwl; ++k) {
-        const uint32_t e = M.wl[k];
-        const int col = (int)(e >> 16), c4 = col >> 2;
-        const float *xr = c_.xrow + (e & 0xffu) * P;
-        uint32_t z[BW];
-        {
-            const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
-            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w;
-            if (BW == 8) { const uint4 z1 = *(const uint4 *)&M.nz4[c4][4]; z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
+    for (int i = tid0; i < P; i += nthr0) {
+        if (c_.pre_on) {
+            const uint4 q0 = cT[i * (BW / 4)];
+            uint32_t any = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
+            if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
+            if (any) continue;  // done by the list pass
         }
         #pragma unroll 1
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            if (c_.pre_on) {
-                const uint4 q0 = cT[i * (BW / 4)];
-                uint32_t any = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
-                if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
-                if (any) continue;  // done by the list pass
-            }
-            float *wp = c_.W + i * WS + col;
+        for (int k = 0; k < nwl; ++k) {   // distinct columns
+            const uint32_t e = M.wl[c4][k];
+            float *wp = c_.W + i * WS + (e >> 16);
             float w = *wp;
-            const float V = 0.0f + xr[i] * c_.nu1;
+            const float V = 0.0f + xrow[(e & 0xffu) * P + i] * c_.nu1;
             w = w + V * c_.dts;
             if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
             *wp = w;
@@ -313,78 +302,73 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int nwl) {
     }
 }
 
-// STDP of one step in row form, general: one row loop per selected column group, pre and post term of a
-// column applied together (pre, post, clamp — the reference's order).  Used for slots with an overflowed
-// event list, more than XR winners, two winners in one column, a winner whose trace row is not staged.
+// STDP of one step of column group c4 in row form, general: pre and post term of a column applied together
+// (pre, post, clamp — the reference's order).  Used for slots with an overflowed event list, more than XR
+// winners, two winners in one column, a winner whose trace row is not staged.
 // `cand` = staged samples (rows of xrow), `xsrc` = the step's input traces in global memory.
 template <int CG, int BW>
-__device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, uint32_t groups, uint32_t colwin, const int *cand, int ns,
-                                        const float *xsrc) {
+__device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const int *cand, int ns, const float *xsrc,
+                                        const float *xrow, int tid0, int nthr0) {
     const PassCtx2 c_ = *cx;
     const int P = c_.P, WS = c_.WS, TJ = 4 * CG;
     const Misc2 &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    const uint4 z0 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
     #pragma unroll 1
-    for (uint32_t lg = groups; lg; lg &= lg - 1) {
-        const int c4 = __ffs(lg) - 1;
-        const uint32_t gwin = (colwin >> (4 * c4)) & 0xFu;
-        const uint4 z0 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][0] : make_uint4(0, 0, 0, 0);
-        #pragma unroll 1
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            uint32_t m[BW];
-            const uint4 q0 = cT[i * (BW / 4)];
-            m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
-            uint32_t anym = m[0] | m[1] | m[2] | m[3];
-            if (BW == 8) {
-                const uint4 q1 = cT[i * (BW / 4) + 1];
-                const uint4 z1 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
-                m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
-                anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+    for (int i = tid0; i < P; i += nthr0) {
+        uint32_t m[BW];
+        const uint4 q0 = cT[i * (BW / 4)];
+        m[0] = q0.x & z0.x; m[1] = q0.y & z0.y; m[2] = q0.z & z0.z; m[3] = q0.w & z0.w;
+        uint32_t anym = m[0] | m[1] | m[2] | m[3];
+        if (BW == 8) {
+            const uint4 q1 = cT[i * (BW / 4) + 1];
+            const uint4 z1 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
+            m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
+            anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+        }
+        const bool pre_t = anym != 0u;
+        if (!(pre_t || gwin)) continue;
+        float U[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pre_t) {
+            #pragma unroll 1
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = m[g];
+                while (mm) {
+                    const int bb = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 t4 = *(const float4 *)(c_.tx + bb * TJ + 4 * c4);
+                    U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                }
             }
-            const bool pre_t = anym != 0u;
-            if (!(pre_t || gwin)) continue;
-            float U[4] = {0.f, 0.f, 0.f, 0.f};
-            if (pre_t) {
+        }
+        float *wp = c_.W + i * WS + 4 * c4;
+        const float4 w4 = *(const float4 *)wp;
+        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        #pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            const bool post_t = (gwin >> c) & 1u;
+            float w = wv[c];
+            if (pre_t) w = w - U[c] * c_.dts;
+            if (post_t) {
+                float V = 0.0f;
                 #pragma unroll 1
-                for (int g = 0; g < BW; ++g) {
-                    uint32_t mm = m[g];
+                for (int g = 0; g < BW; ++g) {  // winners of this column, ascending sample order
+                    uint32_t mm = M.wmask[4 * c4 + c][g];
                     while (mm) {
                         const int bb = g * 32 + __ffs(mm) - 1;
                         mm &= mm - 1;
-                        const float4 t4 = *(const float4 *)(c_.tx + bb * TJ + 4 * c4);
-                        U[0] = U[0] + t4.x; U[1] = U[1] + t4.y; U[2] = U[2] + t4.z; U[3] = U[3] + t4.w;
+                        int sl = -1;
+                        for (int q = 0; q < ns; ++q) if (cand[q] == bb) sl = q;
+                        const float xv = sl >= 0 ? xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i);
+                        V = V + xv * c_.nu1;
                     }
                 }
+                w = w + V * c_.dts;
             }
-            float *wp = c_.W + i * WS + 4 * c4;
-            const float4 w4 = *(const float4 *)wp;
-            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-            #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const bool post_t = (gwin >> c) & 1u;
-                float w = wv[c];
-                if (pre_t) w = w - U[c] * c_.dts;
-                if (post_t) {
-                    float V = 0.0f;
-                    #pragma unroll 1
-                    for (int g = 0; g < BW; ++g) {  // winners of this column, ascending sample order
-                        uint32_t mm = M.wmask[4 * c4 + c][g];
-                        while (mm) {
-                            const int bb = g * 32 + __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            int sl = -1;
-                            for (int q = 0; q < ns; ++q) if (cand[q] == bb) sl = q;
-                            const float xv = sl >= 0 ? c_.xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i);
-                            V = V + xv * c_.nu1;
-                        }
-                    }
-                    w = w + V * c_.dts;
-                }
-                if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
-                wv[c] = w;
-            }
-            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+            wv[c] = w;
         }
+        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
     }
 }
 
@@ -414,17 +398,19 @@ __device__ __forceinline__ float refrac_replay(float rc, float dt, int T) {
 }
 
 // CG: float4 column groups per CTA (TJ = 4 CG columns); BW: 32-bit words of a per-pixel sample mask
-// (4 -> B <= 128).  Threads = Bp * CG, Bp = B rounded up to a multiple of 32: thread (cg, b).
+// (4 -> B <= 128).  Threads = Bp * CG compute threads, thread (cg, b), Bp = B rounded up to a multiple
+// of 32, plus one exchange warp.  The Bp threads of a column group form a pipeline of their own (named
+// barrier 2 + cg): the CTA-wide barriers are the two per step that frame the exchange.
 // VAR bit 1: phase timers compiled in.
 template <int CG, int BW, int VAR>
-__global__ void __launch_bounds__((32 * BW * CG < 1024 ? 32 * BW * CG : 1024), 1)
+__global__ void __launch_bounds__((32 * BW * CG + 32 < 1024 ? 32 * BW * CG + 32 : 1024), 1)
 snn_dc2_window(const __grid_constant__ F2Params Q) {
     constexpr bool PROFV = (VAR & 2) != 0;
     constexpr int TJ = 4 * CG;
     constexpr int WS = (CG & 1) ? TJ : TJ + 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int B = Q.B, Bp = Q.Bp, P = Q.P, n = Q.n, T = Q.T;
-    const int G = (int)gridDim.x;
+    const unsigned int G = gridDim.x;
     float *W = (float *)(smem + Q.o_W);
     float *tx = (float *)(smem + Q.o_tx);
     unsigned char *evb = smem + Q.o_ev;
@@ -433,28 +419,33 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     float *rep = (float *)(smem + Q.o_rep);
     float *theta_s = (float *)(smem + Q.o_theta);   // [32] theta, [32] thresh + decayed theta
     float *thr_s = theta_s + 32;
-    uint16_t *live = (uint16_t *)(smem + Q.o_live);
-    unsigned long long *keyT = (unsigned long long *)(smem + Q.o_tab);  // [2][Bp]
-    uint32_t *isumT = (uint32_t *)(keyT + 2 * Bp);                      // [2][Bp]
-    uint32_t *aispk = isumT + 2 * Bp;                                   // [2][Bp] bit col: Ai (b, col) spiked in that step
-    uint32_t *candstamp = aispk + 2 * Bp;                               // [Bp] step + 1 of the sample's last staged row
-    int *candslot = (int *)(candstamp + Bp);                            // [Bp] its slot in xrow (-1: not staged)
+    uint16_t *live = (uint16_t *)(smem + Q.o_live);  // [CG][Bp] live samples per column group
+    unsigned long long *keyT = (unsigned long long *)(smem + Q.o_tab);  // [2][Bp] one_spike arg-max key of a step, by step parity
+    uint32_t *isumT = (uint32_t *)(keyT + 2 * Bp);                      // [2][Bp] Ai spikes of a step
+    uint32_t *aispk = isumT + 2 * Bp;                                   // [2][Bp] bit col: Ai (b, col) of this tile spiked in that step
+    uint32_t *candstamp = aispk + 2 * Bp;                               // [2][Bp] by step parity: step + 1 of the sample's last staged row
+    int *candslot = (int *)(candstamp + 2 * Bp);                        // [2][Bp] its slot in xrow (-1: not staged)
     const int aicap = Bp * TJ;
     float *ai_v = (float *)(smem + Q.o_ai);
     float *ai_rc = ai_v + aicap;
     uint16_t *ai_id = (uint16_t *)(ai_rc + aicap);      // b * TJ + col
-    uint16_t *ai_in = ai_id + aicap;                     // step at which the partner Ae neuron's spike arrives
-    uint16_t *ai_map = ai_in + aicap;                    // (b * TJ + col) -> list entry, AI_NONE
-    uint8_t *ai_fl = (uint8_t *)(ai_map + aicap);        // bit 0: refractory counter still the undisturbed one; bit 1: spiked last step
+    uint16_t *ai_claim = ai_id + aicap;                  // [2][cap] by step parity: step in which the neuron's owner thread (not the
+                                                         // list pass) runs it
+    uint16_t *ai_map = ai_claim + 2 * aicap;             // (b * TJ + col) -> list entry, AI_NONE
+    uint8_t *ai_fl = (uint8_t *)(ai_map + aicap);        // bit 0: refractory counter still the undisturbed one; bit 1: spiked last
+                                                         // step; bit 2: partner spiked at step -1 (input at step 0)
     Misc2 &M = *(Misc2 *)(smem + Q.o_misc);
     __shared__ PassCtx2 s_cx;
 
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int cg = tid / Bp, b = tid - cg * Bp;   // state ownership: sample b, neurons jc..jc+3 (warp-uniform cg)
+    const int NC = Bp * CG;                        // compute threads; the warp above them is the exchange warp
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool isx = tid >= NC;
+    const int cg = isx ? 0 : tid / Bp, b = isx ? Bp : tid - cg * Bp;   // state ownership: sample b, neurons jc..jc+3 (warp-uniform cg)
     const int j0 = blockIdx.x * TJ;
     const int jc = j0 + 4 * cg;
-    const bool act = b < B && jc < n;
-    const snn_layer_t &E = Q.E, &I = Q.I, &X = Q.X;
+    const bool act = !isx && b < B && jc < n;
+    const int gbar = 2 + cg;                       // the column group's named barrier
+    const snn_layer_t &E = Q.E, &I = Q.I;
     const snn_conn_t &C = Q.C;
     const bool stdp = C.rule >= SNN_RULE_POSTPRE;
     const bool pre_on = stdp && C.nu0 != 0.0f, post_on = stdp && C.nu1 != 0.0f;
@@ -467,42 +458,60 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     long long *pc = M.pc;
     long long pt = clock64();
     #define PROF(k) { if (PROFV && tid == 0) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
+    #define PROFX(k) { if (PROFV && tid == NC) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
 
     // ---- prologue: W tile, theta, inhibition table, tables, Ai list, state registers -----------
-    #pragma unroll 1
-    for (int idx = tid; idx < (P + 1) * TJ; idx += nthr) {
-        const int i = idx / TJ, jj = idx - i * TJ;
-        W[i * WS + jj] = (i < P && j0 + jj < n) ? C.w[(size_t)i * n + j0 + jj] : 0.0f;
+    {
+        constexpr int U = 8;
+        const int total = (P + 1) * TJ, nthr = blockDim.x;
+        #pragma unroll 1
+        for (int base = 0; base < total; base += U * nthr) {
+            float v[U];
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * nthr + tid, i = idx / TJ, jj = idx - i * TJ;
+                v[u] = (idx < total && i < P && j0 + jj < n) ? __ldg(C.w + (size_t)i * n + j0 + jj) : 0.0f;
+            }
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * nthr + tid, i = idx / TJ, jj = idx - i * TJ;
+                if (idx < total) W[i * WS + jj] = v[u];
+            }
+        }
     }
     #pragma unroll 1
-    for (int jj = tid; jj < 32; jj += nthr) {
+    for (int jj = tid; jj < 32; jj += blockDim.x) {
         const float th = (jj < TJ && j0 + jj < n) ? E.theta[j0 + jj] : 0.0f;
         theta_s[jj] = th;
         thr_s[jj] = E.thresh + (E.learning ? th * E.theta_decay : th);   // nodes.py:1078-1079, 1088
     }
     #pragma unroll 1
-    for (int k = tid; k <= Q.nrep; k += nthr) rep[k] = Q.rep[k];
+    for (int k = tid; k <= Q.nrep; k += blockDim.x) rep[k] = Q.rep[k];
     #pragma unroll 1
-    for (int k = tid; k < 2 * Bp; k += nthr) { keyT[k] = 0ull; isumT[k] = 0u; aispk[k] = 0u; }
+    for (int k = tid; k < 2 * Bp; k += blockDim.x) { keyT[k] = 0ull; isumT[k] = 0u; aispk[k] = 0u; }
     #pragma unroll 1
-    for (int k = tid; k < Bp; k += nthr) { candstamp[k] = 0u; candslot[k] = -1; }
+    for (int k = tid; k < 2 * Bp; k += blockDim.x) { candstamp[k] = 0u; candslot[k] = -1; }
+    {
+        uint32_t *m32 = (uint32_t *)ai_map;   // aicap is even (Bp is a multiple of 32)
+        #pragma unroll 1
+        for (int k = tid; k < aicap / 2; k += blockDim.x) m32[k] = 0xFFFFFFFFu;
+    }
     #pragma unroll 1
-    for (int k = tid; k < aicap; k += nthr) ai_map[k] = (uint16_t)AI_NONE;
+    for (int k = tid; k < 64; k += blockDim.x) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
     #pragma unroll 1
-    for (int k = tid; k < 64; k += nthr) { (&M.nz4[0][0])[k] = 0; (&M.cnt[0][0])[k] = 0; }
-    #pragma unroll 1
-    for (int k = tid; k < 32 * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
+    for (int k = tid; k < 32 * 8; k += blockDim.x) (&M.wmask[0][0])[k] = 0;
     if (tid == 0) {
         mbar_init(&M.mbar_in[0], 1);
         mbar_init(&M.mbar_in[1], 1);
-        mbar_init(&M.mbar_x, 1);
+        mbar_init(&M.mbar_x[0], 1);
+        mbar_init(&M.mbar_x[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.abort = 0; M.nwl = 0; M.nlive = 0;
-        M.nact = 0; M.nent = 0; M.bigx = 0;
+        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.abort = 0; M.nact = 0;
+        for (int g = 0; g < 8; ++g) { M.colwin[g] = 0; M.nwl[g] = 0; M.nlive[g] = 0; }
         M.denseflag[0] = Q.dense[0]; M.denseflag[1] = T >= 1 ? Q.dense[1] : 0;
         for (int k = 0; k < NPROF; ++k) M.pc[k] = 0;
         s_cx.W = W; s_cx.tx = tx; s_cx.xrow = xrow; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.M = &M;
-        s_cx.P = P; s_cx.B = B; s_cx.evblk = evblk; s_cx.cntb = cntb; s_cx.WS = WS;
+        s_cx.P = P; s_cx.B = B; s_cx.Bp = Bp; s_cx.evblk = evblk; s_cx.cntb = cntb; s_cx.WS = WS;
         s_cx.pre_on = pre_on; s_cx.has_clamp = C.has_clamp;
         s_cx.dts = dts; s_cx.wmin = C.wmin; s_cx.wmax = C.wmax; s_cx.nu1 = C.nu1;
     }
@@ -511,38 +520,58 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     float vE[4], rE[4], xE[4];
     uint32_t candE = 0, pend = 0, sEfin = 0;  // 4-bit masks over my neurons
     uint32_t vm = 0;                          // my neurons that exist (column < n)
-    #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const bool ok = act && jc + c < n;
-        if (ok) vm |= 1u << c;
-        const size_t k = ok ? (size_t)b * n + jc + c : 0;
-        vE[c] = ok ? E.v[k] : 0.0f; rE[c] = ok ? E.refrac_count[k] : 0.0f;
-        xE[c] = (ok && E.traces) ? E.x[k] : 0.0f;
-        if (ok) {
-            // Ai: a neuron that is not exactly at rest, is refractory, or whose partner spiked at step -1
-            // starts in the list (nodes.py:500-529); everything else is at rest until a spike arrives
-            const float v0 = I.v[k], r0 = I.refrac_count[k];
-            const bool sE0 = E.s[k] != 0, sI0 = I.s[k] != 0;
-            if (sI0) atomicOr(&aispk[Bp + b], 1u << (4 * cg + c));   // parity 1 = step -1
-            if (v0 != I.rest || r0 > 0.0f || sE0) {
-                const int e = atomicAdd(&M.nact, 1);
-                ai_v[e] = v0; ai_rc[e] = r0; ai_id[e] = (uint16_t)(b * TJ + 4 * cg + c);
-                ai_in[e] = sE0 ? (uint16_t)0 : (uint16_t)AI_NONE; ai_fl[e] = 0;
-                ai_map[b * TJ + 4 * cg + c] = (uint16_t)e;
+    {
+        const bool vec = act && (n & 3) == 0 && jc + 3 < n;
+        const size_t k0 = act ? (size_t)b * n + jc : 0;
+        float v0[4], r0[4];
+        uint32_t sE0 = 0, sI0 = 0;
+        if (vec) {
+            const float4 a = *(const float4 *)(E.v + k0), r = *(const float4 *)(E.refrac_count + k0);
+            const float4 x = E.traces ? *(const float4 *)(E.x + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 iv = *(const float4 *)(I.v + k0), ir = *(const float4 *)(I.refrac_count + k0);
+            const uint32_t es = *(const uint32_t *)(E.s + k0), is = *(const uint32_t *)(I.s + k0);
+            vE[0] = a.x; vE[1] = a.y; vE[2] = a.z; vE[3] = a.w; rE[0] = r.x; rE[1] = r.y; rE[2] = r.z; rE[3] = r.w;
+            xE[0] = x.x; xE[1] = x.y; xE[2] = x.z; xE[3] = x.w;
+            v0[0] = iv.x; v0[1] = iv.y; v0[2] = iv.z; v0[3] = iv.w; r0[0] = ir.x; r0[1] = ir.y; r0[2] = ir.z; r0[3] = ir.w;
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) { if ((es >> (8 * c)) & 0xffu) sE0 |= 1u << c; if ((is >> (8 * c)) & 0xffu) sI0 |= 1u << c; }
+            vm = 0xFu;
+        } else {
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool ok = act && jc + c < n;
+                if (ok) vm |= 1u << c;
+                const size_t k = ok ? k0 + c : 0;
+                vE[c] = ok ? E.v[k] : 0.0f; rE[c] = ok ? E.refrac_count[k] : 0.0f;
+                xE[c] = (ok && E.traces) ? E.x[k] : 0.0f;
+                v0[c] = ok ? I.v[k] : I.rest; r0[c] = ok ? I.refrac_count[k] : 0.0f;
+                if (ok && E.s[k]) sE0 |= 1u << c;
+                if (ok && I.s[k]) sI0 |= 1u << c;
             }
         }
+        // Ai: a neuron that is not exactly at rest, is refractory, or whose partner spiked at step -1 starts
+        // in the list (nodes.py:500-529); everything else is at rest until a spike arrives
+        if (sI0) atomicOr(&aispk[Bp + b], sI0 << (4 * cg));   // parity 1 = step -1
+        #pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (((vm >> c) & 1u) && (v0[c] != I.rest || r0[c] > 0.0f || ((sE0 >> c) & 1u))) {
+                const int e = atomicAdd(&M.nact, 1);
+                ai_v[e] = v0[c]; ai_rc[e] = r0[c]; ai_id[e] = (uint16_t)(b * TJ + 4 * cg + c);
+                ai_claim[e] = (uint16_t)AI_NONE; ai_claim[aicap + e] = (uint16_t)AI_NONE; ai_fl[e] = ((sE0 >> c) & 1u) ? 4 : 0;
+                ai_map[b * TJ + 4 * cg + c] = (uint16_t)e;
+            }
     }
-    if (cg == 0 && b < B) isumT[Bp + b] = Q.sisum0[b];
-    if (act && stdp) *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
-    else if (b < Bp && cg < CG) *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!isx && cg == 0 && b < B) isumT[Bp + b] = Q.sisum0[b];
+    if (!isx) *(float4 *)(tx + b * TJ + 4 * cg) = (act && stdp) ? make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     bool livep = false;  // my (sample, column group) pair has a non-zero Ae trace
     if (act && stdp && (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)) {
         livep = true;
         atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
-        live[atomicAdd(&M.nlive, 1)] = (uint16_t)(b * CG + cg);
+        live[cg * Bp + atomicAdd(&M.nlive[cg], 1)] = (uint16_t)b;
     }
     const uint32_t bytesE = (uint32_t)Q.SB, bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
-    const int tid_pf = nthr > 32 ? 32 : 0;  // the thread that issues the slot prefetches
+    const int tid_pf = NC + 1;  // the thread that issues the slot prefetches (exchange warp)
     if (tid == tid_pf) {  // stage slot 0 (spikes of step -1) and slot 1 (spikes of step 0)
         mbar_arrive_expect_tx(&M.mbar_in[0], bytesE + bytesT);
         bulk_g2s(evb, Q.evS, bytesE, &M.mbar_in[0]);
@@ -552,7 +581,9 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         bulk_g2s(inT + P * BW, Q.inT + (size_t)P * BW, bytesT, &M.mbar_in[1]);
     }
     __syncthreads();
+    if (tid == 0) M.nact_snap = M.nact;
     PROF(0)  // prologue
+    if (PROFV && tid == NC) pt = clock64();
 
     // spike-gather of my 4 columns for the spikes of list block `blk` (slot `slot`):
     // p[c] = sum_{i in sX[b]} W[i][c], i ascending (topology.py:437-479)
@@ -560,10 +591,10 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
         const int cnt = ((const uint16_t *)blk)[b];
         if (cnt <= EV_CAP) {
-            const uint2 *l4 = (const uint2 *)(blk + cntb + b * (2 * EV_CAP));
+            const uint2 *l4 = (const uint2 *)(blk + cntb) + b;
             #pragma unroll 1
             for (int k = 0; k < cnt; k += 4) {
-                const uint2 q = l4[k >> 2];  // 4 pixel indices; tail padded with P (zero row)
+                const uint2 q = l4[(k >> 2) * B];  // 4 pixel indices; tail padded with P (zero row)
                 const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
                 const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
                 const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
@@ -578,168 +609,148 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         }
         return make_float4(p0, p1, p2, p3);
     };
+    // one LIFNodes.forward step of list entry e with input xin (nodes.py:500-529); spikes go to the exchange
+    auto ai_step = [&](int e, float xin, int t) {
+        float v = ai_v[e], rc = ai_rc[e];
+        uint32_t fl = ai_fl[e];
+        v = I.decay * (v - I.rest) + I.rest;
+        if (!(fl & 1u)) { if (rc > 0.0f) xin = 0.0f; rc = rc - I.dt; }   // undisturbed counter: <= 0 by construction
+        v = v + xin;
+        fl &= 1u;
+        if (v >= I.thresh) {
+            rc = I.refrac; v = I.reset; fl = 2u;
+            const int id = ai_id[e], sb_ = id / TJ, col = id - sb_ * TJ;
+            atomicOr(&aispk[(t & 1) * Bp + sb_], 1u << col);
+            atomicAdd(Q.sisum + (t % 3) * B + sb_, 1u);
+            if (I.rec_s) I.rec_s[((size_t)t * B + sb_) * n + j0 + col] = 1;
+            if (I.rec_count) atomicAdd(I.rec_count + (size_t)sb_ * n + j0 + col, 1);
+        }
+        ai_v[e] = v; ai_rc[e] = rc; ai_fl[e] = (uint8_t)fl;
+    };
 
-    unsigned long long *myent = Q.ent + (size_t)blockIdx.x * Q.ecap;          // + parity * G * ecap
-    const size_t entpar = (size_t)G * Q.ecap;
+    float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);   // currents of the step about to run, gathered ahead
+    bool havepre = false;
 
     // =====================================================================================
     for (int t = 0; t <= T; ++t) {
         const int buf = t & 1;                       // slot t = spikes of step t-1
         const unsigned char *cE = evb + buf * evblk;
         const int par = t & 1, ppar = par ^ 1;       // parity of step t / of step t-1
+        const int dense_nb = __ldg(Q.dense + (t + 1 <= T ? t + 1 : T));   // slot t+1 holds an overflowed event list (used in the shadow)
 
-        // ---- exchange of step t-1: warp 0 collects every CTA's message ---------------------------
-        if (t > 0 && warp == 0) {
-            const unsigned long long *H = Q.hdr + (size_t)ppar * G;
-            const uint32_t tag = msg_tag(t - 1);
-            unsigned long long h[NHMAX];
-            uint32_t need = 0;
-            #pragma unroll
-            for (int k = 0; k < NHMAX; ++k) if (lane + 32 * k < G) need |= 1u << k;
-            const long long t0 = clock64();
-            #pragma unroll 1
-            while (need) {
-                #pragma unroll
-                for (int k = 0; k < NHMAX; ++k) if ((need >> k) & 1u) h[k] = ld_relaxed_u64(H + lane + 32 * k);
-                #pragma unroll
-                for (int k = 0; k < NHMAX; ++k) if (((need >> k) & 1u) && (uint32_t)(h[k] >> 48) == tag) need &= ~(1u << k);
-                if (need && clock64() - t0 > 4000000000LL) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
-            }
-            uint32_t mine = 0;
-            #pragma unroll
-            for (int k = 0; k < NHMAX; ++k) if (lane + 32 * k < G && !((need >> k) & 1u)) mine += (uint32_t)h[k];
-            uint32_t total = mine;
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            if (total > BIGX) {  // rare (many simultaneous candidates, e.g. the first steps of fresh weights)
-                #pragma unroll
-                for (int k = 0; k < NHMAX; ++k) if (lane + 32 * k < G) M.hcnt[lane + 32 * k] = (uint16_t)h[k];
-                if (lane == 0) M.bigx = (int)total;
-            } else if (mine) {
-                #pragma unroll 1
-                for (int k = 0; k < NHMAX; ++k) {
-                    const int c = lane + 32 * k;
-                    if (c >= G) break;
-                    const int ne = (int)(uint32_t)h[k];
-                    const unsigned long long *ep = Q.ent + (size_t)ppar * entpar + (size_t)c * Q.ecap;
-                    #pragma unroll 1
-                    for (int e = 0; e < ne; ++e) {
-                        unsigned long long w;
-                        do { w = ld_relaxed_u64(ep + e); } while ((uint32_t)(w >> 48) != tag && clock64() - t0 < 4000000000LL);
-                        const int sb_ = (int)((w >> 39) & 0xffu);
-                        if (w & (1ull << 47)) {
-                            const unsigned long long key = ((unsigned long long)((uint32_t)((w >> 8) & 0x7fffffffu) | 0x80000000u) << 32) |
-                                                           (unsigned long long)(c * TJ + (int)(w & 0xffu));
-                            atomicMax(keyT + ppar * Bp + sb_, key);
-                        } else atomicAdd(isumT + ppar * Bp + sb_, (uint32_t)(w & 0xffu));
+        // ---- exchange of step t-1 lands: the exchange warp waits for the grid barrier and copies the
+        // per-sample words of slot (t-1) % 3 into the shared-memory tables of parity `ppar`
+        if (isx && t > 0) {
+            if (lane == 0) {
+                const unsigned int target = G * (unsigned int)t;
+                unsigned int spins = 0;
+                while ((int)(ld_relaxed_u32(Q.bar) - target) < 0 && !(Q.dbg & 16)) {
+                    if ((++spins & 0xfffffu) == 0) {   // ~ a second of polling: give up
+                        if (spins > (4u << 20)) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
                     }
                 }
+                asm volatile("fence.acquire.gpu;" ::: "memory");
             }
+            __syncwarp();
+            PROFX(10)  // barrier wait (exchange warp)
+            const int xs = (t - 1) % 3;
+            {   // all loads in flight together: one L2 round trip
+                unsigned long long kk[BW];
+                unsigned int ss[BW];
+                #pragma unroll
+                for (int u = 0; u < BW; ++u) {
+                    const int k = lane + 32 * u;
+                    kk[u] = k < B ? __ldcg(Q.win + xs * B + k) : 0ull;
+                    ss[u] = k < B ? __ldcg(Q.sisum + xs * B + k) : 0u;
+                }
+                #pragma unroll
+                for (int u = 0; u < BW; ++u) {
+                    const int k = lane + 32 * u;
+                    if (k < Bp) { keyT[ppar * Bp + k] = kk[u]; isumT[ppar * Bp + k] = ss[u]; }
+                }
+            }
+            PROFX(11)  // exchange read
         }
         __syncthreads();
         if (M.abort) return;
-        PROF(1)  // exchange wait
-        if (t > 0 && M.bigx) {  // large exchange: all warps read the entries
-            const uint32_t tag = msg_tag(t - 1);
-            const int nw = nthr >> 5;
-            #pragma unroll 1
-            for (int c = warp; c < G; c += nw) {
-                const int ne = M.hcnt[c];
-                const unsigned long long *ep = Q.ent + (size_t)ppar * entpar + (size_t)c * Q.ecap;
-                #pragma unroll 1
-                for (int e = lane; e < ne; e += 32) {
-                    unsigned long long w;
-                    const long long t0 = clock64();
-                    do { w = ld_relaxed_u64(ep + e); } while ((uint32_t)(w >> 48) != tag && clock64() - t0 < 4000000000LL);
-                    const int sb_ = (int)((w >> 39) & 0xffu);
-                    if (w & (1ull << 47)) {
-                        const unsigned long long key = ((unsigned long long)((uint32_t)((w >> 8) & 0x7fffffffu) | 0x80000000u) << 32) |
-                                                       (unsigned long long)(c * TJ + (int)(w & 0xffu));
-                        atomicMax(keyT + ppar * Bp + sb_, key);
-                    } else atomicAdd(isumT + ppar * Bp + sb_, (uint32_t)(w & 0xffu));
-                }
-            }
-            __syncthreads();
-            if (tid == 0) M.bigx = 0;
-        }
+        PROF(1)  // exchange wait (compute side)
 
-        // ---- winners of step t-1 (nodes.py:1097-1105), Ae trace, partner Ai input, monitors ------
-        const uint32_t lategrp = t > 0 ? M.candgrp[ppar] : 0u;
-        if (t > 0 && pend) {
-            uint32_t sE = 0;
-            if (E.one_spike) {
-                const unsigned long long key = keyT[ppar * Bp + b];
-                const int wj = (int)(uint32_t)(key & 0xffffffffull) - jc;
-                if (key != 0ull && wj >= 0 && wj < 4 && ((candE >> wj) & 1u)) sE = 1u << wj;
-            } else sE = candE;
-            if (E.traces) {
-                #pragma unroll
-                for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], (sE >> c) & 1u, E.trace_decay, E.trace_scale, 0);
-            }
-            if (update_on) {
-                if (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f) {
-                    *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
-                    if (!livep) {
-                        livep = true;
-                        atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
-                        live[atomicAdd(&M.nlive, 1)] = (uint16_t)(b * CG + cg);
+        // ---- column groups that held a candidate at step t-1: winners (nodes.py:1097-1105), Ae trace, partner
+        // Ai neurons, monitors, late STDP — all of it local to the group's own threads
+        const bool lateg = !isx && t > 0 && ((M.candgrp[ppar] >> cg) & 1u);
+        if (lateg) {
+            if (pend) {
+                uint32_t sE = 0;
+                if (E.one_spike) {
+                    const unsigned long long key = keyT[ppar * Bp + b];
+                    const int wj = (int)(uint32_t)(key & 0xffffffffull) - jc;
+                    if (key != 0ull && wj >= 0 && wj < 4 && ((candE >> wj) & 1u)) sE = 1u << wj;
+                } else sE = candE;
+                if (E.traces) {
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], (sE >> c) & 1u, E.trace_decay, E.trace_scale, 0);
+                }
+                if (update_on) {
+                    if (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f) {
+                        *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
+                        if (!livep) {
+                            livep = true;
+                            atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
+                            live[cg * Bp + atomicAdd(&M.nlive[cg], 1)] = (uint16_t)b;
+                        }
                     }
                 }
-            }
-            if (sE) {
-                const int slot = (stage_on && candstamp[b] == (uint32_t)t) ? candslot[b] : -1;   // staged at step t-1
+                const int slot = (stage_on && candstamp[ppar * Bp + b] == (uint32_t)t) ? candslot[ppar * Bp + b] : -1;   // staged at step t-1
                 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    if ((sE >> c) & 1u) {
+                    if ((candE >> c) & 1u) {
                         const int col = 4 * cg + c;
-                        if (update_on && post_on) {
+                        const bool won = (sE >> c) & 1u;
+                        if (won && update_on && post_on) {
                             atomicOr(&M.wmask[col][b >> 5], 1u << (b & 31));
-                            atomicOr(&M.colwin, 1u << col);
-                            const int k = atomicAdd(&M.nwl, 1);
-                            if (k < XR) M.wl[k] = ((uint32_t)col << 16) | ((uint32_t)b << 8) | (slot >= 0 ? (uint32_t)slot : 0xffu);
+                            atomicOr(&M.colwin[cg], 1u << c);
+                            const int k = atomicAdd(&M.nwl[cg], 1);
+                            if (k < XR) M.wl[cg][k] = ((uint32_t)col << 16) | ((uint32_t)b << 8) | (slot >= 0 ? (uint32_t)slot : 0xffu);
                         }
-                        // diagonal Ae->Ai: the partner receives `exc` at step t (network.py:225-248)
-                        unsigned e = ai_map[b * TJ + col];
-                        if (e == AI_NONE) {
-                            e = (unsigned)atomicAdd(&M.nact, 1);
-                            ai_v[e] = I.rest; ai_rc[e] = 0.0f; ai_id[e] = (uint16_t)(b * TJ + col); ai_fl[e] = 1;
-                            ai_map[b * TJ + col] = (uint16_t)e;
+                        // the partner Ai neuron of every candidate runs here (claimed at step t-1): input `exc`
+                        // through the diagonal Ae->Ai iff the candidate won (network.py:225-248)
+                        if (t < T) ai_step((int)ai_map[b * TJ + col], won ? (0.0f + Q.exc) : 0.0f, t);
+                        if (won) {   // monitors (monitors.py:94-111): the launch code cleared the raster
+                            if (E.rec_s) E.rec_s[((size_t)(t - 1) * B + b) * n + jc + c] = 1;
+                            if (E.rec_count) atomicAdd(E.rec_count + (size_t)b * n + jc + c, 1);
                         }
-                        ai_in[e] = (uint16_t)t;
-                        // monitors (monitors.py:94-111): the launch code cleared the raster
-                        if (E.rec_s) E.rec_s[((size_t)(t - 1) * B + b) * n + jc + c] = 1;
-                        if (E.rec_count) atomicAdd(E.rec_count + (size_t)b * n + jc + c, 1);
                     }
+                if (t == T) sEfin = sE;
+                pend = 0;
             }
-            if (t == T) sEfin = sE;
-            pend = 0;
-        }
-        PROF(2)  // winners
-        if (t > 0 && update_on && lategrp) {
-            // STDP of step t-1 for the column groups that held a candidate (MCC_learning.py:234-299)
-            __syncthreads();
-            const int sb_ = buf;   // slot t = spikes of step t-1
-            const uint32_t colwin = post_on ? M.colwin : 0u;
-            const int nwl = post_on ? M.nwl : 0;
-            bool fast = nwl <= XR && nwl == __popc(colwin) && !M.denseflag[sb_];
-            if (fast) {
-                #pragma unroll 1
-                for (int k = 0; k < nwl; ++k) if ((M.wl[k] & 0xffu) == 0xffu) fast = false;
-            }
-            if (nwl && stage_on) { while (!mbar_try_wait(&M.mbar_x, (uint32_t)(t - 1) & 1u)) {} }   // rows staged at step t-1
-            PROF(3)  // late set-up
-            if (fast) {
-                if (pre_on) stdp_list2<CG, BW>(&s_cx, sb_, lategrp, colwin, tid, nthr);
-                if (nwl) post_rows2<CG, BW>(&s_cx, sb_, nwl);
-            } else {
-                stdp_rows2<CG, BW>(&s_cx, sb_, lategrp, colwin, M.candb[ppar], min(M.ncand[ppar], XR),
-                                   Q.xtr ? Q.xtr + (size_t)(t - 1) * B * P : nullptr);
-            }
-            PROF(4)  // late pass
-            __syncthreads();
-            if (colwin) {
-                for (int k = tid; k < TJ * 8; k += nthr) (&M.wmask[0][0])[k] = 0;
-                if (tid == 0) { M.colwin = 0; M.nwl = 0; }
+            PROF(2)  // winners
+            if (update_on) {
+                // STDP of step t-1 for this column group (MCC_learning.py:234-299)
+                bar_group(gbar, Bp);
+                const int sb_ = buf;   // slot t = spikes of step t-1
+                const uint32_t gwin = post_on ? M.colwin[cg] : 0u;
+                const int nwl = post_on ? M.nwl[cg] : 0;
+                bool fast = nwl <= XR && nwl == __popc(gwin) && !M.denseflag[sb_];
+                if (fast) {
+                    #pragma unroll 1
+                    for (int k = 0; k < nwl; ++k) if ((M.wl[cg][k] & 0xffu) == 0xffu) fast = false;
+                }
+                const float *xr = xrow + ppar * XR * P;   // rows staged at step t-1 (buffer of its parity, filled for the ((t-1)>>1)-th time)
+                if (nwl && stage_on) { while (!mbar_try_wait(&M.mbar_x[ppar], (uint32_t)((t - 1) >> 1) & 1u)) {} }
+                PROF(3)  // late set-up
+                if (fast) {
+                    if (pre_on) stdp_list2<CG, BW>(&s_cx, sb_, cg, gwin, xr, b, Bp);
+                    if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, xr, b, Bp);
+                } else {
+                    stdp_rows2<CG, BW>(&s_cx, sb_, cg, gwin, M.candb[ppar], min(M.ncand[ppar], XR),
+                                       Q.xtr ? Q.xtr + (size_t)(t - 1) * B * P : nullptr, xr, b, Bp);
+                }
+                PROF(4)  // late pass
+                bar_group(gbar, Bp);   // the group's weights are final for step t-1
+                if (gwin) {
+                    if (b < 4 * BW) M.wmask[4 * cg + (b / BW)][b % BW] = 0;
+                    if (b == 0) { M.colwin[cg] = 0; M.nwl[cg] = 0; }
+                }
             }
         }
         if (t == 1 && update_on && C.has_clamp) {
@@ -747,19 +758,19 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             // after the first step that is a no-op for untouched weights, so one sweep after step 0 covers it
             __syncthreads();
             #pragma unroll 1
-            for (int idx = tid; idx < P * TJ; idx += nthr) { const int i = idx / TJ, jj = idx - i * TJ; W[i * WS + jj] = clampf(W[i * WS + jj], C.wmin, C.wmax); }
+            for (int idx = tid; idx < P * TJ; idx += blockDim.x) { const int i = idx / TJ, jj = idx - i * TJ; W[i * WS + jj] = clampf(W[i * WS + jj], C.wmin, C.wmax); }
+            __syncthreads();
         }
         if (t == T) break;
 
-        // ---- step t: gather, Ae update, Ai list, candidates ------------------------------------------
-        while (!mbar_try_wait(&M.mbar_in[buf], (uint32_t)(t >> 1) & 1u)) {}   // slot t landed (prefetched one step ago)
-        if (tid == 0) { M.ncand[par] = 0; M.candgrp[par] = 0; M.nent = 0; }
-        __syncthreads();   // W final for step t-1; bookkeeping of parity `par` reset
-        PROF(5)  // slot wait + sync
+        // ---- step t: gather (unless done ahead), Ae update, candidates, Ai list ------------------------
         uint32_t cand = 0;
         if (act) {
-            const float4 pg = gather(cE, t);
-            const float p[4] = {pg.x, pg.y, pg.z, pg.w};
+            if (!havepre) {
+                while (!mbar_try_wait(&M.mbar_in[buf], (uint32_t)(t >> 1) & 1u)) {}   // slot t landed (prefetched one step ago)
+                pre = gather(cE, t);
+            }
+            const float p[4] = {pre.x, pre.y, pre.z, pre.w};
             const float4 th4 = *(const float4 *)(thr_s + 4 * cg);
             const float thr[4] = {th4.x, th4.y, th4.z, th4.w};
             const int isum = (int)isumT[ppar * Bp + b];                 // Ai spikes of step t-1 (lateral inhibition)
@@ -783,32 +794,39 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 }
             }
             if (cand) {
-                uint32_t bh = 0; int bc = 0;
+                unsigned long long mykey = 0ull;
                 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if ((cand >> c) & 1u) {
-                        atomicAdd(&M.cnt[par][4 * cg + c], 1);
+                        const int col = 4 * cg + c;
+                        atomicAdd(&M.cnt[par][col], 1);
                         if (E.one_spike) {
-                            const uint32_t hh = snn_one_spike_hash(Q.seed, (uint32_t)t + Q.step_offset, (uint32_t)Q.liE, (uint32_t)b,
-                                                                   (uint32_t)(jc + c)) | 0x80000000u;
-                            if (hh >= bh) { bh = hh; bc = c; }   // ties: the larger neuron index wins, like the 64-bit key
+                            const unsigned long long k2 = snn_one_spike_key(Q.seed, (uint32_t)t + Q.step_offset, (uint32_t)Q.liE, (uint32_t)b,
+                                                                            (uint32_t)(jc + c));
+                            mykey = k2 > mykey ? k2 : mykey;
                         }
+                        // the partner Ai neuron is mine at step t+1, whether this candidate wins or not
+                        unsigned e = ai_map[b * TJ + col];
+                        if (e == AI_NONE) {
+                            e = (unsigned)atomicAdd(&M.nact, 1);
+                            ai_v[e] = I.rest; ai_rc[e] = 0.0f; ai_id[e] = (uint16_t)(b * TJ + col); ai_fl[e] = 1;
+                            ai_claim[par * aicap + e] = (uint16_t)AI_NONE;
+                            ai_map[b * TJ + col] = (uint16_t)e;
+                        }
+                        ai_claim[ppar * aicap + e] = (uint16_t)(t + 1);   // slot of parity (t + 1) & 1
                     }
                 atomicOr(&M.candgrp[par], 1u << cg);
-                if (E.one_spike) {
-                    const int e = atomicAdd(&M.nent, 1);
-                    st_relaxed_u64(myent + (size_t)par * entpar + e, msg_cand(msg_tag(t), b, bh, 4 * cg + bc));
-                }
+                if (E.one_spike) atomicMax(Q.win + (t % 3) * B + b, mykey);
                 if (stage_on) {  // stage x_pre[b,:] of step t for the post term, once per sample
-                    const uint32_t old = atomicExch(&candstamp[b], (uint32_t)(t + 1));
+                    const uint32_t old = atomicExch(&candstamp[par * Bp + b], (uint32_t)(t + 1));
                     if (old != (uint32_t)(t + 1)) {
                         const int s = atomicAdd(&M.ncand[par], 1);
-                        if (s < XR) {
+                        if (s < XR && !(Q.dbg & 8)) {
                             M.candb[par][s] = b;
-                            candslot[b] = s;
-                            mbar_expect_tx(&M.mbar_x, (uint32_t)(P * 4));
-                            bulk_g2s(xrow + s * P, Q.xtr + ((size_t)t * B + b) * P, (uint32_t)(P * 4), &M.mbar_x);
-                        } else candslot[b] = -1;
+                            candslot[par * Bp + b] = s;
+                            mbar_expect_tx(&M.mbar_x[par], (uint32_t)(P * 4));
+                            bulk_g2s(xrow + (par * XR + s) * P, Q.xtr + ((size_t)t * B + b) * P, (uint32_t)(P * 4), &M.mbar_x[par]);
+                        } else candslot[par * Bp + b] = -1;
                     }
                 }
             } else if (E.traces) {
@@ -820,83 +838,77 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         }
         candE = cand;
         pend = cand;
-        // Ai list (LIFNodes.forward, nodes.py:500-529): input `exc` from the partner's spike of step t-1
-        {
-            const int nact = M.nact;
+        havepre = false;
+        // Ai list (LIFNodes.forward, nodes.py:500-529): the entries nobody claimed for this step get no input
+        if (!isx) {
+            const int nact = M.nact_snap;
             #pragma unroll 1
-            for (int k = tid; k < nact; k += nthr) {
-                float v = ai_v[k], rc = ai_rc[k];
-                uint32_t fl = ai_fl[k];
-                float xin = ai_in[k] == (uint16_t)t ? (0.0f + Q.exc) : 0.0f;
-                v = I.decay * (v - I.rest) + I.rest;
-                if (!(fl & 1u)) { if (rc > 0.0f) xin = 0.0f; rc = rc - I.dt; }   // undisturbed counter: <= 0 by construction
-                v = v + xin;
-                fl &= ~2u;
-                if (v >= I.thresh) {
-                    rc = I.refrac; v = I.reset; fl = 2u;
-                    const int id = ai_id[k], sb_ = id / TJ, col = id - sb_ * TJ;
-                    atomicOr(&aispk[par * Bp + sb_], 1u << col);
-                    const int e = atomicAdd(&M.nent, 1);
-                    st_relaxed_u64(myent + (size_t)par * entpar + e, msg_ai(msg_tag(t), sb_, 1));
-                    if (I.rec_s) I.rec_s[((size_t)t * B + sb_) * n + j0 + col] = 1;
-                    if (I.rec_count) atomicAdd(I.rec_count + (size_t)sb_ * n + j0 + col, 1);
-                }
-                ai_v[k] = v; ai_rc[k] = rc; ai_fl[k] = (uint8_t)fl;
+            for (int k = tid; k < nact; k += NC) {
+                if (ai_claim[par * aicap + k] == (uint16_t)t) continue;
+                ai_step(k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t);
             }
         }
         PROF(6)  // gather + neurons
         __syncthreads();
-        // ---- publish step t's message; theta; prefetch -----------------------------------------------
-        if (tid == 0) {
-            st_relaxed_u64(Q.hdr + (size_t)par * G + blockIdx.x, ((unsigned long long)msg_tag(t) << 48) | (unsigned long long)(uint32_t)M.nent);
-            mbar_arrive(&M.mbar_x);   // phase t of the staged rows: complete once the copies issued above have landed
-        }
-        if (tid < TJ) {
-            // theta = theta * decay + theta_plus * (#candidates of the column)  (nodes.py:1078-1094)
-            float th = theta_s[tid];
-            if (E.learning) th = th * E.theta_decay + E.theta_plus * (float)M.cnt[par][tid];
-            theta_s[tid] = th;
-            thr_s[tid] = E.thresh + (E.learning ? th * E.theta_decay : th);
-            M.cnt[par][tid] = 0;
-        }
-        // tables of step t-1 are consumed: clear them for step t+1
-        for (int k = tid; k < Bp; k += nthr) { keyT[ppar * Bp + k] = 0ull; isumT[ppar * Bp + k] = 0u; aispk[ppar * Bp + k] = 0u; }
-        int dflag = 0;
-        if (tid == tid_pf && t + 2 <= T) {  // prefetch slot t+2 into the buffer the gather just finished with
-            mbar_arrive_expect_tx(&M.mbar_in[buf], bytesE + bytesT);
-            bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar_in[buf]);
-            bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar_in[buf]);
-            dflag = __ldg(Q.dense + t + 2);
-        }
-        PROF(7)  // publish
-        // ---- early STDP of step t, in the shadow of the exchange: pre term of the column groups WITHOUT a
-        // candidate (their step-t traces are final).  Warp 0 goes straight to the exchange.
+        PROF(7)  // step sync
+        // ---- arrive(t): this CTA's contributions to step t's exchange are issued -----------------
         const int nb = buf ^ 1;                                      // slot t+1 = spikes of step t
-        if (update_on && pre_on && (warp > 0 || nthr == 32)) {
+        if (isx) {
+            // clear the exchange slot step t+1 will accumulate into (last read before the previous barrier)
+            if (blockIdx.x == 0)
+                for (int k = lane; k < B; k += 32) { Q.win[((t + 1) % 3) * B + k] = 0ull; Q.sisum[((t + 1) % 3) * B + k] = 0u; }
+            __syncwarp();
+            if (lane == 0) {
+                if (Q.dbg & 128) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
+                else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
+                mbar_arrive(&M.mbar_x[par]);   // the rows staged in step t: complete once the copies issued above have landed
+            }
+            if (tid == tid_pf && t + 2 <= T && (Q.dbg & 1)) mbar_arrive(&M.mbar_in[buf]);
+            if (tid == tid_pf && t + 2 <= T && !(Q.dbg & 1)) {  // prefetch slot t+2 into the buffer the gather just finished with
+                const bool masks = !(Q.dbg & 32);   // (diagnostic: pixel masks not refreshed)
+                mbar_arrive_expect_tx(&M.mbar_in[buf], bytesE + (masks ? bytesT : 0u));
+                bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar_in[buf]);
+                if (masks) bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar_in[buf]);
+            }
+            if (PROFV && tid == NC) pt = clock64();
+        } else {
+            // ---- the shadow of the exchange, per column group: theta, early STDP of step t, gather of step t+1
+            if (b < 4) {
+                // theta = theta * decay + theta_plus * (#candidates of the column)  (nodes.py:1078-1094)
+                const int col = 4 * cg + b;
+                float th = theta_s[col];
+                if (E.learning) th = th * E.theta_decay + E.theta_plus * (float)M.cnt[par][col];
+                theta_s[col] = th;
+                thr_s[col] = E.thresh + (E.learning ? th * E.theta_decay : th);
+                M.cnt[par][col] = 0;
+            }
+            if (cg == 0) aispk[ppar * Bp + b] = 0u;   // own Ai spikes of step t-1: consumed
+            const bool earlyg = !((M.candgrp[par] >> cg) & 1u);
             while (!mbar_try_wait(&M.mbar_in[nb], (uint32_t)((t + 1) >> 1) & 1u)) {}
-            const uint32_t earlygrp = ((1u << CG) - 1u) & ~M.candgrp[par];
-            if (M.denseflag[nb]) {
-                // row form needs every thread: done below, after the exchange (rare)
-            } else stdp_list2<CG, BW>(&s_cx, nb, earlygrp, 0u, nthr > 32 ? tid - 32 : tid, nthr > 32 ? nthr - 32 : nthr);
-        }
-        if (tid == tid_pf && t + 2 <= T) M.denseflag[buf] = dflag;   // read one step from now
-        PROF(8)  // early STDP
-        if (update_on && pre_on && M.denseflag[nb]) {
-            // a sample's event list overflowed: early pass in row form with the whole CTA (its own barrier)
-            while (!mbar_try_wait(&M.mbar_in[nb], (uint32_t)((t + 1) >> 1) & 1u)) {}
-            __syncthreads();
-            const uint32_t earlygrp = ((1u << CG) - 1u) & ~M.candgrp[par];
-            stdp_rows2<CG, BW>(&s_cx, nb, earlygrp, 0u, M.candb[par], 0, nullptr);
+            if (tid == 0) { M.denseflag[nb] = dense_nb; M.ncand[ppar] = 0; M.candgrp[ppar] = 0; M.nact_snap = M.nact; }   // parity ppar: next used by step t+1
+            // early STDP: pre term of a column group WITHOUT a candidate (its step-t traces are final)
+            if (earlyg && update_on && pre_on && !(Q.dbg & 2)) {
+                if (dense_nb) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, b, Bp);
+                else stdp_list2<CG, BW>(&s_cx, nb, cg, 0u, xrow, b, Bp);
+                bar_group(gbar, Bp);
+            }
+            PROF(8)  // early STDP
+            // gather of step t+1 for a group whose weights are final now: off the critical path
+            const bool ahead = t + 1 < T && earlyg && !(t == 0 && update_on && C.has_clamp) && !(Q.dbg & 4);
+            if (ahead && act) pre = gather(evb + nb * evblk, t + 1);
+            havepre = ahead;
+            PROF(9)  // gather ahead
         }
     }
 
     // ---- epilogue: normalize() on the tile (network.py:464-465), write everything back -----
     __syncthreads();
+    PROF(12)
     if (Q.normalize && C.has_norm) {
         float *part = xrow;  // [SNN_NORM_CHUNKS + 1][TJ]
         const int chunk = (P + SNN_NORM_CHUNKS - 1) / SNN_NORM_CHUNKS;
         #pragma unroll 1
-        for (int idx = tid; idx < SNN_NORM_CHUNKS * TJ; idx += nthr) {
+        for (int idx = tid; idx < SNN_NORM_CHUNKS * TJ; idx += blockDim.x) {
             const int c = idx / TJ, jj = idx % TJ;
             float a = 0.0f;
             const int i1 = min((c + 1) * chunk, P);
@@ -912,38 +924,62 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             part[SNN_NORM_CHUNKS * TJ + tid] = C.norm / tot;
         }
         __syncthreads();
-        #pragma unroll 1
-        for (int idx = tid; idx < P * TJ; idx += nthr) { const int i = idx / TJ, jj = idx % TJ; W[i * WS + jj] = W[i * WS + jj] * part[SNN_NORM_CHUNKS * TJ + jj]; }
-        __syncthreads();
+        #pragma unroll 4
+        for (int idx = tid; idx < P * TJ; idx += blockDim.x) {
+            const int i = idx / TJ, jj = idx % TJ;
+            const float w = W[i * WS + jj] * part[SNN_NORM_CHUNKS * TJ + jj];
+            if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = w;
+        }
+    } else {
+        #pragma unroll 4
+        for (int idx = tid; idx < P * TJ; idx += blockDim.x) {
+            const int i = idx / TJ, jj = idx % TJ;
+            if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[i * WS + jj];
+        }
     }
-    #pragma unroll 1
-    for (int idx = tid; idx < P * TJ; idx += nthr) {
-        const int i = idx / TJ, jj = idx % TJ;
-        if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[i * WS + jj];
-    }
-    for (int jj = tid; jj < TJ; jj += nthr)
+    for (int jj = tid; jj < TJ; jj += blockDim.x)
         if (j0 + jj < n) E.theta[j0 + jj] = theta_s[jj];
     if (act) {
+        const size_t k0 = (size_t)b * n + jc;
+        float vI[4], rI[4];
+        uint32_t sI = 0;
+        // Ai: listed neurons from the list, the others only ran their refractory counter down
         #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c) {
+            vI[c] = 0.0f; rI[c] = 0.0f;
             if ((vm >> c) & 1u) {
-                const size_t k = (size_t)b * n + jc + c;
-                E.v[k] = vE[c]; E.refrac_count[k] = rE[c];
-                if (E.traces) E.x[k] = xE[c];
-                E.s[k] = (sEfin >> c) & 1u;
-                // Ai: listed neurons from the list, the others only ran their refractory counter down
                 const unsigned e = ai_map[b * TJ + 4 * cg + c];
-                if (e == AI_NONE) {
-                    I.refrac_count[k] = refrac_replay(I.refrac_count[k], I.dt, T);
-                    I.s[k] = 0;
-                } else {
-                    I.v[k] = ai_v[e];
-                    I.refrac_count[k] = (ai_fl[e] & 1u) ? refrac_replay(I.refrac_count[k], I.dt, T) : ai_rc[e];
-                    I.s[k] = (ai_fl[e] >> 1) & 1u;
+                const float r0 = I.refrac_count[k0 + c];
+                if (e == AI_NONE) { vI[c] = I.rest; rI[c] = refrac_replay(r0, I.dt, T); }
+                else {
+                    vI[c] = ai_v[e];
+                    rI[c] = (ai_fl[e] & 1u) ? refrac_replay(r0, I.dt, T) : ai_rc[e];
+                    sI |= ((ai_fl[e] >> 1) & 1u) << c;
                 }
             }
+        }
+        if (vm == 0xFu && (n & 3) == 0) {
+            *(float4 *)(E.v + k0) = make_float4(vE[0], vE[1], vE[2], vE[3]);
+            *(float4 *)(E.refrac_count + k0) = make_float4(rE[0], rE[1], rE[2], rE[3]);
+            if (E.traces) *(float4 *)(E.x + k0) = make_float4(xE[0], xE[1], xE[2], xE[3]);
+            *(uint32_t *)(E.s + k0) = (sEfin & 1u) | ((sEfin & 2u) << 7) | ((sEfin & 4u) << 14) | ((sEfin & 8u) << 21);
+            *(float4 *)(I.v + k0) = make_float4(vI[0], vI[1], vI[2], vI[3]);
+            *(float4 *)(I.refrac_count + k0) = make_float4(rI[0], rI[1], rI[2], rI[3]);
+            *(uint32_t *)(I.s + k0) = (sI & 1u) | ((sI & 2u) << 7) | ((sI & 4u) << 14) | ((sI & 8u) << 21);
+        } else {
+            #pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if ((vm >> c) & 1u) {
+                    const size_t k = k0 + c;
+                    E.v[k] = vE[c]; E.refrac_count[k] = rE[c];
+                    if (E.traces) E.x[k] = xE[c];
+                    E.s[k] = (sEfin >> c) & 1u;
+                    I.v[k] = vI[c]; I.refrac_count[k] = rI[c];
+                    I.s[k] = (sI >> c) & 1u;
+                }
+        }
     }
-    PROF(9)  // epilogue
+    PROF(13)  // epilogue
     if (PROFV && Q.prof && tid == 0)
         for (int k = 0; k < NPROF; ++k) Q.prof[blockIdx.x * NPROF + k] = pc[k];
 }
@@ -973,7 +1009,6 @@ __global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F
         const int b = b0 + bl;
         int total = 0;
         if (b < B && fast16) {
-            uint16_t *lst = elist + b * EV_CAP;
             const uint4 *row = (const uint4 *)(src0 + (size_t)b * P);
             unsigned char *rec = (slot > 0 && X.rec_s) ? X.rec_s + ((size_t)(slot - 1) * B + b) * P : nullptr;
             const int nchunk = P >> 4;
@@ -1010,7 +1045,7 @@ __global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F
                 while (mm) {
                     const int bit = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    if (pos < EV_CAP) lst[pos] = (uint16_t)(c * 16 + bit);
+                    if (pos < EV_CAP) elist[ev_pos(B, b, pos)] = (uint16_t)(c * 16 + bit);
                     ++pos;
                 }
                 total += __shfl_sync(0xffffffffu, incl, 31);
@@ -1019,11 +1054,10 @@ __global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F
                 if (w * 32 >= P) { sbits[bl * SW + w] = 0u; Q.inS[((size_t)slot * B + b) * SW + w] = 0u; }
             }
             const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
-            if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+            if (total < EV_CAP && lane < padded - total) elist[ev_pos(B, b, total + lane)] = (uint16_t)P;
             if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
             dense |= total > EV_CAP;
         } else if (b < B) {
-            uint16_t *lst = elist + b * EV_CAP;
             for (int w = 0; w < SW; ++w) {
                 const int i = w * 32 + lane;
                 bool s = false;
@@ -1040,12 +1074,12 @@ __global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F
                 if (lane == 0) { sbits[bl * SW + w] = word; Q.inS[((size_t)slot * B + b) * SW + w] = word; }
                 if (s) {  // ascending pixel list: position = spikes before me
                     const int pos = total + __popc(word & ((1u << lane) - 1u));
-                    if (pos < EV_CAP) lst[pos] = (uint16_t)i;
+                    if (pos < EV_CAP) elist[ev_pos(B, b, pos)] = (uint16_t)i;
                 }
                 total += __popc(word);
             }
             const int padded = (total + 3) & ~3;  // pad to a multiple of 4 with the zero row P
-            if (total < EV_CAP && lane < padded - total) lst[total + lane] = (uint16_t)P;
+            if (total < EV_CAP && lane < padded - total) elist[ev_pos(B, b, total + lane)] = (uint16_t)P;
             if (lane == 0) ecnt[b] = (uint16_t)(total > 65535 ? 65535 : total);
             dense |= total > EV_CAP;
         } else {
@@ -1140,7 +1174,7 @@ __global__ void __launch_bounds__(256) snn_dc2_trace_scan(const __grid_constant_
 }
 
 struct Match2 {
-    int lX, lE, lI, cXE, cEI, cIE, CG, BW, threads, grid, SW, SB, Bp, nrep, ecap;
+    int lX, lE, lI, cXE, cEI, cIE, CG, BW, threads, grid, SW, SB, Bp, nrep;
     size_t smem;
 };
 
@@ -1201,12 +1235,11 @@ bool match2(const snn_net_t *net, const snn_run_opts_t *o, Match2 &m) {
     for (int CG = 1; CG <= 8; ++CG) {
         const int TJ = 4 * CG;
         const int grid = (n + TJ - 1) / TJ;
-        const int threads = m.Bp * CG;
-        if (grid > sms || grid > 32 * NHMAX || threads > 1024) continue;
+        const int threads = m.Bp * CG + 32;   // compute threads + the exchange warp
+        if (grid > sms || threads > 1024) continue;
         const SmemLayout2 SL = smem_layout2(P, TJ, B, m.Bp, m.BW, m.nrep);
         if (SL.total > 227 * 1024) continue;
         m.CG = CG; m.grid = grid; m.threads = threads; m.smem = SL.total;
-        m.ecap = m.Bp * CG + m.Bp * TJ;   // one candidate entry per thread + one entry per Ai spike
         return true;
     }
     return false;
@@ -1225,14 +1258,15 @@ cudaError_t launch_cg2(const F2Params &Q, const Match2 &m, cudaStream_t stream) 
     return Q.prof ? launch_var2<CG, 4, 2>(Q, m, stream) : launch_var2<CG, 4, 0>(Q, m, stream);
 }
 
-struct WsLayout2 { size_t dense, hdr, ent, inS, inT, evS, rep, sisum0, xtr, prof, total; };
+struct WsLayout2 { size_t dense, bar, win, sisum, inS, inT, evS, rep, sisum0, xtr, prof, total; };
 WsLayout2 ws_layout2(const Match2 &m, int T, int B, int P, bool traces) {
     WsLayout2 L; size_t o = 0;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-    // dense flags, headers and entries are adjacent: one memset node per window
+    // dense flags, barrier word and exchange slots are adjacent: one memset node per window
     L.dense = o; o += al(sizeof(int) * (size_t)(T + 1));
-    L.hdr = o; o += al(sizeof(unsigned long long) * 2 * (size_t)m.grid);
-    L.ent = o; o += al(sizeof(unsigned long long) * 2 * (size_t)m.grid * m.ecap);
+    L.bar = o; o += al(sizeof(unsigned int) * 64);
+    L.win = o; o += al(sizeof(unsigned long long) * 3 * (size_t)B);
+    L.sisum = o; o += al(sizeof(unsigned int) * 3 * (size_t)B);
     L.inS = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * B * m.SW);
     L.inT = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * P * m.BW);
     L.evS = o; o += al((size_t)(T + 1) * m.SB);
@@ -1273,7 +1307,7 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     Q.C = net->conns[m.cXE];
     Q.exc = net->conns[m.cEI].structure_val; Q.inh_neg = net->conns[m.cIE].structure_val;
     Q.T = T; Q.B = B; Q.Bp = m.Bp; Q.P = P; Q.n = Q.E.n; Q.learning = net->learning; Q.normalize = opts->normalize;
-    Q.G = m.grid; Q.nrep = m.nrep; Q.ecap = m.ecap;
+    Q.G = m.grid; Q.nrep = m.nrep;
     {
         const SmemLayout2 SL = smem_layout2(P, 4 * m.CG, B, m.Bp, m.BW, m.nrep);
         Q.o_W = (uint32_t)SL.W; Q.o_tx = (uint32_t)SL.tx; Q.o_ev = (uint32_t)SL.ev; Q.o_inT = (uint32_t)SL.inT; Q.o_xrow = (uint32_t)SL.xrow;
@@ -1282,19 +1316,24 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     }
     Q.SW = m.SW; Q.SB = m.SB; Q.liE = m.lE; Q.seed = opts->seed; Q.step_offset = opts->step_offset;
     Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
-    Q.dense = (int *)(ws + WL.dense); Q.hdr = (unsigned long long *)(ws + WL.hdr); Q.ent = (unsigned long long *)(ws + WL.ent);
+    Q.dense = (int *)(ws + WL.dense); Q.bar = (unsigned int *)(ws + WL.bar); Q.win = (unsigned long long *)(ws + WL.win);
+    Q.sisum = (unsigned int *)(ws + WL.sisum);
     Q.rep = (float *)(ws + WL.rep); Q.sisum0 = (unsigned int *)(ws + WL.sisum0);
     const bool stdp = Q.C.rule >= SNN_RULE_POSTPRE;
     Q.xtr = (traces && stdp && net->learning && Q.C.nu1 != 0.0f) ? (float *)(ws + WL.xtr) : nullptr;
     Q.err = opts->err_flag;
+    { const char *d = getenv("SNN_B200_DEBUG"); Q.dbg = d ? atoi(d) : 0; }
     const bool prof = getenv("SNN_B200_PROF") != nullptr;
     Q.prof = prof ? (long long *)(ws + WL.prof) : nullptr;
     int nl = 0;
-    // dense flags + message area: stale tags of an earlier window must not be believed
+    // dense flags, barrier counter, exchange slots
     if (cudaMemsetAsync(ws + WL.dense, 0, WL.inS - WL.dense, stream) != cudaSuccess) return SNN_ERR_CUDA;
     // sparse monitors: the window kernel only writes the ones
     if (Q.E.rec_s && cudaMemsetAsync(Q.E.rec_s, 0, (size_t)T * B * Q.n, stream) != cudaSuccess) return SNN_ERR_CUDA;
     if (Q.I.rec_s && cudaMemsetAsync(Q.I.rec_s, 0, (size_t)T * B * Q.n, stream) != cudaSuccess) return SNN_ERR_CUDA;
+    // the two static matrices are replaced by their constants: make sure they still have that structure
+    if (snn_verify_structure(net->conns[m.cEI], Q.n, Q.err, stream) != SNN_OK || snn_verify_structure(net->conns[m.cIE], Q.n, Q.err, stream) != SNN_OK) return SNN_ERR_CUDA;
+    nl += 2;
     snn_dc2_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
     ++nl;
     cudaError_t e = cudaGetLastError();
@@ -1323,18 +1362,18 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (min / mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange wait", "winners", "late set-up", "late pass", "slot wait+sync", "gather+neurons",
-                                           "publish", "early STDP", "epilogue", "", "", "", "", "", ""};
+                                           "step sync", "early STDP", "gather ahead", "x: barrier wait", "x: exchange read", "final sync", "epilogue", "", ""};
         cudaStreamSynchronize(stream);
         static long long hostp[160 * NPROF];
         cudaMemcpy(hostp, Q.prof, sizeof(long long) * (size_t)m.grid * NPROF, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[snn_b200 prof v2] grid=%d threads=%d T=%d (cycles per timestep, thread 0 of each CTA: min / mean / max)\n", m.grid, m.threads, T);
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < 14; ++k) {
             double sum = 0, mx = 0, mn = 1e300;
             for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[g * NPROF + k]; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
-            const double div = (k == 0 || k == 9) ? 1.0 : (double)T;
+            const double div = (k == 0 || k >= 12) ? 1.0 : (double)T;
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f\n", names[k], mn / div, sum / m.grid / div, mx / div);
         }
     }
-    if (launches) *launches = nl;  // two pre-passes + the persistent window kernel
+    if (launches) *launches = nl;  // 2 structure checks + two pre-passes + the persistent window kernel
     return SNN_OK;
 }

@@ -25,6 +25,34 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) conn_compute_kernel(snn_conn_
     }
 }
 
+// Conv2dConnection.compute (topology.py:799-815): out[b, co, oy, ox] = sum of the filter taps whose (zero-padded)
+// input position spiked, in ascending (ci, ky, kx) order, then the bias — the window kernels' gather_conv on
+// byte spikes.  Thread = one target neuron of one sample.
+__global__ void __launch_bounds__(256) conv_compute_kernel(snn_conn_t C, int ns, int nt, int B, const uint8_t *__restrict__ s,
+                                                           float *__restrict__ out) {
+    const size_t total = (size_t)B * nt;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(k / nt), j = (int)(k - (size_t)b * nt);
+        const int L = C.hout * C.wout;
+        const int co = j / L, l = j - co * L, oy = l / C.wout, ox = l - oy * C.wout;
+        const uint8_t *sb = s + (size_t)b * ns;
+        float p = 0.0f;
+        for (int ci = 0; ci < C.cin; ++ci)
+            for (int ky = 0; ky < C.kh; ++ky) {
+                const int iy = oy * C.sh - C.ph + ky * C.dh;
+                if (iy < 0 || iy >= C.hin) continue;
+                for (int kx = 0; kx < C.kw; ++kx) {
+                    const int ix = ox * C.sw - C.pw + kx * C.dw;
+                    if (ix < 0 || ix >= C.win) continue;
+                    if (sb[(ci * C.hin + iy) * C.win + ix]) p = p + C.w[((co * C.cin + ci) * C.kh + ky) * C.kw + kx];
+                }
+            }
+        out[k] = p + C.b[co];
+    }
+}
+
+__global__ void __launch_bounds__(SNN_GEN_THREADS) conv_normalize_kernel(snn_conn_t C) { normalize_conv_item(C, blockIdx.x, gridDim.x); }
+
 // bit-pack the CURRENT spikes of the two layers of a connection into slot 0
 __global__ void pack_bits_kernel(const uint8_t *__restrict__ s, uint32_t *__restrict__ bits, int B, int n, int nw) {
     const int lane = threadIdx.x & 31;
@@ -69,15 +97,44 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t
     if (C.has_norm) normalize_tile(C, ns, nt, blockIdx.x, s_part);
 }
 
+// Checks on the device that a square matrix has the structure a plan claims for it (SNN_W_DIAG: val on the
+// diagonal, 0 elsewhere; SNN_W_OFFDIAG: 0 on the diagonal, val elsewhere) — the fused kernels replace such a
+// matrix by its constant, so a matrix modified behind the host-side cache must not go unnoticed.
+__global__ void verify_structure_kernel(const float *__restrict__ w, int n, int structure, float val, int32_t *err) {
+    const size_t total = (size_t)n * n;
+    bool bad = false;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = k / n, j = k - i * n;
+        const float want = ((i == j) == (structure == SNN_W_DIAG)) ? val : 0.0f;
+        bad |= w[k] != want;
+    }
+    if (bad && err) atomicOr(err, SNN_ERR_STRUCTURE);
+}
+
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? SNN_OK : SNN_ERR_CUDA; }
 
 }  // namespace
+
+int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t stream) {
+    if (C.structure != SNN_W_DIAG && C.structure != SNN_W_OFFDIAG) return SNN_OK;
+    const size_t total = (size_t)n * n;
+    const int blocks = (int)((total + 2047) / 2048 < 592 ? (total + 2047) / 2048 : 592);
+    verify_structure_kernel<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(C.w, n, C.structure, C.structure_val, err);
+    return cuda_rc(cudaGetLastError());
+}
 
 extern "C" {
 
 int snn_b200_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, int32_t B, const uint8_t *s, float *out,
                           void *stream) {
     if (!conn || !conn->w || !s || !out || n_src <= 0 || n_tgt <= 0 || B <= 0) return SNN_ERR_BAD_ARG;
+    if (conn->kind == SNN_CONN_CONV2D) {
+        if (!conn->b || conn->cin * conn->hin * conn->win != n_src || conn->cout * conn->hout * conn->wout != n_tgt) return SNN_ERR_BAD_ARG;
+        const size_t total = (size_t)B * n_tgt;
+        const int blocks = (int)((total + 255) / 256 < 4736 ? (total + 255) / 256 : 4736);
+        conv_compute_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt, B, s, out);
+        return cuda_rc(cudaGetLastError());
+    }
     dim3 grid((n_tgt + SNN_TILE - 1) / SNN_TILE, (B + SNN_GEN_WARPS - 1) / SNN_GEN_WARPS);
     if (grid.y > 64) grid.y = 64;
     conn_compute_kernel<<<grid, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt, B, s, out);
@@ -87,6 +144,11 @@ int snn_b200_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, 
 int snn_b200_conn_update(const snn_net_t *net, int32_t ci, int32_t B, void *workspace, size_t workspace_bytes, void *stream_) {
     if (!net || ci < 0 || ci >= net->n_conns || B <= 0 || !workspace) return SNN_ERR_BAD_ARG;
     const snn_conn_t &C = net->conns[ci];
+    if (C.src < 0 || C.src >= net->n_layers || C.tgt < 0 || C.tgt >= net->n_layers || !C.w) return SNN_ERR_BAD_ARG;
+    // the single-operator update is the dense [n_src, n_tgt] rule application; convolutional weights and the
+    // reward-modulated rules (whose state lives in the window plan) are only updated inside run_window
+    if (C.kind != SNN_CONN_DENSE && C.kind != SNN_CONN_MCC) return SNN_ERR_UNSUPPORTED;
+    if (C.rule == SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
     if (C.rule == SNN_RULE_NONE) return SNN_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     DevNet N;
@@ -117,6 +179,11 @@ int snn_b200_conn_update(const snn_net_t *net, int32_t ci, int32_t B, void *work
 int snn_b200_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, void *stream) {
     if (!conn || !conn->w || n_src <= 0 || n_tgt <= 0) return SNN_ERR_BAD_ARG;
     if (!conn->has_norm) return SNN_OK;
+    if (conn->kind == SNN_CONN_CONV2D) {
+        const int F = conn->cout * conn->cin;
+        conv_normalize_kernel<<<(F + SNN_GEN_THREADS - 1) / SNN_GEN_THREADS, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn);
+        return cuda_rc(cudaGetLastError());
+    }
     conn_normalize_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt);
     return cuda_rc(cudaGetLastError());
 }

@@ -34,11 +34,33 @@ class ShardedWindowRunner:
         self._snap: Optional[torch.Tensor] = None
 
     def _learned(self) -> List[Tuple[object, "_abi.SnnConn"]]:
+        """Connections whose weights change inside a window (a learning rule, or the end-of-run normalize),
+        with the constants the combine needs.  Built from the objects' attributes — not from the per-window
+        plan, which reward-modulated rules can only fill during a run."""
+        from .network.topology import Conv2dConnection
+
         out = []
         for conn in self.network.connections.values():
-            d = _abi.SnnConn()
-            conn._fill_desc(d, float(self.network.dt))
+            if hasattr(conn, "pipeline"):  # MulticompartmentConnection[Weight]: plain-sum normalize, dt-scaled rule
+                d = _abi.SnnConn()
+                conn._fill_desc(d, float(self.network.dt))
+            else:
+                rule = getattr(conn, "update_rule", None)
+                code = getattr(rule, "rule_code", None)
+                code = int(code) if code is not None else _abi.SNN_RULE_NONE
+                d = _abi.SnnConn()
+                d.rule = code
+                d.has_norm = int(conn.norm is not None)
+                d.norm = float(conn.norm) if conn.norm is not None else 0.0
+                d.norm_abs = 1
+                import math
+                d.wmin, d.wmax = float(conn.wmin), float(conn.wmax)
+                d.has_clamp = int(code >= _abi.SNN_RULE_POSTPRE and (math.isfinite(d.wmin) or math.isfinite(d.wmax)))
             if d.rule >= _abi.SNN_RULE_POSTPRE or d.has_norm:
+                if isinstance(conn, Conv2dConnection):
+                    # [Cout,Cin,kh,kw] weights normalise per filter (topology.py:824-837); the combine kernel is
+                    # written for [n_src,n_tgt] matrices with column normalisation
+                    raise NotImplementedError("ShardedWindowRunner: learned Conv2dConnection weights are not combined across ranks yet")
                 out.append((conn, d))
         return out
 

@@ -75,12 +75,14 @@ def weight_structure(conn, w: torch.Tensor):
     return result
 
 
-def fill_conn(d: "_abi.SnnConn", conn, src_idx: int, tgt_idx: int, dt: float, B: int, rule_kwargs=None) -> None:
+def fill_conn(d: "_abi.SnnConn", conn, src_idx: int, tgt_idx: int, dt: float, B: int, rule_kwargs=None, rule: bool = True) -> None:
+    """``rule=False``: geometry, weights and normalisation only (the single-operator compute / normalize calls
+    do not involve the learning rule, whose plan entry may need a run's keyword arguments)."""
     d.src, d.tgt = src_idx, tgt_idx
     rule0 = getattr(conn, "update_rule", None)
-    if hasattr(rule0, "_prepare"):  # rules with state of their own (MSTDP): allocate for this batch size / device
+    if rule and hasattr(rule0, "_prepare"):  # rules with state of their own (MSTDP): allocate for this batch size / device
         rule0._prepare(B, conn.w.device, rule_kwargs or {})
-    conn._fill_desc(d, dt)
+    conn._fill_desc(d, dt, rule)
     w = conn.w
     if w.dtype != torch.float32 or not w.is_contiguous():
         raise TypeError("connection weights must be contiguous float32")
@@ -166,9 +168,9 @@ def build_net(
 
 # ---- single-operator helpers ---------------------------------------------------------------
 
-def _conn_desc(conn, B: int, dt: float = 1.0) -> "_abi.SnnConn":
+def _conn_desc(conn, B: int, dt: float = 1.0, rule: bool = True) -> "_abi.SnnConn":
     d = _abi.SnnConn()
-    fill_conn(d, conn, 0, 1, dt, B)
+    fill_conn(d, conn, 0, 1, dt, B, rule=rule)
     return d
 
 
@@ -179,7 +181,7 @@ def compute_single_connection(conn, s: torch.Tensor) -> torch.Tensor:
     su8 = _as_u8(s if s.dtype in (torch.bool, torch.uint8) else (s != 0)).reshape(B, -1).contiguous()
     su8 = su8.to(conn.w.device)
     out = torch.empty(B, conn.target.n, dtype=torch.float32, device=conn.w.device)
-    d = _conn_desc(conn, B)
+    d = _conn_desc(conn, B, rule=False)
     _backend.conn_compute(d, conn.source.n, conn.target.n, B, su8, out)
     return out.view(B, *conn.target.shape)
 
@@ -207,7 +209,7 @@ def update_single_connection(conn) -> None:
 
 def normalize_single_connection(conn) -> None:
     _backend.require_cuda(conn.w, "connection weights")
-    d = _conn_desc(conn, 1)
+    d = _conn_desc(conn, 1, rule=False)
     _backend.conn_normalize(d, conn.source.n, conn.target.n, conn.w.device)
 
 

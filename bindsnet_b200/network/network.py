@@ -227,7 +227,17 @@ class Network(torch.nn.Module):
             _backend.require_cuda(layer.s, "layer state")
         for conn in self.connections.values():
             _backend.require_cuda(conn.w, "connection weights")
-        _backend.run_window(net, opts, dev)
+        try:
+            _backend.run_window(net, opts, dev)
+        except _backend.BackendError:
+            self._forget_structure()
+            raise
+
+    def _forget_structure(self) -> None:
+        """Drop the cached structure hints of the static weight matrices (``_plan.weight_structure``): after a
+        device-side error they are re-verified on the next window."""
+        for conn in self.connections.values():
+            conn.__dict__.pop("_b200_structure", None)
 
     def _run_stepwise(self, ext, T, normalize, clamps, unclamps, injects, seed, step_offset) -> None:
         """Fallback for per-step observers the kernels cannot serve (monitors on ``x``,
@@ -256,7 +266,11 @@ class Network(torch.nn.Module):
         barrier time-out).  Errors otherwise surface on the next ``run``."""
         dev = self._device()
         if dev.type == "cuda":
-            _backend.poll_errors(dev, sync=True)
+            try:
+                _backend.poll_errors(dev, sync=True)
+            except _backend.BackendError:
+                self._forget_structure()
+                raise
 
     def reset_state_variables(self) -> None:
         """network.py:467-479.  Layers whose reset is the stock one (it is for every population this

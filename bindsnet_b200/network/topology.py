@@ -122,7 +122,7 @@ class Connection(AbstractConnection):
             _plan.normalize_single_connection(self)
 
     # -- plan export -----------------------------------------------------------------------
-    def _fill_desc(self, d: "_abi.SnnConn", dt: float) -> None:
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float, rule: bool = True) -> None:
         d.kind = _abi.SNN_CONN_DENSE
         if self.wmin.numel() != 1 or self.wmax.numel() != 1:
             raise NotImplementedError("per-synapse wmin/wmax tensors are not supported by the CUDA core yet")
@@ -132,7 +132,8 @@ class Connection(AbstractConnection):
         d.norm_abs = 1
         d.norm = float(self.norm) if self.norm is not None else 0.0
         d.dt_scale = 1.0
-        self.update_rule._fill_desc(d)
+        if rule:
+            self.update_rule._fill_desc(d)
 
 
 def _pair(x):
@@ -201,16 +202,21 @@ class Conv2dConnection(AbstractConnection):
                            requires_grad=False)
 
     def compute(self, s: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError(
-            "Conv2dConnection.compute runs inside the Network.run window kernels; the standalone call is not exposed"
-        )
+        """``F.conv2d(s.float(), w, b, stride, padding, dilation)`` for {0,1} spikes (topology.py:799-815), as the
+        spike-gather the window kernels use (``snn_b200_conn_compute``)."""
+        from . import _plan
+
+        return _plan.compute_single_connection(self, s)
 
     def normalize(self) -> None:
-        """topology.py:824-837 (runs at the end of every ``Network.run`` window)."""
+        """Every (out, in) filter scaled to sum ``norm`` (topology.py:824-837); also runs at the end of every
+        ``Network.run`` window."""
         if self.norm is not None:
-            raise NotImplementedError("standalone Conv2dConnection.normalize is not exposed; Network.run applies it")
+            from . import _plan
 
-    def _fill_desc(self, d: "_abi.SnnConn", dt: float) -> None:
+            _plan.normalize_single_connection(self)
+
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float, rule: bool = True) -> None:
         d.kind = _abi.SNN_CONN_CONV2D
         if self.wmin.numel() != 1 or self.wmax.numel() != 1:
             raise NotImplementedError("per-synapse wmin/wmax tensors are not supported by the CUDA core yet")
@@ -226,7 +232,8 @@ class Conv2dConnection(AbstractConnection):
         d.sh, d.sw = self.stride
         d.ph, d.pw = self.padding
         d.dh, d.dw = self.dilation
-        self.update_rule._fill_desc(d)
+        if rule:
+            self.update_rule._fill_desc(d)
 
 
 class AbstractMulticompartmentConnection(ABC, Module):
@@ -314,7 +321,7 @@ class MulticompartmentConnection(AbstractMulticompartmentConnection):
             f._apply(fn)
         return out
 
-    def _fill_desc(self, d: "_abi.SnnConn", dt: float) -> None:
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float, rule: bool = True) -> None:
         d.kind = _abi.SNN_CONN_MCC
         self._weight()._fill_desc(d, dt, self.manual_update)
 

@@ -8,7 +8,7 @@ device staging) while the window kernel of batch k runs, and hands ``run`` a dev
 
     pre = WindowPrefetcher(device, iter_of_host_tensors)
     for x_dev in pre:                 # x_dev is ready on the compute stream
-        net.run({"X": x_dev}, time=T)
+        net.run({"X": x_dev}, time=T)  # the buffer is handed back when the loop asks for the next item
 
 ``AsyncReadback`` is the other direction: the per-window result (spike counts for label assignment,
 ``examples/mnist/batch_eth_mnist.py:300-318``) is copied to pinned host memory without stalling the
@@ -64,24 +64,29 @@ class WindowPrefetcher:
         return self
 
     def __next__(self) -> torch.Tensor:
+        self.release()                             # whatever was enqueued since the last item used that buffer
         if self._pending is None:
             raise StopIteration
         slot = self._pending
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._ready[slot])          # the consumer's stream waits for the copy
         out = self._bufs[slot]
+        out.record_stream(cur)                     # allocated on the copy stream, consumed on this one
+        self._last = slot
         self._issue()                              # start copying the next item right away
-        # mark the buffer free once everything the caller enqueues before its NEXT __next__ is done:
-        # recorded lazily at the next call on the same slot via this event
-        ev = torch.cuda.Event()
-        self._free[slot] = ev
-        self._last = (slot, ev)
         return out
 
     def release(self) -> None:
-        """Record that the consumer is done with the tensor returned last (call after ``run``)."""
-        slot, ev = self._last
+        """Hand the tensor returned last back to the prefetcher: the copy that reuses its buffer waits for
+        everything enqueued on the current stream so far.  Called automatically when the next item is
+        requested; call it earlier (right after ``run``) to let that copy start sooner."""
+        slot = getattr(self, "_last", None)
+        if slot is None:
+            return
+        ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
+        self._free[slot] = ev
+        self._last = None
 
 
 class AsyncReadback:

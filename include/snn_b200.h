@@ -83,6 +83,7 @@ extern "C" {
 #define SNN_ERR_CUDA 8           /* a CUDA runtime call failed                                    */
 #define SNN_ERR_NONBINARY 16     /* (device flag) an Input layer received a value outside {0,1}   */
 #define SNN_ERR_BARRIER 32       /* (device flag) grid barrier timed out — kernel bailed out      */
+#define SNN_ERR_STRUCTURE 64     /* (device flag) a weight matrix does not have the structure its SNN_W_* hint claims */
 
 /* One population of neurons.  Reference: Nodes.__init__ nodes.py:15-86 + subclass ctor. */
 typedef struct snn_layer {

@@ -624,7 +624,8 @@ int snn_oracle_conn_compute(const snn_conn_t *C, int32_t n_src, int32_t n_tgt, i
     if (!C || !C->w || !s || !out) return SNN_ERR_BAD_ARG;
     snn_layer_t S; memset(&S, 0, sizeof(S)); S.n = n_src; S.s = (uint8_t *)s;
     memset(out, 0, sizeof(float) * (size_t)B * n_tgt);
-    conn_compute(C, &S, n_tgt, B, out, 0);
+    if (C->kind == SNN_CONN_CONV2D) conv_compute(C, &S, B, out, 0);
+    else conn_compute(C, &S, n_tgt, B, out, 0);
     return SNN_OK;
 }
 
@@ -649,6 +650,7 @@ int snn_oracle_conn_update(const snn_net_t *net, int32_t ci, int32_t B) {
  * (topology_features.py:250-266). */
 int snn_oracle_conn_normalize(const snn_conn_t *C, int32_t n_src, int32_t n_tgt) {
     if (!C || !C->w) return SNN_ERR_BAD_ARG;
-    if (C->has_norm) normalize_cols(C->w, n_src, n_tgt, C->norm_abs, C->norm);
+    if (C->has_norm && C->kind == SNN_CONN_CONV2D) normalize_conv(C);
+    else if (C->has_norm) normalize_cols(C->w, n_src, n_tgt, C->norm_abs, C->norm);
     return SNN_OK;
 }

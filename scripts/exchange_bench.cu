@@ -16,7 +16,7 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned *p) { unsigned v; 
 __device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long *p) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_relaxed64(unsigned long long *p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
-__global__ void bench(unsigned *bar, unsigned long long *hdr, unsigned long long *ent, unsigned *data, long long *out, int iters, int mode, int nent) {
+__global__ void bench(unsigned *bar, unsigned long long *hdr, unsigned long long *ent, unsigned *data, long long *out, int iters, int mode, int nent, unsigned long long *inbox) {
     const unsigned G = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ unsigned s_sum;
@@ -92,6 +92,41 @@ __global__ void bench(unsigned *bar, unsigned long long *hdr, unsigned long long
                     }
                 }
             }
+        } else if (mode == 8 || mode == 9) {
+            // personalised all-to-all (the NCCL LL idea): every (destination, source) pair owns one 32-byte
+            // sector {header, 3 inline entries}, every word tagged; a CTA stores its message G times (one
+            // copy per destination) and polls only its own inbox — no line is read by more than one CTA
+            const int par = it & 1;
+            const unsigned long long tag = (unsigned long long)(gen & 0xffu) << 56;
+            const int ne = (mode == 9 && (blockIdx.x % 10) == (it % 10)) ? nent : 0;
+            if (tid < (int)G) {
+                unsigned long long *slot = inbox + (((size_t)par * 160 + tid) * 160 + blockIdx.x) * 4;
+                for (int e = 0; e < ne; ++e) st_relaxed64(slot + 1 + e, tag | (unsigned)e);
+                st_relaxed64(slot, tag | (unsigned)ne);
+            }
+            if (warp == 0) {
+                unsigned long long h[5], e0[5], e1[5], e2[5];
+                unsigned need = 0;
+                #pragma unroll
+                for (int k = 0; k < 5; ++k) if (lane + 32 * k < G) need |= 1u << k;
+                while (need) {
+                    #pragma unroll
+                    for (int k = 0; k < 5; ++k) if ((need >> k) & 1u) {
+                        const unsigned long long *slot = inbox + (((size_t)par * 160 + blockIdx.x) * 160 + lane + 32 * k) * 4;
+                        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(h[k]), "=l"(e0[k]) : "l"(slot) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(e1[k]), "=l"(e2[k]) : "l"(slot + 2) : "memory");
+                    }
+                    #pragma unroll
+                    for (int k = 0; k < 5; ++k) if (((need >> k) & 1u) && (h[k] >> 56) == (gen & 0xffu)) {
+                        const int n_ = (int)(h[k] & 0xffu);
+                        bool ok = true;
+                        if (n_ > 0) ok = ok && (e0[k] >> 56) == (gen & 0xffu);
+                        if (n_ > 1) ok = ok && (e1[k] >> 56) == (gen & 0xffu);
+                        if (n_ > 2) ok = ok && (e2[k] >> 56) == (gen & 0xffu);
+                        if (ok) { need &= ~(1u << k); acc += (unsigned)(e0[k] + e1[k]); }
+                    }
+                }
+            }
         } else if (mode == 4) {
             if (tid < 128) {
                 unsigned *w = data + (size_t)tid * 32;  // 128-byte stride
@@ -110,13 +145,13 @@ int main() {
     unsigned *bar, *data; unsigned long long *hdr, *ent; long long *out;
     cudaMalloc(&bar, 1024); cudaMalloc(&data, 128 * 128 * 4); cudaMalloc(&out, 160 * 8);
     cudaMalloc(&hdr, 2 * 160 * 16 * 8); cudaMalloc(&ent, 2 * 160 * 64 * 8);
+    unsigned long long *inbox; cudaMalloc(&inbox, 2 * 160 * 160 * 32); cudaMemset(inbox, 0, 2 * 160 * 160 * 32);
     const int iters = 4000;
-    for (int G : {100, 134, 148}) for (int threads : {384}) for (int mode = 0; mode < 8; ++mode) for (int nent : {0, 2}) {
-        if (nent && mode != 3 && mode != 6) continue;
-        if ((mode == 3 || mode == 6) && !nent) continue;
-        if (mode == 2 || mode == 3) continue;
+    for (int G : {100, 134, 148}) for (int threads : {384}) for (int mode : {0, 4, 8, 9}) for (int nent : {0, 2}) {
+        if (nent && mode != 9) continue;
+        if (mode == 9 && !nent) continue;
         cudaMemset(bar, 0, 1024); cudaMemset(data, 0, 128 * 128 * 4); cudaMemset(hdr, 0, 2 * 160 * 16 * 8); cudaMemset(ent, 0, 2 * 160 * 64 * 8);
-        void *args[] = {&bar, &hdr, &ent, &data, &out, (void *)&iters, &mode, &nent};
+        void *args[] = {&bar, &hdr, &ent, &data, &out, (void *)&iters, &mode, &nent, &inbox};
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
         cudaError_t e = cudaLaunchCooperativeKernel((void *)bench, dim3(G), dim3(threads), args, 0, 0);

@@ -227,8 +227,21 @@ def test_conv2d_connection_constructor_and_window_like_reference_tests():
     assert float(c.w.min()) >= -0.5 and float(c.w.max()) <= 0.5
     with pytest.raises(AssertionError):
         Conv2dConnection(X, LIFNodes(shape=[3, 4, 4]), kernel_size=3, stride=2, padding=1)   # wrong target size
-    with pytest.raises(NotImplementedError):
-        c.compute(torch.zeros(1, 2, 9, 9))                                                    # window-only
+    from bindsnet_b200._backend import BackendError
+    with pytest.raises(BackendError):
+        c.compute(torch.zeros(1, 2, 9, 9))                                                    # CPU tensors: no CPU fallback
+    g0 = torch.Generator().manual_seed(3)
+    s0 = torch.bernoulli(0.3 * torch.ones(4, 2, 9, 9), generator=g0).byte()
+    cn = Conv2dConnection(X, H, kernel_size=3, stride=2, padding=1, wmin=-0.5, wmax=0.5, norm=0.7,
+                          b=torch.tensor([0.1, -0.2, 0.3]))
+    with OracleBackend():  # standalone operators (topology.py:799-815, 824-837) against torch
+        out = cn.compute(s0)
+        ref = torch.nn.functional.conv2d(s0.float(), cn.w, cn.b, stride=2, padding=1)
+        assert out.shape == ref.shape and torch.allclose(out, ref, atol=1e-5)
+        w0 = cn.w.clone()
+        cn.normalize()
+        expect = w0 * (0.7 / w0.sum(dim=(2, 3), keepdim=True))
+        assert torch.allclose(cn.w, expect, rtol=1e-5, atol=1e-6)
     net = Network(dt=1.0, batch_size=2)
     net.add_layer(X, "X"); net.add_layer(H, "H")
     net.add_connection(c, "X", "H")
