@@ -128,15 +128,19 @@ struct Misc2 {  // small per-step scratch (shared memory)
     int ncand[2];           // samples with a candidate in this tile (by step parity)
     uint32_t candgrp[2];    // column groups holding a candidate (by step parity)
     uint32_t colwin[8];     // per column group: bit c: column 4g+c has a winner in the step being finalised
+    uint32_t candmask[2][8][8];  // by step parity, per column group: samples holding a candidate in that group
+    int ncs[2][8];          // ... how many, listed in candlist[parity][group][]
     int nwl[8];             // per column group: number of winners of the step being finalised
     int nlive[8];           // per column group: samples with a non-zero trace, listed in live[g * Bp ...]
     int nact;               // entries of the Ai list
     int nact_snap;          // ... at the last step boundary: what the list pass of the running step covers
     int abort;              // exchange time-out: leave the time loop
+    int negzero;            // the weight tile held a -0.0 when it was loaded (post_rows2 must not skip rows)
     int denseflag[2];       // staged slot (by buffer) holds a sample whose event list overflowed EV_CAP
     long long pc[NPROF];    // phase timers (profiling variant only)
 };
-static_assert(offsetof(Misc2, wl) % 16 == 0 && offsetof(Misc2, nz4) % 16 == 0 && offsetof(Misc2, wmask) % 16 == 0, "Misc2: 16-byte rows");
+static_assert(offsetof(Misc2, wl) % 16 == 0 && offsetof(Misc2, nz4) % 16 == 0 && offsetof(Misc2, wmask) % 16 == 0 &&
+              offsetof(Misc2, candmask) % 16 == 0, "Misc2: 16-byte rows");
 
 struct SmemLayout2 { size_t W, tx, ev, inT, xrow, rep, theta, live, tab, ai, misc, total; };
 
@@ -148,8 +152,9 @@ __host__ __device__ inline int ev_count_bytes(int B) { return (int)al16(2 * (siz
 __host__ __device__ inline int ev_block_bytes(int B) { return ev_count_bytes(B) + 2 * B * EV_CAP; }
 __host__ __device__ inline int ev_pos(int B, int b, int k) { return ((k >> 2) * B + b) * 4 + (k & 3); }   // u16 index behind the counts
 __host__ __device__ inline int tile_stride(int TJ) { return ((TJ / 4) & 1) ? TJ : TJ + 4; }  // odd number of 16-byte chunks per row
-// tab region: keyT u64 [2][Bp] | isumT u32 [2][Bp] | aispk u32 [2][Bp] | candstamp u32 [2][Bp] | candslot i32 [2][Bp]
-__host__ __device__ inline size_t tab_bytes(int Bp) { return (size_t)Bp * (16 + 8 + 8 + 8 + 8); }
+// tab region: keyT u64 [2][Bp] | isumT u32 [2][Bp] | aispk u32 [2][Bp] | candstamp u32 [2][Bp] | candslot i32 [2][Bp] |
+//             candlist u8 [2][8][Bp]
+__host__ __device__ inline size_t tab_bytes(int Bp) { return (size_t)Bp * (16 + 8 + 8 + 8 + 8 + 16); }
 // ai region: v f32 [cap] | rc f32 [cap] | id u16 [cap] | claim u16 [2][cap] | map u16 [cap] | fl u8 [cap]
 __host__ __device__ inline size_t ai_bytes(int cap) { return al16((size_t)cap * (4 + 4 + 2 + 4 + 2 + 1)); }
 __host__ __device__ inline SmemLayout2 smem_layout2(int P, int TJ, int B, int Bp, int BW, int nrep) {
@@ -172,29 +177,54 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int P, int TJ, int B, int Bp
 
 // Constants and pointers of the STDP passes, kept in shared memory so that the passes live out of line
 // (the per-step code has to stay inside the instruction cache).
-struct PassCtx2 {
+// the part the STDP passes copy into registers
+struct PassK {
     float *W, *tx;
-    const float *xrow;
     const uint32_t *inT;
     const unsigned char *evb;
     const uint16_t *live;
+    const uint8_t *candlist;
     Misc2 *M;
     int P, B, Bp, evblk, cntb, WS;
     int pre_on, has_clamp;
     float dts, wmin, wmax, nu1;
 };
+struct PassCtx2 {
+    PassK k;
+    // spike-gather
+    const uint32_t *inS;
+    int SW;
+    // Ai list (LIFNodes constants and arrays), exchange
+    float *ai_v, *ai_rc;
+    uint16_t *ai_id, *ai_claim, *ai_map;
+    uint8_t *ai_fl;
+    uint32_t *aispk;
+    unsigned int *sisum;
+    unsigned long long *win;
+    uint8_t *I_rec_s;
+    int32_t *I_rec_count;
+    float I_decay, I_rest, I_dt, I_thresh, I_refrac, I_reset;
+    int n, j0, TJ, aicap;
+    // candidates
+    uint32_t *candstamp;
+    int *candslot;
+    float *xrow_w;
+    const float *xtr;
+    uint32_t seed, step_offset;
+    int liE, one_spike, stage_on, nostage;
+};
 
-// STDP of one step in list form on ONE column group c4 (MCC_learning.py:234-299, learning.py:390-420), run by
-// the nthr0 threads that own the group: the work items are (live sample of the group, event of that sample).
-// Several samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel owns
-// the row (no atomics), sums the traces of all of them in ascending sample order (the oracle's order) and
-// rewrites the group's 4 weights:  w - U*dt [+ x_pre*nu1*dt for a winner column], clamp.
-// `gwin` != 0 (late pass): columns with a winner get their post term here; rows this pass does not touch
-// get it from post_rows2().
+// STDP pre term of one step in list form on ONE column group c4 (MCC_learning.py:234-263, learning.py:390-405),
+// run by the nthr0 threads that own the group in the shadow of the exchange: the work items are (live sample of
+// the group, event of that sample).  Several samples can spike at the same pixel: the item whose sample is the
+// LOWEST live one at that pixel owns the row (no atomics), sums the traces of all of them in ascending sample
+// order (the oracle's order) and rewrites the group's 4 weights:  w - U*dt, clamp.
+// Rows at which a sample holding a CANDIDATE of this group spiked (`dm`: those samples) are left alone: the
+// candidate's trace is undecided until the exchange lands; stdp_late2 finishes exactly those rows.
 constexpr int EVH = 16;  // list slots enumerated per live sample and round
 template <int CG, int BW>
-__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const float *xrow, int tid0, int nthr0) {
-    const PassCtx2 c_ = *cx;
+__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, const uint32_t *dm, int tid0, int nthr0) {
+    const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS, B = c_.B;
     const Misc2 &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
@@ -202,11 +232,15 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
     const uint16_t *lv = c_.live + c4 * c_.Bp;
     const int total = M.nlive[c4] * EVH;
-    uint32_t z[BW];
+    uint32_t z[BW], d[BW];
     {
-        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
-        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w;
-        if (BW == 8) { const uint4 z1 = *(const uint4 *)&M.nz4[c4][4]; z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
+        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0], d0 = *(const uint4 *)dm;
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w;
+        if (BW == 8) {
+            const uint4 z1 = *(const uint4 *)&M.nz4[c4][4], d1 = *(const uint4 *)(dm + 4);
+            z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w;
+            d[BW - 4] = d1.x; d[BW - 3] = d1.y; d[BW - 2] = d1.z; d[BW - 1] = d1.w;
+        }
     }
     #pragma unroll 1
     for (int idx = tid0; idx < total; idx += nthr0) {
@@ -215,15 +249,18 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint
         #pragma unroll 1
         for (int k = idx % EVH; k < cnt; k += EVH) {
             const int i = el[ev_pos(B, bb, k)];
-            uint32_t a[BW];
+            uint32_t a[BW], defer = 0;
             {
                 const uint4 q0 = cT[i * (BW / 4)];
                 a[0] = q0.x & z[0]; a[1] = q0.y & z[1]; a[2] = q0.z & z[2]; a[3] = q0.w & z[3];
+                defer = (q0.x & d[0]) | (q0.y & d[1]) | (q0.z & d[2]) | (q0.w & d[3]);
                 if (BW == 8) {
                     const uint4 q1 = cT[i * (BW / 4) + 1];
                     a[BW - 4] = q1.x & z[BW - 4]; a[BW - 3] = q1.y & z[BW - 3]; a[BW - 2] = q1.z & z[BW - 2]; a[BW - 1] = q1.w & z[BW - 1];
+                    defer |= (q1.x & d[BW - 4]) | (q1.y & d[BW - 3]) | (q1.z & d[BW - 2]) | (q1.w & d[BW - 1]);
                 }
             }
+            if (defer) continue;
             // owner of row i in this group = the lowest live sample spiking at pixel i
             uint32_t lower = 0;
             #pragma unroll
@@ -233,7 +270,7 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint
             }
             if (lower) continue;
             float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
-            #pragma unroll
+            #pragma unroll 1
             for (int g = 0; g < BW; ++g) {
                 uint32_t mm = a[g];
                 while (mm) {
@@ -249,15 +286,7 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint
             const float Uv[4] = {U0, U1, U2, U3};
             #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                float w = wv[c];
-                w = w - Uv[c] * c_.dts;  // x * 1.0f is exact: the classic rule's missing dt factor is dts = 1
-                if ((gwin >> c) & 1u) {  // the column's single winner (fast late pass): post term
-                    uint32_t e = M.wl[c4][0];
-                    #pragma unroll 1
-                    for (int k2 = 1; k2 < M.nwl[c4]; ++k2) if ((M.wl[c4][k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[c4][k2];
-                    const float V = 0.0f + xrow[(e & 0xffu) * P + i] * c_.nu1;
-                    w = w + V * c_.dts;
-                }
+                float w = wv[c] - Uv[c] * c_.dts;  // x * 1.0f is exact: the classic rule's missing dt factor is dts = 1
                 if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
                 wv[c] = w;
             }
@@ -266,38 +295,131 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, uint
     }
 }
 
+// Late STDP of column group c4 on the rows stdp_list2 left alone — the pixels at which a candidate-holding
+// sample (`dm`) spiked: now that the winners are known, pre term (traces of all live samples at the pixel,
+// ascending), then for a winner column (`gwin`) the post term of its single winner, then clamp
+// (MCC_learning.py:234-299, 86-110).  Work items: (candidate sample, event of that sample); when several
+// candidate samples spike at a pixel the lowest of them owns the row.
+template <int CG, int BW>
+__device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const uint32_t *dm, int par_, const float *xrow,
+                                        int tid0, int nthr0) {
+    const PassK c_ = cx->k;
+    const int P = c_.P, WS = c_.WS, B = c_.B;
+    const Misc2 &M = *c_.M;
+    const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
+    const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
+    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    uint32_t z[BW], d[BW];
+    {
+        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0], d0 = *(const uint4 *)dm;
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w;
+        if (BW == 8) {
+            const uint4 z1 = *(const uint4 *)&M.nz4[c4][4], d1 = *(const uint4 *)(dm + 4);
+            z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w;
+            d[BW - 4] = d1.x; d[BW - 3] = d1.y; d[BW - 2] = d1.z; d[BW - 1] = d1.w;
+        }
+    }
+    const int ncs = M.ncs[par_][c4];
+    const uint8_t *cl = c_.candlist + (par_ * 8 + c4) * c_.Bp;
+    #pragma unroll 1
+    for (int idx = tid0; idx < ncs * EV_CAP; idx += nthr0) {
+        const int bb = cl[idx / EV_CAP];
+        const int k = idx % EV_CAP;
+        if (k >= (int)ec[bb]) continue;
+        const int i = el[ev_pos(B, bb, k)];
+        uint32_t a[BW], cm[BW];
+        {
+            const uint4 q0 = cT[i * (BW / 4)];
+            a[0] = q0.x & z[0]; a[1] = q0.y & z[1]; a[2] = q0.z & z[2]; a[3] = q0.w & z[3];
+            cm[0] = q0.x & d[0]; cm[1] = q0.y & d[1]; cm[2] = q0.z & d[2]; cm[3] = q0.w & d[3];
+            if (BW == 8) {
+                const uint4 q1 = cT[i * (BW / 4) + 1];
+                a[BW - 4] = q1.x & z[BW - 4]; a[BW - 3] = q1.y & z[BW - 3]; a[BW - 2] = q1.z & z[BW - 2]; a[BW - 1] = q1.w & z[BW - 1];
+                cm[BW - 4] = q1.x & d[BW - 4]; cm[BW - 3] = q1.y & d[BW - 3]; cm[BW - 2] = q1.z & d[BW - 2]; cm[BW - 1] = q1.w & d[BW - 1];
+            }
+        }
+        uint32_t lower = 0;   // a lower candidate sample spiking here owns the row
+        #pragma unroll
+        for (int g = 0; g < BW; ++g) {
+            const uint32_t below = g < (bb >> 5) ? 0xffffffffu : (g == (bb >> 5) ? ((1u << (bb & 31)) - 1u) : 0u);
+            lower |= cm[g] & below;
+        }
+        if (lower) continue;
+        float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
+        uint32_t anya = 0;
+        #pragma unroll 1
+        for (int g = 0; g < BW; ++g) {
+            uint32_t mm = a[g];
+            anya |= mm;
+            while (mm) {
+                const int b2 = g * 32 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float4 t4 = *(const float4 *)(c_.tx + b2 * (4 * CG) + 4 * c4);
+                U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
+            }
+        }
+        if (!c_.pre_on) anya = 0;
+        if (!(anya | gwin)) continue;
+        float *wp = c_.W + i * WS + 4 * c4;
+        const float4 w4 = *(const float4 *)wp;
+        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float Uv[4] = {U0, U1, U2, U3};
+        #pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float w = wv[c];
+            if (anya) w = w - Uv[c] * c_.dts;
+            if ((gwin >> c) & 1u) {  // the column's single winner (fast late pass): post term
+                uint32_t e = M.wl[c4][0];
+                #pragma unroll 1
+                for (int k2 = 1; k2 < M.nwl[c4]; ++k2) if ((M.wl[c4][k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[c4][k2];
+                const float V = 0.0f + xrow[(e & 0xffu) * P + i] * c_.nu1;
+                w = w + V * c_.dts;
+            }
+            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+            wv[c] = w;
+        }
+        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    }
+}
+
 // Post term of the fast late pass of column group c4 for the rows stdp_list2 did not touch: per winner
 // (column, staged row): w + x_pre[b,i]*nu1*dt, clamp (MCC_learning.py:267-299, 86-110).  A row was handled
-// by the list pass iff a live sample of the group spiked at its pixel.
+// by stdp_late2 iff a candidate-holding sample (`dm`) spiked at its pixel.  Rows whose pre-synaptic trace is
+// exactly zero are skipped when `skip0` says that is exact: w + 0*nu1*dt == w bitwise unless w is -0.0 (the
+// tile holds none: checked when it is loaded), and the clamp of an in-range weight is the identity.
 template <int CG, int BW>
-__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int nwl, const float *xrow, int tid0, int nthr0) {
-    const PassCtx2 c_ = *cx;
+__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int nwl, const uint32_t *dm, const float *xrow, int skip0, int tid0,
+                                        int nthr0) {
+    const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS;
     const Misc2 &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
-    uint32_t z[BW];
+    uint32_t z[BW];   // the samples whose rows stdp_late2 handles
     {
-        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0];
+        const uint4 z0 = *(const uint4 *)dm;
         z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w;
-        if (BW == 8) { const uint4 z1 = *(const uint4 *)&M.nz4[c4][4]; z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
+        if (BW == 8) { const uint4 z1 = *(const uint4 *)(dm + 4); z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w; }
     }
     #pragma unroll 1
-    for (int i = tid0; i < P; i += nthr0) {
-        if (c_.pre_on) {
-            const uint4 q0 = cT[i * (BW / 4)];
-            uint32_t any = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
-            if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
-            if (any) continue;  // done by the list pass
-        }
-        #pragma unroll 1
-        for (int k = 0; k < nwl; ++k) {   // distinct columns
-            const uint32_t e = M.wl[c4][k];
-            float *wp = c_.W + i * WS + (e >> 16);
-            float w = *wp;
-            const float V = 0.0f + xrow[(e & 0xffu) * P + i] * c_.nu1;
+    for (int k = 0; k < nwl; ++k) {   // distinct columns
+        const uint32_t e = M.wl[c4][k];
+        const float *xr = xrow + (e & 0xffu) * P;
+        float *wcol = c_.W + (e >> 16);
+        #pragma unroll 2
+        for (int i = tid0; i < P; i += nthr0) {
+            const float xv = xr[i];
+            if (skip0 && xv == 0.0f) continue;
+            {
+                const uint4 q0 = cT[i * (BW / 4)];
+                uint32_t any = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
+                if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
+                if (any) continue;  // done by stdp_late2
+            }
+            float w = wcol[i * WS];
+            const float V = 0.0f + xv * c_.nu1;
             w = w + V * c_.dts;
             if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
-            *wp = w;
+            wcol[i * WS] = w;
         }
     }
 }
@@ -305,11 +427,12 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int 
 // STDP of one step of column group c4 in row form, general: pre and post term of a column applied together
 // (pre, post, clamp — the reference's order).  Used for slots with an overflowed event list, more than XR
 // winners, two winners in one column, a winner whose trace row is not staged.
-// `cand` = staged samples (rows of xrow), `xsrc` = the step's input traces in global memory.
+// `cand` = staged samples (rows of xrow), `xsrc` = the step's input traces in global memory.  `dm` != NULL: the
+// pre term only on the rows stdp_list2 left alone (a sample of `dm` spiked there); the post term on every row.
 template <int CG, int BW>
 __device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const int *cand, int ns, const float *xsrc,
-                                        const float *xrow, int tid0, int nthr0) {
-    const PassCtx2 c_ = *cx;
+                                        const float *xrow, const uint32_t *dm, int tid0, int nthr0) {
+    const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS, TJ = 4 * CG;
     const Misc2 &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
@@ -325,6 +448,11 @@ __device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint
             const uint4 z1 = c_.pre_on ? *(const uint4 *)&M.nz4[c4][4] : make_uint4(0, 0, 0, 0);
             m[BW - 4] = q1.x & z1.x; m[BW - 3] = q1.y & z1.y; m[BW - 2] = q1.z & z1.z; m[BW - 1] = q1.w & z1.w;
             anym |= m[BW - 4] | m[BW - 3] | m[BW - 2] | m[BW - 1];
+        }
+        if (dm) {   // rows already finished by the early pass: no pre term
+            uint32_t df = (q0.x & dm[0]) | (q0.y & dm[1]) | (q0.z & dm[2]) | (q0.w & dm[3]);
+            if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; df |= (q1.x & dm[4]) | (q1.y & dm[5]) | (q1.z & dm[6]) | (q1.w & dm[7]); }
+            if (!df) anym = 0u;
         }
         const bool pre_t = anym != 0u;
         if (!(pre_t || gwin)) continue;
@@ -397,6 +525,97 @@ __device__ __forceinline__ float refrac_replay(float rc, float dt, int T) {
     return rc;
 }
 
+// Spike-gather of 4 columns (Wc = the thread's column group in row 0 of the tile) for the spikes of sample b in
+// list block `blk` (slot `slot`): p[c] = sum_{i in sX[b]} W[i][c], i ascending (topology.py:437-479).  One copy
+// for the step itself and for the gather that runs ahead in the shadow of the exchange.
+template <int WS>
+__device__ __noinline__ float4 gather2(const PassCtx2 *cx, const unsigned char *blk, int slot, int b, const float *Wc) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    const int cnt = ((const uint16_t *)blk)[b];
+    const int B = cx->k.B;
+    if (cnt > EV_CAP)   // dense sample: walk the bit row in global memory (rare, slow path)
+        return gather_dense2(cx->inS + ((size_t)slot * B + b) * cx->SW, cx->SW, Wc, WS);
+    const uint2 *l4 = (const uint2 *)(blk + cx->k.cntb) + b;
+    #pragma unroll 1
+    for (int k = 0; k < cnt; k += 4) {
+        const uint2 q = l4[(k >> 2) * B];  // 4 pixel indices; tail padded with P (zero row)
+        const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
+        const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
+        const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
+        const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * WS);
+        p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
+        p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
+        p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
+        p0 = p0 + r3.x; p1 = p1 + r3.y; p2 = p2 + r3.z; p3 = p3 + r3.w;
+    }
+    return make_float4(p0, p1, p2, p3);
+}
+
+// One LIFNodes.forward step (nodes.py:500-529) of Ai list entry e with input xin at step t; a spike goes to the
+// exchange (Ai spike count of the sample), to the tile's own-spike bits and to the monitors.
+__device__ __noinline__ void ai_step2(const PassCtx2 *cx, int e, float xin, int t) {
+    float v = cx->ai_v[e], rc = cx->ai_rc[e];
+    uint32_t fl = cx->ai_fl[e];
+    v = cx->I_decay * (v - cx->I_rest) + cx->I_rest;
+    if (!(fl & 1u)) { if (rc > 0.0f) xin = 0.0f; rc = rc - cx->I_dt; }   // undisturbed counter: <= 0 by construction
+    v = v + xin;
+    fl &= 1u;
+    if (v >= cx->I_thresh) {
+        rc = cx->I_refrac; v = cx->I_reset; fl = 2u;
+        const int id = cx->ai_id[e], sb_ = id >> 8, col = id & 0xff;
+        atomicOr(&cx->aispk[(t & 1) * cx->k.Bp + sb_], 1u << col);
+        atomicAdd(cx->sisum + (t % 3) * cx->k.B + sb_, 1u);
+        if (cx->I_rec_s) cx->I_rec_s[((size_t)t * cx->k.B + sb_) * cx->n + cx->j0 + col] = 1;
+        if (cx->I_rec_count) atomicAdd(cx->I_rec_count + (size_t)sb_ * cx->n + cx->j0 + col, 1);
+    }
+    cx->ai_v[e] = v; cx->ai_rc[e] = rc; cx->ai_fl[e] = (uint8_t)fl;
+}
+
+// A thread found threshold crossers among its 4 neurons at step t (`cand`, nodes.py:1088-1092): count them for
+// theta (nodes.py:1093-1094), send the best one_spike key to the exchange (nodes.py:1097-1105), claim the partner
+// Ai neurons for step t+1, mark the column group / sample as candidate-holding, and stage the sample's input-trace
+// row of step t for a possible post term.  Rare per thread: kept out of line.
+__device__ __noinline__ void on_candidate2(const PassCtx2 *cx, uint32_t cand, int b, int cg, int t) {
+    Misc2 &M = *cx->k.M;
+    const int par = t & 1, TJ = cx->TJ, jc = cx->j0 + 4 * cg, B = cx->k.B, Bp = cx->k.Bp, P = cx->k.P;
+    unsigned long long mykey = 0ull;
+    #pragma unroll 1
+    for (int c = 0; c < 4; ++c)
+        if ((cand >> c) & 1u) {
+            const int col = 4 * cg + c;
+            atomicAdd(&M.cnt[par][col], 1);
+            if (cx->one_spike) {
+                const unsigned long long k2 = snn_one_spike_key(cx->seed, (uint32_t)t + cx->step_offset, (uint32_t)cx->liE, (uint32_t)b, (uint32_t)(jc + c));
+                mykey = k2 > mykey ? k2 : mykey;
+            }
+            // the partner Ai neuron is this thread's at step t+1, whether the candidate wins or not
+            unsigned e = cx->ai_map[b * TJ + col];
+            if (e == AI_NONE) {
+                e = (unsigned)atomicAdd(&M.nact, 1);
+                cx->ai_v[e] = cx->I_rest; cx->ai_rc[e] = 0.0f; cx->ai_id[e] = (uint16_t)((b << 8) | col); cx->ai_fl[e] = 1;
+                cx->ai_claim[par * cx->aicap + e] = (uint16_t)AI_NONE;
+                cx->ai_map[b * TJ + col] = (uint16_t)e;
+            }
+            cx->ai_claim[(par ^ 1) * cx->aicap + e] = (uint16_t)(t + 1);   // slot of parity (t + 1) & 1
+        }
+    atomicOr(&M.candgrp[par], 1u << cg);
+    atomicOr(&M.candmask[par][cg][b >> 5], 1u << (b & 31));
+    ((uint8_t *)cx->k.candlist)[(par * 8 + cg) * Bp + atomicAdd(&M.ncs[par][cg], 1)] = (uint8_t)b;
+    if (cx->one_spike) atomicMax(cx->win + (t % 3) * B + b, mykey);
+    if (cx->stage_on) {  // stage x_pre[b,:] of step t for the post term, once per sample
+        const uint32_t old = atomicExch(&cx->candstamp[par * Bp + b], (uint32_t)(t + 1));
+        if (old != (uint32_t)(t + 1)) {
+            const int s = atomicAdd(&M.ncand[par], 1);
+            if (s < XR && !cx->nostage) {
+                M.candb[par][s] = b;
+                cx->candslot[par * Bp + b] = s;
+                mbar_expect_tx(&M.mbar_x[par], (uint32_t)(P * 4));
+                bulk_g2s(cx->xrow_w + (par * XR + s) * P, cx->xtr + ((size_t)t * B + b) * P, (uint32_t)(P * 4), &M.mbar_x[par]);
+            } else cx->candslot[par * Bp + b] = -1;
+        }
+    }
+}
+
 // CG: float4 column groups per CTA (TJ = 4 CG columns); BW: 32-bit words of a per-pixel sample mask
 // (4 -> B <= 128).  Threads = Bp * CG compute threads, thread (cg, b), Bp = B rounded up to a multiple
 // of 32, plus one exchange warp.  The Bp threads of a column group form a pipeline of their own (named
@@ -425,10 +644,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     uint32_t *aispk = isumT + 2 * Bp;                                   // [2][Bp] bit col: Ai (b, col) of this tile spiked in that step
     uint32_t *candstamp = aispk + 2 * Bp;                               // [2][Bp] by step parity: step + 1 of the sample's last staged row
     int *candslot = (int *)(candstamp + 2 * Bp);                        // [2][Bp] its slot in xrow (-1: not staged)
+    uint8_t *candlist = (uint8_t *)(candslot + 2 * Bp);                 // [2][8][Bp] by step parity, per column group: candidate-holding samples
     const int aicap = Bp * TJ;
     float *ai_v = (float *)(smem + Q.o_ai);
     float *ai_rc = ai_v + aicap;
-    uint16_t *ai_id = (uint16_t *)(ai_rc + aicap);      // b * TJ + col
+    uint16_t *ai_id = (uint16_t *)(ai_rc + aicap);      // b << 8 | col
     uint16_t *ai_claim = ai_id + aicap;                  // [2][cap] by step parity: step in which the neuron's owner thread (not the
                                                          // list pass) runs it
     uint16_t *ai_map = ai_claim + 2 * aicap;             // (b * TJ + col) -> list entry, AI_NONE
@@ -461,6 +681,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     #define PROFX(k) { if (PROFV && tid == NC) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
 
     // ---- prologue: W tile, theta, inhibition table, tables, Ai list, state registers -----------
+    bool negz = false;
     {
         constexpr int U = 8;
         const int total = (P + 1) * TJ, nthr = blockDim.x;
@@ -475,7 +696,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int idx = base + u * nthr + tid, i = idx / TJ, jj = idx - i * TJ;
-                if (idx < total) W[i * WS + jj] = v[u];
+                if (idx < total) { W[i * WS + jj] = v[u]; negz |= __float_as_uint(v[u]) == 0x80000000u; }
             }
         }
     }
@@ -506,17 +727,28 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         mbar_init(&M.mbar_x[0], 1);
         mbar_init(&M.mbar_x[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.abort = 0; M.nact = 0;
+        M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.abort = 0; M.nact = 0; M.negzero = 0;
         for (int g = 0; g < 8; ++g) { M.colwin[g] = 0; M.nwl[g] = 0; M.nlive[g] = 0; }
+        for (int k = 0; k < 2 * 8 * 8; ++k) (&M.candmask[0][0][0])[k] = 0;
+        for (int k = 0; k < 16; ++k) (&M.ncs[0][0])[k] = 0;
         M.denseflag[0] = Q.dense[0]; M.denseflag[1] = T >= 1 ? Q.dense[1] : 0;
         for (int k = 0; k < NPROF; ++k) M.pc[k] = 0;
-        s_cx.W = W; s_cx.tx = tx; s_cx.xrow = xrow; s_cx.inT = inT; s_cx.evb = evb; s_cx.live = live; s_cx.M = &M;
-        s_cx.P = P; s_cx.B = B; s_cx.Bp = Bp; s_cx.evblk = evblk; s_cx.cntb = cntb; s_cx.WS = WS;
-        s_cx.pre_on = pre_on; s_cx.has_clamp = C.has_clamp;
-        s_cx.dts = dts; s_cx.wmin = C.wmin; s_cx.wmax = C.wmax; s_cx.nu1 = C.nu1;
+        s_cx.k.W = W; s_cx.k.tx = tx; s_cx.k.inT = inT; s_cx.k.evb = evb; s_cx.k.live = live; s_cx.k.candlist = candlist; s_cx.k.M = &M;
+        s_cx.k.P = P; s_cx.k.B = B; s_cx.k.Bp = Bp; s_cx.k.evblk = evblk; s_cx.k.cntb = cntb; s_cx.k.WS = WS;
+        s_cx.k.pre_on = pre_on; s_cx.k.has_clamp = C.has_clamp;
+        s_cx.k.dts = dts; s_cx.k.wmin = C.wmin; s_cx.k.wmax = C.wmax; s_cx.k.nu1 = C.nu1;
+        s_cx.inS = Q.inS; s_cx.SW = Q.SW;
+        s_cx.ai_v = ai_v; s_cx.ai_rc = ai_rc; s_cx.ai_id = ai_id; s_cx.ai_claim = ai_claim; s_cx.ai_map = ai_map; s_cx.ai_fl = ai_fl;
+        s_cx.aispk = aispk; s_cx.sisum = Q.sisum; s_cx.win = Q.win; s_cx.I_rec_s = I.rec_s; s_cx.I_rec_count = I.rec_count;
+        s_cx.I_decay = I.decay; s_cx.I_rest = I.rest; s_cx.I_dt = I.dt; s_cx.I_thresh = I.thresh; s_cx.I_refrac = I.refrac; s_cx.I_reset = I.reset;
+        s_cx.n = n; s_cx.j0 = j0; s_cx.TJ = TJ; s_cx.aicap = aicap;
+        s_cx.candstamp = candstamp; s_cx.candslot = candslot; s_cx.xrow_w = xrow; s_cx.xtr = Q.xtr;
+        s_cx.seed = Q.seed; s_cx.step_offset = Q.step_offset; s_cx.liE = Q.liE; s_cx.one_spike = E.one_spike; s_cx.stage_on = stage_on ? 1 : 0;
+        s_cx.nostage = (PROFV && (Q.dbg & 8)) ? 1 : 0;
     }
     __syncthreads();
 
+    if (negz) M.negzero = 1;
     float vE[4], rE[4], xE[4];
     uint32_t candE = 0, pend = 0, sEfin = 0;  // 4-bit masks over my neurons
     uint32_t vm = 0;                          // my neurons that exist (column < n)
@@ -556,7 +788,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         for (int c = 0; c < 4; ++c)
             if (((vm >> c) & 1u) && (v0[c] != I.rest || r0[c] > 0.0f || ((sE0 >> c) & 1u))) {
                 const int e = atomicAdd(&M.nact, 1);
-                ai_v[e] = v0[c]; ai_rc[e] = r0[c]; ai_id[e] = (uint16_t)(b * TJ + 4 * cg + c);
+                ai_v[e] = v0[c]; ai_rc[e] = r0[c]; ai_id[e] = (uint16_t)((b << 8) | (4 * cg + c));
                 ai_claim[e] = (uint16_t)AI_NONE; ai_claim[aicap + e] = (uint16_t)AI_NONE; ai_fl[e] = ((sE0 >> c) & 1u) ? 4 : 0;
                 ai_map[b * TJ + 4 * cg + c] = (uint16_t)e;
             }
@@ -585,49 +817,6 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     PROF(0)  // prologue
     if (PROFV && tid == NC) pt = clock64();
 
-    // spike-gather of my 4 columns for the spikes of list block `blk` (slot `slot`):
-    // p[c] = sum_{i in sX[b]} W[i][c], i ascending (topology.py:437-479)
-    auto gather = [&](const unsigned char *blk, int slot) -> float4 {
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-        const int cnt = ((const uint16_t *)blk)[b];
-        if (cnt <= EV_CAP) {
-            const uint2 *l4 = (const uint2 *)(blk + cntb) + b;
-            #pragma unroll 1
-            for (int k = 0; k < cnt; k += 4) {
-                const uint2 q = l4[(k >> 2) * B];  // 4 pixel indices; tail padded with P (zero row)
-                const float4 r0 = *(const float4 *)(Wc + (q.x & 0xffffu) * WS);
-                const float4 r1 = *(const float4 *)(Wc + (q.x >> 16) * WS);
-                const float4 r2 = *(const float4 *)(Wc + (q.y & 0xffffu) * WS);
-                const float4 r3 = *(const float4 *)(Wc + (q.y >> 16) * WS);
-                p0 = p0 + r0.x; p1 = p1 + r0.y; p2 = p2 + r0.z; p3 = p3 + r0.w;
-                p0 = p0 + r1.x; p1 = p1 + r1.y; p2 = p2 + r1.z; p3 = p3 + r1.w;
-                p0 = p0 + r2.x; p1 = p1 + r2.y; p2 = p2 + r2.z; p3 = p3 + r2.w;
-                p0 = p0 + r3.x; p1 = p1 + r3.y; p2 = p2 + r3.z; p3 = p3 + r3.w;
-            }
-        } else {  // dense sample: walk the bit row in global memory (rare, slow path)
-            return gather_dense2(Q.inS + ((size_t)slot * B + b) * Q.SW, Q.SW, Wc, WS);
-        }
-        return make_float4(p0, p1, p2, p3);
-    };
-    // one LIFNodes.forward step of list entry e with input xin (nodes.py:500-529); spikes go to the exchange
-    auto ai_step = [&](int e, float xin, int t) {
-        float v = ai_v[e], rc = ai_rc[e];
-        uint32_t fl = ai_fl[e];
-        v = I.decay * (v - I.rest) + I.rest;
-        if (!(fl & 1u)) { if (rc > 0.0f) xin = 0.0f; rc = rc - I.dt; }   // undisturbed counter: <= 0 by construction
-        v = v + xin;
-        fl &= 1u;
-        if (v >= I.thresh) {
-            rc = I.refrac; v = I.reset; fl = 2u;
-            const int id = ai_id[e], sb_ = id / TJ, col = id - sb_ * TJ;
-            atomicOr(&aispk[(t & 1) * Bp + sb_], 1u << col);
-            atomicAdd(Q.sisum + (t % 3) * B + sb_, 1u);
-            if (I.rec_s) I.rec_s[((size_t)t * B + sb_) * n + j0 + col] = 1;
-            if (I.rec_count) atomicAdd(I.rec_count + (size_t)sb_ * n + j0 + col, 1);
-        }
-        ai_v[e] = v; ai_rc[e] = rc; ai_fl[e] = (uint8_t)fl;
-    };
-
     float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);   // currents of the step about to run, gathered ahead
     bool havepre = false;
 
@@ -644,7 +833,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             if (lane == 0) {
                 const unsigned int target = G * (unsigned int)t;
                 unsigned int spins = 0;
-                while ((int)(ld_relaxed_u32(Q.bar) - target) < 0 && !(Q.dbg & 16)) {
+                while ((int)(ld_relaxed_u32(Q.bar) - target) < 0 && !(PROFV && (Q.dbg & 16))) {
                     if ((++spins & 0xfffffu) == 0) {   // ~ a second of polling: give up
                         if (spins > (4u << 20)) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
                     }
@@ -652,6 +841,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 asm volatile("fence.acquire.gpu;" ::: "memory");
             }
             __syncwarp();
+            if (PROFV && tid == NC && Q.prof && t > 100 && t <= 132) Q.prof[160 * NPROF + ((t - 101) * 160 + blockIdx.x) * 2 + 1] = clock64() - pt;
             PROFX(10)  // barrier wait (exchange warp)
             const int xs = (t - 1) % 3;
             {   // all loads in flight together: one L2 round trip
@@ -672,6 +862,9 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             PROFX(11)  // exchange read
         }
         __syncthreads();
+        if (PROFV && tid == NC) pt = clock64();
+        const long long g_t0 = PROFV ? clock64() : 0;
+        long long g_t1 = 0, g_t2 = 0, g_t3 = 0, g_ta = 0, g_tb = 0, g_info = 0;
         if (M.abort) return;
         PROF(1)  // exchange wait (compute side)
 
@@ -701,7 +894,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                     }
                 }
                 const int slot = (stage_on && candstamp[ppar * Bp + b] == (uint32_t)t) ? candslot[ppar * Bp + b] : -1;   // staged at step t-1
-                #pragma unroll
+                #pragma unroll 1
                 for (int c = 0; c < 4; ++c)
                     if ((candE >> c) & 1u) {
                         const int col = 4 * cg + c;
@@ -714,7 +907,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                         }
                         // the partner Ai neuron of every candidate runs here (claimed at step t-1): input `exc`
                         // through the diagonal Ae->Ai iff the candidate won (network.py:225-248)
-                        if (t < T) ai_step((int)ai_map[b * TJ + col], won ? (0.0f + Q.exc) : 0.0f, t);
+                        if (t < T) ai_step2(&s_cx, (int)ai_map[b * TJ + col], won ? (0.0f + Q.exc) : 0.0f, t);
                         if (won) {   // monitors (monitors.py:94-111): the launch code cleared the raster
                             if (E.rec_s) E.rec_s[((size_t)(t - 1) * B + b) * n + jc + c] = 1;
                             if (E.rec_count) atomicAdd(E.rec_count + (size_t)b * n + jc + c, 1);
@@ -724,6 +917,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 pend = 0;
             }
             PROF(2)  // winners
+            if (PROFV) g_ta = clock64();
             if (update_on) {
                 // STDP of step t-1 for this column group (MCC_learning.py:234-299)
                 bar_group(gbar, Bp);
@@ -738,12 +932,16 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 const float *xr = xrow + ppar * XR * P;   // rows staged at step t-1 (buffer of its parity, filled for the ((t-1)>>1)-th time)
                 if (nwl && stage_on) { while (!mbar_try_wait(&M.mbar_x[ppar], (uint32_t)((t - 1) >> 1) & 1u)) {} }
                 PROF(3)  // late set-up
+                if (PROFV) { g_tb = clock64(); g_info = (fast ? 2 : 0) | (nwl << 4) | ((long long)M.ncand[ppar] << 12) | ((long long)M.nlive[cg] << 20); }
+                // the shadow pass finished every row of this group except those at which a candidate-holding sample
+                // spiked (unless the slot is dense: then nothing of this group was done yet)
+                const uint32_t *dm = &M.candmask[ppar][cg][0];
                 if (fast) {
-                    if (pre_on) stdp_list2<CG, BW>(&s_cx, sb_, cg, gwin, xr, b, Bp);
-                    if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, xr, b, Bp);
+                    if (pre_on || gwin) stdp_late2<CG, BW>(&s_cx, sb_, cg, gwin, dm, ppar, xr, b, Bp);
+                    if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, dm, xr, M.negzero ? 0 : 1, b, Bp);
                 } else {
                     stdp_rows2<CG, BW>(&s_cx, sb_, cg, gwin, M.candb[ppar], min(M.ncand[ppar], XR),
-                                       Q.xtr ? Q.xtr + (size_t)(t - 1) * B * P : nullptr, xr, b, Bp);
+                                       Q.xtr ? Q.xtr + (size_t)(t - 1) * B * P : nullptr, xr, M.denseflag[sb_] ? nullptr : dm, b, Bp);
                 }
                 PROF(4)  // late pass
                 bar_group(gbar, Bp);   // the group's weights are final for step t-1
@@ -764,12 +962,14 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         if (t == T) break;
 
         // ---- step t: gather (unless done ahead), Ae update, candidates, Ai list ------------------------
+        if (PROFV) g_t1 = clock64();
         uint32_t cand = 0;
         if (act) {
             if (!havepre) {
                 while (!mbar_try_wait(&M.mbar_in[buf], (uint32_t)(t >> 1) & 1u)) {}   // slot t landed (prefetched one step ago)
-                pre = gather(cE, t);
+                pre = gather2<WS>(&s_cx, cE, t, b, Wc);
             }
+            if (PROFV) g_t2 = clock64();
             const float p[4] = {pre.x, pre.y, pre.z, pre.w};
             const float4 th4 = *(const float4 *)(thr_s + 4 * cg);
             const float thr[4] = {th4.x, th4.y, th4.z, th4.w};
@@ -781,9 +981,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                     // network.py:225-248: X->Ae first, then Ai->Ae; the latter is rep[#spiking Ai other than j]
                     const int mI = isum - (int)((own >> c) & 1u);
                     float cur = 0.0f + p[c];
-                    float inh;
-                    if (mI <= Q.nrep) inh = rep[mI];
-                    else { inh = rep[Q.nrep]; for (int m = Q.nrep; m < mI; ++m) inh = inh + Q.inh_neg; }
+                    float inh = rep[min(mI, Q.nrep)];
+                    if (mI > Q.nrep) {   // more simultaneous Ai spikes than the table holds (never with one_spike)
+                        #pragma unroll 1
+                        for (int m = Q.nrep; m < mI; ++m) inh = inh + Q.inh_neg;
+                    }
                     cur = cur + inh;
                     // DiehlAndCookNodes.forward up to the threshold test (nodes.py:1077-1092)
                     vE[c] = E.decay * (vE[c] - E.rest) + E.rest;
@@ -794,41 +996,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 }
             }
             if (cand) {
-                unsigned long long mykey = 0ull;
-                #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if ((cand >> c) & 1u) {
-                        const int col = 4 * cg + c;
-                        atomicAdd(&M.cnt[par][col], 1);
-                        if (E.one_spike) {
-                            const unsigned long long k2 = snn_one_spike_key(Q.seed, (uint32_t)t + Q.step_offset, (uint32_t)Q.liE, (uint32_t)b,
-                                                                            (uint32_t)(jc + c));
-                            mykey = k2 > mykey ? k2 : mykey;
-                        }
-                        // the partner Ai neuron is mine at step t+1, whether this candidate wins or not
-                        unsigned e = ai_map[b * TJ + col];
-                        if (e == AI_NONE) {
-                            e = (unsigned)atomicAdd(&M.nact, 1);
-                            ai_v[e] = I.rest; ai_rc[e] = 0.0f; ai_id[e] = (uint16_t)(b * TJ + col); ai_fl[e] = 1;
-                            ai_claim[par * aicap + e] = (uint16_t)AI_NONE;
-                            ai_map[b * TJ + col] = (uint16_t)e;
-                        }
-                        ai_claim[ppar * aicap + e] = (uint16_t)(t + 1);   // slot of parity (t + 1) & 1
-                    }
-                atomicOr(&M.candgrp[par], 1u << cg);
-                if (E.one_spike) atomicMax(Q.win + (t % 3) * B + b, mykey);
-                if (stage_on) {  // stage x_pre[b,:] of step t for the post term, once per sample
-                    const uint32_t old = atomicExch(&candstamp[par * Bp + b], (uint32_t)(t + 1));
-                    if (old != (uint32_t)(t + 1)) {
-                        const int s = atomicAdd(&M.ncand[par], 1);
-                        if (s < XR && !(Q.dbg & 8)) {
-                            M.candb[par][s] = b;
-                            candslot[par * Bp + b] = s;
-                            mbar_expect_tx(&M.mbar_x[par], (uint32_t)(P * 4));
-                            bulk_g2s(xrow + (par * XR + s) * P, Q.xtr + ((size_t)t * B + b) * P, (uint32_t)(P * 4), &M.mbar_x[par]);
-                        } else candslot[par * Bp + b] = -1;
-                    }
-                }
+                on_candidate2(&s_cx, cand, b, cg, t);
             } else if (E.traces) {
                 // no candidate among my neurons: their step-t trace is already final (no spike)
                 #pragma unroll
@@ -836,6 +1004,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 if (update_on && livep) *(float4 *)(tx + b * TJ + 4 * cg) = make_float4(xE[0] * C.nu0, xE[1] * C.nu0, xE[2] * C.nu0, xE[3] * C.nu0);
             }
         }
+        if (PROFV) g_t3 = clock64();
         candE = cand;
         pend = cand;
         havepre = false;
@@ -845,12 +1014,24 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             #pragma unroll 1
             for (int k = tid; k < nact; k += NC) {
                 if (ai_claim[par * aicap + k] == (uint16_t)t) continue;
-                ai_step(k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t);
+                ai_step2(&s_cx, k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t);
             }
         }
         PROF(6)  // gather + neurons
+        if (PROFV && Q.prof && !isx && b == 0 && t >= 100 && t < 132) {
+            long long *tr = Q.prof + 160 * NPROF + 32 * 160 * 2 + (((t - 100) * 160 + blockIdx.x) * 8 + cg) * 5;
+            const long long now_ = clock64();
+            tr[0] = g_t1 - g_t0; tr[1] = g_t2 - g_t1; tr[2] = g_t3 - g_t2; tr[3] = now_ - g_t3;
+            tr[4] = (lateg ? 1 : 0) | g_info | ((g_ta - g_t0) << 32) | ((g_tb - g_ta) << 48);
+        }
         __syncthreads();
         PROF(7)  // step sync
+        if (PROFV && tid == NC) {   // exchange warp: S1 -> S2 = the CTA's critical path of this step
+            const long long now_ = clock64();
+            pc[14] += now_ - pt;
+            if (Q.prof && t >= 100 && t < 132) Q.prof[160 * NPROF + ((t - 100) * 160 + blockIdx.x) * 2] = now_ - pt;
+            pt = now_;
+        }
         // ---- arrive(t): this CTA's contributions to step t's exchange are issued -----------------
         const int nb = buf ^ 1;                                      // slot t+1 = spikes of step t
         if (isx) {
@@ -859,13 +1040,13 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 for (int k = lane; k < B; k += 32) { Q.win[((t + 1) % 3) * B + k] = 0ull; Q.sisum[((t + 1) % 3) * B + k] = 0u; }
             __syncwarp();
             if (lane == 0) {
-                if (Q.dbg & 128) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
+                if (PROFV && (Q.dbg & 128)) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
                 else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
                 mbar_arrive(&M.mbar_x[par]);   // the rows staged in step t: complete once the copies issued above have landed
             }
-            if (tid == tid_pf && t + 2 <= T && (Q.dbg & 1)) mbar_arrive(&M.mbar_in[buf]);
-            if (tid == tid_pf && t + 2 <= T && !(Q.dbg & 1)) {  // prefetch slot t+2 into the buffer the gather just finished with
-                const bool masks = !(Q.dbg & 32);   // (diagnostic: pixel masks not refreshed)
+            if (PROFV && tid == tid_pf && t + 2 <= T && (Q.dbg & 1)) mbar_arrive(&M.mbar_in[buf]);
+            if (tid == tid_pf && t + 2 <= T && !(PROFV && (Q.dbg & 1))) {  // prefetch slot t+2 into the buffer the gather just finished with
+                const bool masks = !(PROFV && (Q.dbg & 32));   // (diagnostic: pixel masks not refreshed)
                 mbar_arrive_expect_tx(&M.mbar_in[buf], bytesE + (masks ? bytesT : 0u));
                 bulk_g2s(evb + buf * evblk, Q.evS + (size_t)(t + 2) * Q.SB, bytesE, &M.mbar_in[buf]);
                 if (masks) bulk_g2s(inT + buf * P * BW, Q.inT + (size_t)(t + 2) * P * BW, bytesT, &M.mbar_in[buf]);
@@ -886,16 +1067,20 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             const bool earlyg = !((M.candgrp[par] >> cg) & 1u);
             while (!mbar_try_wait(&M.mbar_in[nb], (uint32_t)((t + 1) >> 1) & 1u)) {}
             if (tid == 0) { M.denseflag[nb] = dense_nb; M.ncand[ppar] = 0; M.candgrp[ppar] = 0; M.nact_snap = M.nact; }   // parity ppar: next used by step t+1
-            // early STDP: pre term of a column group WITHOUT a candidate (its step-t traces are final)
-            if (earlyg && update_on && pre_on && !(Q.dbg & 2)) {
-                if (dense_nb) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, b, Bp);
-                else stdp_list2<CG, BW>(&s_cx, nb, cg, 0u, xrow, b, Bp);
-                bar_group(gbar, Bp);
+            // early STDP: the pre term of step t wherever it does not depend on the exchange — every row of a column
+            // group without a candidate; in a group with candidates every row except those at which a candidate-holding
+            // sample spiked (stdp_late2 finishes them once the winners are known)
+            if (b < BW) M.candmask[ppar][cg][b] = 0;   // step t-1's: consumed by the late pass above
+            if (b == 0) M.ncs[ppar][cg] = 0;
+            if (update_on && pre_on && !(PROFV && (Q.dbg & 2))) {
+                if (!dense_nb) stdp_list2<CG, BW>(&s_cx, nb, cg, &M.candmask[par][cg][0], b, Bp);
+                else if (earlyg) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, nullptr, b, Bp);
+                if (earlyg) bar_group(gbar, Bp);
             }
             PROF(8)  // early STDP
             // gather of step t+1 for a group whose weights are final now: off the critical path
-            const bool ahead = t + 1 < T && earlyg && !(t == 0 && update_on && C.has_clamp) && !(Q.dbg & 4);
-            if (ahead && act) pre = gather(evb + nb * evblk, t + 1);
+            const bool ahead = t + 1 < T && earlyg && !(t == 0 && update_on && C.has_clamp) && !(PROFV && (Q.dbg & 4));
+            if (ahead && act) pre = gather2<WS>(&s_cx, evb + nb * evblk, t + 1, b, Wc);
             havepre = ahead;
             PROF(9)  // gather ahead
         }
@@ -1273,7 +1458,7 @@ WsLayout2 ws_layout2(const Match2 &m, int T, int B, int P, bool traces) {
     L.rep = o; o += al(sizeof(float) * (size_t)(m.nrep + 1));
     L.sisum0 = o; o += al(sizeof(unsigned int) * (size_t)B);
     L.xtr = o; o += traces ? al(sizeof(float) * (size_t)T * B * P) : 0;
-    L.prof = o; o += al(sizeof(long long) * 160 * NPROF);
+    L.prof = o; o += al(sizeof(long long) * (160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5));
     L.total = o;
     return L;
 }
@@ -1362,16 +1547,52 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     }
     if (prof) {  // debug only: synchronise and print the per-phase cycle counts (min / mean / max over CTAs)
         static const char *names[NPROF] = {"prologue", "exchange wait", "winners", "late set-up", "late pass", "slot wait+sync", "gather+neurons",
-                                           "step sync", "early STDP", "gather ahead", "x: barrier wait", "x: exchange read", "final sync", "epilogue", "", ""};
+                                           "step sync", "early STDP", "gather ahead", "x: barrier wait", "x: exchange read", "final sync", "epilogue", "x: S1->S2 (CTA)", ""};
         cudaStreamSynchronize(stream);
         static long long hostp[160 * NPROF];
         cudaMemcpy(hostp, Q.prof, sizeof(long long) * (size_t)m.grid * NPROF, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[snn_b200 prof v2] grid=%d threads=%d T=%d (cycles per timestep, thread 0 of each CTA: min / mean / max)\n", m.grid, m.threads, T);
-        for (int k = 0; k < 14; ++k) {
+        for (int k = 0; k < 15; ++k) {
             double sum = 0, mx = 0, mn = 1e300;
             for (int g = 0; g < m.grid; ++g) { const double v = (double)hostp[g * NPROF + k]; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
-            const double div = (k == 0 || k >= 12) ? 1.0 : (double)T;
+            const double div = (k == 0 || k == 12 || k == 13) ? 1.0 : (double)T;
             fprintf(stderr, "  %-18s %10.0f %10.0f %10.0f\n", names[k], mn / div, sum / m.grid / div, mx / div);
+        }
+        if (T >= 133) {   // per-step view, steps 100..131: which CTA makes the others wait, and for how long
+            static long long tr[32 * 160 * 2];
+            cudaMemcpy(tr, Q.prof + 160 * NPROF, sizeof(tr), cudaMemcpyDeviceToHost);
+            double a_mean = 0, a_max = 0, w_mean = 0, w_min = 0;
+            for (int st = 0; st < 32; ++st) {
+                double sm = 0, mx = 0, wm = 0, wn = 1e300;
+                for (int g = 0; g < m.grid; ++g) {
+                    const double a = (double)tr[(st * 160 + g) * 2], w = (double)tr[(st * 160 + g) * 2 + 1];
+                    sm += a / m.grid; mx = a > mx ? a : mx; wm += w / m.grid; wn = w < wn ? w : wn;
+                }
+                a_mean += sm / 32; a_max += mx / 32; w_mean += wm / 32; w_min += wn / 32;
+            }
+            fprintf(stderr, "  per step (t=100..131): S1->S2 mean over CTAs %.0f, slowest CTA %.0f; barrier wait mean %.0f, of the last arriver %.0f\n",
+                    a_mean, a_max, w_mean, w_min);
+            // the slowest column group of the slowest CTA of each step: where its time went
+            static long long gt[32 * 160 * 8 * 5];
+            cudaMemcpy(gt, Q.prof + 160 * NPROF + 32 * 160 * 2, sizeof(gt), cudaMemcpyDeviceToHost);
+            double ph[4] = {0, 0, 0, 0}, late_share = 0;
+            for (int st = 0; st < 32; ++st) {
+                double best = -1; int bg = 0, bc = 0;
+                for (int g = 0; g < m.grid; ++g)
+                    for (int c = 0; c < m.CG; ++c) {
+                        const long long *r = gt + ((st * 160 + g) * 8 + c) * 5;
+                        const double tot = (double)(r[0] + r[1] + r[2] + r[3]);
+                        if (tot > best) { best = tot; bg = g; bc = c; }
+                    }
+                const long long *r = gt + ((st * 160 + bg) * 8 + bc) * 5;
+                for (int k = 0; k < 4; ++k) ph[k] += (double)r[k] / 32;
+                late_share += (double)(r[4] & 1) / 32;
+                fprintf(stderr, "    step %d: CTA %d group %d: late path %lld (winners %lld, set-up %lld), gather %lld, neurons %lld, Ai %lld; fast=%lld nwl=%lld ncand=%lld nlive=%lld\n",
+                        100 + st, bg, bc, r[0], (r[4] >> 32) & 0xffff, (r[4] >> 48) & 0xffff, r[1], r[2], r[3], (r[4] >> 1) & 1, (r[4] >> 4) & 0xff,
+                        (r[4] >> 12) & 0xff, (r[4] >> 20) & 0xfff);
+            }
+            fprintf(stderr, "  slowest group per step: winners+late STDP %.0f, gather %.0f, neurons %.0f, Ai list %.0f cycles; it was a late group in %.0f%% of the steps\n",
+                    ph[0], ph[1], ph[2], ph[3], 100 * late_share);
         }
     }
     if (launches) *launches = nl;  // 2 structure checks + two pre-passes + the persistent window kernel

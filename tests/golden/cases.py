@@ -167,6 +167,12 @@ def dc2015_metric_t40(ns, inputs=None):
     return _dc2015(ns, 1600, 128, 40, 81, 82, True, inputs, poisson=True)
 
 
+# the metric configuration at its full window length: n=1600, B=128, T=250 (north_star: "final weights within 1e-4
+# rel of reference under fixed seed" at 250 steps; one ~5-minute run of the live reference)
+def dc2015_metric_t250(ns, inputs=None):
+    return _dc2015(ns, 1600, 128, 250, 83, 84, True, inputs, poisson=True)
+
+
 # classic Connection + learning.PostPre path with a recurrent inhibitory Connection
 def dc2015v2(ns, inputs=None):
     net = ns.models.DiehlAndCook2015v2(n_inpt=196, n_neurons=64, inh=60.0, nu=(1e-4, 1e-2), reduction=torch.sum,
@@ -334,6 +340,7 @@ CASES = {
     "dc2015_eval": dc2015_eval,
     "dc2015_c2": dc2015_c2,
     "dc2015_metric_t40": dc2015_metric_t40,
+    "dc2015_metric_t250": dc2015_metric_t250,
     "mstdp_dense": mstdp_dense,
     "conv_mstdp": conv_mstdp,
     "conv_stride_norm": conv_stride_norm,
@@ -346,6 +353,6 @@ CASES = {
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)
-LARGE = {"dc2015_metric_t40", "conv_mstdp_c4"}
+LARGE = {"dc2015_metric_t40", "dc2015_metric_t250", "conv_mstdp_c4"}
 #: one_spike tie-break seed used by every case
 ONE_SPIKE_SEED = 20260922
