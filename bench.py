@@ -419,6 +419,42 @@ def main():
     e2e_value = world * BATCH * T_STEPS * K / (float(ms2) * 1e-3)
     net.check_errors()
 
+    # ---- e2e from RATE IMAGES: the on-device encoder (bindsnet_b200.encoding.poisson on CUDA tensors, SURVEY.md §8f
+    # rank 1) writes the spike tensor where Network.run reads it; only the [B, 1, 28, 28] float32 rate image
+    # (400 KB instead of 25 MB) crosses PCIe per window, the result comes back as above -------------------------
+    from bindsnet_b200.encoding import poisson as poisson_dev
+
+    g = torch.Generator().manual_seed(4321 + rank)
+    rate_host = [(128.0 * torch.rand(BATCH, 1, 28, 28, generator=g) * torch.bernoulli(0.19 * torch.ones(BATCH, 1, 28, 28), generator=g)).pin_memory()
+                 for _ in range(POOL)]
+    rate_dev = [torch.empty(BATCH, 1, 28, 28, device=dev) for _ in range(2)]
+
+    def rates_loop(n, first):
+        for i in range(n):
+            r = rate_dev[i & 1]
+            r.copy_(rate_host[(first + i) % POOL], non_blocking=True)          # H2D of this window's input
+            x_dev = poisson_dev(r, time=T_STEPS, dt=1.0, seed=1000 + first + i)   # [T, B, 1, 28, 28] uint8, on the device
+            net.reset_state_variables()
+            runner.run({"X": x_dev}, time=T_STEPS)
+            rb.push(net.monitors["Ae_spikes"].get("s"))
+            if len(rb) == rb.depth:
+                use(rb.pop())
+        while len(rb):
+            use(rb.pop())
+
+    rates_loop(W, 0)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    rates_loop(K, W)
+    r1.record()
+    barrier()
+    ms3 = torch.tensor([max(r0.elapsed_time(r1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+    e2e_rates_value = world * BATCH * T_STEPS * K / (float(ms3) * 1e-3)
+    net.check_errors()
+
     if rank == 0:
         peak, peak_kind = hbm_peak_gbs()
         per_launch_bytes = algorithmic_bytes_per_timestep() * T_STEPS
@@ -449,6 +485,10 @@ def main():
                     "d2h_bytes_per_step": BATCH * N_NEURONS * 4,
                     "note": "pinned host uint8 spike trains -> WindowPrefetcher (H2D on a side stream, overlapped) -> Network.run + SpikeCounter on Ae -> AsyncReadback: the [B, n] per-sample spike counts (what label assignment consumes) copied to pinned host memory and read there every window, one window behind the launches",
                     "wall_s": wall_e2e, "h2d_gbs_measured": h2d_gbs, "windows_read_on_host": consumed[0], "ae_spikes_seen_on_host": consumed[1]},
+            "e2e_from_rates": {"value": e2e_rates_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * N_INPT * 4,
+                               "d2h_bytes_per_step": BATCH * N_NEURONS * 4,
+                               "note": "pinned host float32 rate images [B,1,28,28] -> H2D -> bindsnet_b200.encoding.poisson on the device "
+                                       "(snn_b200_encode_poisson) -> Network.run + SpikeCounter -> AsyncReadback; encoding inside the timed region"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

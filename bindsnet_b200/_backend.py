@@ -55,6 +55,10 @@ def lib() -> C.CDLL:
     L.snn_b200_conn_update.argtypes = [C.POINTER(_abi.SnnNet), i32, i32, vp, sz, vp]
     L.snn_b200_conn_normalize.restype = C.c_int
     L.snn_b200_conn_normalize.argtypes = [C.POINTER(_abi.SnnConn), i32, i32, vp]
+    L.snn_b200_encode_poisson.restype = C.c_int
+    L.snn_b200_encode_poisson.argtypes = [vp, i32, i32, f32, C.c_uint64, vp, vp]
+    L.snn_b200_encode_bernoulli.restype = C.c_int
+    L.snn_b200_encode_bernoulli.argtypes = [vp, i32, i32, C.c_uint64, vp, vp]
     if L.snn_b200_abi_version() != _abi.SNN_ABI_VERSION:
         raise BackendError("libsnn_b200.so ABI version does not match bindsnet_b200/_abi.py — rebuild")
     _lib = L
@@ -203,3 +207,22 @@ def delta_apply(w, w0, dw_sum, has_clamp, wmin, wmax, has_norm, norm_abs, norm) 
         _check(lib().snn_b200_delta_apply(w.data_ptr(), w0.data_ptr(), dw_sum.data_ptr(), w.shape[0], w.shape[1],
                                           int(has_clamp), float(wmin), float(wmax), int(has_norm), int(norm_abs),
                                           float(norm), _stream_ptr(w.device)), "snn_b200_delta_apply")
+
+
+def encode_poisson(rate_hz: torch.Tensor, T: int, dt: float, seed: int, out: torch.Tensor) -> None:
+    """``out[T, n]`` uint8 Poisson spike trains for ``rate_hz[n]`` (Hz) on the tensor's CUDA device."""
+    global launches_total
+    require_cuda(rate_hz, "rate image"); require_cuda(out, "spike tensor")
+    launches_total += 1
+    with torch.cuda.device(rate_hz.device):
+        _check(lib().snn_b200_encode_poisson(rate_hz.data_ptr(), rate_hz.numel(), T, float(dt), seed & (2**64 - 1), out.data_ptr(),
+                                             _stream_ptr(rate_hz.device)), "snn_b200_encode_poisson")
+
+
+def encode_bernoulli(prob: torch.Tensor, T: int, seed: int, out: torch.Tensor) -> None:
+    global launches_total
+    require_cuda(prob, "probability image"); require_cuda(out, "spike tensor")
+    launches_total += 1
+    with torch.cuda.device(prob.device):
+        _check(lib().snn_b200_encode_bernoulli(prob.data_ptr(), prob.numel(), T, seed & (2**64 - 1), out.data_ptr(),
+                                               _stream_ptr(prob.device)), "snn_b200_encode_bernoulli")

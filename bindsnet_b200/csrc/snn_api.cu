@@ -116,7 +116,7 @@ extern "C" {
 int snn_b200_abi_version(void) { return SNN_ABI_VERSION; }
 
 const char *snn_b200_build_info(void) {
-    return "libsnn_b200 sm_100a (generic window + fused DC2015 windows v1/v2), ABI " "6" ", built " __DATE__ " " __TIME__;
+    return "libsnn_b200 sm_100a (generic window + fused DC2015 windows v1/v2), ABI " "7" ", built " __DATE__ " " __TIME__;
 }
 
 int snn_b200_last_launch_count(void) { return g_last_launches; }

@@ -67,7 +67,10 @@ struct F2Params {
     uint32_t *inT;            // [T+1][P][BW]  same spikes: bit b of pixel i
     unsigned char *evS;       // [T+1][SB]     same spikes as lists: u16 count[B] (padded), then u16 idx[B][EV_CAP]
     int *dense;               // [T+1] slot holds a sample whose event list overflowed EV_CAP
-    float *xtr;               // [T][B][P] input traces of every step (pre-pass scan), or NULL
+    uint8_t *xage;            // [T][B][P] input traces of every step as AGES (steps since the pixel's last spike in this
+                              // window, 255 = none yet): the trace is dtab[age] (pre-pass scan), or NULL
+    float *x0c;               // [B][P] the Input layer's trace at the start of the window (for pixels without a spike yet)
+    int *anyx0;               // set by the scan when any of those is non-zero
     float *rep;               // [nrep+1] m-fold sequential sums of the Ai->Ae weight
     unsigned int *sisum0;     // [B] Ai spikes of step -1
     unsigned long long *win;  // [3][B] one_spike arg-max keys, slot t % 3
@@ -164,9 +167,9 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int P, int TJ, int B, int Bp
     L.tx = o; o += al16(sizeof(float) * (size_t)Bp * TJ);
     L.ev = o; o += 2 * al16((size_t)ev_block_bytes(B));
     L.inT = o; o += al16(sizeof(uint32_t) * 2 * (size_t)P * BW);
-    L.xrow = o; o += al16(sizeof(float) * 2 * (size_t)XR * P);   // by step parity
+    L.xrow = o; o += al16(2 * (size_t)XR * P + sizeof(float) * 64 * 17);   // staged age rows by step parity (reused as normalize scratch)
     L.rep = o; o += al16(sizeof(float) * (size_t)(nrep + 1));
-    L.theta = o; o += al16(sizeof(float) * 64);
+    L.theta = o; o += al16(sizeof(float) * (64 + 256));   // theta, threshold, trace-by-age table
     L.live = o; o += al16(sizeof(uint16_t) * (size_t)Bp * (TJ / 4));
     L.tab = o; o += al16(tab_bytes(Bp));
     L.ai = o; o += ai_bytes(Bp * TJ);
@@ -208,8 +211,11 @@ struct PassCtx2 {
     // candidates
     uint32_t *candstamp;
     int *candslot;
-    float *xrow_w;
-    const float *xtr;
+    uint8_t *xrow_w;
+    const uint8_t *xage;
+    const float *x0c, *dtab;
+    float x_decay;
+    int anyx0;
     uint32_t seed, step_offset;
     int liE, one_spike, stage_on, nostage;
 };
@@ -295,14 +301,28 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, cons
     }
 }
 
+// Input trace of sample b at pixel i after step t from its age byte (Nodes.forward, nodes.py:96-103: decay every
+// step, set to trace_scale on a spike): dtab[age]; a pixel without a spike in this window still carries the
+// trace it entered the window with, decayed t + 1 times (rare: replayed).
+__device__ __noinline__ float xval_nospike(const PassCtx2 *cx, int b, int i, int t) {
+    float x = cx->x0c[(size_t)b * cx->k.P + i];
+    #pragma unroll 1
+    for (int k = 0; k <= t; ++k) x = x * cx->x_decay;
+    return x;
+}
+__device__ __forceinline__ float xval(const PassCtx2 *cx, uint32_t age, int b, int i, int t) {
+    if (age != 255u) return cx->dtab[age];
+    return cx->anyx0 ? xval_nospike(cx, b, i, t) : 0.0f;
+}
+
 // Late STDP of column group c4 on the rows stdp_list2 left alone — the pixels at which a candidate-holding
 // sample (`dm`) spiked: now that the winners are known, pre term (traces of all live samples at the pixel,
 // ascending), then for a winner column (`gwin`) the post term of its single winner, then clamp
 // (MCC_learning.py:234-299, 86-110).  Work items: (candidate sample, event of that sample); when several
 // candidate samples spike at a pixel the lowest of them owns the row.
 template <int CG, int BW>
-__device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const uint32_t *dm, int par_, const float *xrow,
-                                        int tid0, int nthr0) {
+__device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const uint32_t *dm, int par_, const uint8_t *xrow,
+                                        int tstep, int tid0, int nthr0) {
     const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS, B = c_.B;
     const Misc2 &M = *c_.M;
@@ -372,7 +392,7 @@ __device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint
                 uint32_t e = M.wl[c4][0];
                 #pragma unroll 1
                 for (int k2 = 1; k2 < M.nwl[c4]; ++k2) if ((M.wl[c4][k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[c4][k2];
-                const float V = 0.0f + xrow[(e & 0xffu) * P + i] * c_.nu1;
+                const float V = 0.0f + xval(cx, xrow[(e & 0xffu) * P + i], (int)((e >> 8) & 0xffu), i, tstep) * c_.nu1;
                 w = w + V * c_.dts;
             }
             if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
@@ -388,8 +408,8 @@ __device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint
 // exactly zero are skipped when `skip0` says that is exact: w + 0*nu1*dt == w bitwise unless w is -0.0 (the
 // tile holds none: checked when it is loaded), and the clamp of an in-range weight is the identity.
 template <int CG, int BW>
-__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int nwl, const uint32_t *dm, const float *xrow, int skip0, int tid0,
-                                        int nthr0) {
+__device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int nwl, const uint32_t *dm, const uint8_t *xrow, int tstep, int skip0,
+                                        int tid0, int nthr0) {
     const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS;
     const Misc2 &M = *c_.M;
@@ -403,11 +423,12 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int 
     #pragma unroll 1
     for (int k = 0; k < nwl; ++k) {   // distinct columns
         const uint32_t e = M.wl[c4][k];
-        const float *xr = xrow + (e & 0xffu) * P;
+        const uint8_t *xr = xrow + (e & 0xffu) * P;
+        const int wb = (int)((e >> 8) & 0xffu);
         float *wcol = c_.W + (e >> 16);
         #pragma unroll 2
         for (int i = tid0; i < P; i += nthr0) {
-            const float xv = xr[i];
+            const float xv = xval(cx, xr[i], wb, i, tstep);
             if (skip0 && xv == 0.0f) continue;
             {
                 const uint4 q0 = cT[i * (BW / 4)];
@@ -427,11 +448,11 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int 
 // STDP of one step of column group c4 in row form, general: pre and post term of a column applied together
 // (pre, post, clamp — the reference's order).  Used for slots with an overflowed event list, more than XR
 // winners, two winners in one column, a winner whose trace row is not staged.
-// `cand` = staged samples (rows of xrow), `xsrc` = the step's input traces in global memory.  `dm` != NULL: the
+// `cand` = staged samples (rows of xrow), `xsrc` = the step's input-trace ages in global memory.  `dm` != NULL: the
 // pre term only on the rows stdp_list2 left alone (a sample of `dm` spiked there); the post term on every row.
 template <int CG, int BW>
-__device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const int *cand, int ns, const float *xsrc,
-                                        const float *xrow, const uint32_t *dm, int tid0, int nthr0) {
+__device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const int *cand, int ns, const uint8_t *xsrc,
+                                        const uint8_t *xrow, int tstep, const uint32_t *dm, int tid0, int nthr0) {
     const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS, TJ = 4 * CG;
     const Misc2 &M = *c_.M;
@@ -487,7 +508,7 @@ __device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint
                         mm &= mm - 1;
                         int sl = -1;
                         for (int q = 0; q < ns; ++q) if (cand[q] == bb) sl = q;
-                        const float xv = sl >= 0 ? xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i);
+                        const float xv = xval(cx, sl >= 0 ? xrow[sl * P + i] : __ldcg(xsrc + (size_t)bb * P + i), bb, i, tstep);
                         V = V + xv * c_.nu1;
                     }
                 }
@@ -609,8 +630,8 @@ __device__ __noinline__ void on_candidate2(const PassCtx2 *cx, uint32_t cand, in
             if (s < XR && !cx->nostage) {
                 M.candb[par][s] = b;
                 cx->candslot[par * Bp + b] = s;
-                mbar_expect_tx(&M.mbar_x[par], (uint32_t)(P * 4));
-                bulk_g2s(cx->xrow_w + (par * XR + s) * P, cx->xtr + ((size_t)t * B + b) * P, (uint32_t)(P * 4), &M.mbar_x[par]);
+                mbar_expect_tx(&M.mbar_x[par], (uint32_t)P);
+                bulk_g2s(cx->xrow_w + (par * XR + s) * P, cx->xage + ((size_t)t * B + b) * P, (uint32_t)P, &M.mbar_x[par]);
             } else cx->candslot[par * Bp + b] = -1;
         }
     }
@@ -634,10 +655,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     float *tx = (float *)(smem + Q.o_tx);
     unsigned char *evb = smem + Q.o_ev;
     uint32_t *inT = (uint32_t *)(smem + Q.o_inT);
-    float *xrow = (float *)(smem + Q.o_xrow);
+    uint8_t *xrow = smem + Q.o_xrow;             // [2][XR][P] staged age rows
     float *rep = (float *)(smem + Q.o_rep);
     float *theta_s = (float *)(smem + Q.o_theta);   // [32] theta, [32] thresh + decayed theta
     float *thr_s = theta_s + 32;
+    float *dtab = theta_s + 64;                  // [256] input trace by age: trace_scale * decay^age, multiplied up step by step
     uint16_t *live = (uint16_t *)(smem + Q.o_live);  // [CG][Bp] live samples per column group
     unsigned long long *keyT = (unsigned long long *)(smem + Q.o_tab);  // [2][Bp] one_spike arg-max key of a step, by step parity
     uint32_t *isumT = (uint32_t *)(keyT + 2 * Bp);                      // [2][Bp] Ai spikes of a step
@@ -670,7 +692,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     const bool stdp = C.rule >= SNN_RULE_POSTPRE;
     const bool pre_on = stdp && C.nu0 != 0.0f, post_on = stdp && C.nu1 != 0.0f;
     const bool update_on = Q.learning && stdp;
-    const bool stage_on = update_on && post_on && Q.xtr != nullptr;
+    const bool stage_on = update_on && post_on && Q.xage != nullptr;
     const float dts = C.rule == SNN_RULE_MCC_POSTPRE ? C.dt_scale : 1.0f;
     const int evblk = (int)al16((size_t)Q.SB);
     const int cntb = ev_count_bytes(B);
@@ -742,7 +764,12 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         s_cx.aispk = aispk; s_cx.sisum = Q.sisum; s_cx.win = Q.win; s_cx.I_rec_s = I.rec_s; s_cx.I_rec_count = I.rec_count;
         s_cx.I_decay = I.decay; s_cx.I_rest = I.rest; s_cx.I_dt = I.dt; s_cx.I_thresh = I.thresh; s_cx.I_refrac = I.refrac; s_cx.I_reset = I.reset;
         s_cx.n = n; s_cx.j0 = j0; s_cx.TJ = TJ; s_cx.aicap = aicap;
-        s_cx.candstamp = candstamp; s_cx.candslot = candslot; s_cx.xrow_w = xrow; s_cx.xtr = Q.xtr;
+        s_cx.candstamp = candstamp; s_cx.candslot = candslot; s_cx.xrow_w = xrow; s_cx.xage = Q.xage;
+        s_cx.x0c = Q.x0c; s_cx.dtab = dtab; s_cx.x_decay = Q.X.trace_decay; s_cx.anyx0 = Q.anyx0 ? *Q.anyx0 : 0;
+        {   // the trace a pixel carries `age` steps after its spike: the scale, then one multiplication per step
+            float x = Q.X.trace_scale;
+            for (int k = 0; k < 256; ++k) { dtab[k] = x; x = x * Q.X.trace_decay; }
+        }
         s_cx.seed = Q.seed; s_cx.step_offset = Q.step_offset; s_cx.liE = Q.liE; s_cx.one_spike = E.one_spike; s_cx.stage_on = stage_on ? 1 : 0;
         s_cx.nostage = (PROFV && (Q.dbg & 8)) ? 1 : 0;
     }
@@ -929,7 +956,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                     #pragma unroll 1
                     for (int k = 0; k < nwl; ++k) if ((M.wl[cg][k] & 0xffu) == 0xffu) fast = false;
                 }
-                const float *xr = xrow + ppar * XR * P;   // rows staged at step t-1 (buffer of its parity, filled for the ((t-1)>>1)-th time)
+                const uint8_t *xr = xrow + ppar * XR * P;   // rows staged at step t-1 (buffer of its parity, filled for the ((t-1)>>1)-th time)
                 if (nwl && stage_on) { while (!mbar_try_wait(&M.mbar_x[ppar], (uint32_t)((t - 1) >> 1) & 1u)) {} }
                 PROF(3)  // late set-up
                 if (PROFV) { g_tb = clock64(); g_info = (fast ? 2 : 0) | (nwl << 4) | ((long long)M.ncand[ppar] << 12) | ((long long)M.nlive[cg] << 20); }
@@ -937,11 +964,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 // spiked (unless the slot is dense: then nothing of this group was done yet)
                 const uint32_t *dm = &M.candmask[ppar][cg][0];
                 if (fast) {
-                    if (pre_on || gwin) stdp_late2<CG, BW>(&s_cx, sb_, cg, gwin, dm, ppar, xr, b, Bp);
-                    if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, dm, xr, M.negzero ? 0 : 1, b, Bp);
+                    if (pre_on || gwin) stdp_late2<CG, BW>(&s_cx, sb_, cg, gwin, dm, ppar, xr, t - 1, b, Bp);
+                    if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, dm, xr, t - 1, M.negzero ? 0 : 1, b, Bp);
                 } else {
                     stdp_rows2<CG, BW>(&s_cx, sb_, cg, gwin, M.candb[ppar], min(M.ncand[ppar], XR),
-                                       Q.xtr ? Q.xtr + (size_t)(t - 1) * B * P : nullptr, xr, M.denseflag[sb_] ? nullptr : dm, b, Bp);
+                                       Q.xage ? Q.xage + (size_t)(t - 1) * B * P : nullptr, xr, t - 1, M.denseflag[sb_] ? nullptr : dm, b, Bp);
                 }
                 PROF(4)  // late pass
                 bar_group(gbar, Bp);   // the group's weights are final for step t-1
@@ -1074,7 +1101,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             if (b == 0) M.ncs[ppar][cg] = 0;
             if (update_on && pre_on && !(PROFV && (Q.dbg & 2))) {
                 if (!dense_nb) stdp_list2<CG, BW>(&s_cx, nb, cg, &M.candmask[par][cg][0], b, Bp);
-                else if (earlyg) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, nullptr, b, Bp);
+                else if (earlyg) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, t, nullptr, b, Bp);
                 if (earlyg) bar_group(gbar, Bp);
             }
             PROF(8)  // early STDP
@@ -1090,7 +1117,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     __syncthreads();
     PROF(12)
     if (Q.normalize && C.has_norm) {
-        float *part = xrow;  // [SNN_NORM_CHUNKS + 1][TJ]
+        float *part = (float *)xrow;  // [SNN_NORM_CHUNKS + 1][TJ]
         const int chunk = (P + SNN_NORM_CHUNKS - 1) / SNN_NORM_CHUNKS;
         #pragma unroll 1
         for (int idx = tid; idx < SNN_NORM_CHUNKS * TJ; idx += blockDim.x) {
@@ -1310,9 +1337,12 @@ __global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F
     }
 }
 
-// Pre-pass 2 (trace scan): the Input layer's trace for every step of the window, Nodes.forward
-// (nodes.py:96-103) applied T times per pixel: xtr[t][b][i] = x after step t.  Thread = 4 pixels of one
-// sample; loads run SCAN_U steps ahead.  Also leaves the layer's final state (x, s) behind.
+// Pre-pass 2 (trace scan): the Input layer's trace for every step of the window, Nodes.forward (nodes.py:96-103)
+// applied T times per pixel.  What the window kernel needs of it — the traces of a winner's sample for the STDP
+// post term — is stored as one AGE byte per (step, sample, pixel): steps since the pixel's last spike in this
+// window (255: none yet), a quarter of the fp32 size so that the whole window stays in L2; the trace is a table
+// lookup by age.  Thread = 4 pixels of one sample; loads run SCAN_U steps ahead.  Also leaves the layer's final
+// state (x, s) behind and keeps the incoming traces (for pixels that have not spiked yet).
 constexpr int SCAN_U = 10;
 __global__ void __launch_bounds__(256) snn_dc2_trace_scan(const __grid_constant__ F2Params Q) {
     const int P4 = Q.P >> 2;
@@ -1321,6 +1351,11 @@ __global__ void __launch_bounds__(256) snn_dc2_trace_scan(const __grid_constant_
     const snn_layer_t &X = Q.X;
     const size_t stride4 = (size_t)Q.B * P4;  // float4 / uchar4 units per timestep
     float4 x = X.traces ? ((const float4 *)X.x)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Q.x0c) {
+        ((float4 *)Q.x0c)[idx] = x;
+        if (x.x != 0.0f || x.y != 0.0f || x.z != 0.0f || x.w != 0.0f) *Q.anyx0 = 1;
+    }
+    uint32_t age = 0xffffffffu;   // 4 age bytes
     uint32_t last = 0;
     for (int t0 = 0; t0 < Q.T; t0 += SCAN_U) {
         uint32_t bits[SCAN_U];
@@ -1346,7 +1381,11 @@ __global__ void __launch_bounds__(256) snn_dc2_trace_scan(const __grid_constant_
                     x.y = trace_step(x.y, w & 0x100u, X.trace_decay, X.trace_scale, X.traces_additive);
                     x.z = trace_step(x.z, w & 0x10000u, X.trace_decay, X.trace_scale, X.traces_additive);
                     x.w = trace_step(x.w, w & 0x1000000u, X.trace_decay, X.trace_scale, X.traces_additive);
-                    if (Q.xtr) __stcs((float4 *)Q.xtr + (size_t)(t0 + u) * stride4 + idx, x);
+                    // ages: +1 per step (saturating below 255 = "none yet" is not needed: T <= 254), 0 on a spike
+                    const uint32_t never = __vcmpeq4(age, 0xffffffffu);            // bytes still 255
+                    age = (__vadd4(age, 0x01010101u) & ~never) | never;            // 255 stays 255
+                    age &= ~(w * 0xffu);                                            // spike: byte -> 0
+                    if (Q.xage) ((uint32_t *)Q.xage)[(size_t)(t0 + u) * stride4 + idx] = age;
                 }
                 last = w;
             }
@@ -1374,7 +1413,7 @@ int device_sms2() {
 }
 
 bool match2(const snn_net_t *net, const snn_run_opts_t *o, Match2 &m) {
-    if (net->n_layers != 3 || net->n_conns != 3 || o->T < 1 || o->T > 65000 || o->one_step) return false;
+    if (net->n_layers != 3 || net->n_conns != 3 || o->T < 1 || o->T > 254 || o->one_step) return false;   // T: one age byte per step
     m.lX = m.lE = m.lI = -1;
     for (int l = 0; l < 3; ++l) {
         const snn_layer_t &L = net->layers[l];
@@ -1410,7 +1449,7 @@ bool match2(const snn_net_t *net, const snn_run_opts_t *o, Match2 &m) {
     if (CX.rule == SNN_RULE_NOOP) return false;
     if (CX.rule >= SNN_RULE_POSTPRE && (!X.traces || !E.traces)) return false;
     const int n = E.n, P = X.n, B = o->B;
-    if (B > 128 || (P & 3) || P >= 65535 || n >= 65535) return false;
+    if (B > 128 || (P & 15) || P >= 65535 || n >= 65535) return false;   // P: 16-byte rows of age bytes for the bulk copies
     const int sms = device_sms2();
     m.SW = ((P + 31) / 32 + 3) / 4 * 4;
     m.BW = 4;
@@ -1443,7 +1482,7 @@ cudaError_t launch_cg2(const F2Params &Q, const Match2 &m, cudaStream_t stream) 
     return Q.prof ? launch_var2<CG, 4, 2>(Q, m, stream) : launch_var2<CG, 4, 0>(Q, m, stream);
 }
 
-struct WsLayout2 { size_t dense, bar, win, sisum, inS, inT, evS, rep, sisum0, xtr, prof, total; };
+struct WsLayout2 { size_t dense, bar, win, sisum, anyx0, inS, inT, evS, rep, sisum0, x0c, xage, prof, total; };
 WsLayout2 ws_layout2(const Match2 &m, int T, int B, int P, bool traces) {
     WsLayout2 L; size_t o = 0;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -1452,12 +1491,14 @@ WsLayout2 ws_layout2(const Match2 &m, int T, int B, int P, bool traces) {
     L.bar = o; o += al(sizeof(unsigned int) * 64);
     L.win = o; o += al(sizeof(unsigned long long) * 3 * (size_t)B);
     L.sisum = o; o += al(sizeof(unsigned int) * 3 * (size_t)B);
+    L.anyx0 = o; o += al(sizeof(int) * 4);
     L.inS = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * B * m.SW);
     L.inT = o; o += al(sizeof(uint32_t) * (size_t)(T + 1) * P * m.BW);
     L.evS = o; o += al((size_t)(T + 1) * m.SB);
     L.rep = o; o += al(sizeof(float) * (size_t)(m.nrep + 1));
     L.sisum0 = o; o += al(sizeof(unsigned int) * (size_t)B);
-    L.xtr = o; o += traces ? al(sizeof(float) * (size_t)T * B * P) : 0;
+    L.x0c = o; o += traces ? al(sizeof(float) * (size_t)B * P) : 0;
+    L.xage = o; o += traces ? al((size_t)T * B * P) : 0;
     L.prof = o; o += al(sizeof(long long) * (160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5));
     L.total = o;
     return L;
@@ -1505,7 +1546,10 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     Q.sisum = (unsigned int *)(ws + WL.sisum);
     Q.rep = (float *)(ws + WL.rep); Q.sisum0 = (unsigned int *)(ws + WL.sisum0);
     const bool stdp = Q.C.rule >= SNN_RULE_POSTPRE;
-    Q.xtr = (traces && stdp && net->learning && Q.C.nu1 != 0.0f) ? (float *)(ws + WL.xtr) : nullptr;
+    const bool need_x = traces && stdp && net->learning && Q.C.nu1 != 0.0f;
+    Q.xage = need_x ? (uint8_t *)(ws + WL.xage) : nullptr;
+    Q.x0c = need_x ? (float *)(ws + WL.x0c) : nullptr;
+    Q.anyx0 = (int *)(ws + WL.anyx0);
     Q.err = opts->err_flag;
     { const char *d = getenv("SNN_B200_DEBUG"); Q.dbg = d ? atoi(d) : 0; }
     const bool prof = getenv("SNN_B200_PROF") != nullptr;

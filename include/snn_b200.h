@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 6
+#define SNN_ABI_VERSION 7
 #define SNN_MAX_LAYERS 8
 #define SNN_MAX_CONNS 12
 
@@ -271,6 +271,17 @@ int snn_b200_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, 
 int snn_b200_conn_update(const snn_net_t *net, int32_t conn_index, int32_t B, void *workspace,
                          size_t workspace_bytes, void *stream);
 int snn_b200_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, void *stream);
+
+/* On-device spike encoders — the step before the hot path: the reference's callers encode on
+ * the CPU and ship [time, batch, ...] uint8 spikes to the device; these write the same tensor on the device from the
+ * rate image.  `out` is [T][n] uint8 (n = batch * pixels, the element order of the rate tensor), 0/1.
+ *   snn_b200_encode_poisson   = bindsnet.encoding.poisson (encodings.py:99-156): rate_hz[n] in Hz, inter-spike intervals
+ *                               ~ Poisson(1000 / (rate * dt)) steps, zero intervals bumped to one, rate 0 never spikes
+ *   snn_b200_encode_bernoulli = bindsnet.encoding.bernoulli (encodings.py:50-96): prob[n] = max_prob * normalised datum,
+ *                               one independent trial per step
+ * Counter-based Philox-4x32-10 keyed by (seed, element): same distribution as the reference, not its random stream. */
+int snn_b200_encode_poisson(const float *rate_hz, int32_t n, int32_t T, float dt, uint64_t seed, uint8_t *out, void *stream);
+int snn_b200_encode_bernoulli(const float *prob, int32_t n, int32_t T, uint64_t seed, uint8_t *out, void *stream);
 
 /* Library/ABI identification. */
 int snn_b200_abi_version(void);
