@@ -25,8 +25,17 @@ def namespace(kind: str) -> SimpleNamespace:
         import types
 
         if "bindsnet" not in sys.modules:
+            import os
+
+            here = os.path.dirname(os.path.abspath(__file__))
+            # the live reference: /root/reference in the build container, else the copy baseline/install_ref.sh made
+            ref = "/root/reference/bindsnet"
+            if not os.path.isdir(ref):
+                ref = os.path.join(here, "..", "..", "baseline", "_ref", "bindsnet")
+            if not os.path.isdir(ref):
+                raise ImportError("the reference is neither at /root/reference nor under baseline/_ref")
             pkg = types.ModuleType("bindsnet")
-            pkg.__path__ = ["/root/reference/bindsnet"]
+            pkg.__path__ = [ref]
             sys.modules["bindsnet"] = pkg
         import bindsnet.utils  # noqa: F401  (import order matters: SURVEY.md §8b)
         import bindsnet.network  # noqa: F401
