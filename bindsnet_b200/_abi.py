@@ -119,6 +119,7 @@ class SnnConn(C.Structure):
         ("elig", C.c_void_p),
         ("mst_spre", C.c_void_p),
         ("mst_spost", C.c_void_p),
+        ("mask", C.c_void_p),
     ]
 
 

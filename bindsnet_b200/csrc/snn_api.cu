@@ -54,6 +54,7 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
         }
         if (C.rule >= SNN_RULE_POSTPRE && C.rule <= SNN_RULE_MCC_POSTPRE && (!net->layers[C.src].traces || !net->layers[C.tgt].traces))
             return SNN_ERR_BAD_ARG;
+        if (C.mask && (C.kind != SNN_CONN_DENSE || C.rule == SNN_RULE_MSTDP)) return SNN_ERR_UNSUPPORTED;
     }
     return SNN_OK;
 }
@@ -169,6 +170,7 @@ int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *
         N.conns[c] = net->conns[c];
         const snn_conn_t &C = net->conns[c];
         if (C.rule == SNN_RULE_MSTDP || (C.kind == SNN_CONN_CONV2D && C.rule != SNN_RULE_NONE)) N.sync_after_learning = 1;
+        if (C.mask) N.any_mask = 1;
     }
     if (cudaMemsetAsync(N.bar, 0, sizeof(unsigned int) * 96, stream) != cudaSuccess) return SNN_ERR_CUDA;
     const int e = snn_generic_launch(N, stream);

@@ -36,6 +36,7 @@ struct DevMstdp {
 
 struct DevNet {
     int32_t n_layers, n_conns, learning, T, B, normalize, total_items, any_one_spike;
+    int32_t any_mask;             // some connection carries a mask (Network.run(..., masks=...))
     int32_t one_step;             // Network.run(one_step=True): layers in insertion order, inputs from current spikes
     int32_t sync_after_learning;  // some rule updates weights another CTA gathers from in the next step
                                   // (MSTDP, conv connections): one more grid barrier per step

@@ -1432,7 +1432,7 @@ bool match2(const snn_net_t *net, const snn_run_opts_t *o, Match2 &m) {
     m.cXE = m.cEI = m.cIE = -1;
     for (int c = 0; c < 3; ++c) {
         const snn_conn_t &C = net->conns[c];
-        if (C.b || C.kind == SNN_CONN_CONV2D || C.rule > SNN_RULE_MCC_POSTPRE) return false;
+        if (C.b || C.mask || C.kind == SNN_CONN_CONV2D || C.rule > SNN_RULE_MCC_POSTPRE) return false;
         if (C.src == m.lX && C.tgt == m.lE) m.cXE = c;
         else if (C.src == m.lE && C.tgt == m.lI) m.cEI = c;
         else if (C.src == m.lI && C.tgt == m.lE) m.cIE = c;

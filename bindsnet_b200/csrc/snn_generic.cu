@@ -120,6 +120,15 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) snn_generic_window(const __gr
             // rows) and conv filters are read by other CTAs in the next step's gather
             if (N.sync_after_learning && !grid_barrier(N.bar, G, N.err)) return;
         }
+        if (N.any_mask) {   // connection masks apply after the update, learning or not (topology.py:127-131)
+            for (int item = blockIdx.x; item < N.total_items; item += G) {
+                int li, tile; item_of(N, item, li, tile);
+                for (int c = 0; c < N.n_conns; ++c) {
+                    const snn_conn_t &C = N.conns[c];
+                    if (C.mask && C.tgt == li && C.kind == SNN_CONN_DENSE) mask_tile(C, N.layers[C.src].L.n, N.layers[li].L.n, tile);
+                }
+            }
+        }
     }
 
     if (N.normalize) {

@@ -466,6 +466,19 @@ __device__ void normalize_conv_item(const snn_conn_t &C, int tile, int ntiles) {
     }
 }
 
+// Connection masks (Network.run(..., masks=...), network.py:449 -> AbstractConnection.update, topology.py:127-131): the
+// masked weights of this column tile are zero after every step's update.
+__device__ void mask_tile(const snn_conn_t &C, int ns, int nt, int tile) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = tile * SNN_TILE + lane;
+    if (j < nt)
+        for (int i = warp; i < ns; i += SNN_GEN_WARPS) {
+            const size_t k = (size_t)i * nt + j;
+            if (C.mask[k]) C.w[k] = 0.0f;
+        }
+    __syncthreads();
+}
+
 // normalize(): Connection.normalize (topology.py:383-392) / AbstractFeature.normalize
 // (topology_features.py:250-266) on one tile; row chunking as documented in snn_b200.h.
 __device__ void normalize_tile(const snn_conn_t &C, int ns, int nt, int tile, float *s_part) {

@@ -161,8 +161,13 @@ def build_net(
                 d.rec_v = _ptr(r[1]); keep.append(r[1])
             if len(r) > 2 and r[2] is not None:
                 d.rec_count = _ptr(r[2]); keep.append(r[2])
+    masks = getattr(network, "_conn_masks", None) or {}
     for i, ((src, tgt), conn) in enumerate(network.connections.items()):
         fill_conn(net.conns[i], conn, index[src], index[tgt], float(network.dt), B, getattr(network, "_rule_kwargs", None))
+        m = masks.get((src, tgt))
+        if m is not None:
+            net.conns[i].mask = _ptr(m)
+            keep.append(m)
     return net, keep
 
 

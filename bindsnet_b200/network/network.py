@@ -90,8 +90,6 @@ class Network(torch.nn.Module):
             "'inputs' must be a dict of names of layers (str) and relevant input tensors. "
             f"Got {type(inputs).__name__} instead."
         )
-        if kwargs.get("masks"):
-            raise NotImplementedError("run(..., masks=...) is outside the implemented hot path")
         # reward-modulated rules (learning.MSTDP) read these from the run's kwargs (network.py:319-377,
         # learning.py:1540-1556); the reward_fn hook of the constructor is not implemented
         self._rule_kwargs = {k: kwargs.get(k, None) for k in ("reward", "a_plus", "a_minus")}
@@ -117,6 +115,7 @@ class Network(torch.nn.Module):
             inputs, timesteps, normalize=bool(kwargs.get("b200_normalize", True)),
             clamp=kwargs.get("clamp", {}), unclamp=kwargs.get("unclamp", {}),
             injects_v=kwargs.get("injects_v", {}), seed=kwargs.get("one_spike_seed", None), one_step=bool(one_step),
+            masks=kwargs.get("masks", {}) or {},
         )
 
     def _device(self) -> torch.device:
@@ -168,10 +167,33 @@ class Network(torch.nn.Module):
                 return name if ok else None
         return None
 
+    def _stage_conn_masks(self, masks, dev: torch.device):
+        """``masks={(source, target): bool tensor}`` (network.py:279-280,321): weights to clamp to zero after every
+        step's update (AbstractConnection.update, topology.py:127-131)."""
+        from .topology import Connection
+
+        out = {}
+        for key, m in (masks or {}).items():
+            if m is None:
+                continue
+            if key not in self.connections:
+                continue                                  # network.py:449 looks masks up per connection: unknown keys are ignored
+            conn = self.connections[key]
+            if hasattr(conn, "pipeline"):
+                continue                                  # MulticompartmentConnection.update ignores the kwarg (topology.py:509-518)
+            if not isinstance(conn, Connection):
+                raise NotImplementedError(f"masks for {type(conn).__name__} are outside the implemented path (dense Connection only)")
+            m = torch.as_tensor(m)
+            if tuple(m.shape) != tuple(conn.w.shape):
+                raise ValueError(f"mask for {key} has shape {tuple(m.shape)}, weights {tuple(conn.w.shape)}")
+            out[key] = (m != 0).to(dev, torch.uint8).contiguous()
+        return out
+
     def _run_window(self, inputs, T: int, normalize: bool, clamp=None, unclamp=None, injects_v=None,
-                    seed: Optional[int] = None, step_offset: int = 0, one_step: bool = False) -> None:
+                    seed: Optional[int] = None, step_offset: int = 0, one_step: bool = False, masks=None) -> None:
         self._one_step = bool(one_step)
         dev = self._device()
+        self._conn_masks = self._stage_conn_masks(masks, dev)
         B = self.batch_size
         if T <= 0:
             if normalize:

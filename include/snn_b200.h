@@ -164,6 +164,10 @@ typedef struct snn_conn {
     float p_plus_decay, p_minus_decay; /* exp(-dt/tc_plus), exp(-dt/tc_minus), computed by the host in fp32 */
     float *p_plus, *p_minus, *elig;
     uint8_t *mst_spre, *mst_spost;
+    /* Network.run(..., masks={(source, target): mask}) (network.py:279-280,321,449): weights whose mask byte is non-zero are
+       forced to 0 after every step's update, learning or not (AbstractConnection.update, topology.py:127-131).  [n_src, n_tgt]
+       bytes, SNN_CONN_DENSE only (MulticompartmentConnection.update ignores the kwarg, topology.py:509-518); NULL = none. */
+    const uint8_t *mask;
 } snn_conn_t;
 
 typedef struct snn_net {

@@ -594,6 +594,14 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
                         for (size_t k = 0; k < (size_t)C->cout * C->cin * C->kh * C->kw; ++k) C->w[k] = C->w[k] * C->weight_decay;
                 } else conn_update(net, C, o, &cws[c], dense);
             }
+        /* connection masks (network.py:449 -> AbstractConnection.update, topology.py:127-131): after the update,
+         * whether or not learning is on */
+        for (int c = 0; c < net->n_conns; ++c) {
+            const snn_conn_t *C = &net->conns[c];
+            if (!C->mask || C->kind != SNN_CONN_DENSE) continue;
+            const size_t NW = (size_t)net->layers[C->src].n * net->layers[C->tgt].n;
+            for (size_t k = 0; k < NW; ++k) if (C->mask[k]) C->w[k] = 0.0f;
+        }
         /* 4. monitors (network.py:460-461, monitors.py:94-111) */
         for (int l = 0; l < net->n_layers; ++l) {
             const snn_layer_t *L = &net->layers[l];

@@ -106,6 +106,26 @@ def lif_postpre_batch(ns, inputs=None):
     return net, inputs, {}, 120
 
 
+# Network.run(..., masks={(source, target): mask}) (network.py:279-280,449; topology.py:127-131): two connections into
+# one layer, one learned + masked, one static (NoOp) + masked, plus a masked connection with learning switched off
+def lif_postpre_masked(ns, inputs=None):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=60, traces=True)
+    Z = ns.nodes.Input(n=20, traces=True)
+    Y = ns.nodes.LIFNodes(n=40, traces=True, thresh=-57.0, refrac=2)
+    C1 = ns.topology.Connection(source=X, target=Y, w=_w((60, 40), 51, 0.9), update_rule=ns.learning.PostPre, nu=(2e-3, 2e-2),
+                                reduction=torch.sum, wmin=0.0, wmax=1.0, norm=15.0)
+    C2 = ns.topology.Connection(source=Z, target=Y, w=_w((20, 40), 52, 0.5))
+    net.add_layer(X, "X"); net.add_layer(Z, "Z"); net.add_layer(Y, "Y")
+    net.add_connection(C1, "X", "Y"); net.add_connection(C2, "Z", "Y")
+    g = torch.Generator().manual_seed(53)
+    masks = {("X", "Y"): torch.bernoulli(0.3 * torch.ones(60, 40), generator=g).bool(),
+             ("Z", "Y"): torch.bernoulli(0.5 * torch.ones(20, 40), generator=g).bool()}
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(90, 3, (60,), 0.15, 54), "Z": _bernoulli_inputs(90, 3, (20,), 0.2, 55)}
+    return net, inputs, {"masks": masks}, 90
+
+
 # WeightDependentPostPre, mean reduction
 def lif_wdep(ns, inputs=None):
     net = ns.Network(dt=1.0)
@@ -342,6 +362,7 @@ CASES = {
     "c1_lif_postpre": c1_lif_postpre,
     "lif_postpre_batch": lif_postpre_batch,
     "lif_wdep": lif_wdep,
+    "lif_postpre_masked": lif_postpre_masked,
     "lif_clamps": lif_clamps,
     "dc2015_multi": dc2015_multi,
     "dc2015_onespike": dc2015_onespike,

@@ -63,8 +63,11 @@ def test_unsupported_reference_features_fail_loudly():
     with pytest.raises(NotImplementedError):
         Connection(X, Y, w_dtype=torch.float16)
     net = TwoLayerNetwork(n_inpt=8, n_neurons=4)
-    with pytest.raises(NotImplementedError):
-        net.run({"X": torch.zeros(3, 1, 8)}, time=3, masks={("X", "Y"): torch.ones(8, 4, dtype=torch.bool)})
+    with OracleBackend():   # masks (network.py:279-280): implemented for dense connections — all weights masked -> all zero
+        net.run({"X": torch.ones(3, 1, 8, dtype=torch.uint8)}, time=3, masks={("X", "Y"): torch.ones(8, 4, dtype=torch.bool)})
+    assert float(net.connections[("X", "Y")].w.abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        net.run({"X": torch.zeros(3, 1, 8)}, time=3, masks={("X", "Y"): torch.ones(4, 8, dtype=torch.bool)})   # wrong shape
     with pytest.raises(AssertionError):
         net.run([torch.zeros(3, 1, 8)], time=3)
 
