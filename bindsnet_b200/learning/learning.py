@@ -57,7 +57,19 @@ class LearningRule(ABC):
 
     def update(self, **kwargs) -> None:
         """Apply this rule once to the connection from the layers' current ``s``/``x``
-        (reference: the rule-specific ``_connection_update`` + learning.py:87-104)."""
+        (reference: the rule-specific ``_connection_update`` + learning.py:87-104).
+
+        A USER-DEFINED rule (a subclass that changes ``self.connection.w`` itself with torch ops and then calls
+        ``super().update()``, learning.py:31-104) gets the reference's base behaviour here: weight decay and the
+        clamp to ``[wmin, wmax]``; ``Network.run`` drives networks with such rules step by step (the scripted tier)."""
+        if self.rule_code is None:
+            w = self.connection.w
+            if self.weight_decay:                                         # learning.py:93-94
+                w *= self.weight_decay
+            wmin, wmax = self.connection.wmin, self.connection.wmax       # learning.py:97-104
+            if bool((wmin != -np.inf).any()) or bool((wmax != np.inf).any()):
+                w.clamp_(float(wmin), float(wmax))
+            return
         from ..network import _plan
 
         _plan.update_single_connection(self.connection)

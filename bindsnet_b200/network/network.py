@@ -208,6 +208,9 @@ class Network(torch.nn.Module):
             seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: torch.manual_seed governs it
         self.last_one_spike_seed = seed
 
+        if self._scripted_required():
+            return self._run_scripted(ext, T, normalize, clamps, unclamps, injects, self._conn_masks, bool(one_step))
+
         fused = {name: self._fusable_monitor(m) for name, m in self.monitors.items()}
         if any(layer is None for layer in fused.values()):
             return self._run_stepwise(ext, T, normalize, clamps, unclamps, injects, seed, step_offset)
@@ -282,6 +285,88 @@ class Network(torch.nn.Module):
                 if isinstance(m, SpikeCounter) and t == 0:
                     m._begin_window(B, self._device())
                 m.record()
+
+    # -- scripted tier: user-defined populations / rules / connections -------------------------------
+    def _scripted_required(self) -> bool:
+        """True when the network holds an object the window kernels cannot execute: a ``Nodes`` subclass with its
+        own ``forward``, a ``LearningRule`` subclass with its own ``update``, a connection class of the user's.
+        Such networks run step by step like the reference's loop (network.py:380-461), every built-in piece still on
+        its CUDA single-operator kernel, the user's pieces as the torch code they are."""
+        from ..learning import learning as L
+        from ..learning import MCC_learning as ML
+        from . import nodes as N, topology as Tp
+
+        builtin_nodes = (N.Input, N.LIFNodes, N.DiehlAndCookNodes)
+        for layer in self.layers.values():
+            if type(layer) not in builtin_nodes and (layer.kind is None or type(layer).forward is not N.Nodes.forward):
+                return True
+        builtin_conns = (Tp.Connection, Tp.MulticompartmentConnection, Tp.Conv2dConnection)
+        for conn in self.connections.values():
+            if type(conn) not in builtin_conns:
+                return True
+            rule = getattr(conn, "update_rule", None)
+            if rule is not None and (rule.rule_code is None or type(rule).update is not L.LearningRule.update
+                                     and type(rule) not in (L.NoOp, L.PostPre, L.WeightDependentPostPre, L.MSTDP)):
+                return True
+        return False
+
+    def _run_scripted(self, ext, T, normalize, clamps, unclamps, injects, masks, one_step) -> None:
+        """Per-timestep executor with the reference's own control flow (network.py:380-465): inputs from the
+        previous step's spikes in connection insertion order, layers in insertion order, clamp / unclamp /
+        injects_v, connection updates, monitors, end-of-run normalize."""
+        B = self.batch_size
+        dev = self._device()
+        rule_kwargs = {k: v for k, v in (getattr(self, "_rule_kwargs", None) or {}).items() if v is not None}
+
+        def get_inputs(only=None):
+            cur = {}
+            for (src, tgt), conn in self.connections.items():                 # network.py:225-248
+                if only is not None and tgt not in only:
+                    continue
+                out = conn.compute(self.layers[src].s)
+                out = out.view(B, *self.layers[tgt].shape).float()
+                cur[tgt] = cur[tgt] + out if tgt in cur else out
+            return cur
+
+        for t in range(T):
+            current = {} if one_step else get_inputs()
+            for lname, layer in self.layers.items():                          # network.py:386-413
+                if one_step:
+                    current.update(get_inputs(only=[lname]))
+                e = ext.get(lname)
+                if e is not None:
+                    x_ext = e[t].view(B, *layer.shape)
+                    if lname in current and not one_step:
+                        x = current[lname] + x_ext.float()
+                    elif lname in current:
+                        x = current[lname]                                    # one-step mode drops the external input (network.py:393-396)
+                    else:
+                        x = x_ext
+                else:
+                    x = current.get(lname)
+                    if x is None:
+                        x = torch.zeros(B, *layer.shape, device=dev)
+                inj = injects.get(lname)
+                if inj is not None:                                           # network.py:398-404
+                    layer.v += (inj[t] if inj.dim() == 2 else inj).view(1, *layer.shape)
+                layer.forward(x=x)
+                c = clamps.get(lname)
+                if c is not None:                                             # network.py:415-421
+                    m = (c[t] if c.dim() == 2 else c).bool().view(1, *layer.shape).expand(B, *layer.shape)
+                    layer.s = layer.s | m if layer.s.dtype == torch.bool else layer.s.masked_fill(m, 1)
+                u = unclamps.get(lname)
+                if u is not None:                                             # network.py:423-429
+                    m = (u[t] if u.dim() == 2 else u).bool().view(1, *layer.shape).expand(B, *layer.shape)
+                    layer.s = layer.s & ~m if layer.s.dtype == torch.bool else layer.s.masked_fill(m, 0)
+            for key, conn in self.connections.items():                        # network.py:431-454
+                conn.update(mask=masks.get(key), learning=self.learning, **rule_kwargs)
+            for m in self.monitors.values():                                  # network.py:460-461
+                if isinstance(m, SpikeCounter) and t == 0:
+                    m._begin_window(B, dev)
+                m.record()
+        if normalize:
+            for conn in self.connections.values():                            # network.py:464-465
+                conn.normalize()
 
     def check_errors(self) -> None:
         """Synchronise and raise if the device reported an error (non-binary input spikes,

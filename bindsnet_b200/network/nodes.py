@@ -92,10 +92,26 @@ class Nodes(torch.nn.Module):
     # -- reference API -------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> None:
         """One simulation step of this population alone (reference: ``Nodes.forward`` and
-        its overrides).  ``x`` is the input of the step, shape ``[B, *shape]``."""
-        from . import _plan
+        its overrides).  ``x`` is the input of the step, shape ``[B, *shape]``.
 
-        _plan.step_single_layer(self, x)
+        For the populations the CUDA core implements (``kind`` set) this submits a one-layer, one-step window.  For a
+        USER-DEFINED population (a subclass that computes ``v`` / ``s`` itself with torch ops and then calls
+        ``super().forward(x)``, the extension contract of docs/source/guide/guide_part_ii.rst:69-73) it is the
+        reference's base behaviour — spike traces and summed input (nodes.py:96-107) — in torch ops on the layer's
+        own device; ``Network.run`` drives such layers step by step (the scripted tier)."""
+        if self.kind is not None:
+            from . import _plan
+
+            _plan.step_single_layer(self, x)
+            return
+        if self.traces:
+            self.x *= self.trace_decay
+            if self.traces_additive:
+                self.x += self.trace_scale * self.s.float()
+            else:
+                self.x.masked_fill_(self.s.bool(), float(self.trace_scale))
+        if self.sum_input:
+            self.summed += x.float()
 
     def reset_state_variables(self) -> None:
         """nodes.py:109-120."""

@@ -59,10 +59,11 @@ class AbstractConnection(ABC, Module):
 
     def update(self, **kwargs) -> None:
         """topology.py:112-139: apply the learning rule to the current layer state."""
-        if kwargs.get("mask", None) is not None:
-            raise NotImplementedError("connection masks are not implemented by the CUDA core")
         if kwargs.get("learning", True):
             self.update_rule.update(**kwargs)
+        mask = kwargs.get("mask", None)
+        if mask is not None:                                              # topology.py:127-131
+            self.w.masked_fill_(mask.to(self.w.device).bool(), 0)
 
     def reset_state_variables(self) -> None:
         pass
