@@ -26,7 +26,8 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
     if (o->T < 0 || o->B <= 0) return SNN_ERR_BAD_ARG;
     for (int l = 0; l < net->n_layers; ++l) {
         const snn_layer_t &L = net->layers[l];
-        if (L.kind < SNN_NODE_INPUT || L.kind > SNN_NODE_DC) return SNN_ERR_UNSUPPORTED;
+        if (L.kind < SNN_NODE_INPUT || L.kind > SNN_NODE_CURRENT_LIF) return SNN_ERR_UNSUPPORTED;
+        if (L.kind == SNN_NODE_CURRENT_LIF && !L.i) return SNN_ERR_BAD_ARG;
         if (L.n <= 0 || !L.s) return SNN_ERR_BAD_ARG;
         if (L.kind != SNN_NODE_INPUT && (!L.v || !L.refrac_count)) return SNN_ERR_BAD_ARG;
         if (L.kind == SNN_NODE_DC && !L.theta) return SNN_ERR_BAD_ARG;

@@ -117,6 +117,31 @@ __device__ __forceinline__ bool lif_step(const snn_layer_t &L, float &v, float &
     return s;
 }
 
+// IFNodes.forward (nodes.py:377-394): no leak, the gate is taken before the refractory decrement, x stays unmasked.
+__device__ __forceinline__ bool if_step(const snn_layer_t &L, float &v, float &rc, float xin) {
+    const float gate = rc <= 0.0f ? 1.0f : 0.0f;
+    v = v + gate * xin;
+    rc = rc - L.dt;
+    const bool s = v >= L.thresh;
+    if (s) { rc = L.refrac; v = L.reset; }
+    if (L.has_lbound && v < L.lbound) v = L.lbound;
+    return s;
+}
+
+// CurrentLIFNodes.forward (nodes.py:770-791): decaying synaptic current `ic`, gate taken after the decrement.
+__device__ __forceinline__ bool clif_step(const snn_layer_t &L, float &v, float &rc, float &ic, float xin) {
+    v = L.decay * (v - L.rest) + L.rest;
+    ic = ic * L.i_decay;
+    rc = rc - L.dt;
+    ic = ic + xin;
+    const float gate = rc <= 0.0f ? 1.0f : 0.0f;
+    v = v + gate * ic;
+    const bool s = v >= L.thresh;
+    if (s) { rc = L.refrac; v = L.reset; }
+    if (L.has_lbound && v < L.lbound) v = L.lbound;
+    return s;
+}
+
 // DiehlAndCookNodes.forward up to the threshold test (nodes.py:1077-1092); `theta` is the
 // already decayed adaptive threshold of the neuron.  Returns the candidate flag.
 __device__ __forceinline__ bool dc_step(const snn_layer_t &L, float &v, float &rc, float xin, float theta) {

@@ -127,6 +127,12 @@ __device__ void phase1(const DevNet &N, int li, int tile, int t, float *s_red, i
                 if (dc) {
                     s = dc_step(L, v, rc, xin, theta);
                     if (L.has_lbound && v < L.lbound) v = L.lbound;  // nodes.py:1108-1109
+                } else if (L.kind == SNN_NODE_IF) {
+                    s = if_step(L, v, rc, xin);
+                } else if (L.kind == SNN_NODE_CURRENT_LIF) {
+                    float ic = L.i[k];
+                    s = clif_step(L, v, rc, ic, xin);
+                    L.i[k] = ic;
                 } else {
                     s = lif_step(L, v, rc, xin);
                 }

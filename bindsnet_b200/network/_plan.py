@@ -44,6 +44,8 @@ def fill_layer(d: "_abi.SnnLayer", layer, name: str, B: int) -> None:
         d.refrac_count = _ptr(_state(layer.refrac_count, "refrac_count", name))
     if d.kind == _abi.SNN_NODE_DC:
         d.theta = _ptr(_state(layer.theta, "theta", name))
+    if d.kind == _abi.SNN_NODE_CURRENT_LIF:
+        d.i = _ptr(_state(layer.i, "i", name))
     if layer.traces:
         d.x = _ptr(_state(layer.x, "x", name))
     if layer.sum_input:

@@ -362,11 +362,128 @@ def _unsupported(name: str, where: str):
     return _Unsupported
 
 
+class IFNodes(Nodes):
+    """Integrate-and-fire without leak (reference: nodes.py:308-415; forward :377-394)."""
+
+    kind = _abi.SNN_NODE_IF
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        thresh: Scalar = -52.0,
+        reset: Scalar = -65.0,
+        refrac: Scalar = 5,
+        lbound: float = None,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive,
+            tc_trace=tc_trace, trace_scale=trace_scale, sum_input=sum_input,
+        )
+        self.register_buffer("reset", torch.as_tensor(reset, dtype=torch.float))
+        self.register_buffer("thresh", torch.as_tensor(thresh, dtype=torch.float))
+        self.register_buffer("refrac", torch.as_tensor(refrac))
+        self.register_buffer("v", torch.zeros(0))
+        self.register_buffer("refrac_count", torch.zeros(0))
+        self.lbound = None if lbound is None else torch.tensor(lbound, dtype=torch.float)
+
+    def reset_state_variables(self) -> None:
+        """nodes.py:396-403."""
+        super().reset_state_variables()
+        self.v.fill_(self.reset)
+        self.refrac_count.zero_()
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:405-415."""
+        super().set_batch_size(batch_size=batch_size)
+        dev = self.v.device
+        self.v = self.reset * torch.ones(batch_size, *self.shape, device=dev)
+        self.refrac_count = torch.zeros_like(self.v)
+
+    def _fill_desc(self, d) -> None:
+        super()._fill_desc(d)
+        d.reset = _scalar(self.reset, "reset")
+        d.thresh = _scalar(self.thresh, "thresh")
+        d.refrac = _scalar(self.refrac, "refrac")
+        d.has_lbound = int(self.lbound is not None)
+        d.lbound = _scalar(self.lbound, "lbound") if self.lbound is not None else 0.0
+
+
+class CurrentLIFNodes(LIFNodes):
+    """Current-based LIF: the input feeds a decaying synaptic current (reference: nodes.py:681-826; forward
+    :770-791)."""
+
+    kind = _abi.SNN_NODE_CURRENT_LIF
+
+    def __init__(self, *args, tc_i_decay: Scalar = 2.0, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.register_buffer("tc_i_decay", torch.as_tensor(tc_i_decay, dtype=torch.float))
+        self.register_buffer("i_decay", torch.zeros(()))
+        self.register_buffer("i", torch.zeros(0))
+
+    def reset_state_variables(self) -> None:
+        """nodes.py:793-801."""
+        super().reset_state_variables()
+        self.i.zero_()
+
+    def _reset_plan(self):
+        zeros, fills = super()._reset_plan()
+        return zeros + [self.i], fills
+
+    def compute_decays(self, dt) -> None:
+        """nodes.py:803-820."""
+        super().compute_decays(dt=dt)
+        self.i_decay = _exp_decay(self.dt, self.tc_i_decay)
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:822-826."""
+        super().set_batch_size(batch_size=batch_size)
+        self.i = torch.zeros_like(self.v)
+
+    def _fill_desc(self, d) -> None:
+        super()._fill_desc(d)
+        d.i_decay = _scalar(self.i_decay, "tc_i_decay")
+
+
+class AdaptiveLIFNodes(DiehlAndCookNodes):
+    """LIF with an adaptive threshold shared across the batch (reference: nodes.py:829-978).  Its ``forward``
+    (:921-946) is ``DiehlAndCookNodes.forward`` without the one-spike arbitration, so it runs on the same kernels
+    with ``one_spike`` off; only the constructor defaults differ (none, in fact)."""
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        rest: Scalar = -65.0,
+        reset: Scalar = -65.0,
+        thresh: Scalar = -52.0,
+        refrac: Scalar = 5,
+        tc_decay: Scalar = 100.0,
+        theta_plus: Scalar = 0.05,
+        tc_theta_decay: Scalar = 1e7,
+        lbound: float = None,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive, tc_trace=tc_trace, trace_scale=trace_scale,
+            sum_input=sum_input, thresh=thresh, rest=rest, reset=reset, refrac=refrac, tc_decay=tc_decay, theta_plus=theta_plus,
+            tc_theta_decay=tc_theta_decay, lbound=lbound, one_spike=False,
+        )
+
+
 McCullochPitts = _unsupported("McCullochPitts", "nodes.py:231-305")
-IFNodes = _unsupported("IFNodes", "nodes.py:308-415")
 BoostedLIFNodes = _unsupported("BoostedLIFNodes", "nodes.py:562-678")
-CurrentLIFNodes = _unsupported("CurrentLIFNodes", "nodes.py:681-826")
-AdaptiveLIFNodes = _unsupported("AdaptiveLIFNodes", "nodes.py:829-978")
 IzhikevichNodes = _unsupported("IzhikevichNodes", "nodes.py:1147-1316")
 CSRMNodes = _unsupported("CSRMNodes", "nodes.py:1319-1552")
 SRM0Nodes = _unsupported("SRM0Nodes", "nodes.py:1555-1701")

@@ -41,7 +41,10 @@ extern "C" {
 /* ---- node kinds (reference: bindsnet/network/nodes.py) ---- */
 #define SNN_NODE_INPUT 0 /* Input            nodes.py:172-228  */
 #define SNN_NODE_LIF 1   /* LIFNodes         nodes.py:418-559  */
-#define SNN_NODE_DC 2    /* DiehlAndCookNodes nodes.py:981-1144 */
+#define SNN_NODE_DC 2    /* DiehlAndCookNodes nodes.py:981-1144; with one_spike = 0 also AdaptiveLIFNodes nodes.py:829-978
+                            (the same arithmetic: decay, theta decay, gated input, threshold + theta, theta += plus * sum_b s) */
+#define SNN_NODE_IF 3         /* IFNodes          nodes.py:308-415: no leak, gate taken before the refractory decrement */
+#define SNN_NODE_CURRENT_LIF 4 /* CurrentLIFNodes nodes.py:681-826: decaying synaptic current i, gate taken after the decrement */
 
 /* ---- connection kinds (reference: bindsnet/network/topology.py) ---- */
 #define SNN_CONN_DENSE 0 /* Connection: s.float() @ w + b                topology.py:332-346 */
@@ -124,6 +127,9 @@ typedef struct snn_layer {
     int32_t *rec_count; /* [B,n] += number of spikes of each neuron over the window (what the
                            reference's callers compute as spikes.sum(time), e.g.
                            examples/mnist/batch_eth_mnist.py:280-284); NULL = not counted */
+    /* SNN_NODE_CURRENT_LIF */
+    float *i;           /* [B,n] synaptic input current, updated in place (nodes.py:771,778) */
+    float i_decay;      /* exp(-dt/tc_i_decay) (nodes.py:818-820) */
 } snn_layer_t;
 
 /* One dense synapse matrix.  Reference: Connection (topology.py:265-399) or

@@ -57,7 +57,8 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
         if (L->kind == SNN_NODE_DC && !L->theta) return SNN_ERR_BAD_ARG;
         if (L->traces && !L->x) return SNN_ERR_BAD_ARG;
         if (L->sum_input && !L->summed) return SNN_ERR_BAD_ARG;
-        if (L->kind < 0 || L->kind > SNN_NODE_DC) return SNN_ERR_UNSUPPORTED;
+        if (L->kind < 0 || L->kind > SNN_NODE_CURRENT_LIF) return SNN_ERR_UNSUPPORTED;
+        if (L->kind == SNN_NODE_CURRENT_LIF && !L->i) return SNN_ERR_BAD_ARG;
     }
     for (int c = 0; c < net->n_conns; ++c) {
         const snn_conn_t *C = &net->conns[c];
@@ -211,6 +212,33 @@ static void layer_forward(const snn_net_t *net, int l, const snn_run_opts_t *o, 
                 if (L->has_lbound && v < L->lbound) v = L->lbound;    /* :526-527 */
                 L->v[k] = v; L->refrac_count[k] = rc; L->s[k] = (uint8_t)s;
                 trace_and_sum(L, k, s, xin);                          /* :529 (masked x) */
+            }
+        } else if (L->kind == SNN_NODE_IF) {
+            /* IFNodes.forward (nodes.py:377-394): no leak; the gate is taken BEFORE the decrement; x is not masked */
+            for (size_t k = 0; k < BN; ++k) {
+                const float gate = L->refrac_count[k] <= 0.0f ? 1.0f : 0.0f;
+                float v = L->v[k] + gate * cur[k];                    /* :378 */
+                float rc = L->refrac_count[k] - L->dt;                /* :381 */
+                int s = v >= L->thresh;                               /* :384 */
+                if (s) { rc = L->refrac; v = L->reset; }              /* :387-388 */
+                if (L->has_lbound && v < L->lbound) v = L->lbound;    /* :391-392 */
+                L->v[k] = v; L->refrac_count[k] = rc; L->s[k] = (uint8_t)s;
+                trace_and_sum(L, k, s, cur[k]);                       /* :394 */
+            }
+        } else if (L->kind == SNN_NODE_CURRENT_LIF) {
+            /* CurrentLIFNodes.forward (nodes.py:770-791): the gate is taken AFTER the decrement, on the current i */
+            for (size_t k = 0; k < BN; ++k) {
+                float v = L->decay * (L->v[k] - L->rest) + L->rest;   /* :770 */
+                float ic = L->i[k] * L->i_decay;                      /* :771 */
+                float rc = L->refrac_count[k] - L->dt;                /* :774 */
+                ic = ic + cur[k];                                     /* :777 */
+                const float gate = rc <= 0.0f ? 1.0f : 0.0f;
+                v = v + gate * ic;                                    /* :778 */
+                int s = v >= L->thresh;                               /* :781 */
+                if (s) { rc = L->refrac; v = L->reset; }              /* :784-785 */
+                if (L->has_lbound && v < L->lbound) v = L->lbound;    /* :788-789 */
+                L->v[k] = v; L->i[k] = ic; L->refrac_count[k] = rc; L->s[k] = (uint8_t)s;
+                trace_and_sum(L, k, s, cur[k]);                       /* :791 */
             }
         } else { /* SNN_NODE_DC: DiehlAndCookNodes.forward (nodes.py:1069-1111) */
             uint8_t *cand = ws->cand;

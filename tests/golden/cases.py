@@ -126,6 +126,36 @@ def lif_postpre_masked(ns, inputs=None):
     return net, inputs, {"masks": masks}, 90
 
 
+# the other neuron models of the generic tier: IFNodes (nodes.py:308-415), CurrentLIFNodes
+# (nodes.py:681-826), AdaptiveLIFNodes (nodes.py:829-978), each as the target of a learned connection
+def _one_layer_model(ns, layer, w_seed, in_seed, T=90, B=3, n_in=70):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=n_in, traces=True)
+    C = ns.topology.Connection(source=X, target=layer, w=_w((n_in, layer.n), w_seed, 1.2), update_rule=ns.learning.PostPre,
+                               nu=(2e-3, 2e-2), reduction=torch.sum, wmin=0.0, wmax=1.5, norm=18.0)
+    net.add_layer(X, "X"); net.add_layer(layer, "Y"); net.add_connection(C, "X", "Y")
+    return net, {"X": _bernoulli_inputs(T, B, (n_in,), 0.15, in_seed)}, {}, T
+
+
+def if_postpre(ns, inputs=None):
+    Y = ns.nodes.IFNodes(n=36, traces=True, sum_input=True, thresh=-50.0, reset=-64.0, refrac=3, lbound=-66.0)
+    net, x, kw, T = _one_layer_model(ns, Y, 61, 62)
+    return net, (inputs or x), kw, T
+
+
+def clif_postpre(ns, inputs=None):
+    Y = ns.nodes.CurrentLIFNodes(n=36, traces=True, thresh=-55.0, rest=-65.0, reset=-63.0, refrac=2, tc_decay=40.0, tc_i_decay=3.0)
+    net, x, kw, T = _one_layer_model(ns, Y, 63, 64)
+    return net, (inputs or x), kw, T
+
+
+def alif_postpre(ns, inputs=None):
+    Y = ns.nodes.AdaptiveLIFNodes(n=36, traces=True, thresh=-56.0, rest=-65.0, reset=-62.0, refrac=2, tc_decay=50.0, theta_plus=0.4,
+                                  tc_theta_decay=200.0, lbound=-68.0)
+    net, x, kw, T = _one_layer_model(ns, Y, 65, 66)
+    return net, (inputs or x), kw, T
+
+
 # WeightDependentPostPre, mean reduction
 def lif_wdep(ns, inputs=None):
     net = ns.Network(dt=1.0)
@@ -363,6 +393,9 @@ CASES = {
     "lif_postpre_batch": lif_postpre_batch,
     "lif_wdep": lif_wdep,
     "lif_postpre_masked": lif_postpre_masked,
+    "if_postpre": if_postpre,
+    "clif_postpre": clif_postpre,
+    "alif_postpre": alif_postpre,
     "lif_clamps": lif_clamps,
     "dc2015_multi": dc2015_multi,
     "dc2015_onespike": dc2015_onespike,

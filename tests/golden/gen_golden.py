@@ -157,7 +157,7 @@ def generate(name: str) -> None:
         out[f"L/{lname}/count"] = raster.sum(dim=(0, 1)).to(torch.int32).numpy()
         out[f"L/{lname}/count_b"] = raster.sum(dim=(0, 2)).to(torch.int32).numpy()
         out[f"L/{lname}/s"] = np.asarray(layer.s.reshape(B, -1).to(torch.uint8).numpy())
-        for var in ("v", "refrac_count", "x", "theta", "summed"):
+        for var in ("v", "refrac_count", "x", "theta", "summed", "i"):
             val = getattr(layer, var, None)
             if isinstance(val, torch.Tensor) and val.numel() > 0:
                 out[f"L/{lname}/{var}"] = val.detach().reshape(-1 if var == "theta" else (B, -1)).float().numpy() \

@@ -52,7 +52,7 @@ def snapshot(net) -> Dict[str, np.ndarray]:
     for lname, layer in net.layers.items():
         B = layer.s.shape[0]
         out[f"L/{lname}/s"] = layer.s.reshape(B, -1).to(torch.uint8).cpu().numpy()
-        for var in ("v", "refrac_count", "x", "summed"):
+        for var in ("v", "refrac_count", "x", "summed", "i"):
             val = getattr(layer, var, None)
             if isinstance(val, torch.Tensor) and val.numel() > 0:
                 out[f"L/{lname}/{var}"] = val.detach().reshape(B, -1).float().cpu().numpy()
