@@ -46,8 +46,11 @@ def test_nodes_initial_state_like_reference():
 
 
 def test_unsupported_reference_features_fail_loudly():
+    from bindsnet_b200.network.nodes import IzhikevichNodes
+
+    assert IFNodes(n=10).kind is not None          # implemented since round 2
     with pytest.raises(NotImplementedError):
-        IFNodes(n=10)
+        IzhikevichNodes(n=10)
     with pytest.raises(NotImplementedError):
         Conv1dConnection(None, None, 3)
     X, Y = Input(n=4, traces=True), LIFNodes(n=4, traces=True)
