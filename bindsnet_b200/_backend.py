@@ -59,6 +59,10 @@ def lib() -> C.CDLL:
     L.snn_b200_encode_poisson.argtypes = [vp, i32, i32, f32, C.c_uint64, vp, vp]
     L.snn_b200_encode_bernoulli.restype = C.c_int
     L.snn_b200_encode_bernoulli.argtypes = [vp, i32, i32, C.c_uint64, vp, vp]
+    L.snn_b200_assign_labels.restype = C.c_int
+    L.snn_b200_assign_labels.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.snn_b200_predict.restype = C.c_int
+    L.snn_b200_predict.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     if L.snn_b200_abi_version() != _abi.SNN_ABI_VERSION:
         raise BackendError("libsnn_b200.so ABI version does not match bindsnet_b200/_abi.py — rebuild")
     _lib = L
@@ -226,3 +230,23 @@ def encode_bernoulli(prob: torch.Tensor, T: int, seed: int, out: torch.Tensor) -
     with torch.cuda.device(prob.device):
         _check(lib().snn_b200_encode_bernoulli(prob.data_ptr(), prob.numel(), T, seed & (2**64 - 1), out.data_ptr(),
                                                _stream_ptr(prob.device)), "snn_b200_encode_bernoulli")
+
+
+def assign_labels(counts, labels, n_labels: int, alpha: float, rates, proportions, assignments) -> None:
+    global launches_total
+    require_cuda(counts, "spike counts")
+    launches_total += 1
+    with torch.cuda.device(counts.device):
+        _check(lib().snn_b200_assign_labels(counts.data_ptr(), labels.data_ptr(), counts.shape[0], counts.shape[1], n_labels, float(alpha),
+                                            rates.data_ptr(), proportions.data_ptr(), assignments.data_ptr(), _stream_ptr(counts.device)),
+               "snn_b200_assign_labels")
+
+
+def predict(counts, assignments, proportions, n_labels: int, predictions) -> None:
+    global launches_total
+    require_cuda(counts, "spike counts")
+    launches_total += 1
+    with torch.cuda.device(counts.device):
+        _check(lib().snn_b200_predict(counts.data_ptr(), assignments.data_ptr(), proportions.data_ptr() if proportions is not None else None,
+                                      counts.shape[0], counts.shape[1], n_labels, predictions.data_ptr(), _stream_ptr(counts.device)),
+               "snn_b200_predict")

@@ -293,6 +293,18 @@ int snn_b200_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt
 int snn_b200_encode_poisson(const float *rate_hz, int32_t n, int32_t T, float dt, uint64_t seed, uint8_t *out, void *stream);
 int snn_b200_encode_bernoulli(const float *prob, int32_t n, int32_t T, uint64_t seed, uint8_t *out, void *stream);
 
+/* Label assignment and classification from per-sample spike counts — the step after the hot path.
+ * `counts` is [n_samples, n_neurons] int32: what snn_layer_t.rec_count accumulates over a window, i.e. the reference's
+ * `spikes.sum(1)` (evaluation.py:41,115,160) without the [n_samples, time, n_neurons] raster.
+ *   snn_b200_assign_labels = bindsnet.evaluation.assign_labels (evaluation/evaluation.py:8-61): rates [n, L] updated in
+ *                            place (alpha-decayed running per-class mean counts), proportions [n, L], assignments [n] (int64)
+ *   snn_b200_predict       = all_activity (evaluation.py:99-136; proportions == NULL) / proportion_weighting (:139-180):
+ *                            predictions [n_samples] int64 */
+int snn_b200_assign_labels(const int32_t *counts, const int64_t *labels, int32_t n_samples, int32_t n_neurons, int32_t n_labels, float alpha,
+                           float *rates, float *proportions, int64_t *assignments, void *stream);
+int snn_b200_predict(const int32_t *counts, const int64_t *assignments, const float *proportions, int32_t n_samples, int32_t n_neurons,
+                     int32_t n_labels, int64_t *predictions, void *stream);
+
 /* Library/ABI identification. */
 int snn_b200_abi_version(void);
 const char *snn_b200_build_info(void);

@@ -149,3 +149,23 @@ def test_sharded_runner_on_two_nccl_ranks_matches_replica_oracle(tmp_path):
             w, th = wn, th + (dths[0] + dths[1])
     assert np.array_equal(r0["w"].numpy(), w.numpy())
     assert np.array_equal(r0["theta"].numpy(), th.numpy())
+
+
+def test_readout_kernels_match_the_torch_formulas():
+    """snn_b200_assign_labels / snn_b200_predict (csrc/snn_readout.cu) against bindsnet_b200.evaluation's CPU formulas
+    (which tests/test_evaluation.py pins against the live reference), from SpikeCounter-style int32 counts."""
+    from bindsnet_b200 import evaluation as ev
+
+    g = torch.Generator().manual_seed(8)
+    S, n, L = 128, 1600, 10
+    counts = torch.poisson(3.0 * torch.rand(S, n, generator=g), generator=g).int()
+    labels = torch.randint(0, L, (S,), generator=g)
+    a_c, p_c, r_c = ev.assign_labels(counts, labels, L)
+    a_g, p_g, r_g = ev.assign_labels(counts.cuda(), labels.cuda(), L)
+    assert torch.equal(a_g.cpu(), a_c) and torch.allclose(p_g.cpu(), p_c, atol=1e-6) and torch.allclose(r_g.cpu(), r_c, atol=1e-5)
+    a2_c, p2_c, r2_c = ev.assign_labels(counts.flip(0), labels, L, rates=r_c.clone(), alpha=0.8)
+    a2_g, p2_g, r2_g = ev.assign_labels(counts.flip(0).cuda(), labels.cuda(), L, rates=r_g.clone(), alpha=0.8)
+    assert torch.equal(a2_g.cpu(), a2_c) and torch.allclose(r2_g.cpu(), r2_c, atol=1e-5)
+    assert torch.equal(ev.all_activity(counts.cuda(), a_g, L).cpu(), ev.all_activity(counts, a_c, L))
+    pw_g, pw_c = ev.proportion_weighting(counts.cuda(), a_g, p_g, L).cpu(), ev.proportion_weighting(counts, a_c, p_c, L)
+    assert (pw_g != pw_c).sum() <= 1   # weighted float sums: a near-tie may fall the other way
