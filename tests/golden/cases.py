@@ -307,8 +307,8 @@ def conv_stride_norm(ns, inputs=None):
 # BASELINE.json config 4 at full geometry (Input[1,32,32] -conv k5 s1-> LIFNodes[16,28,28] -> Connection ->
 # LIFNodes(10), MSTDP nu=1e-2 on both, w in [-1,1] drawn like the constructors do, reward 1, Bernoulli(0.1)
 # input), batch 8 and 40 steps to keep the live reference and the fixture small
-def conv_mstdp_c4(ns, inputs=None):
-    net = ns.Network(dt=1.0, batch_size=8)
+def conv_mstdp_c4(ns, inputs=None, B=8, T=40, in_seed=143):
+    net = ns.Network(dt=1.0, batch_size=B)
     X = ns.nodes.Input(shape=[1, 32, 32], traces=True)
     H = ns.nodes.LIFNodes(shape=[16, 28, 28], traces=True)
     O = ns.nodes.LIFNodes(n=10, traces=True)
@@ -319,8 +319,14 @@ def conv_mstdp_c4(ns, inputs=None):
                                    update_rule=ns.learning.MSTDP, nu=1e-2, reduction=torch.sum, wmin=-1.0, wmax=1.0)
     net.add_connection(conv, "X", "H"); net.add_connection(dense, "H", "O")
     if inputs is None:
-        inputs = {"X": _bernoulli_inputs(40, 8, (1, 32, 32), 0.1, 143)}
-    return net, inputs, {"reward": 1.0}, 40
+        inputs = {"X": _bernoulli_inputs(T, B, (1, 32, 32), 0.1, in_seed)}
+    return net, inputs, {"reward": 1.0}, T
+
+
+# BASELINE.json config 4 at its full batch size: B=128 (T shortened to 24; the live reference, with the per-sample
+# eligibility view of SURVEY.md §0.8, runs ~1 K sample*timesteps/s)
+def conv_mstdp_c4_b128(ns, inputs=None):
+    return conv_mstdp_c4(ns, inputs, B=128, T=24, in_seed=145)
 
 
 # Network.run(one_step=True) (network.py:383-396): feed-forward mode — every layer's input is recomputed from
@@ -408,6 +414,7 @@ CASES = {
     "conv_mstdp": conv_mstdp,
     "conv_stride_norm": conv_stride_norm,
     "conv_mstdp_c4": conv_mstdp_c4,
+    "conv_mstdp_c4_b128": conv_mstdp_c4_b128,
     "one_step_ff": one_step_ff,
     "mstdp_mean_decay": mstdp_mean_decay,
     "conv_bias_stride": conv_bias_stride,
@@ -416,6 +423,6 @@ CASES = {
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)
-LARGE = {"dc2015_metric_t40", "dc2015_metric_t250", "conv_mstdp_c4"}
+LARGE = {"dc2015_metric_t40", "dc2015_metric_t250", "conv_mstdp_c4", "conv_mstdp_c4_b128"}
 #: one_spike tie-break seed used by every case
 ONE_SPIKE_SEED = 20260922

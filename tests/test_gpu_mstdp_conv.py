@@ -11,7 +11,7 @@ import helpers
 
 pytestmark = pytest.mark.gpu
 
-NEW = ["mstdp_dense", "conv_mstdp", "conv_stride_norm", "conv_mstdp_c4", "mstdp_mean_decay", "conv_bias_stride"]
+NEW = ["mstdp_dense", "conv_mstdp", "conv_stride_norm", "conv_mstdp_c4", "conv_mstdp_c4_b128", "mstdp_mean_decay", "conv_bias_stride"]
 
 
 def _rule_state(net):

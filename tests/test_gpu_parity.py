@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 
 ALL = list(cases.CASES)
 # cases whose CUDA path is exercised by test_gpu_mstdp_conv.py (generic tier only)
-NEW_ROWS = ("mstdp_dense", "conv_mstdp", "conv_stride_norm", "conv_mstdp_c4", "mstdp_mean_decay", "conv_bias_stride")
+NEW_ROWS = ("mstdp_dense", "conv_mstdp", "conv_stride_norm", "conv_mstdp_c4", "conv_mstdp_c4_b128", "mstdp_mean_decay", "conv_bias_stride")
 ALL = [c for c in ALL if c not in NEW_ROWS]
-SMALL = [c for c in ALL if c not in ("dc2015_c2", "dc2015_metric_t40")]
+SMALL = [c for c in ALL if c not in ("dc2015_c2", "dc2015_metric_t40", "dc2015_metric_t250")]
 
 
 def run_case_gpu(name, tier=1):
