@@ -185,7 +185,7 @@ struct PassK {
     float *W, *tx;
     const uint32_t *inT;
     const unsigned char *evb;
-    const uint16_t *live;
+    const uint8_t *live;
     const uint8_t *candlist;
     Misc2 *M;
     int P, B, Bp, evblk, cntb, WS;
@@ -206,6 +206,7 @@ struct PassCtx2 {
     unsigned long long *win;
     uint8_t *I_rec_s;
     int32_t *I_rec_count;
+    int I_mon;
     float I_decay, I_rest, I_dt, I_thresh, I_refrac, I_reset;
     int n, j0, TJ, aicap;
     // candidates
@@ -220,87 +221,18 @@ struct PassCtx2 {
     int liE, one_spike, stage_on, nostage;
 };
 
-// STDP pre term of one step in list form on ONE column group c4 (MCC_learning.py:234-263, learning.py:390-405),
-// run by the nthr0 threads that own the group in the shadow of the exchange: the work items are (live sample of
-// the group, event of that sample).  Several samples can spike at the same pixel: the item whose sample is the
-// LOWEST live one at that pixel owns the row (no atomics), sums the traces of all of them in ascending sample
-// order (the oracle's order) and rewrites the group's 4 weights:  w - U*dt, clamp.
-// Rows at which a sample holding a CANDIDATE of this group spiked (`dm`: those samples) are left alone: the
-// candidate's trace is undecided until the exchange lands; stdp_late2 finishes exactly those rows.
-constexpr int EVH = 16;  // list slots enumerated per live sample and round
-template <int CG, int BW>
-__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, const uint32_t *dm, int tid0, int nthr0) {
-    const PassK c_ = cx->k;
-    const int P = c_.P, WS = c_.WS, B = c_.B;
-    const Misc2 &M = *c_.M;
-    const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
-    const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
-    const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
-    const uint16_t *lv = c_.live + c4 * c_.Bp;
-    const int total = M.nlive[c4] * EVH;
-    uint32_t z[BW], d[BW];
-    {
-        const uint4 z0 = *(const uint4 *)&M.nz4[c4][0], d0 = *(const uint4 *)dm;
-        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w;
-        if (BW == 8) {
-            const uint4 z1 = *(const uint4 *)&M.nz4[c4][4], d1 = *(const uint4 *)(dm + 4);
-            z[BW - 4] = z1.x; z[BW - 3] = z1.y; z[BW - 2] = z1.z; z[BW - 1] = z1.w;
-            d[BW - 4] = d1.x; d[BW - 3] = d1.y; d[BW - 2] = d1.z; d[BW - 1] = d1.w;
-        }
-    }
-    #pragma unroll 1
-    for (int idx = tid0; idx < total; idx += nthr0) {
-        const int bb = lv[idx / EVH];
-        const int cnt = min((int)ec[bb], EV_CAP);
-        #pragma unroll 1
-        for (int k = idx % EVH; k < cnt; k += EVH) {
-            const int i = el[ev_pos(B, bb, k)];
-            uint32_t a[BW], defer = 0;
-            {
-                const uint4 q0 = cT[i * (BW / 4)];
-                a[0] = q0.x & z[0]; a[1] = q0.y & z[1]; a[2] = q0.z & z[2]; a[3] = q0.w & z[3];
-                defer = (q0.x & d[0]) | (q0.y & d[1]) | (q0.z & d[2]) | (q0.w & d[3]);
-                if (BW == 8) {
-                    const uint4 q1 = cT[i * (BW / 4) + 1];
-                    a[BW - 4] = q1.x & z[BW - 4]; a[BW - 3] = q1.y & z[BW - 3]; a[BW - 2] = q1.z & z[BW - 2]; a[BW - 1] = q1.w & z[BW - 1];
-                    defer |= (q1.x & d[BW - 4]) | (q1.y & d[BW - 3]) | (q1.z & d[BW - 2]) | (q1.w & d[BW - 1]);
-                }
-            }
-            if (defer) continue;
-            // owner of row i in this group = the lowest live sample spiking at pixel i
-            uint32_t lower = 0;
-            #pragma unroll
-            for (int g = 0; g < BW; ++g) {
-                const uint32_t below = g < (bb >> 5) ? 0xffffffffu : (g == (bb >> 5) ? ((1u << (bb & 31)) - 1u) : 0u);
-                lower |= a[g] & below;
-            }
-            if (lower) continue;
-            float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
-            #pragma unroll 1
-            for (int g = 0; g < BW; ++g) {
-                uint32_t mm = a[g];
-                while (mm) {
-                    const int b2 = g * 32 + __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const float4 t4 = *(const float4 *)(c_.tx + b2 * (4 * CG) + 4 * c4);
-                    U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
-                }
-            }
-            float *wp = c_.W + i * WS + 4 * c4;
-            const float4 w4 = *(const float4 *)wp;
-            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-            const float Uv[4] = {U0, U1, U2, U3};
-            #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float w = wv[c] - Uv[c] * c_.dts;  // x * 1.0f is exact: the classic rule's missing dt factor is dts = 1
-                if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
-                wv[c] = w;
-            }
-            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        }
-    }
-}
-
+// STDP of one step in list form on ONE column group c4 (MCC_learning.py:234-299, learning.py:390-420), run by the
+// nthr0 threads that own the group.  ONE body for its two uses (the per-step code has to stay inside the 32 KB
+// instruction cache, the rarely executed late pass included — a cold path costs an L2 round trip per 8 instructions):
+//   mode 0, early pass in the shadow of the exchange: work items = (live sample of the group, event of that sample).
+//     Several samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel owns
+//     the row (no atomics), sums the traces of all of them in ascending sample order (the oracle's order) and
+//     rewrites the group's 4 weights: w - U*dt, clamp.  Rows at which a sample holding a CANDIDATE of this group
+//     spiked (`dm`: those samples) are left alone: the candidate's trace is undecided until the exchange lands;
+//   mode 1, late pass once the winners are known: exactly those rows — work items = (candidate sample, event), the
+//     lowest candidate at a pixel owns the row: pre term (traces of all live samples at the pixel), then for a winner
+//     column (`gwin`) the post term of its single winner, then clamp.  Rows this pass does not touch get their post
+//     term from post_rows2().
 // Input trace of sample b at pixel i after step t from its age byte (Nodes.forward, nodes.py:96-103: decay every
 // step, set to trace_scale on a spike): dtab[age]; a pixel without a spike in this window still carries the
 // trace it entered the window with, decayed t + 1 times (rare: replayed).
@@ -315,20 +247,19 @@ __device__ __forceinline__ float xval(const PassCtx2 *cx, uint32_t age, int b, i
     return cx->anyx0 ? xval_nospike(cx, b, i, t) : 0.0f;
 }
 
-// Late STDP of column group c4 on the rows stdp_list2 left alone — the pixels at which a candidate-holding
-// sample (`dm`) spiked: now that the winners are known, pre term (traces of all live samples at the pixel,
-// ascending), then for a winner column (`gwin`) the post term of its single winner, then clamp
-// (MCC_learning.py:234-299, 86-110).  Work items: (candidate sample, event of that sample); when several
-// candidate samples spike at a pixel the lowest of them owns the row.
+constexpr int EVH = 16;  // list slots enumerated per sample and round in mode 0 (mode 1: EV_CAP, one round)
 template <int CG, int BW>
-__device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const uint32_t *dm, int par_, const uint8_t *xrow,
-                                        int tstep, int tid0, int nthr0) {
+__device__ __forceinline__ void stdp_list_body(const PassCtx2 *cx, int sb, int c4, int mode, uint32_t gwin, const uint32_t *dm, int par_,
+                                               const uint8_t *xrow, int tstep, int tid0, int nthr0) {
     const PassK c_ = cx->k;
     const int P = c_.P, WS = c_.WS, B = c_.B;
     const Misc2 &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
     const uint16_t *el = (const uint16_t *)(c_.evb + sb * c_.evblk + c_.cntb);
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
+    const uint8_t *lst = mode ? c_.candlist + (par_ * 8 + c4) * c_.Bp : c_.live + c4 * c_.Bp;
+    const int per = mode ? EV_CAP : EVH;
+    const int total = (mode ? M.ncs[par_][c4] : M.nlive[c4]) * per;
     uint32_t z[BW], d[BW];
     {
         const uint4 z0 = *(const uint4 *)&M.nz4[c4][0], d0 = *(const uint4 *)dm;
@@ -339,67 +270,77 @@ __device__ __noinline__ void stdp_late2(const PassCtx2 *cx, int sb, int c4, uint
             d[BW - 4] = d1.x; d[BW - 3] = d1.y; d[BW - 2] = d1.z; d[BW - 1] = d1.w;
         }
     }
-    const int ncs = M.ncs[par_][c4];
-    const uint8_t *cl = c_.candlist + (par_ * 8 + c4) * c_.Bp;
     #pragma unroll 1
-    for (int idx = tid0; idx < ncs * EV_CAP; idx += nthr0) {
-        const int bb = cl[idx / EV_CAP];
-        const int k = idx % EV_CAP;
-        if (k >= (int)ec[bb]) continue;
-        const int i = el[ev_pos(B, bb, k)];
-        uint32_t a[BW], cm[BW];
-        {
-            const uint4 q0 = cT[i * (BW / 4)];
-            a[0] = q0.x & z[0]; a[1] = q0.y & z[1]; a[2] = q0.z & z[2]; a[3] = q0.w & z[3];
-            cm[0] = q0.x & d[0]; cm[1] = q0.y & d[1]; cm[2] = q0.z & d[2]; cm[3] = q0.w & d[3];
-            if (BW == 8) {
-                const uint4 q1 = cT[i * (BW / 4) + 1];
-                a[BW - 4] = q1.x & z[BW - 4]; a[BW - 3] = q1.y & z[BW - 3]; a[BW - 2] = q1.z & z[BW - 2]; a[BW - 1] = q1.w & z[BW - 1];
-                cm[BW - 4] = q1.x & d[BW - 4]; cm[BW - 3] = q1.y & d[BW - 3]; cm[BW - 2] = q1.z & d[BW - 2]; cm[BW - 1] = q1.w & d[BW - 1];
-            }
-        }
-        uint32_t lower = 0;   // a lower candidate sample spiking here owns the row
-        #pragma unroll
-        for (int g = 0; g < BW; ++g) {
-            const uint32_t below = g < (bb >> 5) ? 0xffffffffu : (g == (bb >> 5) ? ((1u << (bb & 31)) - 1u) : 0u);
-            lower |= cm[g] & below;
-        }
-        if (lower) continue;
-        float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
-        uint32_t anya = 0;
+    for (int idx = tid0; idx < total; idx += nthr0) {
+        const int bb = lst[idx / per];
+        const int cnt = min((int)ec[bb], EV_CAP);
         #pragma unroll 1
-        for (int g = 0; g < BW; ++g) {
-            uint32_t mm = a[g];
-            anya |= mm;
-            while (mm) {
-                const int b2 = g * 32 + __ffs(mm) - 1;
-                mm &= mm - 1;
-                const float4 t4 = *(const float4 *)(c_.tx + b2 * (4 * CG) + 4 * c4);
-                U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
+        for (int k = idx % per; k < cnt; k += per) {
+            const int i = el[ev_pos(B, bb, k)];
+            uint32_t a[BW], cm[BW], anyc = 0;
+            {
+                const uint4 q0 = cT[i * (BW / 4)];
+                a[0] = q0.x & z[0]; a[1] = q0.y & z[1]; a[2] = q0.z & z[2]; a[3] = q0.w & z[3];
+                cm[0] = q0.x & d[0]; cm[1] = q0.y & d[1]; cm[2] = q0.z & d[2]; cm[3] = q0.w & d[3];
+                if (BW == 8) {
+                    const uint4 q1 = cT[i * (BW / 4) + 1];
+                    a[BW - 4] = q1.x & z[BW - 4]; a[BW - 3] = q1.y & z[BW - 3]; a[BW - 2] = q1.z & z[BW - 2]; a[BW - 1] = q1.w & z[BW - 1];
+                    cm[BW - 4] = q1.x & d[BW - 4]; cm[BW - 3] = q1.y & d[BW - 3]; cm[BW - 2] = q1.z & d[BW - 2]; cm[BW - 1] = q1.w & d[BW - 1];
+                }
+                #pragma unroll
+                for (int g = 0; g < BW; ++g) anyc |= cm[g];
             }
-        }
-        if (!c_.pre_on) anya = 0;
-        if (!(anya | gwin)) continue;
-        float *wp = c_.W + i * WS + 4 * c4;
-        const float4 w4 = *(const float4 *)wp;
-        float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        const float Uv[4] = {U0, U1, U2, U3};
-        #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float w = wv[c];
-            if (anya) w = w - Uv[c] * c_.dts;
-            if ((gwin >> c) & 1u) {  // the column's single winner (fast late pass): post term
-                uint32_t e = M.wl[c4][0];
-                #pragma unroll 1
-                for (int k2 = 1; k2 < M.nwl[c4]; ++k2) if ((M.wl[c4][k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[c4][k2];
-                const float V = 0.0f + xval(cx, xrow[(e & 0xffu) * P + i], (int)((e >> 8) & 0xffu), i, tstep) * c_.nu1;
-                w = w + V * c_.dts;
+            if (!mode && anyc) continue;   // early pass: the row waits for the winners
+            // owner of row i = the lowest live (early) / candidate-holding (late) sample spiking at pixel i
+            uint32_t lower = 0;
+            #pragma unroll
+            for (int g = 0; g < BW; ++g) {
+                const uint32_t below = g < (bb >> 5) ? 0xffffffffu : (g == (bb >> 5) ? ((1u << (bb & 31)) - 1u) : 0u);
+                lower |= (mode ? cm[g] : a[g]) & below;
             }
-            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
-            wv[c] = w;
+            if (lower) continue;
+            float U0 = 0.f, U1 = 0.f, U2 = 0.f, U3 = 0.f;
+            uint32_t anya = 0;
+            #pragma unroll 1
+            for (int g = 0; g < BW; ++g) {
+                uint32_t mm = a[g];
+                anya |= mm;
+                while (mm) {
+                    const int b2 = g * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 t4 = *(const float4 *)(c_.tx + b2 * (4 * CG) + 4 * c4);
+                    U0 = U0 + t4.x; U1 = U1 + t4.y; U2 = U2 + t4.z; U3 = U3 + t4.w;
+                }
+            }
+            if (!c_.pre_on) anya = 0;
+            if (!(anya | gwin)) continue;
+            float *wp = c_.W + i * WS + 4 * c4;
+            const float4 w4 = *(const float4 *)wp;
+            float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float Uv[4] = {U0, U1, U2, U3};
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float w = wv[c];
+                if (anya) w = w - Uv[c] * c_.dts;  // x * 1.0f is exact: the classic rule's missing dt factor is dts = 1
+                if ((gwin >> c) & 1u) {  // the column's single winner (fast late pass): post term
+                    uint32_t e = M.wl[c4][0];
+                    #pragma unroll 1
+                    for (int k2 = 1; k2 < M.nwl[c4]; ++k2) if ((M.wl[c4][k2] >> 16) == (uint32_t)(4 * c4 + c)) e = M.wl[c4][k2];
+                    const float V = 0.0f + xval(cx, xrow[(e & 0xffu) * P + i], (int)((e >> 8) & 0xffu), i, tstep) * c_.nu1;
+                    w = w + V * c_.dts;
+                }
+                if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+                wv[c] = w;
+            }
+            *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
         }
-        *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
     }
+}
+
+template <int CG, int BW>
+__device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, int mode, uint32_t gwin, const uint32_t *dm, int par_,
+                                        const uint8_t *xrow, int tstep, int tid0, int nthr0) {
+    stdp_list_body<CG, BW>(cx, sb, c4, mode, gwin, dm, par_, xrow, tstep, tid0, nthr0);
 }
 
 // Post term of the fast late pass of column group c4 for the rows stdp_list2 did not touch: per winner
@@ -550,7 +491,7 @@ __device__ __forceinline__ float refrac_replay(float rc, float dt, int T) {
 // list block `blk` (slot `slot`): p[c] = sum_{i in sX[b]} W[i][c], i ascending (topology.py:437-479).  One copy
 // for the step itself and for the gather that runs ahead in the shadow of the exchange.
 template <int WS>
-__device__ __noinline__ float4 gather2(const PassCtx2 *cx, const unsigned char *blk, int slot, int b, const float *Wc) {
+__device__ __forceinline__ float4 gather2(const PassCtx2 *cx, const unsigned char *blk, int slot, int b, const float *Wc) {
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
     const int cnt = ((const uint16_t *)blk)[b];
     const int B = cx->k.B;
@@ -572,9 +513,15 @@ __device__ __noinline__ float4 gather2(const PassCtx2 *cx, const unsigned char *
     return make_float4(p0, p1, p2, p3);
 }
 
+// Ai spike monitors (monitors.py:94-111; the launch code cleared the raster): rarely compiled-in work, out of line.
+__device__ __noinline__ void ai_monitor2(const PassCtx2 *cx, int sb_, int col, int t) {
+    if (cx->I_rec_s) cx->I_rec_s[((size_t)t * cx->k.B + sb_) * cx->n + cx->j0 + col] = 1;
+    if (cx->I_rec_count) atomicAdd(cx->I_rec_count + (size_t)sb_ * cx->n + cx->j0 + col, 1);
+}
+
 // One LIFNodes.forward step (nodes.py:500-529) of Ai list entry e with input xin at step t; a spike goes to the
-// exchange (Ai spike count of the sample), to the tile's own-spike bits and to the monitors.
-__device__ __noinline__ void ai_step2(const PassCtx2 *cx, int e, float xin, int t) {
+// exchange (`sis`: the step's Ai spike counts per sample), to the tile's own-spike bits (`spk`) and to the monitors.
+__device__ __forceinline__ void ai_step_body(const PassCtx2 *cx, int e, float xin, int t, unsigned int *sis, uint32_t *spk) {
     float v = cx->ai_v[e], rc = cx->ai_rc[e];
     uint32_t fl = cx->ai_fl[e];
     v = cx->I_decay * (v - cx->I_rest) + cx->I_rest;
@@ -584,12 +531,15 @@ __device__ __noinline__ void ai_step2(const PassCtx2 *cx, int e, float xin, int 
     if (v >= cx->I_thresh) {
         rc = cx->I_refrac; v = cx->I_reset; fl = 2u;
         const int id = cx->ai_id[e], sb_ = id >> 8, col = id & 0xff;
-        atomicOr(&cx->aispk[(t & 1) * cx->k.Bp + sb_], 1u << col);
-        atomicAdd(cx->sisum + (t % 3) * cx->k.B + sb_, 1u);
-        if (cx->I_rec_s) cx->I_rec_s[((size_t)t * cx->k.B + sb_) * cx->n + cx->j0 + col] = 1;
-        if (cx->I_rec_count) atomicAdd(cx->I_rec_count + (size_t)sb_ * cx->n + cx->j0 + col, 1);
+        atomicOr(spk + sb_, 1u << col);
+        atomicAdd(sis + sb_, 1u);
+        if (cx->I_mon) ai_monitor2(cx, sb_, col, t);
     }
     cx->ai_v[e] = v; cx->ai_rc[e] = rc; cx->ai_fl[e] = (uint8_t)fl;
+}
+
+__device__ __noinline__ void ai_step2(const PassCtx2 *cx, int e, float xin, int t, unsigned int *sis, uint32_t *spk) {
+    ai_step_body(cx, e, xin, t, sis, spk);
 }
 
 // A thread found threshold crossers among its 4 neurons at step t (`cand`, nodes.py:1088-1092): count them for
@@ -660,7 +610,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     float *theta_s = (float *)(smem + Q.o_theta);   // [32] theta, [32] thresh + decayed theta
     float *thr_s = theta_s + 32;
     float *dtab = theta_s + 64;                  // [256] input trace by age: trace_scale * decay^age, multiplied up step by step
-    uint16_t *live = (uint16_t *)(smem + Q.o_live);  // [CG][Bp] live samples per column group
+    uint8_t *live = smem + Q.o_live;             // [CG][Bp] live samples per column group
     unsigned long long *keyT = (unsigned long long *)(smem + Q.o_tab);  // [2][Bp] one_spike arg-max key of a step, by step parity
     uint32_t *isumT = (uint32_t *)(keyT + 2 * Bp);                      // [2][Bp] Ai spikes of a step
     uint32_t *aispk = isumT + 2 * Bp;                                   // [2][Bp] bit col: Ai (b, col) of this tile spiked in that step
@@ -761,7 +711,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         s_cx.k.dts = dts; s_cx.k.wmin = C.wmin; s_cx.k.wmax = C.wmax; s_cx.k.nu1 = C.nu1;
         s_cx.inS = Q.inS; s_cx.SW = Q.SW;
         s_cx.ai_v = ai_v; s_cx.ai_rc = ai_rc; s_cx.ai_id = ai_id; s_cx.ai_claim = ai_claim; s_cx.ai_map = ai_map; s_cx.ai_fl = ai_fl;
-        s_cx.aispk = aispk; s_cx.sisum = Q.sisum; s_cx.win = Q.win; s_cx.I_rec_s = I.rec_s; s_cx.I_rec_count = I.rec_count;
+        s_cx.aispk = aispk; s_cx.sisum = Q.sisum; s_cx.win = Q.win; s_cx.I_rec_s = I.rec_s; s_cx.I_rec_count = I.rec_count; s_cx.I_mon = (I.rec_s || I.rec_count) ? 1 : 0;
         s_cx.I_decay = I.decay; s_cx.I_rest = I.rest; s_cx.I_dt = I.dt; s_cx.I_thresh = I.thresh; s_cx.I_refrac = I.refrac; s_cx.I_reset = I.reset;
         s_cx.n = n; s_cx.j0 = j0; s_cx.TJ = TJ; s_cx.aicap = aicap;
         s_cx.candstamp = candstamp; s_cx.candslot = candslot; s_cx.xrow_w = xrow; s_cx.xage = Q.xage;
@@ -827,7 +777,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     if (act && stdp && (xE[0] != 0.0f || xE[1] != 0.0f || xE[2] != 0.0f || xE[3] != 0.0f)) {
         livep = true;
         atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
-        live[cg * Bp + atomicAdd(&M.nlive[cg], 1)] = (uint16_t)b;
+        live[cg * Bp + atomicAdd(&M.nlive[cg], 1)] = (uint8_t)b;
     }
     const uint32_t bytesE = (uint32_t)Q.SB, bytesT = (uint32_t)(sizeof(uint32_t) * (size_t)P * BW);
     const int tid_pf = NC + 1;  // the thread that issues the slot prefetches (exchange warp)
@@ -852,6 +802,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         const int buf = t & 1;                       // slot t = spikes of step t-1
         const unsigned char *cE = evb + buf * evblk;
         const int par = t & 1, ppar = par ^ 1;       // parity of step t / of step t-1
+        unsigned int *const sis_t = Q.sisum + (t % 3) * B;   // this step's Ai spike counts (exchange slot t % 3)
         const int dense_nb = __ldg(Q.dense + (t + 1 <= T ? t + 1 : T));   // slot t+1 holds an overflowed event list (used in the shadow)
 
         // ---- exchange of step t-1 lands: the exchange warp waits for the grid barrier and copies the
@@ -916,7 +867,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                         if (!livep) {
                             livep = true;
                             atomicOr(&M.nz4[cg][b >> 5], 1u << (b & 31));
-                            live[cg * Bp + atomicAdd(&M.nlive[cg], 1)] = (uint16_t)b;
+                            live[cg * Bp + atomicAdd(&M.nlive[cg], 1)] = (uint8_t)b;
                         }
                     }
                 }
@@ -934,7 +885,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                         }
                         // the partner Ai neuron of every candidate runs here (claimed at step t-1): input `exc`
                         // through the diagonal Ae->Ai iff the candidate won (network.py:225-248)
-                        if (t < T) ai_step2(&s_cx, (int)ai_map[b * TJ + col], won ? (0.0f + Q.exc) : 0.0f, t);
+                        if (t < T) ai_step2(&s_cx, (int)ai_map[b * TJ + col], won ? (0.0f + Q.exc) : 0.0f, t, sis_t, aispk + par * Bp);
                         if (won) {   // monitors (monitors.py:94-111): the launch code cleared the raster
                             if (E.rec_s) E.rec_s[((size_t)(t - 1) * B + b) * n + jc + c] = 1;
                             if (E.rec_count) atomicAdd(E.rec_count + (size_t)b * n + jc + c, 1);
@@ -964,7 +915,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 // spiked (unless the slot is dense: then nothing of this group was done yet)
                 const uint32_t *dm = &M.candmask[ppar][cg][0];
                 if (fast) {
-                    if (pre_on || gwin) stdp_late2<CG, BW>(&s_cx, sb_, cg, gwin, dm, ppar, xr, t - 1, b, Bp);
+                    if (pre_on || gwin) stdp_list2<CG, BW>(&s_cx, sb_, cg, 1, gwin, dm, ppar, xr, t - 1, b, Bp);
                     if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, dm, xr, t - 1, M.negzero ? 0 : 1, b, Bp);
                 } else {
                     stdp_rows2<CG, BW>(&s_cx, sb_, cg, gwin, M.candb[ppar], min(M.ncand[ppar], XR),
@@ -1041,7 +992,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             #pragma unroll 1
             for (int k = tid; k < nact; k += NC) {
                 if (ai_claim[par * aicap + k] == (uint16_t)t) continue;
-                ai_step2(&s_cx, k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t);
+                ai_step_body(&s_cx, k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t, sis_t, aispk + par * Bp);
             }
         }
         PROF(6)  // gather + neurons
@@ -1100,7 +1051,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             if (b < BW) M.candmask[ppar][cg][b] = 0;   // step t-1's: consumed by the late pass above
             if (b == 0) M.ncs[ppar][cg] = 0;
             if (update_on && pre_on && !(PROFV && (Q.dbg & 2))) {
-                if (!dense_nb) stdp_list2<CG, BW>(&s_cx, nb, cg, &M.candmask[par][cg][0], b, Bp);
+                if (!dense_nb) stdp_list_body<CG, BW>(&s_cx, nb, cg, 0, 0u, &M.candmask[par][cg][0], par, xrow, t, b, Bp);
                 else if (earlyg) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, t, nullptr, b, Bp);
                 if (earlyg) bar_group(gbar, Bp);
             }
@@ -1637,6 +1588,25 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
             }
             fprintf(stderr, "  slowest group per step: winners+late STDP %.0f, gather %.0f, neurons %.0f, Ai list %.0f cycles; it was a late group in %.0f%% of the steps\n",
                     ph[0], ph[1], ph[2], ph[3], 100 * late_share);
+            // does a late path cost more the longer its CTA has not run one (instruction-cache eviction)?
+            double dur[4] = {0, 0, 0, 0}; int cntg[4] = {0, 0, 0, 0};
+            for (int g = 0; g < m.grid; ++g) {
+                int last = -1;
+                for (int st = 0; st < 32; ++st) {
+                    bool any = false; double worst = 0;
+                    for (int c = 0; c < m.CG; ++c) {
+                        const long long *r = gt + ((st * 160 + g) * 8 + c) * 5;
+                        if (r[4] & 1) { any = true; worst = (double)r[0] > worst ? (double)r[0] : worst; }
+                    }
+                    if (any) {
+                        if (last >= 0) { const int gap = st - last; const int bk = gap <= 2 ? 0 : gap <= 5 ? 1 : gap <= 10 ? 2 : 3; dur[bk] += worst; ++cntg[bk]; }
+                        last = st;
+                    }
+                }
+            }
+            fprintf(stderr, "  late-path cycles by steps since the CTA's previous late path: <=2: %.0f (%d)  3-5: %.0f (%d)  6-10: %.0f (%d)  >10: %.0f (%d)\n",
+                    cntg[0] ? dur[0] / cntg[0] : 0.0, cntg[0], cntg[1] ? dur[1] / cntg[1] : 0.0, cntg[1], cntg[2] ? dur[2] / cntg[2] : 0.0, cntg[2],
+                    cntg[3] ? dur[3] / cntg[3] : 0.0, cntg[3]);
         }
     }
     if (launches) *launches = nl;  // 2 structure checks + two pre-passes + the persistent window kernel
