@@ -30,18 +30,30 @@ WORKLOAD = (f"DiehlAndCook2015 n_neurons={N_NEURONS} batch={BATCH}/GPU {T_STEPS}
             "(MCC PostPre STDP, one_spike, theta), synthetic Poisson 28x28 (~1.2% density)")
 
 
-def algorithmic_bytes_per_timestep(n=N_NEURONS, B=BATCH, P=N_INPT, monitors=False) -> int:
+def apply_config(name: str) -> None:
+    """--config c3: BASELINE.json configs[2] (n_neurons=6400, batch 256) instead of the metric configuration."""
+    global N_NEURONS, BATCH, METRIC, WORKLOAD
+    if name == "c3":
+        N_NEURONS, BATCH = 6400, 256
+        METRIC = "sample·timesteps/s DiehlAndCook2015 n=6400 b=256 (BASELINE.json configs[2])"
+    WORKLOAD = (f"DiehlAndCook2015 n_neurons={N_NEURONS} batch={BATCH}/GPU {T_STEPS} timesteps/window, learning on "
+                "(MCC PostPre STDP, one_spike, theta), synthetic Poisson 28x28 (~1.2% density)")
+
+
+def algorithmic_bytes_per_timestep(n=None, B=None, P=N_INPT, monitors=False) -> int:
     """read + write of the learned X->Ae weights (STDP + clamp must be visible
     to the next step) + the step's input spikes as delivered (uint8) [+ Ae/Ai rasters]."""
+    n, B = n or N_NEURONS, B or BATCH
     return 2 * P * n * 4 + B * P + (2 * B * n if monitors else 0)
 
 
-def synth_windows(count: int, seed: int, T=T_STEPS, B=BATCH):
+def synth_windows(count: int, seed: int, T=T_STEPS, B=None):
     """SURVEY.md §8d synthetic input: per-pixel rate 128*U(0,1)*Bernoulli(0.19) Hz on 1x28x28,
     Poisson-encoded (bindsnet_b200.encoding.poisson, restating encodings.py:99-156)."""
     import torch
     from bindsnet_b200.encoding import poisson
 
+    B = B or BATCH
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(count):
@@ -273,12 +285,15 @@ def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=320, help="timed windows (default: 320 windows = a timed region of >= 0.5 s at the metric configuration)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tier", type=int, default=0, help="0 auto, 1 generic kernel, 2 fused DC2015 kernel v1 (grid barrier), 3 fused DC2015 kernel v2 (message exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
+                    help="BASELINE.json configs[1] (the metric configuration: n=1600, B=128; default) or configs[2] (n=6400, B=256)")
     args = ap.parse_args()
+    apply_config(args.config)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -342,6 +357,20 @@ def main():
     _backend.kernel_events = None
     net.check_errors()
     value = world * BATCH * T_STEPS * K / (ms_total * 1e-3)
+
+    # ---- the FIRST window of a fresh network (W0 as initialised, theta = 0: every neuron still fires easily, so the
+    # winner / late-STDP paths are busier than in the steady state the loop above measures) ----------------
+    first_ms = None
+    if world == 1:
+        net0 = make_network(dev)
+        net0.force_tier = args.tier
+        _backend.kernel_events = []
+        net0.run({"X": resident[0]}, time=T_STEPS)
+        torch.cuda.synchronize()
+        first_ms = sum(a.elapsed_time(b) for a, b in _backend.kernel_events)
+        _backend.kernel_events = None
+        net0.check_errors()
+        del net0
 
     # ---- the same loop with Ae + Ai spike monitors on (report both) -------------------
     K2 = max(1, min(K, 5))
@@ -462,13 +491,14 @@ def main():
         achieved = per_launch_bytes / (kavg_ms * 1e-3) / 1e9 if kavg_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.config == "c2":
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         from bindsnet_b200 import _abi
-        tier = {0: "auto", 1: "generic", 2: "fused_dc2015_v1", 3: "fused_dc2015_v2"}[args.tier]
+        names = {1: "generic", 2: "fused_dc2015_v1", 3: "fused_dc2015_v2"}
+        tier = names[args.tier] if args.tier else f"auto -> {names.get(_backend.last_tier, _backend.last_tier)}"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -477,8 +507,8 @@ def main():
                 "workload": WORKLOAD,
                 "global_batch": world * BATCH, "timesteps": T_STEPS,
                 "parallelism": f"dp{world}: batch shards, one NCCL all-reduce of dW+dtheta per window" if world > 1 else "single GPU",
-                "l2": f"inputs cycle through {POOL} distinct windows ({POOL * 25} MB > 126 MB L2); the 5 MB weight matrix is resident by design",
-                "kernel_tier": tier, "state_reset_between_windows": True,
+                "l2": f"inputs cycle through {POOL} distinct windows ({POOL * T_STEPS * BATCH * N_INPT // 1000000} MB > 126 MB L2); the {N_INPT * N_NEURONS * 4 // 1000000} MB weight matrix is resident by design",
+                "kernel_tier": tier, "state_reset_between_windows": True, "baseline_config": args.config,
             },
             "value_with_spike_monitors": value_monitors,  # Ae + Ai [T, B, n] rasters written by the kernel every window
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T_STEPS * BATCH * N_INPT,
@@ -492,7 +522,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": kavg_ms,
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": kavg_ms, "first_window_kernel_ms": first_ms,
                          "algorithmic_bytes_per_launch": per_launch_bytes},
         }
         if world == 1 and not args.no_cpu_baseline:

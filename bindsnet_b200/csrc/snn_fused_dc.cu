@@ -160,6 +160,16 @@ struct PassCtx {
     float Bf, dts, weight_decay, wmin, wmax, nu0, nu1;
 };
 
+// The context lives in shared memory and its pointers point into shared memory; loaded back from there they are
+// generic pointers to the compiler (LD/ST through the generic path, 64-bit address arithmetic).  These hints
+// restore the address space: LDS/STS with 32-bit addresses.
+template <class T> __device__ __forceinline__ T *sh(T *p) { __builtin_assume(__isShared((const void *)p)); return p; }
+__device__ __forceinline__ PassCtx load_ctx(const PassCtx *cx) {
+    PassCtx c = *sh(cx);
+    c.W = sh(c.W); c.tx = sh(c.tx); c.xrow = sh(c.xrow); c.inT = sh(c.inT); c.evb = sh(c.evb); c.live = sh(c.live); c.M = sh(c.M);
+    return c;
+}
+
 // STDP of one step on the column groups selected by `groups` (bit per group), thread = input row i
 // (MCC_learning.py:234-299, 86-110; learning.py:641-651 for the weight-dependent pre term).
 //   pre term: for every selected group whose live samples (non-zero Ae trace, Misc::nz4) spiked at
@@ -174,7 +184,7 @@ __device__ __noinline__ void stdp_rows(const PassCtx *cx, int sb, uint32_t group
     constexpr int WS = TJ + 4;
     // the context lives in shared memory: read it ONCE into registers (the stores to W below would
     // otherwise force every field to be reloaded per row)
-    const PassCtx c_ = *cx;
+    const PassCtx c_ = load_ctx(cx);
     const int P = c_.P;
     const Misc &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
@@ -273,7 +283,7 @@ constexpr int EVH = 16;  // list slots enumerated per pair and round
 template <int TJ, int BW>
 __device__ __noinline__ void stdp_list(const PassCtx *cx, int sb, uint32_t groups, uint32_t colwin, int tid0, int nthr0) {
     constexpr int CG = TJ / 4, WS = TJ + 4;
-    const PassCtx c_ = *cx;
+    const PassCtx c_ = load_ctx(cx);
     const int P = c_.P;
     const Misc &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
@@ -355,7 +365,7 @@ template <int TJ, int BW>
 __device__ __noinline__ void late_generic_fn(const PassCtx *cx, const snn_conn_t *Cp, int sb, int ppar, uint32_t lategrp, uint32_t colwin,
                                              int full, const float *xsrc) {
     constexpr int WS = TJ + 4;
-    const PassCtx c_ = *cx;
+    const PassCtx c_ = load_ctx(cx);
     const snn_conn_t &C = *Cp;
     const Misc &M = *c_.M;
     const int P = c_.P, tid = threadIdx.x, nthr = blockDim.x;
@@ -459,6 +469,7 @@ __device__ __noinline__ void late_generic_fn(const PassCtx *cx, const snn_conn_t
 // Spike-gather of a sample whose event list overflowed EV_CAP: walk its bit row in global memory
 // (rare; out of line to keep the hot loop small).
 __device__ __noinline__ float4 gather_dense(const uint32_t *row, int SW, const float *Wc, int WS) {
+    Wc = sh(Wc);
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
     for (int w = 0; w < SW; ++w) {
         uint32_t word = __ldg(row + w);

@@ -49,6 +49,16 @@ namespace {
 constexpr int XR = 8;        // input-trace rows staged per CTA and step (samples with a candidate)
 constexpr int EV_CAP = 32;   // staged events per sample and step; longer lists take the slow path
 constexpr int NPROF = 16;
+// build-time experiment switches (scripts/build_variant.sh)
+#ifndef V2_UNIFY_AI
+#define V2_UNIFY_AI 0     // the Ai list step calls the out-of-line copy the winners' path uses
+#endif
+#ifndef V2_UNIFY_LIST
+#define V2_UNIFY_LIST 0   // the early STDP list pass calls the out-of-line copy the late pass uses
+#endif
+#ifndef V2_POLL_NS
+#define V2_POLL_NS 0      // back-off between two polls of the grid barrier word
+#endif
 constexpr unsigned AI_NONE = 0xFFFFu;
 
 struct F2Params {
@@ -141,6 +151,7 @@ struct Misc2 {  // small per-step scratch (shared memory)
     int negzero;            // the weight tile held a -0.0 when it was loaded (post_rows2 must not skip rows)
     int denseflag[2];       // staged slot (by buffer) holds a sample whose event list overflowed EV_CAP
     long long pc[NPROF];    // phase timers (profiling variant only)
+    long long rs[8][16];    // ... fine stamps inside the late path, per column group
 };
 static_assert(offsetof(Misc2, wl) % 16 == 0 && offsetof(Misc2, nz4) % 16 == 0 && offsetof(Misc2, wmask) % 16 == 0 &&
               offsetof(Misc2, candmask) % 16 == 0, "Misc2: 16-byte rows");
@@ -221,6 +232,16 @@ struct PassCtx2 {
     int liE, one_spike, stage_on, nostage;
 };
 
+// The context lives in shared memory and most of its pointers point into shared memory; loaded back from there
+// they are generic pointers to the compiler (LD/ST through the generic path, 64-bit address arithmetic).  These
+// hints restore the address space: LDS/STS with 32-bit addresses.
+template <class T> __device__ __forceinline__ T *sh(T *p) { __builtin_assume(__isShared((const void *)p)); return p; }
+__device__ __forceinline__ PassK load_k(const PassCtx2 *cx) {
+    PassK k = sh(cx)->k;
+    k.W = sh(k.W); k.tx = sh(k.tx); k.inT = sh(k.inT); k.evb = sh(k.evb); k.live = sh(k.live); k.candlist = sh(k.candlist); k.M = sh(k.M);
+    return k;
+}
+
 // STDP of one step in list form on ONE column group c4 (MCC_learning.py:234-299, learning.py:390-420), run by the
 // nthr0 threads that own the group.  ONE body for its two uses (the per-step code has to stay inside the 32 KB
 // instruction cache, the rarely executed late pass included — a cold path costs an L2 round trip per 8 instructions):
@@ -237,21 +258,23 @@ struct PassCtx2 {
 // step, set to trace_scale on a spike): dtab[age]; a pixel without a spike in this window still carries the
 // trace it entered the window with, decayed t + 1 times (rare: replayed).
 __device__ __noinline__ float xval_nospike(const PassCtx2 *cx, int b, int i, int t) {
+    cx = sh(cx);
     float x = cx->x0c[(size_t)b * cx->k.P + i];
     #pragma unroll 1
     for (int k = 0; k <= t; ++k) x = x * cx->x_decay;
     return x;
 }
 __device__ __forceinline__ float xval(const PassCtx2 *cx, uint32_t age, int b, int i, int t) {
-    if (age != 255u) return cx->dtab[age];
-    return cx->anyx0 ? xval_nospike(cx, b, i, t) : 0.0f;
+    if (age != 255u) return sh(sh(cx)->dtab)[age];
+    return sh(cx)->anyx0 ? xval_nospike(cx, b, i, t) : 0.0f;
 }
 
 constexpr int EVH = 16;  // list slots enumerated per sample and round in mode 0 (mode 1: EV_CAP, one round)
 template <int CG, int BW>
 __device__ __forceinline__ void stdp_list_body(const PassCtx2 *cx, int sb, int c4, int mode, uint32_t gwin, const uint32_t *dm, int par_,
                                                const uint8_t *xrow, int tstep, int tid0, int nthr0) {
-    const PassK c_ = cx->k;
+    const PassK c_ = load_k(cx);
+    dm = sh(dm); xrow = sh(xrow);
     const int P = c_.P, WS = c_.WS, B = c_.B;
     const Misc2 &M = *c_.M;
     const uint16_t *ec = (const uint16_t *)(c_.evb + sb * c_.evblk);
@@ -351,7 +374,8 @@ __device__ __noinline__ void stdp_list2(const PassCtx2 *cx, int sb, int c4, int 
 template <int CG, int BW>
 __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int nwl, const uint32_t *dm, const uint8_t *xrow, int tstep, int skip0,
                                         int tid0, int nthr0) {
-    const PassK c_ = cx->k;
+    const PassK c_ = load_k(cx);
+    dm = sh(dm); xrow = sh(xrow);
     const int P = c_.P, WS = c_.WS;
     const Misc2 &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
@@ -367,21 +391,32 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int 
         const uint8_t *xr = xrow + (e & 0xffu) * P;
         const int wb = (int)((e >> 8) & 0xffu);
         float *wcol = c_.W + (e >> 16);
-        #pragma unroll 2
-        for (int i = tid0; i < P; i += nthr0) {
-            const float xv = xval(cx, xr[i], wb, i, tstep);
-            if (skip0 && xv == 0.0f) continue;
-            {
+        // four rows per thread and round with every load issued before the first use: the pass is a chain of
+        // dependent shared-memory loads otherwise (it sits on the critical path of the step)
+        #pragma unroll 1
+        for (int i0 = tid0; i0 < P; i0 += 4 * nthr0) {
+            uint32_t age[4], any[4];
+            float w[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + u * nthr0, P - 1);
+                age[u] = xr[i];
                 const uint4 q0 = cT[i * (BW / 4)];
-                uint32_t any = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
-                if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
-                if (any) continue;  // done by stdp_late2
+                any[u] = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
+                if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any[u] |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
+                w[u] = wcol[i * WS];
             }
-            float w = wcol[i * WS];
-            const float V = 0.0f + xv * c_.nu1;
-            w = w + V * c_.dts;
-            if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
-            wcol[i * WS] = w;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr0;
+                if (i >= P || any[u]) continue;   // rows with a candidate-holding sample's spike: done by the list pass
+                const float xv = xval(cx, age[u], wb, i, tstep);
+                if (skip0 && xv == 0.0f) continue;
+                const float V = 0.0f + xv * c_.nu1;
+                float wn = w[u] + V * c_.dts;
+                if (c_.has_clamp) wn = clampf(wn, c_.wmin, c_.wmax);
+                wcol[i * WS] = wn;
+            }
         }
     }
 }
@@ -394,7 +429,9 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int 
 template <int CG, int BW>
 __device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint32_t gwin, const int *cand, int ns, const uint8_t *xsrc,
                                         const uint8_t *xrow, int tstep, const uint32_t *dm, int tid0, int nthr0) {
-    const PassK c_ = cx->k;
+    const PassK c_ = load_k(cx);
+    if (dm) dm = sh(dm);
+    xrow = sh(xrow); cand = sh(cand);
     const int P = c_.P, WS = c_.WS, TJ = 4 * CG;
     const Misc2 &M = *c_.M;
     const uint4 *cT = (const uint4 *)(c_.inT + sb * P * BW);
@@ -465,6 +502,7 @@ __device__ __noinline__ void stdp_rows2(const PassCtx2 *cx, int sb, int c4, uint
 // Spike-gather of a sample whose event list overflowed EV_CAP: walk its bit row in global memory
 // (rare; out of line to keep the hot loop small).
 __device__ __noinline__ float4 gather_dense2(const uint32_t *row, int SW, const float *Wc, int WS) {
+    Wc = sh(Wc);
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
     for (int w = 0; w < SW; ++w) {
         uint32_t word = __ldg(row + w);
@@ -493,6 +531,7 @@ __device__ __forceinline__ float refrac_replay(float rc, float dt, int T) {
 template <int WS>
 __device__ __forceinline__ float4 gather2(const PassCtx2 *cx, const unsigned char *blk, int slot, int b, const float *Wc) {
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    cx = sh(cx); blk = sh(blk); Wc = sh(Wc);
     const int cnt = ((const uint16_t *)blk)[b];
     const int B = cx->k.B;
     if (cnt > EV_CAP)   // dense sample: walk the bit row in global memory (rare, slow path)
@@ -522,20 +561,23 @@ __device__ __noinline__ void ai_monitor2(const PassCtx2 *cx, int sb_, int col, i
 // One LIFNodes.forward step (nodes.py:500-529) of Ai list entry e with input xin at step t; a spike goes to the
 // exchange (`sis`: the step's Ai spike counts per sample), to the tile's own-spike bits (`spk`) and to the monitors.
 __device__ __forceinline__ void ai_step_body(const PassCtx2 *cx, int e, float xin, int t, unsigned int *sis, uint32_t *spk) {
-    float v = cx->ai_v[e], rc = cx->ai_rc[e];
-    uint32_t fl = cx->ai_fl[e];
+    cx = sh(cx); spk = sh(spk);
+    float *const ai_v = sh(cx->ai_v), *const ai_rc = sh(cx->ai_rc);
+    uint8_t *const ai_fl = sh(cx->ai_fl);
+    float v = ai_v[e], rc = ai_rc[e];
+    uint32_t fl = ai_fl[e];
     v = cx->I_decay * (v - cx->I_rest) + cx->I_rest;
     if (!(fl & 1u)) { if (rc > 0.0f) xin = 0.0f; rc = rc - cx->I_dt; }   // undisturbed counter: <= 0 by construction
     v = v + xin;
     fl &= 1u;
     if (v >= cx->I_thresh) {
         rc = cx->I_refrac; v = cx->I_reset; fl = 2u;
-        const int id = cx->ai_id[e], sb_ = id >> 8, col = id & 0xff;
+        const int id = sh(cx->ai_id)[e], sb_ = id >> 8, col = id & 0xff;
         atomicOr(spk + sb_, 1u << col);
         atomicAdd(sis + sb_, 1u);
         if (cx->I_mon) ai_monitor2(cx, sb_, col, t);
     }
-    cx->ai_v[e] = v; cx->ai_rc[e] = rc; cx->ai_fl[e] = (uint8_t)fl;
+    ai_v[e] = v; ai_rc[e] = rc; ai_fl[e] = (uint8_t)fl;
 }
 
 __device__ __noinline__ void ai_step2(const PassCtx2 *cx, int e, float xin, int t, unsigned int *sis, uint32_t *spk) {
@@ -547,7 +589,9 @@ __device__ __noinline__ void ai_step2(const PassCtx2 *cx, int e, float xin, int 
 // Ai neurons for step t+1, mark the column group / sample as candidate-holding, and stage the sample's input-trace
 // row of step t for a possible post term.  Rare per thread: kept out of line.
 __device__ __noinline__ void on_candidate2(const PassCtx2 *cx, uint32_t cand, int b, int cg, int t) {
-    Misc2 &M = *cx->k.M;
+    cx = sh(cx);
+    Misc2 &M = *sh(cx->k.M);
+    uint16_t *const ai_map = sh(cx->ai_map), *const ai_claim = sh(cx->ai_claim);
     const int par = t & 1, TJ = cx->TJ, jc = cx->j0 + 4 * cg, B = cx->k.B, Bp = cx->k.Bp, P = cx->k.P;
     unsigned long long mykey = 0ull;
     #pragma unroll 1
@@ -560,29 +604,29 @@ __device__ __noinline__ void on_candidate2(const PassCtx2 *cx, uint32_t cand, in
                 mykey = k2 > mykey ? k2 : mykey;
             }
             // the partner Ai neuron is this thread's at step t+1, whether the candidate wins or not
-            unsigned e = cx->ai_map[b * TJ + col];
+            unsigned e = ai_map[b * TJ + col];
             if (e == AI_NONE) {
                 e = (unsigned)atomicAdd(&M.nact, 1);
-                cx->ai_v[e] = cx->I_rest; cx->ai_rc[e] = 0.0f; cx->ai_id[e] = (uint16_t)((b << 8) | col); cx->ai_fl[e] = 1;
-                cx->ai_claim[par * cx->aicap + e] = (uint16_t)AI_NONE;
-                cx->ai_map[b * TJ + col] = (uint16_t)e;
+                sh(cx->ai_v)[e] = cx->I_rest; sh(cx->ai_rc)[e] = 0.0f; sh(cx->ai_id)[e] = (uint16_t)((b << 8) | col); sh(cx->ai_fl)[e] = 1;
+                ai_claim[par * cx->aicap + e] = (uint16_t)AI_NONE;
+                ai_map[b * TJ + col] = (uint16_t)e;
             }
-            cx->ai_claim[(par ^ 1) * cx->aicap + e] = (uint16_t)(t + 1);   // slot of parity (t + 1) & 1
+            ai_claim[(par ^ 1) * cx->aicap + e] = (uint16_t)(t + 1);   // slot of parity (t + 1) & 1
         }
     atomicOr(&M.candgrp[par], 1u << cg);
     atomicOr(&M.candmask[par][cg][b >> 5], 1u << (b & 31));
-    ((uint8_t *)cx->k.candlist)[(par * 8 + cg) * Bp + atomicAdd(&M.ncs[par][cg], 1)] = (uint8_t)b;
+    sh((uint8_t *)cx->k.candlist)[(par * 8 + cg) * Bp + atomicAdd(&M.ncs[par][cg], 1)] = (uint8_t)b;
     if (cx->one_spike) atomicMax(cx->win + (t % 3) * B + b, mykey);
     if (cx->stage_on) {  // stage x_pre[b,:] of step t for the post term, once per sample
-        const uint32_t old = atomicExch(&cx->candstamp[par * Bp + b], (uint32_t)(t + 1));
+        const uint32_t old = atomicExch(sh(cx->candstamp) + par * Bp + b, (uint32_t)(t + 1));
         if (old != (uint32_t)(t + 1)) {
             const int s = atomicAdd(&M.ncand[par], 1);
             if (s < XR && !cx->nostage) {
                 M.candb[par][s] = b;
-                cx->candslot[par * Bp + b] = s;
+                sh(cx->candslot)[par * Bp + b] = s;
                 mbar_expect_tx(&M.mbar_x[par], (uint32_t)P);
-                bulk_g2s(cx->xrow_w + (par * XR + s) * P, cx->xage + ((size_t)t * B + b) * P, (uint32_t)P, &M.mbar_x[par]);
-            } else cx->candslot[par * Bp + b] = -1;
+                bulk_g2s(sh(cx->xrow_w) + (par * XR + s) * P, cx->xage + ((size_t)t * B + b) * P, (uint32_t)P, &M.mbar_x[par]);
+            } else sh(cx->candslot)[par * Bp + b] = -1;
         }
     }
 }
@@ -812,6 +856,9 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 const unsigned int target = G * (unsigned int)t;
                 unsigned int spins = 0;
                 while ((int)(ld_relaxed_u32(Q.bar) - target) < 0 && !(PROFV && (Q.dbg & 16))) {
+#if V2_POLL_NS
+                    __nanosleep(V2_POLL_NS);
+#endif
                     if ((++spins & 0xfffffu) == 0) {   // ~ a second of polling: give up
                         if (spins > (4u << 20)) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
                     }
@@ -848,8 +895,9 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
 
         // ---- column groups that held a candidate at step t-1: winners (nodes.py:1097-1105), Ae trace, partner
         // Ai neurons, monitors, late STDP — all of it local to the group's own threads
-        const bool lateg = !isx && t > 0 && ((M.candgrp[ppar] >> cg) & 1u);
+        const bool lateg = !isx && t > 0 && (((M.candgrp[ppar] >> cg) & 1u) || (Q.dbg & 256));   // (diagnostic bit 256: every group walks the late path every step)
         if (lateg) {
+            if (PROFV && b == 0) M.rs[cg][0] = clock64();
             if (pend) {
                 uint32_t sE = 0;
                 if (E.one_spike) {
@@ -857,6 +905,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                     const int wj = (int)(uint32_t)(key & 0xffffffffull) - jc;
                     if (key != 0ull && wj >= 0 && wj < 4 && ((candE >> wj) & 1u)) sE = 1u << wj;
                 } else sE = candE;
+                if (PROFV) M.rs[cg][1] = clock64();
                 if (E.traces) {
                     #pragma unroll
                     for (int c = 0; c < 4; ++c) xE[c] = trace_step(xE[c], (sE >> c) & 1u, E.trace_decay, E.trace_scale, 0);
@@ -871,7 +920,9 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                         }
                     }
                 }
+                if (PROFV) M.rs[cg][2] = clock64();
                 const int slot = (stage_on && candstamp[ppar * Bp + b] == (uint32_t)t) ? candslot[ppar * Bp + b] : -1;   // staged at step t-1
+                if (PROFV) M.rs[cg][3] = clock64();
                 #pragma unroll 1
                 for (int c = 0; c < 4; ++c)
                     if ((candE >> c) & 1u) {
@@ -893,12 +944,14 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                     }
                 if (t == T) sEfin = sE;
                 pend = 0;
+                if (PROFV) M.rs[cg][4] = clock64();
             }
             PROF(2)  // winners
             if (PROFV) g_ta = clock64();
             if (update_on) {
                 // STDP of step t-1 for this column group (MCC_learning.py:234-299)
                 bar_group(gbar, Bp);
+                if (PROFV && b == 0) M.rs[cg][5] = clock64();
                 const int sb_ = buf;   // slot t = spikes of step t-1
                 const uint32_t gwin = post_on ? M.colwin[cg] : 0u;
                 const int nwl = post_on ? M.nwl[cg] : 0;
@@ -907,6 +960,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                     #pragma unroll 1
                     for (int k = 0; k < nwl; ++k) if ((M.wl[cg][k] & 0xffu) == 0xffu) fast = false;
                 }
+                if (PROFV && b == 0) M.rs[cg][6] = clock64();
                 const uint8_t *xr = xrow + ppar * XR * P;   // rows staged at step t-1 (buffer of its parity, filled for the ((t-1)>>1)-th time)
                 if (nwl && stage_on) { while (!mbar_try_wait(&M.mbar_x[ppar], (uint32_t)((t - 1) >> 1) & 1u)) {} }
                 PROF(3)  // late set-up
@@ -915,14 +969,26 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 // spiked (unless the slot is dense: then nothing of this group was done yet)
                 const uint32_t *dm = &M.candmask[ppar][cg][0];
                 if (fast) {
+                    if (PROFV && b == 0) M.rs[cg][7] = clock64();
                     if (pre_on || gwin) stdp_list2<CG, BW>(&s_cx, sb_, cg, 1, gwin, dm, ppar, xr, t - 1, b, Bp);
+                    if (PROFV && b == 0) M.rs[cg][8] = clock64();
                     if (nwl) post_rows2<CG, BW>(&s_cx, sb_, cg, nwl, dm, xr, t - 1, M.negzero ? 0 : 1, b, Bp);
                 } else {
                     stdp_rows2<CG, BW>(&s_cx, sb_, cg, gwin, M.candb[ppar], min(M.ncand[ppar], XR),
                                        Q.xage ? Q.xage + (size_t)(t - 1) * B * P : nullptr, xr, t - 1, M.denseflag[sb_] ? nullptr : dm, b, Bp);
                 }
                 PROF(4)  // late pass
+                if (PROFV && b == 0) M.rs[cg][9] = clock64();
                 bar_group(gbar, Bp);   // the group's weights are final for step t-1
+                if (PROFV && b == 0 && Q.prof && ((M.candgrp[ppar] >> cg) & 1u)) {   // fine stamps -> sums over all late paths of the window
+                    M.rs[cg][10] = clock64();
+                    long long *fs = Q.prof + 160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5;
+                    for (int k = 1; k <= 10; ++k) {
+                        const long long d = M.rs[cg][k] - M.rs[cg][k - 1];
+                        if (d > 0 && d < 1000000) atomicAdd((unsigned long long *)fs + k, (unsigned long long)d);
+                    }
+                    atomicAdd((unsigned long long *)fs, 1ull);
+                }
                 if (gwin) {
                     if (b < 4 * BW) M.wmask[4 * cg + (b / BW)][b % BW] = 0;
                     if (b == 0) { M.colwin[cg] = 0; M.nwl[cg] = 0; }
@@ -992,7 +1058,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             #pragma unroll 1
             for (int k = tid; k < nact; k += NC) {
                 if (ai_claim[par * aicap + k] == (uint16_t)t) continue;
+#if V2_UNIFY_AI
+                ai_step2(&s_cx, k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t, sis_t, aispk + par * Bp);
+#else
                 ai_step_body(&s_cx, k, (t == 0 && (ai_fl[k] & 4u)) ? (0.0f + Q.exc) : 0.0f, t, sis_t, aispk + par * Bp);
+#endif
             }
         }
         PROF(6)  // gather + neurons
@@ -1051,7 +1121,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
             if (b < BW) M.candmask[ppar][cg][b] = 0;   // step t-1's: consumed by the late pass above
             if (b == 0) M.ncs[ppar][cg] = 0;
             if (update_on && pre_on && !(PROFV && (Q.dbg & 2))) {
+#if V2_UNIFY_LIST
+                if (!dense_nb) stdp_list2<CG, BW>(&s_cx, nb, cg, 0, 0u, &M.candmask[par][cg][0], par, xrow, t, b, Bp);
+#else
                 if (!dense_nb) stdp_list_body<CG, BW>(&s_cx, nb, cg, 0, 0u, &M.candmask[par][cg][0], par, xrow, t, b, Bp);
+#endif
                 else if (earlyg) stdp_rows2<CG, BW>(&s_cx, nb, cg, 0u, M.candb[par], 0, nullptr, xrow, t, nullptr, b, Bp);
                 if (earlyg) bar_group(gbar, Bp);
             }
@@ -1450,7 +1524,7 @@ WsLayout2 ws_layout2(const Match2 &m, int T, int B, int P, bool traces) {
     L.sisum0 = o; o += al(sizeof(unsigned int) * (size_t)B);
     L.x0c = o; o += traces ? al(sizeof(float) * (size_t)B * P) : 0;
     L.xage = o; o += traces ? al((size_t)T * B * P) : 0;
-    L.prof = o; o += al(sizeof(long long) * (160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5));
+    L.prof = o; o += al(sizeof(long long) * (160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5 + 16));
     L.total = o;
     return L;
 }
@@ -1509,6 +1583,7 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     // dense flags, barrier counter, exchange slots
     if (cudaMemsetAsync(ws + WL.dense, 0, WL.inS - WL.dense, stream) != cudaSuccess) return SNN_ERR_CUDA;
     // sparse monitors: the window kernel only writes the ones
+    if (Q.prof) cudaMemsetAsync(Q.prof + 160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5, 0, sizeof(long long) * 16, stream);
     if (Q.E.rec_s && cudaMemsetAsync(Q.E.rec_s, 0, (size_t)T * B * Q.n, stream) != cudaSuccess) return SNN_ERR_CUDA;
     if (Q.I.rec_s && cudaMemsetAsync(Q.I.rec_s, 0, (size_t)T * B * Q.n, stream) != cudaSuccess) return SNN_ERR_CUDA;
     // the two static matrices are replaced by their constants: make sure they still have that structure
@@ -1603,6 +1678,14 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
                         last = st;
                     }
                 }
+            }
+            {
+                long long fs[16];
+                cudaMemcpy(fs, Q.prof + 160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5, sizeof(fs), cudaMemcpyDeviceToHost);
+                const double nn = fs[0] ? (double)fs[0] : 1.0;
+                fprintf(stderr, "  late path, mean over %lld group events: S1->key %.0f, traces/tx %.0f, slot %.0f, winners loop+Ai %.0f, group barrier %.0f, fast check %.0f, "
+                                "row wait %.0f, list pass %.0f, row pass %.0f, closing barrier %.0f\n", fs[0], fs[1] / nn, fs[2] / nn, fs[3] / nn, fs[4] / nn, fs[5] / nn,
+                        fs[6] / nn, fs[7] / nn, fs[8] / nn, fs[9] / nn, fs[10] / nn);
             }
             fprintf(stderr, "  late-path cycles by steps since the CTA's previous late path: <=2: %.0f (%d)  3-5: %.0f (%d)  6-10: %.0f (%d)  >10: %.0f (%d)\n",
                     cntg[0] ? dur[0] / cntg[0] : 0.0, cntg[0], cntg[1] ? dur[1] / cntg[1] : 0.0, cntg[1], cntg[2] ? dur[2] / cntg[2] : 0.0, cntg[2],

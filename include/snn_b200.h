@@ -189,8 +189,9 @@ typedef struct snn_run_opts {
     int32_t T;             /* timesteps = int(time / dt)  (network.py:356)                    */
     int32_t B;             /* batch size                                                      */
     int32_t normalize;     /* 1: run every connection's normalize() after the loop            */
-    int32_t tier;          /* 0 = auto, 1 = force generic kernel, 2 = force fused DC2015 kernel (v1: grid barrier),
-                              3 = force fused DC2015 kernel v2 (message exchange) */
+    int32_t tier;          /* 0 = auto (fused v1 where it matches, else fused v2, else generic), 1 = force generic kernel,
+                              2 = force fused DC2015 kernel v1 (grid barrier), 3 = force fused DC2015 kernel v2
+                              (exchange warp, per-column-group pipelines) */
     uint32_t seed;         /* one_spike tie-break stream (see snn_one_spike_key)              */
     uint32_t step_offset;  /* added to t in the tie-break hash (lets callers split a window)  */
     int32_t *err_flag;     /* optional int32 (device memory for the CUDA lib); OR-ed with SNN_ERR_* */

@@ -40,18 +40,18 @@ def test_generic_kernel_bit_exact_vs_oracle(name):
 DC = [c for c in ALL if c.startswith("dc2015") and c != "dc2015v2"]
 
 
-@pytest.mark.parametrize("tier", [0, 2])
+@pytest.mark.parametrize("tier", [0, 3])
 @pytest.mark.parametrize("name", DC)
 def test_fused_kernel_selected_and_bit_exact_vs_oracle(name, tier):
-    """tier=0 (auto) must pick the message-exchange fused DiehlAndCook2015 kernel (tier 3) for these
-    graphs, tier=2 the grid-barrier one; both must agree with the oracle bit for bit."""
+    """tier=0 (auto) must pick the grid-barrier fused DiehlAndCook2015 kernel (tier 2, the faster one) for these
+    graphs, tier=3 the column-group kernel; both must agree with the oracle bit for bit."""
     from bindsnet_b200 import _backend
 
     _, s_gpu, c_gpu = run_case_gpu(name, tier=tier)
     _, s_cpu, c_cpu = helpers.run_case_oracle(name)
     helpers.assert_bit_identical(s_gpu, s_cpu, f"{name} state (fused, tier {tier})")
     helpers.assert_bit_identical(c_gpu, c_cpu, f"{name} spike counts (fused, tier {tier})")
-    assert _backend.last_tier == (3 if tier == 0 else 2), "tier selection did not pick the expected fused kernel"
+    assert _backend.last_tier == (2 if tier == 0 else 3), "tier selection did not pick the expected fused kernel"
 
 
 @pytest.mark.parametrize("name", DC)

@@ -47,7 +47,7 @@ def _variants():
         "lbound_decay": (dict(rule=L.PostPre, reduction=torch.sum, lbound=-70.0, weight_decay=1e-3), 6, 28, 60, "poisson"),
         "batch160_lists": (dict(rule=L.PostPre, reduction=torch.sum), 160, 48, 50, "poisson"),
         "multi_spike_lists": (dict(rule=L.PostPre, reduction=torch.sum, one_spike=False, inh=17.5), 24, 64, 80, "poisson"),
-        # the lean option set runs on the message-exchange kernel (tier 3): odd batch / tile shapes, dense input slots
+        # the lean option set also runs on the column-group kernel (tier 3): odd batch / tile shapes, dense input slots
         "lean_b40_n100": (dict(rule=L.PostPre, reduction=torch.sum), 40, 100, 70, "poisson"),
         "lean_b128_n600": (dict(rule=L.PostPre, reduction=torch.sum, nu=(1e-3, 5e-2)), 128, 600, 40, "poisson"),
         "lean_dense_slots": (dict(rule=L.PostPre, reduction=torch.sum, nu=(2e-3, 1e-2)), 8, 40, 70, "bernoulli"),
@@ -82,7 +82,7 @@ def test_fused_variant_bit_exact_vs_oracle(name):
     helpers.add_spike_monitors(net, T, device="cuda")
     net.run(inputs={k: v.cuda() for k, v in inputs.items()}, time=T, one_spike_seed=cases.ONE_SPIKE_SEED)
     net.check_errors()
-    assert _backend.last_tier == (3 if name in TIER3 else 2), "the expected fused kernel was not selected for this graph"
+    assert _backend.last_tier == 2, "the fused kernel was not selected for this graph"
     s_gpu, c_gpu = helpers.snapshot(net), helpers.spike_counts(net, T)
 
     ref, inputs, T = _build(name, "cpu")
@@ -95,8 +95,8 @@ def test_fused_variant_bit_exact_vs_oracle(name):
     helpers.assert_bit_identical(s_gpu, s_cpu, f"{name} state (fused)")
     helpers.assert_bit_identical(c_gpu, c_cpu, f"{name} spike counts (fused)")
 
-    # same network through the generic kernel (and the grid-barrier fused kernel where tier 3 was selected)
-    for tier in ((1, 2) if name in TIER3 else (1,)):
+    # same network through the generic kernel (and the column-group fused kernel where it matches)
+    for tier in ((1, 3) if name in TIER3 else (1,)):
         net2, inputs, T = _build(name, "cuda")
         net2.force_tier = tier
         helpers.add_spike_monitors(net2, T, device="cuda")
