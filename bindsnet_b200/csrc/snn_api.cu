@@ -39,13 +39,14 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
         const snn_conn_t &C = net->conns[c];
         if (C.src < 0 || C.src >= net->n_layers || C.tgt < 0 || C.tgt >= net->n_layers || !C.w) return SNN_ERR_BAD_ARG;
         if (net->layers[C.tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
-        if (C.rule < SNN_RULE_NONE || C.rule > SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+        if (C.rule < SNN_RULE_NONE || C.rule > SNN_RULE_HEBBIAN) return SNN_ERR_UNSUPPORTED;
         if (C.kind < SNN_CONN_DENSE || C.kind > SNN_CONN_CONV2D) return SNN_ERR_UNSUPPORTED;
         if (C.kind == SNN_CONN_CONV2D) {
             const snn_layer_t &S = net->layers[C.src], &G = net->layers[C.tgt];
             if (C.cin * C.hin * C.win != S.n || C.cout * C.hout * C.wout != G.n || !C.b) return SNN_ERR_BAD_ARG;
             if (C.kh < 1 || C.kw < 1 || C.sh < 1 || C.sw < 1 || C.dh < 1 || C.dw < 1) return SNN_ERR_BAD_ARG;
-            if (C.rule != SNN_RULE_NONE && C.rule != SNN_RULE_NOOP && C.rule != SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+            if (C.rule == SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
+            if (SNN_RULE_IS_STDP(C.rule) && (C.dh != 1 || C.dw != 1)) return SNN_ERR_UNSUPPORTED;   // im2col_indices ignores dilation
         }
         if (C.rule == SNN_RULE_MSTDP) {
             if (!C.p_plus || !C.p_minus) return SNN_ERR_BAD_ARG;
@@ -53,7 +54,7 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
             else if (C.kind == SNN_CONN_DENSE) { if (!C.mst_spre || !C.mst_spost) return SNN_ERR_BAD_ARG; }
             else return SNN_ERR_UNSUPPORTED;
         }
-        if (C.rule >= SNN_RULE_POSTPRE && C.rule <= SNN_RULE_MCC_POSTPRE && (!net->layers[C.src].traces || !net->layers[C.tgt].traces))
+        if (SNN_RULE_IS_STDP(C.rule) && (!net->layers[C.src].traces || !net->layers[C.tgt].traces))
             return SNN_ERR_BAD_ARG;
         if (C.mask && (C.kind != SNN_CONN_DENSE || C.rule == SNN_RULE_MSTDP)) return SNN_ERR_UNSUPPORTED;
     }
@@ -62,7 +63,7 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
 
 static bool layer_needs_xpub(const snn_net_t *net, int l) {
     for (int c = 0; c < net->n_conns; ++c)
-        if (net->conns[c].src == l && net->conns[c].rule >= SNN_RULE_POSTPRE && net->conns[c].rule <= SNN_RULE_MCC_POSTPRE) return true;
+        if (net->conns[c].src == l && SNN_RULE_IS_STDP(net->conns[c].rule) && net->conns[c].kind != SNN_CONN_CONV2D) return true;
     return false;
 }
 

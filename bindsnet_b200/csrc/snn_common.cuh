@@ -155,7 +155,7 @@ __device__ __forceinline__ bool dc_step(const snn_layer_t &L, float &v, float &r
 }
 
 // One STDP-family update of a single synapse, in the reference's order: pre term, post term,
-// weight decay, clamp (learning.py:87-104,390-420,626-653; MCC_learning.py:86-110,224-302).
+// weight decay, clamp (learning.py:87-104,390-420,626-653,1110-1136; MCC_learning.py:86-110,224-302).
 // U / V are the batch-reduced outer products of this step for this synapse (0 if untouched).
 __device__ __forceinline__ float apply_rule(const snn_conn_t &C, float w, float U, bool pre_t, float V, bool post_t) {
     if (C.rule == SNN_RULE_WDEP_POSTPRE) {
@@ -169,6 +169,9 @@ __device__ __forceinline__ float apply_rule(const snn_conn_t &C, float w, float 
     } else if (C.rule == SNN_RULE_POSTPRE) {
         if (pre_t) w = w - U;
         if (post_t) w = w + V;
+    } else if (C.rule == SNN_RULE_HEBBIAN) {   // learning.py:1124-1134: U / V are the plain reduced sums
+        if (C.nu0 != 0.0f) w = w + C.nu0 * (pre_t ? U : 0.0f);
+        if (C.nu1 != 0.0f) w = w + C.nu1 * (post_t ? V : 0.0f);
     }
     if (C.weight_decay != 0.0f) w = w * C.weight_decay;
     if (C.has_clamp) w = clampf(w, C.wmin, C.wmax);

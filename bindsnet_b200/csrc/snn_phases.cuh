@@ -249,8 +249,8 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int t, float *s_acc, u
     const bool valid = j < nt;
     const int wr = t & 1;
     const int NG = (B + 31) / 32;
-    const bool stdp = C.rule >= SNN_RULE_POSTPRE;
-    const bool wdep = C.rule == SNN_RULE_WDEP_POSTPRE;
+    const bool stdp = SNN_RULE_IS_STDP(C.rule);
+    const bool wdep = C.rule == SNN_RULE_WDEP_POSTPRE || C.rule == SNN_RULE_HEBBIAN;   // plain sums: nu applied after the reduction
     const bool pre_on = stdp && C.nu0 != 0.0f, post_on = stdp && C.nu1 != 0.0f;
     const bool decay_on = C.weight_decay != 0.0f && C.weight_decay != 1.0f;
     const bool full = decay_on || (C.has_clamp && t == 0);
@@ -412,6 +412,54 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int tile, int t) {
     const int B = N.B, ns = S.L.n, nt = G.L.n, ntiles = G.nw;
     const int K = C.cin * C.kh * C.kw, L = C.hout * C.wout, NWT = C.cout * K;
     const size_t start = (size_t)tile * SNN_GEN_THREADS + threadIdx.x, stride = (size_t)ntiles * SNN_GEN_THREADS;
+    if (SNN_RULE_IS_STDP(C.rule)) {
+        // PostPre / WeightDependentPostPre / Hebbian on the im2col views (learning.py:457-497, 920-975, 1348-1380):
+        // per filter tap (co, k) the inner sum runs over the output positions (ascending) of one sample, the outer
+        // one over the samples (ascending) — the oracle's order.  Traces are read from the layers' own arrays:
+        // the grid barriers before and after the learning phase frame them.
+        const bool hebb = C.rule == SNN_RULE_HEBBIAN;
+        const bool pre_on = C.nu0 != 0.0f || hebb, post_on = C.nu1 != 0.0f || hebb;
+        const int wr = t & 1;
+        for (size_t e = start; e < (size_t)NWT; e += stride) {
+            const int co = (int)(e / K), k = (int)(e - (size_t)co * K);
+            const int ci = k / (C.kh * C.kw), kk = k - ci * C.kh * C.kw, ky = kk / C.kw, kx = kk - ky * C.kw;
+            float U = 0.0f, V = 0.0f;
+            for (int b = 0; b < B; ++b) {
+                const uint32_t *sb = S.bits + ((size_t)wr * B + b) * S.nw, *gb = G.bits + ((size_t)wr * B + b) * G.nw;
+                float u1 = 0.0f, v1 = 0.0f;
+                for (int oy = 0; oy < C.hout; ++oy) {
+                    const int iy = oy * C.sh - C.ph + ky;
+                    if (iy < 0 || iy >= C.hin) continue;
+                    for (int ox = 0; ox < C.wout; ++ox) {
+                        const int ix = ox * C.sw - C.pw + kx;
+                        if (ix < 0 || ix >= C.win) continue;
+                        const int src = (ci * C.hin + iy) * C.win + ix, tgt = co * L + oy * C.wout + ox;
+                        if (pre_on && bit_of(sb, src)) u1 = u1 + __ldcg(G.L.x + (size_t)b * nt + tgt);
+                        if (post_on && bit_of(gb, tgt)) v1 = v1 + __ldcg(S.L.x + (size_t)b * ns + src);
+                    }
+                }
+                U = U + u1; V = V + v1;
+            }
+            if (C.reduction == SNN_REDUCE_MEAN) { U = U / (float)B; V = V / (float)B; }
+            float x = C.w[e];
+            if (C.rule == SNN_RULE_WDEP_POSTPRE) {
+                float upd = 0.0f;
+                if (pre_on) upd = upd - (C.nu0 * U) * (x - C.wmin);
+                if (post_on) upd = upd + (C.nu1 * V) * (C.wmax - x);
+                x = x + upd;
+            } else if (hebb) {
+                x = x + C.nu0 * U;
+                x = x + C.nu1 * V;
+            } else {
+                if (pre_on) x = x - C.nu0 * U;
+                if (post_on) x = x + C.nu1 * V;
+            }
+            if (C.weight_decay != 0.0f) x = x * C.weight_decay;
+            if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
+            C.w[e] = x;
+        }
+        return;
+    }
     if (C.rule != SNN_RULE_MSTDP) {  // learning.NoOp: w *= weight_decay (learning.py:93-94), no clamp
         if (C.rule == SNN_RULE_NOOP && C.weight_decay != 0.0f)
             for (size_t k = start; k < (size_t)NWT; k += stride) C.w[k] = C.w[k] * C.weight_decay;

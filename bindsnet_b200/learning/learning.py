@@ -1,6 +1,6 @@
 """Learning rules for ``Connection`` — host-side mirror of ``bindsnet/learning/learning.py``
-(``LearningRule`` :25-104, ``NoOp`` :107-146, ``PostPre`` :149-420,
-``WeightDependentPostPre`` :562-653).  The rule objects hold hyper-parameters; the update
+(``LearningRule`` :25-104, ``NoOp`` :107-146, ``PostPre`` :149-420 / :457-497 (conv2d),
+``WeightDependentPostPre`` :562-653 / :920-975, ``Hebbian`` :1052-1136 / :1348-1380, ``MSTDP``).  The rule objects hold hyper-parameters; the update
 itself is fused into the CUDA window kernels (``Network.run``) or submitted for one step by
 ``rule.update()``."""
 from __future__ import annotations
@@ -78,7 +78,7 @@ class LearningRule(ABC):
         if self.rule_code is None:
             raise NotImplementedError(
                 f"user-defined learning rule {type(self).__name__} cannot be fused into the CUDA window; "
-                "supported: NoOp, PostPre, WeightDependentPostPre"
+                "supported: NoOp, PostPre, WeightDependentPostPre, Hebbian, MSTDP"
             )
         d.rule = self.rule_code
         d.reduction = self._reduction_code
@@ -92,6 +92,17 @@ class LearningRule(ABC):
         d.has_clamp = int(finite and not isinstance(self, NoOp))
 
 
+def _check_connection(rule, connection) -> None:
+    """The STDP-family rules exist for ``Connection`` (``_connection_update``) and ``Conv2dConnection``
+    (``_conv2d_connection_update``); the reference's im2col ignores dilation, so a dilated filter is refused."""
+    from ..network.topology import Connection, Conv2dConnection
+
+    if not isinstance(connection, (Connection, Conv2dConnection)):
+        raise NotImplementedError("This learning rule is not supported for this Connection type.")
+    if isinstance(connection, Conv2dConnection) and connection._geometry[3] != (1, 1):
+        raise NotImplementedError(f"{type(rule).__name__} on a dilated Conv2dConnection is undefined in the reference (im2col ignores dilation)")
+
+
 class NoOp(LearningRule):
     """Reference: learning.py:107-146 — weight decay only."""
 
@@ -99,7 +110,7 @@ class NoOp(LearningRule):
 
 
 class PostPre(LearningRule):
-    """Pair-based STDP (reference: learning.py:149-420; dense update :390-420)."""
+    """Pair-based STDP (reference: learning.py:149-420; dense update :390-420, conv2d :457-497)."""
 
     rule_code = _abi.SNN_RULE_POSTPRE
 
@@ -108,14 +119,11 @@ class PostPre(LearningRule):
         assert self.source.traces and self.target.traces, (
             "Both pre- and post-synaptic nodes must record spike traces."
         )
-        from ..network.topology import Connection
-
-        if not isinstance(connection, Connection):
-            raise NotImplementedError("This learning rule is not supported for this Connection type.")
+        _check_connection(self, connection)
 
 
 class WeightDependentPostPre(LearningRule):
-    """Weight-dependent STDP (reference: learning.py:562-653; dense update :626-653)."""
+    """Weight-dependent STDP (reference: learning.py:562-653; dense update :626-653, conv2d :920-975)."""
 
     rule_code = _abi.SNN_RULE_WDEP_POSTPRE
 
@@ -126,10 +134,21 @@ class WeightDependentPostPre(LearningRule):
         assert (connection.wmin != -np.inf).any() and (connection.wmax != np.inf).any(), (
             "Connection must define finite wmin and wmax."
         )
-        from ..network.topology import Connection
+        _check_connection(self, connection)
 
-        if not isinstance(connection, Connection):
-            raise NotImplementedError("This learning rule is not supported for this Connection type.")
+
+class Hebbian(LearningRule):
+    """Hebbian rule: both terms positive, learning rates applied after the batch reduction
+    (reference: learning.py:1052-1438; dense update :1110-1136, conv2d :1348-1380)."""
+
+    rule_code = _abi.SNN_RULE_HEBBIAN
+
+    def __init__(self, connection, nu=None, reduction=None, weight_decay: float = 0.0, **kwargs) -> None:
+        super().__init__(connection=connection, nu=nu, reduction=reduction, weight_decay=weight_decay, **kwargs)
+        assert self.source.traces and self.target.traces, (
+            "Both pre- and post-synaptic nodes must record spike traces."
+        )
+        _check_connection(self, connection)
 
 
 class MSTDP(LearningRule):
@@ -222,6 +241,5 @@ def _unsupported(name: str, where: str):
     return _Unsupported
 
 
-Hebbian = _unsupported("Hebbian", "learning.py:1052-1438")
 MSTDPET = _unsupported("MSTDPET", "learning.py:2124-2855")
 Rmax = _unsupported("Rmax", "learning.py:2858-2960")

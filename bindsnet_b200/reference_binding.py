@@ -9,7 +9,7 @@ a library that implements it — ``libsnn_b200.so`` on CUDA tensors, or the orac
 
 Covered: what ``bindsnet.models`` builds for the hot path — ``Input`` / ``LIFNodes`` / ``DiehlAndCookNodes`` layers,
 ``MulticompartmentConnection`` with one ``Weight`` feature (``MCC_learning.NoOp`` / ``PostPre``) and the classic
-``Connection`` with ``learning.NoOp`` / ``PostPre`` / ``WeightDependentPostPre``.  Every attribute is read where the
+``Connection`` with ``learning.NoOp`` / ``PostPre`` / ``WeightDependentPostPre`` / ``Hebbian``.  Every attribute is read where the
 reference keeps it (file:line in the comments); state tensors are handed over by pointer and updated in place.
 """
 from __future__ import annotations
@@ -110,7 +110,7 @@ def fill_connection(d: "_abi.SnnConn", conn, src: int, tgt: int, dt: float) -> N
         d.norm, d.norm_abs = (_f(conn.norm) if conn.norm is not None else 0.0), 1
         d.wmin, d.wmax = _f(conn.wmin), _f(conn.wmax)
         name = type(rule).__name__
-        d.rule = {"NoOp": _abi.SNN_RULE_NOOP, "PostPre": _abi.SNN_RULE_POSTPRE,
+        d.rule = {"NoOp": _abi.SNN_RULE_NOOP, "PostPre": _abi.SNN_RULE_POSTPRE, "Hebbian": _abi.SNN_RULE_HEBBIAN,
                   "WeightDependentPostPre": _abi.SNN_RULE_WDEP_POSTPRE}.get(name, -1)
         if d.rule < 0:
             raise NotImplementedError(f"learning rule {name}")

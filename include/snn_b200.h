@@ -62,6 +62,12 @@ extern "C" {
 #define SNN_RULE_MCC_POSTPRE 4 /* MCC_learning.PostPre._connection_update     MCC_learning.py:224-302 */
 #define SNN_RULE_MSTDP 5       /* learning.MSTDP: reward-modulated STDP; _connection_update learning.py:1504-1574
                                   on SNN_CONN_DENSE, _conv2d_connection_update :1942-2015 on SNN_CONN_CONV2D */
+#define SNN_RULE_HEBBIAN 6     /* learning.Hebbian: both terms positive, nu applied after the batch reduction;
+                                  _connection_update learning.py:1110-1136, _conv2d_connection_update :1348-1380 */
+/* On SNN_CONN_CONV2D the rules SNN_RULE_POSTPRE (learning.py:457-497), SNN_RULE_WDEP_POSTPRE (:920-975) and
+ * SNN_RULE_HEBBIAN correlate the im2col views:  pre[co,k] = reduce_b sum_l x_tgt[b,co,l] * s_src_col[b,k,l],
+ * post[co,k] = reduce_b sum_l s_tgt[b,co,l] * x_src_col[b,k,l]  (dilation 1), nu applied after the reduction. */
+#define SNN_RULE_IS_STDP(r) (((r) >= SNN_RULE_POSTPRE && (r) <= SNN_RULE_MCC_POSTPRE) || (r) == SNN_RULE_HEBBIAN)
 
 /* ---- weight-matrix structure hints (DiehlAndCook2015's static exc/inh matrices,
  *      models.py:204,217-220) ---- */

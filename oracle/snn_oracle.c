@@ -65,13 +65,14 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
         if (C->src < 0 || C->src >= net->n_layers || C->tgt < 0 || C->tgt >= net->n_layers) return SNN_ERR_BAD_ARG;
         if (!C->w) return SNN_ERR_BAD_ARG;
         if (net->layers[C->tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
-        if (C->rule < 0 || C->rule > SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+        if (C->rule < 0 || C->rule > SNN_RULE_HEBBIAN) return SNN_ERR_UNSUPPORTED;
         if (C->kind < 0 || C->kind > SNN_CONN_CONV2D) return SNN_ERR_UNSUPPORTED;
         if (C->kind == SNN_CONN_CONV2D) {
             const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
             if (C->cin * C->hin * C->win != S->n || C->cout * C->hout * C->wout != G->n) return SNN_ERR_BAD_ARG;
             if (C->kh < 1 || C->kw < 1 || C->sh < 1 || C->sw < 1 || C->dh < 1 || C->dw < 1 || !C->b) return SNN_ERR_BAD_ARG;
-            if (C->rule != SNN_RULE_NONE && C->rule != SNN_RULE_NOOP && C->rule != SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+            if (C->rule == SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
+            if (SNN_RULE_IS_STDP(C->rule) && (C->dh != 1 || C->dw != 1)) return SNN_ERR_UNSUPPORTED; /* im2col_indices ignores dilation */
         }
         if (C->rule == SNN_RULE_MSTDP) {
             if (!C->p_plus || !C->p_minus) return SNN_ERR_BAD_ARG;
@@ -79,7 +80,7 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
             else if (C->kind == SNN_CONN_DENSE) { if (!C->mst_spre || !C->mst_spost) return SNN_ERR_BAD_ARG; }
             else return SNN_ERR_UNSUPPORTED;
         }
-        if (C->rule >= SNN_RULE_POSTPRE && C->rule <= SNN_RULE_MCC_POSTPRE) {
+        if (SNN_RULE_IS_STDP(C->rule)) {
             /* learning.py:373-376,597-599; MCC_learning.py:193-196: traces required */
             if (!net->layers[C->src].traces) return SNN_ERR_BAD_ARG;
             if (!net->layers[C->tgt].traces) return SNN_ERR_BAD_ARG; /* target.x is read by every STDP rule */
@@ -315,8 +316,9 @@ static void conn_update(const snn_net_t *net, const snn_conn_t *C, const snn_run
     const int B = o->B, ns = S->n, nt = G->n;
     const size_t NW = (size_t)ns * nt;
     float *w = C->w;
-    const int stdp = C->rule >= SNN_RULE_POSTPRE;
-    const int wdep = C->rule == SNN_RULE_WDEP_POSTPRE;
+    const int stdp = SNN_RULE_IS_STDP(C->rule);
+    const int hebb = C->rule == SNN_RULE_HEBBIAN;
+    const int wdep = C->rule == SNN_RULE_WDEP_POSTPRE || hebb;   /* "raw" sums: nu applied after the reduction */
     const int pre_on = stdp && C->nu0 != 0.0f, post_on = stdp && C->nu1 != 0.0f;
     const float dts = C->rule == SNN_RULE_MCC_POSTPRE ? C->dt_scale : 1.0f;
     const int use_dt = C->rule == SNN_RULE_MCC_POSTPRE;
@@ -393,7 +395,10 @@ static void conn_update(const snn_net_t *net, const snn_conn_t *C, const snn_run
             const int ct = ws->col_t[j];
             if (!full && !rt && !ct) continue;
             float x = wi[j];
-            if (wdep) {
+            if (hebb) {                                                        /* learning.py:1124-1134 */
+                if (pre_on) x = x + C->nu0 * (rt ? Ui[j] : 0.0f);
+                if (post_on) x = x + C->nu1 * (ct ? Vi[j] : 0.0f);
+            } else if (wdep) {
                 float upd = 0.0f;
                 if (pre_on) upd = upd - (C->nu0 * (rt ? Ui[j] : 0.0f)) * (x - C->wmin);  /* learning.py:643-644 */
                 if (post_on) upd = upd + (C->nu1 * (ct ? Vi[j] : 0.0f)) * (C->wmax - x); /* learning.py:648-649 */
@@ -505,6 +510,59 @@ static void mstdp_conv_update(const snn_net_t *net, const snn_conn_t *C, const s
     }
 }
 
+/* PostPre / WeightDependentPostPre / Hebbian on a Conv2dConnection (learning.py:457-497, 920-975, 1348-1380) and the
+ * base class decay + clamp (:87-104).  The reference correlates the im2col views with two bmm's and reduces over
+ * the batch; here per filter tap (co, k): inner sum over the output positions l = (oy, ox) ascending per sample,
+ * outer sum over b ascending. */
+static void stdp_conv_update(const snn_net_t *net, const snn_conn_t *C, const snn_run_opts_t *o, int dense) {
+    const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
+    const int B = o->B, ns = S->n, nt = G->n, L = C->hout * C->wout, K = C->cin * C->kh * C->kw;
+    const int pre_on = C->nu0 != 0.0f || C->rule == SNN_RULE_HEBBIAN, post_on = C->nu1 != 0.0f || C->rule == SNN_RULE_HEBBIAN;
+    const float Bf = (float)B;
+#pragma omp parallel for schedule(static)
+    for (int co = 0; co < C->cout; ++co)
+        for (int ci = 0; ci < C->cin; ++ci)
+            for (int ky = 0; ky < C->kh; ++ky)
+                for (int kx = 0; kx < C->kw; ++kx) {
+                    float U = 0.0f, V = 0.0f;
+                    for (int b = 0; b < B; ++b) {
+                        float u1 = 0.0f, v1 = 0.0f;
+                        for (int oy = 0; oy < C->hout; ++oy) {
+                            const int iy = oy * C->sh - C->ph + ky;
+                            if (iy < 0 || iy >= C->hin) continue;
+                            for (int ox = 0; ox < C->wout; ++ox) {
+                                const int ix = ox * C->sw - C->pw + kx;
+                                if (ix < 0 || ix >= C->win) continue;
+                                const size_t src = (size_t)b * ns + ((size_t)ci * C->hin + iy) * C->win + ix;
+                                const size_t tgt = (size_t)b * nt + (size_t)co * L + (size_t)oy * C->wout + ox;
+                                const uint8_t ts = G->s[tgt], ss = S->s[src];
+                                if (pre_on && (dense || ss)) u1 = u1 + G->x[tgt] * (ss ? 1.0f : 0.0f);
+                                if (post_on && (dense || ts)) v1 = v1 + (ts ? 1.0f : 0.0f) * S->x[src];
+                            }
+                        }
+                        U = U + u1; V = V + v1;
+                    }
+                    if (C->reduction == SNN_REDUCE_MEAN) { U = U / Bf; V = V / Bf; }
+                    const size_t k = (size_t)co * K + ((size_t)ci * C->kh + ky) * C->kw + kx;
+                    float x = C->w[k];
+                    if (C->rule == SNN_RULE_WDEP_POSTPRE) {
+                        float upd = 0.0f;
+                        if (pre_on) upd = upd - (C->nu0 * U) * (x - C->wmin);      /* learning.py:955-961 */
+                        if (post_on) upd = upd + (C->nu1 * V) * (C->wmax - x);     /* :964-972 */
+                        x = x + upd;
+                    } else if (C->rule == SNN_RULE_HEBBIAN) {
+                        x = x + C->nu0 * U;                                        /* learning.py:1374 */
+                        x = x + C->nu1 * V;                                        /* :1378 */
+                    } else {
+                        if (pre_on) x = x - C->nu0 * U;                            /* learning.py:487-491 */
+                        if (post_on) x = x + C->nu1 * V;                           /* :494-497 */
+                    }
+                    if (C->weight_decay != 0.0f) x = x * C->weight_decay;
+                    if (C->has_clamp) x = clampf(x, C->wmin, C->wmax);
+                    C->w[k] = x;
+                }
+}
+
 /* Conv2dConnection.normalize (topology.py:824-837): every (out, in) filter is scaled to sum `norm`
  * (plain sum over kh*kw in ascending order; no guard against a zero sum, like the reference). */
 static void normalize_conv(const snn_conn_t *C) {
@@ -575,7 +633,7 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
     for (int c = 0; c < net->n_conns; ++c) {
         const snn_conn_t *C = &net->conns[c];
         const int ns = net->layers[C->src].n, nt = net->layers[C->tgt].n;
-        if (C->rule >= SNN_RULE_POSTPRE && C->rule <= SNN_RULE_MCC_POSTPRE) {
+        if (SNN_RULE_IS_STDP(C->rule) && C->kind != SNN_CONN_CONV2D) {
             cws[c].U = (float *)calloc((size_t)ns * nt, sizeof(float));
             cws[c].V = (float *)calloc((size_t)ns * nt, sizeof(float));
             cws[c].tx = (float *)calloc((size_t)B * nt, sizeof(float));
@@ -617,6 +675,7 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
                 const snn_conn_t *C = &net->conns[c];
                 if (C->rule == SNN_RULE_MSTDP && C->kind == SNN_CONN_CONV2D) mstdp_conv_update(net, C, o, dense);
                 else if (C->rule == SNN_RULE_MSTDP) mstdp_dense_update(net, C, o, dense);
+                else if (C->kind == SNN_CONN_CONV2D && SNN_RULE_IS_STDP(C->rule)) stdp_conv_update(net, C, o, dense);
                 else if (C->kind == SNN_CONN_CONV2D) {  /* learning.NoOp on a conv connection: decay only */
                     if (C->rule == SNN_RULE_NOOP && C->weight_decay != 0.0f)
                         for (size_t k = 0; k < (size_t)C->cout * C->cin * C->kh * C->kw; ++k) C->w[k] = C->w[k] * C->weight_decay;

@@ -394,6 +394,42 @@ def dc2015_silent(ns, inputs=None):
     return net, inputs, kw, 12
 
 
+# Hebbian on a dense Connection (learning.py:1110-1136): both terms positive, nu after the batch reduction; weight decay
+def hebbian_dense(ns, inputs=None):
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=64, traces=True)
+    Y = ns.nodes.LIFNodes(n=32, traces=True, thresh=-58.0, refrac=2)
+    C = ns.topology.Connection(source=X, target=Y, w=_w((64, 32), 151, 0.6), update_rule=ns.learning.Hebbian, nu=(1e-3, 4e-3),
+                               reduction=torch.mean, weight_decay=2e-3, wmin=0.0, wmax=1.0)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y"); net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(100, 4, (64,), 0.15, 152)}
+    return net, inputs, {}, 100
+
+
+# PostPre / WeightDependentPostPre / Hebbian on a Conv2dConnection (learning.py:457-497, 920-975, 1348-1380) feeding a
+# dense connection under the same rule
+def conv_postpre(ns, inputs=None):
+    net = _conv_net(ns, 3, 50, (1, 10, 10), 3, 3, 1, 0, ns.learning.PostPre, (161, 162), conv_nu=(4e-3, 2e-2))
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(50, 3, (1, 10, 10), 0.12, 163)}
+    return net, inputs, {}, 50
+
+
+def conv_wdep(ns, inputs=None):
+    net = _conv_net(ns, 2, 50, (2, 9, 9), 3, 3, 2, 1, ns.learning.WeightDependentPostPre, (171, 172), n_out=5, conv_nu=(1e-2, 3e-2))
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(50, 2, (2, 9, 9), 0.15, 173)}
+    return net, inputs, {}, 50
+
+
+def conv_hebbian(ns, inputs=None):
+    net = _conv_net(ns, 3, 50, (1, 10, 10), 4, 3, 1, 1, ns.learning.Hebbian, (181, 182), conv_nu=(1e-3, 2e-3))
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(50, 3, (1, 10, 10), 0.12, 183)}
+    return net, inputs, {}, 50
+
+
 CASES = {
     "c1_lif_postpre": c1_lif_postpre,
     "lif_postpre_batch": lif_postpre_batch,
@@ -420,6 +456,10 @@ CASES = {
     "conv_bias_stride": conv_bias_stride,
     "dc2015_b1_t1": dc2015_b1_t1,
     "dc2015_silent": dc2015_silent,
+    "hebbian_dense": hebbian_dense,
+    "conv_postpre": conv_postpre,
+    "conv_wdep": conv_wdep,
+    "conv_hebbian": conv_hebbian,
 }
 
 #: cases whose fixture stores subsampled weights only (full tensors would be several MB)
