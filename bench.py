@@ -281,6 +281,109 @@ def emit(line) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+def run_config4(args) -> None:
+    """BASELINE.json configs[3]: Input[1,32,32] -conv k5-> LIFNodes[16,28,28] -> Connection -> LIFNodes(10), MSTDP on both
+    connections, Bernoulli(0.1) input, 500 timesteps, batch 128 — the generic window kernel.
+    A diagnostic companion of the metric line: device-timed value, the end-to-end leg from pinned host spikes, and the
+    oracle's dense restatement on the host cores on a bounded sample."""
+    import torch
+
+    import __graft_entry__ as entry
+    from bindsnet_b200 import _backend
+    from bindsnet_b200.learning import MSTDP
+    from bindsnet_b200.network import Network, nodes, topology
+
+    B, T = 128, 500
+
+    def build(device):
+        torch.manual_seed(7)
+        net = Network(dt=1.0, batch_size=B)
+        X = nodes.Input(shape=[1, 32, 32], traces=True)
+        H = nodes.LIFNodes(shape=[16, 28, 28], traces=True)
+        O = nodes.LIFNodes(n=10, traces=True)
+        net.add_layer(X, "X"); net.add_layer(H, "H"); net.add_layer(O, "O")
+        net.add_connection(topology.Conv2dConnection(X, H, kernel_size=5, update_rule=MSTDP, nu=1e-2, reduction=torch.sum,
+                                                     wmin=-1.0, wmax=1.0), "X", "H")
+        net.add_connection(topology.Connection(H, O, update_rule=MSTDP, nu=1e-2, reduction=torch.sum, wmin=-1.0, wmax=1.0), "H", "O")
+        return net.to(device) if device is not None else net
+
+    K, W = min(args.steps, 5), min(max(args.warmup, 1), 2)
+    g = torch.Generator().manual_seed(11)
+    if args.impl == "reference":
+        from oracle.oracle import OracleBackend
+
+        cores, Ts = host_threads(), 10
+        x = torch.bernoulli(0.1 * torch.ones(Ts, B, 1, 32, 32), generator=g).byte()
+        ref = build(None)
+        with OracleBackend(dense=1, threads=cores):
+            ref.run({"X": x}, time=Ts, reward=1.0)
+            t0 = time.perf_counter()
+            for _ in range(K):
+                ref.reset_state_variables(); ref.run({"X": x}, time=Ts, reward=1.0)
+            wall = (time.perf_counter() - t0) / K
+        v = B * Ts / wall
+        emit({"impl": "reference", "metric": "sample·timesteps/s conv32x32-16ch-10 MSTDP b=128 (BASELINE.json configs[3])", "value": v, "unit": UNIT,
+              "n_gpus": 1, "steps": K, "warmup": 1, "ms_per_step": wall * 1e3, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "conv 32x32 k5 -> 16x28x28 -> 10, MSTDP on both connections, Bernoulli(0.1) input, B=128", "baseline_config": "c4"},
+              "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{Ts} of {T} timesteps per step, dense mode, OpenMP with {cores} threads; the live reference's conv MSTDP "
+                                         "raises for batch size > 1 (learning.py:2013), so the restatement stands in"},
+              "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    if not _backend.is_built():
+        entry.build()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    host = [torch.bernoulli(0.1 * torch.ones(T, B, 1, 32, 32), generator=g).byte().pin_memory() for _ in range(2)]
+    resident = [h.to(dev) for h in host]
+    net = build(dev)
+
+    def window(x):
+        net.reset_state_variables()
+        net.run({"X": x}, time=T, reward=1.0)
+
+    for i in range(W):
+        window(resident[i & 1])
+    torch.cuda.synchronize()
+    l0 = _backend.launches_total
+    with ClockSampler(0) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            window(resident[i & 1])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = _backend.launches_total - l0
+    net.check_errors()
+    # end to end: pinned host spikes in, the output layer's spikes of the last step out, every window
+    xdev = torch.empty_like(resident[0])
+    out_host = torch.empty(B, 10, dtype=torch.bool).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        xdev.copy_(host[i & 1], non_blocking=True)
+        window(xdev)
+        out_host.copy_(net.layers["O"].s, non_blocking=True)
+        torch.cuda.synchronize()
+        int(out_host.sum())
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / K
+    emit({"metric": "sample·timesteps/s conv32x32-16ch-10 MSTDP b=128 (BASELINE.json configs[3])", "value": B * T / (ms * 1e-3), "unit": UNIT,
+          "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "conv 32x32 k5 -> 16x28x28 -> 10, MSTDP on both connections, Bernoulli(0.1) input, B=128, 500 timesteps/window",
+                     "global_batch": B, "timesteps": T, "parallelism": "single GPU", "kernel_tier": "generic", "baseline_config": "c4",
+                     "l2": "two 65 MB input windows alternate (130 MB > 126 MB L2)"},
+          "e2e": {"value": B * T / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * B * 1024, "d2h_bytes_per_step": B * 10,
+                  "note": "pinned host uint8 spikes -> H2D -> Network.run(reward=1.0) -> output-layer spikes D2H, read on the host every window"},
+          "gpu_launches": launches, "clocks": clocks.summary(),
+          "roofline": {"bound": "hbm", "achieved": None, "peak": hbm_peak_gbs()[0], "unit": "GB/s", "frac": None, "traffic": None,
+                       "kernel_ms": ms, "note": "generic tier, latency-bound (grid barriers per step); no algorithmic-bytes figure is defined for this configuration in SURVEY.md §8d"}})
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -290,11 +393,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tier", type=int, default=0, help="0 auto, 1 generic kernel, 2 fused DC2015 kernel v1 (grid barrier), 3 fused DC2015 kernel v2 (message exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
-                    help="BASELINE.json configs[1] (the metric configuration: n=1600, B=128; default) or configs[2] (n=6400, B=256)")
+    ap.add_argument("--config", default="metric", choices=["metric", "c3", "c4"],
+                    help="metric: the configuration BASELINE.json's metric is quoted on (DiehlAndCook2015 n=1600, B=128; default); "
+                         "c3: configs[2] (n=6400, B=256); c4: configs[3] (conv 32x32 -> 16ch -> 10, MSTDP, 500 timesteps, B=128)")
     args = ap.parse_args()
     apply_config(args.config)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.config == "c4":
+        return run_config4(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -491,7 +597,7 @@ def main():
         achieved = per_launch_bytes / (kavg_ms * 1e-3) / 1e9 if kavg_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath) and args.config == "c2":
+        if os.path.exists(tpath) and args.config == "metric":
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:

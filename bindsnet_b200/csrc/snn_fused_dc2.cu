@@ -404,12 +404,14 @@ __device__ __noinline__ void post_rows2(const PassCtx2 *cx, int sb, int c4, int 
                 const uint4 q0 = cT[i * (BW / 4)];
                 any[u] = (q0.x & z[0]) | (q0.y & z[1]) | (q0.z & z[2]) | (q0.w & z[3]);
                 if (BW == 8) { const uint4 q1 = cT[i * (BW / 4) + 1]; any[u] |= (q1.x & z[BW - 4]) | (q1.y & z[BW - 3]) | (q1.z & z[BW - 2]) | (q1.w & z[BW - 1]); }
-                w[u] = wcol[i * WS];
+                if (i0 + u * nthr0 >= P) any[u] = 1u;   // past the last row
             }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = any[u] ? 0.0f : wcol[(i0 + u * nthr0) * WS];   // rows the list pass owns are not even read
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * nthr0;
-                if (i >= P || any[u]) continue;   // rows with a candidate-holding sample's spike: done by the list pass
+                if (any[u]) continue;   // rows with a candidate-holding sample's spike: done by the list pass
                 const float xv = xval(cx, age[u], wb, i, tstep);
                 if (skip0 && xv == 0.0f) continue;
                 const float V = 0.0f + xv * c_.nu1;
