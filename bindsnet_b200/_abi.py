@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SNN_ABI_VERSION = 7
+SNN_ABI_VERSION = 8
 SNN_MAX_LAYERS = 8
 SNN_MAX_CONNS = 12
 
@@ -146,6 +146,8 @@ class SnnRunOpts(C.Structure):
         ("step_offset", C.c_uint32),
         ("err_flag", C.c_void_p),
         ("one_step", C.c_int32),
+        ("delta_w", C.c_void_p),
+        ("delta_theta", C.c_void_p),
     ]
 
 

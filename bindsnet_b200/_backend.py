@@ -49,6 +49,8 @@ def lib() -> C.CDLL:
     L.snn_b200_delta_prepare.argtypes = [vp, vp, vp, sz, vp]
     L.snn_b200_delta_apply.restype = C.c_int
     L.snn_b200_delta_apply.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, i32, i32, f32, vp]
+    L.snn_b200_delta_apply_fused.restype = C.c_int
+    L.snn_b200_delta_apply_fused.argtypes = [vp, vp, i32, i32, i32, f32, f32, i32, i32, f32, vp, vp, i32, vp]
     L.snn_b200_conn_compute.restype = C.c_int
     L.snn_b200_conn_compute.argtypes = [C.POINTER(_abi.SnnConn), i32, i32, i32, vp, vp, vp]
     L.snn_b200_conn_update.restype = C.c_int
@@ -211,6 +213,18 @@ def delta_apply(w, w0, dw_sum, has_clamp, wmin, wmax, has_norm, norm_abs, norm) 
         _check(lib().snn_b200_delta_apply(w.data_ptr(), w0.data_ptr(), dw_sum.data_ptr(), w.shape[0], w.shape[1],
                                           int(has_clamp), float(wmin), float(wmax), int(has_norm), int(norm_abs),
                                           float(norm), _stream_ptr(w.device)), "snn_b200_delta_apply")
+
+
+def delta_apply_fused(w, dw_sum, has_clamp, wmin, wmax, has_norm, norm_abs, norm, theta=None, dtheta_sum=None) -> None:
+    """In-place combine after a delta window: ``w = clamp(w + dw_sum)``, normalize, ``theta += dtheta_sum`` — one launch."""
+    global launches_total
+    require_cuda(w, "w")
+    launches_total += 1
+    with torch.cuda.device(w.device):
+        _check(lib().snn_b200_delta_apply_fused(w.data_ptr(), dw_sum.data_ptr(), w.shape[0], w.shape[1], int(has_clamp), float(wmin), float(wmax),
+                                                int(has_norm), int(norm_abs), float(norm), theta.data_ptr() if theta is not None else None,
+                                                dtheta_sum.data_ptr() if theta is not None else None, theta.numel() if theta is not None else 0,
+                                                _stream_ptr(w.device)), "snn_b200_delta_apply_fused")
 
 
 def encode_poisson(rate_hz: torch.Tensor, T: int, dt: float, seed: int, out: torch.Tensor) -> None:

@@ -35,6 +35,7 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
         if (L.sum_input && !L.summed) return SNN_ERR_BAD_ARG;
         if (L.ext && L.ext_dtype != SNN_EXT_U8 && L.ext_dtype != SNN_EXT_F32) return SNN_ERR_BAD_ARG;
     }
+    if ((o->delta_w || o->delta_theta) && (o->normalize || !net->learning || o->one_step)) return SNN_ERR_UNSUPPORTED;
     for (int c = 0; c < net->n_conns; ++c) {
         const snn_conn_t &C = net->conns[c];
         if (C.src < 0 || C.src >= net->n_layers || C.tgt < 0 || C.tgt >= net->n_layers || !C.w) return SNN_ERR_BAD_ARG;
@@ -126,6 +127,8 @@ int snn_b200_last_launch_count(void) { return g_last_launches; }
 
 int snn_b200_select_tier(const snn_net_t *net, const snn_run_opts_t *opts) {
     if (validate(net, opts) != SNN_OK) return 0;
+    if (opts->delta_w || opts->delta_theta)   // delta windows exist in the barrier kernel only
+        return (opts->tier == 0 || opts->tier == 2) && snn_fused_dc_supported(net, opts) ? 2 : 0;
     if (opts->tier == 1) return 1;
     if (opts->tier == 3) return snn_fused_dc2_supported(net, opts) ? 3 : 0;
     // auto: the barrier kernel (tier 2) is the faster of the two fused kernels wherever both apply (B200, metric

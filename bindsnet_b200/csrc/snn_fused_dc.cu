@@ -57,6 +57,7 @@ struct FusedParams {
     unsigned long long *win;  // [3][B] arg-max keys, slot t % 3
     unsigned int *sisum;      // [3][B] Ai spike counts, slot t % 3 (slot 2 = step -1)
     float *xpub;              // [3][B][P] published input traces, slot t % 3
+    float *delta_w, *delta_theta;   // snn_run_opts_t: write the window's weight / theta change instead of the new values
     unsigned int *bar;        // [0] arrivals (monotonic), [32] generation
     int *dense;               // [T+1] slot holds a sample whose event list overflowed EV_CAP
     int32_t *err;
@@ -1035,10 +1036,17 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     #pragma unroll 1
     for (int idx = tid; idx < P * TJ; idx += nthr) {
         const int i = idx / TJ, jj = idx % TJ;
-        if (j0 + jj < n) C.w[(size_t)i * n + j0 + jj] = W[i * WS + jj];
+        if (j0 + jj < n) {
+            const size_t k = (size_t)i * n + j0 + jj;
+            if (Q.delta_w) Q.delta_w[k] = W[i * WS + jj] - C.w[k];   // multi-GPU window: the caller's all-reduce buffer
+            else C.w[k] = W[i * WS + jj];
+        }
     }
     for (int jj = tid; jj < TJ; jj += nthr)
-        if (j0 + jj < n) E.theta[j0 + jj] = theta_s[jj];
+        if (j0 + jj < n) {
+            if (Q.delta_theta) Q.delta_theta[j0 + jj] = theta_s[jj] - E.theta[j0 + jj];
+            else E.theta[j0 + jj] = theta_s[jj];
+        }
     if (act) {
         #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -1346,6 +1354,7 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     Q.inS = (uint32_t *)(ws + WL.inS); Q.inT = (uint32_t *)(ws + WL.inT); Q.evS = (unsigned char *)(ws + WL.evS);
     Q.win = (unsigned long long *)(ws + WL.win); Q.sisum = (unsigned int *)(ws + WL.sisum);
     Q.xpub = (float *)(ws + WL.xpub); Q.bar = (unsigned int *)(ws + WL.bar); Q.err = opts->err_flag;
+    Q.delta_w = opts->delta_w; Q.delta_theta = opts->delta_theta;
     const bool prof = getenv("SNN_B200_PROF") != nullptr;
     Q.prof = prof ? (long long *)(ws + WL.prof) : nullptr;
     Q.dense = (int *)(ws + WL.dense);

@@ -82,8 +82,10 @@ __global__ void delta_prepare_kernel(const float *__restrict__ w, const float *_
 }
 
 // w = clamp(w0 + sum_r dw_r), then normalize() — all on one column tile.
-__global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t C, const float *__restrict__ w0,
-                                                                       const float *__restrict__ dws, int ns, int nt) {
+__global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t C, const float *w0, const float *__restrict__ dws, int ns, int nt,
+                                                                       float *theta, const float *__restrict__ dtheta, int n_theta) {
+    if (theta)   // theta = theta0 + sum_r dtheta_r, in place, spread over the grid
+        for (int k = blockIdx.x * SNN_GEN_THREADS + threadIdx.x; k < n_theta; k += gridDim.x * SNN_GEN_THREADS) theta[k] = theta[k] + dtheta[k];
     __shared__ float s_part[(SNN_NORM_CHUNKS + 1) * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * SNN_TILE + lane;
@@ -100,15 +102,26 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t
 // Checks on the device that a square matrix has the structure a plan claims for it (SNN_W_DIAG: val on the
 // diagonal, 0 elsewhere; SNN_W_OFFDIAG: 0 on the diagonal, val elsewhere) — the fused kernels replace such a
 // matrix by its constant, so a matrix modified behind the host-side cache must not go unnoticed.
-__global__ void verify_structure_kernel(const float *__restrict__ w, int n, int structure, float val, int32_t *err) {
+__global__ void __launch_bounds__(256) verify_structure_kernel(const float *__restrict__ w, int n, int structure, float val, int32_t *err) {
     const size_t total = (size_t)n * n;
+    const bool diag = structure == SNN_W_DIAG;
     bool bad = false;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = k / n, j = k - i * n;
-        const float want = ((i == j) == (structure == SNN_W_DIAG)) ? val : 0.0f;
-        bad |= w[k] != want;
+    if ((n & 3) == 0 && (((size_t)w) & 15) == 0) {   // 16-byte loads: the matrix is read once per window (10 MB at n = 1600)
+        const float4 *w4 = (const float4 *)w;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += (size_t)gridDim.x * blockDim.x) {
+            const float4 x = __ldcs(w4 + q);
+            const size_t k = 4 * q, i = k / n, j = k - i * n;   // 4 | n: the four elements share row i
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) bad |= xs[e] != (((i == j + e) == diag) ? val : 0.0f);
+        }
+    } else {
+        for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+            const size_t i = k / n, j = k - i * n;
+            bad |= w[k] != (((i == j) == diag) ? val : 0.0f);
+        }
     }
-    if (bad && err) atomicOr(err, SNN_ERR_STRUCTURE);
+    if (__syncthreads_or(bad) && threadIdx.x == 0 && err) atomicOr(err, SNN_ERR_STRUCTURE);
 }
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? SNN_OK : SNN_ERR_CUDA; }
@@ -118,7 +131,7 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? SNN_OK : SNN_ERR_C
 int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t stream) {
     if (C.structure != SNN_W_DIAG && C.structure != SNN_W_OFFDIAG) return SNN_OK;
     const size_t total = (size_t)n * n;
-    const int blocks = (int)((total + 2047) / 2048 < 592 ? (total + 2047) / 2048 : 592);
+    const int blocks = (int)((total + 2047) / 2048 < 1184 ? (total + 2047) / 2048 : 1184);   // 8 elements per thread, up to 8 CTAs per SM
     verify_structure_kernel<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(C.w, n, C.structure, C.structure_val, err);
     return cuda_rc(cudaGetLastError());
 }
@@ -201,7 +214,19 @@ int snn_b200_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t
     snn_conn_t C;
     memset(&C, 0, sizeof(C));
     C.w = w; C.has_clamp = has_clamp; C.wmin = wmin; C.wmax = wmax; C.has_norm = has_norm; C.norm_abs = norm_abs; C.norm = norm;
-    delta_apply_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(C, w0, dw_sum, n_src, n_tgt);
+    delta_apply_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(C, w0, dw_sum, n_src, n_tgt, nullptr, nullptr, 0);
+    return cuda_rc(cudaGetLastError());
+}
+
+int snn_b200_delta_apply_fused(float *w, const float *dw_sum, int32_t n_src, int32_t n_tgt, int32_t has_clamp, float wmin, float wmax,
+                               int32_t has_norm, int32_t norm_abs, float norm, float *theta, const float *dtheta_sum, int32_t n_theta,
+                               void *stream) {
+    if (!w || !dw_sum || n_src <= 0 || n_tgt <= 0 || (theta && (!dtheta_sum || n_theta <= 0))) return SNN_ERR_BAD_ARG;
+    snn_conn_t C;
+    memset(&C, 0, sizeof(C));
+    C.w = w; C.has_clamp = has_clamp; C.wmin = wmin; C.wmax = wmax; C.has_norm = has_norm; C.norm_abs = norm_abs; C.norm = norm;
+    delta_apply_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(C, w, dw_sum, n_src, n_tgt, theta, dtheta_sum,
+                                                                                                        n_theta);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -10,6 +10,10 @@ boundary the accumulated changes are summed over ranks —
     W = clamp(W0 + sum_r dW_r, wmin, wmax); theta = theta0 + sum_r dtheta_r
     normalize()                                             (snn_b200_delta_apply)
 
+On the fused DiehlAndCook2015 kernel the first line costs nothing: the window's epilogue writes dW_r and dtheta_r
+straight into the all-reduce buffer and leaves W0 / theta0 in place (``snn_run_opts_t.delta_w / delta_theta``), and
+the last two lines are one launch (``snn_b200_delta_apply_fused``) — window kernel, all-reduce, apply.
+
 This is "replicas + one exchange", NOT a single-process run at the global batch size: that
 would need the batch-summed dW and dtheta exchanged every timestep.  tests/test_distributed.py
 checks it against the combination of independent oracle replicas.
@@ -32,6 +36,7 @@ class ShardedWindowRunner:
         self.group = process_group
         self._flat: Optional[torch.Tensor] = None
         self._snap: Optional[torch.Tensor] = None
+        self._delta_windows: Optional[bool] = None   # None: not tried yet; False: this graph / tier has no delta window
 
     def _learned(self) -> List[Tuple[object, "_abi.SnnConn"]]:
         """Connections whose weights change inside a window (a learning rule, or the end-of-run normalize),
@@ -80,6 +85,23 @@ class ShardedWindowRunner:
         if self._flat is None or self._flat.numel() != total or self._flat.device != dev:
             self._flat = torch.empty(total, dtype=torch.float32, device=dev)
             self._snap = torch.empty(total, dtype=torch.float32, device=dev)
+        if (dev.type == "cuda" and self._delta_windows is not False and len(learned) == 1 and len(thetas) == 1
+                and int(time / net.dt) > 0 and learned[0][0].w.dim() == 2):
+            # fused path: the window writes dW / dtheta into the all-reduce buffer, W0 / theta0 stay where they are
+            conn, d = learned[0]
+            w, th = conn.w.detach(), thetas[0]
+            dw, dth = self._flat[:w.numel()].view_as(w), self._flat[w.numel():]
+            try:
+                net.run(inputs, time, b200_normalize=False, b200_delta=(dw, dth), **kwargs)
+                self._delta_windows = True
+            except _backend.BackendError:
+                if self._delta_windows:   # it worked before: a real error
+                    raise
+                self._delta_windows = False   # not the fused DiehlAndCook2015 graph / tier: the general path below
+            else:
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+                _backend.delta_apply_fused(w, dw, d.has_clamp, d.wmin, d.wmax, d.has_norm, d.norm_abs, d.norm, theta=th, dtheta_sum=dth)
+                return
         # snapshot W0 / theta0
         off = 0
         views = []

@@ -112,7 +112,7 @@ class Network(torch.nn.Module):
 
         timesteps = int(time / self.dt)  # network.py:356
         self._run_window(
-            inputs, timesteps, normalize=bool(kwargs.get("b200_normalize", True)),
+            inputs, timesteps, normalize=bool(kwargs.get("b200_normalize", True)), delta=kwargs.get("b200_delta", None),
             clamp=kwargs.get("clamp", {}), unclamp=kwargs.get("unclamp", {}),
             injects_v=kwargs.get("injects_v", {}), seed=kwargs.get("one_spike_seed", None), one_step=bool(one_step),
             masks=kwargs.get("masks", {}) or {},
@@ -190,7 +190,7 @@ class Network(torch.nn.Module):
         return out
 
     def _run_window(self, inputs, T: int, normalize: bool, clamp=None, unclamp=None, injects_v=None,
-                    seed: Optional[int] = None, step_offset: int = 0, one_step: bool = False, masks=None) -> None:
+                    seed: Optional[int] = None, step_offset: int = 0, one_step: bool = False, masks=None, delta=None) -> None:
         self._one_step = bool(one_step)
         dev = self._device()
         self._conn_masks = self._stage_conn_masks(masks, dev)
@@ -208,11 +208,15 @@ class Network(torch.nn.Module):
             seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: torch.manual_seed governs it
         self.last_one_spike_seed = seed
 
+        if delta is not None and (self._scripted_required() or T <= 0):
+            raise _backend.BackendError("b200_delta windows run on the fused DiehlAndCook2015 kernel only")
         if self._scripted_required():
             return self._run_scripted(ext, T, normalize, clamps, unclamps, injects, self._conn_masks, bool(one_step))
 
         fused = {name: self._fusable_monitor(m) for name, m in self.monitors.items()}
         if any(layer is None for layer in fused.values()):
+            if delta is not None:
+                raise _backend.BackendError("b200_delta windows run on the fused DiehlAndCook2015 kernel only")
             return self._run_stepwise(ext, T, normalize, clamps, unclamps, injects, seed, step_offset)
 
         rec: Dict[str, Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]] = {}
@@ -234,6 +238,8 @@ class Network(torch.nn.Module):
         opts.tier = int(getattr(self, "force_tier", 0))
         opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset
         opts.one_step = int(self._one_step)
+        if delta is not None:   # multi-GPU window: weight / theta changes go to the caller's all-reduce buffer (include/snn_b200.h)
+            opts.delta_w, opts.delta_theta = delta[0].data_ptr(), delta[1].data_ptr()
         self._launch(net, opts, dev)
         del keep
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 7
+#define SNN_ABI_VERSION 8
 #define SNN_MAX_LAYERS 8
 #define SNN_MAX_CONNS 12
 
@@ -203,6 +203,13 @@ typedef struct snn_run_opts {
     int32_t *err_flag;     /* optional int32 (device memory for the CUDA lib); OR-ed with SNN_ERR_* */
     int32_t one_step;  /* Network.run(one_step=True), network.py:383-396: each layer's input is recomputed from
                           the CURRENT spikes of its sources just before its forward (generic tier only) */
+    /* Multi-GPU windows (the reference has no counterpart).  When delta_w / delta_theta are set
+     * the window leaves the learned weights / adaptive thresholds of the DiehlAndCook2015 graph as they were at the
+     * start and writes what it would have added instead — delta_w[i*n+j] = w_end - w_start, delta_theta[j] =
+     * theta_end - theta_start — straight into the caller's all-reduce buffer (no snapshot, no separate subtraction
+     * pass).  Fused DC2015 kernel (tier 2) only, normalize must be 0; anything else: SNN_ERR_UNSUPPORTED. */
+    float *delta_w;
+    float *delta_theta;
 } snn_run_opts_t;
 
 /*
@@ -273,6 +280,11 @@ int snn_b200_delta_prepare(const float *w, const float *w0, float *dw, size_t co
 int snn_b200_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t n_src, int32_t n_tgt,
                          int32_t has_clamp, float wmin, float wmax, int32_t has_norm, int32_t norm_abs,
                          float norm, void *stream);
+/* The same combine in place for a window run with snn_run_opts_t.delta_w / delta_theta (w still holds the weights of
+ * the window start): w = clamp(w + dw_sum), normalize(), theta = theta + dtheta_sum — one launch.  theta may be NULL. */
+int snn_b200_delta_apply_fused(float *w, const float *dw_sum, int32_t n_src, int32_t n_tgt, int32_t has_clamp, float wmin, float wmax,
+                               int32_t has_norm, int32_t norm_abs, float norm, float *theta, const float *dtheta_sum, int32_t n_theta,
+                               void *stream);
 
 /* Single-operator entry points — the reference's per-object methods, for callers that drive
  * the objects themselves instead of through Network.run:

@@ -47,6 +47,7 @@ typedef struct {
 
 static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
     if (!net || !o || net->abi_version != SNN_ABI_VERSION) return SNN_ERR_BAD_ARG;
+    if (o->delta_w || o->delta_theta) return SNN_ERR_UNSUPPORTED;   /* a device-side shortcut of the multi-GPU combine */
     if (net->n_layers < 0 || net->n_layers > SNN_MAX_LAYERS) return SNN_ERR_BAD_ARG;
     if (net->n_conns < 0 || net->n_conns > SNN_MAX_CONNS) return SNN_ERR_BAD_ARG;
     if (o->T < 0 || o->B <= 0) return SNN_ERR_BAD_ARG;

@@ -107,6 +107,7 @@ runner.run({{"X": shard}}, time=60, one_spike_seed=17 + rank)
 net.reset_state_variables()
 runner.run({{"X": shard}}, time=60, one_spike_seed=27 + rank)
 net.check_errors()
+assert runner._delta_windows is True, "the fused delta window (epilogue writes dW / dtheta) was not taken"
 torch.save({{"w": net.connections[("X", "Ae")].w.detach().cpu(), "theta": net.layers["Ae"].theta.cpu()}}, os.path.join({out!r}, f"rank{{rank}}.pt"))
 dist.destroy_process_group()
 """
@@ -169,3 +170,44 @@ def test_readout_kernels_match_the_torch_formulas():
     assert torch.equal(ev.all_activity(counts.cuda(), a_g, L).cpu(), ev.all_activity(counts, a_c, L))
     pw_g, pw_c = ev.proportion_weighting(counts.cuda(), a_g, p_g, L).cpu(), ev.proportion_weighting(counts, a_c, p_c, L)
     assert (pw_g != pw_c).sum() <= 1   # weighted float sums: a near-tie may fall the other way
+
+
+def test_delta_window_writes_the_change_and_leaves_the_weights():
+    """snn_run_opts_t.delta_w / delta_theta (fused DiehlAndCook2015 kernel): the window writes W_end - W_start and
+    theta_end - theta_start into the caller's buffer and leaves W / theta untouched; snn_b200_delta_apply_fused then
+    equals the snapshot-based combine, bit for bit."""
+    from bindsnet_b200 import _backend
+    from bindsnet_b200.models import DiehlAndCook2015
+
+    def make():
+        torch.manual_seed(3)
+        return DiehlAndCook2015(n_inpt=784, n_neurons=96, batch_size=8, inpt_shape=(1, 28, 28), norm=78.4, theta_plus=0.05).to("cuda")
+
+    x = torch.bernoulli(0.04 * torch.ones(80, 8, 1, 28, 28), generator=torch.Generator().manual_seed(5)).byte().cuda()
+    a, b = make(), make()
+    w0, th0 = a.connections[("X", "Ae")].w.detach().clone(), a.layers["Ae"].theta.clone()
+    a.run({"X": x}, time=80, one_spike_seed=9, b200_normalize=False)
+    a.check_errors()
+    assert _backend.last_tier == 2
+    wb, thb = b.connections[("X", "Ae")].w.detach(), b.layers["Ae"].theta
+    flat = torch.full((wb.numel() + thb.numel(),), float("nan"), device="cuda")
+    dw, dth = flat[:wb.numel()].view_as(wb), flat[wb.numel():]
+    b.run({"X": x}, time=80, one_spike_seed=9, b200_normalize=False, b200_delta=(dw, dth))
+    b.check_errors()
+    assert _backend.last_tier == 2
+    assert torch.equal(wb, w0) and torch.equal(thb, th0), "a delta window must not touch W / theta"
+    wa, tha = a.connections[("X", "Ae")].w.detach(), a.layers["Ae"].theta
+    assert torch.equal(dw, wa - w0) and torch.equal(dth, tha - th0)
+    assert float(dw.abs().sum()) > 0 and float(dth.abs().sum()) > 0, "nothing learned: nothing tested"
+    for lname in ("Ae", "Ai"):   # everything else is written back as usual
+        assert torch.equal(a.layers[lname].v, b.layers[lname].v) and torch.equal(a.layers[lname].s, b.layers[lname].s)
+    # combine: in place == snapshot based
+    ref_w = torch.empty_like(w0)
+    _backend.delta_apply(ref_w, w0, (2.0 * dw).contiguous(), True, 0.0, 1.0, True, 0, 78.4)
+    two = (2.0 * flat).contiguous()
+    _backend.delta_apply_fused(wb, two[:wb.numel()].view_as(wb), True, 0.0, 1.0, True, 0, 78.4, theta=thb, dtheta_sum=two[wb.numel():])
+    assert torch.equal(wb, ref_w) and torch.equal(thb, th0 + 2.0 * dth)
+    # a graph the fused kernel does not take has no delta window
+    c = make(); c.force_tier = 1
+    with pytest.raises(_backend.BackendError):
+        c.run({"X": x}, time=80, one_spike_seed=9, b200_normalize=False, b200_delta=(dw, dth))
