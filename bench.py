@@ -380,8 +380,20 @@ def run_config4(args) -> None:
           "e2e": {"value": B * T / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * B * 1024, "d2h_bytes_per_step": B * 10,
                   "note": "pinned host uint8 spikes -> H2D -> Network.run(reward=1.0) -> output-layer spikes D2H, read on the host every window"},
           "gpu_launches": launches, "clocks": clocks.summary(),
-          "roofline": {"bound": "hbm", "achieved": None, "peak": hbm_peak_gbs()[0], "unit": "GB/s", "frac": None, "traffic": None,
-                       "kernel_ms": ms, "note": "generic tier, latency-bound (grid barriers per step); no algorithmic-bytes figure is defined for this configuration in SURVEY.md §8d"}})
+          "roofline": c4_roofline(B, T, ms)})
+
+
+def c4_roofline(B: int, T: int, ms: float) -> dict:
+    """input spikes as delivered + read and write of both weight tensors per timestep, state
+    resident: B*1024 + 2*(12544*10*4 + 16*1*5*5*4) = 1 137 792 B/step at B = 128."""
+    per_step = B * 1024 + 2 * (12544 * 10 * 4 + 16 * 25 * 4)
+    peak, src = hbm_peak_gbs()
+    ach = per_step * T / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "kernel_ms": ms,
+            "algorithmic_bytes_per_timestep": per_step, "peak_source": src,
+            "note": "generic tier; this configuration is latency / occupancy-bound, not HBM-bound (SURVEY.md 8d: 0.14 us per step at the HBM "
+                    "peak): the limiter is the grid barriers of a step (3) and the per-step streaming of the [B,12544] neuron / trace / "
+                    "rule state (19 MB) through L2, which the algorithmic figure counts as resident"}
 
 
 def main():

@@ -12,7 +12,7 @@ SNN_ABI_VERSION = 8
 SNN_MAX_LAYERS = 8
 SNN_MAX_CONNS = 12
 
-SNN_NODE_INPUT, SNN_NODE_LIF, SNN_NODE_DC, SNN_NODE_IF, SNN_NODE_CURRENT_LIF = 0, 1, 2, 3, 4
+SNN_NODE_INPUT, SNN_NODE_LIF, SNN_NODE_DC, SNN_NODE_IF, SNN_NODE_CURRENT_LIF, SNN_NODE_BOOSTED_LIF, SNN_NODE_MCP = 0, 1, 2, 3, 4, 5, 6
 SNN_CONN_DENSE, SNN_CONN_MCC, SNN_CONN_CONV2D = 0, 1, 2
 SNN_RULE_NONE, SNN_RULE_NOOP, SNN_RULE_POSTPRE, SNN_RULE_WDEP_POSTPRE, SNN_RULE_MCC_POSTPRE, SNN_RULE_MSTDP, SNN_RULE_HEBBIAN = 0, 1, 2, 3, 4, 5, 6
 SNN_REDUCE_SUM, SNN_REDUCE_MEAN = 0, 1

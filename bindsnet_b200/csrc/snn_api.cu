@@ -5,7 +5,7 @@
 
 #include "snn_common.cuh"
 
-int snn_generic_launch(const DevNet &N, cudaStream_t stream);
+int snn_generic_launch(DevNet &N, cudaStream_t stream);
 int snn_fused_dc_supported(const snn_net_t *net, const snn_run_opts_t *opts);
 size_t snn_fused_dc_workspace_bytes(const snn_net_t *net, const snn_run_opts_t *opts);
 int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *ws, size_t ws_bytes,
@@ -26,10 +26,10 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
     if (o->T < 0 || o->B <= 0) return SNN_ERR_BAD_ARG;
     for (int l = 0; l < net->n_layers; ++l) {
         const snn_layer_t &L = net->layers[l];
-        if (L.kind < SNN_NODE_INPUT || L.kind > SNN_NODE_CURRENT_LIF) return SNN_ERR_UNSUPPORTED;
+        if (L.kind < SNN_NODE_INPUT || L.kind > SNN_NODE_MCP) return SNN_ERR_UNSUPPORTED;
         if (L.kind == SNN_NODE_CURRENT_LIF && !L.i) return SNN_ERR_BAD_ARG;
         if (L.n <= 0 || !L.s) return SNN_ERR_BAD_ARG;
-        if (L.kind != SNN_NODE_INPUT && (!L.v || !L.refrac_count)) return SNN_ERR_BAD_ARG;
+        if (L.kind != SNN_NODE_INPUT && (!L.v || (!L.refrac_count && L.kind != SNN_NODE_MCP))) return SNN_ERR_BAD_ARG;
         if (L.kind == SNN_NODE_DC && !L.theta) return SNN_ERR_BAD_ARG;
         if (L.traces && !L.x) return SNN_ERR_BAD_ARG;
         if (L.sum_input && !L.summed) return SNN_ERR_BAD_ARG;
@@ -90,6 +90,11 @@ static size_t layout_generic(const snn_net_t *net, const snn_run_opts_t *o, char
         const bool xp = L.traces && layer_needs_xpub(net, l);
         if (N) N->layers[l].xpub = xp ? (float *)(ws + off) : nullptr;
         if (xp) off += align_up(sizeof(float) * 2 * B * L.n);
+        const bool th = L.kind == SNN_NODE_DC;   // adaptive threshold: decayed value per step parity + batch counters
+        if (N) N->layers[l].thdec = th ? (float *)(ws + off) : nullptr;
+        if (th) off += align_up(sizeof(float) * 2 * L.n);
+        if (N) N->layers[l].thcnt = th ? (int32_t *)(ws + off) : nullptr;
+        if (th) off += align_up(sizeof(int32_t) * 3 * L.n);
         if (N && os) N->any_one_spike = 1;
     }
     if (N) N->total_items = items;
@@ -178,7 +183,6 @@ int snn_b200_run_window(const snn_net_t *net, const snn_run_opts_t *opts, void *
     for (int c = 0; c < net->n_conns; ++c) {
         N.conns[c] = net->conns[c];
         const snn_conn_t &C = net->conns[c];
-        if (C.rule == SNN_RULE_MSTDP || (C.kind == SNN_CONN_CONV2D && C.rule != SNN_RULE_NONE)) N.sync_after_learning = 1;
         if (C.mask) N.any_mask = 1;
     }
     if (cudaMemsetAsync(N.bar, 0, sizeof(unsigned int) * 96, stream) != cudaSuccess) return SNN_ERR_CUDA;

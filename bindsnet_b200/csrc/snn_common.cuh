@@ -22,6 +22,8 @@ struct DevLayer {
     uint32_t *candbits;         // [B][nw]     DC one_spike: threshold crossers of this step
     unsigned long long *keys;   // [2][B]      DC one_spike: arg-max tie-break keys
     float *xpub;                // [2][B][n]   trace published for STDP readers (slot t&1), or NULL
+    float *thdec;               // [2][n]      DC: the decayed adaptive threshold step t used (slot t&1)
+    int32_t *thcnt;             // [3][n]      DC: threshold crossers of step t summed over the batch (slot t%3)
     int32_t nw;                 // ceil(n / 32)
     int32_t item0;              // first work-item index of this layer
 };
@@ -38,9 +40,10 @@ struct DevNet {
     int32_t n_layers, n_conns, learning, T, B, normalize, total_items, any_one_spike;
     int32_t any_mask;             // some connection carries a mask (Network.run(..., masks=...))
     int32_t one_step;             // Network.run(one_step=True): layers in insertion order, inputs from current spikes
-    int32_t sync_after_learning;  // some rule updates weights another CTA gathers from in the next step
-                                  // (MSTDP, conv connections): one more grid barrier per step
     uint32_t seed, step_offset;
+    int32_t nch, cs;              // phases 1 / 2: sample chunks per tile, samples per chunk
+    int32_t p3_total;             // phase 3: number of work units
+    int32_t p3_first[SNN_MAX_CONNS], p3_rc[SNN_MAX_CONNS];   // first unit / row chunks per tile of every connection
     int32_t *err;               // device error flags (may be NULL)
     unsigned int *bar;          // [0] arrival count, [32] generation, [64] abort
     DevLayer layers[SNN_MAX_LAYERS];
@@ -139,6 +142,17 @@ __device__ __forceinline__ bool clif_step(const snn_layer_t &L, float &v, float 
     const bool s = v >= L.thresh;
     if (s) { rc = L.refrac; v = L.reset; }
     if (L.has_lbound && v < L.lbound) v = L.lbound;
+    return s;
+}
+
+// BoostedLIFNodes.forward (nodes.py:620-647): v *= decay, x masked in place while refractory, reset to 0.
+__device__ __forceinline__ bool boosted_step(const snn_layer_t &L, float &v, float &rc, float &xin) {
+    v = v * L.decay;
+    if (rc > 0.0f) xin = 0.0f;
+    rc = rc - L.dt;
+    v = v + xin;
+    const bool s = v >= L.thresh;
+    if (s) { rc = L.refrac; v = 0.0f; }
     return s;
 }
 

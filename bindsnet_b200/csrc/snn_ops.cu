@@ -66,10 +66,8 @@ __global__ void pack_bits_kernel(const uint8_t *__restrict__ s, uint32_t *__rest
 
 __global__ void __launch_bounds__(SNN_GEN_THREADS) conn_update_kernel(const __grid_constant__ DevNet N, int ci) {
     extern __shared__ float smem[];
-    float *s_acc = smem;
-    uint32_t *s_colmask = (uint32_t *)(s_acc + SNN_GEN_WARPS * 32 * 32);
-    __shared__ int32_t s_flag;
-    phase3(N, ci, blockIdx.x, 0, s_acc, s_colmask, &s_flag);
+    const GenSmem M = gen_carve(smem, N.B);
+    phase3(N, ci, blockIdx.x, 0, N.layers[N.conns[ci].src].nw, 0, M);
 }
 
 __global__ void __launch_bounds__(SNN_GEN_THREADS) conn_normalize_kernel(snn_conn_t C, int ns, int nt) {
@@ -183,7 +181,7 @@ int snn_b200_conn_update(const snn_net_t *net, int32_t ci, int32_t B, void *work
         const int warps = B * D.nw;
         pack_bits_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(D.L.s, D.bits, B, D.L.n, D.nw);
     }
-    const size_t smem = sizeof(float) * SNN_GEN_WARPS * 32 * 32 + sizeof(uint32_t) * 32 * (size_t)((B + 31) / 32);
+    const size_t smem = gen_smem_bytes(B);
     cudaFuncSetAttribute(conn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     conn_update_kernel<<<N.layers[C.tgt].nw, SNN_GEN_THREADS, smem, stream>>>(N, ci);
     return cuda_rc(cudaGetLastError());

@@ -41,7 +41,8 @@ def fill_layer(d: "_abi.SnnLayer", layer, name: str, B: int) -> None:
     d.s = _ptr(_as_u8(layer.s))
     if d.kind != _abi.SNN_NODE_INPUT:
         d.v = _ptr(_state(layer.v, "v", name))
-        d.refrac_count = _ptr(_state(layer.refrac_count, "refrac_count", name))
+        if d.kind != _abi.SNN_NODE_MCP:
+            d.refrac_count = _ptr(_state(layer.refrac_count, "refrac_count", name))
     if d.kind == _abi.SNN_NODE_DC:
         d.theta = _ptr(_state(layer.theta, "theta", name))
     if d.kind == _abi.SNN_NODE_CURRENT_LIF:

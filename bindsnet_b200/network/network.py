@@ -302,7 +302,8 @@ class Network(torch.nn.Module):
         from ..learning import MCC_learning as ML
         from . import nodes as N, topology as Tp
 
-        builtin_nodes = (N.Input, N.LIFNodes, N.DiehlAndCookNodes, N.IFNodes, N.CurrentLIFNodes, N.AdaptiveLIFNodes)
+        builtin_nodes = (N.Input, N.LIFNodes, N.DiehlAndCookNodes, N.IFNodes, N.CurrentLIFNodes, N.AdaptiveLIFNodes, N.BoostedLIFNodes,
+                         N.McCullochPitts)
         for layer in self.layers.values():
             if type(layer) not in builtin_nodes and (layer.kind is None or type(layer).forward is not N.Nodes.forward):
                 return True
@@ -393,8 +394,10 @@ class Network(torch.nn.Module):
 
         from .nodes import CurrentLIFNodes, IFNodes
 
+        from .nodes import BoostedLIFNodes
+
         stock = {Nodes.reset_state_variables, LIFNodes.reset_state_variables, DiehlAndCookNodes.reset_state_variables,
-                 CurrentLIFNodes.reset_state_variables}
+                 CurrentLIFNodes.reset_state_variables, BoostedLIFNodes.reset_state_variables}
         zeros, fills = [], []
         for layer in self.layers.values():
             if type(layer).reset_state_variables in stock and hasattr(layer, "_reset_plan"):

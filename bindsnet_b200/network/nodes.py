@@ -482,8 +482,101 @@ class AdaptiveLIFNodes(DiehlAndCookNodes):
         )
 
 
-McCullochPitts = _unsupported("McCullochPitts", "nodes.py:231-305")
-BoostedLIFNodes = _unsupported("BoostedLIFNodes", "nodes.py:562-678")
+class BoostedLIFNodes(Nodes):
+    """LIF without rest / reset / lower bound: voltages decay towards 0 and reset to 0 (reference: nodes.py:562-678;
+    forward :620-647)."""
+
+    kind = _abi.SNN_NODE_BOOSTED_LIF
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        thresh: Scalar = 13.0,
+        refrac: Scalar = 5,
+        tc_decay: Scalar = 100.0,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive,
+            tc_trace=tc_trace, trace_scale=trace_scale, sum_input=sum_input,
+        )
+        self.register_buffer("thresh", torch.as_tensor(thresh, dtype=torch.float))
+        self.register_buffer("refrac", torch.as_tensor(refrac))
+        self.register_buffer("tc_decay", torch.as_tensor(tc_decay, dtype=torch.float))
+        self.register_buffer("decay", torch.zeros(()))
+        self.register_buffer("v", torch.zeros(0))
+        self.register_buffer("refrac_count", torch.zeros(0))
+
+    def reset_state_variables(self) -> None:
+        """nodes.py:649-656."""
+        super().reset_state_variables()
+        self.v.fill_(0)
+        self.refrac_count.zero_()
+
+    def _reset_plan(self):
+        zeros, fills = super()._reset_plan()
+        return zeros + [self.v, self.refrac_count], fills
+
+    def compute_decays(self, dt) -> None:
+        """nodes.py:658-666."""
+        super().compute_decays(dt=dt)
+        self.decay = _exp_decay(self.dt, self.tc_decay)
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:668-678."""
+        super().set_batch_size(batch_size=batch_size)
+        dev = self.v.device
+        self.v = torch.zeros(batch_size, *self.shape, device=dev)
+        self.refrac_count = torch.zeros_like(self.v)
+
+    def _fill_desc(self, d) -> None:
+        super()._fill_desc(d)
+        d.decay = _scalar(self.decay, "tc_decay")
+        d.thresh = _scalar(self.thresh, "thresh")
+        d.refrac = _scalar(self.refrac, "refrac")
+
+
+class McCullochPitts(Nodes):
+    """McCulloch-Pitts neurons: the voltage IS the input of the step, a spike wherever it reaches the threshold; no
+    memory, no refractory period (reference: nodes.py:231-305; forward :278-288)."""
+
+    kind = _abi.SNN_NODE_MCP
+
+    def __init__(
+        self,
+        n: Optional[int] = None,
+        shape: Optional[Iterable[int]] = None,
+        traces: bool = False,
+        traces_additive: bool = False,
+        tc_trace: Scalar = 20.0,
+        trace_scale: Scalar = 1.0,
+        sum_input: bool = False,
+        thresh: Scalar = 1.0,
+        **kwargs,
+    ) -> None:
+        super().__init__(
+            n=n, shape=shape, traces=traces, traces_additive=traces_additive,
+            tc_trace=tc_trace, trace_scale=trace_scale, sum_input=sum_input,
+        )
+        self.register_buffer("thresh", torch.as_tensor(thresh, dtype=torch.float))
+        self.register_buffer("v", torch.zeros(0))
+
+    def set_batch_size(self, batch_size) -> None:
+        """nodes.py:297-305."""
+        super().set_batch_size(batch_size=batch_size)
+        self.v = torch.zeros(batch_size, *self.shape, device=self.v.device)
+
+    def _fill_desc(self, d) -> None:
+        super()._fill_desc(d)
+        d.thresh = _scalar(self.thresh, "thresh")
+
+
 IzhikevichNodes = _unsupported("IzhikevichNodes", "nodes.py:1147-1316")
 CSRMNodes = _unsupported("CSRMNodes", "nodes.py:1319-1552")
 SRM0Nodes = _unsupported("SRM0Nodes", "nodes.py:1555-1701")

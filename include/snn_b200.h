@@ -45,6 +45,8 @@ extern "C" {
                             (the same arithmetic: decay, theta decay, gated input, threshold + theta, theta += plus * sum_b s) */
 #define SNN_NODE_IF 3         /* IFNodes          nodes.py:308-415: no leak, gate taken before the refractory decrement */
 #define SNN_NODE_CURRENT_LIF 4 /* CurrentLIFNodes nodes.py:681-826: decaying synaptic current i, gate taken after the decrement */
+#define SNN_NODE_BOOSTED_LIF 5 /* BoostedLIFNodes nodes.py:562-678: LIF without rest / reset / lbound: v *= decay, reset to 0 */
+#define SNN_NODE_MCP 6         /* McCullochPitts  nodes.py:231-305: v = x, s = v >= thresh; no refractory state (refrac_count NULL) */
 
 /* ---- connection kinds (reference: bindsnet/network/topology.py) ---- */
 #define SNN_CONN_DENSE 0 /* Connection: s.float() @ w + b                topology.py:332-346 */

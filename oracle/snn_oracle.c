@@ -54,11 +54,11 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
     for (int l = 0; l < net->n_layers; ++l) {
         const snn_layer_t *L = &net->layers[l];
         if (L->n <= 0 || !L->s) return SNN_ERR_BAD_ARG;
-        if (L->kind != SNN_NODE_INPUT && (!L->v || !L->refrac_count)) return SNN_ERR_BAD_ARG;
+        if (L->kind != SNN_NODE_INPUT && (!L->v || (!L->refrac_count && L->kind != SNN_NODE_MCP))) return SNN_ERR_BAD_ARG;
         if (L->kind == SNN_NODE_DC && !L->theta) return SNN_ERR_BAD_ARG;
         if (L->traces && !L->x) return SNN_ERR_BAD_ARG;
         if (L->sum_input && !L->summed) return SNN_ERR_BAD_ARG;
-        if (L->kind < 0 || L->kind > SNN_NODE_CURRENT_LIF) return SNN_ERR_UNSUPPORTED;
+        if (L->kind < 0 || L->kind > SNN_NODE_MCP) return SNN_ERR_UNSUPPORTED;
         if (L->kind == SNN_NODE_CURRENT_LIF && !L->i) return SNN_ERR_BAD_ARG;
     }
     for (int c = 0; c < net->n_conns; ++c) {
@@ -241,6 +241,27 @@ static void layer_forward(const snn_net_t *net, int l, const snn_run_opts_t *o, 
                 if (L->has_lbound && v < L->lbound) v = L->lbound;    /* :788-789 */
                 L->v[k] = v; L->i[k] = ic; L->refrac_count[k] = rc; L->s[k] = (uint8_t)s;
                 trace_and_sum(L, k, s, cur[k]);                       /* :791 */
+            }
+        } else if (L->kind == SNN_NODE_BOOSTED_LIF) {
+            /* BoostedLIFNodes.forward (nodes.py:620-647): no rest, no reset value, no lower bound */
+            for (size_t k = 0; k < BN; ++k) {
+                float v = L->v[k] * L->decay;                         /* :628 */
+                float xin = cur[k];
+                if (L->refrac_count[k] > 0.0f) xin = 0.0f;            /* :632 (in place on x) */
+                float rc = L->refrac_count[k] - L->dt;                /* :635 */
+                v = v + xin;                                          /* :638 */
+                int s = v >= L->thresh;                               /* :641 */
+                if (s) { rc = L->refrac; v = 0.0f; }                  /* :644-645 */
+                L->v[k] = v; L->refrac_count[k] = rc; L->s[k] = (uint8_t)s;
+                trace_and_sum(L, k, s, xin);                          /* :647 (masked x) */
+            }
+        } else if (L->kind == SNN_NODE_MCP) {
+            /* McCullochPitts.forward (nodes.py:278-288) */
+            for (size_t k = 0; k < BN; ++k) {
+                const float v = cur[k];                               /* :285 */
+                int s = v >= L->thresh;                               /* :286 */
+                L->v[k] = v; L->s[k] = (uint8_t)s;
+                trace_and_sum(L, k, s, cur[k]);                       /* :288 */
             }
         } else { /* SNN_NODE_DC: DiehlAndCookNodes.forward (nodes.py:1069-1111) */
             uint8_t *cand = ws->cand;

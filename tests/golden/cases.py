@@ -156,6 +156,24 @@ def alif_postpre(ns, inputs=None):
     return net, (inputs or x), kw, T
 
 
+# BoostedLIFNodes (nodes.py:562-678) and McCullochPitts (nodes.py:231-305) as learned targets; the McCulloch-Pitts layer
+# also drives a second population, so its spikes are exercised as a source
+def boosted_postpre(ns, inputs=None):
+    Y = ns.nodes.BoostedLIFNodes(n=36, traces=True, sum_input=True, thresh=9.0, refrac=3, tc_decay=30.0)
+    net, x, kw, T = _one_layer_model(ns, Y, 67, 68)
+    return net, (inputs or x), kw, T
+
+
+def mcp_postpre(ns, inputs=None):
+    Y = ns.nodes.McCullochPitts(n=36, traces=True, sum_input=True, thresh=7.0)
+    net, x, kw, T = _one_layer_model(ns, Y, 69, 70)
+    Z = ns.nodes.LIFNodes(n=20, traces=True, thresh=-58.0, rest=-65.0, reset=-64.0, refrac=2, tc_decay=60.0)
+    C2 = ns.topology.Connection(source=Y, target=Z, w=_w((36, 20), 71, 3.0), update_rule=ns.learning.PostPre, nu=(1e-3, 1e-2),
+                                reduction=torch.sum, wmin=0.0, wmax=4.0)
+    net.add_layer(Z, "Z"); net.add_connection(C2, "Y", "Z")
+    return net, (inputs or x), kw, T
+
+
 # WeightDependentPostPre, mean reduction
 def lif_wdep(ns, inputs=None):
     net = ns.Network(dt=1.0)
@@ -438,6 +456,8 @@ CASES = {
     "if_postpre": if_postpre,
     "clif_postpre": clif_postpre,
     "alif_postpre": alif_postpre,
+    "boosted_postpre": boosted_postpre,
+    "mcp_postpre": mcp_postpre,
     "lif_clamps": lif_clamps,
     "dc2015_multi": dc2015_multi,
     "dc2015_onespike": dc2015_onespike,
