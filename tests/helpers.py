@@ -94,7 +94,7 @@ def run_case_oracle(name: str, dense: int = 0):
     return fx, snapshot(net), spike_counts(net, T)
 
 
-def assert_close_to_golden(fx: Fixture, state, counts, rtol_w=1e-4, atol_state=1e-4, rtol_state=1e-5, count_slack=0):
+def assert_close_to_golden(fx: Fixture, state, counts, rtol_w=1e-4, atol_state=1e-4, rtol_state=1e-5, count_slack=0, atol_w=2e-6):
     """The north_star's parity statement: final weights within 1e-4 relative, voltages/traces
     within an fp32 tolerance, spike rasters compared by per-neuron count."""
     z = fx.z
@@ -104,10 +104,15 @@ def assert_close_to_golden(fx: Fixture, state, counts, rtol_w=1e-4, atol_state=1
                 ref = z[key]
                 err = np.abs(val - ref).max() / max(np.abs(ref).max(), 1e-12)
                 assert err <= rtol_w, f"{fx.name} {key}: max rel err {err:.3e}"
+                # element-wise as well: |d| <= rtol * |ref| + atol, atol = a few fp32 ulps of the largest weight
+                bad = np.abs(val - ref) > rtol_w * np.abs(ref) + atol_w * max(np.abs(ref).max(), 1e-12)
+                assert not bad.any(), f"{fx.name} {key}: {bad.sum()} entries beyond the element-wise tolerance, max |d| {np.abs(val - ref).max():.3e}"
             else:  # large case: subsampled rows + column sums
                 ref = z[key + "_rows8"]
                 err = np.abs(val[::8] - ref).max() / max(np.abs(ref).max(), 1e-12)
                 assert err <= rtol_w, f"{fx.name} {key} rows: max rel err {err:.3e}"
+                bad = np.abs(val[::8] - ref) > rtol_w * np.abs(ref) + atol_w * max(np.abs(ref).max(), 1e-12)
+                assert not bad.any(), f"{fx.name} {key} rows: {bad.sum()} entries beyond the element-wise tolerance"
                 cs = z[key + "_colsum"]
                 errc = np.abs(val.astype(np.float64).sum(0) - cs).max() / np.abs(cs).max()
                 assert errc <= rtol_w, f"{fx.name} {key} colsum: {errc:.3e}"
