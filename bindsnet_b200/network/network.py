@@ -187,6 +187,16 @@ class Network(torch.nn.Module):
             if tuple(m.shape) != tuple(conn.w.shape):
                 raise ValueError(f"mask for {key} has shape {tuple(m.shape)}, weights {tuple(conn.w.shape)}")
             out[key] = (m != 0).to(dev, torch.uint8).contiguous()
+        # a connection with a structural mask of its own (LocalConnection.update, topology.py:1457-1469) uses it
+        # whenever the caller passes none for it
+        for key, conn in self.connections.items():
+            own = getattr(conn, "mask", None)
+            if key not in out and isinstance(conn, Connection) and isinstance(own, torch.Tensor):
+                cache = getattr(conn, "_b200_mask_u8", None)
+                if cache is None or cache.device != dev or cache.shape != own.shape:
+                    cache = (own != 0).to(dev, torch.uint8).contiguous()
+                    conn._b200_mask_u8 = cache
+                out[key] = cache
         return out
 
     def _run_window(self, inputs, T: int, normalize: bool, clamp=None, unclamp=None, injects_v=None,

@@ -327,6 +327,74 @@ class MulticompartmentConnection(AbstractMulticompartmentConnection):
         self._weight()._fill_desc(d, dt, self.manual_update)
 
 
+class LocalConnection(Connection):
+    """Locally connected synapses (reference: topology.py:1304-1484): a dense ``[source.n, target.n]`` matrix that is
+    non-zero only inside each target neuron's receptive field.  The reference keeps it dense too — ``compute`` is the
+    plain matrix product (:1441-1455) — and holds the structure with a mask of the initially-zero weights that
+    ``update`` passes on when the caller gives none (:1457-1469), so here it IS a dense ``Connection`` whose plan always
+    carries that mask; ``normalize`` divides by the plain column sum (:1471-1479) and ``norm`` is scaled by the kernel
+    size (:1437-1438).  Target neuron ``f * conv_prod + c`` is filter ``f`` at receptive field ``c``."""
+
+    def __init__(
+        self,
+        source: Nodes,
+        target: Nodes,
+        kernel_size,
+        stride,
+        n_filters: int,
+        nu: Optional[Union[float, Sequence[float], Sequence[torch.Tensor]]] = None,
+        reduction: Optional[callable] = None,
+        weight_decay: float = 0.0,
+        w_dtype: torch.dtype = torch.float32,
+        **kwargs,
+    ) -> None:
+        kernel_size, stride = _pair(kernel_size), _pair(stride)
+        shape = kwargs.get("input_shape", None)
+        if shape is None:
+            shape = _pair(int(np.sqrt(source.n)))                                  # topology.py:1370-1373
+        if tuple(kernel_size) == tuple(shape):
+            conv_size = (1, 1)
+        else:
+            conv_size = (int((shape[0] - kernel_size[0]) / stride[0]) + 1, int((shape[1] - kernel_size[1]) / stride[1]) + 1)
+        conv_prod, kernel_prod = int(np.prod(conv_size)), int(np.prod(kernel_size))
+        assert target.n == n_filters * conv_prod, f"Total neurons in target layer must be {n_filters * conv_prod}. Got {target.n}."
+        # topology.py:1393-1407 — the index arithmetic is the reference's (including `k1 * shape[0]`)
+        c1, c2, k1, k2 = np.meshgrid(np.arange(conv_size[0]), np.arange(conv_size[1]), np.arange(kernel_size[0]),
+                                     np.arange(kernel_size[1]), indexing="ij")
+        loc = c1 * stride[0] * shape[1] + c2 * stride[1] + k1 * shape[0] + k2      # [c1, c2, k1, k2]
+        locations = torch.from_numpy(loc.transpose(2, 3, 0, 1).reshape(kernel_prod, conv_prod).astype(np.int64))
+        w = kwargs.get("w", None)
+        if w is None:
+            # topology.py:1410-1423: random weights inside the receptive fields only
+            lo, hi = kwargs.get("wmin", -np.inf), kwargs.get("wmax", np.inf)
+            w = torch.zeros(source.n, target.n)
+            cols = (torch.arange(n_filters).view(-1, 1, 1) * conv_prod + torch.arange(conv_prod).view(1, 1, -1)).expand(n_filters, kernel_prod, conv_prod)
+            rows = locations.view(1, kernel_prod, conv_prod).expand(n_filters, kernel_prod, conv_prod)
+            w[rows.reshape(-1), cols.reshape(-1)] = torch.rand(n_filters * kernel_prod * conv_prod)
+            if np.isinf(lo) or np.isinf(hi):
+                w = torch.clamp(w, lo, hi)
+            else:
+                w = lo + w * (hi - lo)
+            kwargs = dict(kwargs, w=w)
+        kwargs.setdefault("b", torch.zeros(target.n))                              # topology.py:1433
+        super().__init__(source, target, nu=nu, reduction=reduction, weight_decay=weight_decay, w_dtype=w_dtype, **kwargs)
+        self.kernel_size, self.stride, self.n_filters, self.conv_size = kernel_size, stride, n_filters, conv_size
+        self.register_buffer("locations", locations)
+        self.register_buffer("mask", self.w == 0)                                  # topology.py:1431
+        if self.norm is not None:
+            self.norm = self.norm * kernel_prod                                    # topology.py:1437-1438
+
+    def update(self, **kwargs) -> None:
+        """topology.py:1457-1469."""
+        if kwargs.get("mask", None) is None:
+            kwargs["mask"] = self.mask
+        super().update(**kwargs)
+
+    def _fill_desc(self, d: "_abi.SnnConn", dt: float, rule: bool = True) -> None:
+        super()._fill_desc(d, dt, rule)
+        d.norm_abs = 0   # w *= norm / w.sum(0)  (topology.py:1476-1479)
+
+
 def _unsupported(name: str, where: str):
     class _Unsupported:
         __doc__ = f"``{name}`` (reference: {where}) — not on the accelerated path (SURVEY.md §8f)."
@@ -346,7 +414,6 @@ Conv3dConnection = _unsupported("Conv3dConnection", "topology.py:847-1025")
 MaxPool1dConnection = _unsupported("MaxPool1dConnection", "topology.py:1028-1121")
 MaxPool2dConnection = _unsupported("MaxPool2dConnection", "topology.py:1124-1211")
 MaxPoo3dConnection = _unsupported("MaxPoo3dConnection", "topology.py:1214-1301")
-LocalConnection = _unsupported("LocalConnection", "topology.py:1304-1484")
 LocalConnection1D = _unsupported("LocalConnection1D", "topology.py:1487-1620")
 LocalConnection2D = _unsupported("LocalConnection2D", "topology.py:1623-1767")
 LocalConnection3D = _unsupported("LocalConnection3D", "topology.py:1770-1917")

@@ -174,6 +174,22 @@ def mcp_postpre(ns, inputs=None):
     return net, (inputs or x), kw, T
 
 
+# LocalConnection (topology.py:1304-1484): dense weights confined to receptive fields by the connection's own mask,
+# plain-sum normalisation scaled by the kernel size.  Batch size 1: the reference's compute views the result as
+# target.shape (topology.py:1455), which fails for larger batches
+def local_postpre(ns, inputs=None):
+    T, B = 120, 1
+    net = ns.Network(dt=1.0)
+    X = ns.nodes.Input(n=64, traces=True)
+    Y = ns.nodes.LIFNodes(n=72, traces=True, thresh=-60.0, rest=-65.0, reset=-64.0, refrac=2, tc_decay=50.0)
+    probe = ns.topology.LocalConnection(X, Y, kernel_size=3, stride=1, n_filters=2)      # default init: only its mask is used
+    w = _w((64, 72), 73, 0.9) * (~probe.mask.bool()).float()
+    C = ns.topology.LocalConnection(X, Y, kernel_size=3, stride=1, n_filters=2, w=w, update_rule=ns.learning.PostPre, nu=(2e-3, 2e-2),
+                                    reduction=torch.sum, wmin=0.0, wmax=1.0, norm=0.35)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y"); net.add_connection(C, "X", "Y")
+    return net, (inputs or {"X": _bernoulli_inputs(T, B, (64,), 0.2, 74)}), {}, T
+
+
 # WeightDependentPostPre, mean reduction
 def lif_wdep(ns, inputs=None):
     net = ns.Network(dt=1.0)
@@ -457,6 +473,7 @@ CASES = {
     "clif_postpre": clif_postpre,
     "alif_postpre": alif_postpre,
     "boosted_postpre": boosted_postpre,
+    "local_postpre": local_postpre,
     "mcp_postpre": mcp_postpre,
     "lif_clamps": lif_clamps,
     "dc2015_multi": dc2015_multi,
