@@ -8,13 +8,14 @@ from __future__ import annotations
 
 import ctypes as C
 
-SNN_ABI_VERSION = 8
+SNN_ABI_VERSION = 9
 SNN_MAX_LAYERS = 8
 SNN_MAX_CONNS = 12
 
 SNN_NODE_INPUT, SNN_NODE_LIF, SNN_NODE_DC, SNN_NODE_IF, SNN_NODE_CURRENT_LIF, SNN_NODE_BOOSTED_LIF, SNN_NODE_MCP = 0, 1, 2, 3, 4, 5, 6
 SNN_CONN_DENSE, SNN_CONN_MCC, SNN_CONN_CONV2D = 0, 1, 2
 SNN_RULE_NONE, SNN_RULE_NOOP, SNN_RULE_POSTPRE, SNN_RULE_WDEP_POSTPRE, SNN_RULE_MCC_POSTPRE, SNN_RULE_MSTDP, SNN_RULE_HEBBIAN = 0, 1, 2, 3, 4, 5, 6
+SNN_RULE_MSTDPET = 7
 SNN_REDUCE_SUM, SNN_REDUCE_MEAN = 0, 1
 SNN_EXT_NONE, SNN_EXT_U8, SNN_EXT_F32 = 0, 1, 2
 SNN_W_DENSE, SNN_W_DIAG, SNN_W_OFFDIAG = 0, 1, 2
@@ -122,6 +123,10 @@ class SnnConn(C.Structure):
         ("mst_spre", C.c_void_p),
         ("mst_spost", C.c_void_p),
         ("mask", C.c_void_p),
+        ("e_trace", C.c_void_p),
+        ("e_trace_decay", C.c_float),
+        ("tc_e_trace", C.c_float),
+        ("et_coef", C.c_float),
     ]
 
 

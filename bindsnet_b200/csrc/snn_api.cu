@@ -40,7 +40,7 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
         const snn_conn_t &C = net->conns[c];
         if (C.src < 0 || C.src >= net->n_layers || C.tgt < 0 || C.tgt >= net->n_layers || !C.w) return SNN_ERR_BAD_ARG;
         if (net->layers[C.tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
-        if (C.rule < SNN_RULE_NONE || C.rule > SNN_RULE_HEBBIAN) return SNN_ERR_UNSUPPORTED;
+        if (C.rule < SNN_RULE_NONE || C.rule > SNN_RULE_MSTDPET) return SNN_ERR_UNSUPPORTED;
         if (C.kind < SNN_CONN_DENSE || C.kind > SNN_CONN_CONV2D) return SNN_ERR_UNSUPPORTED;
         if (C.kind == SNN_CONN_CONV2D) {
             const snn_layer_t &S = net->layers[C.src], &G = net->layers[C.tgt];
@@ -48,6 +48,10 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
             if (C.kh < 1 || C.kw < 1 || C.sh < 1 || C.sw < 1 || C.dh < 1 || C.dw < 1) return SNN_ERR_BAD_ARG;
             if (C.rule == SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
             if (SNN_RULE_IS_STDP(C.rule) && (C.dh != 1 || C.dw != 1)) return SNN_ERR_UNSUPPORTED;   // im2col_indices ignores dilation
+        }
+        if (C.rule == SNN_RULE_MSTDPET) {   // dense, batch size 1 (learning.py:2187-2249)
+            if (C.kind != SNN_CONN_DENSE || o->B != 1) return SNN_ERR_UNSUPPORTED;
+            if (!C.p_plus || !C.p_minus || !C.mst_spre || !C.mst_spost || !C.e_trace) return SNN_ERR_BAD_ARG;
         }
         if (C.rule == SNN_RULE_MSTDP) {
             if (!C.p_plus || !C.p_minus) return SNN_ERR_BAD_ARG;
@@ -57,7 +61,7 @@ static int validate(const snn_net_t *net, const snn_run_opts_t *o) {
         }
         if (SNN_RULE_IS_STDP(C.rule) && (!net->layers[C.src].traces || !net->layers[C.tgt].traces))
             return SNN_ERR_BAD_ARG;
-        if (C.mask && (C.kind != SNN_CONN_DENSE || C.rule == SNN_RULE_MSTDP)) return SNN_ERR_UNSUPPORTED;
+        if (C.mask && (C.kind != SNN_CONN_DENSE || SNN_RULE_IS_MSTDP(C.rule))) return SNN_ERR_UNSUPPORTED;
     }
     return SNN_OK;
 }
@@ -101,7 +105,7 @@ static size_t layout_generic(const snn_net_t *net, const snn_run_opts_t *o, char
     // second slot of every MSTDP rule's state (DevMstdp)
     for (int c = 0; c < net->n_conns; ++c) {
         const snn_conn_t &C = net->conns[c];
-        if (C.rule != SNN_RULE_MSTDP) continue;
+        if (!SNN_RULE_IS_MSTDP(C.rule)) continue;
         const size_t ns = (size_t)net->layers[C.src].n, nt = (size_t)net->layers[C.tgt].n;
         auto take = [&](size_t bytes) { char *p = ws ? ws + off : nullptr; off += align_up(bytes); return p; };
         char *pp = take(sizeof(float) * B * ns), *pm = take(sizeof(float) * B * nt);
@@ -125,7 +129,7 @@ extern "C" {
 int snn_b200_abi_version(void) { return SNN_ABI_VERSION; }
 
 const char *snn_b200_build_info(void) {
-    return "libsnn_b200 sm_100a (generic window + fused DC2015 windows v1/v2), ABI " "7" ", built " __DATE__ " " __TIME__;
+    return "libsnn_b200 sm_100a (generic window + fused DC2015 windows v1/v2), ABI " "9" ", built " __DATE__ " " __TIME__;
 }
 
 int snn_b200_last_launch_count(void) { return g_last_launches; }

@@ -45,6 +45,7 @@ struct DevNet {
     int32_t p3_total;             // phase 3: number of work units
     int32_t p3_first[SNN_MAX_CONNS], p3_rc[SNN_MAX_CONNS];   // first unit / row chunks per tile of every connection
     int32_t *err;               // device error flags (may be NULL)
+    long long *prof;            // profiling only (env SNN_B200_GPROF): [grid][8] phase cycles of thread 0
     unsigned int *bar;          // [0] arrival count, [32] generation, [64] abort
     DevLayer layers[SNN_MAX_LAYERS];
     snn_conn_t conns[SNN_MAX_CONNS];

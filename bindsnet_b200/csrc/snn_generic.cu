@@ -16,6 +16,9 @@
 //            (learning.py / MCC_learning.py); dense MSTDP by source tiles; conv rules spread over the grid
 //   barrier  (+ masks + barrier when Network.run got masks)
 // After the last step: theta, normalize() by tiles (network.py:464-465).
+#include <cstdio>
+#include <cstdlib>
+
 #include "snn_phases.cuh"
 
 namespace {
@@ -34,6 +37,8 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int G = gridDim.x;
     const int nch = N.nch;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();   // phase timers (profiling only)
+    #define GPROF(k) { if (N.prof && threadIdx.x == 0) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
 
     // prologue: pack the incoming spike state s(-1) into slot 1, clear the arg-max keys and the theta counters
     for (int item = blockIdx.x; item < N.total_items; item += G) {
@@ -53,7 +58,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
         if (N.learning && (N.T & 1))
             for (int c = 0; c < N.n_conns; ++c) {
                 const snn_conn_t &C = N.conns[c];
-                if (C.tgt != li || C.rule != SNN_RULE_MSTDP) continue;
+                if (C.tgt != li || !SNN_RULE_IS_MSTDP(C.rule)) continue;
                 const DevMstdp &Ms = N.mst[c];
                 const size_t ns = (size_t)N.layers[C.src].L.n, nt = (size_t)D.L.n, Bz = (size_t)N.B;
                 const size_t start = (size_t)tile * SNN_GEN_THREADS + threadIdx.x, stride = (size_t)D.nw * SNN_GEN_THREADS;
@@ -66,6 +71,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
             }
     }
     if (!grid_barrier(N.bar, G, N.err)) return;
+    GPROF(7)
 
     for (int t = 0; t < N.T; ++t) {
         if (N.one_step) {
@@ -86,15 +92,19 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                 phase1(N, li, tile, u % nch, t, M);
             }
         }
+        GPROF(0)
         if (N.any_one_spike && !N.one_step) {
             if (!grid_barrier(N.bar, G, N.err)) return;
+            GPROF(1)
             for (int u = blockIdx.x; u < N.total_items * nch; u += G) {
                 int li, tile; item_of(N, u / nch, li, tile);
                 const snn_layer_t &L = N.layers[li].L;
                 if (L.kind == SNN_NODE_DC && L.one_spike) phase2(N, li, tile, u % nch, t);
             }
+            GPROF(2)
         }
         if (!grid_barrier(N.bar, G, N.err)) return;
+        GPROF(3)
         if (N.learning) {
             for (int u = blockIdx.x; u < N.p3_total; u += G) {
                 int c = 0;
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                     if (N.p3_rc[cc] > 0 && u >= N.p3_first[cc]) c = cc;
                 const snn_conn_t &C = N.conns[c];
                 const int v = u - N.p3_first[c];
-                if (C.rule == SNN_RULE_MSTDP) {   // dense MSTDP: by source tiles
+                if (SNN_RULE_IS_MSTDP(C.rule)) {   // dense MSTDP / MSTDPET: by source tiles
                     phase3_mstdp_dense(N, c, v, t, M);
                 } else {
                     const int rcn = N.p3_rc[c], tile = v / rcn, rc = v - tile * rcn;
@@ -111,10 +121,13 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                     phase3(N, c, tile, (int)((long long)rc * nwS / rcn), (int)((long long)(rc + 1) * nwS / rcn), t, M);
                 }
             }
+            GPROF(4)
             for (int c = 0; c < N.n_conns; ++c)
                 if (N.conns[c].kind == SNN_CONN_CONV2D && N.conns[c].rule != SNN_RULE_NONE) phase3_conv(N, c, blockIdx.x, G, t, M);
+            GPROF(5)
             // the units of the learning phase are not the units that gather from the weights in the next step
             if (!grid_barrier(N.bar, G, N.err)) return;
+            GPROF(6)
         }
         if (N.any_mask) {   // connection masks apply after the update, learning or not (topology.py:127-131)
             for (int item = blockIdx.x; item < N.total_items; item += G) {
@@ -128,6 +141,8 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
         }
     }
 
+    if (N.prof && threadIdx.x == 0)
+        for (int k = 0; k < 8; ++k) N.prof[blockIdx.x * 8 + k] = pc[k];
     // theta of the last step (the counters were complete at that step's barrier)
     if (N.T > 0)
         for (int item = blockIdx.x; item < N.total_items; item += G) {
@@ -184,7 +199,7 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
         N.p3_rc[c] = 0;
         if (!N.learning || C.rule == SNN_RULE_NONE || C.kind == SNN_CONN_CONV2D) continue;
         const int nwS = N.layers[C.src].nw, nwT = N.layers[C.tgt].nw;
-        if (C.rule == SNN_RULE_MSTDP) { N.p3_rc[c] = 1; p3 += nwS; continue; }
+        if (SNN_RULE_IS_MSTDP(C.rule)) { N.p3_rc[c] = 1; p3 += nwS; continue; }
         int rc = ceil_div(cap, nwT);
         const int rc_max = ceil_div(nwS, SNN_GEN_WARPS);
         if (rc > rc_max) rc = rc_max;
@@ -200,6 +215,28 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
         if (N.learning && N.conns[c].kind == SNN_CONN_CONV2D && N.conns[c].rule != SNN_RULE_NONE) conv_rule = true;
     int grid = conv_rule ? cap : (int)(units < cap ? units : cap);
     if (grid < 1) grid = 1;
+    static long long *prof_buf = nullptr;   // debug only (env SNN_B200_GPROF): per-phase cycles of thread 0 of every CTA
+    const bool prof = getenv("SNN_B200_GPROF") != nullptr;
+    if (prof) {
+        if (!prof_buf && cudaMalloc(&prof_buf, sizeof(long long) * 8 * 4096) != cudaSuccess) return (int)cudaErrorMemoryAllocation;
+        cudaMemsetAsync(prof_buf, 0, sizeof(long long) * 8 * 4096, stream);
+        N.prof = prof_buf;
+    }
     void *args[] = {(void *)&N};
-    return (int)cudaLaunchCooperativeKernel((void *)snn_generic_window, dim3(grid), dim3(SNN_GEN_THREADS), args, smem, stream);
+    const int rc = (int)cudaLaunchCooperativeKernel((void *)snn_generic_window, dim3(grid), dim3(SNN_GEN_THREADS), args, smem, stream);
+    if (prof && rc == 0 && N.T > 0) {
+        static long long host[8 * 4096];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(host, prof_buf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        static const char *names[8] = {"phase1", "barrierA", "phase2", "barrierB", "phase3", "phase3conv", "barrierC", "prologue"};
+        fprintf(stderr, "[snn_b200 gprof] grid=%d x %d threads, nch=%d cs=%d p3_units=%d T=%d B=%d  (cycles per timestep: min / mean / max over CTAs)\n",
+                grid, SNN_GEN_THREADS, N.nch, N.cs, N.p3_total, N.T, N.B);
+        for (int k = 0; k < 8; ++k) {
+            long long mn = host[k], mx = host[k]; double sum = 0;
+            for (int g = 0; g < grid; ++g) { const long long v = host[g * 8 + k]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += (double)v; }
+            const double d = k == 7 ? 1.0 : (double)N.T;
+            fprintf(stderr, "[snn_b200 gprof]   %-10s %10.0f %10.0f %10.0f\n", names[k], mn / d, sum / grid / d, mx / d);
+        }
+    }
+    return rc;
 }

@@ -159,7 +159,7 @@ int snn_b200_conn_update(const snn_net_t *net, int32_t ci, int32_t B, void *work
     // the single-operator update is the dense [n_src, n_tgt] rule application; convolutional weights and the
     // reward-modulated rules (whose state lives in the window plan) are only updated inside run_window
     if (C.kind != SNN_CONN_DENSE && C.kind != SNN_CONN_MCC) return SNN_ERR_UNSUPPORTED;
-    if (C.rule == SNN_RULE_MSTDP) return SNN_ERR_UNSUPPORTED;
+    if (SNN_RULE_IS_MSTDP(C.rule)) return SNN_ERR_UNSUPPORTED;
     if (C.rule == SNN_RULE_NONE) return SNN_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     DevNet N;

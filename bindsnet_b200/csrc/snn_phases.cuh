@@ -658,7 +658,24 @@ __device__ void phase3_mstdp_dense(const DevNet &N, int ci_, int tile, int t, co
         __syncthreads();
     }
     // weight update from the eligibility of the previous step = p_plus (x) s_post + s_pre (x) p_minus
-    if (i < ns)
+    if (C.rule == SNN_RULE_MSTDPET) {
+        // learning.MSTDPET._connection_update (learning.py:2187-2249), batch size 1: the eligibility feeds a decaying
+        // trace per synapse, the reward modulates the trace
+        if (i < ns)
+            for (int j = warp; j < nt; j += SNN_GEN_WARPS) {
+                const bool ss = staged ? sp_s[lane] != 0 : __ldcg(sp + i) != 0;
+                const bool tt = staged ? st_s[j] != 0 : __ldcg(st + j) != 0;
+                const float ppv = staged ? pp_s[lane] : __ldcg(pp + i), pmv = staged ? pm_s[j] : __ldcg(pm + j);
+                const float e = ppv * (tt ? 1.0f : 0.0f) + (ss ? 1.0f : 0.0f) * pmv;      // :2245-2247 of the previous step
+                float et = __ldcg(C.e_trace + (size_t)i * nt + j) * C.e_trace_decay;   // :2229
+                et = et + e / C.tc_e_trace;                                            // :2230
+                C.e_trace[(size_t)i * nt + j] = et;
+                float x = __ldcg(C.w + (size_t)i * nt + j) + C.et_coef * et;           // :2232-2238
+                if (C.weight_decay != 0.0f) x = x * C.weight_decay;
+                if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
+                C.w[(size_t)i * nt + j] = x;
+            }
+    } else if (i < ns)
         for (int j = warp; j < nt; j += SNN_GEN_WARPS) {
             float upd = 0.0f;
             if (staged) {

@@ -230,6 +230,45 @@ class MSTDP(LearningRule):
             d.mst_spre, d.mst_spost = self._spre.data_ptr(), self._spost.data_ptr()
 
 
+class MSTDPET(MSTDP):
+    """Reward-modulated STDP with an eligibility trace on a dense ``Connection`` (reference: learning.py:2124-2249;
+    ``_connection_update`` :2187-2249).  Batch size 1 only: the reference flattens the spikes of the whole batch into its
+    ``[n]`` traces (:2214-2215), which only has a meaning for one sample.  Rule state like the reference's: ``p_plus [n_src]``,
+    ``p_minus [n_tgt]``, ``eligibility_trace [n_src, n_tgt]``; ``eligibility`` is rebuilt on request from the traces and the
+    spikes the rule saw last.  The convolutional / local forms (:2251-2855) are outside the implemented path."""
+
+    rule_code = _abi.SNN_RULE_MSTDPET
+
+    def __init__(self, connection, nu=None, reduction=None, weight_decay: float = 0.0, **kwargs) -> None:
+        super().__init__(connection=connection, nu=nu, reduction=reduction, weight_decay=weight_decay, **kwargs)
+        if self._conv:
+            raise NotImplementedError("MSTDPET on a Conv2dConnection is outside the implemented path (dense Connection only)")
+        self.tc_e_trace = torch.tensor(kwargs.get("tc_e_trace", 25.0))
+
+    def _prepare(self, B: int, dev: torch.device, run_kwargs: dict) -> None:
+        if B != 1:
+            raise NotImplementedError("MSTDPET is defined for batch size 1 only (learning.py:2214-2215 flattens the batch)")
+        super()._prepare(B, dev, run_kwargs)
+        t = getattr(self, "eligibility_trace", None)
+        shape = tuple(self.connection.w.shape)
+        if not isinstance(t, torch.Tensor) or tuple(t.shape) != shape or t.device != dev:
+            self.eligibility_trace = torch.zeros(*shape, device=dev)
+
+    @property
+    def eligibility(self) -> torch.Tensor:
+        """``[n_src, n_tgt]`` (learning.py:2245-2247)."""
+        return torch.outer(self.p_plus.view(-1), self._spost.float().view(-1)) + torch.outer(self._spre.float().view(-1), self.p_minus.view(-1))
+
+    def _fill_desc(self, d: "_abi.SnnConn") -> None:
+        super()._fill_desc(d)
+        dt = float(self.connection.dt)
+        d.e_trace = self.eligibility_trace.data_ptr()
+        d.e_trace_decay = float(torch.exp(-dt / self.tc_e_trace))          # learning.py:2229
+        d.tc_e_trace = float(self.tc_e_trace)
+        # update = nu[0] * dt * reward * eligibility_trace (learning.py:2232): the scalar product in fp32, left to right
+        d.et_coef = float(self.nu[0].float() * dt * float(self._run_kwargs["reward"]))
+
+
 def _unsupported(name: str, where: str):
     class _Unsupported(LearningRule):
         __doc__ = f"``{name}`` (reference: {where}) — not on the accelerated path (SURVEY.md §8f)."
@@ -241,5 +280,4 @@ def _unsupported(name: str, where: str):
     return _Unsupported
 
 
-MSTDPET = _unsupported("MSTDPET", "learning.py:2124-2855")
 Rmax = _unsupported("Rmax", "learning.py:2858-2960")

@@ -317,13 +317,13 @@ class Network(torch.nn.Module):
         for layer in self.layers.values():
             if type(layer) not in builtin_nodes and (layer.kind is None or type(layer).forward is not N.Nodes.forward):
                 return True
-        builtin_conns = (Tp.Connection, Tp.MulticompartmentConnection, Tp.Conv2dConnection)
+        builtin_conns = (Tp.Connection, Tp.MulticompartmentConnection, Tp.Conv2dConnection, Tp.LocalConnection)
         for conn in self.connections.values():
             if type(conn) not in builtin_conns:
                 return True
             rule = getattr(conn, "update_rule", None)
             if rule is not None and (rule.rule_code is None or type(rule).update is not L.LearningRule.update
-                                     and type(rule) not in (L.NoOp, L.PostPre, L.WeightDependentPostPre, L.MSTDP)):
+                                     and type(rule) not in (L.NoOp, L.PostPre, L.WeightDependentPostPre, L.MSTDP, L.MSTDPET)):
                 return True
         return False
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 8
+#define SNN_ABI_VERSION 9
 #define SNN_MAX_LAYERS 8
 #define SNN_MAX_CONNS 12
 
@@ -69,6 +69,10 @@ extern "C" {
 /* On SNN_CONN_CONV2D the rules SNN_RULE_POSTPRE (learning.py:457-497), SNN_RULE_WDEP_POSTPRE (:920-975) and
  * SNN_RULE_HEBBIAN correlate the im2col views:  pre[co,k] = reduce_b sum_l x_tgt[b,co,l] * s_src_col[b,k,l],
  * post[co,k] = reduce_b sum_l s_tgt[b,co,l] * x_src_col[b,k,l]  (dilation 1), nu applied after the reduction. */
+#define SNN_RULE_MSTDPET 7     /* learning.MSTDPET on a dense Connection (learning.py:2187-2249): reward-modulated STDP with an
+                                  eligibility TRACE; batch size 1 only (the reference flattens the spikes of the whole batch into
+                                  its [n] traces) */
+#define SNN_RULE_IS_MSTDP(r) ((r) == SNN_RULE_MSTDP || (r) == SNN_RULE_MSTDPET)
 #define SNN_RULE_IS_STDP(r) (((r) >= SNN_RULE_POSTPRE && (r) <= SNN_RULE_MCC_POSTPRE) || (r) == SNN_RULE_HEBBIAN)
 
 /* ---- weight-matrix structure hints (DiehlAndCook2015's static exc/inh matrices,
@@ -182,6 +186,12 @@ typedef struct snn_conn {
        forced to 0 after every step's update, learning or not (AbstractConnection.update, topology.py:127-131).  [n_src, n_tgt]
        bytes, SNN_CONN_DENSE only (MulticompartmentConnection.update ignores the kwarg, topology.py:509-518); NULL = none. */
     const uint8_t *mask;
+    /* SNN_RULE_MSTDPET (learning.py:2187-2249), dense, B = 1.  p_plus [n_src], p_minus [n_tgt], mst_spre / mst_spost as for
+       SNN_RULE_MSTDP (the eligibility of the previous step is rebuilt from them); e_trace [n_src, n_tgt] is the rule's
+       eligibility_trace, updated in place:  e_trace = e_trace * e_trace_decay + eligibility / tc_e_trace  (:2229-2230),
+       w += et_coef * e_trace  with et_coef = nu[0] * dt * reward evaluated by the host in fp32 (:2232-2238). */
+    float *e_trace;
+    float e_trace_decay, tc_e_trace, et_coef;
 } snn_conn_t;
 
 typedef struct snn_net {

@@ -66,7 +66,7 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
         if (C->src < 0 || C->src >= net->n_layers || C->tgt < 0 || C->tgt >= net->n_layers) return SNN_ERR_BAD_ARG;
         if (!C->w) return SNN_ERR_BAD_ARG;
         if (net->layers[C->tgt].kind == SNN_NODE_INPUT) return SNN_ERR_UNSUPPORTED;
-        if (C->rule < 0 || C->rule > SNN_RULE_HEBBIAN) return SNN_ERR_UNSUPPORTED;
+        if (C->rule < 0 || C->rule > SNN_RULE_MSTDPET) return SNN_ERR_UNSUPPORTED;
         if (C->kind < 0 || C->kind > SNN_CONN_CONV2D) return SNN_ERR_UNSUPPORTED;
         if (C->kind == SNN_CONN_CONV2D) {
             const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
@@ -74,6 +74,10 @@ static int check_plan(const snn_net_t *net, const snn_run_opts_t *o) {
             if (C->kh < 1 || C->kw < 1 || C->sh < 1 || C->sw < 1 || C->dh < 1 || C->dw < 1 || !C->b) return SNN_ERR_BAD_ARG;
             if (C->rule == SNN_RULE_MCC_POSTPRE) return SNN_ERR_UNSUPPORTED;
             if (SNN_RULE_IS_STDP(C->rule) && (C->dh != 1 || C->dw != 1)) return SNN_ERR_UNSUPPORTED; /* im2col_indices ignores dilation */
+        }
+        if (C->rule == SNN_RULE_MSTDPET) {
+            if (C->kind != SNN_CONN_DENSE || o->B != 1) return SNN_ERR_UNSUPPORTED;
+            if (!C->p_plus || !C->p_minus || !C->mst_spre || !C->mst_spost || !C->e_trace) return SNN_ERR_BAD_ARG;
         }
         if (C->rule == SNN_RULE_MSTDP) {
             if (!C->p_plus || !C->p_minus) return SNN_ERR_BAD_ARG;
@@ -475,6 +479,37 @@ static void mstdp_dense_update(const snn_net_t *net, const snn_conn_t *C, const 
     }
 }
 
+/* learning.MSTDPET._connection_update (learning.py:2187-2249) on a dense Connection, batch size 1 (the reference
+ * flattens the batch into its [n] traces), then the base class decay + clamp (learning.py:87-104).  The eligibility of
+ * the previous step (:2245-2247) is rebuilt from p_plus / p_minus and the spikes the rule saw last, like in
+ * mstdp_dense_update; eligibility_trace is the materialised state. */
+static void mstdpet_dense_update(const snn_net_t *net, const snn_conn_t *C) {
+    const snn_layer_t *S = &net->layers[C->src], *G = &net->layers[C->tgt];
+    const int ns = S->n, nt = G->n;
+    for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < nt; ++j) {
+            const size_t k = (size_t)i * nt + j;
+            const float e = C->p_plus[i] * (C->mst_spost[j] ? 1.0f : 0.0f) + (C->mst_spre[i] ? 1.0f : 0.0f) * C->p_minus[j];
+            float et = C->e_trace[k] * C->e_trace_decay;                      /* :2229 */
+            et = et + e / C->tc_e_trace;                                      /* :2230 */
+            C->e_trace[k] = et;
+            float x = C->w[k] + C->et_coef * et;                              /* :2232-2238 */
+            if (C->weight_decay != 0.0f) x = x * C->weight_decay;             /* learning.py:93-94 */
+            if (C->has_clamp) x = clampf(x, C->wmin, C->wmax);                /* learning.py:97-104 */
+            C->w[k] = x;
+        }
+    for (int i = 0; i < ns; ++i) {                                            /* :2241-2244 */
+        const float x = C->p_plus[i] * C->p_plus_decay;
+        C->p_plus[i] = x + C->a_plus * (S->s[i] ? 1.0f : 0.0f);
+        C->mst_spre[i] = S->s[i] ? 1 : 0;
+    }
+    for (int j = 0; j < nt; ++j) {
+        const float x = C->p_minus[j] * C->p_minus_decay;
+        C->p_minus[j] = x + C->a_minus * (G->s[j] ? 1.0f : 0.0f);
+        C->mst_spost[j] = G->s[j] ? 1 : 0;
+    }
+}
+
 /* learning.MSTDP._conv2d_connection_update (learning.py:1942-2015) with the per-sample eligibility
  * the code intends (:1958-1961 allocate [B,*w.shape]; the final .view(w.size()) at :2013 only works for
  * B = 1, SURVEY.md §0.8: for B > 1 this is the reference with that view taken per sample).  p_plus is
@@ -697,6 +732,7 @@ int snn_oracle_run_window(const snn_net_t *net, const snn_run_opts_t *o, int den
                 const snn_conn_t *C = &net->conns[c];
                 if (C->rule == SNN_RULE_MSTDP && C->kind == SNN_CONN_CONV2D) mstdp_conv_update(net, C, o, dense);
                 else if (C->rule == SNN_RULE_MSTDP) mstdp_dense_update(net, C, o, dense);
+                else if (C->rule == SNN_RULE_MSTDPET) mstdpet_dense_update(net, C);
                 else if (C->kind == SNN_CONN_CONV2D && SNN_RULE_IS_STDP(C->rule)) stdp_conv_update(net, C, o, dense);
                 else if (C->kind == SNN_CONN_CONV2D) {  /* learning.NoOp on a conv connection: decay only */
                     if (C->rule == SNN_RULE_NOOP && C->weight_decay != 0.0f)

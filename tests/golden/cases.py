@@ -301,6 +301,22 @@ def mstdp_dense(ns, inputs=None):
     return net, inputs, {"reward": 0.7, "a_plus": 0.9, "a_minus": -1.1}, 80
 
 
+# MSTDPET on a dense connection (learning.py:2187-2249): eligibility trace, batch size 1 (the only one the reference's
+# flattened traces support), weight decay and clamp through the base class
+def mstdpet_dense(ns, inputs=None):
+    net = ns.Network(dt=1.0, batch_size=1)
+    X = ns.nodes.Input(n=60, traces=True)
+    Y = ns.nodes.LIFNodes(n=20, traces=True, thresh=-62.0, refrac=2)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    C = ns.topology.Connection(source=X, target=Y, w=_w((60, 20), 113, 1.2) - 0.2, update_rule=ns.learning.MSTDPET,
+                               nu=8e-2, reduction=torch.sum, wmin=-1.0, wmax=1.5, tc_plus=15.0, tc_minus=25.0, tc_e_trace=12.0,
+                               weight_decay=1e-3)
+    net.add_connection(C, "X", "Y")
+    if inputs is None:
+        inputs = {"X": _bernoulli_inputs(120, 1, (60,), 0.12, 114)}
+    return net, inputs, {"reward": 0.8, "a_plus": 0.9, "a_minus": -1.1}, 120
+
+
 def _conv_net(ns, B, T, in_shape, out_ch, k, stride, padding, rule, seeds, n_out=6, norm=None, conv_nu=1e-2):
     """BASELINE.json config 4 in small: Input[C,H,W] -> Conv2dConnection -> LIFNodes[Co,Ho,Wo] -> Connection ->
     LIFNodes(n_out), MSTDP on both connections (or no rule), weights in [-1, 1]."""
@@ -474,6 +490,7 @@ CASES = {
     "alif_postpre": alif_postpre,
     "boosted_postpre": boosted_postpre,
     "local_postpre": local_postpre,
+    "mstdpet_dense": mstdpet_dense,
     "mcp_postpre": mcp_postpre,
     "lif_clamps": lif_clamps,
     "dc2015_multi": dc2015_multi,
