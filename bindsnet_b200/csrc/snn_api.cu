@@ -99,6 +99,11 @@ static size_t layout_generic(const snn_net_t *net, const snn_run_opts_t *o, char
         if (th) off += align_up(sizeof(float) * 2 * L.n);
         if (N) N->layers[l].thcnt = th ? (int32_t *)(ws + off) : nullptr;
         if (th) off += align_up(sizeof(int32_t) * 3 * L.n);
+        bool wide_src = false;   // source of a dense connection with more than one gather block
+        for (int c = 0; c < net->n_conns; ++c)
+            if (net->conns[c].src == l && net->conns[c].kind != SNN_CONN_CONV2D && nw > 32) wide_src = true;
+        if (N) N->layers[l].anyf = wide_src ? (uint32_t *)(ws + off) : nullptr;
+        if (wide_src) off += align_up(sizeof(uint32_t) * 3 * B);
         if (N && os) N->any_one_spike = 1;
     }
     if (N) N->total_items = items;

@@ -24,6 +24,8 @@ struct DevLayer {
     float *xpub;                // [2][B][n]   trace published for STDP readers (slot t&1), or NULL
     float *thdec;               // [2][n]      DC: the decayed adaptive threshold step t used (slot t&1)
     int32_t *thcnt;             // [3][n]      DC: threshold crossers of step t summed over the batch (slot t%3)
+    uint32_t *anyf;             // [3][B]      wide source layers (nw > 32) of dense connections: non-zero iff the sample spiked
+                                //             in step t (slot t%3) — lets a gather skip an all-zero bit row without reading it
     int32_t nw;                 // ceil(n / 32)
     int32_t item0;              // first work-item index of this layer
 };
@@ -61,34 +63,37 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Sense-reversal grid barrier on (count, generation) words in global memory.  Requires all
-// CTAs of the grid to be co-resident (cooperative launch).  A time-out (~2 s) raises
-// SNN_ERR_BARRIER and makes every CTA leave the time loop instead of hanging the device.
-__device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nblocks, int32_t *err) {
+// Grid barrier on ONE monotonic arrival counter in global memory: a release reduction to arrive (no return value:
+// one L2 transaction), relaxed polling of the same word with a short back-off until `gen * nblocks` arrivals are in,
+// then one acquire fence.  `gen` is the caller's barrier count (a register, identical in every CTA).  Requires all
+// CTAs of the grid to be co-resident (cooperative launch).  A time-out (~2 s) raises SNN_ERR_BARRIER and makes every
+// CTA leave the time loop instead of hanging the device: the CTA that gives up adds 2^30 to the counter, which
+// releases every present and future wait and is recognised as "abort" by whoever reads it.  The pollers back off
+// (nanosleep): in the generic kernel many CTAs wait here while others still stream state and weights through L2.
+__device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nblocks, int32_t *err, unsigned int &gen) {
     __shared__ int s_abort;
+    ++gen;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int *count = bar, *gen = bar + 32, *abort_w = bar + 64;
-        const unsigned int g = ld_acquire_u32(gen);
-        __threadfence();
-        const unsigned int prev = atomicAdd(count, 1u);
+        const unsigned int target = gen * nblocks;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         int ab = 0;
-        if (prev == nblocks - 1) {
-            *count = 0u;
-            __threadfence();
-            st_release_u32(gen, g + 1u);
-        } else {
-            const long long t0 = clock64();
-            while (ld_acquire_u32(gen) == g) {
-                if (clock64() - t0 > 4000000000LL) {
-                    if (err) atomicOr(err, SNN_ERR_BARRIER);
-                    atomicExch(abort_w, 1u);
-                    break;
-                }
+        const long long t0 = clock64();
+        unsigned int ns = 20;
+        for (;;) {
+            unsigned int v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((int)(v - target) >= 0) { ab = (v - target) >= 0x20000000u; break; }
+            __nanosleep(ns);
+            if (ns < 160) ns += 20;
+            if (clock64() - t0 > 4000000000LL) {
+                if (err) atomicOr(err, SNN_ERR_BARRIER);
+                atomicAdd(bar, 0x40000000u);
+                ab = 1;
+                break;
             }
         }
-        __threadfence();
-        ab = (int)ld_acquire_u32(abort_w);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         s_abort = ab;
     }
     __syncthreads();

@@ -31,12 +31,16 @@ __device__ __forceinline__ void item_of(const DevNet &N, int item, int &li, int 
     tile = item - N.layers[li].item0;
 }
 
-__global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const __grid_constant__ DevNet N) {
+// CTAS = CTAs per SM the variant is compiled for: 3 (80 registers, a few spills) when the shared-memory footprint lets
+// three CTAs share an SM (B <= ~160), 2 (no register cap to speak of) otherwise.
+template <int CTAS>
+__global__ void __launch_bounds__(SNN_GEN_THREADS, CTAS) snn_generic_window(const __grid_constant__ DevNet N) {
     extern __shared__ float smem[];
     const GenSmem M = gen_carve(smem, N.B);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int G = gridDim.x;
     const int nch = N.nch;
+    unsigned int bgen = 0;   // barriers passed so far (grid_barrier)
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();   // phase timers (profiling only)
     #define GPROF(k) { if (N.prof && threadIdx.x == 0) { const long long now_ = clock64(); pc[k] += now_ - pt; pt = now_; } }
 
@@ -53,6 +57,8 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
         if (D.keys && tile == 0)
             for (int b = threadIdx.x; b < 2 * N.B; b += blockDim.x) D.keys[b] = 0ull;
         if (D.thcnt && warp < 3 && j < D.L.n) D.thcnt[(size_t)warp * D.L.n + j] = 0;
+        if (D.anyf && tile == 0)   // slot 2 = step -1: "may have spiked" (conservative); slots 0 / 1 start empty
+            for (int b = threadIdx.x; b < 3 * N.B; b += blockDim.x) D.anyf[b] = b >= 2 * N.B ? 1u : 0u;
         // MSTDP state: step t reads slot (t + T) & 1; for an odd T the first read is slot 1, so the
         // caller's tensors (slot 0) are copied there — the last step then writes slot 0
         if (N.learning && (N.T & 1))
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                 }
             }
     }
-    if (!grid_barrier(N.bar, G, N.err)) return;
+    if (!grid_barrier(N.bar, G, N.err, bgen)) return;
     GPROF(7)
 
     for (int t = 0; t < N.T; ++t) {
@@ -81,10 +87,10 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                 const DevLayer &D = N.layers[l];
                 for (int u = blockIdx.x; u < D.nw * nch; u += G) phase1(N, l, u / nch, u % nch, t, M);
                 if (D.L.kind == SNN_NODE_DC && D.L.one_spike) {
-                    if (!grid_barrier(N.bar, G, N.err)) return;
+                    if (!grid_barrier(N.bar, G, N.err, bgen)) return;
                     for (int u = blockIdx.x; u < D.nw * nch; u += G) phase2(N, l, u / nch, u % nch, t);
                 }
-                if (l + 1 < N.n_layers && !grid_barrier(N.bar, G, N.err)) return;
+                if (l + 1 < N.n_layers && !grid_barrier(N.bar, G, N.err, bgen)) return;
             }
         } else {
             for (int u = blockIdx.x; u < N.total_items * nch; u += G) {
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
         }
         GPROF(0)
         if (N.any_one_spike && !N.one_step) {
-            if (!grid_barrier(N.bar, G, N.err)) return;
+            if (!grid_barrier(N.bar, G, N.err, bgen)) return;
             GPROF(1)
             for (int u = blockIdx.x; u < N.total_items * nch; u += G) {
                 int li, tile; item_of(N, u / nch, li, tile);
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
             }
             GPROF(2)
         }
-        if (!grid_barrier(N.bar, G, N.err)) return;
+        if (!grid_barrier(N.bar, G, N.err, bgen)) return;
         GPROF(3)
         if (N.learning) {
             for (int u = blockIdx.x; u < N.p3_total; u += G) {
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                 if (N.conns[c].kind == SNN_CONN_CONV2D && N.conns[c].rule != SNN_RULE_NONE) phase3_conv(N, c, blockIdx.x, G, t, M);
             GPROF(5)
             // the units of the learning phase are not the units that gather from the weights in the next step
-            if (!grid_barrier(N.bar, G, N.err)) return;
+            if (!grid_barrier(N.bar, G, N.err, bgen)) return;
             GPROF(6)
         }
         if (N.any_mask) {   // connection masks apply after the update, learning or not (topology.py:127-131)
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, 3) snn_generic_window(const _
                     if (C.mask && C.tgt == li && C.kind == SNN_CONN_DENSE) mask_tile(C, N.layers[C.src].L.n, N.layers[li].L.n, tile);
                 }
             }
-            if (!grid_barrier(N.bar, G, N.err)) return;
+            if (!grid_barrier(N.bar, G, N.err, bgen)) return;
         }
     }
 
@@ -178,12 +184,16 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = snn_generic_smem_bytes(N.B);
-    e = cudaFuncSetAttribute(snn_generic_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // three CTAs per SM if their shared memory fits (227 KB per SM, 1 KB reserved per CTA), else two
+    const bool three = 3 * (smem + 1024) <= 227 * 1024;
+    const void *kern = three ? (const void *)snn_generic_window<3> : (const void *)snn_generic_window<2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window, SNN_GEN_THREADS, smem);
+    e = three ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window<3>, SNN_GEN_THREADS, smem)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window<2>, SNN_GEN_THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > (three ? 3 : 2)) per_sm = three ? 3 : 2;
     const int cap = sms * per_sm;
 
     // phases 1 / 2: about four samples per warp and unit, but no more units than ~16 waves of the grid
@@ -223,7 +233,7 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
         N.prof = prof_buf;
     }
     void *args[] = {(void *)&N};
-    const int rc = (int)cudaLaunchCooperativeKernel((void *)snn_generic_window, dim3(grid), dim3(SNN_GEN_THREADS), args, smem, stream);
+    const int rc = (int)cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SNN_GEN_THREADS), args, smem, stream);
     if (prof && rc == 0 && N.T > 0) {
         static long long host[8 * 4096];
         cudaStreamSynchronize(stream);

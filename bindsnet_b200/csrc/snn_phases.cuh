@@ -85,45 +85,59 @@ __device__ __forceinline__ float ld_ext(const snn_layer_t &L, size_t idx, bool &
 // flight from L2 at once — the sum itself stays one fp32 add per spike in ascending i, like the oracle.
 // Weights are read with ld.cg: the CTA that updates a tile in the learning phase is not the CTA that
 // gathers from it.
-// `first` = the lane's word of block 0 (sb[lane]), loaded by the caller ahead of time; the words of the following
-// blocks are fetched one block ahead.
+// `first` = the lane's word of block 0 (sb[lane]), loaded by the caller ahead of time.  The words of up to eight
+// blocks (8192 source neurons) are fetched together, so a wide but sparse source layer (the 6400 inhibitory neurons of
+// BASELINE config 3: 7 blocks, almost always empty) costs one L2 round trip instead of one per block.
 __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__restrict__ sb, int nw_src,
                                         int n_src, int n_tgt, int j, bool valid, int lane, uint16_t *__restrict__ lst, uint32_t first) {
     float p = 0.0f;
     const float *__restrict__ wcol = C.w + j;
-    uint32_t nxt = first;
-    for (int w0 = 0; w0 < nw_src; w0 += 32) {
-        uint32_t mine = nxt;
-        nxt = (w0 + 32 + lane < nw_src) ? __ldcg(sb + w0 + 32 + lane) : 0u;
-        if (!__any_sync(0xffffffffu, mine != 0u)) continue;
-        const int cnt = __popc(mine);
-        int pre = cnt;
+    for (int s0 = 0; s0 < nw_src; s0 += 256) {
+        uint32_t wd[8];
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += v;
+        for (int k = 0; k < 8; ++k) {
+            const int w = s0 + 32 * k + lane;
+            wd[k] = (k == 0 && s0 == 0) ? first : (w < nw_src ? __ldcg(sb + w) : 0u);
         }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
-        int q = pre - cnt;
-        while (mine) {
-            const int r = __ffs(mine) - 1;
-            mine &= mine - 1;
-            lst[q++] = (uint16_t)((lane << 5) | r);
-        }
-        __syncwarp();
-        const int base = w0 * 32;
-        for (int e = 0; e < total; e += 8) {
-            float v[8];
+        uint32_t nzb = 0;   // blocks of this group that hold a spike
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) nzb |= __any_sync(0xffffffffu, wd[k] != 0u) ? (1u << k) : 0u;
+        while (nzb) {
+            const int kb = __ffs(nzb) - 1;
+            nzb &= nzb - 1;
+            uint32_t mine = wd[0];
             #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = base + (int)lst[min(e + k, total - 1)];
-                v[k] = (valid && e + k < total && i < n_src) ? __ldcg(wcol + (size_t)i * n_tgt) : 0.0f;
+            for (int k = 1; k < 8; ++k)
+                if (kb == k) mine = wd[k];
+            const int cnt = __popc(mine);
+            int pre = cnt;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += v;
             }
-            #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (e + k < total) p = p + v[k];
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
+            int q = pre - cnt;
+            while (mine) {
+                const int r = __ffs(mine) - 1;
+                mine &= mine - 1;
+                lst[q++] = (uint16_t)((lane << 5) | r);
+            }
+            __syncwarp();
+            const int base = (s0 + 32 * kb) * 32;
+            for (int e = 0; e < total; e += 8) {
+                float v[8];
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = base + (int)lst[min(e + k, total - 1)];
+                    v[k] = (valid && e + k < total && i < n_src) ? __ldcg(wcol + (size_t)i * n_tgt) : 0.0f;
+                }
+                #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (e + k < total) p = p + v[k];
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     return p;
 }
@@ -214,9 +228,14 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
                     sf = finalize_neuron(N, D, s, xo[q], k, b, j, t, wr);
                 }
                 const uint32_t fw = __ballot_sync(0xffffffffu, valid && sf);
-                if (lane == 0) D.bits[((size_t)wr * B + b) * nw + tile] = fw;
+                if (lane == 0) {
+                    D.bits[((size_t)wr * B + b) * nw + tile] = fw;
+                    if (D.anyf && fw) atomicOr(D.anyf + (size_t)(t % 3) * B + b, 1u);
+                }
             }
         }
+        if (D.anyf && tile == 0)
+            for (int b = b0 + threadIdx.x; b < b1; b += SNN_GEN_THREADS) D.anyf[(size_t)((t + 1) % 3) * B + b] = 0u;
         if (nonbin && N.err) atomicOr(N.err, SNN_ERR_NONBINARY);
         return;
     }
@@ -259,7 +278,14 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
         st_taps = ntaps <= SNN_CONV_STAGE_TAPS;
         if (st_bits) {
             const uint32_t *src = S.bits + ((size_t)conv_slot * B + b0) * S.nw;
-            for (int k = threadIdx.x; k < words; k += SNN_GEN_THREADS) M.cbits[k] = __ldcg(src + k);
+            for (int k0 = threadIdx.x; k0 < words; k0 += 4 * SNN_GEN_THREADS) {
+                uint32_t wq[4];
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) wq[q] = k0 + q * SNN_GEN_THREADS < words ? __ldcg(src + k0 + q * SNN_GEN_THREADS) : 0u;
+                #pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (k0 + q * SNN_GEN_THREADS < words) M.cbits[k0 + q * SNN_GEN_THREADS] = wq[q];
+            }
         }
         if (st_taps)
             for (int k = threadIdx.x; k < ntaps; k += SNN_GEN_THREADS) M.xs[k] = __ldcg(C.w + (size_t)co_base * K + k);
@@ -280,15 +306,16 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
     for (int b = b0 + warp; b < b1; b += SNN_GEN_WARPS) {
         const size_t k = (size_t)b * n + j;
         // every independent load of the sample first: bit words of the dense inputs, then the state
-        uint32_t fw[4];
+        uint32_t fw[4], af[4];   // first bit words; "the sample spiked at all" flags of wide sources
         #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            fw[q] = 0u;
+            fw[q] = 0u; af[q] = 1u;
             if (q < ncl && N.conns[cl[q]].kind != SNN_CONN_CONV2D) {
                 const snn_conn_t &C = N.conns[cl[q]];
                 const DevLayer &S = N.layers[C.src];
                 const int slot = (N.one_step && C.src < li) ? wr : rd;
                 if (lane < S.nw) fw[q] = __ldcg(S.bits + ((size_t)slot * B + b) * S.nw + lane);
+                if (S.anyf) af[q] = __ldcg(S.anyf + (size_t)(slot == wr ? t % 3 : (t + 2) % 3) * B + b);
             }
         }
         float v = 0.0f, rc = 0.0f, xold = 0.0f, ic = 0.0f;
@@ -306,10 +333,10 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
             const snn_conn_t &C = N.conns[c];
             if (C.tgt != li) continue;
             const DevLayer &S = N.layers[C.src];
-            uint32_t first = 0u;
+            uint32_t first = 0u, anysp = 1u;
             #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (q == seen) first = fw[q];
+                if (q == seen) { first = fw[q]; anysp = af[q]; }
             const bool prefetched = seen < 4;
             ++seen;
             // one-step mode (network.py:393-396): sources earlier in the insertion order have already
@@ -329,7 +356,7 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
             } else {
                 const uint32_t *sbr = S.bits + ((size_t)slot * B + b) * S.nw;
                 if (!prefetched) first = lane < S.nw ? __ldcg(sbr + lane) : 0u;
-                p = gather(C, sbr, S.nw, S.L.n, n, j, valid, lane, lst, first);
+                p = anysp ? gather(C, sbr, S.nw, S.L.n, n, j, valid, lane, lst, first) : 0.0f;
                 if (C.b && valid) p = p + C.b[j];
             }
             cur = cur + p;
@@ -379,9 +406,14 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
             bool sf = false;
             if (valid) sf = finalize_neuron(N, D, s, xold, k, b, j, t, wr);
             const uint32_t fw = __ballot_sync(0xffffffffu, valid && sf);
-            if (lane == 0) D.bits[((size_t)wr * B + b) * nw + tile] = fw;
+            if (lane == 0) {
+                D.bits[((size_t)wr * B + b) * nw + tile] = fw;
+                if (D.anyf && fw) atomicOr(D.anyf + (size_t)(t % 3) * B + b, 1u);
+            }
         }
     }
+    if (D.anyf && tile == 0)   // the flag slot of step t + 1 (last read in step t - 1)
+        for (int b = b0 + threadIdx.x; b < b1; b += SNN_GEN_THREADS) D.anyf[(size_t)((t + 1) % 3) * B + b] = 0u;
 
     // theta += theta_plus * sum_b s  (nodes.py:1093-1094)
     if (dc && L.learning && valid && cnt > 0) atomicAdd(D.thcnt + (size_t)(t % 3) * n + j, cnt);
@@ -425,7 +457,10 @@ __device__ void phase2(const DevNet &N, int li, int tile, int chunk, int t) {
             bool sf = false;
             if (valid) sf = finalize_neuron(N, D, s, xo[q], k, b, j, t, wr);
             const uint32_t fw = __ballot_sync(0xffffffffu, valid && sf);
-            if (lane == 0) D.bits[((size_t)wr * B + b) * nw + tile] = fw;
+            if (lane == 0) {
+                D.bits[((size_t)wr * B + b) * nw + tile] = fw;
+                if (D.anyf && fw) atomicOr(D.anyf + (size_t)(t % 3) * B + b, 1u);
+            }
         }
     }
 }
@@ -461,13 +496,18 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
     const bool stage = pre_on && M.xt != nullptr;
 
     if (stage)
-        for (int b = warp; b < B; b += SNN_GEN_WARPS) {
-            float tx = 0.0f;
-            if (valid) {
-                tx = __ldcg(G.L.x + (size_t)b * nt + j);
-                if (!wdep) tx = tx * C.nu0;
+        for (int b0 = warp; b0 < B; b0 += 8 * SNN_GEN_WARPS) {   // eight rows of the trace tile in flight per warp
+            float tx[8];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int b = b0 + q * SNN_GEN_WARPS;
+                tx[q] = (valid && b < B) ? __ldcg(G.L.x + (size_t)b * nt + j) : 0.0f;
             }
-            M.xt[b * 32 + lane] = tx;
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int b = b0 + q * SNN_GEN_WARPS;
+                if (b < B) M.xt[b * 32 + lane] = wdep ? tx[q] : tx[q] * C.nu0;
+            }
         }
 
     // column events: colmask[g*32 + lane] = samples of group g whose target spike hit column j
@@ -517,11 +557,29 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
     const int nev = any_col ? M.evb[SNN_P3_MAXEV] : 0;
     __syncwarp();
 
+    // In the dense regime (large batches: nearly every source row has a spike somewhere in the batch) the weight rows
+    // of a group are fetched before it is known which of them change — their L2 round trip then hides behind the
+    // accumulation; for small batches only the rows that need it are read.
+    const bool eager = B >= 64;
+    const bool post_t = colany != 0u;
     for (int wg = wg0 + warp; wg < wg1; wg += SNN_GEN_WARPS) {
-        if (nev > 0) {   // pre-synaptic traces of the event samples for my 32 rows (coalesced, all in flight)
-            const int i = wg * 32 + lane;
-            for (int e = 0; e < nev; ++e)
-                xsw[e * 32 + lane] = i < ns ? __ldcg(S.xpub + ((size_t)wr * B + M.evb[e]) * ns + i) : 0.0f;
+        const int i0 = wg * 32;
+        float wv[8];
+        if (eager) {
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) wv[q] = (valid && i0 + q < ns) ? __ldcg(C.w + (size_t)(i0 + q) * nt + j) : 0.0f;
+        }
+        if (nev > 0) {   // pre-synaptic traces of the event samples for my 32 rows (coalesced, four in flight)
+            const int i = i0 + lane;
+            for (int e0 = 0; e0 < nev; e0 += 4) {
+                float xv[4];
+                #pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    xv[q] = (e0 + q < nev && i < ns) ? __ldcg(S.xpub + ((size_t)wr * B + M.evb[min(e0 + q, nev - 1)]) * ns + i) : 0.0f;
+                #pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (e0 + q < nev) xsw[(e0 + q) * 32 + lane] = xv[q];
+            }
         }
         uint32_t tmask = 0;
         if (pre_on) {
@@ -559,23 +617,26 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
         }
         __syncwarp();
         if (!full && !tmask && !any_col) continue;
-        const bool post_t = colany != 0u;
         for (int r0 = 0; r0 < 32; r0 += 8) {
-            float wv[8];
             bool nd[8];
             bool anyneed = false;
             #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int r = r0 + q, i = wg * 32 + r;
+                const int r = r0 + q, i = i0 + r;
                 const bool pre_t = (tmask >> r) & 1u;
                 nd[q] = valid && i < ns && (full || pre_t || post_t);
-                wv[q] = nd[q] ? __ldcg(C.w + (size_t)i * nt + j) : 0.0f;
+                if (!eager) wv[q] = nd[q] ? __ldcg(C.w + (size_t)i * nt + j) : 0.0f;
                 anyneed |= nd[q];
+            }
+            float wn[8];   // next group's rows: in flight while this group is rewritten
+            if (eager && r0 + 8 < 32) {
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) wn[q] = (valid && i0 + r0 + 8 + q < ns) ? __ldcg(C.w + (size_t)(i0 + r0 + 8 + q) * nt + j) : 0.0f;
             }
             if (__any_sync(0xffffffffu, anyneed)) {
                 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int r = r0 + q, i = wg * 32 + r;
+                    const int r = r0 + q, i = i0 + r;
                     const bool pre_t = (tmask >> r) & 1u;
                     if (nd[q]) {
                         float U = 0.0f, V = 0.0f;
@@ -603,6 +664,10 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
             #pragma unroll
             for (int q = 0; q < 8; ++q)
                 if ((tmask >> (r0 + q)) & 1u) acc[(r0 + q) * 32 + lane] = 0.0f;
+            if (eager) {
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) wv[q] = wn[q];
+            }
         }
         __syncwarp();
     }
@@ -645,14 +710,34 @@ __device__ void phase3_mstdp_dense(const DevNet &N, int ci_, int tile, int t, co
     uint8_t *sp_s = st_s + ((size_t)B * nt + 15) / 16 * 16;  // [B][32]
     uint32_t *sbw = GS.colmask;                            // [B] source spike word of this tile, step t
     if (staged) {
-        for (int b = warp; b < B; b += SNN_GEN_WARPS) {
-            const bool ok = i < ns;
-            pp_s[b * 32 + lane] = ok ? __ldcg(pp + (size_t)b * ns + i) : 0.0f;
-            sp_s[b * 32 + lane] = ok ? __ldcg(sp + (size_t)b * ns + i) : (uint8_t)0;
+        for (int b0 = warp; b0 < B; b0 += 8 * SNN_GEN_WARPS) {   // eight samples' rows in flight per warp
+            float pv[8]; uint8_t sv[8];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int b = b0 + q * SNN_GEN_WARPS;
+                const bool ok = i < ns && b < B;
+                pv[q] = ok ? __ldcg(pp + (size_t)b * ns + i) : 0.0f;
+                sv[q] = ok ? __ldcg(sp + (size_t)b * ns + i) : (uint8_t)0;
+            }
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int b = b0 + q * SNN_GEN_WARPS;
+                if (b < B) { pp_s[b * 32 + lane] = pv[q]; sp_s[b * 32 + lane] = sv[q]; }
+            }
         }
-        for (int k = threadIdx.x; k < B * nt; k += SNN_GEN_THREADS) {
-            pm_s[k] = __ldcg(pm + k);
-            st_s[k] = __ldcg(st + k);
+        for (int k0 = threadIdx.x; k0 < B * nt; k0 += 4 * SNN_GEN_THREADS) {
+            float pv[4]; uint8_t sv[4];
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + q * SNN_GEN_THREADS;
+                pv[q] = k < B * nt ? __ldcg(pm + k) : 0.0f;
+                sv[q] = k < B * nt ? __ldcg(st + k) : (uint8_t)0;
+            }
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + q * SNN_GEN_THREADS;
+                if (k < B * nt) { pm_s[k] = pv[q]; st_s[k] = sv[q]; }
+            }
         }
         for (int b = threadIdx.x; b < B; b += SNN_GEN_THREADS) sbw[b] = __ldcg(S.bits + ((size_t)wr * B + b) * S.nw + tile);
         __syncthreads();
@@ -884,22 +969,38 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int cta, int ncta, int t, 
     // inside channel co (ci) in ascending order — the same terms in the same order as the dense double loop.
     // Unit = (sample, group of output channels); the sample's two bit rows are staged in shared memory.
     {
-        const int cpc = max(1, SNN_GEN_THREADS / K);                // output channels per unit
+        // output channels per unit: about one (channel, tap) element per thread, and few enough channels for their
+        // P- rows of the sample ([channels][L] floats) to be staged in the 32 KB accumulator region
+        const bool stage_pm = L <= SNN_GEN_WARPS * 32 * 32;
+        const int cpc = stage_pm ? min(max(1, SNN_GEN_THREADS / K), (SNN_GEN_WARPS * 32 * 32) / L) : max(1, SNN_GEN_THREADS / K);
         const int nch = (C.cout + cpc - 1) / cpc;
         const bool staged = S.nw + G.nw <= SNN_CONV_STAGE_WORDS;
-        uint32_t *sb_s = GS.cbits, *gb_s = GS.cbits + S.nw;
+        uint32_t *sb_s = (uint32_t *)GS.xs, *gb_s = (uint32_t *)GS.xs + S.nw;
+        float *pm_s = GS.acc;
         for (int u = cta; u < B * nch; u += ncta) {
             const int b = u / nch, ch = u - b * nch;
             const int co0 = ch * cpc, co1 = min(C.cout, co0 + cpc);
             const uint32_t *sbg = S.bits + ((size_t)wr * B + b) * S.nw, *gbg = G.bits + ((size_t)wr * B + b) * G.nw;
+            const float *ppb = pp + (size_t)b * ns, *pmb = pm + (size_t)b * nt;
+            if (staged || stage_pm) __syncthreads();
             if (staged) {
-                __syncthreads();
                 for (int k = threadIdx.x; k < S.nw; k += SNN_GEN_THREADS) sb_s[k] = __ldcg(sbg + k);
                 for (int k = threadIdx.x; k < G.nw; k += SNN_GEN_THREADS) gb_s[k] = __ldcg(gbg + k);
-                __syncthreads();
             }
+            if (stage_pm) {   // P- of the unit's channels, eight loads in flight per thread
+                const int tot = (co1 - co0) * L;
+                const float *src = pmb + (size_t)co0 * L;
+                for (int k0 = threadIdx.x; k0 < tot; k0 += 8 * SNN_GEN_THREADS) {
+                    float pv8[8];
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q) pv8[q] = k0 + q * SNN_GEN_THREADS < tot ? __ldcg(src + k0 + q * SNN_GEN_THREADS) : 0.0f;
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (k0 + q * SNN_GEN_THREADS < tot) pm_s[k0 + q * SNN_GEN_THREADS] = pv8[q];
+                }
+            }
+            if (staged || stage_pm) __syncthreads();
             const uint32_t *sb = staged ? sb_s : sbg, *gb = staged ? gb_s : gbg;
-            const float *ppb = pp + (size_t)b * ns, *pmb = pm + (size_t)b * nt;
             for (int e = threadIdx.x; e < (co1 - co0) * K; e += SNN_GEN_THREADS) {
                 const int co = co0 + e / K, k = e - (co - co0) * K;
                 const int ci = k / KK, kk = k - ci * KK, ky = kk / C.kw, kx = kk - ky * C.kw;
@@ -938,7 +1039,7 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int cta, int ncta, int t, 
                     }
                     float pv[4];
                     #pragma unroll
-                    for (int q = 0; q < 4; ++q) pv[q] = tg[q] >= 0 ? __ldcg(pmb + tg[q]) : 0.0f;
+                    for (int q = 0; q < 4; ++q) pv[q] = tg[q] >= 0 ? (stage_pm ? pm_s[tg[q] - co0 * L] : __ldcg(pmb + tg[q])) : 0.0f;
                     #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (tg[q] >= 0) {
@@ -949,7 +1050,7 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int cta, int ncta, int t, 
                 M.el[out][(size_t)b * NWT + (size_t)co * K + k] = s1 + s2;
             }
         }
-        if (staged) __syncthreads();
+        if (staged || stage_pm) __syncthreads();
     }
 }
 

@@ -54,8 +54,17 @@ def test_unsupported_reference_features_fail_loudly():
     with pytest.raises(NotImplementedError):
         Conv1dConnection(None, None, 3)
     X, Y = Input(n=4, traces=True), LIFNodes(n=4, traces=True)
+    from bindsnet_b200.learning import Rmax
     with pytest.raises(NotImplementedError):
-        Connection(X, Y, update_rule=MSTDPET)
+        Connection(X, Y, update_rule=Rmax)
+    # MSTDPET is implemented for dense connections at batch size 1 (the only one the reference's flattened traces allow)
+    netb = Network(dt=1.0, batch_size=2)
+    Xb, Yb = Input(n=4, traces=True), LIFNodes(n=4, traces=True)
+    netb.add_layer(Xb, "X"); netb.add_layer(Yb, "Y")
+    netb.add_connection(Connection(Xb, Yb, update_rule=MSTDPET, nu=1e-2, wmin=-1.0, wmax=1.0), "X", "Y")
+    with OracleBackend():
+        with pytest.raises(NotImplementedError):
+            netb.run({"X": torch.zeros(3, 2, 4)}, time=3, reward=1.0)
     # MSTDP is implemented; its reward is mandatory like in the reference
     net = Network(dt=1.0, batch_size=1)
     net.add_layer(X, "X"); net.add_layer(Y, "Y")
