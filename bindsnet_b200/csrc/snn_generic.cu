@@ -185,7 +185,8 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = snn_generic_smem_bytes(N.B);
     // three CTAs per SM if their shared memory fits (227 KB per SM, 1 KB reserved per CTA), else two
-    const bool three = 3 * (smem + 1024) <= 227 * 1024;
+    bool three = 3 * (smem + 1024) <= 227 * 1024;
+    if (const char *v = getenv("SNN_B200_GVAR")) three = three && v[0] == '3';   // experiments: force the 2-CTA variant
     const void *kern = three ? (const void *)snn_generic_window<3> : (const void *)snn_generic_window<2>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

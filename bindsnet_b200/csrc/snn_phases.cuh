@@ -31,6 +31,7 @@ struct GenSmem {
     int32_t *evb;       // [SNN_P3_MAXEV + 1]
     uint8_t *evslot;    // [B]
     float *xt;          // [B][32] or NULL (batch too large to stage)
+    uint32_t *live;     // [ceil(B/32)] samples whose staged trace row is not all zero
     int32_t xt_bytes;
 };
 
@@ -46,6 +47,7 @@ __host__ __device__ inline size_t gen_smem_bytes(int B) {
     s += sizeof(float) * SNN_GEN_WARPS * SNN_P3_MAXEV * 32;        // xs
     s += sizeof(int32_t) * (SNN_P3_MAXEV + 16);                    // evb (padded)
     s += ((size_t)B + 15) / 16 * 16;                               // evslot
+    s += (sizeof(uint32_t) * NG + 15) / 16 * 16;                   // live
     s += gen_xt_bytes(B);
     return s;
 }
@@ -60,8 +62,9 @@ __device__ __forceinline__ GenSmem gen_carve(float *smem, int B) {
     M.xs = (float *)(M.colmask + 32 * NG);
     M.evb = (int32_t *)(M.xs + SNN_GEN_WARPS * SNN_P3_MAXEV * 32);
     M.evslot = (uint8_t *)(M.evb + SNN_P3_MAXEV + 16);
+    M.live = (uint32_t *)(M.evslot + (B + 15) / 16 * 16);
     M.xt_bytes = (int32_t)gen_xt_bytes(B);
-    M.xt = M.xt_bytes ? (float *)(M.evslot + (B + 15) / 16 * 16) : nullptr;
+    M.xt = M.xt_bytes ? (float *)((uint8_t *)M.live + (sizeof(uint32_t) * NG + 15) / 16 * 16) : nullptr;
     return M;
 }
 
@@ -495,7 +498,12 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
     const float Bf = (float)B;
     const bool stage = pre_on && M.xt != nullptr;
 
-    if (stage)
+    // Samples whose target-trace row is all zero in this tile cannot change the pre-synaptic term (adding +-0 to a sum
+    // that started at +0 is a bitwise no-op), and in networks of rarely spiking neurons that is most of them: the
+    // staging pass records the others in `live`, the accumulation looks at nobody else.
+    if (stage) {
+        if (threadIdx.x < NG) M.live[threadIdx.x] = 0u;
+        __syncthreads();
         for (int b0 = warp; b0 < B; b0 += 8 * SNN_GEN_WARPS) {   // eight rows of the trace tile in flight per warp
             float tx[8];
             #pragma unroll
@@ -506,9 +514,15 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
             #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int b = b0 + q * SNN_GEN_WARPS;
-                if (b < B) M.xt[b * 32 + lane] = wdep ? tx[q] : tx[q] * C.nu0;
+                if (b < B) {
+                    const float v = wdep ? tx[q] : tx[q] * C.nu0;
+                    M.xt[b * 32 + lane] = v;
+                    const bool nzrow = __any_sync(0xffffffffu, v != 0.0f);
+                    if (lane == 0 && nzrow) atomicOr(M.live + (b >> 5), 1u << (b & 31));
+                }
             }
         }
+    }
 
     // column events: colmask[g*32 + lane] = samples of group g whose target spike hit column j
     uint32_t colany = 0;
@@ -581,7 +595,7 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
                     if (e0 + q < nev) xsw[(e0 + q) * 32 + lane] = xv[q];
             }
         }
-        uint32_t tmask = 0;
+        uint32_t tmask = 0, umask = 0;   // rows with a pre-synaptic spike / with a non-zero contribution to U
         if (pre_on) {
             for (int g0 = 0; g0 < NG; g0 += 8) {
                 uint32_t mine[8];
@@ -593,6 +607,13 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
                 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint32_t nz = __ballot_sync(0xffffffffu, mine[q] != 0u);
+                    {   // every spiking sample marks its rows; only the live ones are accumulated
+                        uint32_t orw = mine[q];
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) orw |= __shfl_xor_sync(0xffffffffu, orw, o);
+                        tmask |= orw;
+                    }
+                    if (stage && g0 + q < NG) nz &= M.live[g0 + q];
                     while (nz) {
                         const int bb = __ffs(nz) - 1;
                         nz &= nz - 1;
@@ -601,11 +622,14 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
                         float tx = 0.0f;
                         if (stage) {
                             tx = M.xt[b * 32 + lane];
-                        } else if (valid) {
-                            tx = __ldcg(G.L.x + (size_t)b * nt + j);
-                            if (!wdep) tx = tx * C.nu0;
+                        } else {
+                            if (valid) {
+                                tx = __ldcg(G.L.x + (size_t)b * nt + j);
+                                if (!wdep) tx = tx * C.nu0;
+                            }
+                            if (!__any_sync(0xffffffffu, tx != 0.0f)) continue;
                         }
-                        tmask |= word;
+                        umask |= word;
                         while (word) {
                             const int r = __ffs(word) - 1;
                             word &= word - 1;
@@ -616,7 +640,7 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
             }
         }
         __syncwarp();
-        if (!full && !tmask && !any_col) continue;
+        if (!full && !(wdep ? tmask : umask) && !any_col) continue;
         for (int r0 = 0; r0 < 32; r0 += 8) {
             bool nd[8];
             bool anyneed = false;
@@ -624,7 +648,11 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
             for (int q = 0; q < 8; ++q) {
                 const int r = r0 + q, i = i0 + r;
                 const bool pre_t = (tmask >> r) & 1u;
-                nd[q] = valid && i < ns && (full || pre_t || post_t);
+                // a row whose U is +0 in every column is left alone: w - 0 is w, and w has been inside [wmin, wmax] since
+                // the full pass of step 0 (the weight-dependent and Hebbian forms compute w + (+-0), which may flip
+                // the sign of a zero: they always rewrite)
+                const bool touched = wdep ? pre_t : ((umask >> r) & 1u) != 0u;
+                nd[q] = valid && i < ns && (full || touched || post_t);
                 if (!eager) wv[q] = nd[q] ? __ldcg(C.w + (size_t)i * nt + j) : 0.0f;
                 anyneed |= nd[q];
             }
@@ -663,7 +691,7 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
             }
             #pragma unroll
             for (int q = 0; q < 8; ++q)
-                if ((tmask >> (r0 + q)) & 1u) acc[(r0 + q) * 32 + lane] = 0.0f;
+                if ((umask >> (r0 + q)) & 1u) acc[(r0 + q) * 32 + lane] = 0.0f;
             if (eager) {
                 #pragma unroll
                 for (int q = 0; q < 8; ++q) wv[q] = wn[q];
