@@ -84,7 +84,7 @@ __device__ __forceinline__ float ld_ext(const snn_layer_t &L, size_t idx, bool &
 // with a Weight feature (topology.py:437-479, topology_features.py:633-645) without ever
 // materialising the [B, n_src, n_tgt] broadcast.  Per block of 32 words (1024 source neurons) the warp
 // first compacts the set bits into an ascending index list in shared memory (ballot-free prefix sum of
-// the lanes' popcounts), then walks the list eight entries at a time so that eight weight rows are in
+// the lanes' popcounts), then walks the list sixteen entries at a time so that sixteen weight rows are in
 // flight from L2 at once — the sum itself stays one fp32 add per spike in ascending i, like the oracle.
 // Weights are read with ld.cg: the CTA that updates a tile in the learning phase is not the CTA that
 // gathers from it.
@@ -128,15 +128,15 @@ __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__r
             }
             __syncwarp();
             const int base = (s0 + 32 * kb) * 32;
-            for (int e = 0; e < total; e += 8) {
-                float v[8];
+            for (int e = 0; e < total; e += 16) {
+                float v[16];
                 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 16; ++k) {
                     const int i = base + (int)lst[min(e + k, total - 1)];
                     v[k] = (valid && e + k < total && i < n_src) ? __ldcg(wcol + (size_t)i * n_tgt) : 0.0f;
                 }
                 #pragma unroll
-                for (int k = 0; k < 8; ++k)
+                for (int k = 0; k < 16; ++k)
                     if (e + k < total) p = p + v[k];
             }
             __syncwarp();
@@ -306,21 +306,30 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
             ++nin;
         }
 
-    for (int b = b0 + warp; b < b1; b += SNN_GEN_WARPS) {
-        const size_t k = (size_t)b * n + j;
-        // every independent load of the sample first: bit words of the dense inputs, then the state
-        uint32_t fw[4], af[4];   // first bit words; "the sample spiked at all" flags of wide sources
+    // first bit words of the dense inputs and the "sample spiked at all" flags of wide sources, fetched one sample
+    // ahead: the gather of sample b starts without waiting for L2
+    uint32_t fwn[4], afn[4];
+    auto prefetch = [&](int b) {
         #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            fw[q] = 0u; af[q] = 1u;
-            if (q < ncl && N.conns[cl[q]].kind != SNN_CONN_CONV2D) {
+            fwn[q] = 0u; afn[q] = 1u;
+            if (q < ncl && b < b1 && N.conns[cl[q]].kind != SNN_CONN_CONV2D) {
                 const snn_conn_t &C = N.conns[cl[q]];
                 const DevLayer &S = N.layers[C.src];
                 const int slot = (N.one_step && C.src < li) ? wr : rd;
-                if (lane < S.nw) fw[q] = __ldcg(S.bits + ((size_t)slot * B + b) * S.nw + lane);
-                if (S.anyf) af[q] = __ldcg(S.anyf + (size_t)(slot == wr ? t % 3 : (t + 2) % 3) * B + b);
+                if (lane < S.nw) fwn[q] = __ldcg(S.bits + ((size_t)slot * B + b) * S.nw + lane);
+                if (S.anyf) afn[q] = __ldcg(S.anyf + (size_t)(slot == wr ? t % 3 : (t + 2) % 3) * B + b);
             }
         }
+    };
+    prefetch(b0 + warp);
+
+    for (int b = b0 + warp; b < b1; b += SNN_GEN_WARPS) {
+        const size_t k = (size_t)b * n + j;
+        uint32_t fw[4], af[4];
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) { fw[q] = fwn[q]; af[q] = afn[q]; }
+        prefetch(b + SNN_GEN_WARPS);
         float v = 0.0f, rc = 0.0f, xold = 0.0f, ic = 0.0f;
         if (valid) {
             v = L.v[k];
@@ -641,6 +650,35 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
         }
         __syncwarp();
         if (!full && !(wdep ? tmask : umask) && !any_col) continue;
+        // Columns with a post-synaptic event change in every row.  They are few (one spiking neuron in the tile is
+        // the rule), so each is rewritten with one lane per ROW — one pass of the rule for all 32 rows of the group —
+        // instead of dragging the whole warp through 32 row iterations for the sake of one lane.
+        const uint32_t evcols = __ballot_sync(0xffffffffu, post_t);
+        for (uint32_t ec = evcols; ec; ec &= ec - 1) {
+            const int jl = __ffs(ec) - 1, jc = tile * SNN_TILE + jl, i = i0 + lane;
+            if (i < ns) {
+                const bool pre_t = (tmask >> lane) & 1u;
+                float U = 0.0f, V = 0.0f;
+                if (pre_t) {
+                    U = acc[lane * 32 + jl];
+                    if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
+                }
+                for (int g = 0; g < NG; ++g) {
+                    uint32_t m = M.colmask[g * 32 + jl];
+                    while (m) {
+                        const int b = g * 32 + __ffs(m) - 1;
+                        m &= m - 1;
+                        const int slot = M.evslot[b];
+                        const float xs = slot != 0xFF ? xsw[slot * 32 + lane] : __ldcg(S.xpub + ((size_t)wr * B + b) * ns + i);
+                        V = V + xs * (wdep ? 1.0f : C.nu1);
+                    }
+                }
+                if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
+                float *wp = C.w + (size_t)i * nt + jc;
+                *wp = apply_rule(C, __ldcg(wp), U, pre_t, V, true);
+            }
+        }
+        __syncwarp();
         for (int r0 = 0; r0 < 32; r0 += 8) {
             bool nd[8];
             bool anyneed = false;
@@ -652,7 +690,7 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
                 // the full pass of step 0 (the weight-dependent and Hebbian forms compute w + (+-0), which may flip
                 // the sign of a zero: they always rewrite)
                 const bool touched = wdep ? pre_t : ((umask >> r) & 1u) != 0u;
-                nd[q] = valid && i < ns && (full || touched || post_t);
+                nd[q] = valid && i < ns && !post_t && (full || touched);   // event columns: done above
                 if (!eager) wv[q] = nd[q] ? __ldcg(C.w + (size_t)i * nt + j) : 0.0f;
                 anyneed |= nd[q];
             }
@@ -667,25 +705,12 @@ __device__ void phase3(const DevNet &N, int ci, int tile, int wg0, int wg1, int 
                     const int r = r0 + q, i = i0 + r;
                     const bool pre_t = (tmask >> r) & 1u;
                     if (nd[q]) {
-                        float U = 0.0f, V = 0.0f;
+                        float U = 0.0f;
                         if (pre_t) {
                             U = acc[r * 32 + lane];
                             if (C.reduction == SNN_REDUCE_MEAN) U = U / Bf;
                         }
-                        if (post_t) {
-                            for (int g = 0; g < NG; ++g) {
-                                uint32_t m = M.colmask[g * 32 + lane];
-                                while (m) {
-                                    const int b = g * 32 + __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const int slot = M.evslot[b];
-                                    const float xs = slot != 0xFF ? xsw[slot * 32 + r] : __ldcg(S.xpub + ((size_t)wr * B + b) * ns + i);
-                                    V = V + xs * (wdep ? 1.0f : C.nu1);
-                                }
-                            }
-                            if (C.reduction == SNN_REDUCE_MEAN) V = V / Bf;
-                        }
-                        C.w[(size_t)i * nt + j] = apply_rule(C, wv[q], U, pre_t, V, post_t);
+                        C.w[(size_t)i * nt + j] = apply_rule(C, wv[q], U, pre_t, 0.0f, false);
                     }
                 }
             }
