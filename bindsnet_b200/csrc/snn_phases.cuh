@@ -156,6 +156,32 @@ __device__ __forceinline__ float gather_conv(const snn_conn_t &C, const uint32_t
     const int co = j / L, l = j - co * L, oy = l / C.wout, ox = l - oy * C.wout;
     const int KK = C.kh * C.kw;
     float p = 0.0f;
+    if (C.dw == 1 && C.kw <= 32) {
+        // the kw taps of one filter row look at kw CONSECUTIVE source bits: cut that window out of the bit row (two
+        // words, one funnel shift) and visit its set bits only — ascending kx, so the order of the sum is unchanged
+        const int ix0 = ox * C.sw - C.pw;
+        const int kx_lo = max(0, -ix0), kx_hi = min(C.kw, C.win - ix0);
+        if (kx_hi > kx_lo) {
+            const int cnt = kx_hi - kx_lo;
+            const uint32_t cmask = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+            for (int ci = 0; ci < C.cin; ++ci)
+                for (int ky = 0; ky < C.kh; ++ky) {
+                    const int iy = oy * C.sh - C.ph + ky * C.dh;
+                    if (iy < 0 || iy >= C.hin) continue;
+                    const int bit0 = (ci * C.hin + iy) * C.win + ix0 + kx_lo, w0 = bit0 >> 5, sft = bit0 & 31;
+                    const uint32_t lo = STAGED_BITS ? sb[w0] : __ldcg(sb + w0);
+                    const uint32_t hi = sft + cnt > 32 ? (STAGED_BITS ? sb[w0 + 1] : __ldcg(sb + w0 + 1)) : 0u;
+                    uint32_t bits = __funnelshift_r(lo, hi, sft) & cmask;
+                    const int k0 = (ci * C.kh + ky) * C.kw + kx_lo;
+                    while (bits) {
+                        const int k = k0 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        p = p + (STAGED_TAPS ? taps[(co - co_base) * C.cin * KK + k] : __ldcg(C.w + (size_t)co * C.cin * KK + k));
+                    }
+                }
+        }
+        return p + C.b[co];
+    }
     for (int ci = 0; ci < C.cin; ++ci)
         for (int ky = 0; ky < C.kh; ++ky) {
             const int iy = oy * C.sh - C.ph + ky * C.dh;
@@ -1030,6 +1056,13 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int cta, int ncta, int t, 
         const bool staged = S.nw + G.nw <= SNN_CONV_STAGE_WORDS;
         uint32_t *sb_s = (uint32_t *)GS.xs, *gb_s = (uint32_t *)GS.xs + S.nw;
         float *pm_s = GS.acc;
+        // the sample's source spikes as an ascending list of (src << 16 | iy << 8 | ix), decoded once per unit instead
+        // of once per (filter tap, spike); it shares the 16 KB region with the two bit rows
+        uint32_t *slist = (uint32_t *)GS.xs + S.nw + G.nw;
+        const int slist_cap = staged ? SNN_CONV_STAGE_WORDS - S.nw - G.nw - (C.cin + 2) : 0;
+        int32_t *seg = (int32_t *)(slist + (slist_cap > 0 ? slist_cap : 0));   // [cin + 1] first list entry of every input channel
+        const bool listed = staged && ns <= 65535 && C.hin <= 256 && C.win <= 256 && slist_cap >= ns;
+        const bool unit_stride = C.sh == 1 && C.sw == 1;
         for (int u = cta; u < B * nch; u += ncta) {
             const int b = u / nch, ch = u - b * nch;
             const int co0 = ch * cpc, co1 = min(C.cout, co0 + cpc);
@@ -1054,6 +1087,38 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int cta, int ncta, int t, 
             }
             if (staged || stage_pm) __syncthreads();
             const uint32_t *sb = staged ? sb_s : sbg, *gb = staged ? gb_s : gbg;
+            if (listed) {
+                if (warp == 0) {   // ordered compaction of the set bits, 32 words at a time
+                    int n_ent = 0;
+                    for (int w0 = 0; w0 < S.nw; w0 += 32) {
+                        uint32_t mine = w0 + lane < S.nw ? sb_s[w0 + lane] : 0u;
+                        const int cnt = __popc(mine);
+                        int pre = cnt;
+                        #pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                            if (lane >= o) pre += v;
+                        }
+                        int q = n_ent + pre - cnt;
+                        n_ent += __shfl_sync(0xffffffffu, pre, 31);
+                        while (mine) {
+                            const int src = (w0 + lane) * 32 + __ffs(mine) - 1;
+                            mine &= mine - 1;
+                            const int r = src % (C.hin * C.win), iy = r / C.win, ix = r - iy * C.win;
+                            slist[q++] = ((uint32_t)src << 16) | ((uint32_t)iy << 8) | (uint32_t)ix;
+                        }
+                    }
+                    __syncwarp();
+                    // seg[c] = number of entries whose source index lies below channel c
+                    for (int c = lane; c <= C.cin; c += 32) {
+                        const uint32_t lim = (uint32_t)(c * C.hin * C.win);
+                        int lo = 0, hi = n_ent;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((slist[mid] >> 16) < lim) lo = mid + 1; else hi = mid; }
+                        seg[c] = lo;
+                    }
+                }
+                __syncthreads();
+            }
             for (int e = threadIdx.x; e < (co1 - co0) * K; e += SNN_GEN_THREADS) {
                 const int co = co0 + e / K, k = e - (co - co0) * K;
                 const int ci = k / KK, kk = k - ci * KK, ky = kk / C.kw, kx = kk - ky * C.kw;
@@ -1071,7 +1136,28 @@ __device__ void phase3_conv(const DevNet &N, int ci_, int cta, int ncta, int t, 
                     const bool ss = ((staged ? sb[src >> 5] : __ldcg(sb + (src >> 5))) >> (src & 31)) & 1u;
                     s1 = s1 + mst_trace(__ldcg(ppb + src), C.p_plus_decay, C.a_plus, ss);
                 }
-                // pre-synaptic spikes of channel ci, four trace loads in flight
+                // pre-synaptic spikes of channel ci
+                if (listed) {
+                    const int e1 = seg[ci + 1];
+                    for (int q = seg[ci]; q < e1; ++q) {
+                        const uint32_t ent = slist[q];
+                        const int ty = (int)((ent >> 8) & 255u) + C.ph - ky, tx = (int)(ent & 255u) + C.pw - kx;
+                        if (ty < 0 || tx < 0) continue;
+                        int oy = ty, ox = tx;
+                        if (!unit_stride) {
+                            oy = ty / C.sh; ox = tx / C.sw;
+                            if (oy * C.sh != ty || ox * C.sw != tx) continue;
+                        }
+                        if (oy >= C.hout || ox >= C.wout) continue;
+                        const int tgt = co * L + oy * C.wout + ox;
+                        const float pv = stage_pm ? pm_s[tgt - co0 * L] : __ldcg(pmb + tgt);
+                        const bool ts = (gb[tgt >> 5] >> (tgt & 31)) & 1u;
+                        s2 = s2 + mst_trace(pv, C.p_minus_decay, C.a_minus, ts);
+                    }
+                    M.el[out][(size_t)b * NWT + (size_t)co * K + k] = s1 + s2;
+                    continue;
+                }
+                // ... the same walk straight off the bit row (shapes the list does not cover), four trace loads in flight
                 const int cbase = ci * C.hin * C.win;
                 it.init(sb, cbase, cbase + C.hin * C.win, staged);
                 bool done = false;
