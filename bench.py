@@ -391,9 +391,10 @@ def c4_roofline(B: int, T: int, ms: float) -> dict:
     ach = per_step * T / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "kernel_ms": ms,
             "algorithmic_bytes_per_timestep": per_step, "peak_source": src,
-            "note": "generic tier; this configuration is latency / occupancy-bound, not HBM-bound (SURVEY.md 8d: 0.14 us per step at the HBM "
-                    "peak): the limiter is the grid barriers of a step (3) and the per-step streaming of the [B,12544] neuron / trace / "
-                    "rule state (19 MB) through L2, which the algorithmic figure counts as resident"}
+            "note": "generic tier; this configuration is not HBM-bound (SURVEY.md 8d: 0.14 us per step at the HBM peak): measured limiter = "
+                    "instruction issue (ncu: 88 M warp-instructions per timestep, 1.1 IPC per SM at 25 % occupancy — the conv gather, the "
+                    "per-sample eligibility and the [B,12544] neuron / trace / rule state streamed through L2 every step, which the "
+                    "algorithmic figure counts as resident) plus three grid barriers per step"}
 
 
 def main():

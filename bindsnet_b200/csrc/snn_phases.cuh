@@ -84,7 +84,7 @@ __device__ __forceinline__ float ld_ext(const snn_layer_t &L, size_t idx, bool &
 // with a Weight feature (topology.py:437-479, topology_features.py:633-645) without ever
 // materialising the [B, n_src, n_tgt] broadcast.  Per block of 32 words (1024 source neurons) the warp
 // first compacts the set bits into an ascending index list in shared memory (ballot-free prefix sum of
-// the lanes' popcounts), then walks the list sixteen entries at a time so that sixteen weight rows are in
+// the lanes' popcounts), then walks the list eight entries at a time so that eight weight rows are in
 // flight from L2 at once — the sum itself stays one fp32 add per spike in ascending i, like the oracle.
 // Weights are read with ld.cg: the CTA that updates a tile in the learning phase is not the CTA that
 // gathers from it.
@@ -128,15 +128,15 @@ __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__r
             }
             __syncwarp();
             const int base = (s0 + 32 * kb) * 32;
-            for (int e = 0; e < total; e += 16) {
-                float v[16];
+            for (int e = 0; e < total; e += 8) {
+                float v[8];
                 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < 8; ++k) {
                     const int i = base + (int)lst[min(e + k, total - 1)];
                     v[k] = (valid && e + k < total && i < n_src) ? __ldcg(wcol + (size_t)i * n_tgt) : 0.0f;
                 }
                 #pragma unroll
-                for (int k = 0; k < 16; ++k)
+                for (int k = 0; k < 8; ++k)
                     if (e + k < total) p = p + v[k];
             }
             __syncwarp();
@@ -149,39 +149,61 @@ __device__ __forceinline__ float gather(const snn_conn_t &C, const uint32_t *__r
 // sample: the sum of the filter taps whose (zero-padded) input position spiked, in ascending
 // (ci, ky, kx) order, then the bias.  STAGED: the sample's source bit row and the filter taps of the
 // tile's output channels sit in shared memory (phase 1 stages them once per work unit).
-template <bool STAGED_BITS, bool STAGED_TAPS>
-__device__ __forceinline__ float gather_conv(const snn_conn_t &C, const uint32_t *sb, const float *taps, int co_base, int j, bool valid) {
-    if (!valid) return 0.0f;
+// The part of the gather that depends on the target neuron only (not on the sample): computed once per work unit.
+struct ConvGeo {
+    int co;                // output channel of neuron j
+    int y0, x0;            // source row of filter row 0 (oy*sh - ph); source column of the first VALID tap of a filter row
+    int kx_lo, cnt;        // first valid tap of a filter row, number of valid taps
+    int ky_lo, ky_hi;      // valid filter rows (source row inside the image)
+};
+__device__ __forceinline__ ConvGeo conv_geo(const snn_conn_t &C, int j, bool valid) {
+    ConvGeo g;
     const int L = C.hout * C.wout;
-    const int co = j / L, l = j - co * L, oy = l / C.wout, ox = l - oy * C.wout;
+    g.co = valid ? j / L : 0;
+    const int l = valid ? j - g.co * L : 0;
+    const int oy = l / C.wout, ox = l - oy * C.wout;
+    const int ix0 = ox * C.sw - C.pw;
+    g.kx_lo = max(0, -ix0);
+    g.x0 = ix0 + g.kx_lo;
+    g.cnt = min(C.kw, C.win - ix0) - g.kx_lo;
+    // rows: iy = y0 + ky*dh in [0, hin)
+    g.y0 = oy * C.sh - C.ph;
+    g.ky_lo = g.y0 < 0 ? (-g.y0 + C.dh - 1) / C.dh : 0;
+    g.ky_hi = min(C.kh, g.y0 >= C.hin ? 0 : (C.hin - 1 - g.y0) / C.dh + 1);
+    return g;
+}
+
+template <bool STAGED_BITS, bool STAGED_TAPS>
+__device__ __forceinline__ float gather_conv(const snn_conn_t &C, const uint32_t *sb, const float *taps, int co_base, int j, bool valid,
+                                             const ConvGeo &g) {
+    if (!valid) return 0.0f;
+    const int co = g.co;
     const int KK = C.kh * C.kw;
     float p = 0.0f;
     if (C.dw == 1 && C.kw <= 32) {
         // the kw taps of one filter row look at kw CONSECUTIVE source bits: cut that window out of the bit row (two
         // words, one funnel shift) and visit its set bits only — ascending kx, so the order of the sum is unchanged
-        const int ix0 = ox * C.sw - C.pw;
-        const int kx_lo = max(0, -ix0), kx_hi = min(C.kw, C.win - ix0);
-        if (kx_hi > kx_lo) {
-            const int cnt = kx_hi - kx_lo;
-            const uint32_t cmask = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        if (g.cnt > 0) {
+            const float *tp = STAGED_TAPS ? taps + (co - co_base) * C.cin * KK : C.w + (size_t)co * C.cin * KK;
+            const uint32_t cmask = g.cnt >= 32 ? 0xffffffffu : ((1u << g.cnt) - 1u);
             for (int ci = 0; ci < C.cin; ++ci)
-                for (int ky = 0; ky < C.kh; ++ky) {
-                    const int iy = oy * C.sh - C.ph + ky * C.dh;
-                    if (iy < 0 || iy >= C.hin) continue;
-                    const int bit0 = (ci * C.hin + iy) * C.win + ix0 + kx_lo, w0 = bit0 >> 5, sft = bit0 & 31;
+                for (int ky = g.ky_lo; ky < g.ky_hi; ++ky) {
+                    const int iy = g.y0 + ky * C.dh;
+                    const int bit0 = (ci * C.hin + iy) * C.win + g.x0, w0 = bit0 >> 5, sft = bit0 & 31;
                     const uint32_t lo = STAGED_BITS ? sb[w0] : __ldcg(sb + w0);
-                    const uint32_t hi = sft + cnt > 32 ? (STAGED_BITS ? sb[w0 + 1] : __ldcg(sb + w0 + 1)) : 0u;
+                    const uint32_t hi = sft + g.cnt > 32 ? (STAGED_BITS ? sb[w0 + 1] : __ldcg(sb + w0 + 1)) : 0u;
                     uint32_t bits = __funnelshift_r(lo, hi, sft) & cmask;
-                    const int k0 = (ci * C.kh + ky) * C.kw + kx_lo;
+                    const int k0 = (ci * C.kh + ky) * C.kw + g.kx_lo;
                     while (bits) {
                         const int k = k0 + __ffs(bits) - 1;
                         bits &= bits - 1;
-                        p = p + (STAGED_TAPS ? taps[(co - co_base) * C.cin * KK + k] : __ldcg(C.w + (size_t)co * C.cin * KK + k));
+                        p = p + (STAGED_TAPS ? tp[k] : __ldcg(tp + k));
                     }
                 }
         }
         return p + C.b[co];
     }
+    const int L = C.hout * C.wout, l = j - co * L, oy = l / C.wout, ox = l - oy * C.wout;   // dilated columns: tap by tap
     for (int ci = 0; ci < C.cin; ++ci)
         for (int ky = 0; ky < C.kh; ++ky) {
             const int iy = oy * C.sh - C.ph + ky * C.dh;
@@ -292,11 +314,13 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
     // a convolutional input: stage the chunk's source bit rows and the taps of this tile's output channels
     int conv_c = -1, conv_slot = 0, co_base = 0;
     bool st_bits = false, st_taps = false;
+    ConvGeo geo = {};
     for (int c = 0; c < N.n_conns && conv_c < 0; ++c)
         if (N.conns[c].tgt == li && N.conns[c].kind == SNN_CONN_CONV2D) conv_c = c;
     if (conv_c >= 0) {
         const snn_conn_t &C = N.conns[conv_c];
         const DevLayer &S = N.layers[C.src];
+        geo = conv_geo(C, j, valid);
         conv_slot = (N.one_step && C.src < li) ? wr : rd;
         const int words = (b1 - b0) * S.nw;
         st_bits = words <= SNN_CONV_STAGE_WORDS;
@@ -385,11 +409,11 @@ __device__ void phase1(const DevNet &N, int li, int tile, int chunk, int t, cons
                 const uint32_t *gsb = S.bits + ((size_t)slot * B + b) * S.nw;
                 if (c == conv_c && st_bits) {
                     const uint32_t *ssb = M.cbits + (size_t)(b - b0) * S.nw;
-                    p = st_taps ? gather_conv<true, true>(C, ssb, M.xs, co_base, j, valid) : gather_conv<true, false>(C, ssb, nullptr, 0, j, valid);
+                    p = st_taps ? gather_conv<true, true>(C, ssb, M.xs, co_base, j, valid, geo) : gather_conv<true, false>(C, ssb, nullptr, 0, j, valid, geo);
                 } else if (c == conv_c && st_taps) {
-                    p = gather_conv<false, true>(C, gsb, M.xs, co_base, j, valid);
+                    p = gather_conv<false, true>(C, gsb, M.xs, co_base, j, valid, geo);
                 } else {
-                    p = gather_conv<false, false>(C, gsb, nullptr, 0, j, valid);
+                    p = gather_conv<false, false>(C, gsb, nullptr, 0, j, valid, c == conv_c ? geo : conv_geo(C, j, valid));
                 }
             } else {
                 const uint32_t *sbr = S.bits + ((size_t)slot * B + b) * S.nw;
