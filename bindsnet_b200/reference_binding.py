@@ -22,7 +22,10 @@ import torch
 
 from . import _abi
 
-_KIND = {"Input": _abi.SNN_NODE_INPUT, "LIFNodes": _abi.SNN_NODE_LIF, "DiehlAndCookNodes": _abi.SNN_NODE_DC}
+_KIND = {"Input": _abi.SNN_NODE_INPUT, "LIFNodes": _abi.SNN_NODE_LIF, "DiehlAndCookNodes": _abi.SNN_NODE_DC,
+         "AdaptiveLIFNodes": _abi.SNN_NODE_DC,            # DiehlAndCookNodes.forward without the one-spike arbitration (nodes.py:921-946)
+         "IFNodes": _abi.SNN_NODE_IF, "CurrentLIFNodes": _abi.SNN_NODE_CURRENT_LIF, "BoostedLIFNodes": _abi.SNN_NODE_BOOSTED_LIF,
+         "McCullochPitts": _abi.SNN_NODE_MCP}
 
 
 def _f(x) -> float:
@@ -60,18 +63,28 @@ def fill_layer(d: "_abi.SnnLayer", layer, B: int, keep: List[torch.Tensor]) -> N
         layer.s = torch.zeros(B, *layer.shape, dtype=torch.bool, device=layer.s.device)
     d.s = _u8(layer.s).data_ptr()
     if kind != _abi.SNN_NODE_INPUT:
-        d.v, d.refrac_count = layer.v.data_ptr(), layer.refrac_count.data_ptr()
-        d.decay = _f(layer.decay)                                                         # nodes.py:546-548, 1128-1130
-        d.rest, d.reset, d.thresh, d.refrac = _f(layer.rest), _f(layer.reset), _f(layer.thresh), _f(layer.refrac)
+        d.v = layer.v.data_ptr()
+        d.thresh = _f(layer.thresh)
+        if kind != _abi.SNN_NODE_MCP:                                                     # McCullochPitts: v = x, no other state
+            d.refrac_count, d.refrac = layer.refrac_count.data_ptr(), _f(layer.refrac)
+        if hasattr(layer, "decay") and kind not in (_abi.SNN_NODE_IF, _abi.SNN_NODE_MCP):
+            d.decay = _f(layer.decay)                                                     # nodes.py:546-548, 1128-1130
+        if hasattr(layer, "rest"):
+            d.rest = _f(layer.rest)
+        if hasattr(layer, "reset"):
+            d.reset = _f(layer.reset)
         lb = getattr(layer, "lbound", None)
         d.has_lbound, d.lbound = int(lb is not None), (_f(lb) if lb is not None else 0.0)
+    if kind == _abi.SNN_NODE_CURRENT_LIF:
+        d.i, d.i_decay = layer.i.data_ptr(), _f(layer.i_decay)                            # nodes.py:771, 818-820
     if kind == _abi.SNN_NODE_DC:
         d.theta = layer.theta.data_ptr()
         d.theta_plus, d.theta_decay = _f(layer.theta_plus), _f(layer.theta_decay)         # nodes.py:1131-1133
-        d.one_spike = int(layer.one_spike)
+        d.one_spike = int(getattr(layer, "one_spike", False))
 
 
-def fill_connection(d: "_abi.SnnConn", conn, src: int, tgt: int, dt: float) -> None:
+def fill_connection(d: "_abi.SnnConn", conn, src: int, tgt: int, dt: float, keep: Optional[List[torch.Tensor]] = None) -> None:
+    keep = keep if keep is not None else []
     d.src, d.tgt = src, tgt
     d.weight_decay, d.dt_scale = 1.0, 1.0
     if hasattr(conn, "pipeline"):
@@ -101,13 +114,20 @@ def fill_connection(d: "_abi.SnnConn", conn, src: int, tgt: int, dt: float) -> N
             raise NotImplementedError(f"MCC learning rule {name}")
     else:
         # Connection (topology.py:265-399) + learning.LearningRule (learning.py:31-104)
-        if type(conn).__name__ != "Connection":
+        if type(conn).__name__ not in ("Connection", "LocalConnection"):
             raise NotImplementedError(f"{type(conn).__name__} is outside the accelerated path")
         rule = conn.update_rule
         d.kind = _abi.SNN_CONN_DENSE
         w = conn.w
         d.has_norm = int(conn.norm is not None)                                           # topology.py:383-392: sum of |w|
         d.norm, d.norm_abs = (_f(conn.norm) if conn.norm is not None else 0.0), 1
+        if type(conn).__name__ == "LocalConnection":
+            # a dense matrix confined to its receptive fields by the connection's own mask (topology.py:1431, 1457-1469),
+            # plain column sums in normalize (:1471-1479; norm is already scaled by the kernel size, :1437-1438)
+            d.norm_abs = 0
+            m = _u8(conn.mask.to(w.device)).contiguous()
+            keep.append(m)
+            d.mask = m.data_ptr()
         d.wmin, d.wmax = _f(conn.wmin), _f(conn.wmax)
         name = type(rule).__name__
         d.rule = {"NoOp": _abi.SNN_RULE_NOOP, "PostPre": _abi.SNN_RULE_POSTPRE, "Hebbian": _abi.SNN_RULE_HEBBIAN,
@@ -155,7 +175,7 @@ def build_net(network, inputs: Dict[str, torch.Tensor], T: int, B: int):
             net.layers[i].ext_dtype = _abi.SNN_EXT_F32 if x.dtype == torch.float32 else _abi.SNN_EXT_U8
             keep.append(x)
     for i, ((s, t), conn) in enumerate(network.connections.items()):
-        fill_connection(net.conns[i], conn, names.index(s), names.index(t), float(network.dt))
+        fill_connection(net.conns[i], conn, names.index(s), names.index(t), float(network.dt), keep)
     return net, keep
 
 

@@ -103,3 +103,47 @@ def test_abi_filled_from_reference_connection_postpre_matches_reference_run():
     a, b = _twin(build)
     x = cases._bernoulli_inputs(70, 5, (100,), 0.15, 8)
     _run_both(a, b, x, 70)
+
+
+@pytest.mark.parametrize("kind", ["IFNodes", "CurrentLIFNodes", "AdaptiveLIFNodes", "BoostedLIFNodes", "McCullochPitts"])
+def test_abi_filled_from_the_other_reference_neuron_models(kind):
+    """The remaining node kinds of the ABI, each as the learned target of a reference ``Connection`` + ``PostPre``."""
+    def build():
+        net = REF.Network(dt=1.0, batch_size=3)
+        X = REF.nodes.Input(n=70, traces=True)
+        kw = dict(IFNodes=dict(thresh=-50.0, reset=-64.0, refrac=3, lbound=-66.0),
+                  CurrentLIFNodes=dict(thresh=-55.0, rest=-65.0, reset=-63.0, refrac=2, tc_decay=40.0, tc_i_decay=3.0),
+                  AdaptiveLIFNodes=dict(thresh=-56.0, rest=-65.0, reset=-62.0, refrac=2, tc_decay=50.0, theta_plus=0.4, tc_theta_decay=200.0),
+                  BoostedLIFNodes=dict(thresh=9.0, refrac=3, tc_decay=30.0),
+                  McCullochPitts=dict(thresh=7.0))[kind]
+        Y = getattr(REF.nodes, kind)(n=36, traces=True, **kw)
+        c = REF.topology.Connection(X, Y, w=1.2 * torch.rand(70, 36), update_rule=REF.learning.PostPre, nu=(2e-3, 2e-2),
+                                    reduction=torch.sum, wmin=0.0, wmax=1.5, norm=18.0)
+        net.add_layer(X, "X"); net.add_layer(Y, "Y")
+        net.add_connection(c, "X", "Y")
+        return net
+
+    a, b = _twin(build)
+    x = cases._bernoulli_inputs(90, 3, (70,), 0.15, 62)
+    _run_both(a, b, x, 90)
+    assert int(a.layers["Y"].s.sum()) >= 0 and float(a.connections[("X", "Y")].w.sum()) > 0
+
+
+def test_abi_filled_from_reference_localconnection_matches_reference_run():
+    """``LocalConnection`` (topology.py:1304-1484): the binding passes the connection's own mask and the plain-sum
+    normalisation; batch size 1, the only one the reference's ``compute`` supports (:1455)."""
+    def build():
+        net = REF.Network(dt=1.0, batch_size=1)
+        X = REF.nodes.Input(n=64, traces=True)
+        Y = REF.nodes.LIFNodes(n=72, traces=True, thresh=-60.0, rest=-65.0, reset=-64.0, refrac=2, tc_decay=50.0)
+        probe = REF.topology.LocalConnection(X, Y, kernel_size=3, stride=1, n_filters=2)
+        w = 0.9 * torch.rand(64, 72) * (~probe.mask.bool()).float()
+        c = REF.topology.LocalConnection(X, Y, kernel_size=3, stride=1, n_filters=2, w=w, update_rule=REF.learning.PostPre, nu=(2e-3, 2e-2),
+                                         reduction=torch.sum, wmin=0.0, wmax=1.0, norm=0.35)
+        net.add_layer(X, "X"); net.add_layer(Y, "Y")
+        net.add_connection(c, "X", "Y")
+        return net
+
+    a, b = _twin(build)
+    x = cases._bernoulli_inputs(100, 1, (64,), 0.2, 74)
+    _run_both(a, b, x, 100)
