@@ -1,5 +1,5 @@
-// snn_generic.cu — generic persistent window kernel (any topology of Input / IF / LIF / CurrentLIF /
-// DiehlAndCook populations joined by dense and convolutional connections).
+// snn_generic.cu — generic persistent window kernel (any topology of Input / McCullochPitts / IF / LIF / BoostedLIF /
+// CurrentLIF / DiehlAndCook populations joined by dense and convolutional connections).
 //
 // One cooperative grid iterates the whole T-step window of Network.run (reference:
 // bindsnet/network/network.py:380-465) with at most four grid barriers per step and no host involvement.
@@ -31,8 +31,9 @@ __device__ __forceinline__ void item_of(const DevNet &N, int item, int &li, int 
     tile = item - N.layers[li].item0;
 }
 
-// CTAS = CTAs per SM the variant is compiled for: 3 (80 registers, a few spills) when the shared-memory footprint lets
-// three CTAs share an SM (B <= ~160), 2 (no register cap to speak of) otherwise.
+// CTAS = CTAs per SM the variant is compiled for: 2 (128 registers) is what runs — measured faster than 3 (80 registers,
+// spills) on B200 at the metric configuration and at config 4; the 3-CTA variant stays selectable for experiments
+// (SNN_B200_GVAR=3).
 template <int CTAS>
 __global__ void __launch_bounds__(SNN_GEN_THREADS, CTAS) snn_generic_window(const __grid_constant__ DevNet N) {
     extern __shared__ float smem[];

@@ -14,7 +14,9 @@ namespace {
 //                    convolutional gather (second 16 KB)
 //   xs      phase 3: per-warp staged pre-synaptic traces of the samples with a post-synaptic event (16 KB)
 //           phase 1: staged filter taps of a convolutional gather
-//   xt      phase 3: the target traces of the whole tile [B][32]; phase 3 (MSTDP): staged rule state
+//           phase 3 (conv MSTDP): the sample's two bit rows, its decoded source-spike list, the channel offsets
+//   xt      phase 3: the target traces of the whole tile [B][32]; phase 3 (dense MSTDP): staged rule state
+//   acc     phase 3 (conv MSTDP) also: the P- rows of the unit's output channels
 #define SNN_P3_MAXEV 16
 #define SNN_GATHER_BLOCK 1024   // source neurons per gather block (32 words): list capacity per warp
 #define SNN_CONV_STAGE_WORDS 4096   // staged source bit words of a conv gather (second half of acc)
