@@ -286,3 +286,62 @@ def test_mstdp_rule_state_and_eligibility_view():
         p = p * torch.exp(torch.tensor(-1.0) / r.tc_plus) + 1.0
     assert torch.allclose(r.p_plus, p.expand(2, 6))
     assert not torch.equal(c.w, 0.5 * torch.ones(6, 4))   # reward-modulated update happened
+
+
+def test_local_connection_structure_matches_the_reference():
+    """LocalConnection (topology.py:1304-1484): receptive-field structure (mask of the default initialisation), kernel-scaled
+    norm and the bias the reference always creates — compared with the live reference where it is available."""
+    from bindsnet_b200.network.topology import LocalConnection
+
+    X, Y = Input(n=64, traces=True), LIFNodes(n=2 * 36, traces=True)
+    c = LocalConnection(X, Y, kernel_size=3, stride=1, n_filters=2, norm=0.5, wmin=0.0, wmax=1.0)
+    assert c.w.shape == (64, 72) and c.mask.shape == (64, 72) and c.b.shape == (72,)
+    assert int((~c.mask).sum()) == 2 * 36 * 9                       # n_filters * conv_prod * kernel_prod weights inside the fields
+    assert torch.all(c.w[c.mask] == 0) and float(c.norm) == pytest.approx(0.5 * 9)
+    assert bool(((~c.mask).sum(0) == 9).all())                      # every target neuron sees exactly one 3x3 field
+    try:
+        import cases
+        ref = cases.namespace("reference")
+    except Exception:
+        return
+    rx, ry = ref.nodes.Input(n=64, traces=True), ref.nodes.LIFNodes(n=72, traces=True)
+    rc = ref.topology.LocalConnection(rx, ry, kernel_size=3, stride=1, n_filters=2, norm=0.5, wmin=0.0, wmax=1.0)
+    assert torch.equal(rc.mask.bool(), c.mask.bool()) and torch.equal(rc.locations, c.locations)
+    assert float(rc.norm) == pytest.approx(float(c.norm))
+    # rectangular input, stride 2
+    X2, Y2 = Input(n=6 * 8, traces=True), LIFNodes(n=3 * 3 * 3, traces=True)
+    c2 = LocalConnection(X2, Y2, kernel_size=(2, 4), stride=(2, 2), n_filters=3, input_shape=(6, 8))
+    rc2 = ref.topology.LocalConnection(ref.nodes.Input(n=48, traces=True), ref.nodes.LIFNodes(n=27, traces=True), kernel_size=(2, 4),
+                                       stride=(2, 2), n_filters=3, input_shape=(6, 8))
+    assert torch.equal(rc2.locations, c2.locations) and torch.equal(rc2.mask.bool(), c2.mask.bool())
+
+
+def test_boosted_lif_and_mcculloch_pitts_state_like_reference():
+    from bindsnet_b200.network.nodes import BoostedLIFNodes, McCullochPitts
+
+    l = BoostedLIFNodes(n=10, traces=True)
+    l.compute_decays(1.0); l.set_batch_size(2)
+    assert l.v.shape == (2, 10) and torch.all(l.v == 0) and torch.all(l.refrac_count == 0)   # nodes.py:668-678
+    assert float(l.thresh) == 13.0 and float(l.decay) == float(torch.exp(-torch.tensor(1.0) / torch.tensor(100.0)))
+    l.v.fill_(3.0); l.reset_state_variables()
+    assert torch.all(l.v == 0)                                                              # nodes.py:649-656
+    m = McCullochPitts(n=7)
+    m.compute_decays(1.0); m.set_batch_size(3)
+    assert m.v.shape == (3, 7) and float(m.thresh) == 1.0 and m.kind == _abi.SNN_NODE_MCP
+    m.v.fill_(2.0); m.reset_state_variables()
+    assert torch.all(m.v == 2.0)                                                            # nodes.py:290-295: v is not reset
+
+
+def test_mstdpet_state_and_eligibility_shapes():
+    net = Network(dt=1.0, batch_size=1)
+    X, Y = Input(n=6, traces=True), LIFNodes(n=4, traces=True, thresh=-64.0)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    c = Connection(X, Y, w=0.8 * torch.ones(6, 4), update_rule=MSTDPET, nu=5e-2, wmin=-1.0, wmax=1.0, tc_e_trace=10.0)
+    net.add_connection(c, "X", "Y")
+    with OracleBackend():
+        with pytest.raises(KeyError):
+            net.run({"X": torch.ones(3, 1, 6, dtype=torch.uint8)}, time=3)                 # learning.py:2218: kwargs["reward"]
+        net.run({"X": torch.ones(12, 1, 6, dtype=torch.uint8)}, time=12, reward=1.0)
+    r = c.update_rule
+    assert r.p_plus.shape == (1, 6) and r.p_minus.shape == (1, 4) and r.eligibility_trace.shape == (6, 4) and r.eligibility.shape == (6, 4)
+    assert float(r.eligibility_trace.abs().sum()) > 0 and float((c.w - 0.8).abs().sum()) > 0
