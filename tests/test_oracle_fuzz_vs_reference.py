@@ -138,3 +138,23 @@ def test_random_network_oracle_matches_live_reference(seed):
             assert not bad.any(), f"{what}: {k} max |d| {np.abs(a[k] - b[k]).max():.3e}"
     if seed == 0:
         assert sum(int(v.sum()) for k, v in a.items() if k.endswith("Y/s")) >= 0
+
+
+@pytest.mark.parametrize("seed", [1, 4, 9, 12, 16, 19])
+def test_random_network_oracle_dense_equals_sparse(seed):
+    """The oracle's costed dense restatement (zeros multiplied like the reference does) and its zero-skipping mode agree
+    bit for bit on the random networks too."""
+    from oracle.oracle import OracleBackend
+
+    spec = _draw(seed)
+    ns = cases.namespace("b200")
+    outs = []
+    for dense in (0, 1):
+        net, x = _build(ns, spec)
+        helpers.add_spike_monitors(net, spec["T"])
+        with OracleBackend(dense=dense) as ob:
+            net.run(inputs={"X": x}, time=spec["T"])
+            assert ob.err == 0
+        outs.append((helpers.snapshot(net), helpers.spike_counts(net, spec["T"])))
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], f"seed {seed} state")
+    helpers.assert_bit_identical(outs[0][1], outs[1][1], f"seed {seed} spike counts")
