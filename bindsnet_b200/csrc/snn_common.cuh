@@ -7,7 +7,11 @@
 // agree bit for bit.
 #pragma once
 
+#ifdef SNN_EMU   // tests/emu: the same sources compiled for the host on a small CUDA-model emulation (test infrastructure)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/snn_b200.h"
@@ -55,12 +59,20 @@ struct DevNet {
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+#ifdef SNN_EMU
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+#endif
 }
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+#ifdef SNN_EMU
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 
 // Grid barrier on ONE monotonic arrival counter in global memory: a release reduction to arrive (no return value:
@@ -71,18 +83,30 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
 // releases every present and future wait and is recognised as "abort" by whoever reads it.  The pollers back off
 // (nanosleep): in the generic kernel many CTAs wait here while others still stream state and weights through L2.
 __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nblocks, int32_t *err, unsigned int &gen) {
+#ifdef SNN_EMU
+    int &s_abort = emu::tls_cta->s_abort;
+#else
     __shared__ int s_abort;
+#endif
     ++gen;
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int target = gen * nblocks;
+#ifdef SNN_EMU
+        __atomic_fetch_add(bar, 1u, __ATOMIC_RELEASE);
+#else
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+#endif
         int ab = 0;
         const long long t0 = clock64();
         unsigned int ns = 20;
         for (;;) {
             unsigned int v;
+#ifdef SNN_EMU
+            v = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+#else
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+#endif
             if ((int)(v - target) >= 0) { ab = (v - target) >= 0x20000000u; break; }
             __nanosleep(ns);
             if (ns < 160) ns += 20;
@@ -93,7 +117,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nbl
                 break;
             }
         }
+#ifdef SNN_EMU
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
         s_abort = ab;
     }
     __syncthreads();

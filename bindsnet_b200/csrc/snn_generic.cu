@@ -36,7 +36,11 @@ __device__ __forceinline__ void item_of(const DevNet &N, int item, int &li, int 
 // (SNN_B200_GVAR=3).
 template <int CTAS>
 __global__ void __launch_bounds__(SNN_GEN_THREADS, CTAS) snn_generic_window(const __grid_constant__ DevNet N) {
+#ifdef SNN_EMU
+    float *smem = emu::tls_cta->dyn_smem;
+#else
     extern __shared__ float smem[];
+#endif
     const GenSmem M = gen_carve(smem, N.B);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int G = gridDim.x;
@@ -177,29 +181,9 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS, CTAS) snn_generic_window(cons
 
 size_t snn_generic_smem_bytes(int B) { return gen_smem_bytes(B); }
 
-// Launch the generic window: fills in the work decomposition (sample chunks, learning-phase units) for the grid
-// the device can keep co-resident.  Returns a cudaError_t cast to int.
-int snn_generic_launch(DevNet &N, cudaStream_t stream) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = snn_generic_smem_bytes(N.B);
-    // three CTAs per SM if their shared memory fits (227 KB per SM, 1 KB reserved per CTA), else two
-    // measured on B200 (metric configuration and config 4, profiles/): the three-CTA variant's spills cost more than its
-    // occupancy buys — two CTAs per SM unless SNN_B200_GVAR=3 asks for the experiment
-    bool three = false;
-    if (const char *v = getenv("SNN_B200_GVAR")) three = v[0] == '3' && 3 * (smem + 1024) <= 227 * 1024;
-    const void *kern = three ? (const void *)snn_generic_window<3> : (const void *)snn_generic_window<2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    e = three ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window<3>, SNN_GEN_THREADS, smem)
-              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window<2>, SNN_GEN_THREADS, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
-    if (per_sm > (three ? 3 : 2)) per_sm = three ? 3 : 2;
-    const int cap = sms * per_sm;
-
+// The work decomposition (sample chunks of phases 1 / 2, learning-phase units) for a grid of at most `cap` co-resident
+// CTAs; returns the grid size.
+static int plan_units(DevNet &N, int cap) {
     // phases 1 / 2: about four samples per warp and unit, but no more units than ~16 waves of the grid
     int nch = ceil_div(N.B, 4 * SNN_GEN_WARPS);
     while (nch > 1 && (long long)N.total_items * nch > 16LL * cap) --nch;
@@ -228,7 +212,41 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
     for (int c = 0; c < N.n_conns; ++c)
         if (N.learning && N.conns[c].kind == SNN_CONN_CONV2D && N.conns[c].rule != SNN_RULE_NONE) conv_rule = true;
     int grid = conv_rule ? cap : (int)(units < cap ? units : cap);
-    if (grid < 1) grid = 1;
+    return grid < 1 ? 1 : grid;
+}
+
+#ifdef SNN_EMU
+// tests/emu: the kernel's CTAs run as host threads of cooperatively scheduled fibers (cuda_emu.h); a "device" of
+// SNN_EMU_SMS (default 3) SMs x 2 CTAs keeps the grid small while still giving every CTA several units per phase.
+int snn_generic_launch(DevNet &N, cudaStream_t) {
+    int sms = 3;
+    if (const char *v = getenv("SNN_EMU_SMS")) sms = atoi(v) > 0 ? atoi(v) : 3;
+    const int grid = plan_units(N, sms * 2);
+    emu::run_grid(grid, SNN_GEN_THREADS, snn_generic_smem_bytes(N.B), [](void *a) { snn_generic_window<2>(*(const DevNet *)a); }, &N);
+    return 0;
+}
+#else
+// Launch the generic window: fills in the work decomposition (sample chunks, learning-phase units) for the grid
+// the device can keep co-resident.  Returns a cudaError_t cast to int.
+int snn_generic_launch(DevNet &N, cudaStream_t stream) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = snn_generic_smem_bytes(N.B);
+    // measured on B200 (metric configuration and config 4, profiles/): the three-CTA variant's spills cost more than its
+    // occupancy buys — two CTAs per SM unless SNN_B200_GVAR=3 asks for the experiment
+    bool three = false;
+    if (const char *v = getenv("SNN_B200_GVAR")) three = v[0] == '3' && 3 * (smem + 1024) <= 227 * 1024;
+    const void *kern = three ? (const void *)snn_generic_window<3> : (const void *)snn_generic_window<2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = three ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window<3>, SNN_GEN_THREADS, smem)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snn_generic_window<2>, SNN_GEN_THREADS, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+    if (per_sm > (three ? 3 : 2)) per_sm = three ? 3 : 2;
+    const int grid = plan_units(N, sms * per_sm);
     static long long *prof_buf = nullptr;   // debug only (env SNN_B200_GPROF): per-phase cycles of thread 0 of every CTA
     const bool prof = getenv("SNN_B200_GPROF") != nullptr;
     if (prof) {
@@ -254,3 +272,4 @@ int snn_generic_launch(DevNet &N, cudaStream_t stream) {
     }
     return rc;
 }
+#endif

@@ -1,0 +1,181 @@
+// cuda_emu.h — TEST INFRASTRUCTURE: a small CPU emulation of the CUDA execution model, just enough to run the generic
+// window kernel's REAL source (bindsnet_b200/csrc/snn_generic.cu, snn_phases.cuh, snn_common.cuh, snn_api.cu) on the
+// host, so that the CPU test tier can check the kernel's logic — work decomposition, indexing, summation orders —
+// bit for bit against the oracle without a GPU.  It is not a product path and is never loaded by bindsnet_b200.
+//
+// Model: one OS thread per CTA; the CTA's threads are cooperatively scheduled fibers (ucontext).  A warp collective
+// (__shfl*_sync, __ballot_sync, __any_sync, __syncwarp) is a rendezvous of the warp's 32 fibers with a double-buffered
+// exchange slot; __syncthreads a rendezvous of the CTA's fibers; atomics and the grid barrier use the host's atomics, so
+// several CTAs really run concurrently.  What this does NOT model: memory ordering weaker than the host's, L1 coherence,
+// timing, divergence rules — only full-mask collectives reached by all lanes are supported (all the kernel uses).
+#pragma once
+
+#include <sched.h>
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(...)
+#define __grid_constant__
+
+struct emu_uint3 { unsigned int x, y, z; };
+struct dim3 {
+    unsigned int x, y, z;
+    dim3(unsigned int x_ = 1, unsigned int y_ = 1, unsigned int z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+namespace emu {
+
+constexpr int WARP = 32;
+
+struct WarpState {
+    int arrived = 0;
+    unsigned gen = 0;
+    unsigned long long slot[2][WARP];
+};
+
+struct Cta;
+struct Fiber {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    emu_uint3 tid{0, 0, 0};
+    int lane = 0, warp = 0;
+    unsigned wseq = 0;   // warp collectives executed so far (selects the exchange buffer)
+    unsigned cseq = 0;   // CTA collectives executed so far
+    bool done = false;
+    Cta *cta = nullptr;
+};
+
+struct Cta {
+    ucontext_t main_ctx;
+    Fiber *fibers = nullptr;
+    WarpState *warps = nullptr;
+    int nthreads = 0, nwarps = 0, live = 0, current = 0;
+    int c_arrived = 0;
+    unsigned c_gen = 0;
+    int c_or[2] = {0, 0};
+    emu_uint3 bidx{0, 0, 0};
+    dim3 bdim, gdim;
+    float *dyn_smem = nullptr;
+    int s_abort = 0;
+    unsigned long long rng = 1;
+    void (*entry)(void *) = nullptr;
+    void *arg = nullptr;
+};
+
+extern thread_local Cta *tls_cta;
+extern thread_local Fiber *tls_cur;
+
+void yield();                                   // switch to the next runnable fiber of this CTA
+void run_grid(int grid, int block, size_t dyn_smem_bytes, void (*entry)(void *), void *arg);
+
+inline void warp_rendezvous() {
+    Fiber *f = tls_cur;
+    WarpState &w = f->cta->warps[f->warp];
+    const unsigned g = w.gen;
+    if (++w.arrived == WARP) { w.arrived = 0; ++w.gen; }
+    else while (w.gen == g) yield();
+}
+
+inline void cta_rendezvous() {
+    Cta *c = tls_cta;
+    const unsigned g = c->c_gen;
+    if (++c->c_arrived == c->nthreads) { c->c_arrived = 0; ++c->c_gen; }
+    else while (c->c_gen == g) yield();
+}
+
+template <class T> inline unsigned long long to_bits(T v) { unsigned long long b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+
+// every lane deposits `v`; returns the whole warp's values (valid until the lane's next collective)
+template <class T> inline const unsigned long long *warp_exchange(T v) {
+    Fiber *f = tls_cur;
+    WarpState &w = f->cta->warps[f->warp];
+    const unsigned buf = f->wseq++ & 1u;
+    w.slot[buf][f->lane] = to_bits(v);
+    warp_rendezvous();
+    return w.slot[buf];
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::tls_cur->tid)
+#define blockIdx (emu::tls_cta->bidx)
+#define blockDim (emu::tls_cta->bdim)
+#define gridDim (emu::tls_cta->gdim)
+
+// ---- warp / CTA collectives (full mask only)
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::tls_cur->wseq++; emu::warp_rendezvous(); }
+inline void __syncthreads() { emu::tls_cur->cseq++; emu::cta_rendezvous(); }
+inline int __syncthreads_or(int pred) {
+    emu::Cta *c = emu::tls_cta;
+    const unsigned buf = emu::tls_cur->cseq++ & 1u;
+    if (pred) c->c_or[buf] = 1;
+    const unsigned g = c->c_gen;
+    if (++c->c_arrived == c->nthreads) { c->c_or[buf ^ 1u] = 0; c->c_arrived = 0; ++c->c_gen; }
+    else while (c->c_gen == g) emu::yield();
+    return c->c_or[buf];
+}
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) { return emu::from_bits<T>(emu::warp_exchange(v)[src & 31]); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta, int = 32) {
+    const int lane = emu::tls_cur->lane;
+    const unsigned long long *s = emu::warp_exchange(v);
+    return lane >= (int)delta ? emu::from_bits<T>(s[lane - (int)delta]) : v;
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask, int = 32) {
+    const int lane = emu::tls_cur->lane;
+    return emu::from_bits<T>(emu::warp_exchange(v)[(lane ^ mask) & 31]);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    const unsigned long long *s = emu::warp_exchange<int>(pred ? 1 : 0);
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned)(s[l] & 1ull) << l;
+    return m;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+
+// ---- scalar intrinsics
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (s & 31u)); }
+inline long long clock64() { static thread_local long long c = 0; return c += 64; }
+inline void __nanosleep(unsigned) { emu::yield(); sched_yield(); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline float fminf_(float a, float b) { return a < b ? a : b; }
+
+// ---- atomics on "global" memory (shared by the CTAs' OS threads)
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
+// ---- the few runtime calls the generic path makes (host memory stands in for device memory)
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorLaunchOutOfResources = 701, cudaErrorMemoryAllocation = 2 };
+inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }

@@ -1,0 +1,131 @@
+// emu_lib.cpp — TEST INFRASTRUCTURE: builds the generic window kernel's real CUDA sources for the host on top of
+// cuda_emu.h and exports the same C ABI entry points (snn_b200_run_window, snn_b200_workspace_bytes, ...) operating on
+// HOST memory.  tests/emu/emu.py routes the host API to it the way oracle/oracle.py routes it to the oracle.
+//
+//   g++ -O1 -std=c++17 -fPIC -shared -DSNN_EMU -ffp-contract=off -Itests/emu -o tests/emu/libsnn_emu.so tests/emu/emu_lib.cpp -lpthread
+#include <sys/mman.h>
+
+#include <thread>
+#include <vector>
+
+#include "cuda_emu.h"
+
+namespace emu {
+
+thread_local Cta *tls_cta = nullptr;
+thread_local Fiber *tls_cur = nullptr;
+
+static constexpr size_t STACK_BYTES = 512 * 1024;
+
+// SNN_EMU_SHUFFLE=<seed>: instead of round robin, the next fiber is drawn at random — different interleavings of the
+// warps between two synchronisation points, i.e. a poor man's race check for a missing __syncthreads / __syncwarp.
+static unsigned long long g_shuffle = 0;
+
+static inline unsigned next_rand(Cta *c) {
+    unsigned long long x = c->rng;
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    c->rng = x;
+    return (unsigned)(x >> 24);
+}
+
+void yield() {
+    Cta *c = tls_cta;
+    Fiber *from = tls_cur;
+    int k = c->current;
+    if (g_shuffle) {
+        k = (int)(next_rand(c) % (unsigned)c->nthreads);
+        for (int step = 0; step < c->nthreads && c->fibers[k].done; ++step) k = (k + 1) % c->nthreads;
+        if (c->fibers[k].done) return;
+    } else {
+        for (int step = 0; step < c->nthreads; ++step) {
+            k = (k + 1) % c->nthreads;
+            if (!c->fibers[k].done) break;
+        }
+    }
+    if (k == c->current) return;   // nobody else is runnable
+    c->current = k;
+    tls_cur = &c->fibers[k];
+    swapcontext(&from->ctx, &c->fibers[k].ctx);
+}
+
+static void fiber_main() {
+    Fiber *f = tls_cur;
+    Cta *c = f->cta;
+    c->entry(c->arg);
+    f->done = true;
+    --c->live;
+    if (c->live == 0) {
+        setcontext(&c->main_ctx);
+    } else {
+        int k = c->current;
+        do { k = (k + 1) % c->nthreads; } while (c->fibers[k].done);
+        c->current = k;
+        tls_cur = &c->fibers[k];
+        setcontext(&c->fibers[k].ctx);
+    }
+}
+
+static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
+    Cta cta;
+    cta.nthreads = block;
+    cta.nwarps = (block + WARP - 1) / WARP;
+    cta.live = block;
+    cta.bidx = {(unsigned)bid, 0, 0};
+    cta.bdim = dim3(block);
+    cta.gdim = dim3(grid);
+    cta.entry = entry;
+    cta.arg = arg;
+    cta.rng = (g_shuffle + 1) * 0x9E3779B97F4A7C15ull + (unsigned long long)(bid + 1) * 0xD1B54A32D192ED03ull;
+    std::vector<Fiber> fibers(block);
+    std::vector<WarpState> warps(cta.nwarps);
+    std::vector<char> smem(smem_bytes + 64);
+    cta.fibers = fibers.data();
+    cta.warps = warps.data();
+    cta.dyn_smem = (float *)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+    char *stacks = (char *)mmap(nullptr, STACK_BYTES * block, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (stacks == MAP_FAILED) { perror("emu: mmap"); abort(); }
+    tls_cta = &cta;
+    for (int t = 0; t < block; ++t) {
+        Fiber &f = fibers[t];
+        f.tid = {(unsigned)t, 0, 0};
+        f.lane = t % WARP;
+        f.warp = t / WARP;
+        f.cta = &cta;
+        f.stack = stacks + STACK_BYTES * t;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = STACK_BYTES;
+        f.ctx.uc_link = nullptr;
+        makecontext(&f.ctx, (void (*)())fiber_main, 0);
+    }
+    cta.current = 0;
+    tls_cur = &fibers[0];
+    swapcontext(&cta.main_ctx, &fibers[0].ctx);   // returns when the last fiber finishes
+    tls_cur = nullptr;
+    tls_cta = nullptr;
+    munmap(stacks, STACK_BYTES * block);
+}
+
+void run_grid(int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
+    const char *sh = getenv("SNN_EMU_SHUFFLE");
+    g_shuffle = sh ? strtoull(sh, nullptr, 10) : 0ull;
+    std::vector<std::thread> ts;
+    for (int b = 0; b < grid; ++b) ts.emplace_back(run_cta, b, grid, block, smem_bytes, entry, arg);
+    for (auto &t : ts) t.join();
+}
+
+}  // namespace emu
+
+// ---- the product's sources, compiled for the host ---------------------------------------------------------------
+#include "../../bindsnet_b200/csrc/snn_generic.cu"
+
+// the fused DiehlAndCook2015 kernels (TMA, mbarrier, inline PTX) are not emulated: the emulated library has the generic tier only
+struct snn_net;
+int snn_fused_dc_supported(const snn_net_t *, const snn_run_opts_t *) { return 0; }
+size_t snn_fused_dc_workspace_bytes(const snn_net_t *, const snn_run_opts_t *) { return 0; }
+int snn_fused_dc_launch(const snn_net_t *, const snn_run_opts_t *, void *, size_t, cudaStream_t, int *) { return SNN_ERR_UNSUPPORTED; }
+int snn_fused_dc2_supported(const snn_net_t *, const snn_run_opts_t *) { return 0; }
+size_t snn_fused_dc2_workspace_bytes(const snn_net_t *, const snn_run_opts_t *) { return 0; }
+int snn_fused_dc2_launch(const snn_net_t *, const snn_run_opts_t *, void *, size_t, cudaStream_t, int *) { return SNN_ERR_UNSUPPORTED; }
+
+#include "../../bindsnet_b200/csrc/snn_api.cu"

@@ -1,0 +1,72 @@
+"""The generic window kernel's REAL CUDA source (bindsnet_b200/csrc/snn_generic.cu, snn_phases.cuh, snn_common.cuh,
+snn_api.cu), compiled for the host on a small emulation of the CUDA execution model (tests/emu/: one OS thread per CTA,
+cooperatively scheduled fibers per thread, warp / CTA collectives as rendezvous, host atomics for the grid barrier), and
+run on the golden cases — bit for bit against the oracle, like the `-m gpu` parity tests do on the B200.
+
+What this tier checks without a GPU: the kernel's work decomposition (sample chunks, learning units, several units per
+CTA, several CTAs), indexing, summation orders, the staging / prefetch logic and the barrier protocol.  What it cannot
+check: anything that depends on the GPU's memory model or timing — that stays with the `-m gpu` tests."""
+import os
+import sys
+
+import pytest
+
+import cases
+import helpers
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+SKIP = ("dc2015_c2", "dc2015_metric_t40", "dc2015_metric_t250", "conv_mstdp_c4", "conv_mstdp_c4_b128")   # minutes under emulation
+SMALL = [c for c in cases.CASES if c not in SKIP]
+
+
+def _run_emulated(name, env=None):
+    import emu
+
+    fx = helpers.Fixture(name)
+    net, inputs, kw, T = fx.build("cpu")
+    helpers.add_spike_monitors(net, T)
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        with emu.EmuBackend() as eb:
+            net.run(inputs=inputs, time=T, one_spike_seed=cases.ONE_SPIKE_SEED, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert eb.err == 0
+    return helpers.snapshot(net), helpers.spike_counts(net, T)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_emulated_generic_kernel_bit_exact_vs_oracle(name):
+    s_emu, c_emu = _run_emulated(name)
+    _, s_cpu, c_cpu = helpers.run_case_oracle(name)
+    helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated kernel)")
+    helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated kernel)")
+
+
+@pytest.mark.parametrize("name", ["lif_postpre_batch", "dc2015_onespike", "conv_mstdp", "mstdp_dense"])
+@pytest.mark.parametrize("sms", ["1", "7"])
+def test_emulated_kernel_is_independent_of_the_grid_size(name, sms):
+    """One CTA doing every unit in turn and 14 CTAs sharing them give the same bits: nothing depends on which CTA ran what."""
+    s_emu, c_emu = _run_emulated(name, env={"SNN_EMU_SMS": sms})
+    _, s_cpu, c_cpu = helpers.run_case_oracle(name)
+    helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated kernel, {sms} SMs)")
+    helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated kernel, {sms} SMs)")
+
+
+@pytest.mark.parametrize("name", ["lif_postpre_batch", "dc2015_onespike", "conv_mstdp", "mstdp_dense"])
+@pytest.mark.parametrize("seed", ["1"])
+def test_emulated_kernel_under_random_thread_interleavings(name, seed):
+    """SNN_EMU_SHUFFLE: the emulator picks the next thread at random at every synchronisation point instead of round
+    robin — the warps of a CTA interleave differently on every run, so a missing __syncthreads / __syncwarp between a
+    shared-memory write and its readers shows up as a mismatch.  (A logic-level stand-in for racecheck, not a
+    replacement: it knows nothing of the GPU's memory model.)"""
+    s_emu, c_emu = _run_emulated(name, env={"SNN_EMU_SHUFFLE": seed, "SNN_EMU_SMS": "2"})
+    _, s_cpu, c_cpu = helpers.run_case_oracle(name)
+    helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated kernel, shuffled schedule {seed})")
+    helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated kernel, shuffled schedule {seed})")
