@@ -70,3 +70,26 @@ def test_emulated_kernel_under_random_thread_interleavings(name, seed):
     _, s_cpu, c_cpu = helpers.run_case_oracle(name)
     helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated kernel, shuffled schedule {seed})")
     helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated kernel, shuffled schedule {seed})")
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_emulated_kernel_on_random_networks(seed):
+    """The randomly drawn networks of test_oracle_fuzz_vs_reference.py (node kinds x rules x reductions x options x batch
+    sizes) through the emulated kernel, bit for bit against the oracle — the CPU twin of tests/test_zz_gpu_fuzz_vs_oracle.py."""
+    import emu
+    import test_oracle_fuzz_vs_reference as fuzz
+    from oracle.oracle import OracleBackend
+
+    spec = fuzz._draw(seed)
+    ns = cases.namespace("b200")
+    outs = []
+    for backend in (emu.EmuBackend, OracleBackend):
+        net, x = fuzz._build(ns, spec)
+        helpers.add_spike_monitors(net, spec["T"])
+        with backend() as be:
+            net.run(inputs={"X": x}, time=spec["T"])
+            assert be.err == 0
+        outs.append((helpers.snapshot(net), helpers.spike_counts(net, spec["T"])))
+    what = f"seed {seed} {spec['kind']} {spec['rule']} B={spec['B']}"
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], what + " state (emulated kernel)")
+    helpers.assert_bit_identical(outs[0][1], outs[1][1], what + " spike counts (emulated kernel)")
