@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["snn_api.cu", "snn_generic.cu", "snn_fused_dc.cu", "snn_fused_dc2.cu", "snn_ops.cu", "snn_encode.cu", "snn_readout.cu"]
-HEADERS = ["snn_common.cuh", "snn_phases.cuh", os.path.join("..", "..", "include", "snn_b200.h")]
+HEADERS = ["snn_common.cuh", "snn_phases.cuh", "snn_combine.cuh", os.path.join("..", "..", "include", "snn_b200.h")]
 OUT = os.path.join(HERE, "libsnn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -1,6 +1,7 @@
 // snn_ops.cu — single-operator entry points of the C ABI (the reference's per-object methods:
 // Connection.compute, connection.update, normalize) and the multi-GPU window-combine kernels.
 #include "snn_phases.cuh"
+#include "snn_combine.cuh"
 
 namespace {
 
@@ -79,22 +80,13 @@ __global__ void delta_prepare_kernel(const float *__restrict__ w, const float *_
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dw[k] = w[k] - w0[k];
 }
 
-// w = clamp(w0 + sum_r dw_r), then normalize() — all on one column tile.
+// w = clamp(w0 + sum_r dw_r), then normalize() — all on one column tile (snn_combine.cuh).
 __global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t C, const float *w0, const float *__restrict__ dws, int ns, int nt,
                                                                        float *theta, const float *__restrict__ dtheta, int n_theta) {
     if (theta)   // theta = theta0 + sum_r dtheta_r, in place, spread over the grid
         for (int k = blockIdx.x * SNN_GEN_THREADS + threadIdx.x; k < n_theta; k += gridDim.x * SNN_GEN_THREADS) theta[k] = theta[k] + dtheta[k];
     __shared__ float s_part[(SNN_NORM_CHUNKS + 1) * 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * SNN_TILE + lane;
-    if (j < nt)
-        for (int i = warp; i < ns; i += SNN_GEN_WARPS) {
-            const size_t k = (size_t)i * nt + j;
-            float x = w0[k] + dws[k];
-            if (C.has_clamp) x = clampf(x, C.wmin, C.wmax);
-            C.w[k] = x;
-        }
-    if (C.has_norm) normalize_tile(C, ns, nt, blockIdx.x, s_part);
+    delta_apply_tile(C, w0, dws, ns, nt, blockIdx.x, s_part);
 }
 
 // Checks on the device that a square matrix has the structure a plan claims for it (SNN_W_DIAG: val on the

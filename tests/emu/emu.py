@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 LIB = os.path.join(HERE, "libsnn_emu.so")
 _SOURCES = [os.path.join(HERE, "emu_lib.cpp"), os.path.join(HERE, "cuda_emu.h")] + [
-    os.path.join(ROOT, "bindsnet_b200", "csrc", f) for f in ("snn_generic.cu", "snn_phases.cuh", "snn_common.cuh", "snn_api.cu")
+    os.path.join(ROOT, "bindsnet_b200", "csrc", f) for f in ("snn_generic.cu", "snn_phases.cuh", "snn_common.cuh", "snn_api.cu", "snn_combine.cuh")
 ] + [os.path.join(ROOT, "include", "snn_b200.h")]
 _lib = None
 
@@ -45,6 +45,11 @@ def lib() -> C.CDLL:
         L.snn_b200_run_window.argtypes = [C.POINTER(_abi.SnnNet), C.POINTER(_abi.SnnRunOpts), C.c_void_p, C.c_size_t, C.c_void_p]
         L.snn_b200_select_tier.restype = C.c_int
         L.snn_b200_select_tier.argtypes = [C.POINTER(_abi.SnnNet), C.POINTER(_abi.SnnRunOpts)]
+        vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+        L.snn_b200_delta_apply.restype = C.c_int
+        L.snn_b200_delta_apply.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, i32, i32, f32, vp]
+        L.snn_b200_delta_apply_fused.restype = C.c_int
+        L.snn_b200_delta_apply_fused.argtypes = [vp, vp, i32, i32, i32, f32, f32, i32, i32, f32, vp, vp, i32, vp]
         L.snn_b200_abi_version.restype = C.c_int
         assert L.snn_b200_abi_version() == _abi.SNN_ABI_VERSION
         _lib = L

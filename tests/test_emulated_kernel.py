@@ -93,3 +93,36 @@ def test_emulated_kernel_on_random_networks(seed):
     what = f"seed {seed} {spec['kind']} {spec['rule']} B={spec['B']}"
     helpers.assert_bit_identical(outs[0][0], outs[1][0], what + " state (emulated kernel)")
     helpers.assert_bit_identical(outs[0][1], outs[1][1], what + " spike counts (emulated kernel)")
+
+
+@pytest.mark.parametrize("shape,clamp,norm,norm_abs", [((784, 160), True, 78.4, 0), ((100, 37), True, None, 1), ((53, 129), False, 5.0, 1),
+                                                       ((7, 33), True, 2.0, 0), ((260, 64), True, 11.0, 1)])
+def test_emulated_window_combine_bit_exact_vs_oracle(shape, clamp, norm, norm_abs):
+    """The multi-GPU window combine (csrc/snn_combine.cuh: W = clamp(W0 + sum dW), normalize(), eight rows in flight per
+    warp) under emulation against snn_oracle_delta_apply — out of place and in place (the fused form, with theta)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import emu
+    from oracle import oracle
+
+    g = torch.Generator().manual_seed(11)
+    w0 = (0.3 * torch.rand(*shape, generator=g)).contiguous()
+    dsum = (0.08 * torch.randn(*shape, generator=g)).contiguous()
+    ref = torch.empty_like(w0)
+    assert oracle.lib().snn_oracle_delta_apply(ref.data_ptr(), w0.data_ptr(), dsum.data_ptr(), shape[0], shape[1], int(clamp), C.c_float(0.0),
+                                               C.c_float(1.0), int(norm is not None), norm_abs, C.c_float(norm or 0.0)) == 0
+    L = emu.lib()
+    out = torch.full_like(w0, 7.0)
+    assert L.snn_b200_delta_apply(out.data_ptr(), w0.data_ptr(), dsum.data_ptr(), shape[0], shape[1], int(clamp), 0.0, 1.0,
+                                  int(norm is not None), norm_abs, norm or 0.0, None) == 0
+    assert np.array_equal(out.numpy().view(np.uint32), ref.numpy().view(np.uint32))
+    inplace = w0.clone()
+    th, dth = torch.rand(shape[1], generator=g), torch.rand(shape[1], generator=g)
+    th_ref = th + dth
+    assert L.snn_b200_delta_apply_fused(inplace.data_ptr(), dsum.data_ptr(), shape[0], shape[1], int(clamp), 0.0, 1.0, int(norm is not None),
+                                        norm_abs, norm or 0.0, th.data_ptr(), dth.data_ptr(), shape[1], None) == 0
+    assert np.array_equal(inplace.numpy().view(np.uint32), ref.numpy().view(np.uint32))
+    assert torch.equal(th, th_ref)
