@@ -126,3 +126,35 @@ def test_emulated_window_combine_bit_exact_vs_oracle(shape, clamp, norm, norm_ab
                                         norm_abs, norm or 0.0, th.data_ptr(), dth.data_ptr(), shape[1], None) == 0
     assert np.array_equal(inplace.numpy().view(np.uint32), ref.numpy().view(np.uint32))
     assert torch.equal(th, th_ref)
+
+
+def test_emulated_kernel_large_batch_wide_layer_paths():
+    """DiehlAndCook2015 with n = 1100 (35 bit words per sample: two gather blocks, per-sample any-spike flags), B = 70
+    (three sample chunks per tile, the eager weight-row prefetch of the learning phase) — the code paths of BASELINE
+    configs 2-3 that the small goldens do not reach — through the emulated kernel, bit for bit against the oracle."""
+    import torch
+
+    import emu
+    from bindsnet_b200.models import DiehlAndCook2015
+    from oracle.oracle import OracleBackend
+
+    n, B, T = 1100, 70, 24
+
+    def build():
+        torch.manual_seed(5)
+        net = DiehlAndCook2015(n_inpt=784, n_neurons=n, batch_size=B, inpt_shape=(1, 28, 28), dt=1.0, nu=(1e-3, 1e-2), norm=78.4,
+                               theta_plus=0.05, exc=22.5, inh=120.0)
+        g = torch.Generator().manual_seed(9)
+        return net, torch.bernoulli(0.12 * torch.ones(T, B, 1, 28, 28), generator=g).byte()
+
+    outs = []
+    for backend in (emu.EmuBackend, OracleBackend):
+        net, x = build()
+        helpers.add_spike_monitors(net, T)
+        with backend() as be:
+            net.run({"X": x}, time=T, one_spike_seed=3)
+            assert be.err == 0
+        outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
+    assert int(outs[1][1]["L/Ae/count"].sum()) > 100 and int(outs[1][1]["L/Ai/count"].sum()) > 100
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], "state (emulated kernel)")
+    helpers.assert_bit_identical(outs[0][1], outs[1][1], "spike counts (emulated kernel)")
