@@ -158,3 +158,42 @@ def test_emulated_kernel_large_batch_wide_layer_paths():
     assert int(outs[1][1]["L/Ae/count"].sum()) > 100 and int(outs[1][1]["L/Ai/count"].sum()) > 100
     helpers.assert_bit_identical(outs[0][0], outs[1][0], "state (emulated kernel)")
     helpers.assert_bit_identical(outs[0][1], outs[1][1], "spike counts (emulated kernel)")
+
+
+def test_emulated_kernel_monitors_and_state_carry_over():
+    """CPU twins of three `-m gpu` tests: spike and voltage recordings step by step, the in-kernel spike counter, state
+    carried across windows and a batch-size change — emulated kernel against the oracle."""
+    import numpy as np
+    import torch
+
+    import emu
+    from bindsnet_b200.models import DiehlAndCook2015
+    from bindsnet_b200.network.monitors import Monitor, SpikeCounter
+    from oracle.oracle import OracleBackend
+
+    g = torch.Generator().manual_seed(5)
+    w0 = 0.3 * torch.rand(784, 50, generator=g)
+    xa = torch.bernoulli(0.05 * torch.ones(40, 6, 1, 28, 28), generator=g).byte()
+    xb = torch.bernoulli(0.05 * torch.ones(30, 3, 1, 28, 28), generator=g).byte()
+    outs = []
+    for backend in (emu.EmuBackend, OracleBackend):
+        net = DiehlAndCook2015(n_inpt=784, n_neurons=50, batch_size=6, inpt_shape=(1, 28, 28), inh=120.0)
+        with torch.no_grad():
+            net.connections[("X", "Ae")].w.copy_(w0)
+        net.add_monitor(Monitor(net.layers["Ae"], ["s", "v"], time=40), "ae")
+        net.add_monitor(SpikeCounter(net.layers["Ae"]), "count")
+        rec = {}
+        with backend() as be:
+            net.run({"X": xa}, time=40, one_spike_seed=1)
+            rec["s1"], rec["v1"] = net.monitors["ae"].get("s").clone().numpy(), net.monitors["ae"].get("v").clone().numpy()
+            assert torch.equal(net.monitors["count"].get("s"), net.monitors["ae"].get("s").sum(0).to(torch.int32))
+            net.run({"X": xa}, time=40, one_spike_seed=2)           # state carried over
+            rec["s2"] = net.monitors["ae"].get("s").clone().numpy()
+            net.run({"X": xb}, time=30, one_spike_seed=3)           # batch size 6 -> 3: state re-allocated
+            assert be.err == 0
+        assert net.layers["Ae"].v.shape == (3, 50)
+        outs.append((helpers.snapshot(net), rec))
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], "multi-window state (emulated kernel)")
+    for k in outs[0][1]:
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+    assert outs[1][1]["s2"].sum() > 0
