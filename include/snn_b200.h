@@ -23,6 +23,8 @@
  * The same structs are consumed by two libraries:
  *   - libsnn_b200.so   (bindsnet_b200/csrc, CUDA sm_100a; every pointer is a DEVICE pointer)
  *   - libsnn_oracle.so (oracle/, plain C test infrastructure; every pointer is a HOST pointer)
+ * (and by tests/emu/libsnn_emu.so, test infrastructure: the generic kernel's CUDA sources compiled for the host on a small
+ * emulation of the CUDA execution model, HOST pointers).
  */
 #ifndef SNN_B200_H
 #define SNN_B200_H
