@@ -349,13 +349,13 @@ static void conn_update(const snn_net_t *net, const snn_conn_t *C, const snn_run
     const float dts = C->rule == SNN_RULE_MCC_POSTPRE ? C->dt_scale : 1.0f;
     const int use_dt = C->rule == SNN_RULE_MCC_POSTPRE;
     const float Bf = (float)B;
-    int any_row = 0, any_col = 0;
+    int any_col = 0;
 
     if (pre_on) {
         /* U[i,j] = reduce_b s_src[b,i] * (x_tgt[b,j] * nu0)   (WDEP: without nu0) */
         float *tx = ws->tx;
         for (size_t k = 0; k < (size_t)B * nt; ++k) tx[k] = wdep ? G->x[k] : G->x[k] * C->nu0;
-#pragma omp parallel for schedule(static) reduction(|:any_row)
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < ns; ++i) {
             float *Ui = ws->U + (size_t)i * nt;
             int touched = 0;
@@ -363,7 +363,6 @@ static void conn_update(const snn_net_t *net, const snn_conn_t *C, const snn_run
             else for (int b = 0; b < B; ++b) if (S->s[(size_t)b * ns + i]) { touched = 1; break; }
             ws->row_t[i] = (uint8_t)touched;
             if (!touched) continue;
-            any_row = 1;
             for (int j = 0; j < nt; ++j) Ui[j] = 0.0f;
             for (int b = 0; b < B; ++b) {
                 const uint8_t sb = S->s[(size_t)b * ns + i];
