@@ -65,6 +65,24 @@ struct FusedParams {
 };
 constexpr int NPROF = 16;
 
+#ifdef SNN_EMU   // tests/emu: mbarrier / bulk copy / polling loads on the CUDA-model emulation (test infrastructure)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int) { emu::Mbar *m = (emu::Mbar *)bar; m->phase = 0; m->pend = emu::MBAR_ARRIVAL; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { emu::Mbar *m = (emu::Mbar *)bar; m->pend += (int32_t)bytes - emu::MBAR_ARRIVAL; emu::mbar_settle(m); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    const bool ok = (((const emu::Mbar *)bar)->phase & 1u) != parity;
+    if (!ok) emu::yield();
+    return ok;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    memcpy(dst, src, bytes);
+    emu::Mbar *m = (emu::Mbar *)bar; m->pend -= (int32_t)bytes; emu::mbar_settle(m);
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+    const unsigned int v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+    emu::yield(); sched_yield();
+    return v;
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -95,6 +113,7 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 
 // The grid barrier is ONE monotonic arrival counter: a release reduction to arrive, relaxed polling
 // of the same word until nblocks * generation arrivals are in, then one acquire fence
@@ -509,7 +528,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     }
     constexpr int CG = TJ / 4;  // float4 column groups = lanes that share one sample
     constexpr int WS = TJ + 4;  // row stride of the W tile in shared memory (floats)
+#ifdef SNN_EMU
+    unsigned char *smem = (unsigned char *)emu::tls_cta->dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem[];
+#endif
     const int B = Q.B, P = Q.P, n = Q.n, T = Q.T;
     const unsigned int G = gridDim.x;
     const int own = (B + (int)G - 1) / (int)G;
@@ -525,7 +548,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
     float *theta_s = (float *)(smem + Q.o_theta);
     uint16_t *live = (uint16_t *)(smem + Q.o_live);
     Misc &M = *(Misc *)(smem + Q.o_misc);
+#ifdef SNN_EMU
+    PassCtx &s_cx = *(PassCtx *)emu::tls_cta->static_smem;
+#else
     __shared__ PassCtx s_cx;
+#endif
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int b = tid / CG, cg = tid % CG;   // state ownership: sample b, neurons jc..jc+3
@@ -571,7 +598,9 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         for (int m = 1; m <= n; ++m) { a = a + Q.inh_neg; rep[m] = a; }
         mbar_init(&M.mbar[0], 1);
         mbar_init(&M.mbar[1], 1);
+#ifndef SNN_EMU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
         M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.colwin = 0; M.abort = 0; M.nwl = 0; M.nlive = 0;
         M.denseflag[0] = Q.dense[0]; M.denseflag[1] = T >= 1 ? Q.dense[1] : 0;
         for (int k = 0; k < 8; ++k) M.lc[k] = 0;
@@ -955,7 +984,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
         }
         // ---- arrive(t): this CTA's contributions to step t's exchange are issued -----------------
         PROF(6)  // theta, prefetch issue
+#ifdef SNN_EMU
+        if (tid == 0) __atomic_fetch_add(Q.bar, 1u, __ATOMIC_RELEASE);
+#else
         if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
+#endif
         gen += 1;
         PROF(15)  // arrive (release)
         // ---- early(t): in the shadow of the barrier ------------------------------------------------
@@ -997,7 +1030,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
                     if (clock64() - t0 > 4000000000LL) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
                 }
             }
+#ifdef SNN_EMU
+            __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
             asm volatile("fence.acquire.gpu;" ::: "memory");
+#endif
         }
         __syncthreads();
         if (M.abort) return;
@@ -1087,7 +1124,11 @@ snn_dc_fused_window(const __grid_constant__ FusedParams Q0) {
 // flags non-binary input; CTA 0 also resets the exchange slots and counts the incoming Ai spikes.
 __global__ void __launch_bounds__(256) snn_dc_prepass(const __grid_constant__ FusedParams Q, int BW) {
     // grid = (slot, group of 32 samples): each CTA converts 32 samples of one timestep
+#ifdef SNN_EMU
+    uint32_t *sbits = (uint32_t *)emu::tls_cta->dyn_smem;
+#else
     extern __shared__ uint32_t sbits[];  // [32][SW]
+#endif
     const int B = Q.B, P = Q.P, SW = Q.SW, PW = (P + 31) / 32;
     const int slot = blockIdx.x, grp = blockIdx.y, b0 = grp * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -1225,11 +1266,15 @@ struct Match {
 
 int device_sms() {
     static int sms = -1;
+#ifdef SNN_EMU
+    if (sms < 0) { const char *v = getenv("SNN_EMU_FUSED_SMS"); sms = v && atoi(v) > 0 ? atoi(v) : 148; }
+#else
     if (sms < 0) {
         int dev = 0, v = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
         else { sms = 148; (void)cudaGetLastError(); }
     }
+#endif
     return sms;
 }
 
@@ -1284,10 +1329,16 @@ bool match(const snn_net_t *net, const snn_run_opts_t *o, Match &m) {
 
 template <int TJ, int BW, int VAR>
 cudaError_t launch_var(const FusedParams &Q, const Match &m, cudaStream_t stream) {
+#ifdef SNN_EMU
+    (void)stream;
+    emu::run_grid(m.grid, m.threads, m.smem, [](void *a) { snn_dc_fused_window<TJ, BW, VAR>(*(const FusedParams *)a); }, (void *)&Q);
+    return cudaSuccess;
+#else
     cudaError_t e = cudaFuncSetAttribute(snn_dc_fused_window<TJ, BW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&Q};
     return cudaLaunchCooperativeKernel((void *)snn_dc_fused_window<TJ, BW, VAR>, dim3(m.grid), dim3(m.threads), args, m.smem, stream);
+#endif
 }
 
 template <int TJ, int BW>
@@ -1363,7 +1414,15 @@ int snn_fused_dc_launch(const snn_net_t *net, const snn_run_opts_t *opts, void *
     if (prof && cudaMemsetAsync(Q.prof + 320 * NPROF + NPROF * 32 * 160 + 600, 0, 8 * sizeof(long long), stream) != cudaSuccess) return SNN_ERR_CUDA;
     // the two static matrices are replaced by their constants: make sure they still have that structure
     if (snn_verify_structure(net->conns[m.cEI], Q.n, Q.err, stream) != SNN_OK || snn_verify_structure(net->conns[m.cIE], Q.n, Q.err, stream) != SNN_OK) return SNN_ERR_CUDA;
+#ifdef SNN_EMU
+    {
+        struct PreArgs { const FusedParams *Q; int BW; } pa = {&Q, m.BW};
+        emu::run_grid_independent(T + 1, (B + 31) / 32, 256, sizeof(uint32_t) * 32 * (size_t)m.SW,
+                                  [](void *a) { const PreArgs *p = (const PreArgs *)a; snn_dc_prepass(*p->Q, p->BW); }, &pa);
+    }
+#else
     snn_dc_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
+#endif
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
         if (m.BW == 4) {

@@ -27,8 +27,19 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
+#define __builtin_assume(x) ((void)0)
+#define __isShared(p) (true)
 
 struct emu_uint3 { unsigned int x, y, z; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) uint4 { unsigned int x, y, z, w; };
+struct alignas(8) uint2 { unsigned int x, y; };
+struct uchar4 { unsigned char x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return uchar4{x, y, z, w}; }
 struct dim3 {
     unsigned int x, y, z;
     dim3(unsigned int x_ = 1, unsigned int y_ = 1, unsigned int z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -67,6 +78,7 @@ struct Cta {
     emu_uint3 bidx{0, 0, 0};
     dim3 bdim, gdim;
     float *dyn_smem = nullptr;
+    alignas(16) unsigned char static_smem[1024];   // the kernels' few statically declared __shared__ objects
     int s_abort = 0;
     unsigned long long rng = 1;
     void (*entry)(void *) = nullptr;
@@ -78,6 +90,15 @@ extern thread_local Fiber *tls_cur;
 
 void yield();                                   // switch to the next runnable fiber of this CTA
 void run_grid(int grid, int block, size_t dyn_smem_bytes, void (*entry)(void *), void *arg);
+// independent CTAs (no grid-wide synchronisation): a 2-D grid executed by a small pool of host threads
+void run_grid_independent(int gx, int gy, int block, size_t dyn_smem_bytes, void (*entry)(void *), void *arg);
+
+// mbarrier + bulk copy (cp.async.bulk ... mbarrier::complete_tx): the copy happens AT ISSUE — the earliest moment the
+// hardware could overwrite the destination, i.e. the adversarial case for a missing synchronisation before the issue.
+struct Mbar { uint32_t phase; int32_t pend; };   // pend: outstanding bytes (+ 2^30 while the phase's arrival is outstanding)
+static_assert(sizeof(Mbar) == 8, "an mbarrier object is 64 bits");
+constexpr int32_t MBAR_ARRIVAL = 1 << 30;
+inline void mbar_settle(Mbar *m) { if (m->pend == 0) { ++m->phase; m->pend = MBAR_ARRIVAL; } }
 
 inline void warp_rendezvous() {
     Fiber *f = tls_cur;
@@ -153,6 +174,15 @@ inline long long clock64() { static thread_local long long c = 0; return c += 64
 inline void __nanosleep(unsigned) { emu::yield(); sched_yield(); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+inline uint4 __ldcg(const uint4 *p) { return *p; }
+inline float4 __ldcg(const float4 *p) { return *p; }
+template <class T> inline T __ldg(const T *p) { return *p; }
+inline unsigned __vcmpne4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k)
+        if (((a >> (8 * k)) & 0xffu) != ((b >> (8 * k)) & 0xffu)) r |= 0xffu << (8 * k);
+    return r;
+}
 
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
@@ -179,3 +209,7 @@ typedef void *cudaStream_t;
 enum { cudaSuccess = 0, cudaErrorLaunchOutOfResources = 701, cudaErrorMemoryAllocation = 2 };
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyDeviceToHost = 2 };
+inline cudaError_t cudaMemcpy(void *d, const void *s_, size_t n, cudaMemcpyKind) { memcpy(d, s_, n); return cudaSuccess; }

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 LIB = os.path.join(HERE, "libsnn_emu.so")
 _SOURCES = [os.path.join(HERE, "emu_lib.cpp"), os.path.join(HERE, "cuda_emu.h")] + [
-    os.path.join(ROOT, "bindsnet_b200", "csrc", f) for f in ("snn_generic.cu", "snn_phases.cuh", "snn_common.cuh", "snn_api.cu", "snn_combine.cuh")
+    os.path.join(ROOT, "bindsnet_b200", "csrc", f) for f in ("snn_generic.cu", "snn_phases.cuh", "snn_common.cuh", "snn_api.cu", "snn_combine.cuh", "snn_fused_dc.cu")
 ] + [os.path.join(ROOT, "include", "snn_b200.h")]
 _lib = None
 

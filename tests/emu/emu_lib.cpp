@@ -65,14 +65,14 @@ static void fiber_main() {
     }
 }
 
-static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
+static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg, int bid_y = 0, int grid_y = 1) {
     Cta cta;
     cta.nthreads = block;
     cta.nwarps = (block + WARP - 1) / WARP;
     cta.live = block;
-    cta.bidx = {(unsigned)bid, 0, 0};
+    cta.bidx = {(unsigned)bid, (unsigned)bid_y, 0};
     cta.bdim = dim3(block);
-    cta.gdim = dim3(grid);
+    cta.gdim = dim3(grid, grid_y);
     cta.entry = entry;
     cta.arg = arg;
     cta.rng = (g_shuffle + 1) * 0x9E3779B97F4A7C15ull + (unsigned long long)(bid + 1) * 0xD1B54A32D192ED03ull;
@@ -110,7 +110,19 @@ void run_grid(int grid, int block, size_t smem_bytes, void (*entry)(void *), voi
     const char *sh = getenv("SNN_EMU_SHUFFLE");
     g_shuffle = sh ? strtoull(sh, nullptr, 10) : 0ull;
     std::vector<std::thread> ts;
-    for (int b = 0; b < grid; ++b) ts.emplace_back(run_cta, b, grid, block, smem_bytes, entry, arg);
+    for (int b = 0; b < grid; ++b) ts.emplace_back([=]() { run_cta(b, grid, block, smem_bytes, entry, arg); });
+    for (auto &t : ts) t.join();
+}
+
+void run_grid_independent(int gx, int gy, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
+    const char *sh = getenv("SNN_EMU_SHUFFLE");
+    g_shuffle = sh ? strtoull(sh, nullptr, 10) : 0ull;
+    const int total = gx * gy, workers = total < 8 ? total : 8;
+    std::vector<std::thread> ts;
+    for (int w = 0; w < workers; ++w)
+        ts.emplace_back([=]() {
+            for (int id = w; id < total; id += workers) run_cta(id % gx, gx, block, smem_bytes, entry, arg, id / gx, gy);
+        });
     for (auto &t : ts) t.join();
 }
 
@@ -119,11 +131,21 @@ void run_grid(int grid, int block, size_t smem_bytes, void (*entry)(void *), voi
 // ---- the product's sources, compiled for the host ---------------------------------------------------------------
 #include "../../bindsnet_b200/csrc/snn_generic.cu"
 
-// the fused DiehlAndCook2015 kernels (TMA, mbarrier, inline PTX) are not emulated: the emulated library has the generic tier only
-struct snn_net;
-int snn_fused_dc_supported(const snn_net_t *, const snn_run_opts_t *) { return 0; }
-size_t snn_fused_dc_workspace_bytes(const snn_net_t *, const snn_run_opts_t *) { return 0; }
-int snn_fused_dc_launch(const snn_net_t *, const snn_run_opts_t *, void *, size_t, cudaStream_t, int *) { return SNN_ERR_UNSUPPORTED; }
+// the fused DiehlAndCook2015 window kernel (tier 2, the metric's kernel): its bulk copies / mbarriers / polling loads run on
+// the emulation's model of them (cuda_emu.h); the structure check of the static matrices is done on the host here
+int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t) {
+    if (C.structure != SNN_W_DIAG && C.structure != SNN_W_OFFDIAG) return SNN_OK;
+    const bool diag = C.structure == SNN_W_DIAG;
+    bool bad = false;
+    for (size_t i = 0; i < (size_t)n && !bad; ++i)
+        for (size_t j = 0; j < (size_t)n; ++j)
+            if (C.w[i * n + j] != (((i == j) == diag) ? C.structure_val : 0.0f)) { bad = true; break; }
+    if (bad && err) *err |= SNN_ERR_STRUCTURE;
+    return SNN_OK;
+}
+#include "../../bindsnet_b200/csrc/snn_fused_dc.cu"
+
+// the column-group kernel (tier 3, opt-in) is not emulated
 int snn_fused_dc2_supported(const snn_net_t *, const snn_run_opts_t *) { return 0; }
 size_t snn_fused_dc2_workspace_bytes(const snn_net_t *, const snn_run_opts_t *) { return 0; }
 int snn_fused_dc2_launch(const snn_net_t *, const snn_run_opts_t *, void *, size_t, cudaStream_t, int *) { return SNN_ERR_UNSUPPORTED; }

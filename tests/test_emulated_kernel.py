@@ -20,11 +20,12 @@ SKIP = ("dc2015_c2", "dc2015_metric_t40", "dc2015_metric_t250", "conv_mstdp_c4",
 SMALL = [c for c in cases.CASES if c not in SKIP]
 
 
-def _run_emulated(name, env=None):
+def _run_emulated(name, env=None, tier=1):
     import emu
 
     fx = helpers.Fixture(name)
     net, inputs, kw, T = fx.build("cpu")
+    net.force_tier = tier      # 1: the generic window kernel, 2: the fused DiehlAndCook2015 window kernel
     helpers.add_spike_monitors(net, T)
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})
@@ -85,6 +86,7 @@ def test_emulated_kernel_on_random_networks(seed):
     outs = []
     for backend in (emu.EmuBackend, OracleBackend):
         net, x = fuzz._build(ns, spec)
+        net.force_tier = 1
         helpers.add_spike_monitors(net, spec["T"])
         with backend() as be:
             net.run(inputs={"X": x}, time=spec["T"])
@@ -148,16 +150,18 @@ def test_emulated_kernel_large_batch_wide_layer_paths():
         return net, torch.bernoulli(0.12 * torch.ones(T, B, 1, 28, 28), generator=g).byte()
 
     outs = []
-    for backend in (emu.EmuBackend, OracleBackend):
+    for backend, tier in ((emu.EmuBackend, 1), (emu.EmuBackend, 2), (OracleBackend, 0)):
         net, x = build()
+        net.force_tier = tier
         helpers.add_spike_monitors(net, T)
         with backend() as be:
             net.run({"X": x}, time=T, one_spike_seed=3)
             assert be.err == 0
         outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
-    assert int(outs[1][1]["L/Ae/count"].sum()) > 100 and int(outs[1][1]["L/Ai/count"].sum()) > 100
-    helpers.assert_bit_identical(outs[0][0], outs[1][0], "state (emulated kernel)")
-    helpers.assert_bit_identical(outs[0][1], outs[1][1], "spike counts (emulated kernel)")
+    assert int(outs[2][1]["L/Ae/count"].sum()) > 100 and int(outs[2][1]["L/Ai/count"].sum()) > 100
+    for k, what in ((0, "generic"), (1, "fused")):
+        helpers.assert_bit_identical(outs[k][0], outs[2][0], f"state (emulated {what} kernel)")
+        helpers.assert_bit_identical(outs[k][1], outs[2][1], f"spike counts (emulated {what} kernel)")
 
 
 def test_emulated_kernel_monitors_and_state_carry_over():
@@ -176,8 +180,9 @@ def test_emulated_kernel_monitors_and_state_carry_over():
     xa = torch.bernoulli(0.05 * torch.ones(40, 6, 1, 28, 28), generator=g).byte()
     xb = torch.bernoulli(0.05 * torch.ones(30, 3, 1, 28, 28), generator=g).byte()
     outs = []
-    for backend in (emu.EmuBackend, OracleBackend):
+    for backend, tier in ((emu.EmuBackend, 1), (emu.EmuBackend, 2), (OracleBackend, 0)):
         net = DiehlAndCook2015(n_inpt=784, n_neurons=50, batch_size=6, inpt_shape=(1, 28, 28), inh=120.0)
+        net.force_tier = tier
         with torch.no_grad():
             net.connections[("X", "Ae")].w.copy_(w0)
         net.add_monitor(Monitor(net.layers["Ae"], ["s", "v"], time=40), "ae")
@@ -193,7 +198,72 @@ def test_emulated_kernel_monitors_and_state_carry_over():
             assert be.err == 0
         assert net.layers["Ae"].v.shape == (3, 50)
         outs.append((helpers.snapshot(net), rec))
-    helpers.assert_bit_identical(outs[0][0], outs[1][0], "multi-window state (emulated kernel)")
-    for k in outs[0][1]:
-        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
-    assert outs[1][1]["s2"].sum() > 0
+    for q, what in ((0, "generic"), (1, "fused")):
+        helpers.assert_bit_identical(outs[q][0], outs[2][0], f"multi-window state (emulated {what} kernel)")
+        for k in outs[q][1]:
+            assert np.array_equal(outs[q][1][k], outs[2][1][k]), (what, k)
+    assert outs[2][1]["s2"].sum() > 0
+
+
+# ---- the fused DiehlAndCook2015 window kernel (tier 2: the metric's kernel) under emulation ---------------------------
+# Its bulk copies (cp.async.bulk + mbarrier) run on the emulator's model of them: the copy happens at issue — the earliest
+# moment the hardware could overwrite the destination —, waits yield until the phase has completed.
+FUSED_GOLDEN = ["dc2015_multi", "dc2015_onespike", "dc2015_eval", "dc2015_b1_t1", "dc2015_silent"]
+
+
+@pytest.mark.parametrize("name", FUSED_GOLDEN)
+def test_emulated_fused_kernel_bit_exact_vs_oracle(name):
+    s_emu, c_emu = _run_emulated(name, tier=2)
+    _, s_cpu, c_cpu = helpers.run_case_oracle(name)
+    helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated fused kernel)")
+    helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated fused kernel)")
+
+
+def _fused_variant(name, env=None):
+    import emu
+    import test_gpu_variants as V
+    from oracle.oracle import OracleBackend
+
+    outs = []
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        for backend, tier in ((emu.EmuBackend, 2), (OracleBackend, 0)):
+            net, inputs, T = V._build(name, "cpu")
+            net.force_tier = tier
+            helpers.add_spike_monitors(net, T)
+            with backend() as be:
+                net.run(inputs=inputs, time=T, one_spike_seed=cases.ONE_SPIKE_SEED)
+                assert be.err == 0
+            outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert int(outs[1][1]["L/Ae/count"].sum()) > 0
+    return outs
+
+
+def _variant_names():
+    import test_gpu_variants as V
+
+    return list(V._variants())
+
+
+@pytest.mark.parametrize("name", _variant_names())
+def test_emulated_fused_kernel_option_variants(name):
+    """The option variants of tests/test_gpu_variants.py (WeightDependentPostPre, mean reduction, additive traces, voltage
+    bounds, weight decay, batches above 128, multi-spike, dense input slots ...) through the emulated fused kernel."""
+    outs = _fused_variant(name)
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], f"{name} state (emulated fused kernel)")
+    helpers.assert_bit_identical(outs[0][1], outs[1][1], f"{name} spike counts (emulated fused kernel)")
+
+
+@pytest.mark.parametrize("name", ["wdep_mean_lists", "batch160_lists", "lean_dense_slots", "lean_b40_n100"])
+@pytest.mark.parametrize("seed", ["1", "2"])
+def test_emulated_fused_kernel_under_random_thread_interleavings(name, seed):
+    outs = _fused_variant(name, env={"SNN_EMU_SHUFFLE": seed})
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], f"{name} state (emulated fused kernel, shuffled schedule {seed})")
+    helpers.assert_bit_identical(outs[0][1], outs[1][1], f"{name} spike counts (emulated fused kernel, shuffled schedule {seed})")
