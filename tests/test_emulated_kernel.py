@@ -267,3 +267,44 @@ def test_emulated_fused_kernel_under_random_thread_interleavings(name, seed):
     outs = _fused_variant(name, env={"SNN_EMU_SHUFFLE": seed})
     helpers.assert_bit_identical(outs[0][0], outs[1][0], f"{name} state (emulated fused kernel, shuffled schedule {seed})")
     helpers.assert_bit_identical(outs[0][1], outs[1][1], f"{name} spike counts (emulated fused kernel, shuffled schedule {seed})")
+
+
+def test_emulated_delta_window_and_combine():
+    """CPU twin of test_gpu_ops.test_delta_window_writes_the_change_and_leaves_the_weights: the fused kernel's delta window
+    (snn_run_opts_t.delta_w / delta_theta: the multi-GPU combine's input) writes W_end - W_start / theta_end - theta_start and
+    leaves W / theta alone; the in-place combine equals the snapshot-based one — all under emulation."""
+    import torch
+
+    import emu
+    from bindsnet_b200.models import DiehlAndCook2015
+
+    def make():
+        torch.manual_seed(3)
+        net = DiehlAndCook2015(n_inpt=784, n_neurons=96, batch_size=8, inpt_shape=(1, 28, 28), norm=78.4, theta_plus=0.05)
+        net.force_tier = 2
+        return net
+
+    x = torch.bernoulli(0.04 * torch.ones(80, 8, 1, 28, 28), generator=torch.Generator().manual_seed(5)).byte()
+    a, b = make(), make()
+    w0, th0 = a.connections[("X", "Ae")].w.detach().clone(), a.layers["Ae"].theta.clone()
+    wb, thb = b.connections[("X", "Ae")].w.detach(), b.layers["Ae"].theta
+    flat = torch.full((wb.numel() + thb.numel(),), float("nan"))
+    dw, dth = flat[:wb.numel()].view_as(wb), flat[wb.numel():]
+    with emu.EmuBackend() as be:
+        a.run({"X": x}, time=80, one_spike_seed=9, b200_normalize=False)
+        b.run({"X": x}, time=80, one_spike_seed=9, b200_normalize=False, b200_delta=(dw, dth))
+        assert be.err == 0
+    assert torch.equal(wb, w0) and torch.equal(thb, th0), "a delta window must not touch W / theta"
+    wa, tha = a.connections[("X", "Ae")].w.detach(), a.layers["Ae"].theta
+    assert torch.equal(dw, wa - w0) and torch.equal(dth, tha - th0)
+    assert float(dw.abs().sum()) > 0 and float(dth.abs().sum()) > 0, "nothing learned: nothing tested"
+    for lname in ("Ae", "Ai"):
+        assert torch.equal(a.layers[lname].v, b.layers[lname].v) and torch.equal(a.layers[lname].s, b.layers[lname].s)
+    L = emu.lib()
+    ref_w = torch.empty_like(w0)
+    two = (2.0 * flat).contiguous()
+    assert L.snn_b200_delta_apply(ref_w.data_ptr(), w0.data_ptr(), two.data_ptr(), 784, 96, 1, 0.0, 1.0, 1, 0, 78.4, None) == 0
+    thc = thb.clone()
+    assert L.snn_b200_delta_apply_fused(wb.data_ptr(), two.data_ptr(), 784, 96, 1, 0.0, 1.0, 1, 0, 78.4, thc.data_ptr(),
+                                        two[wb.numel():].data_ptr(), 96, None) == 0
+    assert torch.equal(wb, ref_w) and torch.equal(thc, th0 + 2.0 * dth)
