@@ -7,6 +7,7 @@ real source without a GPU and compared with the oracle bit for bit."""
 from __future__ import annotations
 
 import ctypes as C
+import mmap
 import os
 import subprocess
 
@@ -62,9 +63,21 @@ def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts) -> int:
     err = C.c_int32(0)
     opts.err_flag = C.addressof(err)
     nbytes = int(L.snn_b200_workspace_bytes(C.byref(net), C.byref(opts)))
-    ws = np.zeros(max(nbytes, 8) + 256, dtype=np.uint8)
-    base = (ws.ctypes.data + 255) & ~255
-    rc = L.snn_b200_run_window(C.byref(net), C.byref(opts), base, nbytes, None)
+    # the workspace ends at a PROT_NONE guard page: a kernel that writes past snn_b200_workspace_bytes() faults
+    page = mmap.PAGESIZE
+    al = (max(nbytes, 8) + 255) & ~255
+    total = ((al + page - 1) // page + 1) * page
+    buf = mmap.mmap(-1, total)
+    addr = C.addressof(C.c_char.from_buffer(buf))
+    libc = C.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    assert libc.mprotect(addr + total - page, page, 0) == 0
+    base = addr + total - page - al
+    try:
+        rc = L.snn_b200_run_window(C.byref(net), C.byref(opts), base, nbytes, None)
+    finally:
+        libc.mprotect(addr + total - page, page, 3)
+        del addr
     opts.err_flag = None
     if rc != _abi.SNN_OK:
         raise RuntimeError("emulated kernel: " + _abi.describe_error(rc))

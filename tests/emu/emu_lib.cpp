@@ -78,10 +78,15 @@ static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entr
     cta.rng = (g_shuffle + 1) * 0x9E3779B97F4A7C15ull + (unsigned long long)(bid + 1) * 0xD1B54A32D192ED03ull;
     std::vector<Fiber> fibers(block);
     std::vector<WarpState> warps(cta.nwarps);
-    std::vector<char> smem(smem_bytes + 64);
+    // dynamic shared memory ends at a PROT_NONE guard page: an access beyond the size the host computed for the launch
+    // (gen_smem_bytes / smem_layout) faults instead of silently landing in a neighbour
+    const size_t page = 4096, smem_al = (smem_bytes + 63) & ~(size_t)63, smem_map = ((smem_al + page - 1) / page + 1) * page;
+    char *smem_base = (char *)mmap(nullptr, smem_map, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (smem_base == MAP_FAILED) { perror("emu: mmap smem"); abort(); }
+    mprotect(smem_base + smem_map - page, page, PROT_NONE);
     cta.fibers = fibers.data();
     cta.warps = warps.data();
-    cta.dyn_smem = (float *)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+    cta.dyn_smem = (float *)(smem_base + smem_map - page - smem_al);
     char *stacks = (char *)mmap(nullptr, STACK_BYTES * block, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (stacks == MAP_FAILED) { perror("emu: mmap"); abort(); }
     tls_cta = &cta;
@@ -104,6 +109,7 @@ static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entr
     tls_cur = nullptr;
     tls_cta = nullptr;
     munmap(stacks, STACK_BYTES * block);
+    munmap(smem_base, smem_map);
 }
 
 void run_grid(int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
