@@ -16,6 +16,20 @@
 
 #include "../../include/snn_b200.h"
 
+// Kernel launches and statically sized __shared__ arrays of the small kernels (snn_ops.cu, snn_encode.cu, snn_readout.cu)
+// go through these two macros so that tests/emu can run the same sources on its CUDA-model emulation.
+#ifdef SNN_EMU
+#define SNN_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#define SNN_SHARED(type, name, count) type *name = (type *)emu::static_shared(sizeof(type) * (size_t)(count))
+#define SNN_SHARED2(type, name, rows, cols) type(*name)[cols] = (type(*)[cols])emu::static_shared(sizeof(type) * (size_t)(rows) * (cols))
+#define SNN_DYN_SHARED(type, name) type *name = (type *)emu::tls_cta->dyn_smem
+#else
+#define SNN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define SNN_SHARED(type, name, count) __shared__ type name[count]
+#define SNN_SHARED2(type, name, rows, cols) __shared__ type name[rows][cols]
+#define SNN_DYN_SHARED(type, name) extern __shared__ type name[]
+#endif
+
 #define SNN_TILE 32          // neurons (columns) per work item: one warp lane per column
 #define SNN_GEN_THREADS 256  // generic kernel: 8 warps per CTA
 #define SNN_GEN_WARPS (SNN_GEN_THREADS / 32)

@@ -12,10 +12,7 @@
 //   poisson  : inter-spike intervals ~ Poisson(1000 / (rate_hz * dt)) steps, a zero interval counts as one step,
 //              spike times are the running sums of the intervals (encodings.py:137-154); rate 0 never spikes;
 //   bernoulli: one independent trial per step with probability max_prob * p (encodings.py:84-94).
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "../../include/snn_b200.h"
+#include "snn_common.cuh"
 
 namespace {
 
@@ -118,14 +115,14 @@ extern "C" {
 int snn_b200_encode_poisson(const float *rate_hz, int32_t n, int32_t T, float dt, uint64_t seed, uint8_t *out, void *stream) {
     if (!rate_hz || !out || n <= 0 || T < 0 || !(dt > 0.0f)) return SNN_ERR_BAD_ARG;
     if (T == 0) return SNN_OK;
-    encode_poisson_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rate_hz, n, T, dt, seed, out);
+    SNN_LAUNCH(encode_poisson_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, rate_hz, n, T, dt, seed, out);
     return cudaGetLastError() == cudaSuccess ? SNN_OK : SNN_ERR_CUDA;
 }
 
 int snn_b200_encode_bernoulli(const float *prob, int32_t n, int32_t T, uint64_t seed, uint8_t *out, void *stream) {
     if (!prob || !out || n <= 0 || T < 0) return SNN_ERR_BAD_ARG;
     if (T == 0) return SNN_OK;
-    encode_bernoulli_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(prob, n, T, seed, out);
+    SNN_LAUNCH(encode_bernoulli_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, prob, n, T, seed, out);
     return cudaGetLastError() == cudaSuccess ? SNN_OK : SNN_ERR_CUDA;
 }
 

@@ -66,13 +66,13 @@ __global__ void pack_bits_kernel(const uint8_t *__restrict__ s, uint32_t *__rest
 }
 
 __global__ void __launch_bounds__(SNN_GEN_THREADS) conn_update_kernel(const __grid_constant__ DevNet N, int ci) {
-    extern __shared__ float smem[];
+    SNN_DYN_SHARED(float, smem);
     const GenSmem M = gen_carve(smem, N.B);
     phase3(N, ci, blockIdx.x, 0, N.layers[N.conns[ci].src].nw, 0, M);
 }
 
 __global__ void __launch_bounds__(SNN_GEN_THREADS) conn_normalize_kernel(snn_conn_t C, int ns, int nt) {
-    __shared__ float s_part[(SNN_NORM_CHUNKS + 1) * 32];
+    SNN_SHARED(float, s_part, (SNN_NORM_CHUNKS + 1) * 32);
     normalize_tile(C, ns, nt, blockIdx.x, s_part);
 }
 
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(SNN_GEN_THREADS) delta_apply_kernel(snn_conn_t
                                                                        float *theta, const float *__restrict__ dtheta, int n_theta) {
     if (theta)   // theta = theta0 + sum_r dtheta_r, in place, spread over the grid
         for (int k = blockIdx.x * SNN_GEN_THREADS + threadIdx.x; k < n_theta; k += gridDim.x * SNN_GEN_THREADS) theta[k] = theta[k] + dtheta[k];
-    __shared__ float s_part[(SNN_NORM_CHUNKS + 1) * 32];
+    SNN_SHARED(float, s_part, (SNN_NORM_CHUNKS + 1) * 32);
     delta_apply_tile(C, w0, dws, ns, nt, blockIdx.x, s_part);
 }
 
@@ -122,7 +122,7 @@ int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t 
     if (C.structure != SNN_W_DIAG && C.structure != SNN_W_OFFDIAG) return SNN_OK;
     const size_t total = (size_t)n * n;
     const int blocks = (int)((total + 2047) / 2048 < 1184 ? (total + 2047) / 2048 : 1184);   // 8 elements per thread, up to 8 CTAs per SM
-    verify_structure_kernel<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(C.w, n, C.structure, C.structure_val, err);
+    SNN_LAUNCH(verify_structure_kernel, blocks > 0 ? blocks : 1, 256, 0, stream, C.w, n, C.structure, C.structure_val, err);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -135,12 +135,12 @@ int snn_b200_conn_compute(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt, 
         if (!conn->b || conn->cin * conn->hin * conn->win != n_src || conn->cout * conn->hout * conn->wout != n_tgt) return SNN_ERR_BAD_ARG;
         const size_t total = (size_t)B * n_tgt;
         const int blocks = (int)((total + 255) / 256 < 4736 ? (total + 255) / 256 : 4736);
-        conv_compute_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt, B, s, out);
+        SNN_LAUNCH(conv_compute_kernel, blocks, 256, 0, (cudaStream_t)stream, *conn, n_src, n_tgt, B, s, out);
         return cuda_rc(cudaGetLastError());
     }
     dim3 grid((n_tgt + SNN_TILE - 1) / SNN_TILE, (B + SNN_GEN_WARPS - 1) / SNN_GEN_WARPS);
     if (grid.y > 64) grid.y = 64;
-    conn_compute_kernel<<<grid, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt, B, s, out);
+    SNN_LAUNCH(conn_compute_kernel, grid, SNN_GEN_THREADS, 0, (cudaStream_t)stream, *conn, n_src, n_tgt, B, s, out);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -171,11 +171,11 @@ int snn_b200_conn_update(const snn_net_t *net, int32_t ci, int32_t B, void *work
         D.xpub = D.L.x;  // slot 0 = the layer's current trace
         if (off > workspace_bytes) return SNN_ERR_WORKSPACE;
         const int warps = B * D.nw;
-        pack_bits_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(D.L.s, D.bits, B, D.L.n, D.nw);
+        SNN_LAUNCH(pack_bits_kernel, (warps * 32 + 255) / 256, 256, 0, stream, D.L.s, D.bits, B, D.L.n, D.nw);
     }
     const size_t smem = gen_smem_bytes(B);
     cudaFuncSetAttribute(conn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conn_update_kernel<<<N.layers[C.tgt].nw, SNN_GEN_THREADS, smem, stream>>>(N, ci);
+    SNN_LAUNCH(conn_update_kernel, N.layers[C.tgt].nw, SNN_GEN_THREADS, smem, stream, N, ci);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -184,17 +184,17 @@ int snn_b200_conn_normalize(const snn_conn_t *conn, int32_t n_src, int32_t n_tgt
     if (!conn->has_norm) return SNN_OK;
     if (conn->kind == SNN_CONN_CONV2D) {
         const int F = conn->cout * conn->cin;
-        conv_normalize_kernel<<<(F + SNN_GEN_THREADS - 1) / SNN_GEN_THREADS, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn);
+        SNN_LAUNCH(conv_normalize_kernel, (F + SNN_GEN_THREADS - 1) / SNN_GEN_THREADS, SNN_GEN_THREADS, 0, (cudaStream_t)stream, *conn);
         return cuda_rc(cudaGetLastError());
     }
-    conn_normalize_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(*conn, n_src, n_tgt);
+    SNN_LAUNCH(conn_normalize_kernel, (n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream, *conn, n_src, n_tgt);
     return cuda_rc(cudaGetLastError());
 }
 
 int snn_b200_delta_prepare(const float *w, const float *w0, float *dw, size_t count, void *stream) {
     if (!w || !w0 || !dw) return SNN_ERR_BAD_ARG;
     const int blocks = (int)((count + 1023) / 1024 < 1184 ? (count + 1023) / 1024 : 1184);
-    delta_prepare_kernel<<<blocks > 0 ? blocks : 1, 256, 0, (cudaStream_t)stream>>>(w, w0, dw, count);
+    SNN_LAUNCH(delta_prepare_kernel, blocks > 0 ? blocks : 1, 256, 0, (cudaStream_t)stream, w, w0, dw, count);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -204,7 +204,7 @@ int snn_b200_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t
     snn_conn_t C;
     memset(&C, 0, sizeof(C));
     C.w = w; C.has_clamp = has_clamp; C.wmin = wmin; C.wmax = wmax; C.has_norm = has_norm; C.norm_abs = norm_abs; C.norm = norm;
-    delta_apply_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(C, w0, dw_sum, n_src, n_tgt, nullptr, nullptr, 0);
+    SNN_LAUNCH(delta_apply_kernel, (n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream, C, w0, dw_sum, n_src, n_tgt, nullptr, nullptr, 0);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -215,7 +215,7 @@ int snn_b200_delta_apply_fused(float *w, const float *dw_sum, int32_t n_src, int
     snn_conn_t C;
     memset(&C, 0, sizeof(C));
     C.w = w; C.has_clamp = has_clamp; C.wmin = wmin; C.wmax = wmax; C.has_norm = has_norm; C.norm_abs = norm_abs; C.norm = norm;
-    delta_apply_kernel<<<(n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream>>>(C, w, dw_sum, n_src, n_tgt, theta, dtheta_sum,
+    SNN_LAUNCH(delta_apply_kernel, (n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, 0, (cudaStream_t)stream, C, w, dw_sum, n_src, n_tgt, theta, dtheta_sum,
                                                                                                         n_theta);
     return cuda_rc(cudaGetLastError());
 }

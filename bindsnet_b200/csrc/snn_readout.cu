@@ -4,10 +4,7 @@
 // them over time first; the window kernels already deliver that sum (snn_layer_t.rec_count / SpikeCounter), so these
 // kernels start from [n_samples, n_neurons] int32 counts.  Counts are integers: every sum of them is exact in fp32
 // whatever its order; the weighted sums of `proportion_weighting` use a fixed reduction order (deterministic).
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "../../include/snn_b200.h"
+#include "snn_common.cuh"
 
 namespace {
 
@@ -19,8 +16,8 @@ constexpr int MAXL = 64;   // labels (classes)
 __global__ void __launch_bounds__(128) assign_labels_kernel(const int32_t *__restrict__ counts, const int64_t *__restrict__ labels, int S, int n,
                                                              int L, float alpha, float *__restrict__ rates, float *__restrict__ proportions,
                                                              int64_t *__restrict__ assignments) {
-    __shared__ int n_lab[MAXL];
-    extern __shared__ float acc[];   // [L][blockDim.x]
+    SNN_SHARED(int, n_lab, MAXL);
+    SNN_DYN_SHARED(float, acc);   // [L][blockDim.x]
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     for (int i = threadIdx.x; i < L; i += blockDim.x) n_lab[i] = 0;
     for (int i = 0; i < L; ++i) acc[i * blockDim.x + threadIdx.x] = 0.0f;
@@ -58,9 +55,9 @@ __global__ void __launch_bounds__(128) assign_labels_kernel(const int32_t *__res
 __global__ void __launch_bounds__(256) predict_kernel(const int32_t *__restrict__ counts, const int64_t *__restrict__ assignments,
                                                        const float *__restrict__ proportions, int S, int n, int L,
                                                        int64_t *__restrict__ predictions) {
-    __shared__ float part[MAXL][256 / 32];
-    __shared__ int n_as[MAXL];
-    __shared__ float rate[MAXL];
+    SNN_SHARED2(float, part, MAXL, 256 / 32);
+    SNN_SHARED(int, n_as, MAXL);
+    SNN_SHARED(float, rate, MAXL);
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < L; i += blockDim.x) n_as[i] = 0;
     __syncthreads();
@@ -104,8 +101,7 @@ int snn_b200_assign_labels(const int32_t *counts, const int64_t *labels, int32_t
     if (!counts || !labels || !rates || !proportions || !assignments || S <= 0 || n <= 0 || n_labels <= 0) return SNN_ERR_BAD_ARG;
     if (n_labels > MAXL) return SNN_ERR_UNSUPPORTED;
     const int threads = 128;
-    assign_labels_kernel<<<(n + threads - 1) / threads, threads, sizeof(float) * n_labels * threads, (cudaStream_t)stream>>>(
-        counts, labels, S, n, n_labels, alpha, rates, proportions, assignments);
+    SNN_LAUNCH(assign_labels_kernel, (n + threads - 1) / threads, threads, sizeof(float) * n_labels * threads, (cudaStream_t)stream, counts, labels, S, n, n_labels, alpha, rates, proportions, assignments);
     return cudaGetLastError() == cudaSuccess ? SNN_OK : SNN_ERR_CUDA;
 }
 
@@ -113,7 +109,7 @@ int snn_b200_predict(const int32_t *counts, const int64_t *assignments, const fl
                      int64_t *predictions, void *stream) {
     if (!counts || !assignments || !predictions || S <= 0 || n <= 0 || n_labels <= 0) return SNN_ERR_BAD_ARG;
     if (n_labels > MAXL) return SNN_ERR_UNSUPPORTED;
-    predict_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(counts, assignments, proportions, S, n, n_labels, predictions);
+    SNN_LAUNCH(predict_kernel, S, 256, 0, (cudaStream_t)stream, counts, assignments, proportions, S, n, n_labels, predictions);
     return cudaGetLastError() == cudaSuccess ? SNN_OK : SNN_ERR_CUDA;
 }
 

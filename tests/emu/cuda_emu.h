@@ -14,6 +14,7 @@
 #include <ucontext.h>
 
 #include <cmath>
+#include <functional>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -63,6 +64,7 @@ struct Fiber {
     int lane = 0, warp = 0;
     unsigned wseq = 0;   // warp collectives executed so far (selects the exchange buffer)
     unsigned cseq = 0;   // CTA collectives executed so far
+    size_t static_off = 0;   // statically declared __shared__ objects handed out so far (identical in every thread)
     bool done = false;
     Cta *cta = nullptr;
 };
@@ -78,7 +80,7 @@ struct Cta {
     emu_uint3 bidx{0, 0, 0};
     dim3 bdim, gdim;
     float *dyn_smem = nullptr;
-    alignas(16) unsigned char static_smem[1024];   // the kernels' few statically declared __shared__ objects
+    alignas(16) unsigned char static_smem[16384];  // the kernels' statically declared __shared__ objects
     int s_abort = 0;
     unsigned long long rng = 1;
     void (*entry)(void *) = nullptr;
@@ -92,6 +94,18 @@ void yield();                                   // switch to the next runnable f
 void run_grid(int grid, int block, size_t dyn_smem_bytes, void (*entry)(void *), void *arg);
 // independent CTAs (no grid-wide synchronisation): a 2-D grid executed by a small pool of host threads
 void run_grid_independent(int gx, int gy, int block, size_t dyn_smem_bytes, void (*entry)(void *), void *arg);
+
+// a kernel without grid-wide synchronisation: `body` is what each CUDA thread executes (SNN_LAUNCH)
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &body);
+// storage of a statically sized __shared__ array (SNN_SHARED): every thread of the CTA walks the same declarations in the
+// same order, so a per-thread running offset names the same bytes in all of them
+inline void *static_shared(size_t bytes) {
+    Fiber *f = tls_cur;
+    const size_t off = (f->static_off + 15) & ~(size_t)15;
+    f->static_off = off + bytes;
+    if (f->static_off > sizeof(f->cta->static_smem)) { fprintf(stderr, "emu: static shared memory exhausted\n"); abort(); }
+    return f->cta->static_smem + off;
+}
 
 // mbarrier + bulk copy (cp.async.bulk ... mbarrier::complete_tx): the copy happens AT ISSUE — the earliest moment the
 // hardware could overwrite the destination, i.e. the adversarial case for a missing synchronisation before the issue.
@@ -170,6 +184,9 @@ inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (s & 31u)); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
 inline long long clock64() { static thread_local long long c = 0; return c += 64; }
 inline void __nanosleep(unsigned) { emu::yield(); sched_yield(); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
@@ -177,6 +194,7 @@ template <class T> inline T __ldcg(const T *p) { return *(const volatile T *)p; 
 inline uint4 __ldcg(const uint4 *p) { return *p; }
 inline float4 __ldcg(const float4 *p) { return *p; }
 template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T __ldcs(const T *p) { return *p; }
 inline unsigned __vcmpne4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int k = 0; k < 4; ++k)
@@ -210,6 +228,8 @@ enum { cudaSuccess = 0, cudaErrorLaunchOutOfResources = 701, cudaErrorMemoryAllo
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 enum cudaMemcpyKind { cudaMemcpyDeviceToHost = 2 };
 inline cudaError_t cudaMemcpy(void *d, const void *s_, size_t n, cudaMemcpyKind) { memcpy(d, s_, n); return cudaSuccess; }

@@ -120,6 +120,10 @@ void run_grid(int grid, int block, size_t smem_bytes, void (*entry)(void *), voi
     for (auto &t : ts) t.join();
 }
 
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body) {
+    run_grid_independent((int)grid.x, (int)grid.y, (int)block.x, smem_bytes, [](void *a) { (*(const std::function<void()> *)a)(); }, (void *)&body);
+}
+
 void run_grid_independent(int gx, int gy, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
     const char *sh = getenv("SNN_EMU_SHUFFLE");
     g_shuffle = sh ? strtoull(sh, nullptr, 10) : 0ull;
@@ -139,16 +143,7 @@ void run_grid_independent(int gx, int gy, int block, size_t smem_bytes, void (*e
 
 // the fused DiehlAndCook2015 window kernel (tier 2, the metric's kernel): its bulk copies / mbarriers / polling loads run on
 // the emulation's model of them (cuda_emu.h); the structure check of the static matrices is done on the host here
-int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t) {
-    if (C.structure != SNN_W_DIAG && C.structure != SNN_W_OFFDIAG) return SNN_OK;
-    const bool diag = C.structure == SNN_W_DIAG;
-    bool bad = false;
-    for (size_t i = 0; i < (size_t)n && !bad; ++i)
-        for (size_t j = 0; j < (size_t)n; ++j)
-            if (C.w[i * n + j] != (((i == j) == diag) ? C.structure_val : 0.0f)) { bad = true; break; }
-    if (bad && err) *err |= SNN_ERR_STRUCTURE;
-    return SNN_OK;
-}
+int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t stream);   // snn_ops.cu
 #include "../../bindsnet_b200/csrc/snn_fused_dc.cu"
 
 // the column-group kernel (tier 3, opt-in) is not emulated
@@ -158,35 +153,7 @@ int snn_fused_dc2_launch(const snn_net_t *, const snn_run_opts_t *, void *, size
 
 #include "../../bindsnet_b200/csrc/snn_api.cu"
 
-// ---- the multi-GPU combine (bindsnet_b200/csrc/snn_combine.cuh) on host memory --------------------------------------
-#include "../../bindsnet_b200/csrc/snn_combine.cuh"
-
-namespace {
-struct CombineArgs { snn_conn_t C; const float *w0; const float *dws; int ns, nt; };
-void combine_entry(void *a) {
-    const CombineArgs &A = *(const CombineArgs *)a;
-    delta_apply_tile(A.C, A.w0, A.dws, A.ns, A.nt, (int)blockIdx.x, emu::tls_cta->dyn_smem);
-}
-int run_combine(float *w, const float *w0, const float *dw_sum, int n_src, int n_tgt, int has_clamp, float wmin, float wmax, int has_norm,
-                int norm_abs, float norm, float *theta, const float *dtheta, int n_theta) {
-    if (!w || !w0 || !dw_sum || n_src <= 0 || n_tgt <= 0) return SNN_ERR_BAD_ARG;
-    if (theta) for (int k = 0; k < n_theta; ++k) theta[k] = theta[k] + dtheta[k];
-    CombineArgs A;
-    memset(&A, 0, sizeof(A));
-    A.C.w = w; A.C.has_clamp = has_clamp; A.C.wmin = wmin; A.C.wmax = wmax; A.C.has_norm = has_norm; A.C.norm_abs = norm_abs; A.C.norm = norm;
-    A.w0 = w0; A.dws = dw_sum; A.ns = n_src; A.nt = n_tgt;
-    emu::run_grid((n_tgt + SNN_TILE - 1) / SNN_TILE, SNN_GEN_THREADS, sizeof(float) * (SNN_NORM_CHUNKS + 1) * 32, combine_entry, &A);
-    return SNN_OK;
-}
-}  // namespace
-
-extern "C" {
-int snn_b200_delta_apply(float *w, const float *w0, const float *dw_sum, int32_t n_src, int32_t n_tgt, int32_t has_clamp, float wmin, float wmax,
-                         int32_t has_norm, int32_t norm_abs, float norm, void *) {
-    return run_combine(w, w0, dw_sum, n_src, n_tgt, has_clamp, wmin, wmax, has_norm, norm_abs, norm, nullptr, nullptr, 0);
-}
-int snn_b200_delta_apply_fused(float *w, const float *dw_sum, int32_t n_src, int32_t n_tgt, int32_t has_clamp, float wmin, float wmax,
-                               int32_t has_norm, int32_t norm_abs, float norm, float *theta, const float *dtheta_sum, int32_t n_theta, void *) {
-    return run_combine(w, w, dw_sum, n_src, n_tgt, has_clamp, wmin, wmax, has_norm, norm_abs, norm, theta, dtheta_sum, n_theta);
-}
-}
+// ---- the single-operator kernels, the multi-GPU combine, the encoders and the read-out --------------------------------
+#include "../../bindsnet_b200/csrc/snn_ops.cu"
+#include "../../bindsnet_b200/csrc/snn_encode.cu"
+#include "../../bindsnet_b200/csrc/snn_readout.cu"

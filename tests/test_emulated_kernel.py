@@ -308,3 +308,137 @@ def test_emulated_delta_window_and_combine():
     assert L.snn_b200_delta_apply_fused(wb.data_ptr(), two.data_ptr(), 784, 96, 1, 0.0, 1.0, 1, 0, 78.4, thc.data_ptr(),
                                         two[wb.numel():].data_ptr(), 96, None) == 0
     assert torch.equal(wb, ref_w) and torch.equal(thc, th0 + 2.0 * dth)
+
+
+# ---- the small kernels of the library (snn_ops.cu, snn_encode.cu, snn_readout.cu) under emulation -----------------------
+
+def test_emulated_single_operator_entry_points():
+    """CPU twin of test_gpu_parity.test_single_operator_entry_points and test_gpu_ops.test_conv2d_single_operators...:
+    Connection.compute / update / normalize and Conv2dConnection.compute / normalize through the emulated kernels equal the
+    oracle's bit for bit."""
+    import numpy as np
+    import torch
+
+    import emu
+    from bindsnet_b200.learning import PostPre
+    from bindsnet_b200.network import nodes, topology
+    from oracle.oracle import OracleBackend
+
+    res = []
+    for backend in (emu.EmuBackend, OracleBackend):
+        g = torch.Generator().manual_seed(9)
+        X = nodes.Input(n=70, traces=True); Y = nodes.LIFNodes(n=45, traces=True)
+        Cn = topology.Connection(X, Y, w=torch.rand(70, 45, generator=g), b=torch.rand(45, generator=g),
+                                 update_rule=PostPre, nu=(1e-2, 2e-2), reduction=torch.sum, wmin=0.0, wmax=1.0, norm=10.0)
+        for l in (X, Y):
+            l.compute_decays(1.0); l.set_batch_size(5)
+        X.s = torch.bernoulli(0.3 * torch.ones(5, 70), generator=g).bool(); X.x = torch.rand(5, 70, generator=g)
+        Y.s = torch.bernoulli(0.3 * torch.ones(5, 45), generator=g).bool(); Y.x = torch.rand(5, 45, generator=g)
+        Xc = nodes.Input(shape=[2, 11, 9], traces=True); H = nodes.LIFNodes(shape=[5, 6, 5], traces=True)
+        cc = topology.Conv2dConnection(Xc, H, kernel_size=(3, 3), stride=2, padding=1, wmin=-1.0, wmax=1.0, norm=0.4,
+                                       w=torch.rand(5, 2, 3, 3, generator=g) - 0.3, b=torch.rand(5, generator=g))
+        sc = torch.bernoulli(0.3 * torch.ones(7, 2, 11, 9), generator=g).byte()
+        with backend():
+            out = Cn.compute(X.s)
+            Cn.update(learning=True)
+            w_after_update = Cn.w.detach().clone()
+            Cn.normalize()
+            outc = cc.compute(sc)
+            cc.normalize()
+        res.append([t.detach().numpy().copy() for t in (out, w_after_update, Cn.w, outc, cc.w)])
+    for a, b in zip(*res):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert res[0][0].shape == (5, 45) and res[0][3].shape == (7, 5, 6, 5)
+
+
+def test_emulated_readout_kernels_match_the_torch_formulas():
+    """CPU twin of test_gpu_ops.test_readout_kernels_match_the_torch_formulas: snn_b200_assign_labels / snn_b200_predict
+    under emulation against bindsnet_b200.evaluation's CPU formulas (pinned against the live reference elsewhere)."""
+    import torch
+
+    import emu
+    from bindsnet_b200 import _backend, evaluation as ev
+
+    g = torch.Generator().manual_seed(8)
+    S, n, L = 64, 300, 10
+    counts = torch.poisson(3.0 * torch.rand(S, n, generator=g), generator=g).int().contiguous()
+    labels = torch.randint(0, L, (S,), generator=g)
+    a_c, p_c, r_c = ev.assign_labels(counts, labels, L)
+    with emu.EmuBackend():
+        rates = torch.zeros(n, L); prop = torch.empty(n, L); asg = torch.empty(n, dtype=torch.int64)
+        _backend.assign_labels(counts, labels.contiguous(), L, 1.0, rates, prop, asg)
+        assert torch.equal(asg, a_c) and torch.allclose(prop, p_c, atol=1e-6) and torch.allclose(rates, r_c, atol=1e-5)
+        rates2 = rates.clone(); prop2 = torch.empty(n, L); asg2 = torch.empty(n, dtype=torch.int64)
+        _backend.assign_labels(counts.flip(0).contiguous(), labels.contiguous(), L, 0.8, rates2, prop2, asg2)
+        a2_c, p2_c, r2_c = ev.assign_labels(counts.flip(0), labels, L, rates=r_c.clone(), alpha=0.8)
+        assert torch.equal(asg2, a2_c) and torch.allclose(rates2, r2_c, atol=1e-5)
+        pred = torch.empty(S, dtype=torch.int64)
+        _backend.predict(counts, asg, None, L, pred)
+        assert torch.equal(pred, ev.all_activity(counts, a_c, L))
+        predw = torch.empty(S, dtype=torch.int64)
+        _backend.predict(counts, asg, prop.contiguous(), L, predw)
+        assert (predw != ev.proportion_weighting(counts, a_c, p_c, L)).sum() <= 1   # weighted float sums: a near-tie may fall the other way
+
+
+def test_emulated_encoders():
+    """The on-device encoders (csrc/snn_encode.cu) under emulation: Bernoulli rates, Poisson rates against the CPU
+    restatement of the reference's encoder, and the counter-based stream property (a train depends on seed and element only)."""
+    import numpy as np
+    import torch
+
+    import emu
+    from bindsnet_b200 import _backend
+    from bindsnet_b200.encoding import poisson
+
+    with emu.EmuBackend():
+        p = torch.tensor([0.0, 0.05, 0.3, 1.0]).repeat_interleave(1500).contiguous()
+        out = torch.empty(100, p.numel(), dtype=torch.uint8)
+        _backend.encode_bernoulli(p, 100, 3, out)
+        got = out.float().view(100, 4, 1500).mean(dim=(0, 2)).numpy()
+        assert got[0] == 0.0 and got[3] == 1.0
+        assert abs(got[1] - 0.05) < 5 * np.sqrt(0.05 * 0.95 / 1.5e5) and abs(got[2] - 0.3) < 5 * np.sqrt(0.3 * 0.7 / 1.5e5)
+        rates = torch.tensor([0.0, 10.0, 64.0, 128.0]).repeat_interleave(1200).contiguous()
+        T = 200
+        dev = torch.empty(T, rates.numel(), dtype=torch.uint8)
+        _backend.encode_poisson(rates, T, 1.0, 77, dev)
+        again = torch.empty_like(dev)
+        _backend.encode_poisson(rates, T, 1.0, 77, again)
+        other = torch.empty_like(dev)
+        _backend.encode_poisson(rates, T, 1.0, 78, other)
+        assert torch.equal(dev, again) and not torch.equal(dev, other)
+        first = torch.empty(T, 1200, dtype=torch.uint8)                 # the first 1200 elements alone: the same trains
+        _backend.encode_poisson(rates[:1200].contiguous(), T, 1.0, 77, first)
+        assert torch.equal(first, dev[:, :1200])
+    torch.manual_seed(5)
+    ref = poisson(rates, time=T, dt=1.0).numpy()                        # CPU restatement of encodings.py:99-156
+    d = dev.numpy()
+    for k, r in enumerate([0.0, 10.0, 64.0, 128.0]):
+        a, b = ref[:, k * 1200:(k + 1) * 1200].sum(0).astype(np.float64), d[:, k * 1200:(k + 1) * 1200].sum(0).astype(np.float64)
+        if r == 0.0:
+            assert a.sum() == 0 and b.sum() == 0
+            continue
+        se = np.sqrt(a.var() / 1200 + b.var() / 1200) + 1e-9
+        assert abs(a.mean() - b.mean()) < 5 * se + 1e-3, f"{r} Hz: mean count {a.mean():.4f} vs {b.mean():.4f}"
+
+
+def test_emulated_scripted_tier():
+    """The scripted tier (user-defined Nodes / LearningRule subclasses stepped from Python, built-in pieces on their
+    single-operator kernels) with those kernels under emulation: same result as the built-in network it restates."""
+    import torch
+
+    import emu
+    import test_scripted_tier as ST
+
+    g = torch.Generator().manual_seed(2)
+    w0 = 0.9 * torch.rand(50, 30, generator=g)
+    x = torch.bernoulli(0.15 * torch.ones(60, 3, 50), generator=g).byte()
+    a, b = ST._net(True, w0), ST._net(False, w0)
+    assert a._scripted_required() and not b._scripted_required()
+    with emu.EmuBackend() as be:
+        a.run({"X": x}, time=60)
+        b.run({"X": x}, time=60)
+        assert be.err == 0
+    sa, sb = a.monitors["Y"].get("s"), b.monitors["Y"].get("s")
+    assert int(sb.sum()) > 20 and torch.equal(sa, sb)
+    wa, wb = a.connections[("X", "Y")].w, b.connections[("X", "Y")].w
+    assert float((wa - wb).abs().max() / wb.abs().max()) < 1e-5
