@@ -3,7 +3,6 @@
 The live reference cannot run this shape (42 GB of temporaries), so the oracle — pinned
 against the live reference on the smaller configurations — is the checker: the CUDA path must agree with it bit
 for bit (state, weights, spike counts) over a window long enough for Ae to spike, learn and inhibit."""
-import numpy as np
 import pytest
 import torch
 

@@ -5,9 +5,7 @@ networks against the live reference.
 
 Runs last (file name) on purpose: it was written after the round's GPU time was spent, so its first execution is the
 driver's; everything before it is the suite that ran on the B200 during the round."""
-import numpy as np
 import pytest
-import torch
 
 import cases
 import helpers
