@@ -1,0 +1,52 @@
+"""Exploratory sweep (a tool, not part of the test suite): random DiehlAndCook2015-shaped networks — neurons, batch size,
+window length, rule, reduction, traces, bounds, decay, one_spike, inhibition strength, input density, thread schedule —
+through the EMULATED fused kernel, bit for bit against the oracle.
+    python tests/emu/fused_sweep.py <seed> <count>
+profiles/emu_fused_sweep_r2.txt holds the round-2 runs (seeds 1-3, 360 configurations, 0 mismatches)."""
+import os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in ("", "tests", os.path.join("tests", "golden"), os.path.join("tests", "emu")):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import torch, numpy as np
+import cases, helpers, emu
+import test_gpu_variants as V
+from oracle.oracle import OracleBackend
+ns = cases.namespace("b200")
+L = ns.learning
+rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+bad = 0
+for it in range(N):
+    n = rng.choice([17, 20, 33, 48, 64, 75, 100, 130, 200, 260])
+    B = rng.choice([1, 2, 3, 7, 16, 31, 33, 64, 100, 129, 160, 200])
+    T = rng.choice([8, 15, 30, 45])
+    rule = rng.choice([L.PostPre, L.PostPre, L.WeightDependentPostPre])
+    red = rng.choice([torch.sum, torch.mean])
+    kw = dict(rule=rule, reduction=red, nu=(rng.choice([1e-4, 1e-3, 2e-3]), rng.choice([0.0, 1e-2, 5e-2])), additive=rng.random() < 0.3,
+              lbound=(-70.0 if rng.random() < 0.3 else None), weight_decay=(1e-3 if rng.random() < 0.2 else 0.0), one_spike=rng.random() < 0.8,
+              inh=rng.choice([120.0, 17.5, 3.0]), w_seed=rng.randrange(1000))
+    p = rng.choice([0.03, 0.08, 0.2])
+    shuffle = rng.choice([None, "1", "7"])
+    if shuffle: os.environ["SNN_EMU_SHUFFLE"] = shuffle
+    else: os.environ.pop("SNN_EMU_SHUFFLE", None)
+    outs = []
+    t0 = time.time()
+    try:
+        for be, tier in ((emu.EmuBackend, 2), (OracleBackend, 0)):
+            torch.manual_seed(99)
+            net = V._graph(ns, n, B, **kw)
+            net.force_tier = tier
+            x = cases._bernoulli_inputs(T, B, (1, 28, 28), p, 1000 + it)
+            helpers.add_spike_monitors(net, T)
+            with be() as b_:
+                net.run(inputs={"X": x}, time=T, one_spike_seed=cases.ONE_SPIKE_SEED); assert b_.err == 0
+            outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
+        helpers.assert_bit_identical(outs[0][0], outs[1][0], "state"); helpers.assert_bit_identical(outs[0][1], outs[1][1], "counts")
+        status = "ok"
+    except AssertionError as e:
+        status = "MISMATCH " + str(e)[:120]; bad += 1
+    except Exception as e:
+        status = "ERR " + type(e).__name__ + " " + str(e)[:100]
+        if "not implemented" not in str(e): bad += 1
+    print(f"{it:3d} n={n:3d} B={B:3d} T={T:2d} {rule.__name__[:8]:8s} {red.__name__:4s} os={kw['one_spike']} sh={shuffle} p={p} Ae={int(outs[-1][1]['L/Ae/count'].sum()) if outs else -1:5d} {time.time()-t0:5.1f}s {status}", flush=True)
+print("bad:", bad)
