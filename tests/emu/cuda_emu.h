@@ -64,6 +64,7 @@ struct Fiber {
     int lane = 0, warp = 0;
     unsigned wseq = 0;   // warp collectives executed so far (selects the exchange buffer)
     unsigned cseq = 0;   // CTA collectives executed so far
+    unsigned oseq = 0;   // __syncthreads_or calls executed so far (selects the OR accumulator)
     size_t static_off = 0;   // statically declared __shared__ objects handed out so far (identical in every thread)
     bool done = false;
     Cta *cta = nullptr;
@@ -154,7 +155,10 @@ inline void __syncwarp(unsigned = 0xffffffffu) { emu::tls_cur->wseq++; emu::warp
 inline void __syncthreads() { emu::tls_cur->cseq++; emu::cta_rendezvous(); }
 inline int __syncthreads_or(int pred) {
     emu::Cta *c = emu::tls_cta;
-    const unsigned buf = emu::tls_cur->cseq++ & 1u;
+    emu::tls_cur->cseq++;
+    // two accumulators used alternately by successive OR-barriers; the last arriver of one clears the other, so that it is
+    // clean for the next OR-barrier however many plain __syncthreads lie in between
+    const unsigned buf = emu::tls_cur->oseq++ & 1u;
     if (pred) c->c_or[buf] = 1;
     const unsigned g = c->c_gen;
     if (++c->c_arrived == c->nthreads) { c->c_or[buf ^ 1u] = 0; c->c_arrived = 0; ++c->c_gen; }

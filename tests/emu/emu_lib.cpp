@@ -3,7 +3,10 @@
 // HOST memory.  tests/emu/emu.py routes the host API to it the way oracle/oracle.py routes it to the oracle.
 //
 //   g++ -O1 -std=c++17 -fPIC -shared -DSNN_EMU -ffp-contract=off -Itests/emu -o tests/emu/libsnn_emu.so tests/emu/emu_lib.cpp -lpthread
+#include <execinfo.h>
+#include <signal.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <thread>
 #include <vector>
@@ -112,7 +115,32 @@ static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entr
     munmap(smem_base, smem_map);
 }
 
+// SNN_EMU_TRACE=1: a fault inside an emulated kernel (typically an access beyond a guard page) reports the faulting address,
+// the CUDA thread it happened in and a backtrace before the process dies.
+static void on_fault(int sig, siginfo_t *si, void *) {
+    char buf[256];
+    Cta *c = tls_cta; Fiber *f = tls_cur;
+    int n = snprintf(buf, sizeof(buf), "\n[emu] signal %d at address %p in block (%u,%u) thread %u\n", sig, si->si_addr, c ? c->bidx.x : 0u,
+                     c ? c->bidx.y : 0u, f ? f->tid.x : 0u);
+    if (write(2, buf, (size_t)n) < 0) {}
+    void *bt[48];
+    backtrace_symbols_fd(bt, backtrace(bt, 48), 2);
+    _exit(139);
+}
+static void install_fault_handler() {
+    static bool done = false;
+    if (done || !getenv("SNN_EMU_TRACE")) return;
+    done = true;
+    static char altstack[1 << 16];
+    stack_t ss; ss.ss_sp = altstack; ss.ss_size = sizeof(altstack); ss.ss_flags = 0;
+    sigaltstack(&ss, nullptr);
+    struct sigaction sa; memset(&sa, 0, sizeof(sa));
+    sa.sa_sigaction = on_fault; sa.sa_flags = SA_SIGINFO | SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, nullptr); sigaction(SIGBUS, &sa, nullptr);
+}
+
 void run_grid(int grid, int block, size_t smem_bytes, void (*entry)(void *), void *arg) {
+    install_fault_handler();
     const char *sh = getenv("SNN_EMU_SHUFFLE");
     g_shuffle = sh ? strtoull(sh, nullptr, 10) : 0ull;
     std::vector<std::thread> ts;
