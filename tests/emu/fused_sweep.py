@@ -2,7 +2,7 @@
 window length, rule, reduction, traces, bounds, decay, one_spike, inhibition strength, input density, thread schedule —
 through the EMULATED fused kernel, bit for bit against the oracle.
     python tests/emu/fused_sweep.py <seed> <count>
-profiles/emu_fused_sweep_r2.txt holds the round-2 runs (seeds 1-3, 360 configurations, 0 mismatches)."""
+profiles/emu_fused_sweep_r2.txt holds the round-2 runs (seeds 1-4, 480 configurations, 0 mismatches)."""
 import os, random, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in ("", "tests", os.path.join("tests", "golden"), os.path.join("tests", "emu")):
