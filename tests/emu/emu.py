@@ -89,6 +89,7 @@ def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts) -> int:
     libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
     assert libc.mprotect(addr + total - page, page, 0) == 0
     base = addr + total - page - al
+    C.memset(base, 0xA5, al)   # the real workspace is uninitialised device memory: no kernel may count on zeros
     try:
         rc = L.snn_b200_run_window(C.byref(net), C.byref(opts), base, nbytes, None)
     finally:

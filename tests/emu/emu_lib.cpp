@@ -90,6 +90,10 @@ static void run_cta(int bid, int grid, int block, size_t smem_bytes, void (*entr
     cta.fibers = fibers.data();
     cta.warps = warps.data();
     cta.dyn_smem = (float *)(smem_base + smem_map - page - smem_al);
+    // shared memory starts out as garbage on the GPU: poison it (0xFF bytes = NaN floats / -1 integers), so that a kernel
+    // relying on zero-initialised shared memory fails here too (the initcheck class of bugs)
+    memset(cta.dyn_smem, 0xFF, smem_al);
+    memset(cta.static_smem, 0xFF, sizeof(cta.static_smem));
     char *stacks = (char *)mmap(nullptr, STACK_BYTES * block, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (stacks == MAP_FAILED) { perror("emu: mmap"); abort(); }
     tls_cta = &cta;
