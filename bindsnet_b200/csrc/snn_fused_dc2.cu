@@ -92,6 +92,27 @@ struct F2Params {
     long long *prof;          // profiling only (env SNN_B200_PROF): [G][NPROF] phase cycles of thread 0
 };
 
+#ifdef SNN_EMU   // tests/emu: mbarrier / bulk copy / polling loads / named barriers on the CUDA-model emulation (test infrastructure)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int) { emu::Mbar *m = (emu::Mbar *)bar; m->phase = 0; m->pend = emu::MBAR_ARRIVAL; }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { emu::Mbar *m = (emu::Mbar *)bar; m->pend += (int32_t)bytes - emu::MBAR_ARRIVAL; emu::mbar_settle(m); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { ((emu::Mbar *)bar)->pend += (int32_t)bytes; }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { emu::Mbar *m = (emu::Mbar *)bar; m->pend -= emu::MBAR_ARRIVAL; emu::mbar_settle(m); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    const bool ok = (((const emu::Mbar *)bar)->phase & 1u) != parity;
+    if (!ok) emu::yield();
+    return ok;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    memcpy(dst, src, bytes);
+    emu::Mbar *m = (emu::Mbar *)bar; m->pend -= (int32_t)bytes; emu::mbar_settle(m);
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+    const unsigned int v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+    emu::yield(); sched_yield();
+    return v;
+}
+__device__ __forceinline__ void bar_group(int id, int count) { emu::named_barrier(id, count); }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -129,6 +150,7 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
 __device__ __forceinline__ void bar_group(int id, int count) {   // named barrier among `count` threads
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+#endif
 
 struct Misc2 {  // small per-step scratch (shared memory)
     uint64_t mbar_in[2];    // staged spike lists / pixel masks, by buffer
@@ -150,6 +172,8 @@ struct Misc2 {  // small per-step scratch (shared memory)
     int abort;              // exchange time-out: leave the time loop
     int negzero;            // the weight tile held a -0.0 when it was loaded (post_rows2 must not skip rows)
     int denseflag[2];       // staged slot (by buffer) holds a sample whose event list overflowed EV_CAP
+    int defer[8];           // per column group: the early pass left a row of this (candidate-holding) group unclamped; the late path
+                            // clamps the group once the post terms are in (the reference clamps once, after both terms)
     long long pc[NPROF];    // phase timers (profiling variant only)
     long long rs[8][16];    // ... fine stamps inside the late path, per column group
 };
@@ -249,7 +273,12 @@ __device__ __forceinline__ PassK load_k(const PassCtx2 *cx) {
 //     Several samples can spike at the same pixel: the item whose sample is the LOWEST live one at that pixel owns
 //     the row (no atomics), sums the traces of all of them in ascending sample order (the oracle's order) and
 //     rewrites the group's 4 weights: w - U*dt, clamp.  Rows at which a sample holding a CANDIDATE of this group
-//     spiked (`dm`: those samples) are left alone: the candidate's trace is undecided until the exchange lands;
+//     spiked (`dm`: those samples) are left alone: the candidate's trace is undecided until the exchange lands.
+//     In a group that holds a candidate at all, a weight the clamp would change is stored UNCLAMPED and the group is
+//     flagged (Misc2::defer): a winner of the group may still add its post term to that row (its input trace can be
+//     non-zero from an earlier spike of the pixel), and the reference clamps once, after both terms
+//     (learning.py:97-104) — clamp(clamp(w - U) + V) != clamp(w - U + V) when w - U left the range.  The late path
+//     clamps a flagged group after its post terms;
 //   mode 1, late pass once the winners are known: exactly those rows — work items = (candidate sample, event), the
 //     lowest candidate at a pixel owns the row: pre term (traces of all live samples at the pixel), then for a winner
 //     column (`gwin`) the post term of its single winner, then clamp.  Rows this pass does not touch get their post
@@ -293,6 +322,10 @@ __device__ __forceinline__ void stdp_list_body(const PassCtx2 *cx, int sb, int c
             d[BW - 4] = d1.x; d[BW - 3] = d1.y; d[BW - 2] = d1.z; d[BW - 1] = d1.w;
         }
     }
+    uint32_t anyd = 0;   // the group holds a candidate: its post terms are still to come
+    #pragma unroll
+    for (int g = 0; g < BW; ++g) anyd |= d[g];
+    bool deferred = false;
     #pragma unroll 1
     for (int idx = tid0; idx < total; idx += nthr0) {
         const int bb = lst[idx / per];
@@ -352,12 +385,17 @@ __device__ __forceinline__ void stdp_list_body(const PassCtx2 *cx, int sb, int c
                     const float V = 0.0f + xval(cx, xrow[(e & 0xffu) * P + i], (int)((e >> 8) & 0xffu), i, tstep) * c_.nu1;
                     w = w + V * c_.dts;
                 }
-                if (c_.has_clamp) w = clampf(w, c_.wmin, c_.wmax);
+                if (c_.has_clamp) {
+                    const float wc = clampf(w, c_.wmin, c_.wmax);
+                    if (!mode && anyd && wc != w) deferred = true;   // early pass, post term possibly still to come: clamp later
+                    else w = wc;
+                }
                 wv[c] = w;
             }
             *(float4 *)wp = make_float4(wv[0], wv[1], wv[2], wv[3]);
         }
     }
+    if (deferred) sh(c_.M)->defer[c4] = 1;
 }
 
 template <int CG, int BW>
@@ -644,7 +682,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     constexpr bool PROFV = (VAR & 2) != 0;
     constexpr int TJ = 4 * CG;
     constexpr int WS = (CG & 1) ? TJ : TJ + 4;
+#ifdef SNN_EMU
+    unsigned char *smem = (unsigned char *)emu::tls_cta->dyn_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem[];
+#endif
     const int B = Q.B, Bp = Q.Bp, P = Q.P, n = Q.n, T = Q.T;
     const unsigned int G = gridDim.x;
     float *W = (float *)(smem + Q.o_W);
@@ -673,7 +715,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
     uint8_t *ai_fl = (uint8_t *)(ai_map + aicap);        // bit 0: refractory counter still the undisturbed one; bit 1: spiked last
                                                          // step; bit 2: partner spiked at step -1 (input at step 0)
     Misc2 &M = *(Misc2 *)(smem + Q.o_misc);
+#ifdef SNN_EMU
+    PassCtx2 &s_cx = *(PassCtx2 *)emu::tls_cta->static_smem;
+#else
     __shared__ PassCtx2 s_cx;
+#endif
 
     const int NC = Bp * CG;                        // compute threads; the warp above them is the exchange warp
     const int tid = threadIdx.x, lane = tid & 31;
@@ -744,9 +790,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
         mbar_init(&M.mbar_in[1], 1);
         mbar_init(&M.mbar_x[0], 1);
         mbar_init(&M.mbar_x[1], 1);
+#ifndef SNN_EMU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
         M.ncand[0] = M.ncand[1] = 0; M.candgrp[0] = M.candgrp[1] = 0; M.abort = 0; M.nact = 0; M.negzero = 0;
-        for (int g = 0; g < 8; ++g) { M.colwin[g] = 0; M.nwl[g] = 0; M.nlive[g] = 0; }
+        for (int g = 0; g < 8; ++g) { M.colwin[g] = 0; M.nwl[g] = 0; M.nlive[g] = 0; M.defer[g] = 0; }
         for (int k = 0; k < 2 * 8 * 8; ++k) (&M.candmask[0][0][0])[k] = 0;
         for (int k = 0; k < 16; ++k) (&M.ncs[0][0])[k] = 0;
         M.denseflag[0] = Q.dense[0]; M.denseflag[1] = T >= 1 ? Q.dense[1] : 0;
@@ -865,7 +913,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                         if (spins > (4u << 20)) { if (Q.err) atomicOr(Q.err, SNN_ERR_BARRIER); M.abort = 1; break; }
                     }
                 }
+#ifdef SNN_EMU
+                __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
                 asm volatile("fence.acquire.gpu;" ::: "memory");
+#endif
             }
             __syncwarp();
             if (PROFV && tid == NC && Q.prof && t > 100 && t <= 132) Q.prof[160 * NPROF + ((t - 101) * 160 + blockIdx.x) * 2 + 1] = clock64() - pt;
@@ -957,6 +1009,7 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 const int sb_ = buf;   // slot t = spikes of step t-1
                 const uint32_t gwin = post_on ? M.colwin[cg] : 0u;
                 const int nwl = post_on ? M.nwl[cg] : 0;
+                const bool deferg = M.defer[cg] != 0;   // set by the early pass of step t-1 (a __syncthreads ago), uniform in the group
                 bool fast = nwl <= XR && nwl == __popc(gwin) && !M.denseflag[sb_];
                 if (fast) {
                     #pragma unroll 1
@@ -981,7 +1034,18 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 }
                 PROF(4)  // late pass
                 if (PROFV && b == 0) M.rs[cg][9] = clock64();
+                if (deferg) {   // rows the early pass left unclamped (rare): both terms are in now — the reference's single clamp
+                    bar_group(gbar, Bp);
+                    #pragma unroll 1
+                    for (int i = b; i < P; i += Bp) {
+                        float4 w4 = *(float4 *)(W + i * WS + 4 * cg);
+                        w4.x = clampf(w4.x, C.wmin, C.wmax); w4.y = clampf(w4.y, C.wmin, C.wmax);
+                        w4.z = clampf(w4.z, C.wmin, C.wmax); w4.w = clampf(w4.w, C.wmin, C.wmax);
+                        *(float4 *)(W + i * WS + 4 * cg) = w4;
+                    }
+                }
                 bar_group(gbar, Bp);   // the group's weights are final for step t-1
+                if (deferg && b == 0) M.defer[cg] = 0;
                 if (PROFV && b == 0 && Q.prof && ((M.candgrp[ppar] >> cg) & 1u)) {   // fine stamps -> sums over all late paths of the window
                     M.rs[cg][10] = clock64();
                     long long *fs = Q.prof + 160 * NPROF + 32 * 160 * 2 + 32 * 160 * 8 * 5;
@@ -1090,8 +1154,12 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
                 for (int k = lane; k < B; k += 32) { Q.win[((t + 1) % 3) * B + k] = 0ull; Q.sisum[((t + 1) % 3) * B + k] = 0u; }
             __syncwarp();
             if (lane == 0) {
+#ifdef SNN_EMU
+                __atomic_fetch_add(Q.bar, 1u, __ATOMIC_RELEASE);
+#else
                 if (PROFV && (Q.dbg & 128)) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
                 else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.bar) : "memory");
+#endif
                 mbar_arrive(&M.mbar_x[par]);   // the rows staged in step t: complete once the copies issued above have landed
             }
             if (PROFV && tid == tid_pf && t + 2 <= T && (Q.dbg & 1)) mbar_arrive(&M.mbar_in[buf]);
@@ -1230,7 +1298,11 @@ snn_dc2_window(const __grid_constant__ F2Params Q) {
 // monitor raster, flags non-binary input; one CTA also counts the incoming Ai spikes and builds the
 // inhibition table.
 __global__ void __launch_bounds__(256) snn_dc2_prepass(const __grid_constant__ F2Params Q, int BW) {
+#ifdef SNN_EMU
+    uint32_t *sbits = (uint32_t *)emu::tls_cta->dyn_smem;
+#else
     extern __shared__ uint32_t sbits[];  // [32][SW]
+#endif
     const int B = Q.B, P = Q.P, SW = Q.SW, PW = (P + 31) / 32;
     const int slot = blockIdx.x, grp = blockIdx.y, b0 = grp * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -1431,6 +1503,9 @@ struct Match2 {
 
 int device_sms2() {
     static int sms = -1;
+#ifdef SNN_EMU
+    if (sms < 0) { const char *v = getenv("SNN_EMU_FUSED_SMS"); sms = v && atoi(v) > 0 ? atoi(v) : 148; }
+#endif
     if (sms < 0) {
         int dev = 0, v = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
@@ -1498,6 +1573,11 @@ bool match2(const snn_net_t *net, const snn_run_opts_t *o, Match2 &m) {
 
 template <int CG, int BW, int VAR>
 cudaError_t launch_var2(const F2Params &Q, const Match2 &m, cudaStream_t stream) {
+#ifdef SNN_EMU
+    (void)stream;
+    emu::run_grid(m.grid, m.threads, m.smem, [](void *a) { snn_dc2_window<CG, BW, VAR>(*(const F2Params *)a); }, (void *)&Q);
+    return cudaSuccess;
+#endif
     cudaError_t e = cudaFuncSetAttribute(snn_dc2_window<CG, BW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&Q};
@@ -1591,12 +1671,12 @@ int snn_fused_dc2_launch(const snn_net_t *net, const snn_run_opts_t *opts, void 
     // the two static matrices are replaced by their constants: make sure they still have that structure
     if (snn_verify_structure(net->conns[m.cEI], Q.n, Q.err, stream) != SNN_OK || snn_verify_structure(net->conns[m.cIE], Q.n, Q.err, stream) != SNN_OK) return SNN_ERR_CUDA;
     nl += 2;
-    snn_dc2_prepass<<<dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream>>>(Q, m.BW);
+    SNN_LAUNCH(snn_dc2_prepass, dim3(T + 1, (B + 31) / 32), 256, sizeof(uint32_t) * 32 * (size_t)m.SW, stream, Q, m.BW);
     ++nl;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
         const int items = B * (P >> 2);
-        snn_dc2_trace_scan<<<(items + 255) / 256, 256, 0, stream>>>(Q);
+        SNN_LAUNCH(snn_dc2_trace_scan, (items + 255) / 256, 256, 0, stream, Q);
         ++nl;
         e = cudaGetLastError();
     }

@@ -78,6 +78,7 @@ struct Cta {
     int c_arrived = 0;
     unsigned c_gen = 0;
     int c_or[2] = {0, 0};
+    struct { int arrived = 0; unsigned gen = 0; } named[16];   // bar.sync id, count
     emu_uint3 bidx{0, 0, 0};
     dim3 bdim, gdim;
     float *dyn_smem = nullptr;
@@ -128,6 +129,14 @@ inline void cta_rendezvous() {
     const unsigned g = c->c_gen;
     if (++c->c_arrived == c->nthreads) { c->c_arrived = 0; ++c->c_gen; }
     else while (c->c_gen == g) yield();
+}
+
+// bar.sync id, count: a barrier among the `count` threads that name it
+inline void named_barrier(int id, int count) {
+    auto &nb = tls_cta->named[id & 15];
+    const unsigned g = nb.gen;
+    if (++nb.arrived == count) { nb.arrived = 0; ++nb.gen; }
+    else while (nb.gen == g) yield();
 }
 
 template <class T> inline unsigned long long to_bits(T v) { unsigned long long b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &v, sizeof(T)); return b; }
@@ -199,6 +208,18 @@ inline uint4 __ldcg(const uint4 *p) { return *p; }
 inline float4 __ldcg(const float4 *p) { return *p; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcs(const T *p) { return *p; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline unsigned __vcmpeq4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k)
+        if (((a >> (8 * k)) & 0xffu) == ((b >> (8 * k)) & 0xffu)) r |= 0xffu << (8 * k);
+    return r;
+}
+inline unsigned __vadd4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) r |= ((((a >> (8 * k)) & 0xffu) + ((b >> (8 * k)) & 0xffu)) & 0xffu) << (8 * k);
+    return r;
+}
 inline unsigned __vcmpne4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int k = 0; k < 4; ++k)
@@ -229,6 +250,10 @@ inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v)
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0, cudaErrorLaunchOutOfResources = 701, cudaErrorMemoryAllocation = 2 };
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 148; return cudaSuccess; }
+template <class F> inline cudaError_t cudaLaunchCooperativeKernel(F, dim3, dim3, void **, size_t, cudaStream_t) { return 1; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }

@@ -18,8 +18,8 @@ from bindsnet_b200 import _abi
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 LIB = os.path.join(HERE, "libsnn_emu.so")
-_SOURCES = [os.path.join(HERE, "emu_lib.cpp"), os.path.join(HERE, "cuda_emu.h")] + [
-    os.path.join(ROOT, "bindsnet_b200", "csrc", f) for f in ("snn_generic.cu", "snn_phases.cuh", "snn_common.cuh", "snn_api.cu", "snn_combine.cuh", "snn_fused_dc.cu", "snn_ops.cu", "snn_encode.cu", "snn_readout.cu")
+_SOURCES = [os.path.join(HERE, "emu_lib.cpp"), os.path.join(HERE, "emu_dc2.cpp"), os.path.join(HERE, "cuda_emu.h")] + [
+    os.path.join(ROOT, "bindsnet_b200", "csrc", f) for f in ("snn_generic.cu", "snn_phases.cuh", "snn_common.cuh", "snn_api.cu", "snn_combine.cuh", "snn_fused_dc.cu", "snn_fused_dc2.cu", "snn_ops.cu", "snn_encode.cu", "snn_readout.cu")
 ] + [os.path.join(ROOT, "include", "snn_b200.h")]
 _lib = None
 
@@ -28,7 +28,7 @@ def build(force: bool = False) -> str:
     stale = (not os.path.exists(LIB)) or any(os.path.getmtime(f) > os.path.getmtime(LIB) for f in _SOURCES)
     if force or stale:
         cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DSNN_EMU", "-ffp-contract=off", "-Wno-unknown-pragmas",
-               "-I" + HERE, "-o", LIB, os.path.join(HERE, "emu_lib.cpp"), "-lpthread"]
+               "-I" + HERE, "-o", LIB, os.path.join(HERE, "emu_lib.cpp"), os.path.join(HERE, "emu_dc2.cpp"), "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("building the emulated kernel failed:\n" + res.stderr[-4000:])
@@ -73,11 +73,16 @@ def lib() -> C.CDLL:
     return _lib
 
 
+last_tier = 0
+
+
 def run_window(net: _abi.SnnNet, opts: _abi.SnnRunOpts) -> int:
     """One window on HOST tensors through the emulated generic kernel.  Returns the device-style error flags."""
+    global last_tier
     L = lib()
     err = C.c_int32(0)
     opts.err_flag = C.addressof(err)
+    last_tier = int(L.snn_b200_select_tier(C.byref(net), C.byref(opts)))   # the kernel this window goes to (tests assert on it)
     nbytes = int(L.snn_b200_workspace_bytes(C.byref(net), C.byref(opts)))
     # the workspace ends at a PROT_NONE guard page: a kernel that writes past snn_b200_workspace_bytes() faults
     page = mmap.PAGESIZE

@@ -178,10 +178,7 @@ void run_grid_independent(int gx, int gy, int block, size_t smem_bytes, void (*e
 int snn_verify_structure(const snn_conn_t &C, int n, int32_t *err, cudaStream_t stream);   // snn_ops.cu
 #include "../../bindsnet_b200/csrc/snn_fused_dc.cu"
 
-// the column-group kernel (tier 3, opt-in) is not emulated
-int snn_fused_dc2_supported(const snn_net_t *, const snn_run_opts_t *) { return 0; }
-size_t snn_fused_dc2_workspace_bytes(const snn_net_t *, const snn_run_opts_t *) { return 0; }
-int snn_fused_dc2_launch(const snn_net_t *, const snn_run_opts_t *, void *, size_t, cudaStream_t, int *) { return SNN_ERR_UNSUPPORTED; }
+// the column-group kernel (tier 3): emu_dc2.cpp
 
 #include "../../bindsnet_b200/csrc/snn_api.cu"
 

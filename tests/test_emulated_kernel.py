@@ -39,6 +39,7 @@ def _run_emulated(name, env=None, tier=1):
             else:
                 os.environ[k] = v
     assert eb.err == 0
+    assert emu.last_tier == tier, f"window went to tier {emu.last_tier}, not {tier}"
     return helpers.snapshot(net), helpers.spike_counts(net, T)
 
 
@@ -219,7 +220,7 @@ def test_emulated_fused_kernel_bit_exact_vs_oracle(name):
     helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated fused kernel)")
 
 
-def _fused_variant(name, env=None):
+def _fused_variant(name, env=None, fused_tier=2):
     import emu
     import test_gpu_variants as V
     from oracle.oracle import OracleBackend
@@ -228,13 +229,15 @@ def _fused_variant(name, env=None):
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})
     try:
-        for backend, tier in ((emu.EmuBackend, 2), (OracleBackend, 0)):
+        for backend, tier in ((emu.EmuBackend, fused_tier), (OracleBackend, 0)):
             net, inputs, T = V._build(name, "cpu")
             net.force_tier = tier
             helpers.add_spike_monitors(net, T)
             with backend() as be:
                 net.run(inputs=inputs, time=T, one_spike_seed=cases.ONE_SPIKE_SEED)
                 assert be.err == 0
+            if backend is emu.EmuBackend:
+                assert emu.last_tier == fused_tier, f"window went to tier {emu.last_tier}, not {fused_tier}"
             outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
     finally:
         for k, v in old.items():
@@ -267,6 +270,33 @@ def test_emulated_fused_kernel_under_random_thread_interleavings(name, seed):
     outs = _fused_variant(name, env={"SNN_EMU_SHUFFLE": seed})
     helpers.assert_bit_identical(outs[0][0], outs[1][0], f"{name} state (emulated fused kernel, shuffled schedule {seed})")
     helpers.assert_bit_identical(outs[0][1], outs[1][1], f"{name} spike counts (emulated fused kernel, shuffled schedule {seed})")
+
+
+# ---- the column-group fused kernel (tier 3, opt-in) under emulation ---------------------------------------------------
+# The kernel compute-sanitizer's racecheck pointed at in round 1 (hazards fixed since): named barriers per column group,
+# a bulk-copy ring and a relaxed-polling hand-off between CTAs — shuffled thread schedules are the part that matters here.
+@pytest.mark.parametrize("name", FUSED_GOLDEN)
+def test_emulated_column_group_kernel_bit_exact_vs_oracle(name):
+    s_emu, c_emu = _run_emulated(name, tier=3)
+    _, s_cpu, c_cpu = helpers.run_case_oracle(name)
+    helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated column-group kernel)")
+    helpers.assert_bit_identical(c_emu, c_cpu, f"{name} spike counts (emulated column-group kernel)")
+
+
+def _tier3_names():
+    import test_gpu_variants as V
+
+    return sorted(V.TIER3)
+
+
+@pytest.mark.parametrize("name", _tier3_names())
+@pytest.mark.parametrize("seed", [None, "1", "2"])
+def test_emulated_column_group_kernel_variants_and_interleavings(name, seed):
+    """The shapes tests/test_gpu_variants.py sends through tier 3 on the GPU, here in program order (seed None) and under
+    two shuffled thread schedules."""
+    outs = _fused_variant(name, env={"SNN_EMU_SHUFFLE": seed} if seed else None, fused_tier=3)
+    helpers.assert_bit_identical(outs[0][0], outs[1][0], f"{name} state (emulated column-group kernel, schedule {seed})")
+    helpers.assert_bit_identical(outs[0][1], outs[1][1], f"{name} spike counts (emulated column-group kernel, schedule {seed})")
 
 
 def test_emulated_delta_window_and_combine():

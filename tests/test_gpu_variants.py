@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _graph(ns, n, B, *, rule, reduction, nu=(1e-4, 1e-2), additive=False, lbound=None, weight_decay=0.0,
-           one_spike=True, exc=22.5, inh=120.0, norm=78.4, w_seed=7):
+           one_spike=True, exc=22.5, inh=120.0, norm=78.4, w_seed=7, tiny=0.0, huge=0.0):
     """The DiehlAndCook2015 wiring (models.py:94-244) from classic Connection objects, so that the
     learning rule and its options can be chosen freely."""
     net = ns.Network(dt=1.0, batch_size=B)
@@ -27,6 +27,12 @@ def _graph(ns, n, B, *, rule, reduction, nu=(1e-4, 1e-2), additive=False, lbound
     I = ns.nodes.LIFNodes(n=n, traces=False, rest=-60.0, reset=-45.0, thresh=-40.0, tc_decay=10.0, refrac=2,
                           lbound=lbound)
     w = cases._w((784, n), w_seed, 0.3)
+    if tiny:   # a fraction of the weights next to wmin: the pre term drives them below it, the clamp becomes active
+        g = torch.Generator().manual_seed(w_seed + 1)
+        w = torch.where(torch.rand(w.shape, generator=g) < tiny, w * 1e-3, w)
+    if huge:   # ... and next to wmax: the post term drives them above it
+        g = torch.Generator().manual_seed(w_seed + 2)
+        w = torch.where(torch.rand(w.shape, generator=g) < huge, 1.0 - w * 1e-2, w)
     cxe = ns.topology.Connection(source=X, target=E, w=w, update_rule=rule, nu=nu, reduction=reduction, wmin=0.0, wmax=1.0,
                                  norm=norm, weight_decay=weight_decay)
     cei = ns.topology.Connection(source=E, target=I, w=exc * torch.diag(torch.ones(n)), wmin=0.0, wmax=exc)
@@ -53,9 +59,14 @@ def _variants():
         "lean_dense_slots": (dict(rule=L.PostPre, reduction=torch.sum, nu=(2e-3, 1e-2)), 8, 40, 70, "bernoulli"),
         "lean_no_post": (dict(rule=L.PostPre, reduction=torch.sum, nu=(1e-3, 0.0)), 16, 64, 60, "poisson"),
         "lean_weak_inh": (dict(rule=L.PostPre, reduction=torch.sum, inh=3.0, exc=30.0), 16, 64, 90, "poisson"),
+        # weights at the lower bound while pre and post term meet on one row: the reference clamps once, after both
+        "lean_clamped_rows": (dict(rule=L.PostPre, reduction=torch.sum, nu=(2e-3, 1e-2), one_spike=False, inh=3.0, tiny=0.3), 12, 64, 40,
+                              "poisson"),
+        "clamped_rows_wdep": (dict(rule=L.WeightDependentPostPre, reduction=torch.sum, nu=(2e-3, 1e-2), one_spike=False, inh=3.0, tiny=0.3),
+                              12, 64, 40, "poisson"),
     }
 
-TIER3 = {"multi_spike_lists", "lean_b40_n100", "lean_b128_n600", "lean_dense_slots", "lean_no_post", "lean_weak_inh"}
+TIER3 = {"multi_spike_lists", "lean_b40_n100", "lean_b128_n600", "lean_dense_slots", "lean_no_post", "lean_weak_inh", "lean_clamped_rows"}
 
 
 def _build(name, device):
