@@ -34,6 +34,10 @@ for it in range(N):
         B = min(B, 128)
         n = rng.choice([n, 300, 450, 640])
     p = rng.choice([0.03, 0.08, 0.2])
+    # SWEEP_WINDOWS=1: one to three consecutive windows without a reset in between (membrane, refractory counters, traces —
+    # the Input layer's included — and theta carry over), learning switched off for one of them
+    NW = rng.choice([1, 2, 3]) if os.environ.get("SWEEP_WINDOWS") else 1
+    frozen = rng.randrange(NW + 1) if NW > 1 else -1
     shuffle = rng.choice([None, "1", "7"])
     if shuffle: os.environ["SNN_EMU_SHUFFLE"] = shuffle
     else: os.environ.pop("SNN_EMU_SHUFFLE", None)
@@ -47,12 +51,17 @@ for it in range(N):
             torch.manual_seed(99)
             net = V._graph(ns, n, B, **kw)
             net.force_tier = tier
-            x = cases._bernoulli_inputs(T, B, (1, 28, 28), p, 1000 + it)
             helpers.add_spike_monitors(net, T)
             with be() as b_:
-                net.run(inputs={"X": x}, time=T, one_spike_seed=cases.ONE_SPIKE_SEED); assert b_.err == 0
+                for wi in range(NW):
+                    x = cases._bernoulli_inputs(T, B, (1, 28, 28), p, 1000 + it + 7919 * wi)
+                    net.train(wi != frozen)
+                    net.run(inputs={"X": x}, time=T, one_spike_seed=cases.ONE_SPIKE_SEED + wi); assert b_.err == 0
+                    if wi + 1 < NW: outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
             outs.append((helpers.snapshot(net), helpers.spike_counts(net, T)))
-        helpers.assert_bit_identical(outs[0][0], outs[1][0], "state"); helpers.assert_bit_identical(outs[0][1], outs[1][1], "counts")
+        for wi in range(NW):
+            helpers.assert_bit_identical(outs[wi][0], outs[NW + wi][0], f"state after window {wi}")
+            helpers.assert_bit_identical(outs[wi][1], outs[NW + wi][1], f"counts of window {wi}")
         status = "ok"
     except AssertionError as e:
         status = "MISMATCH " + str(e)[:120]; bad += 1
@@ -60,5 +69,5 @@ for it in range(N):
         status = "ERR " + type(e).__name__ + " " + str(e)[:100]
         if "not implemented" in str(e) or "tier" in str(e): status = "skip (" + str(e)[:60] + ")"
         else: bad += 1
-    print(f"{it:3d} n={n:3d} B={B:3d} T={T:2d} {rule.__name__[:8]:8s} {red.__name__:4s} os={kw['one_spike']} sh={shuffle} p={p} Ae={int(outs[-1][1]['L/Ae/count'].sum()) if outs else -1:5d} {time.time()-t0:5.1f}s {status}", flush=True)
+    print(f"{it:3d} n={n:3d} B={B:3d} T={T:2d} {rule.__name__[:8]:8s} {red.__name__:4s} os={kw['one_spike']} sh={shuffle} p={p} w={NW}/{frozen} Ae={int(outs[-1][1]['L/Ae/count'].sum()) if outs else -1:5d} {time.time()-t0:5.1f}s {status}", flush=True)
 print("bad:", bad)

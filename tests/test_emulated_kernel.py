@@ -475,11 +475,12 @@ def test_emulated_scripted_tier():
 
 
 @pytest.mark.parametrize("name,tier", [("dc2015_c2", 2), ("dc2015_c2", 1), ("dc2015_metric_t40", 2), ("dc2015_metric_t40", 1),
-                                       ("dc2015_metric_t250", 2)])
+                                       ("dc2015_metric_t250", 2), ("dc2015_c2", 3), ("dc2015_metric_t40", 3),
+                                       ("conv_mstdp_c4", 1), ("conv_mstdp_c4_b128", 1)])
 def test_emulated_kernels_at_the_baseline_configurations(name, tier):
     """BASELINE.json config 2 (n = 400, B = 32, T = 250) and the metric configuration (n = 1600, B = 128; T = 40 and the full
-    250-step window) through the emulated kernels — tier 2 is the kernel the metric is quoted on — bit for bit against the
-    oracle, which the golden fixtures pin against the live reference at exactly these shapes."""
+    250-step window) through the emulated kernels — tier 2 is the kernel the metric is quoted on —, and config 4 (the
+    convolutional MSTDP network, B = 32 and B = 128) through the generic kernel, bit for bit against the oracle, which the golden fixtures pin against the live reference at exactly these shapes."""
     s_emu, c_emu = _run_emulated(name, tier=tier)
     _, s_cpu, c_cpu = helpers.run_case_oracle(name)
     helpers.assert_bit_identical(s_emu, s_cpu, f"{name} state (emulated kernel, tier {tier})")
