@@ -85,7 +85,8 @@ class ShardedWindowRunner:
         if self._flat is None or self._flat.numel() != total or self._flat.device != dev:
             self._flat = torch.empty(total, dtype=torch.float32, device=dev)
             self._snap = torch.empty(total, dtype=torch.float32, device=dev)
-        if (dev.type == "cuda" and self._delta_windows is not False and len(learned) == 1 and len(thetas) == 1
+        # (`_emulated`: set by tests/test_distributed.py, whose ranks run the CUDA sources on tests/emu's CPU emulation)
+        if ((dev.type == "cuda" or getattr(self, "_emulated", False)) and self._delta_windows is not False and len(learned) == 1 and len(thetas) == 1
                 and int(time / net.dt) > 0 and learned[0][0].w.dim() == 2):
             # fused path: the window writes dW / dtheta into the all-reduce buffer, W0 / theta0 stay where they are
             conn, d = learned[0]

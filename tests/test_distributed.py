@@ -47,30 +47,41 @@ def _patch_cpu_combine():
     _backend.delta_prepare, _backend.delta_apply = prepare, apply
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, emulated=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from bindsnet_b200.distributed import ShardedWindowRunner
     from oracle.oracle import OracleBackend
 
-    _patch_cpu_combine()
+    if emulated:   # the ranks run the library's CUDA sources (fused window with the delta epilogue, in-place apply kernel)
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import emu
+        Backend = emu.EmuBackend
+    else:
+        _patch_cpu_combine()
+        Backend = OracleBackend
     x = _inputs()
     shard = x[:, rank * 4:(rank + 1) * 4]
     net = _make(4)
-    with OracleBackend():
+    with Backend():
         runner = ShardedWindowRunner(net)
+        runner._emulated = emulated
         runner.run({"X": shard}, time=60, one_spike_seed=17 + rank)
         net.reset_state_variables()
         runner.run({"X": shard}, time=60, one_spike_seed=27 + rank)
+        assert not emulated or runner._delta_windows is True, "the fused delta-window path was not taken"
     torch.save({"w": net.connections[("X", "Ae")].w.detach().clone(), "theta": net.layers["Ae"].theta.clone()},
                os.path.join(out, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
 
-def test_two_rank_window_combine_matches_replica_oracle(tmp_path):
-    port = 29500 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("emulated", [False, True])
+def test_two_rank_window_combine_matches_replica_oracle(tmp_path, emulated):
+    """emulated = True: the CPU twin of the 2-GPU NCCL test in tests/test_gpu_ops.py — each rank runs the fused kernel's
+    delta window and the in-place apply kernel (csrc/snn_combine.cuh) under the CUDA-model emulation, gloo does the all-reduce."""
+    port = 29500 + (os.getpid() % 1000) + (1000 if emulated else 0)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), emulated), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "rank0.pt"); r1 = torch.load(tmp_path / "rank1.pt")
     assert torch.equal(r0["w"], r1["w"]) and torch.equal(r0["theta"], r1["theta"]), "ranks diverged"
 
