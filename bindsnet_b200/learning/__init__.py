@@ -10,6 +10,9 @@ from .learning import (
     WeightDependentPostPre,
 )
 
+from .reward import AbstractReward, MovingAvgRPE
+
 __all__ = [
+    "AbstractReward", "MovingAvgRPE",
     "LearningRule", "NoOp", "PostPre", "WeightDependentPostPre", "Hebbian", "MSTDP", "MSTDPET", "Rmax",
 ]

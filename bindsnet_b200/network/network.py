@@ -40,9 +40,8 @@ class Network(torch.nn.Module):
         self.connections = {}
         self.monitors = {}
         self.train(learning)
-        if reward_fn is not None:
-            raise NotImplementedError("reward-modulated learning (reward_fn) is outside the implemented hot path")
-        self.reward_fn = None
+        # network.py:114-117: the class is instantiated here; run() asks it for each window's reward
+        self.reward_fn = reward_fn() if reward_fn is not None else None
         #: seed of the last window's one_spike tie-break stream (see snn_one_spike_key)
         self.last_one_spike_seed: Optional[int] = None
 
@@ -90,8 +89,11 @@ class Network(torch.nn.Module):
             "'inputs' must be a dict of names of layers (str) and relevant input tensors. "
             f"Got {type(inputs).__name__} instead."
         )
+        # network.py:325-326: a reward_fn replaces the run's reward by its own (e.g. a prediction error)
+        if self.reward_fn is not None:
+            kwargs["reward"] = self.reward_fn.compute(**kwargs)
         # reward-modulated rules (learning.MSTDP) read these from the run's kwargs (network.py:319-377,
-        # learning.py:1540-1556); the reward_fn hook of the constructor is not implemented
+        # learning.py:1540-1556)
         self._rule_kwargs = {k: kwargs.get(k, None) for k in ("reward", "a_plus", "a_minus")}
 
         # network.py:329-353: canonical [T, B, ...] shape, batch-size inference, state reset
