@@ -166,7 +166,7 @@ def build_net(
                 d.rec_count = _ptr(r[2]); keep.append(r[2])
     masks = getattr(network, "_conn_masks", None) or {}
     for i, ((src, tgt), conn) in enumerate(network.connections.items()):
-        fill_conn(net.conns[i], conn, index[src], index[tgt], float(network.dt), B, getattr(network, "_rule_kwargs", None))
+        fill_conn(net.conns[i], conn, index[src], index[tgt], float(network.dt), B, network._rule_kwargs_of((src, tgt)))
         m = masks.get((src, tgt))
         if m is not None:
             net.conns[i].mask = _ptr(m)

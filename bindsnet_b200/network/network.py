@@ -120,6 +120,15 @@ class Network(torch.nn.Module):
             masks=kwargs.get("masks", {}) or {},
         )
 
+    def _rule_kwargs_of(self, key) -> dict:
+        """The reward-modulation kwargs one connection's rule sees (network.py:359-377, 440-461): ``a_plus`` /
+        ``a_minus`` may be dicts keyed by connection; a connection without an entry falls back to the rule's default."""
+        out = dict(getattr(self, "_rule_kwargs", None) or {})
+        for k in ("a_plus", "a_minus"):
+            if isinstance(out.get(k, None), dict):
+                out[k] = out[k].get(key, None)
+        return out
+
     def _device(self) -> torch.device:
         return _plan.network_device(self)
 
@@ -147,10 +156,15 @@ class Network(torch.nn.Module):
         elif not is_index:
             out = m.to(dev, torch.uint8)
         else:  # index tensor, as accepted by ``s[:, clamp] = 1`` (network.py:419)
-            if m.dim() != 1:
-                raise NotImplementedError("per-step index clamps are not supported; pass a bool mask [T, n]")
-            out = torch.zeros(layer.n, dtype=torch.uint8, device=dev)
-            out[m.to(dev).long()] = 1
+            idx = m.to(dev).long()
+            if m.dim() == 1:
+                out = torch.zeros(layer.n, dtype=torch.uint8, device=dev)
+                out[idx] = 1
+            else:  # [T, k]: the neurons ``clamp[t]`` names at step t (network.py:421); negative indices wrap like indexing
+                per_step = True
+                idx = idx[:T].reshape(T, -1)
+                out = torch.zeros(T, layer.n, dtype=torch.uint8, device=dev)
+                out.scatter_(1, torch.where(idx < 0, idx + layer.n, idx), 1)
         out = out.reshape(T, layer.n) if per_step else out.reshape(layer.n)
         return out.contiguous()
 
@@ -335,7 +349,6 @@ class Network(torch.nn.Module):
         injects_v, connection updates, monitors, end-of-run normalize."""
         B = self.batch_size
         dev = self._device()
-        rule_kwargs = {k: v for k, v in (getattr(self, "_rule_kwargs", None) or {}).items() if v is not None}
 
         def get_inputs(only=None):
             cur = {}
@@ -378,6 +391,7 @@ class Network(torch.nn.Module):
                     m = (u[t] if u.dim() == 2 else u).bool().view(1, *layer.shape).expand(B, *layer.shape)
                     layer.s = layer.s & ~m if layer.s.dtype == torch.bool else layer.s.masked_fill(m, 0)
             for key, conn in self.connections.items():                        # network.py:431-454
+                rule_kwargs = {k: v for k, v in self._rule_kwargs_of(key).items() if v is not None}
                 conn.update(mask=masks.get(key), learning=self.learning, **rule_kwargs)
             for m in self.monitors.values():                                  # network.py:460-461
                 if isinstance(m, SpikeCounter) and t == 0:
