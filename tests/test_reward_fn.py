@@ -2,7 +2,8 @@
 MSTDP kernels are launched with is the reward_fn's ``compute`` of the run's kwargs.  Three episodes of a dense MSTDP
 network with ``MovingAvgRPE`` through the LIVE reference and through our host API on the oracle: same prediction
 state, same spikes, weights within the north_star's 1e-4.  CPU only; a GPU twin runs the same episodes on the kernels
-against the oracle bit for bit."""
+against the oracle bit for bit
+(tests/test_zz_gpu_late_additions.py)."""
 import importlib
 
 import numpy as np
@@ -126,12 +127,6 @@ def _kernel_vs_oracle(rule, backend, to_dev):
     assert seen_dev == seen_cpu
     assert float(cpu.connections[("X", "Y")].w.abs().sum()) > 0
     helpers.assert_bit_identical(helpers.snapshot(dev), helpers.snapshot(cpu), f"{rule} with reward_fn")
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("rule", ["MSTDP", "MSTDPET"])
-def test_reward_fn_on_the_kernels_bit_exact_vs_oracle(rule):
-    _kernel_vs_oracle(rule, None, lambda x: x.cuda())
 
 
 @pytest.mark.parametrize("rule", ["MSTDP", "MSTDPET"])
