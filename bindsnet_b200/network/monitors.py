@@ -5,7 +5,7 @@ reference's ``[time, batch, *shape]`` view from that buffer."""
 from __future__ import annotations
 
 from abc import ABC
-from typing import Iterable, Optional
+from typing import Dict, Iterable, Optional
 
 import torch
 
@@ -127,8 +127,77 @@ class SpikeCounter(AbstractMonitor):
 
 
 class NetworkMonitor(AbstractMonitor):
-    """Reference: monitors.py:127-329 — whole-network snapshots every step; not on the
-    accelerated path."""
+    """Whole-network recorder (reference: monitors.py:127-329): every step, the named state variables
+    (default ``v``, ``s``, ``w``) of the chosen layers and connections.  Not one of the monitors the window
+    kernels fill themselves: a network that carries one runs its windows step by step (``Network._run_stepwise``)
+    and ``record`` reads the tensors between the steps, as the reference does.  ``time=None`` grows the recordings
+    (:222-236), ``time=T`` keeps the last ``T`` steps (:238-254); layer variables are stored as float, connection
+    variables as they are.  Recordings stay on the device of what they record."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("NetworkMonitor is outside the hot path bindsnet_b200 implements")
+    def __init__(self, network, layers=None, connections=None, state_vars=None, time: Optional[int] = None):
+        super().__init__()
+        self.network = network
+        self.layers = layers if layers is not None else list(network.layers.keys())
+        self.connections = connections if connections is not None else list(network.connections.keys())
+        self.state_vars = state_vars if state_vars is not None else ("v", "s", "w")
+        self.time = time
+        self.reset_state_variables()
+
+    def _sources(self):
+        """(key, variable, object, is_layer) of everything recorded: a variable is skipped where the object does not
+        have it (:166-173); a MulticompartmentConnection has no ``w`` of its own in the reference (it lives in the
+        pipeline's feature), so none is recorded for it."""
+        for v in self.state_vars:
+            for l in self.layers:
+                if hasattr(self.network.layers[l], v):
+                    yield l, v, self.network.layers[l], True
+            for c in self.connections:
+                obj = self.network.connections[c]
+                if hasattr(obj, v) and not (v == "w" and hasattr(obj, "pipeline")):
+                    yield c, v, obj, False
+
+    def get(self) -> Dict:
+        return self.recording
+
+    def record(self) -> None:
+        for key, v, obj, is_layer in self._sources():
+            data = getattr(obj, v).detach()
+            data = (data.float() if is_layer else data).unsqueeze(0)
+            old = self.recording[key][v]
+            if self.time is not None:
+                old = old[1:]                                   # rolling window of the last `time` steps
+            if old.numel() == 0 and old.dim() <= 1:
+                self.recording[key][v] = data.clone()
+            else:
+                self.recording[key][v] = torch.cat((old.to(device=data.device, dtype=data.dtype), data), 0)
+        if self.time is not None:
+            self.i += 1
+
+    def save(self, path: str, fmt: str = "npz") -> None:
+        """monitors.py:258-292: ``npz`` (keys ``<layer>_<var>`` / ``<source>-<target>_<var>``) or ``pickle``."""
+        import os
+
+        import numpy as np
+
+        folder = os.path.dirname(path)
+        if folder and not os.path.exists(folder):
+            os.makedirs(folder)
+        if fmt == "npz":
+            arrays = {}
+            for key, rec in self.recording.items():
+                stem = "-".join(key) if isinstance(key, tuple) else key
+                for v, t in rec.items():
+                    arrays[f"{stem}_{v}"] = t.cpu().numpy()
+            np.savez_compressed(path, **arrays)
+        elif fmt == "pickle":
+            with open(path, "wb") as f:
+                torch.save(self.recording, f)
+
+    def reset_state_variables(self) -> None:
+        """monitors.py:294-329: empty recordings, or ``time`` rows of zeros per variable."""
+        self.recording = {k: {} for k in list(self.layers) + list(self.connections)}
+        if self.time is not None:
+            self.i = 0
+        for key, v, obj, _ in self._sources():
+            t = getattr(obj, v)
+            self.recording[key][v] = torch.Tensor() if self.time is None else torch.zeros(self.time, *t.size(), device=t.device)

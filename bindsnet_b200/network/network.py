@@ -308,7 +308,7 @@ class Network(torch.nn.Module):
             i = {k: (v[t] if v.dim() == 2 else v) for k, v in injects.items()}
             net, keep = _plan.build_net(self, B, e, c, u, i, {})
             opts = _abi.SnnRunOpts()
-            opts.T, opts.B, opts.normalize = 1, B, int(normalize and t == T - 1)
+            opts.T, opts.B, opts.normalize = 1, B, 0     # the end-of-run normalize follows the last record (below)
             opts.tier = int(getattr(self, "force_tier", 0))
             opts.seed, opts.step_offset = seed & 0xFFFFFFFF, step_offset + t
             opts.one_step = int(getattr(self, "_one_step", False))
@@ -317,6 +317,9 @@ class Network(torch.nn.Module):
                 if isinstance(m, SpikeCounter) and t == 0:
                     m._begin_window(B, self._device())
                 m.record()
+        if normalize:                                     # network.py:463-465: after the last step's monitors
+            for c in self.connections.values():
+                c.normalize()
 
     # -- scripted tier: user-defined populations / rules / connections -------------------------------
     def _scripted_required(self) -> bool:

@@ -58,3 +58,24 @@ def test_canned_models_on_the_kernels_bit_exact_vs_oracle(which):
     assert int(b[1]["L/Y/count"].sum()) > 10
     helpers.assert_bit_identical(a[0], b[0], f"{which} state")
     helpers.assert_bit_identical(a[1], b[1], f"{which} spike counts")
+
+
+def test_network_monitor_on_the_kernels_bit_exact_vs_oracle():
+    """NetworkMonitor makes the run step-wise (one-step windows, the end-of-run normalize as a single operator after
+    the last record): recordings on the device equal the oracle's."""
+    import torch
+
+    import test_network_monitor as t
+    from oracle.oracle import OracleBackend
+
+    ns = cases.namespace("b200")
+    net, x = t._net(ns)
+    net.to("cuda")
+    mon = ns.monitors.NetworkMonitor(net)
+    net.add_monitor(mon, "all")
+    net.run(inputs={"X": x.cuda()}, time=t.T)
+    net.check_errors()
+    ref = t._record(ns, None, OracleBackend)
+    for key in ref.get():
+        for v in ref.get()[key]:
+            assert torch.equal(mon.get()[key][v].cpu(), ref.get()[key][v]), (key, v)
