@@ -129,6 +129,21 @@ class Network(torch.nn.Module):
                 out[k] = out[k].get(key, None)
         return out
 
+    def _get_inputs(self, layers=None) -> Dict[str, torch.Tensor]:
+        """What every layer (or the named ones) receives from the connections ending in it, given the sources'
+        current spikes: the sum of ``compute`` over those connections in insertion order (network.py:211-250).
+        Inside a window the kernels do this themselves (the gather phase); this host form — one single-operator
+        launch per connection — serves the scripted tier and callers that step a network by hand."""
+        B = self.batch_size
+        cur = {}
+        for (src, tgt), conn in self.connections.items():
+            if layers is not None and tgt not in layers:
+                continue
+            out = conn.compute(self.layers[src].s)
+            out = out.view(B, *self.layers[tgt].shape).float()
+            cur[tgt] = cur[tgt] + out if tgt in cur else out
+        return cur
+
     def _device(self) -> torch.device:
         return _plan.network_device(self)
 
@@ -352,22 +367,13 @@ class Network(torch.nn.Module):
         injects_v, connection updates, monitors, end-of-run normalize."""
         B = self.batch_size
         dev = self._device()
-
-        def get_inputs(only=None):
-            cur = {}
-            for (src, tgt), conn in self.connections.items():                 # network.py:225-248
-                if only is not None and tgt not in only:
-                    continue
-                out = conn.compute(self.layers[src].s)
-                out = out.view(B, *self.layers[tgt].shape).float()
-                cur[tgt] = cur[tgt] + out if tgt in cur else out
-            return cur
+        get_inputs = self._get_inputs
 
         for t in range(T):
             current = {} if one_step else get_inputs()
             for lname, layer in self.layers.items():                          # network.py:386-413
                 if one_step:
-                    current.update(get_inputs(only=[lname]))
+                    current.update(get_inputs([lname]))
                 e = ext.get(lname)
                 if e is not None:
                     x_ext = e[t].view(B, *layer.shape)

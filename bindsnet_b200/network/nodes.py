@@ -157,7 +157,8 @@ class Nodes(torch.nn.Module):
         if self.kind is None:
             raise NotImplementedError(
                 f"{type(self).__name__} has no CUDA implementation in bindsnet_b200 "
-                "(supported: Input, LIFNodes, DiehlAndCookNodes)"
+                "(built in: Input, McCullochPitts, IFNodes, LIFNodes, BoostedLIFNodes, CurrentLIFNodes, AdaptiveLIFNodes, "
+                "DiehlAndCookNodes; a subclass with its own forward() runs on the scripted tier)"
             )
         d.kind = self.kind
         d.n = self.n

@@ -87,3 +87,32 @@ def test_network_monitor_on_the_emulated_kernel_bit_exact_vs_oracle(tmp_path):
     assert a.get()["Y"]["s"].numel() == 0
     rolling = ns.monitors.NetworkMonitor(a.network, layers=["Y"], connections=[], state_vars=("s", "theta"), time=5)
     assert list(rolling.get()) == ["Y"] and list(rolling.get()["Y"]) == ["s"] and rolling.get()["Y"]["s"].shape == (5, B, 12)
+
+
+@pytest.mark.skipif(REF is None, reason="live reference not available")
+def test_get_inputs_matches_the_live_reference():
+    """``Network._get_inputs`` (network.py:211-250) as a host call: per-target sums of ``compute`` over the connections."""
+    from oracle.oracle import OracleBackend
+
+    def build(ns):
+        net, _ = _net(ns)
+        g = torch.Generator().manual_seed(5)
+        Z = ns.nodes.LIFNodes(n=12, traces=True)
+        net.add_layer(Z, "Z")
+        net.add_connection(ns.topology.Connection(source=Z, target=net.layers["Y"], w=torch.rand(12, 12, generator=g) - 0.5,
+                                                  b=0.1 * torch.rand(12, generator=g)), "Z", "Y")
+        net.add_connection(ns.topology.Connection(source=net.layers["Y"], target=Z, w=torch.rand(12, 12, generator=g)), "Y", "Z")
+        for name, p in (("X", 0.3), ("Y", 0.4), ("Z", 0.5)):
+            net.layers[name].s = torch.bernoulli(p * torch.ones(B, net.layers[name].n), generator=g).bool()
+        return net
+
+    ref = build(REF)
+    a = ref._get_inputs()
+    ours = build(cases.namespace("b200"))
+    with OracleBackend():
+        b = ours._get_inputs()
+        only = ours._get_inputs(["Z"])
+    assert sorted(a) == sorted(b) == ["Y", "Z"] and list(only) == ["Z"]
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), k
+    assert torch.equal(only["Z"], b["Z"]) and float(a["Y"].abs().sum()) > 0
