@@ -1,5 +1,7 @@
-"""Spike-train encoders — own restatement of the two encoders the hot path's callers use
-(reference: bindsnet/encoding/encodings.py ``bernoulli`` :50-96, ``poisson`` :99-156).  They
+"""Spike-train encoders — own restatement of the encoders the hot path's callers use
+(reference: bindsnet/encoding/encodings.py ``bernoulli`` :50-96, ``poisson`` :99-156 — the two with kernels of their
+own — and the deterministic ``single`` :6-33, ``repeat`` :36-47, ``rank_order`` :159-191 as device-resident tensor
+code; ``encoders.py``'s callable wrappers).  They
 produce the ``[time, *shape]`` uint8 tensors ``Network.run`` consumes; bench.py uses
 ``poisson`` to synthesise the metric's 28x28 input.
 
@@ -38,6 +40,13 @@ def poisson(datum: torch.Tensor, time: int, dt: float = 1.0, device="cpu", **kwa
     """Spike trains whose inter-spike intervals are Poisson(1000 / (rate * dt)) distributed
     steps, zero intervals bumped to one (reference semantics: encodings.py:99-156; ``datum``
     is the firing rate in Hz)."""
+    if kwargs.get("approx", False):
+        # encodings.py:130-137: |N(0,1)| ** ((rate * 0.11 + 5) / 50) < 0.6, torch's generator on the datum's device
+        dev = datum.device if datum.is_cuda else torch.device(device)
+        steps = int(time / dt)
+        x = torch.randn((steps, datum.numel()), device=dev).abs()
+        x = torch.pow(x, (datum.flatten().to(dev) * 0.11 + 5) / 50)
+        return (x < 0.6).view(steps, *datum.shape).byte()
     if datum.is_cuda:
         return _poisson_cuda(datum, int(time / dt), dt, kwargs.get("seed"))
     assert (datum >= 0).all(), "Inputs must be non-negative"
@@ -80,3 +89,98 @@ def _bernoulli_cuda(datum: torch.Tensor, steps: int, max_prob: float, seed=None)
     out = torch.empty((steps,) + tuple(datum.shape), dtype=torch.uint8, device=datum.device)
     _backend.encode_bernoulli(p, steps, _seed(seed), out)
     return out
+
+
+def single(datum: torch.Tensor, time: int, dt: float = 1.0, sparsity: float = 0.5, device="cpu", **kwargs) -> torch.Tensor:
+    """One spike at the first step for every feature above the ``1 - sparsity`` quantile, silence afterwards
+    (reference semantics: encodings.py:6-33).  Deterministic; computed where ``datum`` lives (CUDA tensors stay on
+    the device), else on ``device``."""
+    steps = int(time / dt)
+    dev = datum.device if datum.is_cuda else torch.device(device)
+    d = datum.detach().to(dev)
+    s = torch.zeros((steps, *d.shape), dtype=torch.uint8, device=dev)
+    s[0] = (d > torch.quantile(d, 1 - sparsity)).to(torch.uint8)
+    return s
+
+
+def repeat(datum: torch.Tensor, time: int, dt: float = 1.0, **kwargs) -> torch.Tensor:
+    """``datum`` at every one of the ``int(time / dt)`` steps (encodings.py:36-47)."""
+    steps = int(time / dt)
+    return datum.repeat([steps, *([1] * datum.dim())])
+
+
+def rank_order(datum: torch.Tensor, time: int, dt: float = 1.0, device="cpu", **kwargs) -> torch.Tensor:
+    """At most one spike per feature, the stronger the earlier: feature ``i`` fires at step
+    ``ceil(steps * (max / x_i) / max_j(max / x_j)) - 1`` when that lies inside the window; zero-valued features and those
+    landing on the last step stay silent (reference semantics: encodings.py:159-191, same float32 operations in the
+    same order, the per-feature loop replaced by one scatter).  Unlike the reference the caller's tensor is not
+    normalised in place."""
+    assert (datum >= 0).all(), "Inputs must be non-negative"
+    shape, size = datum.shape, datum.numel()
+    dev = datum.device if datum.is_cuda else torch.device(device)
+    d = datum.detach().flatten().to(dev).clone()
+    steps = int(time / dt)
+    d /= d.max()
+    times = torch.zeros(size, device=dev)
+    live = d != 0
+    times[live] = 1 / d[live]
+    times *= steps / times.max()
+    times = torch.ceil(times).long()
+    fires = (times > 0) & (times < steps)
+    spikes = torch.zeros(steps, size, dtype=torch.uint8, device=dev)
+    spikes[times[fires] - 1, torch.arange(size, device=dev)[fires]] = 1
+    return spikes.reshape(steps, *shape)
+
+
+class Encoder:
+    """Callable that applies one of the encodings above with fixed arguments (reference: encoders.py:4-18)."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        self.enc_args = args
+        self.enc_kwargs = kwargs
+
+    def __call__(self, img):
+        return self.enc(img, *self.enc_args, **self.enc_kwargs)
+
+
+class NullEncoder(Encoder):
+    """Hands the datum through unchanged (encoders.py:21-34)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def __call__(self, img):
+        return img
+
+
+def _encoder(name: str, fn, where: str, **defaults):
+    def __init__(self, time: int, dt: float = 1.0, **kwargs):
+        Encoder.__init__(self, time, dt=dt, **{**defaults, **kwargs})
+        self.enc = fn
+
+    return type(name, (Encoder,), {"__init__": __init__, "__doc__": f"``{fn.__name__}`` with fixed arguments (reference: {where})."})
+
+
+SingleEncoder = _encoder("SingleEncoder", single, "encoders.py:37-51", sparsity=0.5)
+RepeatEncoder = _encoder("RepeatEncoder", repeat, "encoders.py:54-66")
+BernoulliEncoder = _encoder("BernoulliEncoder", bernoulli, "encoders.py:69-85")
+PoissonEncoder = _encoder("PoissonEncoder", poisson, "encoders.py:88-102", approx=False)
+RankOrderEncoder = _encoder("RankOrderEncoder", rank_order, "encoders.py:105-117")
+
+
+def _loader(fn, where: str, pass_max_prob: bool = False):
+    def loader(data, time=None, dt: float = 1.0, **kwargs):
+        for i in range(len(data)):
+            if pass_max_prob:   # loaders.py:31: the reference reads ``max_prob`` from the ``dt`` keyword (always 1.0)
+                yield fn(datum=data[i], time=time, dt=dt, max_prob=kwargs.get("dt", 1.0))
+            else:
+                yield fn(datum=data[i], time=time, dt=dt)
+
+    loader.__name__ = f"{fn.__name__}_loader"
+    loader.__doc__ = f"Lazily encodes ``data[i]`` with ``{fn.__name__}``, one item per ``next`` (reference: {where})."
+    return loader
+
+
+bernoulli_loader = _loader(bernoulli, "loaders.py:8-33", pass_max_prob=True)
+poisson_loader = _loader(poisson, "loaders.py:36-55")
+rank_order_loader = _loader(rank_order, "loaders.py:58-77")
