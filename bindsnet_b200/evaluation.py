@@ -81,3 +81,61 @@ def all_activity(spikes: torch.Tensor, assignments: torch.Tensor, n_labels: int)
 def proportion_weighting(spikes: torch.Tensor, assignments: torch.Tensor, proportions: torch.Tensor, n_labels: int) -> torch.Tensor:
     """The same, every neuron weighted by its class proportion (evaluation.py:139-180)."""
     return _predict(spikes, assignments, proportions, n_labels)
+
+
+def _steps_with_spikes(activity: torch.Tensor):
+    """Per step that has spikes, the firing neurons in ascending order — one ``nonzero`` (and one device → host copy)
+    per example instead of one per step."""
+    T = activity.shape[0]
+    idx = torch.nonzero(activity.reshape(T, -1)).cpu()           # row-major: by step, then by neuron
+    steps = {}
+    for t, j in idx.tolist():
+        steps.setdefault(t, []).append(j)
+    return [steps[t] for t in sorted(steps)]
+
+
+def ngram(spikes: torch.Tensor, ngram_scores, n_labels: int, n: int) -> torch.Tensor:
+    """Class per example from the scores of the length-``n`` runs in its firing order (evaluation.py:183-217):
+    neurons are read step by step, ascending within a step; like the reference, the last ``n``-gram of an example is
+    not scored (its loop stops at ``len - n``)."""
+    out = []
+    for activity in spikes:
+        order = [j for step in _steps_with_spikes(activity) for j in step]
+        score = torch.zeros(n_labels, device=spikes.device)
+        for k in range(len(order) - n):
+            hit = ngram_scores.get(tuple(order[k:k + n]))
+            if hit is not None:
+                score += hit
+        out.append(int(torch.argmax(score)))
+    return torch.tensor(out, device=spikes.device).long()
+
+
+def update_ngram_scores(spikes: torch.Tensor, labels: torch.Tensor, n_labels: int, n: int, ngram_scores):
+    """Adds, for every ``n`` consecutive steps-with-spikes of every example, one count of the example's label to each
+    sequence that takes one firing neuron from each of those steps (evaluation.py:220-258).  ``ngram_scores`` is
+    updated in place and returned."""
+    from itertools import product
+
+    for i, activity in enumerate(spikes):
+        steps = _steps_with_spikes(activity)
+        label = int(labels[i])
+        for start in range(len(steps) - n + 1):
+            for seq in product(*steps[start:start + n]):
+                if seq not in ngram_scores:
+                    ngram_scores[seq] = torch.zeros(n_labels, device=spikes.device)
+                ngram_scores[seq][label] += 1
+    return ngram_scores
+
+
+def logreg_fit(spikes: torch.Tensor, labels: torch.Tensor, logreg):
+    """(Re)fits a scikit-learn ``LogisticRegression`` on time-summed spikes (evaluation.py:64-79); device tensors are
+    brought to the host, where scikit-learn works."""
+    logreg.fit(spikes.detach().cpu(), labels.detach().cpu())
+    return logreg
+
+
+def logreg_predict(spikes: torch.Tensor, logreg) -> torch.Tensor:
+    """Classes from a fitted model, ``-1`` for every example while it is unfitted (evaluation.py:82-96)."""
+    if getattr(logreg, "coef_", None) is None:
+        return -1 * torch.ones(spikes.size(0)).long()
+    return torch.Tensor(logreg.predict(spikes.detach().cpu())).long()
