@@ -24,21 +24,11 @@ from ..network.topology_features import Weight
 class TwoLayerNetwork(Network):
     """``Input -> LIFNodes`` with a PostPre ``Connection`` (reference: models.py:21-91)."""
 
-    def __init__(
-        self,
-        n_inpt: int,
-        n_neurons: int = 100,
-        dt: float = 1.0,
-        wmin: float = 0.0,
-        wmax: float = 1.0,
-        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
-        reduction: Optional[callable] = None,
-        norm: float = 78.4,
-    ) -> None:
+    def __init__(self, n_inpt: int, n_neurons: int = 100, dt: float = 1.0, wmin: float = 0.0, wmax: float = 1.0,
+                 nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2), reduction: Optional[callable] = None,
+                 norm: float = 78.4) -> None:
         super().__init__(dt=dt)
-        self.n_inpt = n_inpt
-        self.n_neurons = n_neurons
-        self.dt = dt
+        self.n_inpt, self.n_neurons, self.dt = n_inpt, n_neurons, dt
         self.add_layer(Input(n=self.n_inpt, traces=True, tc_trace=20.0), name="X")
         self.add_layer(
             LIFNodes(n=self.n_neurons, traces=True, rest=-65.0, reset=-65.0, thresh=-52.0, refrac=5,
@@ -57,34 +47,14 @@ class DiehlAndCook2015(Network):
     """Diehl & Cook (2015): ``X -> Ae <-> Ai`` with MCC connections (reference:
     models.py:94-244).  This is the graph the fused CUDA window kernel recognises."""
 
-    def __init__(
-        self,
-        n_inpt: int,
-        device: str = "cpu",
-        batch_size: int = None,
-        sparse: bool = False,
-        n_neurons: int = 100,
-        exc: float = 22.5,
-        inh: float = 17.5,
-        dt: float = 1.0,
-        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
-        reduction: Optional[callable] = None,
-        wmin: float = 0.0,
-        wmax: float = 1.0,
-        w_dtype: torch.dtype = torch.float32,
-        norm: float = 78.4,
-        theta_plus: float = 0.05,
-        tc_theta_decay: float = 1e7,
-        inpt_shape: Optional[Iterable[int]] = None,
-        inh_thresh: float = -40.0,
-        exc_thresh: float = -52.0,
-    ) -> None:
+    def __init__(self, n_inpt: int, device: str = "cpu", batch_size: int = None, sparse: bool = False,
+                 n_neurons: int = 100, exc: float = 22.5, inh: float = 17.5, dt: float = 1.0,
+                 nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2), reduction: Optional[callable] = None,
+                 wmin: float = 0.0, wmax: float = 1.0, w_dtype: torch.dtype = torch.float32, norm: float = 78.4,
+                 theta_plus: float = 0.05, tc_theta_decay: float = 1e7, inpt_shape: Optional[Iterable[int]] = None,
+                 inh_thresh: float = -40.0, exc_thresh: float = -52.0) -> None:
         super().__init__(dt=dt)
-        self.n_inpt = n_inpt
-        self.inpt_shape = inpt_shape
-        self.n_neurons = n_neurons
-        self.exc = exc
-        self.inh = inh
+        self.n_inpt, self.inpt_shape, self.n_neurons, self.exc, self.inh = n_inpt, inpt_shape, n_neurons, exc, inh
         self.dt = dt
 
         input_layer = Input(n=self.n_inpt, shape=self.inpt_shape, traces=True, tc_trace=20.0)
@@ -130,28 +100,13 @@ class DiehlAndCook2015v2(Network):
     """Variant with recurrent lateral inhibition instead of an inhibitory layer, built from
     classic ``Connection`` + ``learning.PostPre`` (reference: models.py:247-346)."""
 
-    def __init__(
-        self,
-        n_inpt: int,
-        n_neurons: int = 100,
-        inh: float = 17.5,
-        dt: float = 1.0,
-        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
-        reduction: Optional[callable] = None,
-        wmin: Optional[float] = 0.0,
-        wmax: Optional[float] = 1.0,
-        norm: float = 78.4,
-        theta_plus: float = 0.05,
-        tc_theta_decay: float = 1e7,
-        inpt_shape: Optional[Iterable[int]] = None,
-        exc_thresh: float = -52.0,
-    ) -> None:
+    def __init__(self, n_inpt: int, n_neurons: int = 100, inh: float = 17.5, dt: float = 1.0,
+                 nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2), reduction: Optional[callable] = None,
+                 wmin: Optional[float] = 0.0, wmax: Optional[float] = 1.0, norm: float = 78.4,
+                 theta_plus: float = 0.05, tc_theta_decay: float = 1e7, inpt_shape: Optional[Iterable[int]] = None,
+                 exc_thresh: float = -52.0) -> None:
         super().__init__(dt=dt)
-        self.n_inpt = n_inpt
-        self.inpt_shape = inpt_shape
-        self.n_neurons = n_neurons
-        self.inh = inh
-        self.dt = dt
+        self.n_inpt, self.inpt_shape, self.n_neurons, self.inh, self.dt = n_inpt, inpt_shape, n_neurons, inh, dt
 
         self.add_layer(Input(n=self.n_inpt, shape=self.inpt_shape, traces=True, tc_trace=20.0), name="X")
         self.add_layer(
@@ -181,31 +136,15 @@ class IncreasingInhibitionNetwork(Network):
     divided by its maximum, times ``max_inhib`` plus ``start_inhib`` — on the diagonal too, and with a positive
     sign (:439-449)."""
 
-    def __init__(
-        self,
-        n_input: int,
-        n_neurons: int = 100,
-        start_inhib: float = 1.0,
-        max_inhib: float = 100.0,
-        dt: float = 1.0,
-        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
-        reduction: Optional[callable] = None,
-        wmin: float = 0.0,
-        wmax: float = 1.0,
-        norm: float = 78.4,
-        theta_plus: float = 0.05,
-        tc_theta_decay: float = 1e7,
-        inpt_shape: Optional[Iterable[int]] = None,
-        exc_thresh: float = -52.0,
-    ) -> None:
+    def __init__(self, n_input: int, n_neurons: int = 100, start_inhib: float = 1.0, max_inhib: float = 100.0,
+                 dt: float = 1.0, nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
+                 reduction: Optional[callable] = None, wmin: float = 0.0, wmax: float = 1.0, norm: float = 78.4,
+                 theta_plus: float = 0.05, tc_theta_decay: float = 1e7, inpt_shape: Optional[Iterable[int]] = None,
+                 exc_thresh: float = -52.0) -> None:
         super().__init__(dt=dt)
-        self.n_input = n_input
-        self.n_neurons = n_neurons
+        self.n_input, self.n_neurons = n_input, n_neurons
         self.n_sqrt = int(np.sqrt(n_neurons))
-        self.start_inhib = start_inhib
-        self.max_inhib = max_inhib
-        self.dt = dt
-        self.inpt_shape = inpt_shape
+        self.start_inhib, self.max_inhib, self.dt, self.inpt_shape = start_inhib, max_inhib, dt, inpt_shape
 
         self.add_layer(Input(n=self.n_input, shape=self.inpt_shape, traces=True, tc_trace=20.0), name="X")
         self.add_layer(
@@ -236,38 +175,16 @@ class LocallyConnectedNetwork(Network):
     """``Input -> DiehlAndCookNodes`` through a ``LocalConnection`` with PostPre, the output neurons that share a
     receptive field inhibiting each other through a recurrent ``Connection`` (reference: models.py:457-584)."""
 
-    def __init__(
-        self,
-        n_inpt: int,
-        input_shape,
-        kernel_size,
-        stride,
-        n_filters: int,
-        inh: float = 25.0,
-        dt: float = 1.0,
-        nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
-        reduction: Optional[callable] = None,
-        theta_plus: float = 0.05,
-        tc_theta_decay: float = 1e7,
-        wmin: float = 0.0,
-        wmax: float = 1.0,
-        norm: Optional[float] = 0.2,
-        exc_thresh: float = -52.0,
-    ) -> None:
+    def __init__(self, n_inpt: int, input_shape, kernel_size, stride, n_filters: int, inh: float = 25.0,
+                 dt: float = 1.0, nu: Optional[Union[float, Sequence[float]]] = (1e-4, 1e-2),
+                 reduction: Optional[callable] = None, theta_plus: float = 0.05, tc_theta_decay: float = 1e7,
+                 wmin: float = 0.0, wmax: float = 1.0, norm: Optional[float] = 0.2,
+                 exc_thresh: float = -52.0) -> None:
         super().__init__(dt=dt)
         kernel_size, stride = _pair(kernel_size), _pair(stride)
-        self.n_inpt = n_inpt
-        self.input_shape = input_shape
-        self.kernel_size = kernel_size
-        self.stride = stride
-        self.n_filters = n_filters
-        self.inh = inh
-        self.dt = dt
-        self.theta_plus = theta_plus
-        self.tc_theta_decay = tc_theta_decay
-        self.wmin = wmin
-        self.wmax = wmax
-        self.norm = norm
+        self.n_inpt, self.input_shape, self.kernel_size, self.stride = n_inpt, input_shape, kernel_size, stride
+        self.n_filters, self.inh, self.dt, self.theta_plus = n_filters, inh, dt, theta_plus
+        self.tc_theta_decay, self.wmin, self.wmax, self.norm = tc_theta_decay, wmin, wmax, norm
 
         if kernel_size == input_shape:                                           # models.py:530-536
             conv_size = (1, 1)
