@@ -62,10 +62,9 @@ class ShardedWindowRunner:
                 d.wmin, d.wmax = float(conn.wmin), float(conn.wmax)
                 d.has_clamp = int(code >= _abi.SNN_RULE_POSTPRE and (math.isfinite(d.wmin) or math.isfinite(d.wmax)))
             if d.rule >= _abi.SNN_RULE_POSTPRE or d.has_norm:
-                if isinstance(conn, Conv2dConnection):
-                    # [Cout,Cin,kh,kw] weights normalise per filter (topology.py:824-837); the combine kernel is
-                    # written for [n_src,n_tgt] matrices with column normalisation
-                    raise NotImplementedError("ShardedWindowRunner: learned Conv2dConnection weights are not combined across ranks yet")
+                # [Cout,Cin,kh,kw] weights normalise per filter (topology.py:824-837), the combine kernel per column of an
+                # [n_src,n_tgt] matrix: for them it applies sum + clamp only, the connection's own normalize follows
+                d._conv = isinstance(conn, Conv2dConnection)
                 out.append((conn, d))
         return out
 
@@ -120,6 +119,13 @@ class ShardedWindowRunner:
         k = 0
         for conn, d in learned:
             t, v0, o = views[k]; k += 1
+            if getattr(d, "_conv", False):
+                rows = conn.w.shape[0]
+                _backend.delta_apply(conn.w.detach().view(rows, -1), v0.view(rows, -1), self._flat[o:o + t.numel()].view(rows, -1),
+                                     d.has_clamp, d.wmin, d.wmax, 0, 1, 0.0)
+                if d.has_norm:
+                    conn.normalize()
+                continue
             _backend.delta_apply(conn.w.detach(), v0, self._flat[o:o + t.numel()].view_as(t), d.has_clamp, d.wmin,
                                  d.wmax, d.has_norm, d.norm_abs, d.norm)
         for th in thetas:

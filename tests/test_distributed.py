@@ -110,3 +110,74 @@ def test_two_rank_window_combine_matches_replica_oracle(tmp_path, emulated):
             w, th = wn, th + (dths[0] + dths[1])
     assert np.array_equal(r0["w"].numpy(), w.numpy())
     assert np.array_equal(r0["theta"].numpy(), th.numpy())
+
+
+# ---- learned Conv2dConnection weights (config 4's graph in small): sum + clamp by the combine kernel on the flattened filters, then the
+# connection's own per-filter normalize -------------------------------------------------------------------------------------------------
+def _conv_make(B):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+
+    ns = cases.namespace("b200")
+    return cases._conv_net(ns, B, 40, (2, 9, 9), 3, 3, 2, 1, ns.learning.MSTDP, (131, 132), n_out=5, norm=1.5)
+
+
+def _conv_inputs():
+    g = torch.Generator().manual_seed(77)
+    return torch.bernoulli(0.15 * torch.ones(40, 8, 2, 9, 9), generator=g).byte()
+
+
+def _conv_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bindsnet_b200.distributed import ShardedWindowRunner
+    from oracle.oracle import OracleBackend
+
+    _patch_cpu_combine()
+    shard = _conv_inputs()[:, rank * 4:(rank + 1) * 4]
+    net = _conv_make(4)
+    with OracleBackend():
+        runner = ShardedWindowRunner(net)
+        for window in range(2):
+            if window:
+                net.reset_state_variables()
+            runner.run({"X": shard}, time=40, reward=0.8 + 0.3 * window)
+    torch.save({f"{s}->{t}": c.w.detach().clone() for (s, t), c in net.connections.items()}, os.path.join(out, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_combine_of_learned_conv_weights_matches_replica_oracle(tmp_path):
+    port = 31500 + (os.getpid() % 1000)
+    mp.spawn(_conv_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt"); r1 = torch.load(tmp_path / "rank1.pt")
+    assert all(torch.equal(r0[k], r1[k]) for k in r0), "ranks diverged"
+
+    from oracle.oracle import OracleBackend
+
+    x = _conv_inputs()
+    nets = [_conv_make(4), _conv_make(4)]
+    keys = list(nets[0].connections)
+    w = {k: nets[0].connections[k].w.detach().clone() for k in keys}
+    with OracleBackend():
+        for window in range(2):
+            sums = {k: torch.zeros_like(w[k]) for k in keys}
+            for r, net in enumerate(nets):
+                with torch.no_grad():
+                    for k in keys:
+                        net.connections[k].w.copy_(w[k])
+                if window:
+                    net.reset_state_variables()
+                net.run({"X": x[:, r * 4:(r + 1) * 4]}, time=40, reward=0.8 + 0.3 * window, b200_normalize=False)
+                for k in keys:
+                    sums[k] += net.connections[k].w.detach() - w[k]
+            for k in keys:
+                c = nets[0].connections[k]
+                with torch.no_grad():
+                    c.w.copy_(torch.clamp(w[k] + sums[k], float(c.wmin), float(c.wmax)))
+                if c.norm is not None:
+                    c.normalize()
+                w[k] = c.w.detach().clone()
+    for (s, t) in keys:
+        assert np.array_equal(r0[f"{s}->{t}"].numpy(), w[(s, t)].numpy()), (s, t)
+    assert not torch.equal(w[keys[0]], _conv_make(4).connections[keys[0]].w)      # something was learnt
