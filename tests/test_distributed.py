@@ -127,17 +127,23 @@ def _conv_inputs():
     return torch.bernoulli(0.15 * torch.ones(40, 8, 2, 9, 9), generator=g).byte()
 
 
-def _conv_worker(rank, world, port, out):
+def _conv_worker(rank, world, port, out, emulated=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from bindsnet_b200.distributed import ShardedWindowRunner
     from oracle.oracle import OracleBackend
 
-    _patch_cpu_combine()
+    if emulated:   # the generic window kernel, delta_prepare / delta_apply and the conv normalize operator from their CUDA sources
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import emu
+        Backend = emu.EmuBackend
+    else:
+        _patch_cpu_combine()
+        Backend = OracleBackend
     shard = _conv_inputs()[:, rank * 4:(rank + 1) * 4]
     net = _conv_make(4)
-    with OracleBackend():
+    with Backend():
         runner = ShardedWindowRunner(net)
         for window in range(2):
             if window:
@@ -147,9 +153,10 @@ def _conv_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_combine_of_learned_conv_weights_matches_replica_oracle(tmp_path):
-    port = 31500 + (os.getpid() % 1000)
-    mp.spawn(_conv_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("emulated", [False, True])
+def test_two_rank_combine_of_learned_conv_weights_matches_replica_oracle(tmp_path, emulated):
+    port = 31500 + (os.getpid() % 1000) + (1000 if emulated else 0)
+    mp.spawn(_conv_worker, args=(2, port, str(tmp_path), emulated), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "rank0.pt"); r1 = torch.load(tmp_path / "rank1.pt")
     assert all(torch.equal(r0[k], r1[k]) for k in r0), "ranks diverged"
 
