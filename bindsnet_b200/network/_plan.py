@@ -202,9 +202,30 @@ def _pair_net(conn, B: int) -> "_abi.SnnNet":
     for k, layer in enumerate((conn.source, conn.target)):
         if layer.dt is None:
             layer.compute_decays(dt)
-        fill_layer(net.layers[k], layer, f"layer{k}", B)
+        if layer.kind is None:
+            _fill_endpoint(net.layers[k], layer, f"layer{k}", B)
+        else:
+            fill_layer(net.layers[k], layer, f"layer{k}", B)
     fill_conn(net.conns[0], conn, 0, 1, float(dt), B)
     return net
+
+
+def _fill_endpoint(d: "_abi.SnnLayer", layer, name: str, B: int) -> None:
+    """A USER-DEFINED population (no ``kind``: its ``forward`` is torch code, scripted tier) as the source or target of a
+    built-in connection's single-operator update: the rule reads the population's current spikes and traces and nothing
+    else (snn_b200_conn_update), so that is all the descriptor carries."""
+    if layer.s.dtype not in (torch.bool, torch.uint8) or layer.s.numel() != B * layer.n:
+        raise TypeError(f"{name}.s must be a bool / uint8 tensor of {B} x {layer.n} spikes, got {layer.s.dtype} {tuple(layer.s.shape)}")
+    if not layer.s.is_contiguous():
+        layer.s = layer.s.contiguous()
+    d.kind, d.n = _abi.SNN_NODE_INPUT, layer.n
+    d.traces = int(bool(layer.traces))
+    d.traces_additive = int(bool(layer.traces_additive))
+    d.learning = int(bool(getattr(layer, "learning", True)))
+    d.dt = float(layer.dt) if layer.dt is not None else 1.0
+    d.s = _ptr(_as_u8(layer.s))
+    if layer.traces:
+        d.x = _ptr(_state(layer.x, "x", name))
 
 
 def update_single_connection(conn) -> None:

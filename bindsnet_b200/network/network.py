@@ -246,7 +246,12 @@ class Network(torch.nn.Module):
         unclamps = {k: self._stage_mask(k, v, T, dev, False) for k, v in (unclamp or {}).items() if v is not None}
         injects = {k: self._stage_mask(k, v, T, dev, True) for k, v in (injects_v or {}).items() if v is not None}
         if seed is None:
-            seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: torch.manual_seed governs it
+            # only a one_spike population consumes the tie-break stream; a network without one leaves torch's generator
+            # alone (as the reference does: its only draw on the path is DiehlAndCookNodes' multinomial, nodes.py:1097-1105)
+            if any(getattr(l, "one_spike", False) for l in self.layers.values()):
+                seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: torch.manual_seed governs it
+            else:
+                seed = 0
         self.last_one_spike_seed = seed
 
         if delta is not None and (self._scripted_required() or T <= 0):

@@ -580,4 +580,55 @@ class McCullochPitts(Nodes):
 
 IzhikevichNodes = _unsupported("IzhikevichNodes", "nodes.py:1147-1316")
 CSRMNodes = _unsupported("CSRMNodes", "nodes.py:1319-1552")
-SRM0Nodes = _unsupported("SRM0Nodes", "nodes.py:1555-1701")
+
+
+class SRM0Nodes(Nodes):
+    """Simplified spike-response neurons with escape noise (reference: nodes.py:1555-1701; forward :1642-1673):
+    leaky voltage, input scaled by ``eps_0`` outside the refractory period, a spike with probability
+    ``1 - exp(-rho_0 * exp((v - thresh) / d_thresh) * dt)`` per step.
+
+    The spike draw is ``torch.rand_like`` — torch's generator on the layer's device, as in the reference — so there is
+    no bit-reproducible kernel form to pin against an oracle: the class has no ``kind``, and a network that contains
+    it runs on the scripted tier (``Network._run_scripted``), this ``forward`` as device-resident torch operations in
+    the reference's order (so that one seed gives the reference's spikes on the CPU), everything built-in still on
+    its kernels."""
+
+    def __init__(self, n: Optional[int] = None, shape: Optional[Iterable[int]] = None, traces: bool = False,
+                 traces_additive: bool = False, tc_trace: Scalar = 20.0, trace_scale: Scalar = 1.0, sum_input: bool = False,
+                 thresh: Scalar = -50.0, rest: Scalar = -70.0, reset: Scalar = -70.0, refrac: Scalar = 5, tc_decay: Scalar = 10.0,
+                 lbound: float = None, eps_0: Scalar = 1.0, rho_0: Scalar = 1.0, d_thresh: Scalar = 5.0, **kwargs) -> None:
+        super().__init__(n=n, shape=shape, traces=traces, traces_additive=traces_additive, tc_trace=tc_trace,
+                         trace_scale=trace_scale, sum_input=sum_input)
+        for name, value in (("rest", rest), ("reset", reset), ("thresh", thresh), ("refrac", refrac), ("tc_decay", tc_decay),
+                            ("decay", tc_decay), ("eps_0", eps_0), ("rho_0", rho_0), ("d_thresh", d_thresh)):
+            self.register_buffer(name, torch.tensor(value))
+        self.register_buffer("v", torch.FloatTensor())
+        self.register_buffer("refrac_count", torch.FloatTensor())
+        self.lbound = lbound
+
+    def forward(self, x: torch.Tensor) -> None:
+        self.v = self.decay * (self.v - self.rest) + self.rest
+        self.v += (self.refrac_count <= 0).float() * self.eps_0 * x
+        self.rho = self.rho_0 * torch.exp((self.v - self.thresh) / self.d_thresh)      # stochastic intensity
+        self.s_prob = 1.0 - torch.exp(-self.rho * self.dt)
+        self.refrac_count -= self.dt
+        self.s = torch.rand_like(self.s_prob) < self.s_prob
+        self.refrac_count.masked_fill_(self.s, self.refrac)
+        self.v.masked_fill_(self.s, self.reset)
+        if self.lbound is not None:
+            self.v.masked_fill_(self.v < self.lbound, self.lbound)
+        super().forward(x)
+
+    def reset_state_variables(self) -> None:
+        super().reset_state_variables()
+        self.v.fill_(self.rest)
+        self.refrac_count.zero_()
+
+    def compute_decays(self, dt) -> None:
+        super().compute_decays(dt=dt)
+        self.decay = torch.exp(-self.dt / self.tc_decay)
+
+    def set_batch_size(self, batch_size) -> None:
+        super().set_batch_size(batch_size=batch_size)
+        self.v = self.rest * torch.ones(batch_size, *self.shape, device=self.v.device)
+        self.refrac_count = torch.zeros_like(self.v)

@@ -60,11 +60,12 @@ class MyPostPre(LearningRule):
         super().update()
 
 
-def _net(custom: bool, w0):
+def _net(custom: bool, w0, custom_rule=None):
+    custom_rule = custom if custom_rule is None else custom_rule
     net = Network(dt=1.0, batch_size=3)
     X = Input(n=50, traces=True)
     Y = (MyLIF if custom else LIFNodes)(n=30, traces=True, thresh=-57.0, refrac=2, tc_decay=60.0)
-    C = Connection(X, Y, w=w0.clone(), update_rule=MyPostPre if custom else PostPre, nu=(2e-3, 2e-2), reduction=torch.sum,
+    C = Connection(X, Y, w=w0.clone(), update_rule=MyPostPre if custom_rule else PostPre, nu=(2e-3, 2e-2), reduction=torch.sum,
                    wmin=0.0, wmax=1.0, norm=12.0)
     net.add_layer(X, "X"); net.add_layer(Y, "Y"); net.add_connection(C, "X", "Y")
     net.add_monitor(Monitor(Y, ["s", "v"], time=60), "Y")
@@ -87,3 +88,20 @@ def test_user_defined_nodes_and_rule_run_through_the_scripted_tier():
     wa, wb = a.connections[("X", "Y")].w, b.connections[("X", "Y")].w
     assert float((wa - wb).abs().max() / wb.abs().max()) < 1e-5
     assert torch.allclose(a.layers["Y"].x, b.layers["Y"].x, atol=1e-6)
+
+
+def test_user_defined_nodes_under_a_built_in_rule():
+    """A user's population as the target of a built-in connection with a built-in rule: the rule's single-operator
+    update reads the population's spikes and traces (bindsnet_b200/network/_plan.py:_fill_endpoint); the result is the
+    built-in network's, bit for bit (same kernels on both sides of the update)."""
+    g = torch.Generator().manual_seed(4)
+    w0 = 0.9 * torch.rand(50, 30, generator=g)
+    x = torch.bernoulli(0.15 * torch.ones(60, 3, 50), generator=g).byte()
+    a, b = _net(True, w0, custom_rule=False), _net(False, w0)
+    assert a._scripted_required()
+    with OracleBackend():
+        a.run({"X": x}, time=60)
+        b.run({"X": x}, time=60)
+    assert torch.equal(a.monitors["Y"].get("s"), b.monitors["Y"].get("s")) and int(b.monitors["Y"].get("s").sum()) > 20
+    wa, wb = a.connections[("X", "Y")].w, b.connections[("X", "Y")].w
+    assert float((wa - wb).abs().max() / wb.abs().max()) < 1e-5

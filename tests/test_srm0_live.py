@@ -1,0 +1,61 @@
+"""``SRM0Nodes`` (reference: nodes.py:1555-1701) on the scripted tier: with torch's generator seeded alike, a learning
+window of ``Input -> SRM0Nodes`` (PostPre, normalize) equals the live reference's — same spikes, voltages and weights
+within the north_star's tolerances (the built-in pieces run on the oracle backend here).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import helpers
+
+try:
+    REF = cases.namespace("reference")
+except Exception:  # pragma: no cover
+    REF = None
+
+pytestmark = pytest.mark.skipif(REF is None, reason="live reference not available")
+T, B = 80, 3
+
+
+def _net(ns, lbound=None):
+    g = torch.Generator().manual_seed(61)
+    net = ns.Network(dt=1.0, batch_size=B)
+    X = ns.nodes.Input(n=40, traces=True)
+    Y = ns.nodes.SRM0Nodes(n=15, traces=True, thresh=-55.0, rest=-70.0, reset=-72.0, refrac=3, tc_decay=12.0, eps_0=1.5,
+                           rho_0=0.8, d_thresh=4.0, lbound=lbound, sum_input=True)
+    net.add_layer(X, "X"); net.add_layer(Y, "Y")
+    net.add_connection(ns.topology.Connection(source=X, target=Y, w=2.5 * torch.rand(40, 15, generator=g), update_rule=ns.learning.PostPre,
+                                              nu=(1e-3, 1e-2), reduction=torch.sum, wmin=0.0, wmax=3.0, norm=40.0), "X", "Y")
+    x = torch.bernoulli(0.25 * torch.ones(T, B, 40), generator=g).byte()
+    return net, x
+
+
+@pytest.mark.parametrize("lbound", [None, -71.0])
+def test_srm0_window_matches_the_live_reference(lbound):
+    from oracle.oracle import OracleBackend
+
+    ref, x = _net(REF, lbound)
+    rm = REF.monitors.Monitor(ref.layers["Y"], ["s", "v"], time=T); ref.add_monitor(rm, "Y")
+    torch.manual_seed(2024)
+    ref.run(inputs={"X": x.clone()}, time=T)
+
+    ours, x2 = _net(cases.namespace("b200"), lbound)
+    assert ours._scripted_required()
+    om = cases.namespace("b200").monitors.Monitor(ours.layers["Y"], ["s", "v"], time=T); ours.add_monitor(om, "Y")
+    torch.manual_seed(2024)
+    with OracleBackend() as ob:
+        ours.run(inputs={"X": x2}, time=T)
+        assert ob.err == 0
+    assert torch.equal(rm.get("s"), om.get("s")) and int(rm.get("s").sum()) > 20
+    assert torch.allclose(rm.get("v"), om.get("v"), rtol=1e-5, atol=1e-4)
+    a, b = helpers.snapshot(ref), helpers.snapshot(ours)
+    assert a.keys() == b.keys()
+    for k in a:
+        if k.endswith("/s"):
+            assert np.array_equal(a[k], b[k]), k
+        else:
+            tol = (2e-6 + 1e-4 * np.abs(a[k])) if k.endswith("/w") else (1e-4 + 1e-5 * np.abs(a[k]))
+            assert not (np.abs(a[k].astype(np.float64) - b[k]) > tol).any(), f"{k} max |d| {np.abs(a[k] - b[k]).max():.3e}"
+    # reset_state_variables (nodes.py:1675-1682)
+    ours.reset_state_variables()
+    assert float(ours.layers["Y"].v.min()) == float(ours.layers["Y"].v.max()) == -70.0 and float(ours.layers["Y"].refrac_count.abs().sum()) == 0
