@@ -79,3 +79,30 @@ def test_network_monitor_on_the_kernels_bit_exact_vs_oracle():
     for key in ref.get():
         for v in ref.get()[key]:
             assert torch.equal(mon.get()[key][v].cpu(), ref.get()[key][v]), (key, v)
+
+
+def test_srm0_nodes_on_the_device():
+    """SRM0Nodes' spike draw is torch's CUDA generator (no oracle can follow it): the window must run on the device
+    through the scripted tier — built-in PostPre update and normalize on their kernels with the host population as
+    the target — and behave like the CPU run in distribution (rates within a wide band, weights inside their bounds,
+    columns normalised)."""
+    import torch
+
+    import test_srm0_live as t
+    from oracle.oracle import OracleBackend
+
+    ns = cases.namespace("b200")
+    net, x = t._net(ns)
+    net.to("cuda")
+    torch.manual_seed(7)
+    net.run(inputs={"X": x.cuda()}, time=t.T)
+    net.check_errors()
+    Y, w = net.layers["Y"], net.connections[("X", "Y")].w
+    assert Y.s.is_cuda and Y.v.is_cuda and w.is_cuda
+    cpu, x2 = t._net(ns)
+    torch.manual_seed(7)
+    with OracleBackend():
+        cpu.run(inputs={"X": x2}, time=t.T)
+    assert float(w.min()) >= 0.0 and float(w.max()) <= 3.0
+    assert torch.allclose(w.sum(0).cpu(), torch.full((15,), 40.0), rtol=1e-4)
+    assert float(Y.summed.sum()) > 0 and abs(float(Y.summed.mean()) / float(cpu.layers["Y"].summed.mean()) - 1.0) < 0.5
