@@ -280,4 +280,36 @@ def _unsupported(name: str, where: str):
     return _Unsupported
 
 
-Rmax = _unsupported("Rmax", "learning.py:2858-2960")
+class Rmax(LearningRule):
+    """Reward-maximisation rule for stochastic ``SRM0Nodes`` targets (reference: learning.py:2858-2960; update
+    :2921-2960): per synapse an eligibility trace that decays by ``1 - dt / tc_e_trace`` and gains
+    ``(s_post - p / (1 + tc_c / dt * p)) * x_pre`` each step (``p`` the target's spike probability of the step), and
+    ``w += nu[0] * reward * eligibility``.  Its target draws from torch's generator, so — like ``SRM0Nodes`` — the rule
+    has no kernel form: it is host torch code on the connection's device and the network runs on the scripted tier.
+    As in the reference the flattened views make it a batch-size-1 rule."""
+
+    rule_code = None
+
+    def __init__(self, connection, nu=None, reduction=None, weight_decay: float = 0.0, **kwargs) -> None:
+        super().__init__(connection=connection, nu=nu, reduction=reduction, weight_decay=weight_decay, **kwargs)
+        from ..network.nodes import SRM0Nodes
+        from ..network.topology import Connection
+
+        assert self.source.traces and self.source.traces_additive, "Pre-synaptic nodes must use additive spike traces."
+        assert isinstance(self.target, SRM0Nodes), "R-max needs stochastically firing neurons, use SRM0Nodes."
+        if not isinstance(connection, Connection):        # Connection and its subclass LocalConnection (learning.py:2905-2910)
+            raise NotImplementedError("This learning rule is not supported for this Connection type.")
+        self.tc_c = torch.tensor(kwargs.get("tc_c", 5.0))                 # 0: naive Hebbian ... inf: policy gradient
+        self.tc_e_trace = torch.tensor(kwargs.get("tc_e_trace", 25.0))
+
+    def update(self, **kwargs) -> None:
+        w, dt = self.connection.w, self.connection.dt
+        if not hasattr(self, "eligibility_trace"):
+            self.eligibility_trace = torch.zeros(*w.shape, device=w.device)
+        fired = self.target.s.view(-1).float()
+        p = self.target.s_prob.view(-1)
+        self.eligibility_trace *= 1 - dt / self.tc_e_trace
+        self.eligibility_trace += (fired - p / (1.0 + self.tc_c / dt * p)) * self.source.x.view(-1)[:, None]
+        with torch.no_grad():
+            w += self.nu[0] * kwargs["reward"] * self.eligibility_trace
+        super().update()

@@ -59,3 +59,38 @@ def test_srm0_window_matches_the_live_reference(lbound):
     # reset_state_variables (nodes.py:1675-1682)
     ours.reset_state_variables()
     assert float(ours.layers["Y"].v.min()) == float(ours.layers["Y"].v.max()) == -70.0 and float(ours.layers["Y"].refrac_count.abs().sum()) == 0
+
+
+def test_rmax_on_srm0_matches_the_live_reference():
+    """``learning.Rmax`` (learning.py:2858-2960): eligibility trace per synapse, reward-scaled update — batch size 1,
+    additive input traces, an SRM0 target; three windows with different rewards against the live reference."""
+    from oracle.oracle import OracleBackend
+
+    def build(ns):
+        g = torch.Generator().manual_seed(62)
+        net = ns.Network(dt=1.0, batch_size=1)
+        X = ns.nodes.Input(n=30, traces=True, traces_additive=True)
+        Y = ns.nodes.SRM0Nodes(n=10, traces=True, thresh=-56.0, refrac=2, tc_decay=15.0, rho_0=0.7, d_thresh=4.0)
+        net.add_layer(X, "X"); net.add_layer(Y, "Y")
+        net.add_connection(ns.topology.Connection(source=X, target=Y, w=2.0 * torch.rand(30, 10, generator=g), update_rule=ns.learning.Rmax,
+                                                  nu=2e-2, wmin=0.0, wmax=3.0, weight_decay=1e-3, tc_c=4.0, tc_e_trace=20.0), "X", "Y")
+        xs = [torch.bernoulli(0.3 * torch.ones(50, 1, 30), generator=g).byte() for _ in range(3)]
+        return net, xs
+
+    ref, xs = build(REF)
+    torch.manual_seed(99)
+    for r, x in zip((1.0, -0.5, 0.8), xs):
+        ref.run(inputs={"X": x.clone()}, time=50, reward=r)
+    ours, xs2 = build(cases.namespace("b200"))
+    assert ours._scripted_required()
+    torch.manual_seed(99)
+    with OracleBackend() as ob:
+        for r, x in zip((1.0, -0.5, 0.8), xs2):
+            ours.run(inputs={"X": x}, time=50, reward=r)
+        assert ob.err == 0
+    assert torch.equal(ref.layers["Y"].s, ours.layers["Y"].s)
+    assert torch.allclose(ref.layers["Y"].v, ours.layers["Y"].v, rtol=1e-5, atol=1e-4)
+    wa, wb = ref.connections[("X", "Y")].w.detach(), ours.connections[("X", "Y")].w.detach()
+    assert not ((wa - wb).abs() > 2e-6 + 1e-4 * wa.abs()).any(), float((wa - wb).abs().max())
+    ea, eb = ref.connections[("X", "Y")].update_rule.eligibility_trace, ours.connections[("X", "Y")].update_rule.eligibility_trace
+    assert torch.allclose(ea, eb, rtol=1e-4, atol=1e-5) and float(eb.abs().sum()) > 0
