@@ -578,7 +578,61 @@ class McCullochPitts(Nodes):
         d.thresh = _scalar(self.thresh, "thresh")
 
 
-IzhikevichNodes = _unsupported("IzhikevichNodes", "nodes.py:1147-1316")
+
+
+class IzhikevichNodes(Nodes):
+    """Izhikevich neurons with their built-in lateral matrix ``S`` (reference: nodes.py:1147-1316; forward :1262-1289).
+    A fraction ``excitatory`` of the population (the first ``int(n * excitatory)`` neurons) is regular-spiking with
+    positive outgoing ``S`` columns, the rest fast-spiking with negative ones; the per-neuron parameters are drawn at
+    construction in the reference's order (excitatory ``r``, its ``S`` columns, inhibitory ``r``, its ``S`` columns), so a
+    seeded construction gives the reference's population.  Per-neuron parameter tensors and a population-internal matrix
+    are outside what the window kernels describe, so the class has no ``kind``: host torch code on the layer's device,
+    scripted tier, everything built-in around it on its kernels."""
+
+    def __init__(self, n: Optional[int] = None, shape: Optional[Iterable[int]] = None, traces: bool = False,
+                 traces_additive: bool = False, tc_trace: Scalar = 20.0, trace_scale: Scalar = 1.0, sum_input: bool = False,
+                 excitatory: float = 1, thresh: Scalar = 45.0, rest: Scalar = -65.0, lbound: float = None, **kwargs) -> None:
+        super().__init__(n=n, shape=shape, traces=traces, traces_additive=traces_additive, tc_trace=tc_trace,
+                         trace_scale=trace_scale, sum_input=sum_input)
+        n = self.n
+        self.register_buffer("rest", torch.tensor(rest))
+        self.register_buffer("thresh", torch.tensor(thresh))
+        self.lbound = lbound
+        ex = int(n * min(max(excitatory, 0), 1))
+        r_ex, S_ex = torch.rand(ex), 0.5 * torch.rand(n, ex)            # regular spiking (nodes.py:1203-1210, 1233-1239)
+        r_in, S_in = torch.rand(n - ex), -torch.rand(n, n - ex)         # fast spiking (:1211-1218, 1241-1247)
+        self.register_buffer("r", torch.cat((r_ex, r_in)))
+        self.register_buffer("a", torch.cat((0.02 * torch.ones(ex), 0.02 + 0.08 * r_in)))
+        self.register_buffer("b", torch.cat((0.2 * torch.ones(ex), 0.25 - 0.05 * r_in)))
+        self.register_buffer("c", torch.cat((-65.0 + 15 * r_ex ** 2, -65.0 * torch.ones(n - ex))))
+        self.register_buffer("d", torch.cat((8 - 6 * r_ex ** 2, 2 * torch.ones(n - ex))))
+        self.register_buffer("S", torch.cat((S_ex, S_in), dim=1))
+        self.register_buffer("excitatory", (torch.arange(n) < ex).byte())
+        self.register_buffer("v", self.rest * torch.ones(n))
+        self.register_buffer("u", self.b * self.v)
+
+    def forward(self, x: torch.Tensor) -> None:
+        self.v = torch.where(self.s, self.c, self.v)                    # last step's spikes: reset v, bump the recovery
+        self.u = torch.where(self.s, self.u + self.d, self.u)
+        if self.s.any():                                                # lateral input from the neurons that just fired
+            x += torch.stack([self.S[:, fired].sum(dim=1) for fired in self.s])
+        for _ in range(2):                                              # two half steps (:1276-1277)
+            self.v += self.dt * 0.5 * (0.04 * self.v ** 2 + 5 * self.v + 140 - self.u + x)
+        self.u += self.dt * self.a * (self.b * self.v - self.u)
+        if self.lbound is not None:
+            self.v.masked_fill_(self.v < self.lbound, self.lbound)
+        self.s = self.v >= self.thresh
+        super().forward(x)
+
+    def reset_state_variables(self) -> None:
+        super().reset_state_variables()
+        self.v.fill_(self.rest)
+        self.u = self.b * self.v
+
+    def set_batch_size(self, batch_size) -> None:
+        super().set_batch_size(batch_size=batch_size)
+        self.v = self.rest * torch.ones(batch_size, *self.shape, device=self.v.device)
+        self.u = self.b * self.v
 CSRMNodes = _unsupported("CSRMNodes", "nodes.py:1319-1552")
 
 

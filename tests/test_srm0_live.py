@@ -1,6 +1,7 @@
 """``SRM0Nodes`` (reference: nodes.py:1555-1701) on the scripted tier: with torch's generator seeded alike, a learning
 window of ``Input -> SRM0Nodes`` (PostPre, normalize) equals the live reference's — same spikes, voltages and weights
-within the north_star's tolerances (the built-in pieces run on the oracle backend here).  CPU only."""
+within the north_star's tolerances (the built-in pieces run on the oracle backend here).  Also here, on the same tier:
+``learning.Rmax`` (the rule made for SRM0 targets) and ``IzhikevichNodes``.  CPU only."""
 import numpy as np
 import pytest
 import torch
@@ -94,3 +95,38 @@ def test_rmax_on_srm0_matches_the_live_reference():
     assert not ((wa - wb).abs() > 2e-6 + 1e-4 * wa.abs()).any(), float((wa - wb).abs().max())
     ea, eb = ref.connections[("X", "Y")].update_rule.eligibility_trace, ours.connections[("X", "Y")].update_rule.eligibility_trace
     assert torch.allclose(ea, eb, rtol=1e-4, atol=1e-5) and float(eb.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("excitatory", [1, 0, 0.75])
+def test_izhikevich_nodes_match_the_live_reference(excitatory):
+    """``IzhikevichNodes`` (nodes.py:1147-1316): a seeded construction gives the reference's per-neuron parameters and
+    lateral matrix; a PostPre window through the scripted tier equals the live reference's."""
+    from oracle.oracle import OracleBackend
+
+    def build(ns):
+        torch.manual_seed(321)
+        net = ns.Network(dt=1.0, batch_size=2)
+        X = ns.nodes.Input(n=30, traces=True)
+        Y = ns.nodes.IzhikevichNodes(n=12, traces=True, excitatory=excitatory, thresh=30.0, lbound=-80.0, sum_input=True)
+        net.add_layer(X, "X"); net.add_layer(Y, "Y")
+        g = torch.Generator().manual_seed(63)
+        net.add_connection(ns.topology.Connection(source=X, target=Y, w=6.0 * torch.rand(30, 12, generator=g), update_rule=ns.learning.PostPre,
+                                                  nu=(1e-3, 1e-2), reduction=torch.sum, wmin=0.0, wmax=8.0), "X", "Y")
+        return net, torch.bernoulli(0.3 * torch.ones(70, 2, 30), generator=g).byte()
+
+    ref, x = build(REF)
+    ours, x2 = build(cases.namespace("b200"))
+    for name in ("r", "a", "b", "c", "d", "S", "excitatory", "u"):
+        assert torch.equal(getattr(ref.layers["Y"], name), getattr(ours.layers["Y"], name)), name
+    rm = REF.monitors.Monitor(ref.layers["Y"], ["s"], time=70); ref.add_monitor(rm, "Y")
+    om = cases.namespace("b200").monitors.Monitor(ours.layers["Y"], ["s"], time=70); ours.add_monitor(om, "Y")
+    ref.run(inputs={"X": x.clone()}, time=70)
+    assert ours._scripted_required()
+    with OracleBackend() as ob:
+        ours.run(inputs={"X": x2}, time=70)
+        assert ob.err == 0
+    assert torch.equal(rm.get("s"), om.get("s")) and int(om.get("s").sum()) > 10
+    for name in ("v", "u", "x", "summed"):
+        assert torch.allclose(getattr(ref.layers["Y"], name), getattr(ours.layers["Y"], name), rtol=1e-4, atol=1e-3), name
+    wa, wb = ref.connections[("X", "Y")].w.detach(), ours.connections[("X", "Y")].w.detach()
+    assert not ((wa - wb).abs() > 2e-6 + 1e-4 * wa.abs()).any(), float((wa - wb).abs().max())
