@@ -46,16 +46,17 @@ def test_nodes_initial_state_like_reference():
 
 
 def test_unsupported_reference_features_fail_loudly():
-    from bindsnet_b200.network.nodes import IzhikevichNodes
+    from bindsnet_b200.network.nodes import CSRMNodes, IzhikevichNodes
 
     assert IFNodes(n=10).kind is not None          # implemented since round 2
+    assert IzhikevichNodes(n=10).kind is None      # host class on the scripted tier (tests/test_srm0_live.py)
     with pytest.raises(NotImplementedError):
-        IzhikevichNodes(n=10)
+        CSRMNodes(n=10)
     with pytest.raises(NotImplementedError):
         Conv1dConnection(None, None, 3)
     X, Y = Input(n=4, traces=True), LIFNodes(n=4, traces=True)
     from bindsnet_b200.learning import Rmax
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):            # learning.py:2899-2904: additive input traces and an SRM0Nodes target
         Connection(X, Y, update_rule=Rmax)
     # MSTDPET is implemented for dense connections at batch size 1 (the only one the reference's flattened traces allow)
     netb = Network(dt=1.0, batch_size=2)
